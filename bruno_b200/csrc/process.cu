@@ -1,0 +1,791 @@
+// Exchangeable Student-t / Gaussian process kernels (replaces nn_extra_student.py / nn_extra_gauss.py of the
+// reference, whose every method expands into ~45 tiny TF ops per sequence step).
+//
+// Design (HBM-bound scan):
+//   * The reference recursion (student:85-106) has O(1) state, and unrolled it is a function of the prefix sums
+//     S1 = sum(x - mu0), S2 = sum((x - mu0)^2) only (utils_stats.py:87-95 states the same closed form).  Everything
+//     else -- dd_n, k_n, b_n, nu_n, the lgamma quotient -- depends on (step, dim) but not on the batch element, so a
+//     tiny fp64 "table" kernel evaluates it once per (step, dim) and the scan kernel reads it through L1/L2.
+//   * scan kernel: one thread = 4 consecutive latent dims (128-bit loads along D) x NB batch rows; the sequence is
+//     walked in registers; per step the per-row partial sums are reduced over D with a value-halving butterfly of
+//     warp shuffles, then across warps through shared memory in a fixed order (bit-reproducible).
+//   * hand-written backward: pass 1 re-reads z to form the total sums, pass 2 walks the sequence in reverse,
+//     carrying the suffix sums of dL/dS1, dL/dS2; coefficient gradients are chained to the raw variables with the
+//     fp64 forward-mode derivatives stored by the table kernel.
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace bruno {
+
+// ------------------------------------------------------------------------------------------------------------
+// last error (thread-local so concurrent host threads do not trample each other)
+// ------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward-mode dual numbers in fp64 (3 tangents: raw var, raw nu, raw corr)
+// ------------------------------------------------------------------------------------------------------------
+struct D3 {
+  double v, d[3];
+};
+__device__ inline D3 mk(double v) { return D3{v, {0.0, 0.0, 0.0}}; }
+__device__ inline D3 seed(double v, int i) {
+  D3 r = mk(v);
+  r.d[i] = 1.0;
+  return r;
+}
+__device__ inline D3 operator+(D3 a, D3 b) { return D3{a.v + b.v, {a.d[0] + b.d[0], a.d[1] + b.d[1], a.d[2] + b.d[2]}}; }
+__device__ inline D3 operator-(D3 a, D3 b) { return D3{a.v - b.v, {a.d[0] - b.d[0], a.d[1] - b.d[1], a.d[2] - b.d[2]}}; }
+__device__ inline D3 operator*(D3 a, D3 b) {
+  return D3{a.v * b.v, {a.d[0] * b.v + a.v * b.d[0], a.d[1] * b.v + a.v * b.d[1], a.d[2] * b.v + a.v * b.d[2]}};
+}
+__device__ inline D3 operator/(D3 a, D3 b) {
+  double q = a.v / b.v, ib = 1.0 / b.v;
+  return D3{q, {(a.d[0] - q * b.d[0]) * ib, (a.d[1] - q * b.d[1]) * ib, (a.d[2] - q * b.d[2]) * ib}};
+}
+__device__ inline D3 operator+(D3 a, double s) { a.v += s; return a; }
+__device__ inline D3 operator-(D3 a, double s) { a.v -= s; return a; }
+__device__ inline D3 operator*(D3 a, double s) { return D3{a.v * s, {a.d[0] * s, a.d[1] * s, a.d[2] * s}}; }
+__device__ inline D3 chain(D3 a, double f, double df) { return D3{f, {a.d[0] * df, a.d[1] * df, a.d[2] * df}}; }
+__device__ inline D3 dlog(D3 a) { return chain(a, log(a.v), 1.0 / a.v); }
+__device__ inline D3 dsqrt(D3 a) {
+  double s = sqrt(a.v);
+  return chain(a, s, 0.5 / s);
+}
+__device__ inline D3 dexp(D3 a) {
+  double e = exp(a.v);
+  return chain(a, e, e);
+}
+__device__ inline double digamma(double x) {
+  double r = 0.0;
+  while (x < 8.0) {
+    r -= 1.0 / x;
+    x += 1.0;
+  }
+  double f = 1.0 / (x * x);
+  double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0)))));
+  return r + log(x) - 0.5 / x + t;
+}
+__device__ inline D3 dlgamma(D3 a) { return chain(a, lgamma(a.v), digamma(a.v)); }
+__device__ inline D3 dsoftplus(D3 a) {  // tf.nn.softplus
+  double x = a.v;
+  double sp = x > 30.0 ? x : log1p(exp(x));
+  double sg = 1.0 / (1.0 + exp(-x));
+  return chain(a, sp, sg);
+}
+__device__ inline D3 dsigmoid(D3 a) {
+  double sg = 1.0 / (1.0 + exp(-a.v));
+  return chain(a, sg, sg * (1.0 - sg));
+}
+
+constexpr int TP_NCF = 7;  // w, ddw, e, f, C, A2, B2
+constexpr int GP_NCF = 3;  // dd, I, C
+constexpr int N_PRIOR = 3;
+__host__ __device__ constexpr int ncf_of(int kind) { return kind == BRUNO_TP ? TP_NCF : GP_NCF; }
+
+#define LN2_D 0.69314718055994530942
+#define LNPI_D 1.14472988584940017414
+
+// One thread per (row-group n in [0, T], dim d); n == T builds the prior constants.
+__global__ void process_table_kernel(int kind, const float* __restrict__ var_vbl, const float* __restrict__ nu_vbl,
+                                     const float* __restrict__ corr_vbl, const float* __restrict__ mask_dim,
+                                     float min_nu, int n0, int T, int D, int with_grad, float* __restrict__ table) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;  // 0..T
+  if (d >= D) return;
+  const int NCF = ncf_of(kind);
+  const bool is_prior = row == T;
+  const double n = is_prior ? 0.0 : static_cast<double>(n0 + row);
+  const double m = mask_dim ? static_cast<double>(mask_dim[d]) : 1.0;
+
+  D3 sp = dsoftplus(seed(static_cast<double>(var_vbl[d]), 0));
+  D3 v = sp * sp;                                                       // student:38
+  D3 rho = dsigmoid(seed(static_cast<double>(corr_vbl[d]), 2));         // student:60
+  D3 c = rho * v;                                                       // student:61
+  D3 dd = c / (v + c * (n - 1.0));                                      // student:93
+  D3 k = v - dd * c * n;                                                // closed form of student:101
+  D3 out[TP_NCF];
+  int nout;
+  if (kind == BRUNO_TP) {
+    D3 nu0 = dexp(seed(static_cast<double>(nu_vbl[d]), 1)) + static_cast<double>(min_nu);  // student:46
+    D3 c0 = k * (nu0 - 2.0);          // (nu_n - 2) * sigma_n at beta = 0
+    D3 s = mk(1.0) / c0;
+    D3 w = dsqrt(s);
+    D3 iv = mk(1.0) / (v - c);        // a_i - b_i of student:97-98, constant in i
+    D3 b = (mk(0.0) - c) / ((v - c) * (c * (n - 1.0) + v));             // student:98
+    D3 A = (nu0 + (n + 1.0)) * 0.5;   // (1 + nu_n) / 2
+    D3 C = dlgamma(A) - dlgamma((nu0 + n) * 0.5) - dlog(c0) * 0.5 - 0.5 * LNPI_D;
+    if (!is_prior) {
+      out[0] = w;
+      out[1] = dd * w;
+      out[2] = iv / (nu0 - 2.0);
+      out[3] = b / (nu0 - 2.0);
+      out[4] = C * m;
+      out[5] = A * (LN2_D * m);
+      out[6] = (A - 0.5) * (LN2_D * m);
+      nout = TP_NCF;
+    } else {
+      out[0] = s;
+      out[1] = C * m;
+      out[2] = A * (LN2_D * m);
+      nout = N_PRIOR;
+    }
+  } else {
+    // gauss:75-96: sigma_n follows the same recursion as k_n.
+    D3 I = mk(0.5) / k;
+    D3 C = (dlog(k) + log(2.0 * 3.14159265358979323846)) * (-0.5);
+    if (!is_prior) {
+      out[0] = dd;
+      out[1] = I * m;
+      out[2] = C * m;
+      nout = GP_NCF;
+    } else {
+      out[0] = I * m;
+      out[1] = C * m;
+      out[2] = mk(0.0);
+      nout = N_PRIOR;
+    }
+  }
+  const int row0 = is_prior ? T * NCF : row * NCF;
+  const size_t gbase = static_cast<size_t>(T * NCF + N_PRIOR) * D;
+  for (int i = 0; i < nout; ++i) {
+    table[static_cast<size_t>(row0 + i) * D + d] = static_cast<float>(out[i].v);
+    if (with_grad)
+      for (int p = 0; p < 3; ++p)
+        table[gbase + (static_cast<size_t>(row0 + i) * 3 + p) * D + d] = static_cast<float>(out[i].d[p]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small vector helpers
+// ------------------------------------------------------------------------------------------------------------
+template <int VEC>
+struct Vf {
+  float x[VEC];
+};
+template <int VEC>
+__device__ __forceinline__ Vf<VEC> ldv(const float* p) {
+  Vf<VEC> r;
+  if constexpr (VEC == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.x[0] = t.x; r.x[1] = t.y; r.x[2] = t.z; r.x[3] = t.w;
+  } else {
+    r.x[0] = __ldg(p);
+  }
+  return r;
+}
+// streaming (read-once) variant for z
+template <int VEC>
+__device__ __forceinline__ Vf<VEC> ldv_stream(const float* p) {
+  Vf<VEC> r;
+  if constexpr (VEC == 4) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x[0]), "=f"(r.x[1]), "=f"(r.x[2]), "=f"(r.x[3])
+                 : "l"(p));
+  } else {
+    r.x[0] = __ldg(p);
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void stv(float* p, const Vf<VEC>& v) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v.x[0], v.x[1], v.x[2], v.x[3]);
+  } else {
+    p[0] = v.x[0];
+  }
+}
+template <int VEC>
+__device__ __forceinline__ Vf<VEC> zerov() {
+  Vf<VEC> r;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) r.x[i] = 0.f;
+  return r;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Reduce NV (power of two <= 32) values per lane across the warp with NV-1 + log2(32/NV) shuffles.
+// On return lane L holds in v[0] the warp total of value index (L >> (5 - log2 NV)) ... see slot_of_lane.
+template <int NV>
+__device__ __forceinline__ void warp_multi_reduce(float (&v)[NV], int lane) {
+  int cnt = NV;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (cnt > 1) {
+      cnt >>= 1;
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < NV / 2; ++i) {
+        if (i < cnt) {
+          float send = upper ? v[i] : v[i + cnt];
+          float keep = upper ? v[i + cnt] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    }
+  }
+}
+template <int NV>
+__device__ __forceinline__ int slot_of_lane(int lane) {
+  // value index held by this lane after warp_multi_reduce: built from the lane bits used while halving
+  int idx = 0, cnt = NV;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (cnt > 1) {
+      cnt >>= 1;
+      if (lane & off) idx += cnt;
+    }
+  }
+  return idx;
+}
+template <int NV>
+__device__ __forceinline__ bool lane_is_writer(int lane) {
+  // lanes whose un-used (fully reduced) bits are zero
+  int used = 0, cnt = NV;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (cnt > 1) {
+      cnt >>= 1;
+      used |= off;
+    }
+  }
+  return (lane & ~used & 31) == 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward scan
+// ------------------------------------------------------------------------------------------------------------
+template <int KIND, int VEC, int NB, bool PRIOR>
+__global__ void __launch_bounds__(256)
+process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, const float* __restrict__ tab,
+                   float* __restrict__ s1, float* __restrict__ s2, float* __restrict__ lp,
+                   float* __restrict__ lp_prior, float* __restrict__ scratch, int B, int T, int D) {
+  constexpr int NCF = ncf_of(KIND);
+  constexpr int NV = NB * 2;
+  extern __shared__ float sred[];  // [T][nwarps][NV]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int d0 = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
+  const bool active = d0 < D;
+  const int b0 = blockIdx.x * NB;
+  const size_t rowTD = static_cast<size_t>(T) * D;
+
+  Vf<VEC> S1[NB], S2[NB], mu = zerov<VEC>(), pc[N_PRIOR];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    S1[j] = zerov<VEC>();
+    S2[j] = zerov<VEC>();
+  }
+#pragma unroll
+  for (int i = 0; i < N_PRIOR; ++i) pc[i] = zerov<VEC>();
+  if (active) {
+    mu = ldv<VEC>(mu0 + d0);
+    if (PRIOR) {
+#pragma unroll
+      for (int i = 0; i < N_PRIOR; ++i) pc[i] = ldv<VEC>(tab + static_cast<size_t>(T * NCF + i) * D + d0);
+    }
+    if (s1 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (b0 + j < B) {
+          S1[j] = ldv<VEC>(s1 + static_cast<size_t>(b0 + j) * D + d0);
+          if (KIND == BRUNO_TP) S2[j] = ldv<VEC>(s2 + static_cast<size_t>(b0 + j) * D + d0);
+        }
+    }
+  }
+  // register double buffer of the observations
+  Vf<VEC> xn[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+    xn[j] = (active && b0 + j < B && T > 0) ? ldv_stream<VEC>(z + static_cast<size_t>(b0 + j) * rowTD + d0) : zerov<VEC>();
+
+  for (int n = 0; n < T; ++n) {
+    Vf<VEC> x[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) x[j] = xn[j];
+    if (n + 1 < T) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (active && b0 + j < B)
+          xn[j] = ldv_stream<VEC>(z + static_cast<size_t>(b0 + j) * rowTD + static_cast<size_t>(n + 1) * D + d0);
+    }
+    Vf<VEC> cf[NCF];
+#pragma unroll
+    for (int i = 0; i < NCF; ++i)
+      cf[i] = active ? ldv<VEC>(tab + static_cast<size_t>(n * NCF + i) * D + d0) : zerov<VEC>();
+
+    float vals[NV];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      float acc = 0.f, accp = 0.f;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float xz = x[j].x[e] - mu.x[e];
+        if constexpr (KIND == BRUNO_TP) {
+          const float s1v = S1[j].x[e];
+          const float r = fmaf(-cf[1].x[e], s1v, cf[0].x[e] * xz);
+          const float q = fmaf(cf[3].x[e], s1v * s1v, fmaf(cf[2].x[e], S2[j].x[e], 1.f));
+          const float u = fmaf(r, r, q);
+          acc += fmaf(cf[6].x[e], fast_lg2(q), fmaf(-cf[5].x[e], fast_lg2(u), cf[4].x[e]));
+          if (PRIOR) accp += fmaf(-pc[2].x[e], fast_lg2(fmaf(xz * xz, pc[0].x[e], 1.f)), pc[1].x[e]);
+          S1[j].x[e] = s1v + xz;
+          S2[j].x[e] = fmaf(xz, xz, S2[j].x[e]);
+        } else {
+          const float r = fmaf(-cf[0].x[e], S1[j].x[e], xz);
+          acc += fmaf(-cf[1].x[e], r * r, cf[2].x[e]);
+          if (PRIOR) accp += fmaf(-pc[0].x[e], xz * xz, pc[1].x[e]);
+          S1[j].x[e] += xz;
+        }
+      }
+      const bool ok = active && (b0 + j < B);
+      vals[2 * j] = ok ? acc : 0.f;
+      vals[2 * j + 1] = ok ? accp : 0.f;
+    }
+    warp_multi_reduce<NV>(vals, lane);
+    if (lane_is_writer<NV>(lane)) sred[(n * nwarps + warp) * NV + slot_of_lane<NV>(lane)] = vals[0];
+  }
+  __syncthreads();
+  const int nseg = gridDim.y;
+  for (int i = threadIdx.x; i < T * NV; i += blockDim.x) {
+    const int n = i / NV, idx = i % NV, j = idx >> 1, which = idx & 1;
+    if (b0 + j >= B) continue;
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += sred[(n * nwarps + w) * NV + idx];
+    if (nseg == 1) {
+      if (which == 0) lp[static_cast<size_t>(b0 + j) * T + n] = s;
+      else if (PRIOR) lp_prior[static_cast<size_t>(b0 + j) * T + n] = s;
+    } else {
+      scratch[((static_cast<size_t>(blockIdx.y) * B + b0 + j) * T + n) * 2 + which] = s;
+    }
+  }
+  if (s1 != nullptr && active) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (b0 + j < B) {
+        stv<VEC>(s1 + static_cast<size_t>(b0 + j) * D + d0, S1[j]);
+        if (KIND == BRUNO_TP) stv<VEC>(s2 + static_cast<size_t>(b0 + j) * D + d0, S2[j]);
+      }
+  }
+}
+
+__global__ void process_fwd_finalize(const float* __restrict__ scratch, float* __restrict__ lp,
+                                     float* __restrict__ lp_prior, int nseg, int BT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BT) return;
+  float a = 0.f, b = 0.f;
+  for (int s = 0; s < nseg; ++s) {
+    a += scratch[(static_cast<size_t>(s) * BT + i) * 2];
+    b += scratch[(static_cast<size_t>(s) * BT + i) * 2 + 1];
+  }
+  lp[i] = a;
+  if (lp_prior) lp_prior[i] = b;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward scan
+// ------------------------------------------------------------------------------------------------------------
+template <int KIND, int VEC, int NB, bool PRIOR>
+__global__ void __launch_bounds__(256)
+process_bwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, const float* __restrict__ tab,
+                   const float* __restrict__ dlp, const float* __restrict__ dlpp, float* __restrict__ dz,
+                   float* __restrict__ partial, int B, int T, int D, int groups_per_block) {
+  constexpr int NCF = ncf_of(KIND);
+  constexpr float INV_LN2 = 1.4426950408889634f;
+  const int d0 = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
+  if (d0 >= D) return;
+  const size_t rowTD = static_cast<size_t>(T) * D;
+  const float* gtab = tab + static_cast<size_t>(T * NCF + N_PRIOR) * D;
+  const Vf<VEC> mu = ldv<VEC>(mu0 + d0);
+  Vf<VEC> pc[N_PRIOR];
+#pragma unroll
+  for (int i = 0; i < N_PRIOR; ++i) pc[i] = ldv<VEC>(tab + static_cast<size_t>(T * NCF + i) * D + d0);
+
+  Vf<VEC> pg[3], pcg[N_PRIOR];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) pg[p] = zerov<VEC>();
+#pragma unroll
+  for (int i = 0; i < N_PRIOR; ++i) pcg[i] = zerov<VEC>();
+
+  for (int g = 0; g < groups_per_block; ++g) {
+    const int b0 = (blockIdx.x * groups_per_block + g) * NB;
+    if (b0 >= B) break;
+    Vf<VEC> S1[NB], S2[NB], G1[NB], G2[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      S1[j] = zerov<VEC>(); S2[j] = zerov<VEC>(); G1[j] = zerov<VEC>(); G2[j] = zerov<VEC>();
+    }
+    // pass 1: totals
+    for (int n = 0; n < T; ++n) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        if (b0 + j < B) {
+          Vf<VEC> x = ldv<VEC>(z + static_cast<size_t>(b0 + j) * rowTD + static_cast<size_t>(n) * D + d0);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const float xz = x.x[e] - mu.x[e];
+            S1[j].x[e] += xz;
+            S2[j].x[e] = fmaf(xz, xz, S2[j].x[e]);
+          }
+        }
+    }
+    // pass 2: reverse
+    for (int n = T - 1; n >= 0; --n) {
+      Vf<VEC> cf[NCF], cg[NCF];
+#pragma unroll
+      for (int i = 0; i < NCF; ++i) {
+        cf[i] = ldv<VEC>(tab + static_cast<size_t>(n * NCF + i) * D + d0);
+        cg[i] = zerov<VEC>();
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (b0 + j >= B) continue;
+        const size_t off = static_cast<size_t>(b0 + j) * rowTD + static_cast<size_t>(n) * D + d0;
+        Vf<VEC> x = ldv<VEC>(z + off), gx;
+        const float dl = __ldg(dlp + static_cast<size_t>(b0 + j) * T + n);
+        const float dlq = PRIOR ? __ldg(dlpp + static_cast<size_t>(b0 + j) * T + n) : 0.f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float xz = x.x[e] - mu.x[e];
+          float dxz, dS1, dS2 = 0.f;
+          if constexpr (KIND == BRUNO_TP) {
+            const float s1v = S1[j].x[e] - xz;            // prefix sums BEFORE observation n
+            const float s2v = fmaf(-xz, xz, S2[j].x[e]);
+            S1[j].x[e] = s1v;
+            S2[j].x[e] = s2v;
+            const float s1sq = s1v * s1v;
+            const float r = fmaf(-cf[1].x[e], s1v, cf[0].x[e] * xz);
+            const float q = fmaf(cf[3].x[e], s1sq, fmaf(cf[2].x[e], s2v, 1.f));
+            const float u = fmaf(r, r, q);
+            const float gu = -cf[5].x[e] * INV_LN2 * fast_rcp(u) * dl;
+            const float gq = fmaf(cf[6].x[e] * INV_LN2 * dl, fast_rcp(q), gu);
+            const float gr = 2.f * r * gu;
+            dxz = gr * cf[0].x[e];
+            dS1 = fmaf(gq * cf[3].x[e], 2.f * s1v, -gr * cf[1].x[e]);
+            dS2 = gq * cf[2].x[e];
+            cg[0].x[e] = fmaf(gr, xz, cg[0].x[e]);
+            cg[1].x[e] = fmaf(-gr, s1v, cg[1].x[e]);
+            cg[2].x[e] = fmaf(gq, s2v, cg[2].x[e]);
+            cg[3].x[e] = fmaf(gq, s1sq, cg[3].x[e]);
+            cg[4].x[e] += dl;
+            cg[5].x[e] = fmaf(-fast_lg2(u), dl, cg[5].x[e]);
+            cg[6].x[e] = fmaf(fast_lg2(q), dl, cg[6].x[e]);
+            if (PRIOR) {
+              const float x2 = xz * xz;
+              const float up = fmaf(x2, pc[0].x[e], 1.f);
+              const float gup = -pc[2].x[e] * INV_LN2 * fast_rcp(up) * dlq;
+              dxz = fmaf(gup * 2.f * pc[0].x[e], xz, dxz);
+              pcg[0].x[e] = fmaf(gup, x2, pcg[0].x[e]);
+              pcg[1].x[e] += dlq;
+              pcg[2].x[e] = fmaf(-fast_lg2(up), dlq, pcg[2].x[e]);
+            }
+          } else {
+            const float s1v = S1[j].x[e] - xz;
+            S1[j].x[e] = s1v;
+            const float r = fmaf(-cf[0].x[e], s1v, xz);
+            const float gr = -2.f * cf[1].x[e] * r * dl;
+            dxz = gr;
+            dS1 = -gr * cf[0].x[e];
+            cg[0].x[e] = fmaf(-gr, s1v, cg[0].x[e]);
+            cg[1].x[e] = fmaf(-r * r, dl, cg[1].x[e]);
+            cg[2].x[e] += dl;
+            if (PRIOR) {
+              dxz = fmaf(-2.f * pc[0].x[e] * dlq, xz, dxz);
+              pcg[0].x[e] = fmaf(-xz * xz, dlq, pcg[0].x[e]);
+              pcg[1].x[e] += dlq;
+            }
+          }
+          gx.x[e] = dxz + G1[j].x[e] + 2.f * xz * G2[j].x[e];
+          G1[j].x[e] += dS1;
+          G2[j].x[e] += dS2;
+        }
+        stv<VEC>(dz + off, gx);
+      }
+      // chain the coefficient gradients of this step to the raw variables
+#pragma unroll
+      for (int i = 0; i < NCF; ++i)
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          if (KIND == BRUNO_GP && p == 1) continue;
+          Vf<VEC> dc = ldv<VEC>(gtab + (static_cast<size_t>(n * NCF + i) * 3 + p) * D + d0);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) pg[p].x[e] = fmaf(cg[i].x[e], dc.x[e], pg[p].x[e]);
+        }
+    }
+  }
+  if (PRIOR) {
+#pragma unroll
+    for (int i = 0; i < N_PRIOR; ++i)
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        Vf<VEC> dc = ldv<VEC>(gtab + (static_cast<size_t>(T * NCF + i) * 3 + p) * D + d0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) pg[p].x[e] = fmaf(pcg[i].x[e], dc.x[e], pg[p].x[e]);
+      }
+  }
+#pragma unroll
+  for (int p = 0; p < 3; ++p) stv<VEC>(partial + (static_cast<size_t>(blockIdx.x) * 3 + p) * D + d0, pg[p]);
+}
+
+__global__ void process_bwd_finalize(const float* __restrict__ partial, int nblk, int D, float* __restrict__ dvar,
+                                     float* __restrict__ dnu, float* __restrict__ dcorr) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float a[3] = {0.f, 0.f, 0.f};
+  for (int k = 0; k < nblk; ++k)
+    for (int p = 0; p < 3; ++p) a[p] += partial[(static_cast<size_t>(k) * 3 + p) * D + d];
+  dvar[d] = a[0];
+  if (dnu) dnu[d] = a[1];
+  dcorr[d] = a[2];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// posterior after each prefix + sampler (sampling branch only; follows the reference recursion literally)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+__global__ void process_posterior_kernel(int kind, const float* __restrict__ z, const float* __restrict__ var_vbl,
+                                         const float* __restrict__ nu_vbl, const float* __restrict__ corr_vbl,
+                                         const float* __restrict__ mu0, float min_nu, float* __restrict__ mu_out,
+                                         float* __restrict__ var_out, float* __restrict__ nu_out, int B, int T, int D) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (d >= D) return;
+  const float sp = softplus_f(var_vbl[d]);
+  const float v = sp * sp;
+  const float c = v / (1.f + expf(-corr_vbl[d]));
+  const float nu0 = kind == BRUNO_TP ? expf(nu_vbl[d]) + min_nu : 0.f;
+  const float m0 = mu0[d];
+  float mu = m0, sigma = v, nu = nu0, beta = 0.f, xs = 0.f, k = v;
+  const size_t o = (static_cast<size_t>(b) * (T + 1)) * D + d;
+  mu_out[o] = mu;
+  var_out[o] = sigma;
+  if (kind == BRUNO_TP && b == 0) nu_out[d] = nu;
+  for (int t = 0; t < T; ++t) {
+    const float x = z[(static_cast<size_t>(b) * T + t) * D + d];
+    const float i = static_cast<float>(t + 1);
+    const float xz = x - m0;
+    const float dd = c / (v + c * (i - 1.f));
+    mu = (1.f - dd) * mu + x * dd;
+    if (kind == BRUNO_TP) {
+      const float a_i = (c * (i - 2.f) + v) / ((v - c) * (c * (i - 1.f) + v));
+      const float b_i = -c / ((v - c) * (c * (i - 1.f) + v));
+      const float b_p = -c / ((v - c) * (c * (i - 2.f) + v));
+      beta = beta + (a_i - b_i) * xz * xz + b_i * (xs + xz) * (xs + xz) - b_p * xs * xs;
+      xs += xz;
+      k = (1.f - dd) * k + (v - c) * dd;
+      nu = nu + 1.f;
+      sigma = (nu0 + beta - 2.f) / (nu - 2.f) * k;
+      if (b == 0) nu_out[static_cast<size_t>(t + 1) * D + d] = nu;
+    } else {
+      sigma = (1.f - dd) * sigma + (v - c) * dd;
+    }
+    mu_out[o + static_cast<size_t>(t + 1) * D] = mu;
+    var_out[o + static_cast<size_t>(t + 1) * D] = sigma;
+  }
+}
+
+__global__ void process_sample_kernel(int kind, const float* __restrict__ rvs, const float* __restrict__ mu,
+                                      const float* __restrict__ var, const float* __restrict__ nu,
+                                      float* __restrict__ out, int n, int B, int D, long stride_b) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(n) * B * D;
+  if (i >= total) return;
+  const int d = static_cast<int>(i % D);
+  const int b = static_cast<int>((i / D) % B);
+  const float m = mu[static_cast<size_t>(b) * stride_b + d], s = var[static_cast<size_t>(b) * stride_b + d];
+  if (kind == BRUNO_TP) {
+    const float r0 = rvs[i], r1 = rvs[total + i];
+    const float a = fminf(r0, r1), bb = fmaxf(r0, r1);
+    const float ang = 2.f * 3.14159265358979323846f * a / bb;
+    const float u = bb * cosf(ang), v = bb * sinf(ang);
+    const float w = u * u + v * v;
+    const float nv = nu[d];
+    const float t = u * sqrtf(nv * (powf(w, -2.f / nv) - 1.f) / w);
+    out[i] = m + sqrtf(s * (nv - 2.f) / nv) * t;
+  } else {
+    out[i] = m + sqrtf(s) * rvs[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------------------
+struct ScanGeom {
+  int vec, threads, nseg;
+};
+static ScanGeom scan_geom(int D, bool ptr_ok) {
+  ScanGeom g;
+  g.vec = (D % 4 == 0 && ptr_ok) ? 4 : 1;
+  const int chunks = D / g.vec;
+  g.threads = chunks >= 256 ? 256 : ((chunks + 31) / 32) * 32;
+  g.nseg = (chunks + g.threads - 1) / g.threads;
+  return g;
+}
+
+constexpr int FWD_NB = 4;
+constexpr int BWD_NB = 2;
+
+template <int KIND, int VEC>
+static int launch_fwd(const float* z, const float* mu0, const float* table, float* s1, float* s2, float* lp,
+                      float* lp_prior, float* scratch, int B, int T, int D, const ScanGeom& g, cudaStream_t st) {
+  dim3 grid(ceil_div(B, FWD_NB), g.nseg);
+  const size_t smem = static_cast<size_t>(T) * (g.threads / 32) * FWD_NB * 2 * sizeof(float);
+  auto kp = process_fwd_kernel<KIND, VEC, FWD_NB, true>;
+  auto kn = process_fwd_kernel<KIND, VEC, FWD_NB, false>;
+  auto k = lp_prior ? kp : kn;
+  if (smem > 48 * 1024) {
+    if (smem > 200 * 1024) {
+      set_last_error("bruno_process_fwd: T=%d too long for one launch (smem %zu)", T, smem);
+      return BRUNO_EINVAL;
+    }
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  }
+  k<<<grid, g.threads, smem, st>>>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D);
+  int rc = check_launch("process_fwd_kernel");
+  if (rc) return rc;
+  if (g.nseg > 1) {
+    process_fwd_finalize<<<ceil_div(B * T, 256), 256, 0, st>>>(scratch, lp, lp_prior, g.nseg, B * T);
+    rc = check_launch("process_fwd_finalize");
+  }
+  return rc;
+}
+
+static int bwd_blocks(int B) {
+  const int groups = ceil_div(B, BWD_NB);
+  return groups < 592 ? groups : 592;
+}
+
+template <int KIND, int VEC>
+static int launch_bwd(const float* z, const float* mu0, const float* table, const float* dlp, const float* dlpp,
+                      float* dz, float* dvar, float* dnu, float* dcorr, float* scratch, int B, int T, int D,
+                      const ScanGeom& g, cudaStream_t st) {
+  const int groups = ceil_div(B, BWD_NB);
+  const int nblk = bwd_blocks(B);
+  const int gpb = ceil_div(groups, nblk);
+  const int nblk_used = ceil_div(groups, gpb);
+  dim3 grid(nblk_used, g.nseg);
+  if (dlpp)
+    process_bwd_kernel<KIND, VEC, BWD_NB, true><<<grid, g.threads, 0, st>>>(z, mu0, table, dlp, dlpp, dz, scratch, B, T, D, gpb);
+  else
+    process_bwd_kernel<KIND, VEC, BWD_NB, false><<<grid, g.threads, 0, st>>>(z, mu0, table, dlp, dlpp, dz, scratch, B, T, D, gpb);
+  int rc = check_launch("process_bwd_kernel");
+  if (rc) return rc;
+  process_bwd_finalize<<<ceil_div(D, 256), 256, 0, st>>>(scratch, nblk_used, D, dvar, KIND == BRUNO_TP ? dnu : nullptr, dcorr);
+  return check_launch("process_bwd_finalize");
+}
+
+}  // namespace bruno
+
+using namespace bruno;
+
+extern "C" {
+
+const char* bruno_last_error(void) { return g_err; }
+int bruno_abi_version(void) { return 1; }
+
+size_t bruno_process_table_floats(int kind, int T, int D, int with_grad) {
+  return static_cast<size_t>(T * ncf_of(kind) + N_PRIOR) * D * (with_grad ? 4 : 1);
+}
+
+int bruno_process_table(int kind, const float* var_vbl, const float* nu_vbl, const float* corr_vbl, const float* mu0,
+                        const float* mask_dim, float min_nu, int n0, int T, int D, int with_grad, float* table,
+                        void* stream) {
+  (void)mu0;
+  BRUNO_REQUIRE(kind == BRUNO_TP || kind == BRUNO_GP, "bruno_process_table: bad kind %d", kind);
+  BRUNO_REQUIRE(T >= 0 && D > 0 && n0 >= 0, "bruno_process_table: bad sizes T=%d D=%d n0=%d", T, D, n0);
+  BRUNO_REQUIRE(var_vbl && corr_vbl && table && (kind == BRUNO_GP || nu_vbl), "bruno_process_table: null pointer");
+  dim3 grid(ceil_div(D, 128), T + 1);
+  process_table_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(kind, var_vbl, nu_vbl, corr_vbl, mask_dim,
+                                                                              min_nu, n0, T, D, with_grad, table);
+  return check_launch("process_table_kernel");
+}
+
+size_t bruno_process_scratch_floats(int B, int T, int D) {
+  const int nseg = scan_geom(D, false).nseg;  // worst case: the scalar (unaligned) path
+  return nseg > 1 ? static_cast<size_t>(nseg) * B * T * 2 : 0;
+}
+
+int bruno_process_fwd(int kind, const float* z, const float* mu0, const float* table, float* s1, float* s2, float* lp,
+                      float* lp_prior, float* scratch, int B, int T, int D, void* stream) {
+  BRUNO_REQUIRE(kind == BRUNO_TP || kind == BRUNO_GP, "bruno_process_fwd: bad kind %d", kind);
+  BRUNO_REQUIRE(B > 0 && T > 0 && D > 0, "bruno_process_fwd: bad sizes B=%d T=%d D=%d", B, T, D);
+  BRUNO_REQUIRE(z && mu0 && table && lp, "bruno_process_fwd: null pointer");
+  BRUNO_REQUIRE((s1 == nullptr) == (s2 == nullptr) || kind == BRUNO_GP, "bruno_process_fwd: s1/s2 must come together");
+  const bool ptr_ok = aligned16(z) && aligned16(mu0) && aligned16(table) && (!s1 || aligned16(s1)) && (!s2 || aligned16(s2));
+  ScanGeom g = scan_geom(D, ptr_ok);
+  BRUNO_REQUIRE(g.nseg == 1 || scratch, "bruno_process_fwd: scratch required when D is split (D=%d)", D);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (kind == BRUNO_TP)
+    return g.vec == 4 ? launch_fwd<BRUNO_TP, 4>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st)
+                      : launch_fwd<BRUNO_TP, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+  return g.vec == 4 ? launch_fwd<BRUNO_GP, 4>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st)
+                    : launch_fwd<BRUNO_GP, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+}
+
+size_t bruno_process_bwd_scratch_floats(int B, int T, int D) {
+  (void)T;
+  return static_cast<size_t>(bwd_blocks(B)) * 3 * D;
+}
+
+int bruno_process_bwd(int kind, const float* z, const float* mu0, const float* table, const float* dlp,
+                      const float* dlp_prior, float* dz, float* dvar_vbl, float* dnu_vbl, float* dcorr_vbl,
+                      float* scratch, int B, int T, int D, void* stream) {
+  BRUNO_REQUIRE(kind == BRUNO_TP || kind == BRUNO_GP, "bruno_process_bwd: bad kind %d", kind);
+  BRUNO_REQUIRE(B > 0 && T > 0 && D > 0, "bruno_process_bwd: bad sizes B=%d T=%d D=%d", B, T, D);
+  BRUNO_REQUIRE(z && mu0 && table && dlp && dz && dvar_vbl && dcorr_vbl && scratch && (kind == BRUNO_GP || dnu_vbl),
+                "bruno_process_bwd: null pointer");
+  const bool ptr_ok = aligned16(z) && aligned16(mu0) && aligned16(table) && aligned16(dz) && aligned16(scratch);
+  ScanGeom g = scan_geom(D, ptr_ok);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (kind == BRUNO_TP)
+    return g.vec == 4
+               ? launch_bwd<BRUNO_TP, 4>(z, mu0, table, dlp, dlp_prior, dz, dvar_vbl, dnu_vbl, dcorr_vbl, scratch, B, T, D, g, st)
+               : launch_bwd<BRUNO_TP, 1>(z, mu0, table, dlp, dlp_prior, dz, dvar_vbl, dnu_vbl, dcorr_vbl, scratch, B, T, D, g, st);
+  return g.vec == 4
+             ? launch_bwd<BRUNO_GP, 4>(z, mu0, table, dlp, dlp_prior, dz, dvar_vbl, dnu_vbl, dcorr_vbl, scratch, B, T, D, g, st)
+             : launch_bwd<BRUNO_GP, 1>(z, mu0, table, dlp, dlp_prior, dz, dvar_vbl, dnu_vbl, dcorr_vbl, scratch, B, T, D, g, st);
+}
+
+int bruno_process_posterior(int kind, const float* z, const float* var_vbl, const float* nu_vbl, const float* corr_vbl,
+                            const float* mu0, float min_nu, float* mu_out, float* var_out, float* nu_out, int B, int T,
+                            int D, void* stream) {
+  BRUNO_REQUIRE(kind == BRUNO_TP || kind == BRUNO_GP, "bruno_process_posterior: bad kind %d", kind);
+  BRUNO_REQUIRE(B > 0 && T >= 0 && D > 0, "bruno_process_posterior: bad sizes");
+  BRUNO_REQUIRE((z || T == 0) && var_vbl && corr_vbl && mu0 && mu_out && var_out && (kind == BRUNO_GP || (nu_vbl && nu_out)),
+                "bruno_process_posterior: null pointer");
+  dim3 grid(ceil_div(D, 128), B);
+  process_posterior_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(kind, z, var_vbl, nu_vbl, corr_vbl, mu0,
+                                                                                  min_nu, mu_out, var_out, nu_out, B, T, D);
+  return check_launch("process_posterior_kernel");
+}
+
+int bruno_process_sample(int kind, const float* rvs, const float* mu, const float* var, const float* nu, float* out,
+                         int n, int B, int D, long stride_b, void* stream) {
+  BRUNO_REQUIRE(kind == BRUNO_TP || kind == BRUNO_GP, "bruno_process_sample: bad kind %d", kind);
+  BRUNO_REQUIRE(n > 0 && B > 0 && D > 0, "bruno_process_sample: bad sizes");
+  BRUNO_REQUIRE(rvs && mu && var && out && (kind == BRUNO_GP || nu), "bruno_process_sample: null pointer");
+  const size_t total = static_cast<size_t>(n) * B * D;
+  process_sample_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      kind, rvs, mu, var, nu, out, n, B, D, stride_b);
+  return check_launch("process_sample_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+"""Micro-benchmark of the t-process scan kernels (HBM roofline): python tools/bench_process.py [B ...]"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bruno_b200 import _lib  # noqa: E402
+from bruno_b200.nn_extra_student import StudentRecurrentLayer  # noqa: E402
+from bruno_b200.nn_extra_gauss import GaussianRecurrentLayer  # noqa: E402
+from bruno_b200.process import build_table  # noqa: E402
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def main():
+    peaks = json.load(open(os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json'))) if os.path.exists(
+        os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json')) else {'hbm_gbs': 6650.0}
+    Bs = [int(a) for a in sys.argv[1:]] or [32, 4096, 16384, 65536]
+    T, D = 20, 784
+    for kind, layer in (('tp', StudentRecurrentLayer((D,))), ('gp', GaussianRecurrentLayer((D,)))):
+        for B in Bs:
+            z = torch.randn(B, T, D, device='cuda')
+            k = layer.kind
+            nu = layer.nu_vbl.detach() if kind == 'tp' else None
+            tab = build_table(k, layer.var_vbl.detach(), nu, layer.corr_vbl.detach(), layer.mu, None, 2.0, 0, T, True)
+            lp = torch.empty(B, T, device='cuda')
+            lpp = torch.empty(B, T, device='cuda')
+            dz = torch.empty_like(z)
+            dv = torch.empty(1, D, device='cuda')
+            scratch = torch.empty(max(_lib.query('bruno_process_bwd_scratch_floats', B, T, D), 1), device='cuda')
+            for name, fn, nbytes in (
+                ('fwd', lambda: _lib.call('bruno_process_fwd', k, z, layer.mu, tab, None, None, lp, None, scratch, B, T, D),
+                 4 * B * T * D + 4 * B * T),
+                ('fwd+prior', lambda: _lib.call('bruno_process_fwd', k, z, layer.mu, tab, None, None, lp, lpp, scratch, B, T, D),
+                 4 * B * T * D + 8 * B * T),
+                ('bwd', lambda: _lib.call('bruno_process_bwd', k, z, layer.mu, tab, lp, None, dz, dv, dv if kind == 'gp' else torch.empty_like(dv), dv, scratch, B, T, D),
+                 8 * B * T * D + 4 * B * T),
+            ):
+                t = timeit(fn)
+                gbs = nbytes / t * 1e-9
+                print('%s %-9s B=%6d T=%d D=%d  %8.1f us  %7.1f GB/s  (%.1f%% of measured %.0f GB/s)' % (
+                    kind, name, B, T, D, t * 1e6, gbs, 100 * gbs / peaks['hbm_gbs'], peaks['hbm_gbs']), flush=True)
+
+
+if __name__ == '__main__':
+    main()
