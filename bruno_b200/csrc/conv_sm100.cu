@@ -1,0 +1,524 @@
+// 3x3 64->64 convolutions of the Real NVP s/t ResNet (nn_extra_nvp.py:108-141, conv2d_wn :378-404) as tcgen05
+// implicit GEMMs on sm_100a, forward / dgrad (one kernel, different epilogues) and wgrad.
+//
+//   forward / dgrad:  D[128 positions][64 out-ch] = sum over 9 taps, 4 K-steps of  A_tap[128][16] * W_tap[16][64]
+//     A_tap is a ROW-SHIFTED view of one shared-memory slab (see slab.cuh): no im2col, one 1-D bulk copy per tile.
+//     Warp roles: warp 0 = bulk-copy producer, warp 1 = single-thread tcgen05.mma issuer, warps 2..5 = epilogue
+//     (tcgen05.ld -> bias / ELU / residual / ELU' -> bf16 -> swizzled store).  TMEM accumulators are double buffered so
+//     the epilogue of tile i overlaps the MMAs of tile i+1.  Persistent: one CTA per SM, weights loaded once.
+//   wgrad:  dW[tap][ci][co] = sum over positions  X[pos + shift(tap)][ci] * G[pos][co]
+//     both operands MN-major (contraction over positions = rows); two taps share one M=128 instruction (the two
+//     64-channel atoms are LBO bytes apart = the row shift between the taps); the bias gradient rides along as the
+//     spare atom of the ninth tap (a constant "ones" operand).  fp32 accumulation in TMEM over all tiles of the CTA.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "slab.cuh"
+
+namespace bruno {
+
+constexpr int W_TAP_BYTES = 64 * 128;        // one tap: 64 rows (N) x 64 bf16 (K)
+constexpr int W_BYTES = 9 * W_TAP_BYTES;     // 73728
+constexpr int NSTAGE = 3;
+constexpr int CONV_THREADS = 192;
+
+enum ConvMode { MODE_ELU = 0, MODE_RES_ELU = 1, MODE_MUL = 2, MODE_ADD_MUL = 3, MODE_LINEAR = 4 };
+
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+// derivative of ELU expressed through its OUTPUT o: 1 if o > 0 else o + 1
+__device__ __forceinline__ float elu_grad_from_out(float o) { return o > 0.f ? 1.f : o + 1.f; }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+}
+
+struct ConvSmem {
+  uint64_t full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2], wbar;
+  uint32_t tmem_base;
+  float bias[64];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
+               const uint8_t* __restrict__ aux1, const uint8_t* __restrict__ aux2, uint8_t* __restrict__ out,
+               SlabGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t slab_bytes = static_cast<uint32_t>(TILE_M + 2 * g.HALO) * SLAB_ROW_BYTES;
+  uint8_t* wsm = smem;
+  uint8_t* slabs = smem + W_BYTES;
+  ConvSmem* cs = reinterpret_cast<ConvSmem*>(slabs + NSTAGE * slab_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&cs->full[s], 1);
+      mbar_init(&cs->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&cs->tfull[a], 1);
+      mbar_init(&cs->tempty[a], 4);
+    }
+    mbar_init(&cs->wbar, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 64) cs->bias[threadIdx.x] = (MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR) ? bias[threadIdx.x] : 0.f;
+  if (warp == 0) {
+    tmem_alloc(&cs->tmem_base, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = cs->tmem_base;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
+      bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.NT; tile += gridDim.x, ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        mbar_wait(&cs->empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&cs->full[s], slab_bytes);
+        bulk_g2s(slabs + s * slab_bytes, in + static_cast<size_t>(tile) * TILE_M * SLAB_ROW_BYTES, slab_bytes, &cs->full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      mbar_wait(&cs->wbar, 0);
+      const uint32_t w_addr = smem_u32(wsm);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.NT; tile += gridDim.x, ++it) {
+        const int s = it % NSTAGE;
+        const uint32_t ph = (it / NSTAGE) & 1;
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&cs->tempty[a], aph ^ 1);
+        mbar_wait(&cs->full[s], ph);
+        tc_fence_after();
+        const uint32_t slab_addr = smem_u32(slabs + s * slab_bytes);
+        const uint32_t d_tmem = tmem + a * 64;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int row_off = g.HALO + (tap / 3 - 1) * g.P + (tap % 3 - 1);
+          const uint32_t a_base = slab_addr + row_off * SLAB_ROW_BYTES;
+          const uint32_t b_base = w_addr + tap * W_TAP_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(d_tmem, umma_desc_sw128(a_base + k * 32, 16, 1024), umma_desc_sw128(b_base + k * 32, 16, 1024),
+                      idesc, (tap | k) != 0);
+          }
+        }
+        umma_commit(&cs->empty[s]);
+        umma_commit(&cs->tfull[a]);
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < g.NT; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int data_row = tile * TILE_M + row;
+      const size_t R = static_cast<size_t>(g.HALO) + data_row;
+      const bool valid = slab_row_is_pixel(data_row, g);
+      uint4 x1[8], x2[8];
+      if (MODE != MODE_ELU && MODE != MODE_LINEAR) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          x1[j] = valid ? ldg_nc_u4(reinterpret_cast<const uint4*>(aux1 + slab_chunk_off(R, j))) : make_uint4(0, 0, 0, 0);
+          if (MODE == MODE_ADD_MUL)
+            x2[j] = valid ? ldg_nc_u4(reinterpret_cast<const uint4*>(aux2 + slab_chunk_off(R, j))) : make_uint4(0, 0, 0, 0);
+        }
+      }
+      mbar_wait(&cs->tfull[a], aph);
+      tc_fence_after();
+      uint32_t v[2][32];
+      const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 64;
+      tmem_ld32(taddr, v[0]);
+      tmem_ld32(taddr + 32, v[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cs->tempty[a]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j >> 2][(j & 3) * 8 + e]);
+        if (MODE == MODE_ELU || MODE == MODE_LINEAR) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float t = o[e] + cs->bias[j * 8 + e];
+            o[e] = MODE == MODE_ELU ? elu_f(t) : t;
+          }
+        } else if (MODE == MODE_RES_ELU) {
+          float s[8];
+          unpack8(x1[j], s);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = elu_f(o[e] + cs->bias[j * 8 + e] + s[e]);
+        } else if (MODE == MODE_MUL) {
+          float s[8];
+          unpack8(x1[j], s);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(s[e]);
+        } else {
+          float s[8], t[8];
+          unpack8(x1[j], s);
+          unpack8(x2[j], t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(s[e]);
+        }
+        const uint4 packed = valid ? pack8(o) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(out + slab_chunk_off(R, j)) = packed;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wgrad
+// ------------------------------------------------------------------------------------------------------------
+constexpr int WG_STAGES = 3;
+constexpr int ONES_BYTES = 16 * 128;
+
+struct WgradSmem {
+  uint64_t full[WG_STAGES], empty[WG_STAGES], done;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3_wgrad_kernel(const uint8_t* __restrict__ x, const uint8_t* __restrict__ gr, float* __restrict__ dW,
+                     float* __restrict__ db, SlabGeom g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t xs_bytes = static_cast<uint32_t>(TILE_M + 2 * g.HALO) * SLAB_ROW_BYTES;
+  const uint32_t gs_bytes = TILE_M * SLAB_ROW_BYTES;
+  const uint32_t stage_bytes = xs_bytes + gs_bytes;       // multiple of 1024
+  uint8_t* stages = smem;
+  uint8_t* ones = smem + WG_STAGES * stage_bytes;         // 1024-aligned, AFTER the stages (positive LBO)
+  WgradSmem* ws = reinterpret_cast<WgradSmem*>(ones + ONES_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // constant operand: logical channel 0 of every row = 1.0, everything else 0 (swizzled like a slab row)
+  for (int i = threadIdx.x; i < ONES_BYTES / 16; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (c == (r & 7)) val.x = 0x00003f80u;  // bf16 1.0 in element 0
+    reinterpret_cast<uint4*>(ones)[i] = val;
+  }
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&ws->full[s], 1);
+      mbar_init(&ws->empty[s], 1);
+    }
+    mbar_init(&ws->done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&ws->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ws->tmem_base;
+
+  // contiguous tile range per CTA (keeps the fp32 accumulation order fixed for a given grid)
+  const int per = (g.NT + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per;
+  const int t1 = min(t0 + per, g.NT);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = t0; tile < t1; ++tile, ++it) {
+        const int s = it % WG_STAGES;
+        const uint32_t ph = (it / WG_STAGES) & 1;
+        mbar_wait(&ws->empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&ws->full[s], stage_bytes);
+        uint8_t* st = stages + s * stage_bytes;
+        bulk_g2s(st, x + static_cast<size_t>(tile) * TILE_M * SLAB_ROW_BYTES, xs_bytes, &ws->full[s]);
+        bulk_g2s(st + xs_bytes, gr + (static_cast<size_t>(tile) * TILE_M + g.HALO) * SLAB_ROW_BYTES, gs_bytes, &ws->full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      const uint32_t ones_addr = smem_u32(ones);
+      int it = 0;
+      for (int tile = t0; tile < t1; ++tile, ++it) {
+        const int s = it % WG_STAGES;
+        const uint32_t ph = (it / WG_STAGES) & 1;
+        mbar_wait(&ws->full[s], ph);
+        tc_fence_after();
+        const uint32_t xs_addr = smem_u32(stages + s * stage_bytes);
+        const uint32_t gs_addr = xs_addr + xs_bytes;
+#pragma unroll 1
+        for (int ks = 0; ks < TILE_M / 16; ++ks) {
+          const uint64_t bdesc = umma_desc_sw128(gs_addr + ks * 16 * SLAB_ROW_BYTES, 16, 1024);
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            const int tapA = 2 * c;
+            const int offA = g.HALO + (tapA / 3 - 1) * g.P + (tapA % 3 - 1) + ks * 16;
+            const uint32_t a_addr = xs_addr + offA * SLAB_ROW_BYTES;
+            uint32_t lbo;
+            if (c < 4) {
+              const int tapB = tapA + 1;
+              const int offB = g.HALO + (tapB / 3 - 1) * g.P + (tapB % 3 - 1) + ks * 16;
+              lbo = static_cast<uint32_t>(offB - offA) * SLAB_ROW_BYTES;
+            } else {
+              lbo = ones_addr - a_addr;
+            }
+            umma_bf16(tmem + c * 64, umma_desc_sw128(a_addr, lbo, 1024), bdesc, idesc, (it | ks) != 0);
+          }
+        }
+        umma_commit(&ws->empty[s]);
+      }
+      umma_commit(&ws->done);
+    }
+  } else if (t1 > t0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;  // accumulator row: [0,64) = tap A channels, [64,128) = tap B channels
+    mbar_wait(&ws->done, 0);
+    tc_fence_after();
+    for (int c = 0; c < 5; ++c) {
+      const int tap = 2 * c + (m >> 6);
+      const int ci = m & 63;
+      uint32_t v[32];
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c * 64 + half * 32, v);
+        tmem_ld_wait();
+        float* dst = nullptr;
+        if (tap < 9) dst = dW + (static_cast<size_t>(tap) * 64 + ci) * 64 + half * 32;
+        else if (ci == 0) dst = db + half * 32;
+        if (dst) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            red_add_v4(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                       __uint_as_float(v[e + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight-norm pack (forward + transposed/flipped operand for dgrad) and weight-norm backward
+//   W[ky,kx,ci,co] = g[co] * V[ky,kx,ci,co] / sqrt(max(sum_{ky,kx,ci} V^2, 1e-12))      nn_extra_nvp.py:389
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_wn_pack_kernel(const float* __restrict__ V, const float* __restrict__ gain, uint8_t* __restrict__ wfwd,
+                    uint8_t* __restrict__ wbwd) {
+  __shared__ float scale[64];
+  __shared__ float part[4][64];
+  const int l = blockIdx.x;
+  const float* v = V + static_cast<size_t>(l) * 9 * 64 * 64;
+  const int co = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  float s = 0.f;
+  for (int r = grp; r < 9 * 64; r += 4) {
+    const float t = v[r * 64 + co];
+    s = fmaf(t, t, s);
+  }
+  part[grp][co] = s;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const float n2 = part[0][co] + part[1][co] + part[2][co] + part[3][co];
+    scale[co] = gain[l * 64 + co] * rsqrtf(fmaxf(n2, 1e-12f));
+  }
+  __syncthreads();
+  uint8_t* wf = wfwd + static_cast<size_t>(l) * W_BYTES;
+  uint8_t* wb = wbwd ? wbwd + static_cast<size_t>(l) * W_BYTES : nullptr;
+  // forward operand: [tap][row = co][k = ci]; one thread packs 8 consecutive k
+  for (int i = threadIdx.x; i < 9 * 64 * 8; i += blockDim.x) {
+    const int tap = i / 512, rem = i % 512, rowi = rem >> 3, j = rem & 7;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = v[(tap * 64 + (j * 8 + e)) * 64 + rowi] * scale[rowi];
+    *reinterpret_cast<uint4*>(wf + tap * W_TAP_BYTES + rowi * 128 + ((j ^ (rowi & 7)) << 4)) = pack8(f);
+    if (wb) {
+      // dgrad operand: tap' = 8 - tap, [row = ci][k = co]
+      float h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = v[(tap * 64 + rowi) * 64 + (j * 8 + e)] * scale[j * 8 + e];
+      *reinterpret_cast<uint4*>(wb + (8 - tap) * W_TAP_BYTES + rowi * 128 + ((j ^ (rowi & 7)) << 4)) = pack8(h);
+    }
+  }
+}
+
+// dV, dg from dW (all [L][9][64][64] / [L][64]); K = rows per output channel (576 for 3x3, C for the 1x1 c1)
+__global__ void __launch_bounds__(256)
+conv_wn_bwd_kernel(const float* __restrict__ V, const float* __restrict__ gain, const float* __restrict__ dW,
+                   float* __restrict__ dV, float* __restrict__ dgain, int K) {
+  __shared__ float p_n2[4][64], p_dot[4][64], s_a[64], s_b[64];
+  const int l = blockIdx.x;
+  const float* v = V + static_cast<size_t>(l) * K * 64;
+  const float* dw = dW + static_cast<size_t>(l) * K * 64;
+  const int co = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  float n2 = 0.f, dot = 0.f;
+  for (int r = grp; r < K; r += 4) {
+    const float t = v[r * 64 + co];
+    n2 = fmaf(t, t, n2);
+    dot = fmaf(t, dw[r * 64 + co], dot);
+  }
+  p_n2[grp][co] = n2;
+  p_dot[grp][co] = dot;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const float N2 = fmaxf(p_n2[0][co] + p_n2[1][co] + p_n2[2][co] + p_n2[3][co], 1e-12f);
+    const float DOT = p_dot[0][co] + p_dot[1][co] + p_dot[2][co] + p_dot[3][co];
+    const float inv = rsqrtf(N2);
+    const float gg = gain[l * 64 + co];
+    dgain[l * 64 + co] = DOT * inv;
+    s_a[co] = gg * inv;               // dV = a * dW - b * V
+    s_b[co] = gg * inv * DOT / N2;
+  }
+  __syncthreads();
+  float* dv = dV + static_cast<size_t>(l) * K * 64;
+  for (int r = grp; r < K; r += 4) dv[r * 64 + co] = s_a[co] * dw[r * 64 + co] - s_b[co] * v[r * 64 + co];
+}
+
+static size_t conv_smem_bytes(const SlabGeom& g) {
+  return 1024 + W_BYTES + static_cast<size_t>(NSTAGE) * (TILE_M + 2 * g.HALO) * SLAB_ROW_BYTES + sizeof(ConvSmem) + 64;
+}
+static size_t wgrad_smem_bytes(const SlabGeom& g) {
+  return 1024 + static_cast<size_t>(WG_STAGES) * ((TILE_M + 2 * g.HALO) + TILE_M) * SLAB_ROW_BYTES + ONES_BYTES +
+         sizeof(WgradSmem) + 64;
+}
+
+static int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
+template <int MODE>
+static int launch_conv(const void* in, const void* w, const float* bias, const void* a1, const void* a2, void* out,
+                       const SlabGeom& g, cudaStream_t st) {
+  const size_t smem = conv_smem_bytes(g);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv3x3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
+  const int grid = g.NT < num_sms() ? g.NT : num_sms();
+  conv3x3_kernel<MODE><<<grid, CONV_THREADS, smem, st>>>(
+      static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias, static_cast<const uint8_t*>(a1),
+      static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g);
+  return check_launch("conv3x3_kernel");
+}
+
+}  // namespace bruno
+
+using namespace bruno;
+
+extern "C" {
+
+size_t bruno_slab_bytes(int N, int H, int W) {
+  const SlabGeom g = slab_geom(N, H, W);
+  return static_cast<size_t>(g.rows) * SLAB_ROW_BYTES;
+}
+
+size_t bruno_conv_wpack_bytes(void) { return W_BYTES; }
+
+int bruno_conv_wn_pack(const float* V, const float* g, void* wfwd, void* wbwd, int L, void* stream) {
+  BRUNO_REQUIRE(V && g && wfwd && L > 0, "bruno_conv_wn_pack: bad arguments");
+  BRUNO_REQUIRE(aligned16(wfwd) && (!wbwd || aligned16(wbwd)), "bruno_conv_wn_pack: packed operands must be 16-byte aligned");
+  conv_wn_pack_kernel<<<L, 256, 0, static_cast<cudaStream_t>(stream)>>>(V, g, static_cast<uint8_t*>(wfwd),
+                                                                        static_cast<uint8_t*>(wbwd));
+  return check_launch("conv_wn_pack_kernel");
+}
+
+int bruno_conv_wn_bwd(const float* V, const float* g, const float* dW, float* dV, float* dg, int L, int K, void* stream) {
+  BRUNO_REQUIRE(V && g && dW && dV && dg && L > 0 && K > 0, "bruno_conv_wn_bwd: bad arguments");
+  conv_wn_bwd_kernel<<<L, 256, 0, static_cast<cudaStream_t>(stream)>>>(V, g, dW, dV, dg, K);
+  return check_launch("conv_wn_bwd_kernel");
+}
+
+int bruno_conv3x3(int mode, const void* in_slab, const void* wpack, const float* bias, const void* aux1, const void* aux2,
+                  void* out_slab, int N, int H, int W, void* stream) {
+  BRUNO_REQUIRE(in_slab && wpack && out_slab && N > 0 && H > 0 && W > 0, "bruno_conv3x3: bad arguments");
+  BRUNO_REQUIRE(aligned16(in_slab) && aligned16(wpack) && aligned16(out_slab), "bruno_conv3x3: 16-byte alignment required");
+  BRUNO_REQUIRE(in_slab != out_slab, "bruno_conv3x3: in-place convolution is not possible");
+  const SlabGeom g = slab_geom(N, H, W);
+  BRUNO_REQUIRE(conv_smem_bytes(g) <= 227 * 1024, "bruno_conv3x3: W=%d too wide for the shared-memory slab", W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (mode) {
+    case MODE_ELU:
+      BRUNO_REQUIRE(bias, "bruno_conv3x3: bias required");
+      return launch_conv<MODE_ELU>(in_slab, wpack, bias, nullptr, nullptr, out_slab, g, st);
+    case MODE_RES_ELU:
+      BRUNO_REQUIRE(bias && aux1, "bruno_conv3x3: bias and skip slab required");
+      return launch_conv<MODE_RES_ELU>(in_slab, wpack, bias, aux1, nullptr, out_slab, g, st);
+    case MODE_MUL:
+      BRUNO_REQUIRE(aux1, "bruno_conv3x3: saved-activation slab required");
+      return launch_conv<MODE_MUL>(in_slab, wpack, nullptr, aux1, nullptr, out_slab, g, st);
+    case MODE_ADD_MUL:
+      BRUNO_REQUIRE(aux1 && aux2, "bruno_conv3x3: saved-activation and addend slabs required");
+      return launch_conv<MODE_ADD_MUL>(in_slab, wpack, nullptr, aux1, aux2, out_slab, g, st);
+    case MODE_LINEAR:
+      BRUNO_REQUIRE(bias, "bruno_conv3x3: bias required");
+      return launch_conv<MODE_LINEAR>(in_slab, wpack, bias, nullptr, nullptr, out_slab, g, st);
+    default:
+      set_last_error("bruno_conv3x3: unknown mode %d", mode);
+      return BRUNO_EINVAL;
+  }
+}
+
+int bruno_conv3x3_wgrad(const void* x_slab, const void* g_slab, float* dW, float* db, int N, int H, int W, void* stream) {
+  BRUNO_REQUIRE(x_slab && g_slab && dW && db && N > 0 && H > 0 && W > 0, "bruno_conv3x3_wgrad: bad arguments");
+  BRUNO_REQUIRE(aligned16(x_slab) && aligned16(g_slab) && aligned16(dW) && aligned16(db), "bruno_conv3x3_wgrad: alignment");
+  const SlabGeom g = slab_geom(N, H, W);
+  const size_t smem = wgrad_smem_bytes(g);
+  BRUNO_REQUIRE(smem <= 227 * 1024, "bruno_conv3x3_wgrad: W=%d too wide", W);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
+  const int grid = g.NT < num_sms() ? g.NT : num_sms();
+  conv3x3_wgrad_kernel<<<grid, CONV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(x_slab), static_cast<const uint8_t*>(g_slab), dW, db, g);
+  return check_launch("conv3x3_wgrad_kernel");
+}
+
+}  // extern "C"

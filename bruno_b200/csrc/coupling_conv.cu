@@ -1,0 +1,77 @@
+// Host-side orchestration of one CouplingLayerConv (nn_extra_nvp.py:58-187): the whole layer -- c1, R residual
+// blocks of two tensor-core convolutions, the two heads, the coupling and the log-det -- is ONE call through the C ABI
+// (19 kernel launches forward for R = 8), so the Python host adds one ctypes call per layer, not one per op.
+#include "common.cuh"
+
+using namespace bruno;
+
+extern "C" {
+
+size_t bruno_coupling_conv_slabs(int R, int save) { return save ? static_cast<size_t>(2 * R + 1) : 3; }
+
+int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float* ld_out, int N, int H, int W, int C, int R,
+                            int mask_type, int inverse, const float* V1, const float* g1, const float* b1,
+                            const void* wfwd, const float* br, const float* Ks, const float* bs, const float* Kt,
+                            const float* bt, void* slabs, int n_slabs, void* stream) {
+  BRUNO_REQUIRE(x && ld_in && y && ld_out && V1 && g1 && b1 && wfwd && br && Ks && bs && Kt && bt && slabs,
+                "bruno_coupling_conv_fwd: null pointer");
+  BRUNO_REQUIRE(R >= 1 && (n_slabs >= 3), "bruno_coupling_conv_fwd: need >= 3 slabs (got %d)", n_slabs);
+  const bool save = n_slabs >= 2 * R + 1;
+  const size_t sb = bruno_slab_bytes(N, H, W), wb = bruno_conv_wpack_bytes();
+  auto S = [&](int i) { return static_cast<void*>(static_cast<uint8_t*>(slabs) + static_cast<size_t>(i) * sb); };
+  auto Wp = [&](int l) { return static_cast<const void*>(static_cast<const uint8_t*>(wfwd) + static_cast<size_t>(l) * wb); };
+  int rc;
+  if ((rc = bruno_c1_fwd(x, V1, g1, b1, S(0), N, H, W, C, mask_type, stream))) return rc;
+  int hi = 0;
+  for (int r = 0; r < R; ++r) {
+    const int ui = save ? 2 * r + 1 : (hi + 1) % 3;
+    const int ni = save ? 2 * r + 2 : (hi + 2) % 3;
+    if ((rc = bruno_conv3x3(0, S(hi), Wp(2 * r), br + (2 * r) * 64, nullptr, nullptr, S(ui), N, H, W, stream))) return rc;
+    if ((rc = bruno_conv3x3(1, S(ui), Wp(2 * r + 1), br + (2 * r + 1) * 64, S(hi), nullptr, S(ni), N, H, W, stream))) return rc;
+    hi = ni;
+  }
+  return bruno_heads_coupling(x, S(hi), Ks, bs, Kt, bt, ld_in, y, ld_out, N, H, W, C, mask_type, inverse, stream);
+}
+
+int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, int N, int H, int W, int C, int R,
+                            int mask_type, const float* V1, const float* g1, const float* Vr, const float* gr,
+                            const void* wbwd, const float* Ks, const float* bs, const float* Kt, const float* bt,
+                            const void* saved_slabs, void* gslabs, float* dx, float* dV1, float* dg1, float* db1, float* dVr,
+                            float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt, void* stream) {
+  BRUNO_REQUIRE(x && dy && dld && V1 && g1 && Vr && gr && wbwd && Ks && bs && Kt && bt && saved_slabs && gslabs && dx && dV1 &&
+                    dg1 && db1 && dVr && dgr && dbr && dKs && dbs && dKt && dbt, "bruno_coupling_conv_bwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t sb = bruno_slab_bytes(N, H, W), wb = bruno_conv_wpack_bytes();
+  auto S = [&](int i) { return static_cast<const void*>(static_cast<const uint8_t*>(saved_slabs) + static_cast<size_t>(i) * sb); };
+  auto Wp = [&](int l) { return static_cast<const void*>(static_cast<const uint8_t*>(wbwd) + static_cast<size_t>(l) * wb); };
+  void* G[3];
+  for (int i = 0; i < 3; ++i) G[i] = static_cast<uint8_t*>(gslabs) + static_cast<size_t>(i) * sb;
+  cudaMemsetAsync(dVr, 0, static_cast<size_t>(2 * R) * 9 * 64 * 64 * sizeof(float), st);
+  cudaMemsetAsync(dbr, 0, static_cast<size_t>(2 * R) * 64 * sizeof(float), st);
+  cudaMemsetAsync(dV1, 0, static_cast<size_t>(C) * 64 * sizeof(float), st);
+  cudaMemsetAsync(db1, 0, 64 * sizeof(float), st);
+  cudaMemsetAsync(dKs, 0, static_cast<size_t>(C) * 64 * sizeof(float), st);
+  cudaMemsetAsync(dKt, 0, static_cast<size_t>(C) * 64 * sizeof(float), st);
+  cudaMemsetAsync(dbs, 0, static_cast<size_t>(C) * sizeof(float), st);
+  cudaMemsetAsync(dbt, 0, static_cast<size_t>(C) * sizeof(float), st);
+  int rc;
+  if ((rc = bruno_heads_coupling_bwd(x, S(2 * R), Ks, bs, Kt, bt, dy, dld, dx, G[0], dKs, dbs, dKt, dbt, N, H, W, C,
+                                     mask_type, stream))) return rc;
+  int a = 0;
+  for (int r = R - 1; r >= 0; --r) {
+    const int b = (a + 1) % 3, c = (a + 2) % 3;
+    float* dW3 = dVr + static_cast<size_t>(2 * r + 1) * 9 * 64 * 64;
+    float* dW2 = dVr + static_cast<size_t>(2 * r) * 9 * 64 * 64;
+    if ((rc = bruno_conv3x3_wgrad(S(2 * r + 1), G[a], dW3, dbr + (2 * r + 1) * 64, N, H, W, stream))) return rc;
+    if ((rc = bruno_conv3x3(2, G[a], Wp(2 * r + 1), nullptr, S(2 * r + 1), nullptr, G[b], N, H, W, stream))) return rc;
+    if ((rc = bruno_conv3x3_wgrad(S(2 * r), G[b], dW2, dbr + (2 * r) * 64, N, H, W, stream))) return rc;
+    if ((rc = bruno_conv3x3(3, G[b], Wp(2 * r), nullptr, S(2 * r), G[a], G[c], N, H, W, stream))) return rc;
+    a = c;
+  }
+  if ((rc = bruno_c1_bwd(x, V1, g1, G[a], dx, dV1, db1, N, H, W, C, mask_type, stream))) return rc;
+  // weight-norm backward, in place over the raw weight gradients
+  if ((rc = bruno_conv_wn_bwd(Vr, gr, dVr, dVr, dgr, 2 * R, 9 * 64, stream))) return rc;
+  return bruno_conv_wn_bwd(V1, g1, dV1, dV1, dg1, 1, C, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,341 @@
+// Dense (fully connected) coupling layers: CouplingLayerDense (nn_extra_nvp.py:190-274) with dense_wn (:408-432).
+//   h1 = ELU((x b) V1 * g1/|V1| + b1);  h2 = ELU(h1 V2 * g2/|V2| + b2)
+//   s = tanh(h2 Ks + bs)(1-b);  t = (h2 Kt + bt)(1-b);  y = x b + (1-b)(x e^s + t);  ld += sum s
+// fp32 throughout (these layers carry 0.4 % of the FLOPs of bn2_omniglot and all of the parity budget of the dense
+// en2 config): a register-tiled CUDA-core SGEMM with fused column-scale / bias / ELU epilogue, plus the elementwise
+// coupling kernels and the hand-written backward, orchestrated in C so that one coupling is ONE host call.
+#include "common.cuh"
+
+namespace bruno {
+
+constexpr int GB = 64;   // block tile M and N
+constexpr int GK = 16;
+
+struct GemmEpi {
+  const float* col_scale;  // out = acc * col_scale[n]          (may be null)
+  const float* bias;       // + bias[n]                         (may be null)
+  float* pre_out;          // store the pre-activation here too (may be null)
+  int act;                 // 0 none, 1 ELU
+  int accumulate;          // C += result
+  const float* a_kscale;   // A[m,k] *= a_kscale[k]             (may be null)
+};
+
+// C[M,N] = op(A)[M,K] * op(B)[K,N];  transA: A stored [K,M];  transB: B stored [N,K].  Row-major, leading dims given.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+             float* __restrict__ C, int ldc, GemmEpi ep) {
+  __shared__ float As[GK][GB + 4];
+  __shared__ float Bs[GK][GB + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
+  const int tx = tid & 15, ty = tid >> 4;  // thread computes rows ty*4.., cols tx*4..
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m, k;
+      if (TA) { m = tid & 63; k = (tid >> 6) + 4 * i; }
+      else    { k = tid & 15; m = (tid >> 4) + 16 * i; }
+      float v = 0.f;
+      if (m0 + m < M && k0 + k < K) {
+        v = TA ? A[static_cast<size_t>(k0 + k) * lda + m0 + m] : A[static_cast<size_t>(m0 + m) * lda + k0 + k];
+        if (ep.a_kscale) v *= ep.a_kscale[k0 + k];
+      }
+      As[k][m] = v;
+      int n, kb;
+      if (TB) { kb = tid & 15; n = (tid >> 4) + 16 * i; }
+      else    { n = tid & 63; kb = (tid >> 6) + 4 * i; }
+      float w = 0.f;
+      if (n0 + n < N && k0 + kb < K)
+        w = TB ? B[static_cast<size_t>(n0 + n) * ldb + k0 + kb] : B[static_cast<size_t>(k0 + kb) * ldb + n0 + n];
+      Bs[kb][n] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (ep.col_scale) v *= ep.col_scale[n];
+      if (ep.bias) v += ep.bias[n];
+      const size_t o = static_cast<size_t>(m) * ldc + n;
+      if (ep.pre_out) ep.pre_out[o] = v;
+      if (ep.act == 1) v = v > 0.f ? v : expm1f(v);
+      if (ep.accumulate) v += C[o];
+      C[o] = v;
+    }
+  }
+}
+
+static int gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                const GemmEpi& ep, cudaStream_t st) {
+  dim3 grid(ceil_div(N, GB), ceil_div(M, GB));
+  if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
+  else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
+  else if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
+  else sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
+  return check_launch("sgemm_kernel");
+}
+
+__device__ __forceinline__ float dense_mask_b(int mask_type, int d) {
+  // nn_extra_nvp.py:199-221: 'even' -> b = idx % 2, 'odd' -> 1 - idx % 2 on the flattened (h, w, c) index
+  return mask_type == BRUNO_MASK_EVEN ? static_cast<float>(d & 1) : static_cast<float>(1 - (d & 1));
+}
+
+// sc[j] = g[j] / ||V[:, j]||_2   (tf.norm, no epsilon: nvp:419)
+__global__ void dense_wn_scale_kernel(const float* __restrict__ V, const float* __restrict__ g, float* __restrict__ sc,
+                                      int K, int N) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float n2 = 0.f;
+  for (int k = 0; k < K; ++k) n2 = fmaf(V[static_cast<size_t>(k) * N + j], V[static_cast<size_t>(k) * N + j], n2);
+  sc[j] = g[j] * rsqrtf(n2);
+}
+
+__global__ void dense_mask_mul_kernel(const float* __restrict__ x, float* __restrict__ xm, size_t total, int D, int mask_type) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < total) xm[i] = x[i] * dense_mask_b(mask_type, static_cast<int>(i % D));
+}
+
+__device__ __forceinline__ float block_sum_256d(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w];
+  return s;
+}
+
+// one block per row
+__global__ void __launch_bounds__(256)
+dense_coupling_kernel(const float* __restrict__ x, const float* __restrict__ s_pre, const float* __restrict__ t_pre,
+                      const float* __restrict__ ld_in, float* __restrict__ y, float* __restrict__ ld_out, int D,
+                      int mask_type, int inverse) {
+  __shared__ float red[8];
+  const int n = blockIdx.x;
+  const size_t o = static_cast<size_t>(n) * D;
+  float ssum = 0.f;
+  for (int d = threadIdx.x; d < D; d += 256) {
+    const float xv = x[o + d];
+    float out = xv;
+    if (dense_mask_b(mask_type, d) == 0.f) {
+      const float s = tanhf(s_pre[o + d]);
+      ssum += s;
+      out = inverse ? (xv - t_pre[o + d]) * expf(-s) : fmaf(xv, expf(s), t_pre[o + d]);
+    }
+    y[o + d] = out;
+  }
+  const float tot = block_sum_256d(ssum, red);
+  if (threadIdx.x == 0) ld_out[n] = ld_in[n] + (inverse ? -tot : tot);
+}
+
+__global__ void dense_coupling_bwd_kernel(const float* __restrict__ x, const float* __restrict__ s_pre,
+                                          const float* __restrict__ dy, const float* __restrict__ dld,
+                                          float* __restrict__ dx, float* __restrict__ ds_pre, float* __restrict__ dt_pre,
+                                          size_t total, int D, int mask_type) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int d = static_cast<int>(i % D);
+  const size_t n = i / D;
+  const float g = dy[i];
+  float dxv = g, dsp = 0.f, dtp = 0.f;
+  if (dense_mask_b(mask_type, d) == 0.f) {
+    const float s = tanhf(s_pre[i]);
+    const float es = expf(s);
+    dxv = g * es;
+    dtp = g;
+    dsp = (g * x[i] * es + dld[n]) * (1.f - s * s);
+  }
+  dx[i] = dxv;
+  ds_pre[i] = dsp;
+  dt_pre[i] = dtp;
+}
+
+// dpre = dh * ELU'(pre)
+__global__ void elu_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dh, float* __restrict__ dpre,
+                               size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float p = pre[i];
+  dpre[i] = dh[i] * (p > 0.f ? 1.f : expf(p));
+}
+
+// out1[j] = sum_m A[m,j];  out2[j] = sum_m A[m,j] * Bm[m,j] (if Bm)      -- one thread per column (M is small)
+__global__ void col_reduce_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ out1,
+                                  float* __restrict__ out2, int M, int N) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float a = 0.f, b = 0.f;
+  for (int m = 0; m < M; ++m) {
+    const float v = A[static_cast<size_t>(m) * N + j];
+    a += v;
+    if (Bm) b = fmaf(v, Bm[static_cast<size_t>(m) * N + j], b);
+  }
+  out1[j] = a;
+  if (out2) out2[j] = b;
+}
+
+// weight-norm backward for dense_wn.  dVraw = x^T dpre;  r1 = colsum(dpre * pre);  db = colsum(dpre).
+//   u = (pre - b)/sc  =>  dsc = (r1 - b db)/sc;  dg = dsc/nrm;  dV = dVraw sc - dsc g / nrm^3 V
+__global__ void dense_wn_bwd_kernel(const float* __restrict__ V, const float* __restrict__ g, const float* __restrict__ b,
+                                    const float* __restrict__ r1, const float* __restrict__ db, float* __restrict__ dV /*in: dVraw*/,
+                                    float* __restrict__ dg, int K, int N) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float n2 = 0.f;
+  for (int k = 0; k < K; ++k) n2 = fmaf(V[static_cast<size_t>(k) * N + j], V[static_cast<size_t>(k) * N + j], n2);
+  const float inv = rsqrtf(n2);
+  const float sc = g[j] * inv;
+  const float dsc = fabsf(sc) > 1e-30f ? (r1[j] - b[j] * db[j]) / sc : 0.f;
+  dg[j] = dsc * inv;
+  const float coef = dsc * g[j] * inv * inv * inv;
+  for (int k = 0; k < K; ++k) {
+    const size_t o = static_cast<size_t>(k) * N + j;
+    dV[o] = dV[o] * sc - coef * V[o];
+  }
+}
+
+__global__ void masked_accumulate_kernel(float* __restrict__ dx, const float* __restrict__ dxm, size_t total, int D, int mask_type) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < total) dx[i] += dxm[i] * dense_mask_b(mask_type, static_cast<int>(i % D));
+}
+
+static inline unsigned nblk(size_t total) { return static_cast<unsigned>((total + 255) / 256); }
+
+struct DenseWs {
+  float *sc1, *sc2, *xm, *pre1, *pre2, *h1, *h2, *s_pre, *t_pre;
+};
+static DenseWs carve(float* ws, int N, int D, int U) {
+  DenseWs w;
+  size_t o = 0;
+  auto take = [&](size_t n) { float* p = ws + o; o += (n + 3) / 4 * 4; return p; };
+  w.sc1 = take(U); w.sc2 = take(U);
+  w.xm = take(static_cast<size_t>(N) * D);
+  w.pre1 = take(static_cast<size_t>(N) * U); w.pre2 = take(static_cast<size_t>(N) * U);
+  w.h1 = take(static_cast<size_t>(N) * U); w.h2 = take(static_cast<size_t>(N) * U);
+  w.s_pre = take(static_cast<size_t>(N) * D); w.t_pre = take(static_cast<size_t>(N) * D);
+  return w;
+}
+
+}  // namespace bruno
+
+using namespace bruno;
+
+extern "C" {
+
+size_t bruno_coupling_dense_ws_floats(int N, int D, int U) {
+  return 2 * (static_cast<size_t>(U) + 4) + 3 * (static_cast<size_t>(N) * D + 4) + 4 * (static_cast<size_t>(N) * U + 4);
+}
+size_t bruno_coupling_dense_bwd_ws_floats(int N, int D, int U) {
+  return 3 * (static_cast<size_t>(N) * D + 4) + 2 * (static_cast<size_t>(N) * U + 4) + 4 * (static_cast<size_t>(U) + 4);
+}
+
+int bruno_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                int ldc, const float* col_scale, const float* bias, int act, int accumulate, void* stream) {
+  BRUNO_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bruno_sgemm: bad arguments");
+  GemmEpi ep{col_scale, bias, nullptr, act, accumulate, nullptr};
+  return gemm(transA != 0, transB != 0, M, N, K, A, lda, B, ldb, C, ldc, ep, static_cast<cudaStream_t>(stream));
+}
+
+int bruno_coupling_dense_fwd(const float* x, const float* ld_in, float* y, float* ld_out, int N, int D, int U, int mask_type,
+                             int inverse, const float* V1, const float* g1, const float* b1, const float* V2,
+                             const float* g2, const float* b2, const float* Ks, const float* bs, const float* Kt,
+                             const float* bt, float* ws, void* stream) {
+  BRUNO_REQUIRE(x && ld_in && y && ld_out && V1 && g1 && b1 && V2 && g2 && b2 && Ks && bs && Kt && bt && ws,
+                "bruno_coupling_dense_fwd: null pointer");
+  BRUNO_REQUIRE(N > 0 && D > 0 && U > 0 && (mask_type == BRUNO_MASK_EVEN || mask_type == BRUNO_MASK_ODD),
+                "bruno_coupling_dense_fwd: bad sizes / mask");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DenseWs w = carve(ws, N, D, U);
+  const size_t ND = static_cast<size_t>(N) * D;
+  dense_wn_scale_kernel<<<ceil_div(U, 128), 128, 0, st>>>(V1, g1, w.sc1, D, U);
+  dense_wn_scale_kernel<<<ceil_div(U, 128), 128, 0, st>>>(V2, g2, w.sc2, U, U);
+  dense_mask_mul_kernel<<<nblk(ND), 256, 0, st>>>(x, w.xm, ND, D, mask_type);
+  int rc;
+  if ((rc = gemm(false, false, N, U, D, w.xm, D, V1, U, w.h1, U, GemmEpi{w.sc1, b1, w.pre1, 1, 0, nullptr}, st))) return rc;
+  if ((rc = gemm(false, false, N, U, U, w.h1, U, V2, U, w.h2, U, GemmEpi{w.sc2, b2, w.pre2, 1, 0, nullptr}, st))) return rc;
+  if ((rc = gemm(false, false, N, D, U, w.h2, U, Ks, D, w.s_pre, D, GemmEpi{nullptr, bs, nullptr, 0, 0, nullptr}, st))) return rc;
+  if ((rc = gemm(false, false, N, D, U, w.h2, U, Kt, D, w.t_pre, D, GemmEpi{nullptr, bt, nullptr, 0, 0, nullptr}, st))) return rc;
+  dense_coupling_kernel<<<N, 256, 0, st>>>(x, w.s_pre, w.t_pre, ld_in, y, ld_out, D, mask_type, inverse);
+  return check_launch("dense_coupling_kernel");
+}
+
+int bruno_coupling_dense_bwd(const float* x, const float* dy, const float* dld, int N, int D, int U, int mask_type,
+                             const float* V1, const float* g1, const float* b1, const float* V2, const float* g2,
+                             const float* b2, const float* Ks, const float* Kt, const float* ws_fwd, float* ws_bwd,
+                             float* dx, float* dV1, float* dg1, float* db1, float* dV2, float* dg2, float* db2, float* dKs,
+                             float* dbs, float* dKt, float* dbt, void* stream) {
+  BRUNO_REQUIRE(x && dy && dld && V1 && g1 && b1 && V2 && g2 && b2 && Ks && Kt && ws_fwd && ws_bwd && dx && dV1 && dg1 &&
+                    db1 && dV2 && dg2 && db2 && dKs && dbs && dKt && dbt, "bruno_coupling_dense_bwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DenseWs w = carve(const_cast<float*>(ws_fwd), N, D, U);
+  const size_t ND = static_cast<size_t>(N) * D, NU = static_cast<size_t>(N) * U;
+  size_t o = 0;
+  auto take = [&](size_t n) { float* p = ws_bwd + o; o += (n + 3) / 4 * 4; return p; };
+  float* ds_pre = take(ND);
+  float* dt_pre = take(ND);
+  float* dxm = take(ND);
+  float* dh = take(NU);
+  float* dpre = take(NU);
+  float* r1 = take(U);
+  int rc;
+  const GemmEpi plain{nullptr, nullptr, nullptr, 0, 0, nullptr};
+  const GemmEpi accum{nullptr, nullptr, nullptr, 0, 1, nullptr};
+  dense_coupling_bwd_kernel<<<nblk(ND), 256, 0, st>>>(x, w.s_pre, dy, dld, dx, ds_pre, dt_pre, ND, D, mask_type);
+  // heads
+  if ((rc = gemm(true, false, U, D, N, w.h2, U, ds_pre, D, dKs, D, plain, st))) return rc;
+  if ((rc = gemm(true, false, U, D, N, w.h2, U, dt_pre, D, dKt, D, plain, st))) return rc;
+  col_reduce_kernel<<<ceil_div(D, 128), 128, 0, st>>>(ds_pre, nullptr, dbs, nullptr, N, D);
+  col_reduce_kernel<<<ceil_div(D, 128), 128, 0, st>>>(dt_pre, nullptr, dbt, nullptr, N, D);
+  if ((rc = gemm(false, true, N, U, D, ds_pre, D, Ks, D, dh, U, plain, st))) return rc;
+  if ((rc = gemm(false, true, N, U, D, dt_pre, D, Kt, D, dh, U, accum, st))) return rc;
+  // d2
+  elu_bwd_kernel<<<nblk(NU), 256, 0, st>>>(w.pre2, dh, dpre, NU);
+  col_reduce_kernel<<<ceil_div(U, 128), 128, 0, st>>>(dpre, w.pre2, db2, r1, N, U);
+  if ((rc = gemm(true, false, U, U, N, w.h1, U, dpre, U, dV2, U, plain, st))) return rc;
+  dense_wn_bwd_kernel<<<ceil_div(U, 128), 128, 0, st>>>(V2, g2, b2, r1, db2, dV2, dg2, U, U);
+  {
+    GemmEpi e = plain;
+    e.a_kscale = w.sc2;
+    if ((rc = gemm(false, true, N, U, U, dpre, U, V2, U, dh, U, e, st))) return rc;
+  }
+  // d1
+  elu_bwd_kernel<<<nblk(NU), 256, 0, st>>>(w.pre1, dh, dpre, NU);
+  col_reduce_kernel<<<ceil_div(U, 128), 128, 0, st>>>(dpre, w.pre1, db1, r1, N, U);
+  if ((rc = gemm(true, false, D, U, N, w.xm, D, dpre, U, dV1, U, plain, st))) return rc;
+  dense_wn_bwd_kernel<<<ceil_div(U, 128), 128, 0, st>>>(V1, g1, b1, r1, db1, dV1, dg1, D, U);
+  {
+    GemmEpi e = plain;
+    e.a_kscale = w.sc1;
+    if ((rc = gemm(false, true, N, D, U, dpre, U, V1, U, dxm, D, e, st))) return rc;
+  }
+  masked_accumulate_kernel<<<nblk(ND), 256, 0, st>>>(dx, dxm, ND, D, mask_type);
+  return check_launch("bruno_coupling_dense_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,504 @@
+// Memory-bound pieces of the Real NVP stack around the tensor-core convolutions (nn_extra_nvp.py):
+//   pre-processing (ScaleLayer :41-55, LogitLayer :22-38), squeeze (:277-298), factor-out slices (:301-346),
+//   the 1x1 input conv c1 of the s/t ResNet (:115) with the mask multiply fused in, and the two 1x1 output heads
+//   (:129-139) fused with tanh, mask, the affine coupling (:162-187) and the per-image log-det reduction.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "slab.cuh"
+
+namespace bruno {
+
+// ------------------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
+  // deterministic: fixed shuffle tree + fixed-order sum of the warp totals.  blockDim.x == 256.
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w];
+  return s;
+}
+
+__device__ __forceinline__ float mask_b(int mask_type, int y, int x, int c, int C) {
+  // nn_extra_nvp.py:143-160.  b = 1: pass-through / conditioning half.
+  switch (mask_type) {
+    case BRUNO_MASK_CHECKERBOARD0: return static_cast<float>((y + x) & 1);
+    case BRUNO_MASK_CHECKERBOARD1: return static_cast<float>(1 - ((y + x) & 1));
+    case BRUNO_MASK_CHANNEL0: return c < C / 2 ? 1.f : 0.f;
+    default: return c >= C / 2 ? 1.f : 0.f;
+  }
+}
+
+__device__ __forceinline__ void unpack8f(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack2f(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+__device__ __forceinline__ float elu_grad_from_out(float o) { return o > 0.f ? 1.f : o + 1.f; }
+
+// ------------------------------------------------------------------------------------------------------------
+// pre-processing: one block per image, per-image log-det reduced in a fixed order
+// ------------------------------------------------------------------------------------------------------------
+enum PreOp { PRE_SCALE_FWD = 0, PRE_LOGIT_FWD = 1, PRE_LOGIT_INV = 2, PRE_SCALE_INV = 3, PRE_FUSED_FWD = 4, PRE_FUSED_INV = 5 };
+
+__global__ void __launch_bounds__(256)
+pre_kernel(int op, const float* __restrict__ x, const float* __restrict__ ld_in, float* __restrict__ y,
+           float* __restrict__ ld_out, int D, float scale, float alpha, int conditional_variant) {
+  __shared__ float red[8];
+  const int n = blockIdx.x;
+  const float* xi = x + static_cast<size_t>(n) * D;
+  float* yi = y + static_cast<size_t>(n) * D;
+  const float l1a = conditional_variant ? 0.f : log1pf(-alpha);  // nn_extra_nvp_conditional.py:13 omits ln(1-alpha)
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < D; i += 256) {
+    float v = xi[i];
+    if (op == PRE_SCALE_FWD || op == PRE_FUSED_FWD) v = v / scale;                          // nvp:47
+    if (op == PRE_LOGIT_FWD || op == PRE_FUSED_FWD) {                                       // nvp:27-30
+      const float t = v * (1.f - alpha) + alpha * 0.5f;
+      const float la = logf(t), lb = logf(1.f - t);
+      acc += -la - lb + l1a;
+      v = la - lb;
+    }
+    if (op == PRE_LOGIT_INV || op == PRE_FUSED_INV) {                                       // nvp:34-37
+      const float yv = v;
+      const float sg = 1.f / (1.f + expf(-yv));
+      v = (sg - 0.5f * alpha) / (1.f - alpha);
+      const float sp = yv > 15.f ? yv + log1pf(expf(-yv)) : log1pf(expf(yv));
+      acc += yv - 2.f * sp - l1a;
+    }
+    if (op == PRE_SCALE_INV || op == PRE_FUSED_INV) v = v * scale;                          // nvp:53
+    yi[i] = v;
+  }
+  const float tot = block_sum_256(acc, red);
+  if (threadIdx.x == 0) {
+    float l = ld_in ? ld_in[n] : 0.f;
+    const float lsc = logf(scale) * static_cast<float>(D);
+    if (op == PRE_SCALE_FWD || op == PRE_FUSED_FWD) l -= lsc;                               // nvp:48
+    l += tot;
+    if (op == PRE_SCALE_INV || op == PRE_FUSED_INV) l += lsc;                               // nvp:54
+    ld_out[n] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// squeeze / channel slices (pure index remaps on the small C-channel tensors)
+// ------------------------------------------------------------------------------------------------------------
+// tf.space_to_depth(x, 2): out[n,h,w,(dy*2+dx)*C + c] = in[n,2h+dy,2w+dx,c]      (nvp:284)
+__global__ void space_to_depth_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C,
+                                      int inverse) {
+  const size_t total = static_cast<size_t>(N) * H * W * C;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // i indexes the LARGE-resolution tensor [N,H,W,C]
+  const int c = static_cast<int>(i % C);
+  const int x = static_cast<int>((i / C) % W);
+  const int y = static_cast<int>((i / (static_cast<size_t>(C) * W)) % H);
+  const int n = static_cast<int>(i / (static_cast<size_t>(C) * W * H));
+  const size_t j = ((static_cast<size_t>(n) * (H / 2) + y / 2) * (W / 2) + x / 2) * (4 * C) + ((y & 1) * 2 + (x & 1)) * C + c;
+  if (inverse) out[i] = in[j];
+  else out[j] = in[i];
+}
+
+// dst[r, dst_off + c] = src[r, src_off + c] for c < nch
+__global__ void channel_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t rows, int src_C,
+                                    int src_off, int dst_C, int dst_off, int nch) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * nch) return;
+  const size_t r = i / nch;
+  const int c = static_cast<int>(i % nch);
+  dst[r * dst_C + dst_off + c] = src[r * src_C + src_off + c];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// c1: 1x1 weight-normalised conv C -> 64 on the masked input + ELU, written as a swizzled bf16 slab.  nvp:113-115
+// ------------------------------------------------------------------------------------------------------------
+constexpr int MAXC = 16;
+
+__device__ __forceinline__ void c1_weights_to_smem(const float* __restrict__ V1, const float* __restrict__ g1, int C,
+                                                   float* w_s /*[C][64]*/) {
+  // W1[c][co] = g1[co] * V1[c][co] / sqrt(max(sum_c V1^2, 1e-12))
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    float n2 = 0.f;
+    for (int c = 0; c < C; ++c) n2 = fmaf(V1[c * 64 + i], V1[c * 64 + i], n2);
+    const float sc = g1[i] * rsqrtf(fmaxf(n2, 1e-12f));
+    for (int c = 0; c < C; ++c) w_s[c * 64 + i] = V1[c * 64 + i] * sc;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const float* __restrict__ g1,
+              const float* __restrict__ b1, uint8_t* __restrict__ out, SlabGeom g, int C, int mask_type) {
+  __shared__ float w_s[MAXC * 64];
+  __shared__ float b_s[64];
+  if (threadIdx.x < 64) b_s[threadIdx.x] = b1[threadIdx.x];
+  c1_weights_to_smem(V1, g1, C, w_s);
+  const int total = g.NT * TILE_M * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int data_row = i >> 3, j = i & 7;
+    const size_t R = static_cast<size_t>(g.HALO) + data_row;
+    uint4 packed = make_uint4(0, 0, 0, 0);
+    if (slab_row_is_pixel(data_row, g)) {
+      const int n = data_row / g.IMG, q = data_row % g.IMG;
+      const int yy = q / g.P - 1, xx = q % g.P - 1;
+      const float* xp = x + ((static_cast<size_t>(n) * g.H + yy) * g.W + xx) * C;
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = b_s[j * 8 + e];
+      for (int c = 0; c < C; ++c) {
+        const float xm = xp[c] * mask_b(mask_type, yy, xx, c, C);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(xm, w_s[c * 64 + j * 8 + e], acc[e]);
+      }
+      packed = make_uint4(pack2f(elu_f(acc[0]), elu_f(acc[1])), pack2f(elu_f(acc[2]), elu_f(acc[3])),
+                          pack2f(elu_f(acc[4]), elu_f(acc[5])), pack2f(elu_f(acc[6]), elu_f(acc[7])));
+    }
+    *reinterpret_cast<uint4*>(out + slab_chunk_off(R, j)) = packed;
+  }
+}
+
+// c1 backward: one block per image.  g1 slab = dL/d(pre-activation of c1).
+//   dx[n,y,x,c] += b * sum_co g1[co] W1[c][co];  dW1[c][co] += sum_p xm[p][c] g1[p][co];  db1[co] += sum_p g1[p][co]
+__global__ void __launch_bounds__(256)
+c1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const float* __restrict__ g1w,
+              const uint8_t* __restrict__ gslab, float* __restrict__ dx, float* __restrict__ dW1, float* __restrict__ db1,
+              SlabGeom g, int C, int mask_type) {
+  extern __shared__ float sm[];
+  float* w_s = sm;                       // [C][64]
+  float* g_s = w_s + MAXC * 64;          // [256][65]
+  float* x_s = g_s + 256 * 65;           // [256][MAXC+1]
+  c1_weights_to_smem(V1, g1w, C, w_s);
+  const int n = blockIdx.x;
+  const int HW = g.H * g.W;
+  const int nout = (C + 1) * 64;
+  float acc[(MAXC + 1) * 64 / 256 + 1];
+#pragma unroll
+  for (int i = 0; i < (MAXC + 1) * 64 / 256 + 1; ++i) acc[i] = 0.f;
+  for (int p0 = 0; p0 < HW; p0 += 256) {
+    const int p = p0 + threadIdx.x;
+    const bool ok = p < HW;
+    float gv[64];
+    if (ok) {
+      const int yy = p / g.W, xx = p % g.W;
+      const size_t R = static_cast<size_t>(g.HALO) + static_cast<size_t>(n) * g.IMG + (yy + 1) * g.P + (xx + 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 u = *reinterpret_cast<const uint4*>(gslab + slab_chunk_off(R, j));
+        unpack8f(u, gv + j * 8);
+      }
+      const size_t xo = (static_cast<size_t>(n) * HW + p) * C;
+      for (int c = 0; c < C; ++c) {
+        const float b = mask_b(mask_type, yy, xx, c, C);
+        float d = 0.f;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) d = fmaf(gv[k], w_s[c * 64 + k], d);
+        dx[xo + c] += b * d;
+        x_s[threadIdx.x * (MAXC + 1) + c] = x[xo + c] * b;
+      }
+      x_s[threadIdx.x * (MAXC + 1) + C] = 1.f;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 64; ++k) gv[k] = 0.f;
+      for (int c = 0; c <= C; ++c) x_s[threadIdx.x * (MAXC + 1) + c] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 64; ++k) g_s[threadIdx.x * 65 + k] = gv[k];
+    __syncthreads();
+    int ai = 0;
+    for (int o = threadIdx.x; o < nout; o += 256, ++ai) {
+      const int co = o & 63, c = o >> 6;
+      float a = 0.f;
+      for (int pp = 0; pp < 256; ++pp) a = fmaf(x_s[pp * (MAXC + 1) + c], g_s[pp * 65 + co], a);
+      acc[ai] += a;
+    }
+    __syncthreads();
+  }
+  int ai = 0;
+  for (int o = threadIdx.x; o < nout; o += 256, ++ai) {
+    const int co = o & 63, c = o >> 6;
+    if (c < C) atomicAdd(dW1 + c * 64 + co, acc[ai]);
+    else atomicAdd(db1 + co, acc[ai]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// heads + coupling.  One block per image.
+//   s = tanh(h . Ks + bs) (1-b),  t = (h . Kt + bt) (1-b)                                       nvp:129-139
+//   forward : y = x b + (1-b)(x e^s + t),        ld += sum s                                      nvp:168-172
+//   inverse : x = y b + (y (1-b) - t) e^{-s},    ld -= sum s                                      nvp:181-186
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+heads_coupling_kernel(const float* __restrict__ xin, const uint8_t* __restrict__ hslab, const float* __restrict__ Ks,
+                      const float* __restrict__ bs, const float* __restrict__ Kt, const float* __restrict__ bt,
+                      const float* __restrict__ ld_in, float* __restrict__ yout, float* __restrict__ ld_out, SlabGeom g,
+                      int C, int mask_type, int inverse) {
+  __shared__ float ks_s[64 * MAXC], kt_s[64 * MAXC], bs_s[MAXC], bt_s[MAXC], red[8];
+  for (int i = threadIdx.x; i < 64 * C; i += 256) {
+    ks_s[i] = Ks[i];
+    kt_s[i] = Kt[i];
+  }
+  if (threadIdx.x < C) {
+    bs_s[threadIdx.x] = bs[threadIdx.x];
+    bt_s[threadIdx.x] = bt[threadIdx.x];
+  }
+  __syncthreads();
+  const int n = blockIdx.x;
+  const int HW = g.H * g.W;
+  float ssum = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    const int yy = p / g.W, xx = p % g.W;
+    const size_t R = static_cast<size_t>(g.HALO) + static_cast<size_t>(n) * g.IMG + (yy + 1) * g.P + (xx + 1);
+    float h[64];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 u = *reinterpret_cast<const uint4*>(hslab + slab_chunk_off(R, j));
+      unpack8f(u, h + j * 8);
+    }
+    const size_t xo = (static_cast<size_t>(n) * HW + p) * C;
+    for (int c = 0; c < C; ++c) {
+      const float b = mask_b(mask_type, yy, xx, c, C);
+      const float xv = xin[xo + c];
+      float out = xv;
+      if (b == 0.f) {
+        float sp = bs_s[c], tp = bt_s[c];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+          sp = fmaf(h[k], ks_s[k * C + c], sp);
+          tp = fmaf(h[k], kt_s[k * C + c], tp);
+        }
+        const float s = tanhf(sp);
+        ssum += s;
+        out = inverse ? (xv - tp) * expf(-s) : fmaf(xv, expf(s), tp);
+      }
+      yout[xo + c] = out;
+    }
+  }
+  const float tot = block_sum_256(ssum, red);
+  if (threadIdx.x == 0) ld_out[n] = ld_in[n] + (inverse ? -tot : tot);
+}
+
+// Backward of the forward coupling.  Given dy, dld:
+//   dx (direct part) = dy (b + (1-b) e^s);  dt = dy (1-b);  ds = dy (1-b) x e^s + dld[n]
+//   d(s_pre) = ds (1 - tanh^2),  d(t_pre) = dt
+//   dh = Ks d(s_pre) + Kt d(t_pre);   gslab = dh * ELU'(h)   (h = output of the last residual block)
+//   dKs[k][c] += h[k] d(s_pre)[c] ...  (accumulated per block, then atomics)
+__global__ void __launch_bounds__(256)
+heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restrict__ hslab, const float* __restrict__ Ks,
+                          const float* __restrict__ bs, const float* __restrict__ Kt, const float* __restrict__ bt,
+                          const float* __restrict__ dy, const float* __restrict__ dld, float* __restrict__ dx,
+                          uint8_t* __restrict__ gslab, float* __restrict__ dKs, float* __restrict__ dbs,
+                          float* __restrict__ dKt, float* __restrict__ dbt, SlabGeom g, int C, int mask_type) {
+  extern __shared__ float sm[];
+  float* ks_s = sm;                        // [64][C]
+  float* kt_s = ks_s + 64 * MAXC;
+  float* bs_s = kt_s + 64 * MAXC;
+  float* bt_s = bs_s + MAXC;
+  float* h_s = bt_s + MAXC;                // [256][65]  (column 64 = 1 -> bias gradient)
+  float* d_s = h_s + 256 * 65;             // [256][2*MAXC]
+  for (int i = threadIdx.x; i < 64 * C; i += 256) {
+    ks_s[i] = Ks[i];
+    kt_s[i] = Kt[i];
+  }
+  if (threadIdx.x < C) {
+    bs_s[threadIdx.x] = bs[threadIdx.x];
+    bt_s[threadIdx.x] = bt[threadIdx.x];
+  }
+  __syncthreads();
+  const int n = blockIdx.x;
+  const int HW = g.H * g.W;
+  const float dl = dld[n];
+  const int nout = 65 * 2 * C;
+  constexpr int NACC = 65 * 2 * MAXC / 256 + 1;
+  float acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+
+  for (int p0 = 0; p0 < HW; p0 += 256) {
+    const int p = p0 + threadIdx.x;
+    const bool ok = p < HW;
+    float h[64];
+    float* dpre = d_s + threadIdx.x * 2 * MAXC;
+    if (ok) {
+      const int yy = p / g.W, xx = p % g.W;
+      const size_t R = static_cast<size_t>(g.HALO) + static_cast<size_t>(n) * g.IMG + (yy + 1) * g.P + (xx + 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 u = *reinterpret_cast<const uint4*>(hslab + slab_chunk_off(R, j));
+        unpack8f(u, h + j * 8);
+      }
+      const size_t xo = (static_cast<size_t>(n) * HW + p) * C;
+      for (int c = 0; c < C; ++c) {
+        const float b = mask_b(mask_type, yy, xx, c, C);
+        const float g_y = dy[xo + c];
+        float dsp = 0.f, dtp = 0.f, dxv = g_y;
+        if (b == 0.f) {
+          float sp = bs_s[c];
+#pragma unroll
+          for (int k = 0; k < 64; ++k) sp = fmaf(h[k], ks_s[k * C + c], sp);
+          const float s = tanhf(sp);
+          const float es = expf(s);
+          dxv = g_y * es;
+          dtp = g_y;
+          dsp = (g_y * xin[xo + c] * es + dl) * (1.f - s * s);
+        }
+        dx[xo + c] = dxv;
+        dpre[c] = dsp;
+        dpre[C + c] = dtp;
+      }
+      // dh and the gradient w.r.t. the pre-activation of the last residual block
+      uint32_t packed[32];
+#pragma unroll
+      for (int k = 0; k < 64; k += 2) {
+        float d0 = 0.f, d1 = 0.f;
+        for (int c = 0; c < C; ++c) {
+          d0 = fmaf(dpre[c], ks_s[k * C + c], fmaf(dpre[C + c], kt_s[k * C + c], d0));
+          d1 = fmaf(dpre[c], ks_s[(k + 1) * C + c], fmaf(dpre[C + c], kt_s[(k + 1) * C + c], d1));
+        }
+        packed[k >> 1] = pack2f(d0 * elu_grad_from_out(h[k]), d1 * elu_grad_from_out(h[k + 1]));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(gslab + slab_chunk_off(R, j)) =
+            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 64; ++k) h[k] = 0.f;
+      for (int c = 0; c < 2 * C; ++c) dpre[c] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 64; ++k) h_s[threadIdx.x * 65 + k] = h[k];
+    h_s[threadIdx.x * 65 + 64] = ok ? 1.f : 0.f;
+    __syncthreads();
+    int ai = 0;
+    for (int o = threadIdx.x; o < nout; o += 256, ++ai) {
+      const int k = o % 65, c2 = o / 65;
+      float a = 0.f;
+      for (int pp = 0; pp < 256; ++pp) a = fmaf(h_s[pp * 65 + k], d_s[pp * 2 * MAXC + c2], a);
+      acc[ai] += a;
+    }
+    __syncthreads();
+  }
+  int ai = 0;
+  for (int o = threadIdx.x; o < nout; o += 256, ++ai) {
+    const int k = o % 65, c2 = o / 65;
+    const bool is_t = c2 >= C;
+    const int c = is_t ? c2 - C : c2;
+    float* dst = k < 64 ? (is_t ? dKt : dKs) + k * C + c : (is_t ? dbt : dbs) + c;
+    atomicAdd(dst, acc[ai]);
+  }
+}
+
+// zero the rows of a slab that heads_coupling_bwd does not write (padding positions), so the slab invariant holds
+__global__ void slab_zero_padding_kernel(uint8_t* __restrict__ slab, SlabGeom g) {
+  const int total = g.NT * TILE_M * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int data_row = i >> 3, j = i & 7;
+    if (!slab_row_is_pixel(data_row, g))
+      *reinterpret_cast<uint4*>(slab + slab_chunk_off(static_cast<size_t>(g.HALO) + data_row, j)) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+}  // namespace bruno
+
+using namespace bruno;
+
+extern "C" {
+
+int bruno_pre(int op, const float* x, const float* ld_in, float* y, float* ld_out, int N, int D, float scale, float alpha,
+              int conditional_variant, void* stream) {
+  BRUNO_REQUIRE(op >= 0 && op <= 5 && x && y && ld_out && N > 0 && D > 0, "bruno_pre: bad arguments");
+  pre_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(op, x, ld_in, y, ld_out, D, scale, alpha, conditional_variant);
+  return check_launch("pre_kernel");
+}
+
+int bruno_space_to_depth(const float* in, float* out, int N, int H, int W, int C, int inverse, void* stream) {
+  BRUNO_REQUIRE(in && out && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0,
+                "bruno_space_to_depth: bad arguments (H, W are the LARGE resolution and must be even)");
+  const size_t total = static_cast<size_t>(N) * H * W * C;
+  space_to_depth_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, out, N, H, W, C, inverse);
+  return check_launch("space_to_depth_kernel");
+}
+
+int bruno_channel_copy(const float* src, float* dst, long rows, int src_C, int src_off, int dst_C, int dst_off, int nch,
+                       void* stream) {
+  BRUNO_REQUIRE(src && dst && rows > 0 && nch > 0 && src_off + nch <= src_C && dst_off + nch <= dst_C,
+                "bruno_channel_copy: bad arguments");
+  const size_t total = static_cast<size_t>(rows) * nch;
+  channel_copy_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, dst, static_cast<size_t>(rows), src_C, src_off, dst_C, dst_off, nch);
+  return check_launch("channel_copy_kernel");
+}
+
+int bruno_c1_fwd(const float* x, const float* V1, const float* g1, const float* b1, void* out_slab, int N, int H, int W,
+                 int C, int mask_type, void* stream) {
+  BRUNO_REQUIRE(x && V1 && g1 && b1 && out_slab && C >= 1 && C <= MAXC, "bruno_c1_fwd: bad arguments (C <= %d)", MAXC);
+  const SlabGeom g = slab_geom(N, H, W);
+  const int total = g.NT * TILE_M * 8;
+  int blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  c1_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, V1, g1, b1, static_cast<uint8_t*>(out_slab), g, C,
+                                                                        mask_type);
+  return check_launch("c1_fwd_kernel");
+}
+
+int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g_slab, float* dx, float* dW1, float* db1,
+                 int N, int H, int W, int C, int mask_type, void* stream) {
+  BRUNO_REQUIRE(x && V1 && g1 && g_slab && dx && dW1 && db1 && C >= 1 && C <= MAXC, "bruno_c1_bwd: bad arguments");
+  const SlabGeom g = slab_geom(N, H, W);
+  const size_t smem = (MAXC * 64 + 256 * 65 + 256 * (MAXC + 1)) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(c1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = true;
+  }
+  c1_bwd_kernel<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, V1, g1, static_cast<const uint8_t*>(g_slab), dx, dW1,
+                                                                      db1, g, C, mask_type);
+  return check_launch("c1_bwd_kernel");
+}
+
+int bruno_heads_coupling(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
+                         const float* bt, const float* ld_in, float* y, float* ld_out, int N, int H, int W, int C,
+                         int mask_type, int inverse, void* stream) {
+  BRUNO_REQUIRE(x && h_slab && Ks && bs && Kt && bt && ld_in && y && ld_out && C >= 1 && C <= MAXC,
+                "bruno_heads_coupling: bad arguments");
+  const SlabGeom g = slab_geom(N, H, W);
+  heads_coupling_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<const uint8_t*>(h_slab), Ks, bs, Kt,
+                                                                           bt, ld_in, y, ld_out, g, C, mask_type, inverse);
+  return check_launch("heads_coupling_kernel");
+}
+
+int bruno_heads_coupling_bwd(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
+                             const float* bt, const float* dy, const float* dld, float* dx, void* g_slab, float* dKs,
+                             float* dbs, float* dKt, float* dbt, int N, int H, int W, int C, int mask_type, void* stream) {
+  BRUNO_REQUIRE(x && h_slab && Ks && bs && Kt && bt && dy && dld && dx && g_slab && dKs && dbs && dKt && dbt && C >= 1 &&
+                    C <= MAXC, "bruno_heads_coupling_bwd: bad arguments");
+  const SlabGeom g = slab_geom(N, H, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = (2 * 64 * MAXC + 2 * MAXC + 256 * 65 + 256 * 2 * MAXC) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(heads_coupling_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = true;
+  }
+  slab_zero_padding_kernel<<<148 * 4, 256, 0, st>>>(static_cast<uint8_t*>(g_slab), g);
+  heads_coupling_bwd_kernel<<<N, 256, smem, st>>>(x, static_cast<const uint8_t*>(h_slab), Ks, bs, Kt, bt, dy, dld, dx,
+                                                  static_cast<uint8_t*>(g_slab), dKs, dbs, dKt, dbt, g, C, mask_type);
+  return check_launch("heads_coupling_bwd_kernel");
+}
+
+}  // extern "C"

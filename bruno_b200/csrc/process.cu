@@ -618,7 +618,8 @@ __global__ void process_sample_kernel(int kind, const float* __restrict__ rvs, c
     const float u = bb * cosf(ang), v = bb * sinf(ang);
     const float w = u * u + v * v;
     const float nv = nu[d];
-    const float t = u * sqrtf(nv * (powf(w, -2.f / nv) - 1.f) / w);
+    // pow(w, -2/nu) - 1 evaluated as expm1(-2/nu * ln w): same value, without the fp32 cancellation
+    const float t = u * sqrtf(nv * expm1f(-2.f / nv * logf(w)) / w);
     out[i] = m + sqrtf(s * (nv - 2.f) / nv) * t;
   } else {
     out[i] = m + sqrtf(s) * rvs[i];

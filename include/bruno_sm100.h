@@ -87,6 +87,120 @@ int bruno_process_posterior(int kind, const float* z, const float* var_vbl, cons
 int bruno_process_sample(int kind, const float* rvs, const float* mu, const float* var, const float* nu,
                          float* out, int n, int B, int D, long stride_b, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Real NVP coupling stack (nn_extra_nvp.py).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* mask types: CouplingLayerConv.get_mask (nvp:143-160), CouplingLayerDense.get_mask (nvp:199-221); b = 1 marks the
+ * pass-through (conditioning) half. */
+#define BRUNO_MASK_CHECKERBOARD0 0
+#define BRUNO_MASK_CHECKERBOARD1 1
+#define BRUNO_MASK_CHANNEL0 2
+#define BRUNO_MASK_CHANNEL1 3
+#define BRUNO_MASK_EVEN 4
+#define BRUNO_MASK_ODD 5
+
+/* Pre-processing.  op: 0 ScaleLayer.forward_and_jacobian (nvp:45-49), 1 LogitLayer.forward_and_jacobian (:26-31),
+ * 2 LogitLayer.backward (:33-38), 3 ScaleLayer.backward (:51-55), 4 = 0 then 1 fused, 5 = 2 then 3 fused.
+ * x,y [N,D]; ld_in (NULL = zeros), ld_out [N].  conditional_variant != 0 drops the ln(1-alpha) term
+ * (nn_extra_nvp_conditional.py:13). */
+int bruno_pre(int op, const float* x, const float* ld_in, float* y, float* ld_out, int N, int D, float scale, float alpha,
+              int conditional_variant, void* stream);
+
+/* SqueezingLayer (nvp:277-298): tf.space_to_depth / depth_to_space with block 2.  H, W = the LARGE resolution;
+ * inverse = 0: in [N,H,W,C] -> out [N,H/2,W/2,4C]; inverse = 1: in [N,H/2,W/2,4C] -> out [N,H,W,C]. */
+int bruno_space_to_depth(const float* in, float* out, int N, int H, int W, int C, int inverse, void* stream);
+
+/* FactorOutLayer slices / concats (nvp:313-319, :336-344): dst[r, dst_off + c] = src[r, src_off + c], c < nch. */
+int bruno_channel_copy(const float* src, float* dst, long rows, int src_C, int src_off, int dst_C, int dst_off, int nch,
+                       void* stream);
+
+/* --- conv coupling layer, CouplingLayerConv (nvp:58-187) with function_s_t_wn (:108-141) -------------------------
+ * Hidden activations (64 channels) live in bf16 "slabs" (layout: bruno_b200/csrc/slab.cuh); bruno_slab_bytes gives
+ * the size of one, which the caller allocates ZERO-INITIALISED once (kernels keep the padding rows zero). */
+size_t bruno_slab_bytes(int N, int H, int W);
+size_t bruno_conv_wpack_bytes(void);
+
+/* conv2d_wn weight normalisation (nvp:389) of L stacked 3x3 64->64 kernels V [L,3,3,64,64] (HWIO), g [L,64] into the
+ * packed bf16 tensor-core operands: wfwd [L] (forward) and wbwd [L] (dgrad: transposed + flipped; may be NULL). */
+int bruno_conv_wn_pack(const float* V, const float* g, void* wfwd, void* wbwd, int L, void* stream);
+/* backward of the normalisation: dW [L,K,64] -> dV [L,K,64], dg [L,64]  (K = kh*kw*cin rows per output channel) */
+int bruno_conv_wn_bwd(const float* V, const float* g, const float* dW, float* dV, float* dg, int L, int K, void* stream);
+
+/* One 3x3, 64->64, stride-1 SAME convolution (tf.nn.conv2d at nvp:392) as a tcgen05 implicit GEMM, fused epilogue:
+ *   mode 0: out = ELU(conv + bias)                      c2 of a residual block (nvp:120)
+ *   mode 1: out = ELU(conv + bias + aux1)               c3 + skip (nvp:121-124)
+ *   mode 2: out = conv * ELU'(aux1)                     dgrad through c3, aux1 = saved output of c2
+ *   mode 3: out = (conv + aux2) * ELU'(aux1)            dgrad through c2 + skip gradient, aux1 = saved block input
+ *   mode 4: out = conv + bias                           (data-dependent init, nvp:394-398)
+ * ELU' is evaluated from the saved OUTPUT o of the ELU: 1 if o > 0 else o + 1. */
+int bruno_conv3x3(int mode, const void* in_slab, const void* wpack, const float* bias, const void* aux1, const void* aux2,
+                  void* out_slab, int N, int H, int W, void* stream);
+/* dW [3,3,64,64] (HWIO) += sum_pos x[pos + tap] (x) g[pos];  db [64] += sum_pos g[pos]   (fp32, atomically added) */
+int bruno_conv3x3_wgrad(const void* x_slab, const void* g_slab, float* dW, float* db, int N, int H, int W, void* stream);
+
+/* c1 (nvp:113-115): out_slab = ELU(conv1x1_wn(x * mask)), x [N,H,W,C] fp32, V1 [C,64], g1, b1 [64]. */
+int bruno_c1_fwd(const float* x, const float* V1, const float* g1, const float* b1, void* out_slab, int N, int H, int W,
+                 int C, int mask_type, void* stream);
+/* g_slab = dL/d(pre-activation of c1): dx += mask * (g W1^T); dW1 [C,64] += (x mask)^T g; db1 [64] += sum g. */
+int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g_slab, float* dx, float* dW1, float* db1,
+                 int N, int H, int W, int C, int mask_type, void* stream);
+
+/* conv_out_scale / conv_out_translation heads (nvp:129-139) + affine coupling + log-det (forward :162-174, inverse
+ * :176-187).  Ks, Kt [64,C]; bs, bt [C]; x, y [N,H,W,C]; ld [N]. */
+int bruno_heads_coupling(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
+                         const float* bt, const float* ld_in, float* y, float* ld_out, int N, int H, int W, int C,
+                         int mask_type, int inverse, void* stream);
+/* backward of the forward coupling: dx = direct part (the s/t-network part is added by bruno_c1_bwd), g_slab =
+ * dL/d(pre-activation of the last residual block); dKs, dbs, dKt, dbt are ACCUMULATED (zero them first). */
+int bruno_heads_coupling_bwd(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
+                             const float* bt, const float* dy, const float* dld, float* dx, void* g_slab, float* dKs,
+                             float* dbs, float* dKt, float* dbt, int N, int H, int W, int C, int mask_type, void* stream);
+
+/* The whole CouplingLayerConv in one call.  forward_and_jacobian (nvp:162-174) / backward (:176-187, inverse = 1).
+ * Stacked parameters: V1 [C,64], g1, b1 [64] (c1); packed residual weights wfwd [2R] (order c2_0, c3_0, c2_1, ...,
+ * from bruno_conv_wn_pack), br [2R,64]; Ks, Kt [64,C], bs, bt [C].  `slabs`: n_slabs zero-initialised slabs of
+ * bruno_slab_bytes each; n_slabs >= 2R+1 keeps every activation for the backward (slab 0 = c1 output, 2r+1 = c2_r
+ * output, 2r+2 = block-r output), n_slabs = 3 ping-pongs (inference). */
+size_t bruno_coupling_conv_slabs(int R, int save);
+int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float* ld_out, int N, int H, int W, int C, int R,
+                            int mask_type, int inverse, const float* V1, const float* g1, const float* b1,
+                            const void* wfwd, const float* br, const float* Ks, const float* bs, const float* Kt,
+                            const float* bt, void* slabs, int n_slabs, void* stream);
+/* Hand-written backward of the forward coupling: dx [N,H,W,C] and the gradients of every variable of the layer
+ * (weight-norm backward included: dVr, dgr are w.r.t. V and g).  saved_slabs = the 2R+1 slabs of the forward;
+ * gslabs = 3 zero-initialised scratch slabs; wbwd = dgrad operands from bruno_conv_wn_pack. */
+int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, int N, int H, int W, int C, int R,
+                            int mask_type, const float* V1, const float* g1, const float* Vr, const float* gr,
+                            const void* wbwd, const float* Ks, const float* bs, const float* Kt, const float* bt,
+                            const void* saved_slabs, void* gslabs, float* dx, float* dV1, float* dg1, float* db1, float* dVr,
+                            float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt, void* stream);
+
+/* --- dense coupling layer, CouplingLayerDense (nvp:190-274) with dense_wn (:408-432), fp32 ---------------------- */
+size_t bruno_coupling_dense_ws_floats(int N, int D, int U);
+size_t bruno_coupling_dense_bwd_ws_floats(int N, int D, int U);
+/* x, y [N,D]; V1 [D,U], V2 [U,U], Ks, Kt [U,D]; `ws` keeps what the backward needs.  inverse = 1: CouplingLayer.backward. */
+int bruno_coupling_dense_fwd(const float* x, const float* ld_in, float* y, float* ld_out, int N, int D, int U, int mask_type,
+                             int inverse, const float* V1, const float* g1, const float* b1, const float* V2,
+                             const float* g2, const float* b2, const float* Ks, const float* bs, const float* Kt,
+                             const float* bt, float* ws, void* stream);
+int bruno_coupling_dense_bwd(const float* x, const float* dy, const float* dld, int N, int D, int U, int mask_type,
+                             const float* V1, const float* g1, const float* b1, const float* V2, const float* g2,
+                             const float* b2, const float* Ks, const float* Kt, const float* ws_fwd, float* ws_bwd,
+                             float* dx, float* dV1, float* dg1, float* db1, float* dV2, float* dg2, float* db2, float* dKs,
+                             float* dbs, float* dKt, float* dbt, void* stream);
+/* C[M,N] (+)= act(op(A) op(B) * col_scale + bias), row-major fp32 (tf.matmul at nvp:418, tf.layers.dense :262,:268) */
+int bruno_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                int ldc, const float* col_scale, const float* bias, int act, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimiser steps with TF-1.7 semantics (config_rnn/train.py:121-131) over a flat fp32 buffer; grad_scale folds the
+ * 1/nr_gpu tower average (train.py:103-105) and the student-grad schedule (train.py:108-111).
+ * ---------------------------------------------------------------------------------------------------------- */
+int bruno_rmsprop_tf17(float* p, const float* g, float* ms, size_t n, float lr, float decay, float eps, float grad_scale,
+                       void* stream);
+int bruno_adam_tf17(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                    int t, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,111 @@
+"""GPU: the tcgen05 implicit-GEMM convolution kernels (forward / dgrad epilogues, wgrad, weight-norm pack) against
+a float64 restatement of conv2d_wn (nn_extra_nvp.py:378-404) on bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float64)
+
+
+def conv_ref(x, w_hwio):
+    y = F.conv2d(x.permute(0, 3, 1, 2), w_hwio.permute(3, 2, 0, 1), padding=1)
+    return y.permute(0, 2, 3, 1)
+
+
+def wn(V, g):
+    nrm = torch.sqrt(torch.clamp((V * V).sum(dim=(0, 1, 2), keepdim=True), min=1e-12))
+    return g.view(1, 1, 1, -1) * V / nrm
+
+
+def elu_grad_from_out(o):
+    return torch.where(o > 0, torch.ones_like(o), o + 1)
+
+
+def _setup(N, H, W, seed):
+    from bruno_b200 import _lib, slab
+    g = torch.Generator().manual_seed(seed)
+    V = torch.randn(2, 3, 3, 64, 64, generator=g, dtype=torch.float64) * 0.05
+    gain = 0.5 + torch.rand(2, 64, generator=g, dtype=torch.float64) * 3
+    bias = torch.randn(64, generator=g, dtype=torch.float64) * 0.2
+    x = torch.randn(N, H, W, 64, generator=g, dtype=torch.float64)
+    a1 = torch.randn(N, H, W, 64, generator=g, dtype=torch.float64)
+    a2 = torch.randn(N, H, W, 64, generator=g, dtype=torch.float64)
+    wb = _lib.query('bruno_conv_wpack_bytes')
+    wf = torch.empty(2, wb, dtype=torch.uint8, device='cuda')
+    wbw = torch.empty(2, wb, dtype=torch.uint8, device='cuda')
+    _lib.call('bruno_conv_wn_pack', V.float().cuda().contiguous(), gain.float().cuda().contiguous(), wf, wbw, 2)
+    return V, gain, bias, x, a1, a2, wf, wbw
+
+
+@pytest.mark.parametrize('N,H,W', [(3, 28, 28), (5, 14, 14), (2, 32, 32), (1, 16, 16), (40, 14, 14)])
+def test_conv3x3_all_epilogues(N, H, W):
+    from bruno_b200 import _lib, slab
+    V, gain, bias, x, a1, a2, wf, wbw = _setup(N, H, W, seed=N * H)
+    Wt = bf(wn(V[0].float().double(), gain[0].float().double()))   # the kernel rounds the normalised weights to bf16
+    xs, a1s, a2s = [slab.nhwc_to_slab(t.float().cuda()) for t in (x, a1, a2)]
+    xq, a1q, a2q = bf(x), bf(a1), bf(a2)
+    out = slab.alloc_slabs(1, N, H, W, 'cuda')[0]
+    b32 = bias.float().cuda()
+    conv = conv_ref(xq, Wt)
+    # dgrad operand: correlation with the flipped, transposed kernel
+    Wd = Wt.flip(0, 1).permute(0, 1, 3, 2)
+    dconv = conv_ref(xq, Wd)
+    cases = [
+        (0, wf[0], F.elu(conv + bias.float().double())),
+        (1, wf[0], F.elu(conv + bias.float().double() + a1q)),
+        (2, wbw[0], dconv * elu_grad_from_out(a1q)),
+        (3, wbw[0], (dconv + a2q) * elu_grad_from_out(a1q)),
+        (4, wf[0], conv + bias.float().double()),
+    ]
+    for mode, w, ref in cases:
+        out.zero_()
+        _lib.call('bruno_conv3x3', mode, xs, w, b32, a1s, a2s, out, N, H, W)
+        got = slab.slab_to_nhwc(out, N, H, W, check_padding=True).double().cpu()
+        err = (got - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        assert err <= 2.0 ** -7 * scale + 1e-3, (mode, err, scale)
+        # mean error must be far below the bf16 output quantum (catches systematic tap/channel mix-ups)
+        assert (got - ref).abs().mean().item() <= 3e-3 * scale, (mode, (got - ref).abs().mean().item())
+
+
+@pytest.mark.parametrize('N,H,W', [(3, 28, 28), (5, 14, 14), (2, 32, 32), (300, 14, 14)])
+def test_conv3x3_wgrad(N, H, W):
+    from bruno_b200 import _lib, slab
+    g = torch.Generator().manual_seed(7 + N)
+    x = torch.randn(N, H, W, 64, generator=g, dtype=torch.float64)
+    gr = torch.randn(N, H, W, 64, generator=g, dtype=torch.float64) * 0.1
+    xs, gs = slab.nhwc_to_slab(x.float().cuda()), slab.nhwc_to_slab(gr.float().cuda())
+    dW = torch.zeros(3, 3, 64, 64, device='cuda')
+    db = torch.zeros(64, device='cuda')
+    _lib.call('bruno_conv3x3_wgrad', xs, gs, dW, db, N, H, W)
+    xq, gq = bf(x), bf(gr)
+    w = torch.zeros(3, 3, 64, 64, dtype=torch.float64, requires_grad=True)
+    (conv_ref(xq, w) * gq).sum().backward()
+    ref = w.grad
+    scale = ref.abs().max().item()
+    assert (dW.double().cpu() - ref).abs().max().item() <= 2e-4 * scale + 1e-4
+    refb = gq.sum(dim=(0, 1, 2))
+    assert (db.double().cpu() - refb).abs().max().item() <= 2e-4 * refb.abs().max().item() + 1e-4
+    # accumulation semantics: a second call doubles the result
+    _lib.call('bruno_conv3x3_wgrad', xs, gs, dW, db, N, H, W)
+    assert (dW.double().cpu() - 2 * ref).abs().max().item() <= 4e-4 * scale + 2e-4
+
+
+def test_wn_backward():
+    from bruno_b200 import _lib
+    g = torch.Generator().manual_seed(3)
+    V = (torch.randn(2, 3, 3, 64, 64, generator=g, dtype=torch.float64) * 0.05).requires_grad_(True)
+    gain = (0.5 + torch.rand(2, 64, generator=g, dtype=torch.float64)).requires_grad_(True)
+    dW = torch.randn(2, 3, 3, 64, 64, generator=g, dtype=torch.float64)
+    Wn = torch.stack([wn(V[i], gain[i]) for i in range(2)])
+    (Wn * dW).sum().backward()
+    dV = torch.empty(2, 576, 64, device='cuda')
+    dg = torch.empty(2, 64, device='cuda')
+    _lib.call('bruno_conv_wn_bwd', V.detach().float().cuda().contiguous(), gain.detach().float().cuda().contiguous(),
+              dW.float().cuda().contiguous(), dV, dg, 2, 576)
+    assert torch.allclose(dV.double().cpu().view(2, 3, 3, 64, 64), V.grad, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(dg.double().cpu(), gain.grad, rtol=1e-4, atol=1e-5)

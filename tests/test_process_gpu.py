@@ -150,7 +150,7 @@ def test_sampler_matches_oracle():
             noise = torch.rand(2, n, B, D, generator=g) if kind == 'tp' else torch.randn(n, B, D, generator=g)
             ref = proc.sample_from_uniforms(noise.double()) if kind == 'tp' else proc.sample_from_normals(noise.double())
             out = layer.sample_from(mu[:, t], var[:, t], None if nu is None else nu[t], noise.cuda())
-            _close(out, ref, rtol=2e-4, atol=2e-4)
+            _close(out, ref, rtol=5e-4, atol=5e-4)   # fp32 sin/cos/sqrt chain of the polar method
             if t < T:
                 proc.update_distribution(z[:, t, :].double())
 
