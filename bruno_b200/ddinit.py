@@ -1,0 +1,86 @@
+"""Data-dependent initialisation of the weight-normalised layers (nn_extra_nvp.py:394-398, 422-426; run once at
+iteration 0, config_rnn/train.py:178-182).  One-off host logic: the pre-activations come from the CUDA kernels (mode 4
+of bruno_conv3x3 / the fp32 workspace of the dense coupling), the per-channel moments are plain torch reductions.
+Like the reference, the layer's OUTPUT during the init pass is computed with the OLD g, b; they are re-assigned after."""
+import torch
+
+from . import _lib
+from .slab import slab_to_nhwc, alloc_slabs
+
+
+def _assign(g, b, pre, dims):
+    m = pre.mean(dim=dims)
+    v = pre.var(dim=dims, unbiased=False)
+    scale_init = 1.0 / torch.sqrt(v + 1e-10)
+    g.mul_(scale_init)                                   # g.assign(g * scale_init)
+    b.add_(-m * scale_init)                              # b.assign_add(-m_init * scale_init)
+
+
+def conv_coupling_init(layer, x):
+    with torch.no_grad():
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        R = layer.num_res_blocks
+        slabs = layer._saved_slabs(N, H, W, x.device)
+        wb = _lib.query('bruno_conv_wpack_bytes')
+        wfwd = torch.empty(2 * R, wb, dtype=torch.uint8, device=x.device)
+        _lib.call('bruno_conv_wn_pack', layer.Vr, layer.gr, wfwd, None, 2 * R)
+        ld = torch.zeros(N, device=x.device)
+        y = torch.empty_like(x)
+        _lib.call('bruno_coupling_conv_fwd', x, ld, y, torch.empty_like(ld), N, H, W, C, R, layer.mask_id, 0, layer.V1,
+                  layer.g1, layer.b1, wfwd, layer.br, layer.Ks, layer.bs, layer.Kt, layer.bt, slabs, int(slabs.shape[0]))
+        # c1: pre-activation on the masked input
+        hh = torch.arange(H, device=x.device).view(H, 1, 1)
+        ww = torch.arange(W, device=x.device).view(1, W, 1)
+        cc = torch.arange(C, device=x.device).view(1, 1, C)
+        mt = layer.mask_type
+        if mt.startswith('checkerboard'):
+            b = ((hh + ww) % 2).float().expand(H, W, C)
+            b = 1 - b if mt == 'checkerboard1' else b
+        else:
+            b = ((cc < C // 2) if mt == 'channel0' else (cc >= C // 2)).float().expand(H, W, C)
+        nrm = torch.sqrt(torch.clamp((layer.V1 ** 2).sum(0), min=1e-12))
+        W1 = layer.V1 * (layer.g1 / nrm)
+        pre = (x * b).reshape(-1, C) @ W1 + layer.b1
+        new = [(layer.g1, layer.b1, pre, (0,))]
+        tmp = alloc_slabs(1, N, H, W, x.device)[0]
+        pres = []
+        for l in range(2 * R):
+            _lib.call('bruno_conv3x3', 4, slabs[l], wfwd[l], layer.br[l].contiguous(), None, None, tmp, N, H, W)
+            pres.append(slab_to_nhwc(tmp, N, H, W))
+        _assign(layer.g1, layer.b1, pre, (0,))
+        for l in range(2 * R):
+            _assign(layer.gr[l], layer.br[l], pres[l], (0, 1, 2))
+
+
+def _dense_ws_offsets(N, D, U):
+    def r4(n):
+        return (n + 3) // 4 * 4
+    o, out = 0, {}
+    for name, n in (('sc1', U), ('sc2', U), ('xm', N * D), ('pre1', N * U), ('pre2', N * U), ('h1', N * U), ('h2', N * U),
+                    ('s_pre', N * D), ('t_pre', N * D)):
+        out[name] = (o, n)
+        o += r4(n)
+    return out
+
+
+def dense_coupling_init(layer, x):
+    with torch.no_grad():
+        xs = x.shape
+        x = x.contiguous()
+        N, U = xs[0], layer.n_units
+        D = x.numel() // N
+        ws = torch.empty(_lib.query('bruno_coupling_dense_ws_floats', N, D, U), device=x.device)
+        ld = torch.zeros(N, device=x.device)
+
+        def run():
+            _lib.call('bruno_coupling_dense_fwd', x, ld, torch.empty_like(x), torch.empty_like(ld), N, D, U, layer.mask_id, 0,
+                      layer.V1, layer.g1, layer.b1, layer.V2, layer.g2, layer.b2, layer.Ks, layer.bs, layer.Kt, layer.bt, ws)
+        off = _dense_ws_offsets(N, D, U)
+        run()
+        o, n = off['pre1']
+        pre1 = ws[o:o + n].view(N, U).clone()
+        o, n = off['pre2']
+        pre2 = ws[o:o + n].view(N, U).clone()
+        _assign(layer.g1, layer.b1, pre1, (0,))
+        _assign(layer.g2, layer.b2, pre2, (0,))

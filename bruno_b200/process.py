@@ -162,6 +162,20 @@ class RecurrentProcessLayer(object):
     def get_log_likelihood_under_prior(self, observation, mask_dim=None):  # student:120-130 / gauss:98-105
         return self._step(observation, mask_dim, False)[1]
 
+    def log_likelihood_with_state(self, observation, s1, s2, n_obs, mask_dim=None):
+        """get_log_likelihood(observation [n,D]) under the distribution reached after `n_obs` observations whose
+        prefix sums are s1, s2 [n,D] (left untouched)."""
+        with torch.no_grad():
+            obs = observation.detach().to(torch.float32).contiguous()
+            n, D = obs.shape
+            table = build_table(self.kind, self.var_vbl.detach(), None if self.nu_vbl is None else self.nu_vbl.detach(),
+                                self.corr_vbl.detach(), self.mu, mask_dim, self.min_nu, int(n_obs), 1, False)
+            lp = torch.empty(n, 1, device=obs.device)
+            scratch = _empty(_lib.query('bruno_process_scratch_floats', n, 1, D), obs)
+            _lib.call('bruno_process_fwd', self.kind, obs.view(n, 1, D), self.mu, table, s1.clone(), s2.clone(), lp, None,
+                      scratch, n, 1, D)
+            return lp[:, 0]
+
     def posterior_sequence(self, z_vec):
         """current_distribution after 0..T observations: mu, var [B,T+1,D] and nu [T+1,D] (None for GP)."""
         with torch.no_grad():

@@ -1,0 +1,78 @@
+"""Synthetic stand-ins for the reference's dataset iterators (data_iter.py), which need data/*.npy files that do not
+exist here.  Same shape / range contract as data_iter.py:61-74: x = pixel + U[0,1) with pixel in {0..255}, float32,
+shape (batch_size, seq_len) + obs_shape; `generate()` yields batches, `get_observation_size()` returns
+(seq_len,) + obs_shape.  'strokes' mimics Omniglot (sparse saturated strokes), 'bytes' is uniform noise."""
+import numpy as np
+
+
+class SyntheticExchSeqDataIterator(object):
+    def __init__(self, seq_len, batch_size, obs_shape=(28, 28, 1), kind='strokes', rng=None, noise_rng=None,
+                 n_batches=None, dataset='train', **kwargs):
+        self.seq_len = seq_len
+        self.batch_size = batch_size
+        self.obs_shape = tuple(obs_shape)
+        self.kind = kind
+        self.rng = rng if rng is not None else np.random.RandomState(42)
+        self.noise_rng = noise_rng if noise_rng is not None else np.random.RandomState(317070)
+        self.nsamples = n_batches
+        self.set = dataset
+
+    def get_observation_size(self):
+        return (self.seq_len,) + self.obs_shape
+
+    def _batch(self):
+        shape = (self.batch_size, self.seq_len) + self.obs_shape
+        if self.kind == 'strokes':
+            # one "class" prototype per sequence + per-frame jitter: frames of a sequence are exchangeable, not iid
+            proto = self.rng.uniform(size=(self.batch_size, 1) + self.obs_shape) < 0.1
+            flip = self.rng.uniform(size=shape) < 0.03
+            pix = np.logical_xor(np.broadcast_to(proto, shape), flip).astype(np.float32) * 255.0
+        else:
+            pix = self.rng.randint(0, 256, size=shape).astype(np.float32)
+        noise = self.noise_rng.uniform(size=shape).astype(np.float32)
+        return np.minimum(pix + noise, np.float32(255.99998))
+
+    def generate(self, rng=None, noise_rng=None):
+        i = 0
+        while self.nsamples is None or i < self.nsamples:
+            yield self._batch()
+            i += 1
+
+    def generate_each_digit(self, **kwargs):
+        for x in self.generate():
+            yield x, np.zeros((self.batch_size,), dtype='int32')
+
+
+class SyntheticFewShotIterator(object):
+    """Shape contract of OmniglotTestBatchSeqDataIterator.generate (data_iter.py:204-241): k-way n-shot episodes as
+    x [k, n+1, ...] where row j holds n shots of class j followed by THE SAME test image in every row, plus the label
+    index of the true class."""
+
+    def __init__(self, seq_len, batch_size, obs_shape=(28, 28, 1), rng=None, n_classes=50, **kwargs):
+        self.seq_len, self.batch_size, self.obs_shape = seq_len, batch_size, tuple(obs_shape)
+        self.rng = rng if rng is not None else np.random.RandomState(317070)
+        self.n_classes = n_classes
+        self.protos = (self.rng.uniform(size=(n_classes,) + self.obs_shape) < 0.12)
+
+    def get_observation_size(self):
+        return (self.seq_len,) + self.obs_shape
+
+    def _draw(self, c):
+        flip = self.rng.uniform(size=self.obs_shape) < 0.02
+        return np.logical_xor(self.protos[c], flip).astype(np.float32) * 255.0
+
+    def generate(self, trial=0, condition_on_train=False):
+        k, n = self.batch_size, self.seq_len - 1
+        for true_cls in range(self.n_classes):
+            others = [c for c in range(self.n_classes) if c != true_cls]
+            classes = [true_cls] + list(self.rng.choice(others, k - 1, replace=False))
+            self.rng.shuffle(classes)
+            x = np.zeros((k, self.seq_len) + self.obs_shape, dtype=np.float32)
+            for j, c in enumerate(classes):
+                for s in range(n):
+                    x[j, s] = self._draw(c)
+            test = self._draw(true_cls)
+            x[:, -1] = test[None]
+            noise = self.rng.uniform(size=(1,) + x.shape[1:]).astype(np.float32)   # same noise in every row (data_iter.py:233-238)
+            x = np.minimum(x + noise, np.float32(255.99998))
+            yield x, np.asarray(classes), true_cls

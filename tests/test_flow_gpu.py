@@ -1,0 +1,137 @@
+"""GPU parity of the whole hot path (flow + process, forward and hand-written backward, inverse / sampling) against
+the CPU oracle on identical synthetic inputs and weights.
+
+Tolerances.  Dense (en2) path is fp32 end to end: per-example log-likelihood within 1e-4 relative (north star).
+Conv path: bf16 tensor-core operands with fp32 accumulation and bf16 hidden activations -> stated looser bound:
+per-example log-likelihood within 2e-3 relative (measured ~3e-4), gradients within 5e-2 of each tensor's max."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bruno_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_LL = {'en2_noconv_mnist_tp': 1e-4, 'bn2_omniglot_tp': 2e-3, 'bn2_omniglot_gp': 2e-3, 'an2_cifar_tp': 2e-3}
+TOL_GRAD = {'en2_noconv_mnist_tp': 2e-3, 'bn2_omniglot_tp': 5e-2, 'bn2_omniglot_gp': 5e-2, 'an2_cifar_tp': 5e-2}
+
+
+def fresh_config(name):
+    mod = importlib.import_module('bruno_b200.config_rnn.' + name)
+    return importlib.reload(mod)
+
+
+def setup(name, B, T, seed):
+    spec = O.spec_for(name)
+    P = O.init_params(spec, seed=seed, dtype=torch.float64, perturb_process=True)
+    x = O.synthetic_batch(spec, B, T, seed=seed + 1, kind='strokes' if 'cifar' not in name else 'bytes')
+    x = x.float().double()
+    O.data_dependent_init(spec, P, x)
+    P = O.cast_params(O.cast_params(P, torch.float32), torch.float64)   # both sides see the same fp32 numbers
+    cfg = fresh_config(name)
+    xg = x.float().cuda()
+    cfg.build_model(xg[:1])              # creates the variables
+    cfg.model.load_tf_variables(P)
+    return spec, P, x, cfg, xg
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu()
+    return ((a - b).abs() / b.abs().clamp_min(1.0)).max().item()
+
+
+@pytest.mark.parametrize('name,B,T', [('en2_noconv_mnist_tp', 4, 5), ('bn2_omniglot_tp', 2, 3), ('bn2_omniglot_gp', 2, 2),
+                                      ('an2_cifar_tp', 1, 2)])
+def test_forward_and_backward_match_oracle(name, B, T):
+    spec, P, x, cfg, xg = setup(name, B, T, seed=5)
+    with torch.no_grad():
+        lp_o, lat_o, pri_o, z_o = O.build_model(spec, P, x)
+    lp, lat, pri, z = cfg.build_model(xg)
+    e = {k: rel_err(a, b) for k, a, b in (('log_probs', lp, lp_o), ('latent', lat, lat_o), ('prior', pri, pri_o))}
+    ez = (z.detach().double().cpu() - z_o).abs().max().item()
+    print('\n[%s] per-example log-lik rel err %s, max |dz| %.3e' % (name, e, ez))
+    for k, v in e.items():
+        assert v <= TOL_LL[name], (k, v)
+    # bits/dim (test_nll.py:61-66)
+    bpd = lambda t: (-t.double().mean() / np.log(2.) / spec.ndim).item()
+    assert abs(bpd(lp.detach().cpu()) - bpd(lp_o)) <= TOL_LL[name] * abs(bpd(lp_o))
+    # hand-written backward vs oracle autograd
+    loss_o, grads_o = O.loss_and_grads(spec, P, x)
+    loss = cfg.loss(lp)
+    params = cfg.model.parameters()
+    grads = torch.autograd.grad(loss, params)
+    by_id = {id(p): g for p, g in zip(params, grads)}
+    worst = (0.0, None)
+    for tfname, view in cfg.model.named_tf_variables():
+        base = view._base if view._base is not None else view
+        g = by_id[id(base)] if id(base) in by_id else by_id[id(view)]
+        # re-create the same view on the gradient tensor
+        gv = g.as_strided(view.shape, view.stride(), view.storage_offset() - base.storage_offset()).double().cpu()
+        ref = grads_o[tfname]
+        scale = ref.abs().max().item() + 1e-12
+        err = (gv - ref).abs().max().item() / scale
+        if err > worst[0]:
+            worst = (err, tfname)
+        assert err <= TOL_GRAD[name], (tfname, err, scale)
+    print('[%s] loss %.6f (oracle %.6f); worst gradient error %.3e of max at %s' % (name, loss.item(), loss_o.item(), worst[0], worst[1]))
+    assert abs(loss.item() - loss_o.item()) <= TOL_LL[name] * abs(loss_o.item())
+
+
+@pytest.mark.parametrize('name', ['en2_noconv_mnist_tp', 'bn2_omniglot_tp', 'an2_cifar_tp'])
+def test_inverse_round_trip(name):
+    """backward(forward(x)) == x and the two log-dets cancel (size-independent property of the flow)."""
+    spec, P, x, cfg, xg = setup(name, 1, 3, seed=9)
+    m = cfg.model
+    with torch.no_grad():
+        xb = xg.reshape((-1,) + tuple(xg.shape[2:]))
+        z, ld = m.flow_forward(xb)
+        xr, ldr = m.flow_inverse(z)
+    tol = 1e-3 if name.startswith('en2') else 0.35      # pixels in [0,256); conv path: bf16 s/t nets evaluated twice
+    err = (xr - xb).abs().max().item()
+    print('\n[%s] round-trip max |x - x_rec| = %.3e (pixel units), |ld + ld_inv| = %.3e' % (name, err, (ld + ldr).abs().max().item()))
+    assert err <= tol
+    assert (ld + ldr).abs().max().item() <= (1e-2 if name.startswith('en2') else 2.0)
+
+
+@pytest.mark.parametrize('name', ['en2_noconv_mnist_tp', 'bn2_omniglot_tp'])
+def test_sampling_branch_matches_oracle(name):
+    """sampling_mode=True (test_samples.py:48-52) with the random draws supplied: samples from fixed latents."""
+    spec, P, x, cfg, xg = setup(name, 1, 3, seed=13)
+    T, n, D = 3, cfg.n_samples, spec.ndim
+    g = torch.Generator().manual_seed(3)
+    noise = [torch.rand(2, n, 1, D, generator=g) for _ in range(T + 1)]
+    with torch.no_grad():
+        xs_o, lp_o = O.build_model_sampling(spec, P, x, [t.double() for t in noise])
+    xs, lp = cfg.build_model(xg, sampling_mode=True, noise=[t.cuda() for t in noise])
+    assert tuple(xs.shape) == tuple(xs_o.shape) and tuple(lp.shape) == tuple(lp_o.shape)
+    ex = (xs.double().cpu() - xs_o).abs().max().item()
+    el = rel_err(lp, lp_o)
+    print('\n[%s] sampling: max |x_s - oracle| = %.3e (pixel units), log-prob rel err %.3e' % (name, ex, el))
+    assert ex <= (2e-2 if name.startswith('en2') else 2.0)
+    assert el <= (2e-4 if name.startswith('en2') else 5e-3)
+
+
+def test_few_shot_argmax_matches_oracle():
+    """test_few_shot_omniglot scoring (:64-80): argmax over the k candidate sequences of log_probs[:, -1]."""
+    name = 'bn2_omniglot_tp'
+    spec = O.spec_for(name)
+    P = O.init_params(spec, seed=21, dtype=torch.float64, perturb_process=True)
+    from bruno_b200.synthetic_data import SyntheticFewShotIterator
+    it = SyntheticFewShotIterator(seq_len=2, batch_size=20, rng=np.random.RandomState(4), n_classes=3)
+    x0 = torch.from_numpy(next(it.generate())[0]).double()
+    O.data_dependent_init(spec, P, x0)
+    P = O.cast_params(O.cast_params(P, torch.float32), torch.float64)
+    cfg = fresh_config(name)
+    cfg.build_model(x0[:1].float().cuda())
+    cfg.model.load_tf_variables(P)
+    for xb, classes, true_cls in it.generate():
+        xb = torch.from_numpy(xb)
+        with torch.no_grad():
+            s_o = O.build_model(spec, P, xb.double())[0][:, -1]
+            s_g = cfg.build_model(xb.cuda())[0][:, -1]
+        assert int(s_o.argmax()) == int(s_g.argmax())
+        top2 = torch.topk(s_o, 2).values
+        print('\nfew-shot: argmax %d, oracle margin %.3f, max score err %.3e' % (int(s_g.argmax()), (top2[0] - top2[1]).item(),
+                                                                               (s_g.double().cpu() - s_o).abs().max().item()))

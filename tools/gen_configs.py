@@ -1,0 +1,121 @@
+"""Writes the four thin config modules under bruno_b200/config_rnn/ from one template (they differ only in the
+attributes the reference's config files differ in).  Run once: python tools/gen_configs.py"""
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+TMPL = '''"""B200 mirror of the reference's {ref}: same module attributes and the same
+build_model / loss surface (SURVEY 8b); the graph runs on hand-written sm_100a kernels."""
+import sys
+
+import numpy as np
+
+from .. import nn_extra_nvp, {procmod}, synthetic_data
+from . import defaults, _common
+
+batch_size = {batch_size}
+sample_batch_size = 1
+n_samples = 4
+rng = np.random.RandomState(42)
+rng_test = np.random.RandomState(317070)
+seq_len = defaults.seq_len
+
+nonlinearity = nn_extra_nvp.elu
+weight_norm = True
+
+# The reference builds dataset iterators here ({ref}:{iterlines}); the datasets are not available, so synthetic
+# iterators with the same shape / range contract stand in (bruno_b200/synthetic_data.py).
+_obs = {obs}
+train_data_iter = synthetic_data.SyntheticExchSeqDataIterator(seq_len=seq_len, batch_size=batch_size, obs_shape=_obs,
+                                                              kind='{kind}', rng=rng, dataset='train')
+test_data_iter = synthetic_data.SyntheticExchSeqDataIterator(seq_len=seq_len, batch_size=batch_size, obs_shape=_obs,
+                                                             kind='{kind}', rng=rng_test, dataset='test')
+valid_data_iter = test_data_iter
+test_data_iter2 = synthetic_data.SyntheticFewShotIterator(seq_len=seq_len, batch_size=batch_size, obs_shape=_obs,
+                                                          rng=rng_test)
+
+obs_shape = train_data_iter.get_observation_size()  # (seq_len, H, W, C)
+print('obs shape', obs_shape)
+
+ndim = int(np.prod(obs_shape[1:]))
+corr_init = np.ones((ndim,), dtype='float32') * 0.1
+nu_init = 1000
+
+optimizer = 'rmsprop'
+learning_rate = 0.001
+lr_decay = 0.999995
+{sched}
+nvp_layers = []
+nvp_dense_layers = []
+student_layer = None
+model = None
+has_conv = {has_conv}
+supports_mask_dims = {mask_dims}
+
+
+def make_process_layer(device):
+    return {proc_ctor}
+
+
+def build_model(x, init=False, sampling_mode=False, noise=None, want_prior=True):
+    """{ref} build_model: returns (log_probs, latent_log_probs, latent_log_probs_prior, z_vec), or
+    (x_samples, log_probs) when sampling_mode."""
+    return _common.run_build_model(sys.modules[__name__], x, init, sampling_mode, noise=noise, want_prior=want_prior)
+
+
+def build_nvp_model():
+    _common.build_nvp_model(nvp_layers, nonlinearity, weight_norm)
+
+
+def build_nvp_dense_model():
+    _common.build_nvp_dense_model(nvp_dense_layers, nonlinearity, weight_norm, n_units=512)
+
+
+def loss(log_probs):
+    return -log_probs.mean()
+'''
+
+SCHED_BN2 = '''
+scale_student_grad = 0.
+max_iter = 200000
+save_every = 1000
+student_grad_schedule = {0: 0., 100: 0.1}
+
+
+class _LrSchedule(object):
+    """bn2_omniglot_tp.py:46-52 builds a 200000-entry dict: lr_i = 1e-3 * 0.999995^(i+1), times 1.5 from i = 100."""
+
+    def __contains__(self, i):
+        return 0 <= i < max_iter
+
+    def __getitem__(self, i):
+        return learning_rate * (0.999995 ** (i + 1)) * (1.5 if i >= 100 else 1.0)
+
+
+learning_rate_schedule = _LrSchedule()
+'''
+
+SCHED_PLAIN = '''
+scale_student_grad = 0.
+max_iter = %d
+save_every = 1000%s
+student_grad_schedule = {0: 0., 100: 0.1}
+'''
+
+TP = "nn_extra_student.StudentRecurrentLayer(shape=(ndim,), corr_init=corr_init, nu_init=nu_init, device=device)"
+GP = "nn_extra_gauss.GaussianRecurrentLayer(shape=(ndim,), corr_init=corr_init, device=device)"
+
+CFGS = [
+    ('bn2_omniglot_tp', 32, '(28, 28, 1)', 'strokes', SCHED_BN2, True, False, 'nn_extra_student', TP, '20-29'),
+    ('bn2_omniglot_gp', 32, '(28, 28, 1)', 'strokes', SCHED_BN2, True, False, 'nn_extra_gauss', GP, '20-29'),
+    ('an2_cifar_tp', 16, '(32, 32, 3)', 'bytes', SCHED_PLAIN % (70000, ''), True, False, 'nn_extra_student', TP, '19-24'),
+    ('en2_noconv_mnist_tp', 64, '(28, 28, 1)', 'strokes', SCHED_PLAIN % (100000, '\nvalidate_every = 1000\nn_valid_batches = 20'),
+     False, True, 'nn_extra_student', TP, '19-27'),
+]
+
+for name, bs, obs, kind, sched, conv, md, procmod, ctor, il in CFGS:
+    path = os.path.join(ROOT, 'bruno_b200', 'config_rnn', name + '.py')
+    with open(path, 'w') as fh:
+        fh.write(TMPL.format(ref='config_rnn/%s.py' % name, procmod=procmod, batch_size=bs, obs=obs, kind=kind, sched=sched,
+                             has_conv=conv, mask_dims=md, proc_ctor=ctor, iterlines=il))
+    print('wrote', path)
