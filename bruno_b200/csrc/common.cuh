@@ -4,13 +4,31 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/bruno_sm100.h"
 
 namespace bruno {
 
 void set_last_error(const char* fmt, ...);
 
+extern std::atomic<long> g_launches;
+
+// RAII CUDA-event span around one kernel launch (no-op unless bruno_profile_enable(1))
+class ProfSpan {
+ public:
+  ProfSpan(int kind, cudaStream_t st);
+  ~ProfSpan();
+
+ private:
+  int kind_;
+  cudaStream_t st_;
+  bool active_;
+  void *begin_ = nullptr, *end_ = nullptr;
+};
+
 inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_error("%s: %s", what, cudaGetErrorString(e));

@@ -441,6 +441,7 @@ static int launch_conv(const void* in, const void* w, const float* bias, const v
     configured = true;
   }
   const int grid = g.NT < num_sms() ? g.NT : num_sms();
+  ProfSpan span(BRUNO_PROF_CONV, st);
   conv3x3_kernel<MODE><<<grid, CONV_THREADS, smem, st>>>(
       static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias, static_cast<const uint8_t*>(a1),
       static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g);
@@ -516,6 +517,7 @@ int bruno_conv3x3_wgrad(const void* x_slab, const void* g_slab, float* dW, float
     configured = true;
   }
   const int grid = g.NT < num_sms() ? g.NT : num_sms();
+  ProfSpan span(BRUNO_PROF_WGRAD, static_cast<cudaStream_t>(stream));
   conv3x3_wgrad_kernel<<<grid, CONV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint8_t*>(x_slab), static_cast<const uint8_t*>(g_slab), dW, db, g);
   return check_launch("conv3x3_wgrad_kernel");

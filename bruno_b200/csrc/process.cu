@@ -13,22 +13,10 @@
 //     carrying the suffix sums of dL/dS1, dL/dS2; coefficient gradients are chained to the raw variables with the
 //     fp64 forward-mode derivatives stored by the table kernel.
 #include <math.h>
-#include <stdarg.h>
 
 #include "common.cuh"
 
 namespace bruno {
-
-// ------------------------------------------------------------------------------------------------------------
-// last error (thread-local so concurrent host threads do not trample each other)
-// ------------------------------------------------------------------------------------------------------------
-static thread_local char g_err[512] = "";
-void set_last_error(const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(g_err, sizeof(g_err), fmt, ap);
-  va_end(ap);
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // forward-mode dual numbers in fp64 (3 tangents: raw var, raw nu, raw corr)
@@ -659,8 +647,12 @@ static int launch_fwd(const float* z, const float* mu0, const float* table, floa
     }
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   }
-  k<<<grid, g.threads, smem, st>>>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D);
-  int rc = check_launch("process_fwd_kernel");
+  int rc;
+  {
+    ProfSpan span(BRUNO_PROF_PROCESS_FWD, st);
+    k<<<grid, g.threads, smem, st>>>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D);
+    rc = check_launch("process_fwd_kernel");
+  }
   if (rc) return rc;
   if (g.nseg > 1) {
     process_fwd_finalize<<<ceil_div(B * T, 256), 256, 0, st>>>(scratch, lp, lp_prior, g.nseg, B * T);
@@ -683,11 +675,15 @@ static int launch_bwd(const float* z, const float* mu0, const float* table, cons
   const int gpb = ceil_div(groups, nblk);
   const int nblk_used = ceil_div(groups, gpb);
   dim3 grid(nblk_used, g.nseg);
-  if (dlpp)
-    process_bwd_kernel<KIND, VEC, BWD_NB, true><<<grid, g.threads, 0, st>>>(z, mu0, table, dlp, dlpp, dz, scratch, B, T, D, gpb);
-  else
-    process_bwd_kernel<KIND, VEC, BWD_NB, false><<<grid, g.threads, 0, st>>>(z, mu0, table, dlp, dlpp, dz, scratch, B, T, D, gpb);
-  int rc = check_launch("process_bwd_kernel");
+  int rc;
+  {
+    ProfSpan span(BRUNO_PROF_PROCESS_BWD, st);
+    if (dlpp)
+      process_bwd_kernel<KIND, VEC, BWD_NB, true><<<grid, g.threads, 0, st>>>(z, mu0, table, dlp, dlpp, dz, scratch, B, T, D, gpb);
+    else
+      process_bwd_kernel<KIND, VEC, BWD_NB, false><<<grid, g.threads, 0, st>>>(z, mu0, table, dlp, dlpp, dz, scratch, B, T, D, gpb);
+    rc = check_launch("process_bwd_kernel");
+  }
   if (rc) return rc;
   process_bwd_finalize<<<ceil_div(D, 256), 256, 0, st>>>(scratch, nblk_used, D, dvar, KIND == BRUNO_TP ? dnu : nullptr, dcorr);
   return check_launch("process_bwd_finalize");
@@ -698,9 +694,6 @@ static int launch_bwd(const float* z, const float* mu0, const float* table, cons
 using namespace bruno;
 
 extern "C" {
-
-const char* bruno_last_error(void) { return g_err; }
-int bruno_abi_version(void) { return 1; }
 
 size_t bruno_process_table_floats(int kind, int T, int D, int with_grad) {
   return static_cast<size_t>(T * ncf_of(kind) + N_PRIOR) * D * (with_grad ? 4 : 1);

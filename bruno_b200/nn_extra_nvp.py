@@ -128,7 +128,7 @@ class _ConvCouplingFn(torch.autograd.Function):
         ld = ld.contiguous()
         N, H, W, C = x.shape
         R = layer.num_res_blocks
-        need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (x, ld, V1, g1, b1, Vr, gr, br, Ks, bs, Kt, bt))
+        need_grad = any(ctx.needs_input_grad)
         wb = _lib.query('bruno_conv_wpack_bytes')
         wfwd = torch.empty(2 * R, wb, dtype=torch.uint8, device=x.device)
         wbwd = torch.empty(2 * R, wb, dtype=torch.uint8, device=x.device) if need_grad else None
@@ -272,7 +272,7 @@ class _DenseCouplingFn(torch.autograd.Function):
         ld_out = torch.empty_like(ld)
         _lib.call('bruno_coupling_dense_fwd', x, ld, y, ld_out, N, D, U, layer.mask_id, int(inverse), V1, g1, b1, V2, g2, b2,
                   Ks, bs, Kt, bt, ws)
-        need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (x, ld, V1, g1, b1, V2, g2, b2, Ks, bs, Kt, bt))
+        need_grad = any(ctx.needs_input_grad)
         if need_grad:
             if inverse:
                 raise RuntimeError('backward through the inverse pass is not implemented (sampling is inference-only)')

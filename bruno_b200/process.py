@@ -42,8 +42,7 @@ class ProcessSequenceLogLik(torch.autograd.Function):
     def forward(ctx, z, var_vbl, nu_vbl, corr_vbl, mu, mask_dim, kind, min_nu, want_prior):
         z = z.contiguous()
         B, T, D = z.shape
-        need_grad = z.requires_grad or var_vbl.requires_grad or corr_vbl.requires_grad or \
-            (nu_vbl is not None and nu_vbl.requires_grad)
+        need_grad = any(ctx.needs_input_grad)
         table = build_table(kind, var_vbl, nu_vbl, corr_vbl, mu, mask_dim, min_nu, 0, T, need_grad)
         lp = torch.empty(B, T, dtype=torch.float32, device=z.device)
         lpp = torch.empty(B, T, dtype=torch.float32, device=z.device) if want_prior else None

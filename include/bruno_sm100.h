@@ -30,6 +30,18 @@ extern "C" {
 
 const char* bruno_last_error(void);
 int bruno_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (evidence for bench.py's gpu_launches) */
+long bruno_launch_count(void);
+
+/* Optional CUDA-event timing of every launch of a kernel family on its own stream (off by default; bench.py turns it
+ * on for a second pass over the timed region to get the live per-launch duration of the dominant kernel). */
+#define BRUNO_PROF_CONV 0         /* conv3x3 forward / dgrad (tcgen05 implicit GEMM) */
+#define BRUNO_PROF_WGRAD 1        /* conv3x3 wgrad */
+#define BRUNO_PROF_PROCESS_FWD 2  /* t-process / GP scan forward */
+#define BRUNO_PROF_PROCESS_BWD 3
+#define BRUNO_PROF_KINDS 4
+int bruno_profile_enable(int on);
+int bruno_profile_read(int kind, double* total_ms, long* launches);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Exchangeable Student-t / Gaussian process over each latent dimension.
