@@ -1,0 +1,91 @@
+"""The data-parallel training step of config_rnn/train.py:57-131 on the B200 path.
+
+Reference semantics kept: per-tower loss = mean over the tower's shard (train.py:88-90), gradients summed over towers
+and divided by nr_gpu (:96-105), gradients of the prior_* variables multiplied by the student-grad schedule value
+(:108-111), RMSProp/Adam with TF-1.7 semantics (:121-131), iteration 0 = data-dependent init without a weight update
+(:178-182).  B200 design: one process per GPU; the towers' sum is ONE NCCL allreduce over the flat gradient buffer
+(NVLink 5 / NVSwitch); the 1/nr_gpu factor is folded into the optimiser kernel."""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class Trainer(object):
+    def __init__(self, config, device, world_size=1, rank=0):
+        self.cfg = config
+        self.device = torch.device(device)
+        self.world_size = world_size
+        self.rank = rank
+        self.model = None
+        self.iteration = 0
+        self.slots = None
+
+    # -- variables -----------------------------------------------------------------------------------------
+    def materialize(self, x_init, init=True):
+        """Creates the variables from the first batch, runs the data-dependent init pass (rank 0's batch, like the
+        reference which uses the full init batch on one device, train.py:60-61) and broadcasts the result."""
+        cfg = self.cfg
+        with torch.no_grad():
+            cfg.build_model(x_init[:1], want_prior=False)           # shapes the variables
+            self.model = cfg.model
+            if init:
+                cfg.build_model(x_init, init=True, want_prior=False)
+        self.flat, self.flat_grad = self.model.flatten_parameters()
+        if self.world_size > 1:
+            dist.broadcast(self.flat, 0)
+        opt = getattr(cfg, 'optimizer', 'rmsprop')
+        if opt == 'rmsprop':
+            self.slots = (torch.ones_like(self.flat),)                  # TF initialises the rms slot to 1
+        else:
+            self.slots = (torch.zeros_like(self.flat), torch.zeros_like(self.flat))
+        self.opt_steps = 0
+        return self
+
+    @property
+    def n_params(self):
+        return sum(p.numel() for p in self.model.parameters())
+
+    # -- one step ------------------------------------------------------------------------------------------
+    def forward_backward(self, x):
+        self.flat_grad.zero_()
+        log_probs = self.cfg.build_model(x, want_prior=False)[0]
+        loss = self.cfg.loss(log_probs)
+        loss.backward()
+        return loss.detach()
+
+    def apply_gradients(self, lr, student_scale=1.0):
+        if self.world_size > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)        # grads[0][j] += grads[i][j], train.py:97-102
+        if student_scale != 1.0:
+            for off, n in self.model.student_param_ranges():             # train.py:108-111
+                self.flat_grad[off:off + n].mul_(student_scale)
+        gs = 1.0 / self.world_size                                       # train.py:103-105
+        n = self.flat.numel()
+        self.opt_steps += 1
+        if len(self.slots) == 1:
+            _lib.call('bruno_rmsprop_tf17', self.flat, self.flat_grad, self.slots[0], n, float(lr), 0.9, 1e-10, gs)
+        else:
+            _lib.call('bruno_adam_tf17', self.flat, self.flat_grad, self.slots[0], self.slots[1], n, float(lr), 0.95, 0.9995,
+                      1e-8, self.opt_steps, gs)
+
+    def train_step(self, x, lr, student_scale=1.0):
+        loss = self.forward_backward(x)
+        self.apply_gradients(lr, student_scale)
+        return loss
+
+    def eval_step(self, x):
+        with torch.no_grad():
+            return self.cfg.build_model(x, want_prior=True)
+
+    # -- checkpoint (train.py:225-239 keeps params + optimiser slots + meta) ---------------------------------
+    def state_dict(self):
+        return {'variables': self.model.export_tf_variables(), 'flat': self.flat.detach().cpu(),
+                'slots': [s.cpu() for s in self.slots], 'opt_steps': self.opt_steps, 'iteration': self.iteration}
+
+    def load_state_dict(self, sd):
+        self.flat.copy_(sd['flat'].to(self.device))
+        for s, t in zip(self.slots, sd['slots']):
+            s.copy_(t.to(self.device))
+        self.opt_steps = sd['opt_steps']
+        self.iteration = sd['iteration']

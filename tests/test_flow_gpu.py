@@ -64,13 +64,16 @@ def test_forward_and_backward_match_oracle(name, B, T):
     grads = torch.autograd.grad(loss, params)
     by_id = {id(p): g for p, g in zip(params, grads)}
     worst = (0.0, None)
+    # absolute floor: for C = 1 the c1 weight-norm gradient w.r.t. V is exactly 0 in exact arithmetic (W = g sign(V));
+    # fp32 leaves the cancellation residue of two O(|g/V| dW) terms there
+    floor = 1e-5 * max(v.abs().max().item() for v in grads_o.values())
     for tfname, view in cfg.model.named_tf_variables():
         base = view._base if view._base is not None else view
         g = by_id[id(base)] if id(base) in by_id else by_id[id(view)]
         # re-create the same view on the gradient tensor
         gv = g.as_strided(view.shape, view.stride(), view.storage_offset() - base.storage_offset()).double().cpu()
         ref = grads_o[tfname]
-        scale = ref.abs().max().item() + 1e-12
+        scale = ref.abs().max().item() + floor
         err = (gv - ref).abs().max().item() / scale
         if err > worst[0]:
             worst = (err, tfname)
