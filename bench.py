@@ -1,0 +1,255 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the BRUNO hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm  (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     # reference arm: the CPU restatement of the reference
+                                                           # (TF-1.7 cannot run here), timed on the box's host cores
+
+Workload (BASELINE.json): bn2_omniglot_tp training -- conv Real NVP + recurrent t-process on synthetic Omniglot-shaped
+28x28 sequences, seq_len 20, 32 sequences per GPU (weak scaling: per-GPU batch fixed), one step = forward + hand-written
+backward + NCCL gradient allreduce + TF-semantics RMSProp.  Also reports forward NLL-eval throughput.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIG = 'bn2_omniglot_tp'
+R_BLOCKS, FILTERS = 8, 64
+
+
+def conv_launch_flops(per_gpu_images):
+    """Algorithmic FLOPs (2*MAC) of the 3x3 64->64 convolutions per forward pass: 16 per coupling, 3 couplings at
+    28x28 and 7 at 14x14."""
+    per_px = 2 * 9 * FILTERS * FILTERS
+    return per_gpu_images * 16 * per_px * (3 * 28 * 28 + 7 * 14 * 14)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if 'Active' in v and 'Not' not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+def cpu_reference_line(args, steps, warmup, as_reference_arm):
+    """The reference's own CPU path cannot run (TF-1.7 absent): time the oracle restatement (PyTorch-CPU fp32, all host
+    threads) on a bounded sample of the same workload: `sample_b` sequences of 20 frames, forward + backward."""
+    import torch
+    from oracle import bruno_oracle as O
+    spec = O.spec_for(CONFIG)
+    sample_b = args.cpu_sample_seqs
+    P = O.init_params(spec, seed=0, dtype=torch.float32)
+    x = O.synthetic_batch(spec, sample_b, args.seq_len, seed=1, dtype=torch.float32)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.loss_and_grads(spec, P, x)
+        times.append(time.perf_counter() - t0)
+    t = sum(times[warmup:]) / max(steps, 1)
+    val = sample_b / t
+    cb = {'value': val, 'unit': 'seqs/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+          'sample': '%d sequence(s) x %d frames 28x28, forward+backward of bn2_omniglot_tp (oracle restatement, '
+                    'PyTorch-CPU fp32, no optimiser step), %d timed repetition(s)' % (sample_b, args.seq_len, steps)}
+    if not as_reference_arm:
+        return cb
+    return {'metric': 'bn2_omniglot_tp_train_seqs_per_sec', 'value': val, 'unit': 'seqs/s', 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': 'bn2_omniglot_tp training step (fwd+bwd), 28x28x1, seq_len %d' % args.seq_len,
+                       'per_step_sample_seqs': sample_b},
+            'cpu_baseline': cb, 'e2e': {'value': val, 'unit': 'seqs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='bruno_b200')
+    ap.add_argument('--batch', type=int, default=32, help='sequences per GPU')
+    ap.add_argument('--seq_len', type=int, default=20)
+    ap.add_argument('--cpu_sample_seqs', type=int, default=1)
+    ap.add_argument('--no_cpu_baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+
+    if args.impl == 'reference':
+        if rank == 0:
+            print(json.dumps(cpu_reference_line(args, min(args.steps, 3), min(args.warmup, 1), True)), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    warmup = max(args.warmup, 3)
+    steps = args.steps
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    from bruno_b200 import _lib
+    from bruno_b200.config_rnn import defaults
+    from bruno_b200.trainer import Trainer
+    defaults.seq_len = args.seq_len
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        cfg = importlib.import_module('bruno_b200.config_rnn.' + CONFIG)
+    cfg.batch_size = args.batch * world                      # reference semantics: global batch, split over towers
+    B, T = args.batch, args.seq_len
+    H, W, C = cfg.obs_shape[1:]
+
+    from bruno_b200.synthetic_data import SyntheticExchSeqDataIterator
+    import numpy as np
+    it = SyntheticExchSeqDataIterator(seq_len=T, batch_size=B, obs_shape=(H, W, C), kind='strokes',
+                                      rng=np.random.RandomState(42 + rank), noise_rng=np.random.RandomState(317070 + rank))
+    gen = it.generate()
+    n_host = 4
+    host = [torch.from_numpy(next(gen)).pin_memory() for _ in range(n_host)]
+    devx = [h.to(dev) for h in host]
+
+    tr = Trainer(cfg, dev, world_size=world, rank=rank).materialize(devx[0], init=True)
+    # the reference's heads are zero-initialised (flow = identity at step 0); a few real steps move them off zero
+    lr = cfg.learning_rate_schedule[200]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    losses = []
+
+    def train_resident(i):
+        losses.append(tr.train_step(devx[i % n_host], lr, 0.1))
+
+    def train_e2e(i):
+        x = host[i % n_host].to(dev, non_blocking=True)
+        loss = tr.train_step(x, lr, 0.1)
+        losses.append(loss.item())                          # device->host read of the step's result
+
+    def eval_resident(i):
+        tr.eval_step(devx[i % n_host])
+
+    for i in range(warmup):
+        train_resident(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.query('bruno_launch_count')
+    ms_train = timed(train_resident, steps)
+    launches = _lib.query('bruno_launch_count') - l0
+    if sampler:
+        sampler.stop_flag = True
+    ms_e2e = timed(train_e2e, steps)
+    for i in range(2):
+        eval_resident(i)
+    ms_eval = timed(eval_resident, steps)
+
+    # second pass with per-launch CUDA events on the conv kernels (live durations inside the step)
+    _lib.query('bruno_profile_enable', 1)
+    timed(train_resident, steps)
+    import ctypes
+    tot, cnt = ctypes.c_double(), ctypes.c_long()
+    prof = {}
+    for kind, name in ((0, 'conv3x3_fwd_dgrad'), (1, 'conv3x3_wgrad'), (2, 'process_fwd'), (3, 'process_bwd')):
+        _lib.load().bruno_profile_read(kind, ctypes.byref(tot), ctypes.byref(cnt))
+        prof[name] = {'total_ms': tot.value, 'launches': cnt.value}
+    _lib.query('bruno_profile_enable', 0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback'
+    n_img = B * T
+    conv = prof['conv3x3_fwd_dgrad']
+    # forward convs + dgrad convs: 2 x the forward count per step, `steps` steps in the profiled region
+    flops_total = 2.0 * conv_launch_flops(n_img) * steps
+    achieved = flops_total / (conv['total_ms'] * 1e-3) / 1e12 if conv['total_ms'] > 0 else None
+    seqs = B * world
+    line = {
+        'metric': 'bn2_omniglot_tp_train_seqs_per_sec', 'value': seqs * steps / (ms_train * 1e-3), 'unit': 'seqs/s',
+        'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms_train / steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': 'bn2_omniglot_tp training step: conv Real NVP (10 conv + 6 dense couplings) + recurrent '
+                               't-process, fwd + hand-written bwd + NCCL allreduce + RMSProp(TF-1.7)',
+                   'obs_shape': [H, W, C], 'seq_len': T, 'seqs_per_gpu': B, 'global_batch': seqs, 'parallelism': 'dp%d' % world,
+                   'params': tr.n_params,
+                   'l2_note': 'working set per step (6.3 GB of saved bf16 activations) >> 126 MB L2; inputs rotate over %d batches' % n_host},
+        'eval_nll': {'value': seqs * steps / (ms_eval * 1e-3), 'unit': 'seqs/s', 'ms_per_step': ms_eval / steps,
+                     'what': 'forward NLL (log_probs, latent, prior) of the same batch shape'},
+        'e2e': {'value': seqs * steps / (ms_e2e * 1e-3), 'unit': 'seqs/s', 'h2d_bytes_per_step': int(host[0].numel() * 4),
+                'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / steps},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_kernel (tcgen05 implicit GEMM, fwd + dgrad launches)',
+                     'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                     'frac': (achieved / peak_tf) if achieved else None, 'traffic': None, 'peak_source': peak_src,
+                     'launches': conv['launches'], 'avg_launch_us': 1e3 * conv['total_ms'] / max(conv['launches'], 1),
+                     'share_of_step': conv['total_ms'] / (ms_train) if ms_train else None},
+        'kernel_time_ms_per_step': {k: v['total_ms'] / steps for k, v in prof.items()},
+        'clocks': sampler.summary() if sampler else None,
+        'final_loss': float(losses[-1]) if losses else None,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line['cpu_baseline'] = cpu_reference_line(args, 2, 1, False)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

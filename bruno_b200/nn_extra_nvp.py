@@ -123,12 +123,12 @@ def preprocess_backward(y, ld, scale=256., alpha=1e-5):
 # ------------------------------------------------------------------------------------------------------------------
 class _ConvCouplingFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, ld, V1, g1, b1, Vr, gr, br, Ks, bs, Kt, bt, layer, inverse):
+    def forward(ctx, x, ld, V1, g1, b1, Vr, gr, br, Ks, bs, Kt, bt, layer, inverse, track):
         x = x.contiguous()
         ld = ld.contiguous()
         N, H, W, C = x.shape
         R = layer.num_res_blocks
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = track and any(ctx.needs_input_grad)
         wb = _lib.query('bruno_conv_wpack_bytes')
         wfwd = torch.empty(2 * R, wb, dtype=torch.uint8, device=x.device)
         wbwd = torch.empty(2 * R, wb, dtype=torch.uint8, device=x.device) if need_grad else None
@@ -165,7 +165,7 @@ class _ConvCouplingFn(torch.autograd.Function):
         dKs, dbs, dKt, dbt = torch.empty_like(Ks), torch.empty_like(bs), torch.empty_like(Kt), torch.empty_like(bt)
         _lib.call('bruno_coupling_conv_bwd', x, dy, dld, N, H, W, C, R, layer.mask_id, V1, g1, Vr, gr, ctx.wbwd, Ks, bs, Kt, bt,
                   ctx.slabs, gsl, dx, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt)
-        return dx, dld, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt, None, None
+        return dx, dld, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt, None, None, None
 
 
 class CouplingLayerConv(Layer):                                             # nvp:58-187
@@ -242,7 +242,7 @@ class CouplingLayerConv(Layer):                                             # nv
         if self.V1 is None:
             self._build(int(x.shape[3]), x.device)
         out = _ConvCouplingFn.apply(x, ld, self.V1, self.g1, self.b1, self.Vr, self.gr, self.br, self.Ks, self.bs,
-                                    self.Kt, self.bt, self, inverse)
+                                    self.Kt, self.bt, self, inverse, torch.is_grad_enabled())
         if _INIT_MODE[0]:                      # outputs above use the OLD g, b (nvp:396-398: tf.identity(x))
             from .ddinit import conv_coupling_init
             conv_coupling_init(self, x)
@@ -262,7 +262,7 @@ class CouplingLayerConv(Layer):                                             # nv
 # ------------------------------------------------------------------------------------------------------------------
 class _DenseCouplingFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, ld, V1, g1, b1, V2, g2, b2, Ks, bs, Kt, bt, layer, inverse):
+    def forward(ctx, x, ld, V1, g1, b1, V2, g2, b2, Ks, bs, Kt, bt, layer, inverse, track):
         xs = x.shape
         x = x.contiguous()
         ld = ld.contiguous()
@@ -272,7 +272,7 @@ class _DenseCouplingFn(torch.autograd.Function):
         ld_out = torch.empty_like(ld)
         _lib.call('bruno_coupling_dense_fwd', x, ld, y, ld_out, N, D, U, layer.mask_id, int(inverse), V1, g1, b1, V2, g2, b2,
                   Ks, bs, Kt, bt, ws)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = track and any(ctx.needs_input_grad)
         if need_grad:
             if inverse:
                 raise RuntimeError('backward through the inverse pass is not implemented (sampling is inference-only)')
@@ -294,7 +294,7 @@ class _DenseCouplingFn(torch.autograd.Function):
         dV1, dg1, db1, dV2, dg2, db2, dKs = outs
         _lib.call('bruno_coupling_dense_bwd', x, dy.contiguous(), dld.contiguous(), N, D, U, ctx.layer.mask_id, V1, g1, b1,
                   V2, g2, b2, Ks, Kt, ws, ws2, dx, dV1, dg1, db1, dV2, dg2, db2, dKs, dbs, dKt, dbt)
-        return dx, dld, dV1, dg1, db1, dV2, dg2, db2, dKs, dbs, dKt, dbt, None, None
+        return dx, dld, dV1, dg1, db1, dV2, dg2, db2, dKs, dbs, dKt, dbt, None, None, None
 
 
 class CouplingLayerDense(Layer):                                            # nvp:190-274
@@ -350,7 +350,7 @@ class CouplingLayerDense(Layer):                                            # nv
         if self.V1 is None:
             self._build(int(np.prod(x.shape[1:])), x.device)
         out = _DenseCouplingFn.apply(x, ld, self.V1, self.g1, self.b1, self.V2, self.g2, self.b2, self.Ks, self.bs,
-                                     self.Kt, self.bt, self, inverse)
+                                     self.Kt, self.bt, self, inverse, torch.is_grad_enabled())
         if _INIT_MODE[0]:                      # outputs above use the OLD g, b (nvp:424-426)
             from .ddinit import dense_coupling_init
             dense_coupling_init(self, x)

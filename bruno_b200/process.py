@@ -39,10 +39,10 @@ class ProcessSequenceLogLik(torch.autograd.Function):
     """(z[B,T,D], raw variables) -> (log_probs[B,T], log_probs_under_prior[B,T]); hand-written CUDA backward."""
 
     @staticmethod
-    def forward(ctx, z, var_vbl, nu_vbl, corr_vbl, mu, mask_dim, kind, min_nu, want_prior):
+    def forward(ctx, z, var_vbl, nu_vbl, corr_vbl, mu, mask_dim, kind, min_nu, want_prior, track):
         z = z.contiguous()
         B, T, D = z.shape
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = track and any(ctx.needs_input_grad)
         table = build_table(kind, var_vbl, nu_vbl, corr_vbl, mu, mask_dim, min_nu, 0, T, need_grad)
         lp = torch.empty(B, T, dtype=torch.float32, device=z.device)
         lpp = torch.empty(B, T, dtype=torch.float32, device=z.device) if want_prior else None
@@ -68,7 +68,7 @@ class ProcessSequenceLogLik(torch.autograd.Function):
         dcorr = torch.empty(1, D, dtype=torch.float32, device=z.device)
         scratch = _empty(_lib.query('bruno_process_bwd_scratch_floats', B, T, D), z)
         _lib.call('bruno_process_bwd', ctx.kind, z, mu, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D)
-        return dz, dvar, dnu, dcorr, None, None, None, None, None
+        return dz, dvar, dnu, dcorr, None, None, None, None, None, None
 
 
 class RecurrentProcessLayer(object):
@@ -117,7 +117,7 @@ class RecurrentProcessLayer(object):
         if mask_dim is not None:
             mask_dim = mask_dim.reshape(-1).to(torch.float32).contiguous()
         lp, lpp = ProcessSequenceLogLik.apply(z_vec, self.var_vbl, self.nu_vbl, self.corr_vbl, self.mu, mask_dim,
-                                              self.kind, self.min_nu, bool(want_prior))
+                                              self.kind, self.min_nu, bool(want_prior), torch.is_grad_enabled())
         return lp, (lpp if want_prior else None)
 
     # ---- the reference's step-by-step protocol (stateful, no autograd) --------------------------------
