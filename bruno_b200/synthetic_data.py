@@ -75,4 +75,7 @@ class SyntheticFewShotIterator(object):
             x[:, -1] = test[None]
             noise = self.rng.uniform(size=(1,) + x.shape[1:]).astype(np.float32)   # same noise in every row (data_iter.py:233-238)
             x = np.minimum(x + noise, np.float32(255.99998))
-            yield x, np.asarray(classes), true_cls
+            # (x_batch, y_batch [k, seq_len] with the true label in the last column, episode id): data_iter.py:204-241
+            y = np.repeat(np.asarray(classes)[:, None], self.seq_len, axis=1)
+            y[:, -1] = true_cls
+            yield x, y, true_cls

@@ -158,7 +158,7 @@ def test_few_shot_argmax_matches_oracle():
     cfg = fresh_config(name)
     cfg.build_model(x0[:1].float().cuda())
     cfg.model.load_tf_variables(P)
-    for ep, (xb, classes, true_cls) in enumerate(it.generate()):
+    for ep, (xb, y_batch, x_number) in enumerate(it.generate()):
         if ep >= 3:
             break
         xb = torch.from_numpy(xb)
