@@ -15,10 +15,13 @@ from oracle import bruno_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-# against the oracle run WITH the declared bf16 storage points emulated (oracle.emulate_bf16): only accumulation
-# order / fp32-vs-fp64 rounding remain -> tight bound, also for the conv path
-TOL_LL_EMU = 3e-4
-TOL_GRAD_EMU = 2e-2
+# against the oracle run WITH the declared bf16 storage points emulated (oracle.emulate_bf16).  One conv layer then
+# agrees bit for bit except ~0.01-0.03 % one-ulp flips (fp32 accumulation order), but every flipped value perturbs 576
+# downstream sums and re-flips a few of them: the mismatch fraction grows ~2.5x per layer and saturates near the bf16
+# noise floor after ~16 layers (tools/dbg_coupling.py, DESIGN.md "Precision").  So the whole-model bound vs the
+# emulating oracle is only ~2-4x tighter than vs the exact oracle; the bitwise statement is made per layer below.
+TOL_LL_EMU = 1.5e-3
+TOL_GRAD_EMU = 3e-2
 TOL_LL = {'en2_noconv_mnist_tp': 1e-4, 'bn2_omniglot_tp': 6e-3, 'bn2_omniglot_gp': 6e-3, 'an2_cifar_tp': 6e-3}
 TOL_GRAD = {'en2_noconv_mnist_tp': 2e-3, 'bn2_omniglot_tp': 1e-1, 'bn2_omniglot_gp': 1e-1, 'an2_cifar_tp': 1.0}
 
@@ -169,3 +172,42 @@ def test_few_shot_argmax_matches_oracle():
         top2 = torch.topk(s_o, 2).values
         print('\nfew-shot: argmax %d, oracle margin %.3f, max score err %.3e' % (int(s_g.argmax()), (top2[0] - top2[1]).item(),
                                                                                (s_g.double().cpu() - s_o).abs().max().item()))
+
+
+def test_conv_coupling_activations_bitwise_vs_emulating_oracle():
+    """Layer-level parity of the tensor-core path: c1 output bit-exact, first 3x3 conv output identical except
+    < 0.1 % one-ulp (bf16) flips, every slab keeps its zero padding."""
+    from bruno_b200 import _lib, slab
+    name = 'bn2_omniglot_tp'
+    spec, P, x, cfg, xg = setup(name, 2, 3, seed=5)
+    layer = cfg.model.nvp_layers[0]
+    xb = x.reshape(-1, 28, 28, 1)
+    N, H, W, C = xb.shape
+    with torch.no_grad():
+        y32, _ = O.logit_forward(*O.scale_forward(xb.float(), torch.zeros(N)))
+    yin = y32.double()
+    acts = []
+    with O.emulate_bf16(), torch.no_grad():
+        b = O.conv_mask(yin.shape, 'checkerboard0', torch.float64)
+        sc = 'model/Checkerboard0_1/function_s_t_wn'
+        h = O._act_store(O._wn_conv_pre(yin * b, P, sc + '/c1'))
+        acts.append(h)
+        u = O._act_store(O._wn_conv_pre(h, P, sc + '/c2_0', quant_w=True))
+        acts.append(u)
+        acts.append(O._act_store(O._wn_conv_pre(u, P, sc + '/c3_0', quant_w=True) + h))
+    R = layer.num_res_blocks
+    wf = torch.empty(2 * R, _lib.query('bruno_conv_wpack_bytes'), dtype=torch.uint8, device='cuda')
+    _lib.call('bruno_conv_wn_pack', layer.Vr, layer.gr, wf, None, 2 * R)
+    slabs = slab.alloc_slabs(2 * R + 1, N, H, W, 'cuda')
+    yg = yin.float().cuda()
+    ld = torch.zeros(N, device='cuda')
+    _lib.call('bruno_coupling_conv_fwd', yg, ld, torch.empty_like(yg), torch.empty_like(ld), N, H, W, C, R, layer.mask_id, 0,
+              layer.V1, layer.g1, layer.b1, wf, layer.br, layer.Ks, layer.bs, layer.Kt, layer.bt, slabs, 2 * R + 1)
+    frac = []
+    for i, a in enumerate(acts):
+        got = slab.slab_to_nhwc(slabs[i], N, H, W, check_padding=True).double().cpu()
+        frac.append((got != a).double().mean().item())
+        ulp = (got - a).abs().max().item() / max(a.abs().max().item(), 1e-9)
+        assert ulp <= 2.0 ** -7
+    print('\nmismatching bf16 values: c1 %.4f%%, c2_0 %.4f%%, block-0 output %.4f%%' % tuple(100 * f for f in frac))
+    assert frac[0] == 0.0 and frac[1] < 1e-3 and frac[2] < 2e-3
