@@ -45,14 +45,25 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
 }
 
+constexpr int FWD_THREADS = 224;             // producer, MMA issuer, 4 epilogue warps, store warp
+constexpr int TILE_BYTES = TILE_M * SLAB_ROW_BYTES;   // 16 KB: one output / aux tile
+
 struct ConvSmem {
   uint64_t full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2], wbar;
+  uint64_t auxfull[2], outready[2], stfree[2];
   uint32_t tmem_base;
   float bias[64];
 };
 
+__host__ __device__ constexpr bool mode_has_aux1(int m) { return m == MODE_RES_ELU || m == MODE_MUL || m == MODE_ADD_MUL; }
+__host__ __device__ constexpr bool mode_has_aux2(int m) { return m == MODE_ADD_MUL; }
+
+// Epilogue data path: aux tiles come in and the output tile goes out through 16 KB bulk async copies (TMA engine) staged
+// in shared memory; epilogue threads only touch shared memory (row r, 16-byte chunk j at chunk j ^ (r & 7): conflict
+// free).  Per-thread 16-byte global accesses to 32 different lines cost ~66 LSU cycles per instruction and made the
+// first version of this kernel LSU-bound at ~4200 cycles per tile (profiles/r01_launches_v0.txt).
 template <int MODE>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
                const uint8_t* __restrict__ aux1, const uint8_t* __restrict__ aux2, uint8_t* __restrict__ out,
                SlabGeom g) {
@@ -61,7 +72,9 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
   const uint32_t slab_bytes = static_cast<uint32_t>(TILE_M + 2 * g.HALO) * SLAB_ROW_BYTES;
   uint8_t* wsm = smem;
   uint8_t* slabs = smem + W_BYTES;
-  ConvSmem* cs = reinterpret_cast<ConvSmem*>(slabs + NSTAGE * slab_bytes);
+  uint8_t* stage1 = slabs + NSTAGE * slab_bytes;                       // [2][16 KB] aux1 in / output out (in place)
+  uint8_t* stage2 = stage1 + 2 * TILE_BYTES;                           // [2][16 KB] aux2 (MODE_ADD_MUL only)
+  ConvSmem* cs = reinterpret_cast<ConvSmem*>(stage2 + (mode_has_aux2(MODE) ? 2 * TILE_BYTES : 0));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -72,12 +85,16 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
     for (int a = 0; a < 2; ++a) {
       mbar_init(&cs->tfull[a], 1);
       mbar_init(&cs->tempty[a], 4);
+      mbar_init(&cs->auxfull[a], 1);
+      mbar_init(&cs->outready[a], 128);
+      mbar_init(&cs->stfree[a], 1);
     }
     mbar_init(&cs->wbar, 1);
     fence_mbar_init();
   }
   if (threadIdx.x < 64) cs->bias[threadIdx.x] = (MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR) ? bias[threadIdx.x] : 0.f;
   if (warp == 0) {
+    __syncwarp();
     tmem_alloc(&cs->tmem_base, 128);
     tmem_relinquish();
   }
@@ -87,7 +104,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
   const uint32_t tmem = cs->tmem_base;
 
   if (warp == 0) {
-    // ===== producer =====
+    // ===== producer: weights once, then per tile the activation slab and the aux tile(s) =====
     if (lane == 0) {
       mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
       bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);
@@ -98,6 +115,18 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         mbar_wait(&cs->empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&cs->full[s], slab_bytes);
         bulk_g2s(slabs + s * slab_bytes, in + static_cast<size_t>(tile) * TILE_M * SLAB_ROW_BYTES, slab_bytes, &cs->full[s]);
+        // staging buffer b is free once the store of tile it-2 has finished reading it
+        const int b = it & 1;
+        const uint32_t bph = (it >> 1) & 1;
+        mbar_wait(&cs->stfree[b], bph ^ 1);
+        if (mode_has_aux1(MODE)) {
+          const size_t off = (static_cast<size_t>(tile) * TILE_M + g.HALO) * SLAB_ROW_BYTES;
+          mbar_arrive_expect_tx(&cs->auxfull[b], mode_has_aux2(MODE) ? 2 * TILE_BYTES : TILE_BYTES);
+          bulk_g2s(stage1 + b * TILE_BYTES, aux1 + off, TILE_BYTES, &cs->auxfull[b]);
+          if (mode_has_aux2(MODE)) bulk_g2s(stage2 + b * TILE_BYTES, aux2 + off, TILE_BYTES, &cs->auxfull[b]);
+        } else {
+          mbar_arrive(&cs->auxfull[b]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -132,7 +161,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         umma_commit(&cs->tfull[a]);
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ===== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -141,17 +170,9 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int data_row = tile * TILE_M + row;
-      const size_t R = static_cast<size_t>(g.HALO) + data_row;
       const bool valid = slab_row_is_pixel(data_row, g);
-      uint4 x1[8], x2[8];
-      if (MODE != MODE_ELU && MODE != MODE_LINEAR) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          x1[j] = valid ? ldg_nc_u4(reinterpret_cast<const uint4*>(aux1 + slab_chunk_off(R, j))) : make_uint4(0, 0, 0, 0);
-          if (MODE == MODE_ADD_MUL)
-            x2[j] = valid ? ldg_nc_u4(reinterpret_cast<const uint4*>(aux2 + slab_chunk_off(R, j))) : make_uint4(0, 0, 0, 0);
-        }
-      }
+      uint8_t* st1 = stage1 + a * TILE_BYTES + row * SLAB_ROW_BYTES;
+      const uint8_t* st2 = stage2 + a * TILE_BYTES + row * SLAB_ROW_BYTES;
       mbar_wait(&cs->tfull[a], aph);
       tc_fence_after();
       uint32_t v[2][32];
@@ -162,8 +183,10 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&cs->tempty[a]);
+      mbar_wait(&cs->auxfull[a], aph);          // aux tile(s) landed / staging buffer free
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        const int pos = (j ^ (row & 7)) << 4;
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j >> 2][(j & 3) * 8 + e]);
@@ -174,30 +197,49 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
             o[e] = MODE == MODE_ELU ? elu_f(t) : t;
           }
         } else if (MODE == MODE_RES_ELU) {
-          float s[8];
-          unpack8(x1[j], s);
+          float sk[8];
+          unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = elu_f(o[e] + cs->bias[j * 8 + e] + s[e]);
+          for (int e = 0; e < 8; ++e) o[e] = elu_f(o[e] + cs->bias[j * 8 + e] + sk[e]);
         } else if (MODE == MODE_MUL) {
-          float s[8];
-          unpack8(x1[j], s);
+          float sk[8];
+          unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(s[e]);
+          for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(sk[e]);
         } else {
-          float s[8], t[8];
-          unpack8(x1[j], s);
-          unpack8(x2[j], t);
+          float sk[8], t[8];
+          unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
+          unpack8(*reinterpret_cast<const uint4*>(st2 + pos), t);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(s[e]);
+          for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
         }
-        const uint4 packed = valid ? pack8(o) : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(out + slab_chunk_off(R, j)) = packed;
+        *reinterpret_cast<uint4*>(st1 + pos) = valid ? pack8(o) : make_uint4(0, 0, 0, 0);
       }
+      fence_proxy_async_smem();                 // my generic-proxy writes -> visible to the bulk store
+      mbar_arrive(&cs->outready[a]);
+    }
+  } else {
+    // ===== store warp: one 16 KB bulk store per tile =====
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < g.NT; tile += gridDim.x, ++it) {
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&cs->outready[a], aph);
+        bulk_s2g(out + (static_cast<size_t>(tile) * TILE_M + g.HALO) * SLAB_ROW_BYTES, stage1 + a * TILE_BYTES, TILE_BYTES);
+        bulk_commit();
+        bulk_wait_read<0>();                    // smem has been read: the staging buffer may be refilled
+        mbar_arrive(&cs->stfree[a]);
+      }
+      bulk_wait_all<0>();
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 128);
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem, 128);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -410,8 +452,9 @@ conv_wn_bwd_kernel(const float* __restrict__ V, const float* __restrict__ gain, 
   for (int r = grp; r < K; r += 4) dv[r * 64 + co] = s_a[co] * dw[r * 64 + co] - s_b[co] * v[r * 64 + co];
 }
 
-static size_t conv_smem_bytes(const SlabGeom& g) {
-  return 1024 + W_BYTES + static_cast<size_t>(NSTAGE) * (TILE_M + 2 * g.HALO) * SLAB_ROW_BYTES + sizeof(ConvSmem) + 64;
+static size_t conv_smem_bytes(const SlabGeom& g, int mode = MODE_ADD_MUL) {
+  return 1024 + W_BYTES + static_cast<size_t>(NSTAGE) * (TILE_M + 2 * g.HALO) * SLAB_ROW_BYTES +
+         (mode_has_aux2(mode) ? 4 : 2) * TILE_BYTES + sizeof(ConvSmem) + 64;
 }
 static size_t wgrad_smem_bytes(const SlabGeom& g) {
   return 1024 + static_cast<size_t>(WG_STAGES) * ((TILE_M + 2 * g.HALO) + TILE_M) * SLAB_ROW_BYTES + ONES_BYTES +
@@ -434,7 +477,7 @@ static int num_sms() {
 template <int MODE>
 static int launch_conv(const void* in, const void* w, const float* bias, const void* a1, const void* a2, void* out,
                        const SlabGeom& g, cudaStream_t st) {
-  const size_t smem = conv_smem_bytes(g);
+  const size_t smem = conv_smem_bytes(g, MODE);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(conv3x3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -442,7 +485,7 @@ static int launch_conv(const void* in, const void* w, const float* bias, const v
   }
   const int grid = g.NT < num_sms() ? g.NT : num_sms();
   ProfSpan span(BRUNO_PROF_CONV, st);
-  conv3x3_kernel<MODE><<<grid, CONV_THREADS, smem, st>>>(
+  conv3x3_kernel<MODE><<<grid, FWD_THREADS, smem, st>>>(
       static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias, static_cast<const uint8_t*>(a1),
       static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g);
   return check_launch("conv3x3_kernel");
