@@ -45,6 +45,14 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
 }
 
+// Optional pipeline trace (debug): CTA 0 records clock64() at role events into a caller-provided device buffer
+// [tile][8]: 0 slab load issued, 1 slab landed (MMA thread), 2 MMAs issued, 3 accumulator ready (epilogue warp 2),
+// 4 epilogue math done, 5 store issued, 6 store smem-read done.
+__device__ long long* g_conv_trace = nullptr;
+__device__ __forceinline__ void trace(int it, int slot) {
+  if (g_conv_trace != nullptr && blockIdx.x == 0 && it < 64) g_conv_trace[it * 8 + slot] = clock64();
+}
+
 constexpr int FWD_THREADS = 224;             // producer, MMA issuer, 4 epilogue warps, store warp
 constexpr int TILE_BYTES = TILE_M * SLAB_ROW_BYTES;   // 16 KB: one output / aux tile
 
@@ -115,6 +123,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         mbar_wait(&cs->empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&cs->full[s], slab_bytes);
         bulk_g2s(slabs + s * slab_bytes, in + static_cast<size_t>(tile) * TILE_M * SLAB_ROW_BYTES, slab_bytes, &cs->full[s]);
+        trace(it, 0);
         // staging buffer b is free once the store of tile it-2 has finished reading it
         const int b = it & 1;
         const uint32_t bph = (it >> 1) & 1;
@@ -144,6 +153,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         mbar_wait(&cs->tempty[a], aph ^ 1);
         mbar_wait(&cs->full[s], ph);
         tc_fence_after();
+        trace(it, 1);
         const uint32_t slab_addr = smem_u32(slabs + s * slab_bytes);
         const uint32_t d_tmem = tmem + a * 64;
 #pragma unroll
@@ -159,6 +169,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         }
         umma_commit(&cs->empty[s]);
         umma_commit(&cs->tfull[a]);
+        trace(it, 2);
       }
     }
   } else if (warp < 6) {
@@ -175,6 +186,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       const uint8_t* st2 = stage2 + a * TILE_BYTES + row * SLAB_ROW_BYTES;
       mbar_wait(&cs->tfull[a], aph);
       tc_fence_after();
+      if (warp == 2 && lane == 0) trace(it, 3);
       uint32_t v[2][32];
       const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 64;
       tmem_ld32(taddr, v[0]);
@@ -216,6 +228,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         *reinterpret_cast<uint4*>(st1 + pos) = valid ? pack8(o) : make_uint4(0, 0, 0, 0);
       }
       fence_proxy_async_smem();                 // my generic-proxy writes -> visible to the bulk store
+      if (warp == 2 && lane == 0) trace(it, 4);
       mbar_arrive(&cs->outready[a]);
     }
   } else {
@@ -228,7 +241,9 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         mbar_wait(&cs->outready[a], aph);
         bulk_s2g(out + (static_cast<size_t>(tile) * TILE_M + g.HALO) * SLAB_ROW_BYTES, stage1 + a * TILE_BYTES, TILE_BYTES);
         bulk_commit();
+        trace(it, 5);
         bulk_wait_read<0>();                    // smem has been read: the staging buffer may be refilled
+        trace(it, 6);
         mbar_arrive(&cs->stfree[a]);
       }
       bulk_wait_all<0>();
@@ -503,6 +518,15 @@ size_t bruno_slab_bytes(int N, int H, int W) {
 }
 
 size_t bruno_conv_wpack_bytes(void) { return W_BYTES; }
+
+int bruno_debug_conv_trace(long long* device_buffer) {
+  cudaError_t e = cudaMemcpyToSymbol(g_conv_trace, &device_buffer, sizeof(device_buffer));
+  if (e != cudaSuccess) {
+    set_last_error("bruno_debug_conv_trace: %s", cudaGetErrorString(e));
+    return BRUNO_ECUDA;
+  }
+  return BRUNO_OK;
+}
 
 int bruno_conv_wn_pack(const float* V, const float* g, void* wfwd, void* wbwd, int L, void* stream) {
   BRUNO_REQUIRE(V && g && wfwd && L > 0, "bruno_conv_wn_pack: bad arguments");
