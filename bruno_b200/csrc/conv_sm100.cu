@@ -53,23 +53,32 @@ __device__ __forceinline__ void trace(int it, int slot) {
   if (g_conv_trace != nullptr && blockIdx.x == 0 && it < 64) g_conv_trace[it * 8 + slot] = clock64();
 }
 
-constexpr int FWD_THREADS = 224;             // producer, MMA issuer, 4 epilogue warps, store warp
-constexpr int TILE_BYTES = TILE_M * SLAB_ROW_BYTES;   // 16 KB: one output / aux tile
+constexpr int FWD_EPI_WARPS = 8;             // 2 per TMEM lane quarter: each handles 32 rows x 32 channels
+constexpr int FWD_THREADS = 32 * (2 + FWD_EPI_WARPS + 1);   // producer, MMA issuer, epilogue warps, aux/store warp
+constexpr int TILE_BYTES = TILE_M * SLAB_ROW_BYTES;          // 16 KB: one output / aux tile
 
 struct ConvSmem {
   uint64_t full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2], wbar;
-  uint64_t auxfull[2], outready[2], stfree[2];
+  uint64_t auxfull[2], outready[2];
   uint32_t tmem_base;
-  float bias[64];
 };
 
 __host__ __device__ constexpr bool mode_has_aux1(int m) { return m == MODE_RES_ELU || m == MODE_MUL || m == MODE_ADD_MUL; }
 __host__ __device__ constexpr bool mode_has_aux2(int m) { return m == MODE_ADD_MUL; }
 
-// Epilogue data path: aux tiles come in and the output tile goes out through 16 KB bulk async copies (TMA engine) staged
-// in shared memory; epilogue threads only touch shared memory (row r, 16-byte chunk j at chunk j ^ (r & 7): conflict
-// free).  Per-thread 16-byte global accesses to 32 different lines cost ~66 LSU cycles per instruction and made the
-// first version of this kernel LSU-bound at ~4200 cycles per tile (profiles/r01_launches_v0.txt).
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// ELU with one MUFU: exp(x) - 1 = 2^(x log2 e) - 1 (abs. error ~1e-7, far below the bf16 output quantum)
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : ex2_ftz(x * 1.4426950408889634f) - 1.f; }
+
+// Pipeline (measured with the clock64 trace, tools/dbg_trace.py): the first version spent ~3500 cycles per tile in a
+// 4-warp epilogue (one warp per scheduler, dependent-issue latency bound, 16-byte global accesses to 32 lines per
+// instruction) against ~1800 cycles of tensor work.  Now: 8 epilogue warps, one MUFU per ELU, all global traffic as
+// 16 KB bulk async copies staged in shared memory (row r, chunk j at chunk j ^ (r & 7): conflict free), and a
+// dedicated warp that prefetches the aux tiles / drains the output tiles so the slab producer never waits on a store.
 template <int MODE>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
@@ -84,6 +93,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
   uint8_t* stage2 = stage1 + 2 * TILE_BYTES;                           // [2][16 KB] aux2 (MODE_ADD_MUL only)
   ConvSmem* cs = reinterpret_cast<ConvSmem*>(stage2 + (mode_has_aux2(MODE) ? 2 * TILE_BYTES : 0));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr bool HAS_BIAS = MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -92,15 +102,13 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&cs->tfull[a], 1);
-      mbar_init(&cs->tempty[a], 4);
+      mbar_init(&cs->tempty[a], FWD_EPI_WARPS);
       mbar_init(&cs->auxfull[a], 1);
-      mbar_init(&cs->outready[a], 128);
-      mbar_init(&cs->stfree[a], 1);
+      mbar_init(&cs->outready[a], FWD_EPI_WARPS * 32);
     }
     mbar_init(&cs->wbar, 1);
     fence_mbar_init();
   }
-  if (threadIdx.x < 64) cs->bias[threadIdx.x] = (MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR) ? bias[threadIdx.x] : 0.f;
   if (warp == 0) {
     __syncwarp();
     tmem_alloc(&cs->tmem_base, 128);
@@ -112,7 +120,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
   const uint32_t tmem = cs->tmem_base;
 
   if (warp == 0) {
-    // ===== producer: weights once, then per tile the activation slab and the aux tile(s) =====
+    // ===== producer: weights once, then the activation slab of every tile =====
     if (lane == 0) {
       mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
       bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);
@@ -124,18 +132,6 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         mbar_arrive_expect_tx(&cs->full[s], slab_bytes);
         bulk_g2s(slabs + s * slab_bytes, in + static_cast<size_t>(tile) * TILE_M * SLAB_ROW_BYTES, slab_bytes, &cs->full[s]);
         trace(it, 0);
-        // staging buffer b is free once the store of tile it-2 has finished reading it
-        const int b = it & 1;
-        const uint32_t bph = (it >> 1) & 1;
-        mbar_wait(&cs->stfree[b], bph ^ 1);
-        if (mode_has_aux1(MODE)) {
-          const size_t off = (static_cast<size_t>(tile) * TILE_M + g.HALO) * SLAB_ROW_BYTES;
-          mbar_arrive_expect_tx(&cs->auxfull[b], mode_has_aux2(MODE) ? 2 * TILE_BYTES : TILE_BYTES);
-          bulk_g2s(stage1 + b * TILE_BYTES, aux1 + off, TILE_BYTES, &cs->auxfull[b]);
-          if (mode_has_aux2(MODE)) bulk_g2s(stage2 + b * TILE_BYTES, aux2 + off, TILE_BYTES, &cs->auxfull[b]);
-        } else {
-          mbar_arrive(&cs->auxfull[b]);
-        }
       }
     }
   } else if (warp == 1) {
@@ -143,7 +139,10 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
       mbar_wait(&cs->wbar, 0);
-      const uint32_t w_addr = smem_u32(wsm);
+      const uint64_t bdesc0 = umma_desc_sw128(smem_u32(wsm), 16, 1024);
+      uint32_t tap_off[9];                                   // (row shift of the tap) * 128 B, in 16-byte units
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>(g.HALO + (tap / 3 - 1) * g.P + (tap % 3 - 1)) * 8u;
       int it = 0;
       for (int tile = blockIdx.x; tile < g.NT; tile += gridDim.x, ++it) {
         const int s = it % NSTAGE;
@@ -154,16 +153,14 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         mbar_wait(&cs->full[s], ph);
         tc_fence_after();
         trace(it, 1);
-        const uint32_t slab_addr = smem_u32(slabs + s * slab_bytes);
+        const uint64_t adesc0 = umma_desc_sw128(smem_u32(slabs + s * slab_bytes), 16, 1024);
         const uint32_t d_tmem = tmem + a * 64;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const int row_off = g.HALO + (tap / 3 - 1) * g.P + (tap % 3 - 1);
-          const uint32_t a_base = slab_addr + row_off * SLAB_ROW_BYTES;
-          const uint32_t b_base = w_addr + tap * W_TAP_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_bf16(d_tmem, umma_desc_sw128(a_base + k * 32, 16, 1024), umma_desc_sw128(b_base + k * 32, 16, 1024),
+            // start-address field = low 14 bits of the descriptor, in 16-byte units: advance by plain addition
+            umma_bf16(d_tmem, adesc0 + (tap_off[tap] + 2u * k), bdesc0 + static_cast<uint32_t>((tap * W_TAP_BYTES + k * 32) >> 4),
                       idesc, (tap | k) != 0);
           }
         }
@@ -172,10 +169,14 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         trace(it, 2);
       }
     }
-  } else if (warp < 6) {
-    // ===== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====
+  } else if (warp < 2 + FWD_EPI_WARPS) {
+    // ===== epilogue: warp w -> TMEM lane quarter (w & 3), channel half ((w - 2) >> 2) =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    float bch[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) bch[e] = HAS_BIAS ? __ldg(bias + half * 32 + e) : 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < g.NT; tile += gridDim.x, ++it) {
       const int a = it & 1;
@@ -187,32 +188,31 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       mbar_wait(&cs->tfull[a], aph);
       tc_fence_after();
       if (warp == 2 && lane == 0) trace(it, 3);
-      uint32_t v[2][32];
-      const uint32_t taddr = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 64;
-      tmem_ld32(taddr, v[0]);
-      tmem_ld32(taddr + 32, v[1]);
+      uint32_t v[32];
+      tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 64 + half * 32, v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&cs->tempty[a]);
       mbar_wait(&cs->auxfull[a], aph);          // aux tile(s) landed / staging buffer free
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = half * 4 + jj;
         const int pos = (j ^ (row & 7)) << 4;
         float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j >> 2][(j & 3) * 8 + e]);
+        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[jj * 8 + e]);
         if (MODE == MODE_ELU || MODE == MODE_LINEAR) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float t = o[e] + cs->bias[j * 8 + e];
-            o[e] = MODE == MODE_ELU ? elu_f(t) : t;
+            const float t = o[e] + bch[jj * 8 + e];
+            o[e] = MODE == MODE_ELU ? elu_fast(t) : t;
           }
         } else if (MODE == MODE_RES_ELU) {
           float sk[8];
           unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = elu_f(o[e] + cs->bias[j * 8 + e] + sk[e]);
+          for (int e = 0; e < 8; ++e) o[e] = elu_fast(o[e] + bch[jj * 8 + e] + sk[e]);
         } else if (MODE == MODE_MUL) {
           float sk[8];
           unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
@@ -232,19 +232,34 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       mbar_arrive(&cs->outready[a]);
     }
   } else {
-    // ===== store warp: one 16 KB bulk store per tile =====
+    // ===== aux / store warp: prefetch the aux tile(s) of tile `it`, then drain the output tile of tile `it - 1` =====
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < g.NT; tile += gridDim.x, ++it) {
-        const int a = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(&cs->outready[a], aph);
-        bulk_s2g(out + (static_cast<size_t>(tile) * TILE_M + g.HALO) * SLAB_ROW_BYTES, stage1 + a * TILE_BYTES, TILE_BYTES);
-        bulk_commit();
-        trace(it, 5);
-        bulk_wait_read<0>();                    // smem has been read: the staging buffer may be refilled
-        trace(it, 6);
-        mbar_arrive(&cs->stfree[a]);
+      int prev_tile = -1;
+      for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
+        const bool live = tile < g.NT;
+        if (live) {
+          const int b = it & 1;
+          bulk_wait_read<0>();                  // store of tile it-2 (same staging buffer) has finished reading it
+          if (mode_has_aux1(MODE)) {
+            const size_t off = (static_cast<size_t>(tile) * TILE_M + g.HALO) * SLAB_ROW_BYTES;
+            mbar_arrive_expect_tx(&cs->auxfull[b], mode_has_aux2(MODE) ? 2 * TILE_BYTES : TILE_BYTES);
+            bulk_g2s(stage1 + b * TILE_BYTES, aux1 + off, TILE_BYTES, &cs->auxfull[b]);
+            if (mode_has_aux2(MODE)) bulk_g2s(stage2 + b * TILE_BYTES, aux2 + off, TILE_BYTES, &cs->auxfull[b]);
+          } else {
+            mbar_arrive(&cs->auxfull[b]);
+          }
+        }
+        if (prev_tile >= 0) {
+          const int pit = it - 1;
+          const int pa = pit & 1;
+          mbar_wait(&cs->outready[pa], (pit >> 1) & 1);
+          bulk_s2g(out + (static_cast<size_t>(prev_tile) * TILE_M + g.HALO) * SLAB_ROW_BYTES, stage1 + pa * TILE_BYTES, TILE_BYTES);
+          bulk_commit();
+          trace(pit, 5);
+        }
+        if (!live) break;
+        prev_tile = tile;
       }
       bulk_wait_all<0>();
     }
