@@ -20,13 +20,26 @@ struct GemmEpi {
   const float* a_kscale;   // A[m,k] *= a_kscale[k]             (may be null)
 };
 
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
+  const int sz = valid ? 4 : 0;   // src-size 0 -> the 4 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int GSTAGES = 4;
+
 // C[M,N] = op(A)[M,K] * op(B)[K,N];  transA: A stored [K,M];  transB: B stored [N,K].  Row-major, leading dims given.
+// 64x64x16 block tile, 4x4 register tile, 4-stage cp.async (LDGSTS) pipeline: the K loop is latency bound otherwise
+// (these GEMMs are 640 x 512 x 784: one partial wave of 80 CTAs).
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
              float* __restrict__ C, int ldc, GemmEpi ep) {
-  __shared__ float As[GK][GB + 4];
-  __shared__ float Bs[GK][GB + 4];
+  __shared__ __align__(16) float As[GSTAGES][GK][GB + 4];
+  __shared__ __align__(16) float Bs[GSTAGES][GK][GB + 4];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
   const int tx = tid & 15, ty = tid >> 4;  // thread computes rows ty*4.., cols tx*4..
@@ -36,38 +49,51 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const fl
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  const int nk = (K + GK - 1) / GK;
+  auto load_stage = [&](int kt) {
+    const int st = kt % GSTAGES;
+    const int k0 = kt * GK;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int m, k;
       if (TA) { m = tid & 63; k = (tid >> 6) + 4 * i; }
       else    { k = tid & 15; m = (tid >> 4) + 16 * i; }
-      float v = 0.f;
-      if (m0 + m < M && k0 + k < K) {
-        v = TA ? A[static_cast<size_t>(k0 + k) * lda + m0 + m] : A[static_cast<size_t>(m0 + m) * lda + k0 + k];
-        if (ep.a_kscale) v *= ep.a_kscale[k0 + k];
-      }
-      As[k][m] = v;
+      const bool va = (m0 + m < M) && (k0 + k < K);
+      const float* pa = TA ? A + static_cast<size_t>(k0 + k) * lda + m0 + m : A + static_cast<size_t>(m0 + m) * lda + k0 + k;
+      cp_async4(&As[st][k][m], va ? pa : A, va);
       int n, kb;
       if (TB) { kb = tid & 15; n = (tid >> 4) + 16 * i; }
       else    { n = tid & 63; kb = (tid >> 6) + 4 * i; }
-      float w = 0.f;
-      if (n0 + n < N && k0 + kb < K)
-        w = TB ? B[static_cast<size_t>(n0 + n) * ldb + k0 + kb] : B[static_cast<size_t>(k0 + kb) * ldb + n0 + n];
-      Bs[kb][n] = w;
+      const bool vb = (n0 + n < N) && (k0 + kb < K);
+      const float* pb = TB ? B + static_cast<size_t>(n0 + n) * ldb + k0 + kb : B + static_cast<size_t>(k0 + kb) * ldb + n0 + n;
+      cp_async4(&Bs[st][kb][n], vb ? pb : B, vb);
     }
+  };
+#pragma unroll
+  for (int s = 0; s < GSTAGES - 1; ++s) {
+    if (s < nk) load_stage(s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<GSTAGES - 2>();
     __syncthreads();
+    if (kt + GSTAGES - 1 < nk) load_stage(kt + GSTAGES - 1);
+    cp_async_commit();
+    const int st = kt % GSTAGES;
 #pragma unroll
     for (int k = 0; k < GK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float4 a = *reinterpret_cast<const float4*>(&As[st][k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[st][k][tx * 4]);
+      if (ep.a_kscale) {
+        const float sc = (kt * GK + k < K) ? __ldg(ep.a_kscale + kt * GK + k) : 0.f;
+        a.x *= sc; a.y *= sc; a.z *= sc; a.w *= sc;
+      }
       const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -104,14 +130,37 @@ __device__ __forceinline__ float dense_mask_b(int mask_type, int d) {
   return mask_type == BRUNO_MASK_EVEN ? static_cast<float>(d & 1) : static_cast<float>(1 - (d & 1));
 }
 
-// sc[j] = g[j] / ||V[:, j]||_2   (tf.norm, no epsilon: nvp:419)
-__global__ void dense_wn_scale_kernel(const float* __restrict__ V, const float* __restrict__ g, float* __restrict__ sc,
-                                      int K, int N) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
+// Column reductions: block = 32 columns x 8 row groups (256 threads); a warp reads 32 consecutive columns of one row
+// (coalesced), the 8 row groups are combined in shared memory in a fixed order (deterministic).
+__device__ __forceinline__ float col_block_reduce(float v, float (*sh)[33]) {
+  const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+  sh[r][c] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += sh[i][c];
+  __syncthreads();
+  return s;
+}
+
+// sc[j] = g[j] / ||V[:, j]||_2   (tf.norm, no epsilon: nvp:419);  inv_nrm[j] = 1 / ||V[:, j]||
+__global__ void __launch_bounds__(256)
+dense_wn_scale_kernel(const float* __restrict__ V, const float* __restrict__ g, float* __restrict__ sc,
+                      float* __restrict__ inv_nrm, int K, int N) {
+  __shared__ float sh[8][33];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   float n2 = 0.f;
-  for (int k = 0; k < K; ++k) n2 = fmaf(V[static_cast<size_t>(k) * N + j], V[static_cast<size_t>(k) * N + j], n2);
-  sc[j] = g[j] * rsqrtf(n2);
+  if (j < N)
+    for (int k = threadIdx.x >> 5; k < K; k += 8) {
+      const float t = V[static_cast<size_t>(k) * N + j];
+      n2 = fmaf(t, t, n2);
+    }
+  n2 = col_block_reduce(n2, sh);
+  if (j < N && threadIdx.x < 32) {
+    const float inv = rsqrtf(n2);
+    sc[j] = g[j] * inv;
+    if (inv_nrm) inv_nrm[j] = inv;
+  }
 }
 
 __global__ void dense_mask_mul_kernel(const float* __restrict__ x, float* __restrict__ xm, size_t total, int D, int mask_type) {
@@ -185,39 +234,41 @@ __global__ void elu_bwd_kernel(const float* __restrict__ pre, const float* __res
   dpre[i] = dh[i] * (p > 0.f ? 1.f : expf(p));
 }
 
-// out1[j] = sum_m A[m,j];  out2[j] = sum_m A[m,j] * Bm[m,j] (if Bm)      -- one thread per column (M is small)
-__global__ void col_reduce_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ out1,
-                                  float* __restrict__ out2, int M, int N) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
+// out1[j] = sum_m A[m,j];  out2[j] = sum_m A[m,j] * Bm[m,j] (if Bm)
+__global__ void __launch_bounds__(256)
+col_reduce_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ out1,
+                  float* __restrict__ out2, int M, int N) {
+  __shared__ float sh[8][33];
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   float a = 0.f, b = 0.f;
-  for (int m = 0; m < M; ++m) {
-    const float v = A[static_cast<size_t>(m) * N + j];
-    a += v;
-    if (Bm) b = fmaf(v, Bm[static_cast<size_t>(m) * N + j], b);
+  if (j < N)
+    for (int m = threadIdx.x >> 5; m < M; m += 8) {
+      const float v = A[static_cast<size_t>(m) * N + j];
+      a += v;
+      if (Bm) b = fmaf(v, Bm[static_cast<size_t>(m) * N + j], b);
+    }
+  a = col_block_reduce(a, sh);
+  if (Bm) b = col_block_reduce(b, sh);
+  if (j < N && threadIdx.x < 32) {
+    out1[j] = a;
+    if (out2) out2[j] = b;
   }
-  out1[j] = a;
-  if (out2) out2[j] = b;
 }
 
 // weight-norm backward for dense_wn.  dVraw = x^T dpre;  r1 = colsum(dpre * pre);  db = colsum(dpre).
 //   u = (pre - b)/sc  =>  dsc = (r1 - b db)/sc;  dg = dsc/nrm;  dV = dVraw sc - dsc g / nrm^3 V
-__global__ void dense_wn_bwd_kernel(const float* __restrict__ V, const float* __restrict__ g, const float* __restrict__ b,
-                                    const float* __restrict__ r1, const float* __restrict__ db, float* __restrict__ dV /*in: dVraw*/,
-                                    float* __restrict__ dg, int K, int N) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
-  float n2 = 0.f;
-  for (int k = 0; k < K; ++k) n2 = fmaf(V[static_cast<size_t>(k) * N + j], V[static_cast<size_t>(k) * N + j], n2);
-  const float inv = rsqrtf(n2);
-  const float sc = g[j] * inv;
-  const float dsc = fabsf(sc) > 1e-30f ? (r1[j] - b[j] * db[j]) / sc : 0.f;
-  dg[j] = dsc * inv;
-  const float coef = dsc * g[j] * inv * inv * inv;
-  for (int k = 0; k < K; ++k) {
-    const size_t o = static_cast<size_t>(k) * N + j;
-    dV[o] = dV[o] * sc - coef * V[o];
-  }
+// sc and inv_nrm = 1/nrm come from the forward pass.  Elementwise over [K, N] (coalesced).
+__global__ void __launch_bounds__(256)
+dense_wn_bwd_kernel(const float* __restrict__ V, const float* __restrict__ g, const float* __restrict__ b,
+                    const float* __restrict__ sc, const float* __restrict__ inv_nrm, const float* __restrict__ r1,
+                    const float* __restrict__ db, float* __restrict__ dV /*in: dVraw*/, float* __restrict__ dg, int K, int N) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(K) * N) return;
+  const int j = static_cast<int>(i % N);
+  const float s_ = sc[j], inv = inv_nrm[j];
+  const float dsc = fabsf(s_) > 1e-30f ? (r1[j] - b[j] * db[j]) / s_ : 0.f;
+  if (i < static_cast<size_t>(N)) dg[j] = dsc * inv;
+  dV[i] = dV[i] * s_ - dsc * g[j] * inv * inv * inv * V[i];
 }
 
 __global__ void masked_accumulate_kernel(float* __restrict__ dx, const float* __restrict__ dxm, size_t total, int D, int mask_type) {
@@ -228,13 +279,13 @@ __global__ void masked_accumulate_kernel(float* __restrict__ dx, const float* __
 static inline unsigned nblk(size_t total) { return static_cast<unsigned>((total + 255) / 256); }
 
 struct DenseWs {
-  float *sc1, *sc2, *xm, *pre1, *pre2, *h1, *h2, *s_pre, *t_pre;
+  float *sc1, *sc2, *in1, *in2, *xm, *pre1, *pre2, *h1, *h2, *s_pre, *t_pre;
 };
 static DenseWs carve(float* ws, int N, int D, int U) {
   DenseWs w;
   size_t o = 0;
   auto take = [&](size_t n) { float* p = ws + o; o += (n + 3) / 4 * 4; return p; };
-  w.sc1 = take(U); w.sc2 = take(U);
+  w.sc1 = take(U); w.sc2 = take(U); w.in1 = take(U); w.in2 = take(U);
   w.xm = take(static_cast<size_t>(N) * D);
   w.pre1 = take(static_cast<size_t>(N) * U); w.pre2 = take(static_cast<size_t>(N) * U);
   w.h1 = take(static_cast<size_t>(N) * U); w.h2 = take(static_cast<size_t>(N) * U);
@@ -249,7 +300,7 @@ using namespace bruno;
 extern "C" {
 
 size_t bruno_coupling_dense_ws_floats(int N, int D, int U) {
-  return 2 * (static_cast<size_t>(U) + 4) + 3 * (static_cast<size_t>(N) * D + 4) + 4 * (static_cast<size_t>(N) * U + 4);
+  return 4 * (static_cast<size_t>(U) + 4) + 3 * (static_cast<size_t>(N) * D + 4) + 4 * (static_cast<size_t>(N) * U + 4);
 }
 size_t bruno_coupling_dense_bwd_ws_floats(int N, int D, int U) {
   return 3 * (static_cast<size_t>(N) * D + 4) + 2 * (static_cast<size_t>(N) * U + 4) + 4 * (static_cast<size_t>(U) + 4);
@@ -273,8 +324,8 @@ int bruno_coupling_dense_fwd(const float* x, const float* ld_in, float* y, float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DenseWs w = carve(ws, N, D, U);
   const size_t ND = static_cast<size_t>(N) * D;
-  dense_wn_scale_kernel<<<ceil_div(U, 128), 128, 0, st>>>(V1, g1, w.sc1, D, U);
-  dense_wn_scale_kernel<<<ceil_div(U, 128), 128, 0, st>>>(V2, g2, w.sc2, U, U);
+  dense_wn_scale_kernel<<<ceil_div(U, 32), 256, 0, st>>>(V1, g1, w.sc1, w.in1, D, U);
+  dense_wn_scale_kernel<<<ceil_div(U, 32), 256, 0, st>>>(V2, g2, w.sc2, w.in2, U, U);
   dense_mask_mul_kernel<<<nblk(ND), 256, 0, st>>>(x, w.xm, ND, D, mask_type);
   int rc;
   if ((rc = gemm(false, false, N, U, D, w.xm, D, V1, U, w.h1, U, GemmEpi{w.sc1, b1, w.pre1, 1, 0, nullptr}, st))) return rc;
@@ -310,15 +361,15 @@ int bruno_coupling_dense_bwd(const float* x, const float* dy, const float* dld, 
   // heads
   if ((rc = gemm(true, false, U, D, N, w.h2, U, ds_pre, D, dKs, D, plain, st))) return rc;
   if ((rc = gemm(true, false, U, D, N, w.h2, U, dt_pre, D, dKt, D, plain, st))) return rc;
-  col_reduce_kernel<<<ceil_div(D, 128), 128, 0, st>>>(ds_pre, nullptr, dbs, nullptr, N, D);
-  col_reduce_kernel<<<ceil_div(D, 128), 128, 0, st>>>(dt_pre, nullptr, dbt, nullptr, N, D);
+  col_reduce_kernel<<<ceil_div(D, 32), 256, 0, st>>>(ds_pre, nullptr, dbs, nullptr, N, D);
+  col_reduce_kernel<<<ceil_div(D, 32), 256, 0, st>>>(dt_pre, nullptr, dbt, nullptr, N, D);
   if ((rc = gemm(false, true, N, U, D, ds_pre, D, Ks, D, dh, U, plain, st))) return rc;
   if ((rc = gemm(false, true, N, U, D, dt_pre, D, Kt, D, dh, U, accum, st))) return rc;
   // d2
   elu_bwd_kernel<<<nblk(NU), 256, 0, st>>>(w.pre2, dh, dpre, NU);
-  col_reduce_kernel<<<ceil_div(U, 128), 128, 0, st>>>(dpre, w.pre2, db2, r1, N, U);
+  col_reduce_kernel<<<ceil_div(U, 32), 256, 0, st>>>(dpre, w.pre2, db2, r1, N, U);
   if ((rc = gemm(true, false, U, U, N, w.h1, U, dpre, U, dV2, U, plain, st))) return rc;
-  dense_wn_bwd_kernel<<<ceil_div(U, 128), 128, 0, st>>>(V2, g2, b2, r1, db2, dV2, dg2, U, U);
+  dense_wn_bwd_kernel<<<nblk(static_cast<size_t>(U) * U), 256, 0, st>>>(V2, g2, b2, w.sc2, w.in2, r1, db2, dV2, dg2, U, U);
   {
     GemmEpi e = plain;
     e.a_kscale = w.sc2;
@@ -326,9 +377,9 @@ int bruno_coupling_dense_bwd(const float* x, const float* dy, const float* dld, 
   }
   // d1
   elu_bwd_kernel<<<nblk(NU), 256, 0, st>>>(w.pre1, dh, dpre, NU);
-  col_reduce_kernel<<<ceil_div(U, 128), 128, 0, st>>>(dpre, w.pre1, db1, r1, N, U);
+  col_reduce_kernel<<<ceil_div(U, 32), 256, 0, st>>>(dpre, w.pre1, db1, r1, N, U);
   if ((rc = gemm(true, false, D, U, N, w.xm, D, dpre, U, dV1, U, plain, st))) return rc;
-  dense_wn_bwd_kernel<<<ceil_div(U, 128), 128, 0, st>>>(V1, g1, b1, r1, db1, dV1, dg1, D, U);
+  dense_wn_bwd_kernel<<<nblk(static_cast<size_t>(D) * U), 256, 0, st>>>(V1, g1, b1, w.sc1, w.in1, r1, db1, dV1, dg1, D, U);
   {
     GemmEpi e = plain;
     e.a_kscale = w.sc1;

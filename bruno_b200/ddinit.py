@@ -57,7 +57,7 @@ def _dense_ws_offsets(N, D, U):
     def r4(n):
         return (n + 3) // 4 * 4
     o, out = 0, {}
-    for name, n in (('sc1', U), ('sc2', U), ('xm', N * D), ('pre1', N * U), ('pre2', N * U), ('h1', N * U), ('h2', N * U),
+    for name, n in (('sc1', U), ('sc2', U), ('in1', U), ('in2', U), ('xm', N * D), ('pre1', N * U), ('pre2', N * U), ('h1', N * U), ('h2', N * U),
                     ('s_pre', N * D), ('t_pre', N * D)):
         out[name] = (o, n)
         o += r4(n)
