@@ -55,12 +55,17 @@ __device__ __forceinline__ void trace(int it, int slot) {
 
 constexpr int FWD_EPI_WARPS = 8;             // 2 per TMEM lane quarter: each handles 32 rows x 32 channels
 constexpr int FWD_THREADS = 32 * (2 + FWD_EPI_WARPS + 1);   // producer, MMA issuer, epilogue warps, aux/store warp
-constexpr int TILE_BYTES = TILE_M * SLAB_ROW_BYTES;          // 16 KB: one output / aux tile
+constexpr int TILE_BYTES = TILE_M * SLAB_ROW_BYTES;          // 16 KB: one aux / gradient tile of the wgrad kernel
+constexpr int OUT_ROWS = 126;                // output rows per tile of the dx-fused forward kernel (see below)
+constexpr int STG_ROWS = 136;                // staging rows: 126 + up to 7 rows of 8-row phase alignment, rounded
+constexpr int STG_BYTES = STG_ROWS * SLAB_ROW_BYTES;
+constexpr int OUT_BYTES = OUT_ROWS * SLAB_ROW_BYTES;
 
 struct ConvSmem {
   uint64_t full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2], wbar;
   uint64_t auxfull[2], outready[2];
   uint32_t tmem_base;
+  float xch[2][2][4][2][32];   // [tile parity][dx block 0 / 2][lane quarter][channel half][32 channels]
 };
 
 __host__ __device__ constexpr bool mode_has_aux1(int m) { return m == MODE_RES_ELU || m == MODE_MUL || m == MODE_ADD_MUL; }
@@ -74,24 +79,32 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // ELU with one MUFU: exp(x) - 1 = 2^(x log2 e) - 1 (abs. error ~1e-7, far below the bf16 output quantum)
 __device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : ex2_ftz(x * 1.4426950408889634f) - 1.f; }
 
-// Pipeline (measured with the clock64 trace, tools/dbg_trace.py): the first version spent ~3500 cycles per tile in a
-// 4-warp epilogue (one warp per scheduler, dependent-issue latency bound, 16-byte global accesses to 32 lines per
-// instruction) against ~1800 cycles of tensor work.  Now: 8 epilogue warps, one MUFU per ELU, all global traffic as
-// 16 KB bulk async copies staged in shared memory (row r, chunk j at chunk j ^ (r & 7): conflict free), and a
-// dedicated warp that prefetches the aux tiles / drains the output tiles so the slab producer never waits on a store.
+// ---- dx-fused implicit GEMM --------------------------------------------------------------------------------------
+// A 64 -> 64 convolution issued as nine M=128, N=64 MMAs per K step reads 6 KB of shared memory per 128x64x16 MMA and is
+// bound by the 128 B/clk shared-memory port at 49 cycles per MMA = 65 % of the tensor peak (tools/umma_bench.cu).
+// Instead, for each vertical tap dy ONE MMA with N = 192 computes the three horizontal taps at once from the SAME
+// activation rows:   E_dx[q] = sum_dy in[q + dy P] W[dy, dx]      (D[q][dx*64 + co], 12 MMAs of N = 192 per tile,
+// 10 KB of shared memory per 128x192x16 MMA = 96 cycles = tensor-bound), and the epilogue applies the horizontal shift
+//                    out[p] = E_-1[p - 1] + E_0[p] + E_+1[p + 1]
+// with one warp shuffle per value (neighbouring positions are neighbouring TMEM lanes = neighbouring threads); the two
+// boundary lanes of every warp are exchanged through shared memory, and consecutive tiles overlap by two rows
+// (128 computed rows, 126 stored) so no value is ever needed from another tile.
+// Warp roles: 0 slab producer, 1 MMA issuer, 2..9 epilogue, 10 aux prefetch / output drain; all global traffic is bulk
+// async copies (TMA engine); TMEM accumulators (2 x 192 columns) are double buffered.
 template <int MODE>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
                const uint8_t* __restrict__ aux1, const uint8_t* __restrict__ aux2, uint8_t* __restrict__ out,
-               SlabGeom g) {
+               SlabGeom g, int ntiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const uint32_t slab_bytes = static_cast<uint32_t>(TILE_M + 2 * g.HALO) * SLAB_ROW_BYTES;
+  const int slab_rows = TILE_M + 2 * g.HALO + 8;
+  const uint32_t slab_bytes = static_cast<uint32_t>(slab_rows) * SLAB_ROW_BYTES;
   uint8_t* wsm = smem;
   uint8_t* slabs = smem + W_BYTES;
-  uint8_t* stage1 = slabs + NSTAGE * slab_bytes;                       // [2][16 KB] aux1 in / output out (in place)
-  uint8_t* stage2 = stage1 + 2 * TILE_BYTES;                           // [2][16 KB] aux2 (MODE_ADD_MUL only)
-  ConvSmem* cs = reinterpret_cast<ConvSmem*>(stage2 + (mode_has_aux2(MODE) ? 2 * TILE_BYTES : 0));
+  uint8_t* stage1 = slabs + NSTAGE * slab_bytes;                       // [2][STG_BYTES] aux1 in / output out (in place)
+  uint8_t* stage2 = stage1 + 2 * STG_BYTES;                            // [2][STG_BYTES] aux2 (MODE_ADD_MUL only)
+  ConvSmem* cs = reinterpret_cast<ConvSmem*>(stage2 + (mode_has_aux2(MODE) ? 2 * STG_BYTES : 0));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool HAS_BIAS = MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR;
 
@@ -111,7 +124,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
   }
   if (warp == 0) {
     __syncwarp();
-    tmem_alloc(&cs->tmem_base, 128);
+    tmem_alloc(&cs->tmem_base, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -119,49 +132,52 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
   tc_fence_after();
   const uint32_t tmem = cs->tmem_base;
 
+  // geometry of tile t: computed rows = data rows [126 t - 1, 126 t + 127); stored rows = data rows [126 t, 126 t + 126)
+  //   first computed buffer row  Rc = HALO + 126 t - 1;  slab load starts at LS = floor8(Rc - P)
+  //   first stored buffer row    Rf = HALO + 126 t;      staging row 0 <-> buffer row RB = floor8(Rf)
   if (warp == 0) {
     // ===== producer: weights once, then the activation slab of every tile =====
     if (lane == 0) {
       mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
       bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);
       int it = 0;
-      for (int tile = blockIdx.x; tile < g.NT; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
+        const int LS = (g.HALO + OUT_ROWS * tile - 1 - g.P) & ~7;
         mbar_wait(&cs->empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&cs->full[s], slab_bytes);
-        bulk_g2s(slabs + s * slab_bytes, in + static_cast<size_t>(tile) * TILE_M * SLAB_ROW_BYTES, slab_bytes, &cs->full[s]);
+        bulk_g2s(slabs + s * slab_bytes, in + static_cast<size_t>(LS) * SLAB_ROW_BYTES, slab_bytes, &cs->full[s]);
         trace(it, 0);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: 3 vertical taps x 4 K steps, N = 192 =====
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 192, 0, 0);
       mbar_wait(&cs->wbar, 0);
       const uint64_t bdesc0 = umma_desc_sw128(smem_u32(wsm), 16, 1024);
-      uint32_t tap_off[9];                                   // (row shift of the tap) * 128 B, in 16-byte units
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>(g.HALO + (tap / 3 - 1) * g.P + (tap % 3 - 1)) * 8u;
       int it = 0;
-      for (int tile = blockIdx.x; tile < g.NT; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % NSTAGE;
         const uint32_t ph = (it / NSTAGE) & 1;
         const int a = it & 1;
         const uint32_t aph = (it >> 1) & 1;
+        const int Rc = g.HALO + OUT_ROWS * tile - 1;
+        const int LS = (Rc - g.P) & ~7;
         mbar_wait(&cs->tempty[a], aph ^ 1);
         mbar_wait(&cs->full[s], ph);
         tc_fence_after();
         trace(it, 1);
         const uint64_t adesc0 = umma_desc_sw128(smem_u32(slabs + s * slab_bytes), 16, 1024);
-        const uint32_t d_tmem = tmem + a * 64;
+        const uint32_t d_tmem = tmem + a * 256;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int dy = 0; dy < 3; ++dy) {
+          const uint32_t a_off = static_cast<uint32_t>(Rc + (dy - 1) * g.P - LS) * 8u;   // rows * 128 B, in 16-byte units
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            // start-address field = low 14 bits of the descriptor, in 16-byte units: advance by plain addition
-            umma_bf16(d_tmem, adesc0 + (tap_off[tap] + 2u * k), bdesc0 + static_cast<uint32_t>((tap * W_TAP_BYTES + k * 32) >> 4),
-                      idesc, (tap | k) != 0);
+            umma_bf16(d_tmem, adesc0 + (a_off + 2u * k), bdesc0 + static_cast<uint32_t>((dy * 3 * W_TAP_BYTES + k * 32) >> 4),
+                      idesc, (dy | k) != 0);
           }
         }
         umma_commit(&cs->empty[s]);
@@ -173,59 +189,96 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
     // ===== epilogue: warp w -> TMEM lane quarter (w & 3), channel half ((w - 2) >> 2) =====
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int row = q * 32 + lane;
+    const int row = q * 32 + lane;              // computed row inside the tile (0..127); rows 1..126 are stored
     float bch[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) bch[e] = HAS_BIAS ? __ldg(bias + half * 32 + e) : 0.f;
     int it = 0;
-    for (int tile = blockIdx.x; tile < g.NT; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      const int data_row = tile * TILE_M + row;
-      const bool valid = slab_row_is_pixel(data_row, g);
-      uint8_t* st1 = stage1 + a * TILE_BYTES + row * SLAB_ROW_BYTES;
-      const uint8_t* st2 = stage2 + a * TILE_BYTES + row * SLAB_ROW_BYTES;
+      const int data_row = OUT_ROWS * tile - 1 + row;
+      const bool stored = row >= 1 && row <= OUT_ROWS;
+      const bool valid = stored && data_row >= 0 && slab_row_is_pixel(data_row, g);
+      const int Rf = g.HALO + OUT_ROWS * tile;
+      const int srow = (Rf & 7) + row - 1;      // staging row (only meaningful when stored)
+      const int R7 = (g.HALO + data_row) & 7;   // swizzle phase of the buffer row
+      uint8_t* st1 = stage1 + a * STG_BYTES + srow * SLAB_ROW_BYTES;
+      const uint8_t* st2 = stage2 + a * STG_BYTES + srow * SLAB_ROW_BYTES;
       mbar_wait(&cs->tfull[a], aph);
       tc_fence_after();
       if (warp == 2 && lane == 0) trace(it, 3);
-      uint32_t v[32];
-      tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 64 + half * 32, v);
-      tmem_ld_wait();
+      const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 256 + half * 32;
+      float acc[32];
+      // pass 1: own-row term E_0 ... plus the shuffled neighbours; boundary lanes publish their values first
+      float* xw0 = cs->xch[a][0][q][half];      // my E_-1 block (dx = -1), needed by row + 1 -> written by lane 31
+      float* xw2 = cs->xch[a][1][q][half];      // my E_+1 block (dx = +1), needed by row - 1 -> written by lane 0
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t e0[8], e1[8], e2[8];
+        tmem_ld8(tbase + 0 * 64 + c * 8, e0);
+        tmem_ld8(tbase + 1 * 64 + c * 8, e1);
+        tmem_ld8(tbase + 2 * 64 + c * 8, e2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float f0 = __uint_as_float(e0[e]), f2 = __uint_as_float(e2[e]);
+          if (lane == 31) xw0[c * 8 + e] = f0;
+          if (lane == 0) xw2[c * 8 + e] = f2;
+          const float up = __shfl_up_sync(0xffffffffu, f0, 1);      // E_-1 of row - 1
+          const float dn = __shfl_down_sync(0xffffffffu, f2, 1);    // E_+1 of row + 1
+          acc[c * 8 + e] = __uint_as_float(e1[e]) + (lane > 0 ? up : 0.f) + (lane < 31 ? dn : 0.f);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&cs->tempty[a]);
+      // boundary exchange between the four lane quarters (same channel half)
+      asm volatile("bar.sync 1, %0;" ::"n"(FWD_EPI_WARPS * 32) : "memory");
+      if (lane == 0 && q > 0) {
+        const float* xr = cs->xch[a][0][q - 1][half];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] += xr[e];
+      }
+      if (lane == 31 && q < 3) {
+        const float* xr = cs->xch[a][1][q + 1][half];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] += xr[e];
+      }
       mbar_wait(&cs->auxfull[a], aph);          // aux tile(s) landed / staging buffer free
+      if (stored) {
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = half * 4 + jj;
-        const int pos = (j ^ (row & 7)) << 4;
-        float o[8];
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = half * 4 + jj;
+          const int pos = (j ^ R7) << 4;
+          float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[jj * 8 + e]);
-        if (MODE == MODE_ELU || MODE == MODE_LINEAR) {
+          for (int e = 0; e < 8; ++e) o[e] = acc[jj * 8 + e];
+          if (MODE == MODE_ELU || MODE == MODE_LINEAR) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float t = o[e] + bch[jj * 8 + e];
-            o[e] = MODE == MODE_ELU ? elu_fast(t) : t;
+            for (int e = 0; e < 8; ++e) {
+              const float t = o[e] + bch[jj * 8 + e];
+              o[e] = MODE == MODE_ELU ? elu_fast(t) : t;
+            }
+          } else if (MODE == MODE_RES_ELU) {
+            float sk[8];
+            unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = elu_fast(o[e] + bch[jj * 8 + e] + sk[e]);
+          } else if (MODE == MODE_MUL) {
+            float sk[8];
+            unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(sk[e]);
+          } else {
+            float sk[8], t[8];
+            unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
+            unpack8(*reinterpret_cast<const uint4*>(st2 + pos), t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
           }
-        } else if (MODE == MODE_RES_ELU) {
-          float sk[8];
-          unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = elu_fast(o[e] + bch[jj * 8 + e] + sk[e]);
-        } else if (MODE == MODE_MUL) {
-          float sk[8];
-          unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(sk[e]);
-        } else {
-          float sk[8], t[8];
-          unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
-          unpack8(*reinterpret_cast<const uint4*>(st2 + pos), t);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
+          *reinterpret_cast<uint4*>(st1 + pos) = valid ? pack8(o) : make_uint4(0, 0, 0, 0);
         }
-        *reinterpret_cast<uint4*>(st1 + pos) = valid ? pack8(o) : make_uint4(0, 0, 0, 0);
       }
       fence_proxy_async_smem();                 // my generic-proxy writes -> visible to the bulk store
       if (warp == 2 && lane == 0) trace(it, 4);
@@ -237,15 +290,17 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       int it = 0;
       int prev_tile = -1;
       for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
-        const bool live = tile < g.NT;
+        const bool live = tile < ntiles;
         if (live) {
           const int b = it & 1;
+          const int Rf = g.HALO + OUT_ROWS * tile;
           bulk_wait_read<0>();                  // store of tile it-2 (same staging buffer) has finished reading it
           if (mode_has_aux1(MODE)) {
-            const size_t off = (static_cast<size_t>(tile) * TILE_M + g.HALO) * SLAB_ROW_BYTES;
-            mbar_arrive_expect_tx(&cs->auxfull[b], mode_has_aux2(MODE) ? 2 * TILE_BYTES : TILE_BYTES);
-            bulk_g2s(stage1 + b * TILE_BYTES, aux1 + off, TILE_BYTES, &cs->auxfull[b]);
-            if (mode_has_aux2(MODE)) bulk_g2s(stage2 + b * TILE_BYTES, aux2 + off, TILE_BYTES, &cs->auxfull[b]);
+            const size_t off = static_cast<size_t>(Rf) * SLAB_ROW_BYTES;
+            const uint32_t soff = static_cast<uint32_t>(Rf & 7) * SLAB_ROW_BYTES;
+            mbar_arrive_expect_tx(&cs->auxfull[b], mode_has_aux2(MODE) ? 2 * OUT_BYTES : OUT_BYTES);
+            bulk_g2s(stage1 + b * STG_BYTES + soff, aux1 + off, OUT_BYTES, &cs->auxfull[b]);
+            if (mode_has_aux2(MODE)) bulk_g2s(stage2 + b * STG_BYTES + soff, aux2 + off, OUT_BYTES, &cs->auxfull[b]);
           } else {
             mbar_arrive(&cs->auxfull[b]);
           }
@@ -253,8 +308,9 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         if (prev_tile >= 0) {
           const int pit = it - 1;
           const int pa = pit & 1;
+          const int Rf = g.HALO + OUT_ROWS * prev_tile;
           mbar_wait(&cs->outready[pa], (pit >> 1) & 1);
-          bulk_s2g(out + (static_cast<size_t>(prev_tile) * TILE_M + g.HALO) * SLAB_ROW_BYTES, stage1 + pa * TILE_BYTES, TILE_BYTES);
+          bulk_s2g(out + static_cast<size_t>(Rf) * SLAB_ROW_BYTES, stage1 + pa * STG_BYTES + (Rf & 7) * SLAB_ROW_BYTES, OUT_BYTES);
           bulk_commit();
           trace(pit, 5);
         }
@@ -268,7 +324,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
   __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc(tmem, 128);
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -483,8 +539,8 @@ conv_wn_bwd_kernel(const float* __restrict__ V, const float* __restrict__ gain, 
 }
 
 static size_t conv_smem_bytes(const SlabGeom& g, int mode = MODE_ADD_MUL) {
-  return 1024 + W_BYTES + static_cast<size_t>(NSTAGE) * (TILE_M + 2 * g.HALO) * SLAB_ROW_BYTES +
-         (mode_has_aux2(mode) ? 4 : 2) * TILE_BYTES + sizeof(ConvSmem) + 64;
+  return 1024 + W_BYTES + static_cast<size_t>(NSTAGE) * (TILE_M + 2 * g.HALO + 8) * SLAB_ROW_BYTES +
+         (mode_has_aux2(mode) ? 4 : 2) * STG_BYTES + sizeof(ConvSmem) + 64;
 }
 static size_t wgrad_smem_bytes(const SlabGeom& g) {
   return 1024 + static_cast<size_t>(WG_STAGES) * ((TILE_M + 2 * g.HALO) + TILE_M) * SLAB_ROW_BYTES + ONES_BYTES +
@@ -513,11 +569,12 @@ static int launch_conv(const void* in, const void* w, const float* bias, const v
     cudaFuncSetAttribute(conv3x3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured = true;
   }
-  const int grid = g.NT < num_sms() ? g.NT : num_sms();
+  const int ntiles = (g.data_rows + OUT_ROWS - 1) / OUT_ROWS;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
   ProfSpan span(BRUNO_PROF_CONV, st);
   conv3x3_kernel<MODE><<<grid, FWD_THREADS, smem, st>>>(
       static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias, static_cast<const uint8_t*>(a1),
-      static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g);
+      static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g, ntiles);
   return check_launch("conv3x3_kernel");
 }
 

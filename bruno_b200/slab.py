@@ -16,7 +16,7 @@ class SlabGeom(object):
         self.HALO = ((self.P + 1 + 7) // 8) * 8
         self.data_rows = N * self.IMG
         self.NT = (self.data_rows + TILE_M - 1) // TILE_M
-        self.rows = self.NT * TILE_M + 2 * self.HALO
+        self.rows = (self.NT + 2) * TILE_M + 2 * self.HALO
 
     @property
     def nbytes(self):
