@@ -65,7 +65,7 @@ struct ConvSmem {
   uint64_t full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2], wbar;
   uint64_t auxfull[2], outready[2];
   uint32_t tmem_base;
-  float xch[2][2][4][2][32];   // [tile parity][dx block 0 / 2][lane quarter][channel half][32 channels]
+  alignas(16) float xch[2][2][4][2][32];   // [tile parity][dx block 0 / 2][lane quarter][channel half][32 channels]
 };
 
 __host__ __device__ constexpr bool mode_has_aux1(int m) { return m == MODE_RES_ELU || m == MODE_MUL || m == MODE_ADD_MUL; }
@@ -210,24 +210,37 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       if (warp == 2 && lane == 0) trace(it, 3);
       const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 256 + half * 32;
       float acc[32];
-      // pass 1: own-row term E_0 ... plus the shuffled neighbours; boundary lanes publish their values first
-      float* xw0 = cs->xch[a][0][q][half];      // my E_-1 block (dx = -1), needed by row + 1 -> written by lane 31
-      float* xw2 = cs->xch[a][1][q][half];      // my E_+1 block (dx = +1), needed by row - 1 -> written by lane 0
+      // E_0 of the own row plus the two shuffled neighbours; the boundary lanes of the warp publish the values their
+      // neighbours in the adjacent lane quarter need (vector stores, 2 per 8-channel chunk).  TMEM loads are software
+      // pipelined one chunk ahead.
+      float* xw0 = cs->xch[a][0][q][half];      // my dx = -1 block, needed by row + 1 -> written by lane 31
+      float* xw2 = cs->xch[a][1][q][half];      // my dx = +1 block, needed by row - 1 -> written by lane 0
+      uint32_t e0[2][8], e1[2][8], e2[2][8];
+      tmem_ld8(tbase + 0 * 64, e0[0]);
+      tmem_ld8(tbase + 1 * 64, e1[0]);
+      tmem_ld8(tbase + 2 * 64, e2[0]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t e0[8], e1[8], e2[8];
-        tmem_ld8(tbase + 0 * 64 + c * 8, e0);
-        tmem_ld8(tbase + 1 * 64 + c * 8, e1);
-        tmem_ld8(tbase + 2 * 64 + c * 8, e2);
+        const int cur = c & 1, nxt = cur ^ 1;
         tmem_ld_wait();
+        if (c < 3) {
+          tmem_ld8(tbase + 0 * 64 + (c + 1) * 8, e0[nxt]);
+          tmem_ld8(tbase + 1 * 64 + (c + 1) * 8, e1[nxt]);
+          tmem_ld8(tbase + 2 * 64 + (c + 1) * 8, e2[nxt]);
+        }
+        if (lane == 31) {
+          *reinterpret_cast<uint4*>(xw0 + c * 8) = make_uint4(e0[cur][0], e0[cur][1], e0[cur][2], e0[cur][3]);
+          *reinterpret_cast<uint4*>(xw0 + c * 8 + 4) = make_uint4(e0[cur][4], e0[cur][5], e0[cur][6], e0[cur][7]);
+        }
+        if (lane == 0) {
+          *reinterpret_cast<uint4*>(xw2 + c * 8) = make_uint4(e2[cur][0], e2[cur][1], e2[cur][2], e2[cur][3]);
+          *reinterpret_cast<uint4*>(xw2 + c * 8 + 4) = make_uint4(e2[cur][4], e2[cur][5], e2[cur][6], e2[cur][7]);
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float f0 = __uint_as_float(e0[e]), f2 = __uint_as_float(e2[e]);
-          if (lane == 31) xw0[c * 8 + e] = f0;
-          if (lane == 0) xw2[c * 8 + e] = f2;
-          const float up = __shfl_up_sync(0xffffffffu, f0, 1);      // E_-1 of row - 1
-          const float dn = __shfl_down_sync(0xffffffffu, f2, 1);    // E_+1 of row + 1
-          acc[c * 8 + e] = __uint_as_float(e1[e]) + (lane > 0 ? up : 0.f) + (lane < 31 ? dn : 0.f);
+          const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[cur][e]), 1);      // dx = -1 term of row - 1
+          const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[cur][e]), 1);    // dx = +1 term of row + 1
+          acc[c * 8 + e] = __uint_as_float(e1[cur][e]) + (lane > 0 ? up : 0.f) + (lane < 31 ? dn : 0.f);
         }
       }
       tc_fence_before();
@@ -235,15 +248,13 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       if (lane == 0) mbar_arrive(&cs->tempty[a]);
       // boundary exchange between the four lane quarters (same channel half)
       asm volatile("bar.sync 1, %0;" ::"n"(FWD_EPI_WARPS * 32) : "memory");
-      if (lane == 0 && q > 0) {
-        const float* xr = cs->xch[a][0][q - 1][half];
+      if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
+        const float4* xr = reinterpret_cast<const float4*>(lane == 0 ? cs->xch[a][0][q - 1][half] : cs->xch[a][1][q + 1][half]);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] += xr[e];
-      }
-      if (lane == 31 && q < 3) {
-        const float* xr = cs->xch[a][1][q + 1][half];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] += xr[e];
+        for (int e = 0; e < 8; ++e) {
+          const float4 t = xr[e];
+          acc[4 * e] += t.x; acc[4 * e + 1] += t.y; acc[4 * e + 2] += t.z; acc[4 * e + 3] += t.w;
+        }
       }
       mbar_wait(&cs->auxfull[a], aph);          // aux tile(s) landed / staging buffer free
       if (stored) {
