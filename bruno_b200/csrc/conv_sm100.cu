@@ -203,8 +203,8 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       const int Rf = g.HALO + OUT_ROWS * tile;
       const int srow = (Rf & 7) + row - 1;      // staging row (only meaningful when stored)
       const int R7 = (g.HALO + data_row) & 7;   // swizzle phase of the buffer row
-      uint8_t* st1 = stage1 + a * STG_BYTES + srow * SLAB_ROW_BYTES;
-      const uint8_t* st2 = stage2 + a * STG_BYTES + srow * SLAB_ROW_BYTES;
+      const uint32_t st1 = smem_u32(stage1 + a * STG_BYTES + srow * SLAB_ROW_BYTES);
+      const uint32_t st2 = smem_u32(stage2 + a * STG_BYTES + srow * SLAB_ROW_BYTES);
       mbar_wait(&cs->tfull[a], aph);
       tc_fence_after();
       if (warp == 2 && lane == 0) trace(it, 3);
@@ -213,8 +213,9 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       // E_0 of the own row plus the two shuffled neighbours; the boundary lanes of the warp publish the values their
       // neighbours in the adjacent lane quarter need (vector stores, 2 per 8-channel chunk).  TMEM loads are software
       // pipelined one chunk ahead.
-      float* xw0 = cs->xch[a][0][q][half];      // my dx = -1 block, needed by row + 1 -> written by lane 31
-      float* xw2 = cs->xch[a][1][q][half];      // my dx = +1 block, needed by row - 1 -> written by lane 0
+      const uint32_t xw0 = smem_u32(cs->xch[a][0][q][half]);   // my dx = -1 block, needed by row + 1 -> written by lane 31
+      const uint32_t xw2 = smem_u32(cs->xch[a][1][q][half]);   // my dx = +1 block, needed by row - 1 -> written by lane 0
+      const float m_up = lane > 0 ? 1.f : 0.f, m_dn = lane < 31 ? 1.f : 0.f;   // warp-edge lanes get theirs via smem
       uint32_t e0[2][8], e1[2][8], e2[2][8];
       tmem_ld8(tbase + 0 * 64, e0[0]);
       tmem_ld8(tbase + 1 * 64, e1[0]);
@@ -229,18 +230,18 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
           tmem_ld8(tbase + 2 * 64 + (c + 1) * 8, e2[nxt]);
         }
         if (lane == 31) {
-          *reinterpret_cast<uint4*>(xw0 + c * 8) = make_uint4(e0[cur][0], e0[cur][1], e0[cur][2], e0[cur][3]);
-          *reinterpret_cast<uint4*>(xw0 + c * 8 + 4) = make_uint4(e0[cur][4], e0[cur][5], e0[cur][6], e0[cur][7]);
+          sts_u4(xw0 + c * 32, make_uint4(e0[cur][0], e0[cur][1], e0[cur][2], e0[cur][3]));
+          sts_u4(xw0 + c * 32 + 16, make_uint4(e0[cur][4], e0[cur][5], e0[cur][6], e0[cur][7]));
         }
         if (lane == 0) {
-          *reinterpret_cast<uint4*>(xw2 + c * 8) = make_uint4(e2[cur][0], e2[cur][1], e2[cur][2], e2[cur][3]);
-          *reinterpret_cast<uint4*>(xw2 + c * 8 + 4) = make_uint4(e2[cur][4], e2[cur][5], e2[cur][6], e2[cur][7]);
+          sts_u4(xw2 + c * 32, make_uint4(e2[cur][0], e2[cur][1], e2[cur][2], e2[cur][3]));
+          sts_u4(xw2 + c * 32 + 16, make_uint4(e2[cur][4], e2[cur][5], e2[cur][6], e2[cur][7]));
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[cur][e]), 1);      // dx = -1 term of row - 1
           const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[cur][e]), 1);    // dx = +1 term of row + 1
-          acc[c * 8 + e] = __uint_as_float(e1[cur][e]) + (lane > 0 ? up : 0.f) + (lane < 31 ? dn : 0.f);
+          acc[c * 8 + e] = fmaf(dn, m_dn, fmaf(up, m_up, __uint_as_float(e1[cur][e])));
         }
       }
       tc_fence_before();
@@ -249,11 +250,12 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       // boundary exchange between the four lane quarters (same channel half)
       asm volatile("bar.sync 1, %0;" ::"n"(FWD_EPI_WARPS * 32) : "memory");
       if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
-        const float4* xr = reinterpret_cast<const float4*>(lane == 0 ? cs->xch[a][0][q - 1][half] : cs->xch[a][1][q + 1][half]);
+        const uint32_t xr = smem_u32(lane == 0 ? cs->xch[a][0][q - 1][half] : cs->xch[a][1][q + 1][half]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float4 t = xr[e];
-          acc[4 * e] += t.x; acc[4 * e + 1] += t.y; acc[4 * e + 2] += t.z; acc[4 * e + 3] += t.w;
+          const uint4 t = lds_u4(xr + e * 16);
+          acc[4 * e] += __uint_as_float(t.x); acc[4 * e + 1] += __uint_as_float(t.y);
+          acc[4 * e + 2] += __uint_as_float(t.z); acc[4 * e + 3] += __uint_as_float(t.w);
         }
       }
       mbar_wait(&cs->auxfull[a], aph);          // aux tile(s) landed / staging buffer free
@@ -273,22 +275,22 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
             }
           } else if (MODE == MODE_RES_ELU) {
             float sk[8];
-            unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
+            unpack8(lds_u4(st1 + pos), sk);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = elu_fast(o[e] + bch[jj * 8 + e] + sk[e]);
           } else if (MODE == MODE_MUL) {
             float sk[8];
-            unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
+            unpack8(lds_u4(st1 + pos), sk);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(sk[e]);
           } else {
             float sk[8], t[8];
-            unpack8(*reinterpret_cast<const uint4*>(st1 + pos), sk);
-            unpack8(*reinterpret_cast<const uint4*>(st2 + pos), t);
+            unpack8(lds_u4(st1 + pos), sk);
+            unpack8(lds_u4(st2 + pos), t);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
           }
-          *reinterpret_cast<uint4*>(st1 + pos) = valid ? pack8(o) : make_uint4(0, 0, 0, 0);
+          sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
         }
       }
       fence_proxy_async_smem();                 // my generic-proxy writes -> visible to the bulk store
