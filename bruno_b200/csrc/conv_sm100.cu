@@ -11,6 +11,7 @@
 //     64-channel atoms are LBO bytes apart = the row shift between the taps); the bias gradient rides along as the
 //     spare atom of the ninth tap (a constant "ones" operand).  fp32 accumulation in TMEM over all tiles of the CTA.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -53,7 +54,8 @@ __device__ __forceinline__ void trace(int it, int slot) {
   if (g_conv_trace != nullptr && blockIdx.x == 0 && it < 64) g_conv_trace[it * 8 + slot] = clock64();
 }
 
-constexpr int FWD_EPI_WARPS = 8;             // 2 per TMEM lane quarter: each handles 32 rows x 32 channels
+constexpr int FWD_EPI_WARPS = 16;            // 4 per TMEM lane quarter: each handles 32 rows x 16 channels
+constexpr int EPI_CH = 64 / (FWD_EPI_WARPS / 4);   // channels per epilogue warp
 constexpr int FWD_THREADS = 32 * (2 + FWD_EPI_WARPS + 1);   // producer, MMA issuer, epilogue warps, aux/store warp
 constexpr int TILE_BYTES = TILE_M * SLAB_ROW_BYTES;          // 16 KB: one aux / gradient tile of the wgrad kernel
 constexpr int OUT_ROWS = 126;                // output rows per tile of the dx-fused forward kernel (see below)
@@ -65,7 +67,7 @@ struct ConvSmem {
   uint64_t full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2], wbar;
   uint64_t auxfull[2], outready[2];
   uint32_t tmem_base;
-  alignas(16) float xch[2][2][4][2][32];   // [tile parity][dx block 0 / 2][lane quarter][channel half][32 channels]
+  alignas(16) float xch[2][2][4][FWD_EPI_WARPS / 4][EPI_CH];   // [tile parity][dx block 0 / 2][lane quarter][channel group][channels]
 };
 
 __host__ __device__ constexpr bool mode_has_aux1(int m) { return m == MODE_RES_ELU || m == MODE_MUL || m == MODE_ADD_MUL; }
@@ -186,13 +188,15 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       }
     }
   } else if (warp < 2 + FWD_EPI_WARPS) {
-    // ===== epilogue: warp w -> TMEM lane quarter (w & 3), channel half ((w - 2) >> 2) =====
+    // ===== epilogue: warp w -> TMEM lane quarter (w & 3), channel group ((w - 2) >> 2) of EPI_CH channels =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int cg = (warp - 2) >> 2;
     const int row = q * 32 + lane;              // computed row inside the tile (0..127); rows 1..126 are stored
-    float bch[32];
+    constexpr int NCH = EPI_CH / 8;             // 8-channel chunks per warp
+    float bch[EPI_CH];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) bch[e] = HAS_BIAS ? __ldg(bias + half * 32 + e) : 0.f;
+    for (int e = 0; e < EPI_CH; ++e) bch[e] = HAS_BIAS ? __ldg(bias + cg * EPI_CH + e) : 0.f;
+    const float m_up = lane > 0 ? 1.f : 0.f, m_dn = lane < 31 ? 1.f : 0.f;   // warp-edge lanes get theirs via smem
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int a = it & 1;
@@ -208,51 +212,46 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       mbar_wait(&cs->tfull[a], aph);
       tc_fence_after();
       if (warp == 2 && lane == 0) trace(it, 3);
-      const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 256 + half * 32;
-      float acc[32];
+      const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 256 + cg * EPI_CH;
       // E_0 of the own row plus the two shuffled neighbours; the boundary lanes of the warp publish the values their
-      // neighbours in the adjacent lane quarter need (vector stores, 2 per 8-channel chunk).  TMEM loads are software
-      // pipelined one chunk ahead.
-      const uint32_t xw0 = smem_u32(cs->xch[a][0][q][half]);   // my dx = -1 block, needed by row + 1 -> written by lane 31
-      const uint32_t xw2 = smem_u32(cs->xch[a][1][q][half]);   // my dx = +1 block, needed by row - 1 -> written by lane 0
-      const float m_up = lane > 0 ? 1.f : 0.f, m_dn = lane < 31 ? 1.f : 0.f;   // warp-edge lanes get theirs via smem
-      uint32_t e0[2][8], e1[2][8], e2[2][8];
-      tmem_ld8(tbase + 0 * 64, e0[0]);
-      tmem_ld8(tbase + 1 * 64, e1[0]);
-      tmem_ld8(tbase + 2 * 64, e2[0]);
+      // neighbours in the adjacent lane quarter need.
+      uint32_t e0[NCH][8], e1[NCH][8], e2[NCH][8];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int cur = c & 1, nxt = cur ^ 1;
-        tmem_ld_wait();
-        if (c < 3) {
-          tmem_ld8(tbase + 0 * 64 + (c + 1) * 8, e0[nxt]);
-          tmem_ld8(tbase + 1 * 64 + (c + 1) * 8, e1[nxt]);
-          tmem_ld8(tbase + 2 * 64 + (c + 1) * 8, e2[nxt]);
-        }
-        if (lane == 31) {
-          sts_u4(xw0 + c * 32, make_uint4(e0[cur][0], e0[cur][1], e0[cur][2], e0[cur][3]));
-          sts_u4(xw0 + c * 32 + 16, make_uint4(e0[cur][4], e0[cur][5], e0[cur][6], e0[cur][7]));
-        }
-        if (lane == 0) {
-          sts_u4(xw2 + c * 32, make_uint4(e2[cur][0], e2[cur][1], e2[cur][2], e2[cur][3]));
-          sts_u4(xw2 + c * 32 + 16, make_uint4(e2[cur][4], e2[cur][5], e2[cur][6], e2[cur][7]));
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[cur][e]), 1);      // dx = -1 term of row - 1
-          const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[cur][e]), 1);    // dx = +1 term of row + 1
-          acc[c * 8 + e] = fmaf(dn, m_dn, fmaf(up, m_up, __uint_as_float(e1[cur][e])));
-        }
+      for (int c = 0; c < NCH; ++c) {
+        tmem_ld8(tbase + 0 * 64 + c * 8, e0[c]);
+        tmem_ld8(tbase + 1 * 64 + c * 8, e1[c]);
+        tmem_ld8(tbase + 2 * 64 + c * 8, e2[c]);
       }
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&cs->tempty[a]);
-      // boundary exchange between the four lane quarters (same channel half)
-      asm volatile("bar.sync 1, %0;" ::"n"(FWD_EPI_WARPS * 32) : "memory");
-      if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
-        const uint32_t xr = smem_u32(lane == 0 ? cs->xch[a][0][q - 1][half] : cs->xch[a][1][q + 1][half]);
+      const uint32_t xw0 = smem_u32(cs->xch[a][0][q][cg]);   // my dx = -1 block, needed by row + 1 -> written by lane 31
+      const uint32_t xw2 = smem_u32(cs->xch[a][1][q][cg]);   // my dx = +1 block, needed by row - 1 -> written by lane 0
+      float acc[EPI_CH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (lane == 31) {
+          sts_u4(xw0 + c * 32, make_uint4(e0[c][0], e0[c][1], e0[c][2], e0[c][3]));
+          sts_u4(xw0 + c * 32 + 16, make_uint4(e0[c][4], e0[c][5], e0[c][6], e0[c][7]));
+        }
+        if (lane == 0) {
+          sts_u4(xw2 + c * 32, make_uint4(e2[c][0], e2[c][1], e2[c][2], e2[c][3]));
+          sts_u4(xw2 + c * 32 + 16, make_uint4(e2[c][4], e2[c][5], e2[c][6], e2[c][7]));
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
+          const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[c][e]), 1);      // dx = -1 term of row - 1
+          const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[c][e]), 1);    // dx = +1 term of row + 1
+          acc[c * 8 + e] = fmaf(dn, m_dn, fmaf(up, m_up, __uint_as_float(e1[c][e])));
+        }
+      }
+      // boundary exchange between the four lane quarters (same channel group)
+      asm volatile("bar.sync 1, %0;" ::"n"(FWD_EPI_WARPS * 32) : "memory");
+      if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
+        const uint32_t xr = smem_u32(lane == 0 ? cs->xch[a][0][q - 1][cg] : cs->xch[a][1][q + 1][cg]);
+#pragma unroll
+        for (int e = 0; e < EPI_CH / 4; ++e) {
           const uint4 t = lds_u4(xr + e * 16);
           acc[4 * e] += __uint_as_float(t.x); acc[4 * e + 1] += __uint_as_float(t.y);
           acc[4 * e + 2] += __uint_as_float(t.z); acc[4 * e + 3] += __uint_as_float(t.w);
@@ -261,8 +260,8 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       mbar_wait(&cs->auxfull[a], aph);          // aux tile(s) landed / staging buffer free
       if (stored) {
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = half * 4 + jj;
+        for (int jj = 0; jj < NCH; ++jj) {
+          const int j = cg * NCH + jj;
           const int pos = (j ^ R7) << 4;
           float o[8];
 #pragma unroll

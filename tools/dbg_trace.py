@@ -21,4 +21,4 @@ for mode in (0, 1):
     t0 = int(t[0, 0])
     print('mode', mode, ' columns: load_issued slab_landed mma_issued acc_ready epi_done store_issued store_read_done (cycles since first load)')
     for i in range(30):
-        print(i, [int(v - t0) if v else None for v in t[i, :7]])
+        print(i, [int(v - t0) if v else None for v in t[i, :8]])
