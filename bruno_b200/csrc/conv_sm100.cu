@@ -47,15 +47,15 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // Optional pipeline trace (debug): CTA 0 records clock64() at role events into a caller-provided device buffer
-// [tile][8]: 0 slab load issued, 1 slab landed (MMA thread), 2 MMAs issued, 3 accumulator ready (epilogue warp 2),
+// [tile][16]: 0 slab load issued, 1 slab landed (MMA thread), 2 MMAs issued, 3 accumulator ready (epilogue warp 2),
 // 4 epilogue math done, 5 store issued, 6 store smem-read done.
 __device__ long long* g_conv_trace = nullptr;
 __device__ __forceinline__ void trace(int it, int slot) {
-  if (g_conv_trace != nullptr && blockIdx.x == 0 && it < 64) g_conv_trace[it * 8 + slot] = clock64();
+  if (g_conv_trace != nullptr && blockIdx.x == 0 && it < 64) g_conv_trace[it * 16 + slot] = clock64();
 }
 
 constexpr int FWD_EPI_WARPS = 16;            // 4 per TMEM lane quarter: each handles 32 rows x 16 channels
-constexpr int EPI_CH = 64 / (FWD_EPI_WARPS / 4);   // channels per epilogue warp
+constexpr int EPI_CH = 16;                   // channels per epilogue pass
 constexpr int FWD_THREADS = 32 * (2 + FWD_EPI_WARPS + 1);   // producer, MMA issuer, epilogue warps, aux/store warp
 constexpr int TILE_BYTES = TILE_M * SLAB_ROW_BYTES;          // 16 KB: one aux / gradient tile of the wgrad kernel
 constexpr int OUT_ROWS = 126;                // output rows per tile of the dx-fused forward kernel (see below)
@@ -67,7 +67,8 @@ struct ConvSmem {
   uint64_t full[NSTAGE], empty[NSTAGE], tfull[2], tempty[2], wbar;
   uint64_t auxfull[2], outready[2];
   uint32_t tmem_base;
-  alignas(16) float xch[2][2][4][FWD_EPI_WARPS / 4][EPI_CH];   // [tile parity][dx block 0 / 2][lane quarter][channel group][channels]
+  alignas(16) float bias[64];
+  alignas(16) float xch[2][2][4][4][EPI_CH];   // [tile parity][dx block 0 / 2][lane quarter][channel group][channels]
 };
 
 __host__ __device__ constexpr bool mode_has_aux1(int m) { return m == MODE_RES_ELU || m == MODE_MUL || m == MODE_ADD_MUL; }
@@ -117,13 +118,14 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&cs->tfull[a], 1);
-      mbar_init(&cs->tempty[a], FWD_EPI_WARPS);
+      mbar_init(&cs->tempty[a], FWD_EPI_WARPS / 2);
       mbar_init(&cs->auxfull[a], 1);
-      mbar_init(&cs->outready[a], FWD_EPI_WARPS * 32);
+      mbar_init(&cs->outready[a], FWD_EPI_WARPS * 16);
     }
     mbar_init(&cs->wbar, 1);
     fence_mbar_init();
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) cs->bias[threadIdx.x - 64] = HAS_BIAS ? bias[threadIdx.x - 64] : 0.f;
   if (warp == 0) {
     __syncwarp();
     tmem_alloc(&cs->tmem_base, 512);
@@ -188,22 +190,30 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       }
     }
   } else if (warp < 2 + FWD_EPI_WARPS) {
-    // ===== epilogue: warp w -> TMEM lane quarter (w & 3), channel group ((w - 2) >> 2) of EPI_CH channels =====
+    // ===== epilogue: two groups of 8 warps alternate tiles (group = accumulator / staging buffer index), so that the
+    // TMEM-load + shuffle phase of one tile overlaps the math + store phase of the previous one.  Inside a group,
+    // warp -> TMEM lane quarter (w & 3) and channel half; each half is processed as two passes of EPI_CH channels.
+    const int grp = (warp - 2) >> 3;
     const int q = warp & 3;
-    const int cg = (warp - 2) >> 2;
+    const int half = ((warp - 2) >> 2) & 1;
     const int row = q * 32 + lane;              // computed row inside the tile (0..127); rows 1..126 are stored
-    constexpr int NCH = EPI_CH / 8;             // 8-channel chunks per warp
-    float bch[EPI_CH];
-#pragma unroll
-    for (int e = 0; e < EPI_CH; ++e) bch[e] = HAS_BIAS ? __ldg(bias + cg * EPI_CH + e) : 0.f;
+    constexpr int NCH = EPI_CH / 8;             // 8-channel chunks per pass
     const float m_up = lane > 0 ? 1.f : 0.f, m_dn = lane < 31 ? 1.f : 0.f;   // warp-edge lanes get theirs via smem
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int a = it & 1;
+    const bool stored = row >= 1 && row <= OUT_ROWS;
+    const int a = grp;
+    // row bookkeeping without integer division in the loop: q_img = data_row mod IMG advances by a constant per tile
+    const int tile_stride = 2 * gridDim.x;
+    const int step_mod = (OUT_ROWS * tile_stride) % g.IMG;
+    int tile = blockIdx.x + grp * gridDim.x;
+    int data_row = OUT_ROWS * tile - 1 + row;
+    int q_img = ((data_row % g.IMG) + g.IMG) % g.IMG;
+    const float inv_p = 1.0f / static_cast<float>(g.P);
+    int it = grp;
+    for (; tile < ntiles; tile += tile_stride, it += 2) {
       const uint32_t aph = (it >> 1) & 1;
-      const int data_row = OUT_ROWS * tile - 1 + row;
-      const bool stored = row >= 1 && row <= OUT_ROWS;
-      const bool valid = stored && data_row >= 0 && slab_row_is_pixel(data_row, g);
+      const int yy = static_cast<int>((static_cast<float>(q_img) + 0.5f) * inv_p);   // exact for q_img < 2^20
+      const int xx = q_img - yy * g.P;
+      const bool valid = stored && data_row >= 0 && data_row < g.data_rows && yy >= 1 && xx >= 1;
       const int Rf = g.HALO + OUT_ROWS * tile;
       const int srow = (Rf & 7) + row - 1;      // staging row (only meaningful when stored)
       const int R7 = (g.HALO + data_row) & 7;   // swizzle phase of the buffer row
@@ -212,89 +222,101 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       mbar_wait(&cs->tfull[a], aph);
       tc_fence_after();
       if (warp == 2 && lane == 0) trace(it, 3);
-      const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 256 + cg * EPI_CH;
-      // E_0 of the own row plus the two shuffled neighbours; the boundary lanes of the warp publish the values their
-      // neighbours in the adjacent lane quarter need.
-      uint32_t e0[NCH][8], e1[NCH][8], e2[NCH][8];
+#pragma unroll 1
+      for (int p = 0; p < 2; ++p) {
+        const int cg = half * 2 + p;
+        const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 256 + cg * EPI_CH;
+        uint32_t e0[NCH][8], e1[NCH][8], e2[NCH][8];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        tmem_ld8(tbase + 0 * 64 + c * 8, e0[c]);
-        tmem_ld8(tbase + 1 * 64 + c * 8, e1[c]);
-        tmem_ld8(tbase + 2 * 64 + c * 8, e2[c]);
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&cs->tempty[a]);
-      const uint32_t xw0 = smem_u32(cs->xch[a][0][q][cg]);   // my dx = -1 block, needed by row + 1 -> written by lane 31
-      const uint32_t xw2 = smem_u32(cs->xch[a][1][q][cg]);   // my dx = +1 block, needed by row - 1 -> written by lane 0
-      float acc[EPI_CH];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        if (lane == 31) {
-          sts_u4(xw0 + c * 32, make_uint4(e0[c][0], e0[c][1], e0[c][2], e0[c][3]));
-          sts_u4(xw0 + c * 32 + 16, make_uint4(e0[c][4], e0[c][5], e0[c][6], e0[c][7]));
+        for (int c = 0; c < NCH; ++c) {
+          tmem_ld8(tbase + 0 * 64 + c * 8, e0[c]);
+          tmem_ld8(tbase + 1 * 64 + c * 8, e1[c]);
+          tmem_ld8(tbase + 2 * 64 + c * 8, e2[c]);
         }
-        if (lane == 0) {
-          sts_u4(xw2 + c * 32, make_uint4(e2[c][0], e2[c][1], e2[c][2], e2[c][3]));
-          sts_u4(xw2 + c * 32 + 16, make_uint4(e2[c][4], e2[c][5], e2[c][6], e2[c][7]));
+        tmem_ld_wait();
+        if (p == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cs->tempty[a]);
         }
+        const uint32_t xw0 = smem_u32(cs->xch[a][0][q][cg]);   // my dx = -1 block, needed by row + 1 -> written by lane 31
+        const uint32_t xw2 = smem_u32(cs->xch[a][1][q][cg]);   // my dx = +1 block, needed by row - 1 -> written by lane 0
+        float acc[EPI_CH];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[c][e]), 1);      // dx = -1 term of row - 1
-          const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[c][e]), 1);    // dx = +1 term of row + 1
-          acc[c * 8 + e] = fmaf(dn, m_dn, fmaf(up, m_up, __uint_as_float(e1[c][e])));
-        }
-      }
-      // boundary exchange between the four lane quarters (same channel group)
-      asm volatile("bar.sync 1, %0;" ::"n"(FWD_EPI_WARPS * 32) : "memory");
-      if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
-        const uint32_t xr = smem_u32(lane == 0 ? cs->xch[a][0][q - 1][cg] : cs->xch[a][1][q + 1][cg]);
-#pragma unroll
-        for (int e = 0; e < EPI_CH / 4; ++e) {
-          const uint4 t = lds_u4(xr + e * 16);
-          acc[4 * e] += __uint_as_float(t.x); acc[4 * e + 1] += __uint_as_float(t.y);
-          acc[4 * e + 2] += __uint_as_float(t.z); acc[4 * e + 3] += __uint_as_float(t.w);
-        }
-      }
-      mbar_wait(&cs->auxfull[a], aph);          // aux tile(s) landed / staging buffer free
-      if (stored) {
-#pragma unroll
-        for (int jj = 0; jj < NCH; ++jj) {
-          const int j = cg * NCH + jj;
-          const int pos = (j ^ R7) << 4;
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = acc[jj * 8 + e];
-          if (MODE == MODE_ELU || MODE == MODE_LINEAR) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float t = o[e] + bch[jj * 8 + e];
-              o[e] = MODE == MODE_ELU ? elu_fast(t) : t;
-            }
-          } else if (MODE == MODE_RES_ELU) {
-            float sk[8];
-            unpack8(lds_u4(st1 + pos), sk);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = elu_fast(o[e] + bch[jj * 8 + e] + sk[e]);
-          } else if (MODE == MODE_MUL) {
-            float sk[8];
-            unpack8(lds_u4(st1 + pos), sk);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(sk[e]);
-          } else {
-            float sk[8], t[8];
-            unpack8(lds_u4(st1 + pos), sk);
-            unpack8(lds_u4(st2 + pos), t);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
+        for (int c = 0; c < NCH; ++c) {
+          if (lane == 31) {
+            sts_u4(xw0 + c * 32, make_uint4(e0[c][0], e0[c][1], e0[c][2], e0[c][3]));
+            sts_u4(xw0 + c * 32 + 16, make_uint4(e0[c][4], e0[c][5], e0[c][6], e0[c][7]));
           }
-          sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
+          if (lane == 0) {
+            sts_u4(xw2 + c * 32, make_uint4(e2[c][0], e2[c][1], e2[c][2], e2[c][3]));
+            sts_u4(xw2 + c * 32 + 16, make_uint4(e2[c][4], e2[c][5], e2[c][6], e2[c][7]));
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[c][e]), 1);      // dx = -1 term of row - 1
+            const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[c][e]), 1);    // dx = +1 term of row + 1
+            acc[c * 8 + e] = fmaf(dn, m_dn, fmaf(up, m_up, __uint_as_float(e1[c][e])));
+          }
+        }
+        // boundary exchange between the four lane quarters of this group (barrier id 1 + group, 256 threads)
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
+        if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
+          const uint32_t xr = smem_u32(lane == 0 ? cs->xch[a][0][q - 1][cg] : cs->xch[a][1][q + 1][cg]);
+#pragma unroll
+          for (int e = 0; e < EPI_CH / 4; ++e) {
+            const uint4 t = lds_u4(xr + e * 16);
+            acc[4 * e] += __uint_as_float(t.x); acc[4 * e + 1] += __uint_as_float(t.y);
+            acc[4 * e + 2] += __uint_as_float(t.z); acc[4 * e + 3] += __uint_as_float(t.w);
+          }
+        }
+        if (p == 0) mbar_wait(&cs->auxfull[a], aph);          // aux tile(s) landed / staging buffer free
+        if (stored) {
+#pragma unroll
+          for (int jj = 0; jj < NCH; ++jj) {
+            const int j = cg * NCH + jj;
+            const int pos = (j ^ R7) << 4;
+            float o[8], bj[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = acc[jj * 8 + e];
+            if (HAS_BIAS) {
+              const float4 b0 = *reinterpret_cast<const float4*>(&cs->bias[j * 8]);
+              const float4 b1 = *reinterpret_cast<const float4*>(&cs->bias[j * 8 + 4]);
+              bj[0] = b0.x; bj[1] = b0.y; bj[2] = b0.z; bj[3] = b0.w; bj[4] = b1.x; bj[5] = b1.y; bj[6] = b1.z; bj[7] = b1.w;
+            }
+            if (MODE == MODE_ELU || MODE == MODE_LINEAR) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float t = o[e] + bj[e];
+                o[e] = MODE == MODE_ELU ? elu_fast(t) : t;
+              }
+            } else if (MODE == MODE_RES_ELU) {
+              float sk[8];
+              unpack8(lds_u4(st1 + pos), sk);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = elu_fast(o[e] + bj[e] + sk[e]);
+            } else if (MODE == MODE_MUL) {
+              float sk[8];
+              unpack8(lds_u4(st1 + pos), sk);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(sk[e]);
+            } else {
+              float sk[8], t[8];
+              unpack8(lds_u4(st1 + pos), sk);
+              unpack8(lds_u4(st2 + pos), t);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
+            }
+            sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
+          }
         }
       }
       fence_proxy_async_smem();                 // my generic-proxy writes -> visible to the bulk store
       if (warp == 2 && lane == 0) trace(it, 4);
       mbar_arrive(&cs->outready[a]);
+      data_row += OUT_ROWS * tile_stride;
+      q_img += step_mod;
+      if (q_img >= g.IMG) q_img -= g.IMG;
     }
   } else {
     // ===== aux / store warp: prefetch the aux tile(s) of tile `it`, then drain the output tile of tile `it - 1` =====

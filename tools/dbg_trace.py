@@ -12,13 +12,13 @@ bias = torch.zeros(64, device='cuda')
 for mode in (0, 1):
     for _ in range(3):
         _lib.call('bruno_conv3x3', mode, sl[0], wf[0], bias, sl[2], None, sl[1], N, H, W)
-    tr = torch.zeros(64 * 8, dtype=torch.int64, device='cuda')
+    tr = torch.zeros(64 * 16, dtype=torch.int64, device='cuda')
     _lib.load().bruno_debug_conv_trace(tr.data_ptr())
     _lib.call('bruno_conv3x3', mode, sl[0], wf[0], bias, sl[2], None, sl[1], N, H, W)
     torch.cuda.synchronize()
     _lib.load().bruno_debug_conv_trace(None)
-    t = tr.view(64, 8).cpu()
+    t = tr.view(64, 16).cpu()
     t0 = int(t[0, 0])
     print('mode', mode, ' columns: load_issued slab_landed mma_issued acc_ready epi_done store_issued store_read_done (cycles since first load)')
     for i in range(30):
-        print(i, [int(v - t0) if v else None for v in t[i, :8]])
+        print(i, 'load %d landed %d mma_done %d | epi: acc %d tmem %d shfl %d bar %d fix %d aux %d math %d fence %d | store %d' % tuple(int(t[i, k] - t0) for k in (0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 4, 5)))
