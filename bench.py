@@ -107,10 +107,18 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    # exactly ONE line may reach stdout: route everything else (NCCL banner, config prints) to stderr
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + '\n')
+        real_stdout.flush()
 
     if args.impl == 'reference':
         if rank == 0:
-            print(json.dumps(cpu_reference_line(args, min(args.steps, 3), min(args.warmup, 1), True)), flush=True)
+            emit(cpu_reference_line(args, min(args.steps, 3), min(args.warmup, 1), True))
         return
 
     import torch
@@ -127,9 +135,7 @@ def main():
     from bruno_b200.config_rnn import defaults
     from bruno_b200.trainer import Trainer
     defaults.seq_len = args.seq_len
-    import contextlib
-    with contextlib.redirect_stdout(sys.stderr):
-        cfg = importlib.import_module('bruno_b200.config_rnn.' + CONFIG)
+    cfg = importlib.import_module('bruno_b200.config_rnn.' + CONFIG)
     cfg.batch_size = args.batch * world                      # reference semantics: global batch, split over towers
     B, T = args.batch, args.seq_len
     H, W, C = cfg.obs_shape[1:]
@@ -186,9 +192,9 @@ def main():
     l0 = _lib.query('bruno_launch_count')
     ms_train = timed(train_resident, steps)
     launches = _lib.query('bruno_launch_count') - l0
+    ms_e2e = timed(train_e2e, steps)
     if sampler:
         sampler.stop_flag = True
-    ms_e2e = timed(train_e2e, steps)
     for i in range(2):
         eval_resident(i)
     ms_eval = timed(eval_resident, steps)
@@ -246,7 +252,7 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
         line['cpu_baseline'] = cpu_reference_line(args, 2, 1, False)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
