@@ -390,6 +390,17 @@ __global__ void process_fwd_finalize(const float* __restrict__ scratch, float* _
 // ------------------------------------------------------------------------------------------------------------
 // backward scan
 // ------------------------------------------------------------------------------------------------------------
+// double-single accumulation of S2 = sum (x - mu0)^2 in the backward: the reverse pass recovers the prefix sums by
+// SUBTRACTING observations from the total, and q = 1 + e S2 + f S1^2 needs S2 to an absolute accuracy << 1/e even when
+// the total is ~1e8 (untrained flows produce |z| ~ 1e4): plain fp32 leaves a residue of +-32 there and q < 0 -> NaN.
+__device__ __forceinline__ void ds_add(float& hi, float& lo, float v, float ve) {
+  const float s = hi + v;
+  const float bb = s - hi;
+  const float err = (hi - (s - bb)) + (v - bb);
+  hi = s;
+  lo += err + ve;
+}
+
 template <int KIND, int VEC, int NB, bool PRIOR>
 __global__ void __launch_bounds__(256)
 process_bwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, const float* __restrict__ tab,
@@ -415,10 +426,10 @@ process_bwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
   for (int g = 0; g < groups_per_block; ++g) {
     const int b0 = (blockIdx.x * groups_per_block + g) * NB;
     if (b0 >= B) break;
-    Vf<VEC> S1[NB], S2[NB], G1[NB], G2[NB];
+    Vf<VEC> S1[NB], S2[NB], S2lo[NB], G1[NB], G2[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-      S1[j] = zerov<VEC>(); S2[j] = zerov<VEC>(); G1[j] = zerov<VEC>(); G2[j] = zerov<VEC>();
+      S1[j] = zerov<VEC>(); S2[j] = zerov<VEC>(); S2lo[j] = zerov<VEC>(); G1[j] = zerov<VEC>(); G2[j] = zerov<VEC>();
     }
     // pass 1: totals
     for (int n = 0; n < T; ++n) {
@@ -430,7 +441,10 @@ process_bwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
           for (int e = 0; e < VEC; ++e) {
             const float xz = x.x[e] - mu.x[e];
             S1[j].x[e] += xz;
-            S2[j].x[e] = fmaf(xz, xz, S2[j].x[e]);
+            if (KIND == BRUNO_TP) {
+              const float p2 = xz * xz;
+              ds_add(S2[j].x[e], S2lo[j].x[e], p2, fmaf(xz, xz, -p2));
+            }
           }
         }
     }
@@ -455,9 +469,10 @@ process_bwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
           float dxz, dS1, dS2 = 0.f;
           if constexpr (KIND == BRUNO_TP) {
             const float s1v = S1[j].x[e] - xz;            // prefix sums BEFORE observation n
-            const float s2v = fmaf(-xz, xz, S2[j].x[e]);
+            const float p2 = xz * xz;
+            ds_add(S2[j].x[e], S2lo[j].x[e], -p2, -fmaf(xz, xz, -p2));
+            const float s2v = fmaxf(S2[j].x[e] + S2lo[j].x[e], 0.f);
             S1[j].x[e] = s1v;
-            S2[j].x[e] = s2v;
             const float s1sq = s1v * s1v;
             const float r = fmaf(-cf[1].x[e], s1v, cf[0].x[e] * xz);
             const float q = fmaf(cf[3].x[e], s1sq, fmaf(cf[2].x[e], s2v, 1.f));

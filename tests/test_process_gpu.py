@@ -167,3 +167,26 @@ def test_exchangeability_at_scale(kind):
     lq, _ = layer.sequence_log_likelihoods(z[:, perm, :].contiguous())
     a, b = lp.sum(1).double(), lq.sum(1).double()
     assert torch.allclose(a, b, rtol=2e-5, atol=1e-2), (a - b).abs().max().item()
+
+
+@pytest.mark.parametrize('kind', ['tp', 'gp'])
+def test_backward_is_finite_for_huge_latents(kind):
+    """Untrained flows emit |z| ~ 1e4: the reverse pass must not lose the prefix sums (q = 1 + e S2 + f S1^2 > 0)."""
+    B, T, D = 2, 3, 64
+    layer, P = _layer(kind, D, seed=5)
+    g = torch.Generator().manual_seed(2)
+    z = (torch.randn(B, T, D, generator=g) * 3e3 + 1.2e4).float()
+    keys = ['model/prior_var', 'model/prior_nu', 'model/prior_corr'] if kind == 'tp' else ['model/gaussian/prior_var', 'model/gaussian/prior_corr']
+    leaves = {k: P[k].clone().requires_grad_(True) for k in keys}
+    zo = z.double().requires_grad_(True)
+    lp_o, _ = O.process_log_probs(_oracle_proc(kind, leaves), zo)
+    grads = torch.autograd.grad(lp_o.sum(), [zo] + [leaves[k] for k in keys])
+    zg = z.cuda().requires_grad_(True)
+    lp, _ = layer.sequence_log_likelihoods(zg)
+    params = [layer.var_vbl, layer.nu_vbl, layer.corr_vbl] if kind == 'tp' else [layer.var_vbl, layer.corr_vbl]
+    gg = torch.autograd.grad(lp.sum(), [zg] + params)
+    _close(lp, lp_o, rtol=1e-4, atol=1e-2)
+    for a, b in zip(gg, grads):
+        a = a.double().cpu()
+        assert torch.isfinite(a).all()
+        assert (a - b).abs().max().item() <= 5e-3 * (b.abs().max().item() + 1e-12)
