@@ -44,8 +44,8 @@ int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, i
   const size_t sb = bruno_slab_bytes(N, H, W), wb = bruno_conv_wpack_bytes();
   auto S = [&](int i) { return static_cast<const void*>(static_cast<const uint8_t*>(saved_slabs) + static_cast<size_t>(i) * sb); };
   auto Wp = [&](int l) { return static_cast<const void*>(static_cast<const uint8_t*>(wbwd) + static_cast<size_t>(l) * wb); };
-  void* G[3];
-  for (int i = 0; i < 3; ++i) G[i] = static_cast<uint8_t*>(gslabs) + static_cast<size_t>(i) * sb;
+  // GS(0) = gradient w.r.t. the c1 pre-activation; GS(l + 1) = gradient w.r.t. the pre-activation of conv layer l
+  auto GS = [&](int i) { return static_cast<void*>(static_cast<uint8_t*>(gslabs) + static_cast<size_t>(i) * sb); };
   cudaMemsetAsync(dVr, 0, static_cast<size_t>(2 * R) * 9 * 64 * 64 * sizeof(float), st);
   cudaMemsetAsync(dbr, 0, static_cast<size_t>(2 * R) * 64 * sizeof(float), st);
   cudaMemsetAsync(dV1, 0, static_cast<size_t>(C) * 64 * sizeof(float), st);
@@ -55,20 +55,16 @@ int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, i
   cudaMemsetAsync(dbs, 0, static_cast<size_t>(C) * sizeof(float), st);
   cudaMemsetAsync(dbt, 0, static_cast<size_t>(C) * sizeof(float), st);
   int rc;
-  if ((rc = bruno_heads_coupling_bwd(x, S(2 * R), Ks, bs, Kt, bt, dy, dld, dx, G[0], dKs, dbs, dKt, dbt, N, H, W, C,
+  if ((rc = bruno_heads_coupling_bwd(x, S(2 * R), Ks, bs, Kt, bt, dy, dld, dx, GS(2 * R), dKs, dbs, dKt, dbt, N, H, W, C,
                                      mask_type, stream))) return rc;
-  int a = 0;
   for (int r = R - 1; r >= 0; --r) {
-    const int b = (a + 1) % 3, c = (a + 2) % 3;
-    float* dW3 = dVr + static_cast<size_t>(2 * r + 1) * 9 * 64 * 64;
-    float* dW2 = dVr + static_cast<size_t>(2 * r) * 9 * 64 * 64;
-    if ((rc = bruno_conv3x3_wgrad(S(2 * r + 1), G[a], dW3, dbr + (2 * r + 1) * 64, N, H, W, stream))) return rc;
-    if ((rc = bruno_conv3x3(2, G[a], Wp(2 * r + 1), nullptr, S(2 * r + 1), nullptr, G[b], N, H, W, stream))) return rc;
-    if ((rc = bruno_conv3x3_wgrad(S(2 * r), G[b], dW2, dbr + (2 * r) * 64, N, H, W, stream))) return rc;
-    if ((rc = bruno_conv3x3(3, G[b], Wp(2 * r), nullptr, S(2 * r), G[a], G[c], N, H, W, stream))) return rc;
-    a = c;
+    // g2 = dgrad_c3(g3) * ELU'(u_r);   g3' (or g1) = (dgrad_c2(g2) + g3) * ELU'(block input)
+    if ((rc = bruno_conv3x3(2, GS(2 * r + 2), Wp(2 * r + 1), nullptr, S(2 * r + 1), nullptr, GS(2 * r + 1), N, H, W, stream))) return rc;
+    if ((rc = bruno_conv3x3(3, GS(2 * r + 1), Wp(2 * r), nullptr, S(2 * r), GS(2 * r + 2), GS(2 * r), N, H, W, stream))) return rc;
   }
-  if ((rc = bruno_c1_bwd(x, V1, g1, G[a], dx, dV1, db1, N, H, W, C, mask_type, stream))) return rc;
+  // all 2R weight (and bias) gradients in one launch: conv layer l reads its input slab S(l) and gradient GS(l + 1)
+  if ((rc = bruno_conv3x3_wgrad_batched(S(0), GS(1), dVr, dbr, 2 * R, N, H, W, stream))) return rc;
+  if ((rc = bruno_c1_bwd(x, V1, g1, GS(0), dx, dV1, db1, N, H, W, C, mask_type, stream))) return rc;
   // weight-norm backward, in place over the raw weight gradients
   if ((rc = bruno_conv_wn_bwd(Vr, gr, dVr, dVr, dgr, 2 * R, 9 * 64, stream))) return rc;
   return bruno_conv_wn_bwd(V1, g1, dV1, dV1, dg1, 1, C, stream);

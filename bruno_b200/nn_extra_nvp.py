@@ -158,7 +158,7 @@ class _ConvCouplingFn(torch.autograd.Function):
         R = layer.num_res_blocks
         dy = dy.contiguous()
         dld = dld.contiguous()
-        gsl = SLABS.get('grad', 3, N, H, W, x.device)
+        gsl = SLABS.get('grad', 2 * R + 1, N, H, W, x.device)
         dx = torch.empty_like(x)
         dV1, dg1, db1 = torch.empty_like(V1), torch.empty_like(g1), torch.empty_like(g1)
         dVr, dgr, dbr = torch.empty_like(Vr), torch.empty_like(gr), torch.empty_like(gr)

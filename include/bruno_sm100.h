@@ -151,6 +151,10 @@ int bruno_conv3x3(int mode, const void* in_slab, const void* wpack, const float*
                   void* out_slab, int N, int H, int W, void* stream);
 /* dW [3,3,64,64] (HWIO) += sum_pos x[pos + tap] (x) g[pos];  db [64] += sum_pos g[pos]   (fp32, atomically added) */
 int bruno_conv3x3_wgrad(const void* x_slab, const void* g_slab, float* dW, float* db, int N, int H, int W, void* stream);
+/* the same for L layers in ONE launch: layer l uses slab l of x_slab / g_slab (consecutive slabs of bruno_slab_bytes),
+ * dW + l*3*3*64*64, db + l*64; the grid is divided among the layers. */
+int bruno_conv3x3_wgrad_batched(const void* x_slab, const void* g_slab, float* dW, float* db, int L, int N, int H, int W,
+                                void* stream);
 
 /* c1 (nvp:113-115): out_slab = ELU(conv1x1_wn(x * mask)), x [N,H,W,C] fp32, V1 [C,64], g1, b1 [64]. */
 int bruno_c1_fwd(const float* x, const float* V1, const float* g1, const float* b1, void* out_slab, int N, int H, int W,
@@ -182,7 +186,9 @@ int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float*
                             const float* bt, void* slabs, int n_slabs, void* stream);
 /* Hand-written backward of the forward coupling: dx [N,H,W,C] and the gradients of every variable of the layer
  * (weight-norm backward included: dVr, dgr are w.r.t. V and g).  saved_slabs = the 2R+1 slabs of the forward;
- * gslabs = 3 zero-initialised scratch slabs; wbwd = dgrad operands from bruno_conv_wn_pack. */
+ * gslabs = 2R+1 zero-initialised scratch slabs (slab 0: gradient w.r.t. the c1 pre-activation, slab l+1: gradient
+ * w.r.t. the pre-activation of conv layer l -- all kept so that the 2R weight gradients are ONE batched launch);
+ * wbwd = dgrad operands from bruno_conv_wn_pack. */
 int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, int N, int H, int W, int C, int R,
                             int mask_type, const float* V1, const float* g1, const float* Vr, const float* gr,
                             const void* wbwd, const float* Ks, const float* bs, const float* Kt, const float* bt,
