@@ -551,16 +551,17 @@ conv_wn_pack_kernel(const float* __restrict__ V, const float* __restrict__ gain,
 }
 
 // dV, dg from dW (all [L][9][64][64] / [L][64]); K = rows per output channel (576 for 3x3, C for the 1x1 c1)
-__global__ void __launch_bounds__(256)
+constexpr int WNB_GROUPS = 16;
+__global__ void __launch_bounds__(64 * WNB_GROUPS)
 conv_wn_bwd_kernel(const float* __restrict__ V, const float* __restrict__ gain, const float* __restrict__ dW,
                    float* __restrict__ dV, float* __restrict__ dgain, int K) {
-  __shared__ float p_n2[4][64], p_dot[4][64], s_a[64], s_b[64];
+  __shared__ float p_n2[WNB_GROUPS][64], p_dot[WNB_GROUPS][64], s_a[64], s_b[64];
   const int l = blockIdx.x;
   const float* v = V + static_cast<size_t>(l) * K * 64;
   const float* dw = dW + static_cast<size_t>(l) * K * 64;
   const int co = threadIdx.x & 63, grp = threadIdx.x >> 6;
   float n2 = 0.f, dot = 0.f;
-  for (int r = grp; r < K; r += 4) {
+  for (int r = grp; r < K; r += WNB_GROUPS) {
     const float t = v[r * 64 + co];
     n2 = fmaf(t, t, n2);
     dot = fmaf(t, dw[r * 64 + co], dot);
@@ -569,8 +570,13 @@ conv_wn_bwd_kernel(const float* __restrict__ V, const float* __restrict__ gain, 
   p_dot[grp][co] = dot;
   __syncthreads();
   if (threadIdx.x < 64) {
-    const float N2 = fmaxf(p_n2[0][co] + p_n2[1][co] + p_n2[2][co] + p_n2[3][co], 1e-12f);
-    const float DOT = p_dot[0][co] + p_dot[1][co] + p_dot[2][co] + p_dot[3][co];
+    float N2 = 0.f, DOT = 0.f;
+#pragma unroll
+    for (int i = 0; i < WNB_GROUPS; ++i) {
+      N2 += p_n2[i][co];
+      DOT += p_dot[i][co];
+    }
+    N2 = fmaxf(N2, 1e-12f);
     const float inv = rsqrtf(N2);
     const float gg = gain[l * 64 + co];
     dgain[l * 64 + co] = DOT * inv;
@@ -579,7 +585,7 @@ conv_wn_bwd_kernel(const float* __restrict__ V, const float* __restrict__ gain, 
   }
   __syncthreads();
   float* dv = dV + static_cast<size_t>(l) * K * 64;
-  for (int r = grp; r < K; r += 4) dv[r * 64 + co] = s_a[co] * dw[r * 64 + co] - s_b[co] * v[r * 64 + co];
+  for (int r = grp; r < K; r += WNB_GROUPS) dv[r * 64 + co] = s_a[co] * dw[r * 64 + co] - s_b[co] * v[r * 64 + co];
 }
 
 static size_t conv_smem_bytes(const SlabGeom& g, int mode = MODE_ADD_MUL) {
@@ -654,7 +660,7 @@ int bruno_conv_wn_pack(const float* V, const float* g, void* wfwd, void* wbwd, i
 
 int bruno_conv_wn_bwd(const float* V, const float* g, const float* dW, float* dV, float* dg, int L, int K, void* stream) {
   BRUNO_REQUIRE(V && g && dW && dV && dg && L > 0 && K > 0, "bruno_conv_wn_bwd: bad arguments");
-  conv_wn_bwd_kernel<<<L, 256, 0, static_cast<cudaStream_t>(stream)>>>(V, g, dW, dV, dg, K);
+  conv_wn_bwd_kernel<<<L, 64 * WNB_GROUPS, 0, static_cast<cudaStream_t>(stream)>>>(V, g, dW, dV, dg, K);
   return check_launch("conv_wn_bwd_kernel");
 }
 

@@ -36,9 +36,9 @@ int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float*
 int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, int N, int H, int W, int C, int R,
                             int mask_type, const float* V1, const float* g1, const float* Vr, const float* gr,
                             const void* wbwd, const float* Ks, const float* bs, const float* Kt, const float* bt,
-                            const void* saved_slabs, void* gslabs, float* dx, float* dV1, float* dg1, float* db1, float* dVr,
-                            float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt, void* stream) {
-  BRUNO_REQUIRE(x && dy && dld && V1 && g1 && Vr && gr && wbwd && Ks && bs && Kt && bt && saved_slabs && gslabs && dx && dV1 &&
+                            const void* saved_slabs, void* gslabs, float* scratch, float* dx, float* dV1, float* dg1, float* db1,
+                            float* dVr, float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt, void* stream) {
+  BRUNO_REQUIRE(x && dy && dld && V1 && g1 && Vr && gr && wbwd && Ks && bs && Kt && bt && saved_slabs && gslabs && scratch && dx && dV1 &&
                     dg1 && db1 && dVr && dgr && dbr && dKs && dbs && dKt && dbt, "bruno_coupling_conv_bwd: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t sb = bruno_slab_bytes(N, H, W), wb = bruno_conv_wpack_bytes();
@@ -50,12 +50,8 @@ int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, i
   cudaMemsetAsync(dbr, 0, static_cast<size_t>(2 * R) * 64 * sizeof(float), st);
   cudaMemsetAsync(dV1, 0, static_cast<size_t>(C) * 64 * sizeof(float), st);
   cudaMemsetAsync(db1, 0, 64 * sizeof(float), st);
-  cudaMemsetAsync(dKs, 0, static_cast<size_t>(C) * 64 * sizeof(float), st);
-  cudaMemsetAsync(dKt, 0, static_cast<size_t>(C) * 64 * sizeof(float), st);
-  cudaMemsetAsync(dbs, 0, static_cast<size_t>(C) * sizeof(float), st);
-  cudaMemsetAsync(dbt, 0, static_cast<size_t>(C) * sizeof(float), st);
   int rc;
-  if ((rc = bruno_heads_coupling_bwd(x, S(2 * R), Ks, bs, Kt, bt, dy, dld, dx, GS(2 * R), dKs, dbs, dKt, dbt, N, H, W, C,
+  if ((rc = bruno_heads_coupling_bwd(x, S(2 * R), Ks, bs, Kt, bt, dy, dld, dx, GS(2 * R), dKs, dbs, dKt, dbt, scratch, N, H, W, C,
                                      mask_type, stream))) return rc;
   for (int r = R - 1; r >= 0; --r) {
     // g2 = dgrad_c3(g3) * ELU'(u_r);   g3' (or g1) = (dgrad_c2(g2) + g3) * ELU'(block input)

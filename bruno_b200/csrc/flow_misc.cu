@@ -127,6 +127,7 @@ __global__ void channel_copy_kernel(const float* __restrict__ src, float* __rest
 // c1: 1x1 weight-normalised conv C -> 64 on the masked input + ELU, written as a swizzled bf16 slab.  nvp:113-115
 // ------------------------------------------------------------------------------------------------------------
 constexpr int MAXC = 16;
+constexpr int HEADS_BWD_BLOCKS = 296;   // 2 resident blocks per SM
 
 __device__ __forceinline__ void c1_weights_to_smem(const float* __restrict__ V1, const float* __restrict__ g1, int C,
                                                    float* w_s /*[C][64]*/) {
@@ -300,8 +301,7 @@ __global__ void __launch_bounds__(256)
 heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restrict__ hslab, const float* __restrict__ Ks,
                           const float* __restrict__ bs, const float* __restrict__ Kt, const float* __restrict__ bt,
                           const float* __restrict__ dy, const float* __restrict__ dld, float* __restrict__ dx,
-                          uint8_t* __restrict__ gslab, float* __restrict__ dKs, float* __restrict__ dbs,
-                          float* __restrict__ dKt, float* __restrict__ dbt, SlabGeom g, int C, int mask_type) {
+                          uint8_t* __restrict__ gslab, float* __restrict__ partial, SlabGeom g, int C, int mask_type) {
   extern __shared__ float sm[];
   float* ks_s = sm;                        // [64][C]
   float* kt_s = ks_s + 64 * MAXC;
@@ -318,15 +318,17 @@ heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restri
     bt_s[threadIdx.x] = bt[threadIdx.x];
   }
   __syncthreads();
-  const int n = blockIdx.x;
   const int HW = g.H * g.W;
-  const float dl = dld[n];
   const int nout = 65 * 2 * C;
   constexpr int NACC = 65 * 2 * MAXC / 256 + 1;
   float acc[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
 
+  // persistent over images: the head-weight gradients are accumulated in registers across all images of the block and
+  // leave as ONE partial vector per block (640 blocks x same-address atomics serialised for ~200 us at L2 before)
+  for (int n = blockIdx.x; n < g.N; n += gridDim.x) {
+  const float dl = dld[n];
   for (int p0 = 0; p0 < HW; p0 += 256) {
     const int p = p0 + threadIdx.x;
     const bool ok = p < HW;
@@ -392,14 +394,24 @@ heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restri
     }
     __syncthreads();
   }
-  int ai = 0;
-  for (int o = threadIdx.x; o < nout; o += 256, ++ai) {
-    const int k = o % 65, c2 = o / 65;
-    const bool is_t = c2 >= C;
-    const int c = is_t ? c2 - C : c2;
-    float* dst = k < 64 ? (is_t ? dKt : dKs) + k * C + c : (is_t ? dbt : dbs) + c;
-    atomicAdd(dst, acc[ai]);
   }
+  int ai = 0;
+  for (int o = threadIdx.x; o < nout; o += 256, ++ai) partial[static_cast<size_t>(blockIdx.x) * nout + o] = acc[ai];
+}
+
+// fixed-order sum of the per-block partials -> dKs, dbs, dKt, dbt (overwritten)
+__global__ void heads_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dKs,
+                                          float* __restrict__ dbs, float* __restrict__ dKt, float* __restrict__ dbt) {
+  const int nout = 65 * 2 * C;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= nout) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[static_cast<size_t>(b) * nout + o];
+  const int k = o % 65, c2 = o / 65;
+  const bool is_t = c2 >= C;
+  const int c = is_t ? c2 - C : c2;
+  float* dst = k < 64 ? (is_t ? dKt : dKs) + k * C + c : (is_t ? dbt : dbs) + c;
+  *dst = s;
 }
 
 // zero the rows of a slab that heads_coupling_bwd does not write (padding positions), so the slab invariant holds
@@ -482,11 +494,14 @@ int bruno_heads_coupling(const float* x, const void* h_slab, const float* Ks, co
   return check_launch("heads_coupling_kernel");
 }
 
+size_t bruno_heads_bwd_scratch_floats(int C) { return static_cast<size_t>(HEADS_BWD_BLOCKS) * 65 * 2 * C; }
+
 int bruno_heads_coupling_bwd(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
                              const float* bt, const float* dy, const float* dld, float* dx, void* g_slab, float* dKs,
-                             float* dbs, float* dKt, float* dbt, int N, int H, int W, int C, int mask_type, void* stream) {
-  BRUNO_REQUIRE(x && h_slab && Ks && bs && Kt && bt && dy && dld && dx && g_slab && dKs && dbs && dKt && dbt && C >= 1 &&
-                    C <= MAXC, "bruno_heads_coupling_bwd: bad arguments");
+                             float* dbs, float* dKt, float* dbt, float* scratch, int N, int H, int W, int C, int mask_type,
+                             void* stream) {
+  BRUNO_REQUIRE(x && h_slab && Ks && bs && Kt && bt && dy && dld && dx && g_slab && dKs && dbs && dKt && dbt && scratch &&
+                    C >= 1 && C <= MAXC, "bruno_heads_coupling_bwd: bad arguments");
   const SlabGeom g = slab_geom(N, H, W);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = (2 * 64 * MAXC + 2 * MAXC + 256 * 65 + 256 * 2 * MAXC) * sizeof(float);
@@ -496,9 +511,13 @@ int bruno_heads_coupling_bwd(const float* x, const void* h_slab, const float* Ks
     configured = true;
   }
   slab_zero_padding_kernel<<<148 * 4, 256, 0, st>>>(static_cast<uint8_t*>(g_slab), g);
-  heads_coupling_bwd_kernel<<<N, 256, smem, st>>>(x, static_cast<const uint8_t*>(h_slab), Ks, bs, Kt, bt, dy, dld, dx,
-                                                  static_cast<uint8_t*>(g_slab), dKs, dbs, dKt, dbt, g, C, mask_type);
-  return check_launch("heads_coupling_bwd_kernel");
+  const int nblk = N < HEADS_BWD_BLOCKS ? N : HEADS_BWD_BLOCKS;
+  heads_coupling_bwd_kernel<<<nblk, 256, smem, st>>>(x, static_cast<const uint8_t*>(h_slab), Ks, bs, Kt, bt, dy, dld, dx,
+                                                     static_cast<uint8_t*>(g_slab), scratch, g, C, mask_type);
+  int rc = check_launch("heads_coupling_bwd_kernel");
+  if (rc) return rc;
+  heads_bwd_finalize_kernel<<<ceil_div(65 * 2 * C, 128), 128, 0, st>>>(scratch, nblk, C, dKs, dbs, dKt, dbt);
+  return check_launch("heads_bwd_finalize_kernel");
 }
 
 }  // extern "C"

@@ -163,8 +163,9 @@ class _ConvCouplingFn(torch.autograd.Function):
         dV1, dg1, db1 = torch.empty_like(V1), torch.empty_like(g1), torch.empty_like(g1)
         dVr, dgr, dbr = torch.empty_like(Vr), torch.empty_like(gr), torch.empty_like(gr)
         dKs, dbs, dKt, dbt = torch.empty_like(Ks), torch.empty_like(bs), torch.empty_like(Kt), torch.empty_like(bt)
+        scratch = _new_like(x, _lib.query('bruno_heads_bwd_scratch_floats', C))
         _lib.call('bruno_coupling_conv_bwd', x, dy, dld, N, H, W, C, R, layer.mask_id, V1, g1, Vr, gr, ctx.wbwd, Ks, bs, Kt, bt,
-                  ctx.slabs, gsl, dx, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt)
+                  ctx.slabs, gsl, scratch, dx, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt)
         return dx, dld, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt, None, None, None
 
 

@@ -169,10 +169,13 @@ int bruno_heads_coupling(const float* x, const void* h_slab, const float* Ks, co
                          const float* bt, const float* ld_in, float* y, float* ld_out, int N, int H, int W, int C,
                          int mask_type, int inverse, void* stream);
 /* backward of the forward coupling: dx = direct part (the s/t-network part is added by bruno_c1_bwd), g_slab =
- * dL/d(pre-activation of the last residual block); dKs, dbs, dKt, dbt are ACCUMULATED (zero them first). */
+ * dL/d(pre-activation of the last residual block); dKs, dbs, dKt, dbt are overwritten (deterministic two-level sum:
+ * per-block partials in `scratch` of bruno_heads_bwd_scratch_floats(C) floats, then a fixed-order reduction). */
+size_t bruno_heads_bwd_scratch_floats(int C);
 int bruno_heads_coupling_bwd(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
                              const float* bt, const float* dy, const float* dld, float* dx, void* g_slab, float* dKs,
-                             float* dbs, float* dKt, float* dbt, int N, int H, int W, int C, int mask_type, void* stream);
+                             float* dbs, float* dKt, float* dbt, float* scratch, int N, int H, int W, int C, int mask_type,
+                             void* stream);
 
 /* The whole CouplingLayerConv in one call.  forward_and_jacobian (nvp:162-174) / backward (:176-187, inverse = 1).
  * Stacked parameters: V1 [C,64], g1, b1 [64] (c1); packed residual weights wfwd [2R] (order c2_0, c3_0, c2_1, ...,
@@ -188,12 +191,12 @@ int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float*
  * (weight-norm backward included: dVr, dgr are w.r.t. V and g).  saved_slabs = the 2R+1 slabs of the forward;
  * gslabs = 2R+1 zero-initialised scratch slabs (slab 0: gradient w.r.t. the c1 pre-activation, slab l+1: gradient
  * w.r.t. the pre-activation of conv layer l -- all kept so that the 2R weight gradients are ONE batched launch);
- * wbwd = dgrad operands from bruno_conv_wn_pack. */
+ * wbwd = dgrad operands from bruno_conv_wn_pack; scratch = bruno_heads_bwd_scratch_floats(C) floats. */
 int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, int N, int H, int W, int C, int R,
                             int mask_type, const float* V1, const float* g1, const float* Vr, const float* gr,
                             const void* wbwd, const float* Ks, const float* bs, const float* Kt, const float* bt,
-                            const void* saved_slabs, void* gslabs, float* dx, float* dV1, float* dg1, float* db1, float* dVr,
-                            float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt, void* stream);
+                            const void* saved_slabs, void* gslabs, float* scratch, float* dx, float* dV1, float* dg1, float* db1,
+                            float* dVr, float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt, void* stream);
 
 /* --- dense coupling layer, CouplingLayerDense (nvp:190-274) with dense_wn (:408-432), fp32 ---------------------- */
 size_t bruno_coupling_dense_ws_floats(int N, int D, int U);
