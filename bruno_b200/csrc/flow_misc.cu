@@ -308,7 +308,7 @@ heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restri
   float* bs_s = kt_s + 64 * MAXC;
   float* bt_s = bs_s + MAXC;
   float* h_s = bt_s + MAXC;                // [256][65]  (column 64 = 1 -> bias gradient)
-  float* d_s = h_s + 256 * 65;             // [256][2*MAXC]
+  float* d_s = h_s + 256 * 65;             // [256][2*MAXC + 1]  (odd row stride: the per-thread rows are bank-conflict free)
   for (int i = threadIdx.x; i < 64 * C; i += 256) {
     ks_s[i] = Ks[i];
     kt_s[i] = Kt[i];
@@ -333,7 +333,7 @@ heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restri
     const int p = p0 + threadIdx.x;
     const bool ok = p < HW;
     float h[64];
-    float* dpre = d_s + threadIdx.x * 2 * MAXC;
+    float* dpre = d_s + threadIdx.x * (2 * MAXC + 1);
     if (ok) {
       const int yy = p / g.W, xx = p % g.W;
       const size_t R = static_cast<size_t>(g.HALO) + static_cast<size_t>(n) * g.IMG + (yy + 1) * g.P + (xx + 1);
@@ -389,7 +389,7 @@ heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restri
     for (int o = threadIdx.x; o < nout; o += 256, ++ai) {
       const int k = o % 65, c2 = o / 65;
       float a = 0.f;
-      for (int pp = 0; pp < 256; ++pp) a = fmaf(h_s[pp * 65 + k], d_s[pp * 2 * MAXC + c2], a);
+      for (int pp = 0; pp < 256; ++pp) a = fmaf(h_s[pp * 65 + k], d_s[pp * (2 * MAXC + 1) + c2], a);
       acc[ai] += a;
     }
     __syncthreads();
@@ -504,7 +504,7 @@ int bruno_heads_coupling_bwd(const float* x, const void* h_slab, const float* Ks
                     C >= 1 && C <= MAXC, "bruno_heads_coupling_bwd: bad arguments");
   const SlabGeom g = slab_geom(N, H, W);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = (2 * 64 * MAXC + 2 * MAXC + 256 * 65 + 256 * 2 * MAXC) * sizeof(float);
+  const size_t smem = (2 * 64 * MAXC + 2 * MAXC + 256 * 65 + 256 * (2 * MAXC + 1)) * sizeof(float);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(heads_coupling_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

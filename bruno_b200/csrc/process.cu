@@ -13,6 +13,7 @@
 //     carrying the suffix sums of dL/dS1, dL/dS2; coefficient gradients are chained to the raw variables with the
 //     fp64 forward-mode derivatives stored by the table kernel.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -262,8 +263,8 @@ __device__ __forceinline__ bool lane_is_writer(int lane) {
 // ------------------------------------------------------------------------------------------------------------
 // forward scan
 // ------------------------------------------------------------------------------------------------------------
-template <int KIND, int VEC, int NB, bool PRIOR>
-__global__ void __launch_bounds__(256)
+template <int KIND, int VEC, int NB, bool PRIOR, int PF, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, const float* __restrict__ tab,
                    float* __restrict__ s1, float* __restrict__ s2, float* __restrict__ lp,
                    float* __restrict__ lp_prior, float* __restrict__ scratch, int B, int T, int D) {
@@ -299,21 +300,29 @@ process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
         }
     }
   }
-  // register double buffer of the observations
-  Vf<VEC> xn[NB];
+  // register ring of the observations, PF steps deep (memory-level parallelism: PF * NB 128-bit loads in flight)
+  Vf<VEC> xq[PF][NB];
 #pragma unroll
-  for (int j = 0; j < NB; ++j)
-    xn[j] = (active && b0 + j < B && T > 0) ? ldv_stream<VEC>(z + static_cast<size_t>(b0 + j) * rowTD + d0) : zerov<VEC>();
+  for (int p = 0; p < PF; ++p)
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      xq[p][j] = (active && b0 + j < B && p < T)
+                     ? ldv_stream<VEC>(z + static_cast<size_t>(b0 + j) * rowTD + static_cast<size_t>(p) * D + d0)
+                     : zerov<VEC>();
 
-  for (int n = 0; n < T; ++n) {
+  for (int n0 = 0; n0 < T; n0 += PF) {
+#pragma unroll
+   for (int pp = 0; pp < PF; ++pp) {
+    const int n = n0 + pp;
+    if (n >= T) break;
     Vf<VEC> x[NB];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) x[j] = xn[j];
-    if (n + 1 < T) {
+    for (int j = 0; j < NB; ++j) x[j] = xq[pp][j];
+    if (n + PF < T) {
 #pragma unroll
       for (int j = 0; j < NB; ++j)
         if (active && b0 + j < B)
-          xn[j] = ldv_stream<VEC>(z + static_cast<size_t>(b0 + j) * rowTD + static_cast<size_t>(n + 1) * D + d0);
+          xq[pp][j] = ldv_stream<VEC>(z + static_cast<size_t>(b0 + j) * rowTD + static_cast<size_t>(n + PF) * D + d0);
     }
     Vf<VEC> cf[NCF];
 #pragma unroll
@@ -349,6 +358,7 @@ process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
     }
     warp_multi_reduce<NV>(vals, lane);
     if (lane_is_writer<NV>(lane)) sred[(n * nwarps + warp) * NV + slot_of_lane<NV>(lane)] = vals[0];
+   }
   }
   __syncthreads();
   const int nseg = gridDim.y;
@@ -644,16 +654,18 @@ static ScanGeom scan_geom(int D, bool ptr_ok) {
   return g;
 }
 
-constexpr int FWD_NB = 4;
 constexpr int BWD_NB = 2;
 
-template <int KIND, int VEC>
-static int launch_fwd(const float* z, const float* mu0, const float* table, float* s1, float* s2, float* lp,
-                      float* lp_prior, float* scratch, int B, int T, int D, const ScanGeom& g, cudaStream_t st) {
-  dim3 grid(ceil_div(B, FWD_NB), g.nseg);
-  const size_t smem = static_cast<size_t>(T) * (g.threads / 32) * FWD_NB * 2 * sizeof(float);
-  auto kp = process_fwd_kernel<KIND, VEC, FWD_NB, true>;
-  auto kn = process_fwd_kernel<KIND, VEC, FWD_NB, false>;
+// Variants of the forward scan (rows per thread NB, prefetch depth PF, resident blocks MINB), picked for occupancy /
+// memory-level parallelism: the first version (NB 4, PF 1, 128 registers, 14 warps per SM) reached 72 % of HBM peak for
+// the GP but only 36 % for the TP, whose 3 MUFU + ~17 FP ops per element need more warps to hide latency.
+template <int KIND, int VEC, int NB, int PF, int MINB>
+static int launch_fwd_variant(const float* z, const float* mu0, const float* table, float* s1, float* s2, float* lp,
+                              float* lp_prior, float* scratch, int B, int T, int D, const ScanGeom& g, cudaStream_t st) {
+  dim3 grid(ceil_div(B, NB), g.nseg);
+  const size_t smem = static_cast<size_t>(T) * (g.threads / 32) * NB * 2 * sizeof(float);
+  auto kp = process_fwd_kernel<KIND, VEC, NB, true, PF, MINB>;
+  auto kn = process_fwd_kernel<KIND, VEC, NB, false, PF, MINB>;
   auto k = lp_prior ? kp : kn;
   if (smem > 48 * 1024) {
     if (smem > 200 * 1024) {
@@ -674,6 +686,26 @@ static int launch_fwd(const float* z, const float* mu0, const float* table, floa
     rc = check_launch("process_fwd_finalize");
   }
   return rc;
+}
+
+static int fwd_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BRUNO_TP_VARIANT");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+template <int KIND, int VEC>
+static int launch_fwd(const float* z, const float* mu0, const float* table, float* s1, float* s2, float* lp,
+                      float* lp_prior, float* scratch, int B, int T, int D, const ScanGeom& g, cudaStream_t st) {
+  switch (fwd_variant()) {
+    case 0: return launch_fwd_variant<KIND, VEC, 4, 1, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+    case 2: return launch_fwd_variant<KIND, VEC, 1, 4, 4>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+    case 3: return launch_fwd_variant<KIND, VEC, 2, 4, 3>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+    default: return launch_fwd_variant<KIND, VEC, 2, 2, 4>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+  }
 }
 
 static int bwd_blocks(int B) {
