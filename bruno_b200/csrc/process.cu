@@ -270,6 +270,8 @@ process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
                    float* __restrict__ lp_prior, float* __restrict__ scratch, int B, int T, int D) {
   constexpr int NCF = ncf_of(KIND);
   constexpr int NV = NB * 2;
+  constexpr int RS = 32 / NV;      // steps whose partial sums are reduced together: ONE 32-value butterfly per RS steps
+  static_assert(RS % PF == 0, "prefetch depth must divide the reduce batch");
   extern __shared__ float sred[];  // [T][nwarps][NV]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int d0 = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
@@ -278,6 +280,7 @@ process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
   const size_t rowTD = static_cast<size_t>(T) * D;
 
   Vf<VEC> S1[NB], S2[NB], mu = zerov<VEC>(), pc[N_PRIOR];
+  Vf<VEC> c_e = zerov<VEC>(), c_a0 = zerov<VEC>(), c_da = zerov<VEC>();   // TP: coefficients that need no per-step load
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
     S1[j] = zerov<VEC>();
@@ -290,6 +293,14 @@ process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
     if (PRIOR) {
 #pragma unroll
       for (int i = 0; i < N_PRIOR; ++i) pc[i] = ldv<VEC>(tab + static_cast<size_t>(T * NCF + i) * D + d0);
+    }
+    if (KIND == BRUNO_TP) {
+      // e' = 1 / ((v - c)(nu0 - 2)) does not depend on the step; A2_n = A2_0 + n dA, B2_n = A2_n - dA (dA = m ln2 / 2)
+      c_e = ldv<VEC>(tab + static_cast<size_t>(2) * D + d0);
+      c_a0 = ldv<VEC>(tab + static_cast<size_t>(5) * D + d0);
+      const Vf<VEC> b0v = ldv<VEC>(tab + static_cast<size_t>(6) * D + d0);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) c_da.x[e] = c_a0.x[e] - b0v.x[e];
     }
     if (s1 != nullptr) {
 #pragma unroll
@@ -310,55 +321,69 @@ process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
                      ? ldv_stream<VEC>(z + static_cast<size_t>(b0 + j) * rowTD + static_cast<size_t>(p) * D + d0)
                      : zerov<VEC>();
 
-  for (int n0 = 0; n0 < T; n0 += PF) {
+  for (int n0 = 0; n0 < T; n0 += RS) {
+    float vals[32];
 #pragma unroll
-   for (int pp = 0; pp < PF; ++pp) {
-    const int n = n0 + pp;
-    if (n >= T) break;
-    Vf<VEC> x[NB];
+    for (int pp = 0; pp < RS; ++pp) {
+      const int n = n0 + pp;
+      const bool live = n < T;
+      Vf<VEC> x[NB];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) x[j] = xq[pp][j];
-    if (n + PF < T) {
+      for (int j = 0; j < NB; ++j) x[j] = xq[pp % PF][j];
+      if (n + PF < T) {
 #pragma unroll
-      for (int j = 0; j < NB; ++j)
-        if (active && b0 + j < B)
-          xq[pp][j] = ldv_stream<VEC>(z + static_cast<size_t>(b0 + j) * rowTD + static_cast<size_t>(n + PF) * D + d0);
-    }
-    Vf<VEC> cf[NCF];
-#pragma unroll
-    for (int i = 0; i < NCF; ++i)
-      cf[i] = active ? ldv<VEC>(tab + static_cast<size_t>(n * NCF + i) * D + d0) : zerov<VEC>();
-
-    float vals[NV];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      float acc = 0.f, accp = 0.f;
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const float xz = x[j].x[e] - mu.x[e];
-        if constexpr (KIND == BRUNO_TP) {
-          const float s1v = S1[j].x[e];
-          const float r = fmaf(-cf[1].x[e], s1v, cf[0].x[e] * xz);
-          const float q = fmaf(cf[3].x[e], s1v * s1v, fmaf(cf[2].x[e], S2[j].x[e], 1.f));
-          const float u = fmaf(r, r, q);
-          acc += fmaf(cf[6].x[e], fast_lg2(q), fmaf(-cf[5].x[e], fast_lg2(u), cf[4].x[e]));
-          if (PRIOR) accp += fmaf(-pc[2].x[e], fast_lg2(fmaf(xz * xz, pc[0].x[e], 1.f)), pc[1].x[e]);
-          S1[j].x[e] = s1v + xz;
-          S2[j].x[e] = fmaf(xz, xz, S2[j].x[e]);
-        } else {
-          const float r = fmaf(-cf[0].x[e], S1[j].x[e], xz);
-          acc += fmaf(-cf[1].x[e], r * r, cf[2].x[e]);
-          if (PRIOR) accp += fmaf(-pc[0].x[e], xz * xz, pc[1].x[e]);
-          S1[j].x[e] += xz;
-        }
+        for (int j = 0; j < NB; ++j)
+          if (active && b0 + j < B)
+            xq[pp % PF][j] = ldv_stream<VEC>(z + static_cast<size_t>(b0 + j) * rowTD + static_cast<size_t>(n + PF) * D + d0);
       }
-      const bool ok = active && (b0 + j < B);
-      vals[2 * j] = ok ? acc : 0.f;
-      vals[2 * j + 1] = ok ? accp : 0.f;
+      const bool ld = active && live;
+      Vf<VEC> cw, cdd, cf3, cC;   // TP: w, dd w, f', C;   GP: dd, I, C in cw, cdd, cC
+      if (KIND == BRUNO_TP) {
+        cw = ld ? ldv<VEC>(tab + static_cast<size_t>(n * NCF + 0) * D + d0) : zerov<VEC>();
+        cdd = ld ? ldv<VEC>(tab + static_cast<size_t>(n * NCF + 1) * D + d0) : zerov<VEC>();
+        cf3 = ld ? ldv<VEC>(tab + static_cast<size_t>(n * NCF + 3) * D + d0) : zerov<VEC>();
+        cC = ld ? ldv<VEC>(tab + static_cast<size_t>(n * NCF + 4) * D + d0) : zerov<VEC>();
+      } else {
+        cw = ld ? ldv<VEC>(tab + static_cast<size_t>(n * NCF + 0) * D + d0) : zerov<VEC>();
+        cdd = ld ? ldv<VEC>(tab + static_cast<size_t>(n * NCF + 1) * D + d0) : zerov<VEC>();
+        cC = ld ? ldv<VEC>(tab + static_cast<size_t>(n * NCF + 2) * D + d0) : zerov<VEC>();
+        cf3 = zerov<VEC>();
+      }
+      const float fn = static_cast<float>(n);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        float acc = 0.f, accp = 0.f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float xz = x[j].x[e] - mu.x[e];
+          if constexpr (KIND == BRUNO_TP) {
+            const float s1v = S1[j].x[e];
+            const float a2 = fmaf(fn, c_da.x[e], c_a0.x[e]);
+            const float r = fmaf(-cdd.x[e], s1v, cw.x[e] * xz);
+            const float q = fmaf(cf3.x[e], s1v * s1v, fmaf(c_e.x[e], S2[j].x[e], 1.f));
+            const float u = fmaf(r, r, q);
+            acc += fmaf(a2 - c_da.x[e], fast_lg2(q), fmaf(-a2, fast_lg2(u), cC.x[e]));
+            if (PRIOR) accp += fmaf(-pc[2].x[e], fast_lg2(fmaf(xz * xz, pc[0].x[e], 1.f)), pc[1].x[e]);
+            S1[j].x[e] = s1v + xz;
+            S2[j].x[e] = fmaf(xz, xz, S2[j].x[e]);
+          } else {
+            const float r = fmaf(-cw.x[e], S1[j].x[e], xz);
+            acc += fmaf(-cdd.x[e], r * r, cC.x[e]);
+            if (PRIOR) accp += fmaf(-pc[0].x[e], xz * xz, pc[1].x[e]);
+            S1[j].x[e] += xz;
+          }
+        }
+        const bool ok = ld && (b0 + j < B);
+        vals[pp * NV + 2 * j] = ok ? acc : 0.f;
+        vals[pp * NV + 2 * j + 1] = ok ? accp : 0.f;
+      }
     }
-    warp_multi_reduce<NV>(vals, lane);
-    if (lane_is_writer<NV>(lane)) sred[(n * nwarps + warp) * NV + slot_of_lane<NV>(lane)] = vals[0];
-   }
+    warp_multi_reduce<32>(vals, lane);
+    {
+      const int slot = slot_of_lane<32>(lane);     // = pp * NV + idx
+      const int n = n0 + slot / NV;
+      if (n < T) sred[(n * nwarps + warp) * NV + (slot % NV)] = vals[0];
+    }
   }
   __syncthreads();
   const int nseg = gridDim.y;
@@ -701,10 +726,10 @@ template <int KIND, int VEC>
 static int launch_fwd(const float* z, const float* mu0, const float* table, float* s1, float* s2, float* lp,
                       float* lp_prior, float* scratch, int B, int T, int D, const ScanGeom& g, cudaStream_t st) {
   switch (fwd_variant()) {
-    case 0: return launch_fwd_variant<KIND, VEC, 4, 1, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
-    case 2: return launch_fwd_variant<KIND, VEC, 1, 4, 4>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+    case 0: return launch_fwd_variant<KIND, VEC, 4, 1, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+    case 2: return launch_fwd_variant<KIND, VEC, 2, 2, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
     case 3: return launch_fwd_variant<KIND, VEC, 2, 4, 3>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
-    default: return launch_fwd_variant<KIND, VEC, 2, 2, 4>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+    default: return launch_fwd_variant<KIND, VEC, 4, 2, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
   }
 }
 
