@@ -364,13 +364,15 @@ process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
             const float u = fmaf(r, r, q);
             acc += fmaf(a2 - c_da.x[e], fast_lg2(q), fmaf(-a2, fast_lg2(u), cC.x[e]));
             if (PRIOR) accp += fmaf(-pc[2].x[e], fast_lg2(fmaf(xz * xz, pc[0].x[e], 1.f)), pc[1].x[e]);
-            S1[j].x[e] = s1v + xz;
-            S2[j].x[e] = fmaf(xz, xz, S2[j].x[e]);
+            if (live) {                      // padded steps of the last reduce batch must not touch the state
+              S1[j].x[e] = s1v + xz;
+              S2[j].x[e] = fmaf(xz, xz, S2[j].x[e]);
+            }
           } else {
             const float r = fmaf(-cw.x[e], S1[j].x[e], xz);
             acc += fmaf(-cdd.x[e], r * r, cC.x[e]);
             if (PRIOR) accp += fmaf(-pc[0].x[e], xz * xz, pc[1].x[e]);
-            S1[j].x[e] += xz;
+            if (live) S1[j].x[e] += xz;
           }
         }
         const bool ok = ld && (b0 + j < B);
@@ -717,7 +719,7 @@ static int fwd_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("BRUNO_TP_VARIANT");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 0;
   }
   return v;
 }
