@@ -199,6 +199,20 @@ def main():
         eval_resident(i)
     ms_eval = timed(eval_resident, steps)
 
+    # 20-way 1-shot scoring episodes (test_few_shot_omniglot: batch 20, seq_len 2, forward only) -- latency-bound case
+    from bruno_b200.synthetic_data import SyntheticFewShotIterator
+    fs_it = SyntheticFewShotIterator(seq_len=2, batch_size=20, obs_shape=(H, W, C), rng=np.random.RandomState(7 + rank), n_classes=24)
+    fs_x = [torch.from_numpy(e[0]).to(dev) for e, _ in zip(fs_it.generate(), range(4))]
+
+    def few_shot(i):
+        with torch.no_grad():
+            cfg.build_model(fs_x[i % 4], want_prior=False)[0][:, -1].argmax()
+
+    for i in range(3):
+        few_shot(i)
+    fs_steps = max(steps, 10)
+    ms_fs = timed(few_shot, fs_steps)
+
     # second pass with per-launch CUDA events on the conv kernels (live durations inside the step)
     _lib.query('bruno_profile_enable', 1)
     timed(train_resident, steps)
@@ -238,6 +252,8 @@ def main():
                    'l2_note': 'working set per step (6.3 GB of saved bf16 activations) >> 126 MB L2; inputs rotate over %d batches' % n_host},
         'eval_nll': {'value': seqs * steps / (ms_eval * 1e-3), 'unit': 'seqs/s', 'ms_per_step': ms_eval / steps,
                      'what': 'forward NLL (log_probs, latent, prior) of the same batch shape'},
+        'few_shot_20way_1shot': {'value': world * fs_steps / (ms_fs * 1e-3), 'unit': 'episodes/s', 'ms_per_episode': ms_fs / fs_steps,
+                                 'what': 'test_few_shot_omniglot scoring: 20 candidate sequences x 2 frames, forward + argmax'},
         'e2e': {'value': seqs * steps / (ms_e2e * 1e-3), 'unit': 'seqs/s', 'h2d_bytes_per_step': int(host[0].numel() * 4),
                 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / steps},
         'gpu_launches': int(launches),
