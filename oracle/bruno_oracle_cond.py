@@ -1,0 +1,321 @@
+"""CPU oracle for CONDITIONAL BRUNO (config_conditional/m1_shapenet.py on nn_extra_nvp_conditional.py) -- TEST
+INFRASTRUCTURE ONLY, same rules as bruno_oracle.py (never imported by the product package).
+
+Pinning status: "parity unpinned" -- the reference ships no test / golden vector for the conditional path; pinned by the
+same self-consistency checks as the unconditional flow (invertibility; the GP recurrence itself is pinned through
+bruno_oracle.GaussOracle against tests_gp_tp/utils_stats.py).
+
+Restates, with the reference file:line next to each function (paths relative to /root/reference):
+  * label-conditioned weight-normalised conv / dense layers      nn_extra_nvp_conditional.py:396-471
+  * label-conditioned plain conv / dense heads                    nn_extra_nvp_conditional.py:350-392
+  * coupling layers (conv ResNet with num_res_blocks, dense)      nn_extra_nvp_conditional.py:34-266
+  * pre-processing without the ln(1 - alpha) term                 nn_extra_nvp_conditional.py:10-24
+  * build_model with n_context and the GP latent                  config_conditional/m1_shapenet.py:46-140
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import bruno_oracle as O
+
+LEAK = 0.2        # tf.nn.leaky_relu default alpha  [TF-1.7 semantics]
+
+
+class CondSpec(object):
+    def __init__(self, obs_hwc=(32, 32, 1), batch_size=4, label_dim=2, label_units=32, num_scales=3, num_filters=64,
+                 num_res_blocks=6, n_units=256, corr_init=0.1, var_init=1.0):
+        self.name = 'm1_shapenet'
+        self.obs_hwc = tuple(obs_hwc)
+        self.batch_size = batch_size
+        self.label_dim, self.label_units = label_dim, label_units
+        self.num_filters, self.num_res_blocks, self.n_units = num_filters, num_res_blocks, n_units
+        self.corr_init, self.var_init = corr_init, var_init
+        self.process = 'gp'
+        layers = []                                                   # m1_shapenet.py:143-198
+        for scale in range(num_scales - 1):
+            for i, m in enumerate(['checkerboard0', 'checkerboard1', 'checkerboard0']):
+                layers.append(('conv', m, 'Checkerboard%d_%d' % (scale, i + 1)))
+            layers.append(('squeeze', 'Squeeze%d' % scale))
+            for i, m in enumerate(['channel0', 'channel1', 'channel0']):
+                layers.append(('conv', m, 'Channel%d_%d' % (scale, i + 1)))
+            layers.append(('factor', scale, 'FactorOut%d' % scale))
+        scale = num_scales - 1
+        for i, m in enumerate(['checkerboard0', 'checkerboard1', 'checkerboard0', 'checkerboard1']):
+            layers.append(('conv', m, 'Checkerboard%d_%d' % (scale, i + 1)))
+        layers.append(('factor', scale, 'FactorOut%d' % scale))
+        self.conv_layers = layers
+        self.dense_layers = O._dense_stack()                         # m1_shapenet.py:201-209
+
+    @property
+    def ndim(self):
+        return int(np.prod(self.obs_hwc))
+
+
+def leaky(x):
+    return F.leaky_relu(x, LEAK)
+
+
+def _dense_wn(x, P, scope, act=None, init=False):
+    """dense_wn without label, nn_extra_nvp_conditional.py:439-459 (b exists and is added even when use_bias=False)."""
+    return O.dense_wn(x, P, scope, nonlinearity=act, init=init)
+
+
+def conv2d_wn_label(x, y_label, P, scope, act, init=False):
+    """conv2d_wn(..., y_label), nn_extra_nvp_conditional.py:422-433: conv_wn(x) + dense_wn(y_label)[:, None, None, :]."""
+    h = _dense_wn(y_label, P, scope + '/label_h', None, init)
+    out = O._wn_conv_pre(x, P, scope + '/conv_h', init, quant_w=O.EMULATE_BF16 and P[scope + '/conv_h/V'].shape[0] == 3)
+    out = out + h[:, None, None, :]
+    return out if act is None else act(out)
+
+
+def conv2d_label(x, y_label, P, scope, act):
+    """conv2d(..., y_label), nn_extra_nvp_conditional.py:372-392 (plain tf.layers.conv2d + bias-free label dense)."""
+    name = scope.rsplit('/', 1)[1]
+    h = y_label @ P[scope + '/label_h/kernel']
+    out = O._conv_nhwc(x, P['%s/%s/kernel' % (scope, name)]) + P['%s/%s/bias' % (scope, name)]
+    out = out + h[:, None, None, :]
+    return out if act is None else act(out)
+
+
+def dense_wn_label(x, y_label, P, scope, act, init=False):
+    """dense_wn(..., y_label), nn_extra_nvp_conditional.py:461-471."""
+    name = scope.rsplit('/', 1)[1]
+    h = _dense_wn(y_label, P, scope + '/label_h', leaky, init)
+    o1 = torch.cat([h, x], -1)
+    return _dense_wn(o1, P, '%s/%s' % (scope, name), act, init)
+
+
+def dense_label(x, y_label, P, scope, act):
+    """dense(..., y_label), nn_extra_nvp_conditional.py:350-369."""
+    name = scope.rsplit('/', 1)[1]
+    h = leaky(y_label @ P[scope + '/label_W1/kernel'] + P[scope + '/label_W1/bias'])
+    o1 = torch.cat([h, x], -1)
+    out = o1 @ P['%s/%s/kernel' % (scope, name)] + P['%s/%s/bias' % (scope, name)]
+    return out if act is None else act(out)
+
+
+def s_t_conv(x1, mask, y_label, P, layer, R, init):
+    """CouplingLayerConv.function_s_t_wn, nn_extra_nvp_conditional.py:83-113."""
+    sc = layer + '/function_s_t_wn'
+    y = O._act_store(conv2d_wn_label(x1, y_label, P, sc + '/c1', None, init))
+    skip = y
+    for r in range(R):
+        y = O._act_store(conv2d_wn_label(y, y_label, P, sc + '/c2_%d' % r, None, init))
+        y = conv2d_wn_label(y, y_label, P, sc + '/c3_%d' % r, None, init)
+        y = O._act_store(y + skip)
+        skip = y
+    s = conv2d_label(y, y_label, P, sc + '/conv_out_scale', torch.tanh) * (1 - mask)
+    t = conv2d_label(y, y_label, P, sc + '/conv_out_translation', None) * (1 - mask)
+    return s, t
+
+
+def s_t_dense(x1, mask, y_label, P, layer, init):
+    """CouplingLayerDense.function_s_t_wn, nn_extra_nvp_conditional.py:240-266."""
+    sc = layer + '/function_s_t_dense_wn'
+    xs = x1.shape
+    y = x1.reshape(xs[0], -1)
+    y = dense_wn_label(y, y_label, P, sc + '/d1', O.elu, init)
+    y = dense_wn_label(y, y_label, P, sc + '/d2', O.elu, init)
+    s = dense_label(y, y_label, P, sc + '/d_scale', torch.tanh).reshape(xs) * (1 - mask)
+    t = dense_label(y, y_label, P, sc + '/d_translate', None).reshape(xs) * (1 - mask)
+    return s, t
+
+
+def label_embedding(y_label_bs, P):
+    """labels_layer, m1_shapenet.py:66-67: plain dense 2 -> 32 with leaky_relu."""
+    return leaky(y_label_bs @ P['model/labels_layer/kernel'] + P['model/labels_layer/bias'])
+
+
+def pre_forward(x_bs):
+    """dequantization + logit without ln(1 - alpha), nn_extra_nvp_conditional.py:10-24."""
+    d = x_bs.shape[1] * x_bs.shape[2] * x_bs.shape[3]
+    alpha = 1e-5
+    y = x_bs / 256.0
+    ld = torch.zeros(x_bs.shape[0], dtype=x_bs.dtype) - math.log(256.0) * d
+    y = y * (1 - alpha) + alpha * 0.5
+    ld = ld + (-torch.log(y) - torch.log(1 - y)).sum(dim=(1, 2, 3))
+    return torch.log(y) - torch.log(1.0 - y), ld
+
+
+def flow_forward(spec, P, x_bs, yl, init=False):
+    dtype = x_bs.dtype
+    if O.EMULATE_BF16:
+        y, ld = pre_forward(x_bs.float())
+        y, ld = y.to(dtype), ld.to(dtype)
+    else:
+        y, ld = pre_forward(x_bs)
+    z = None
+    for layer in spec.conv_layers:
+        if layer[0] == 'conv':
+            _, mtype, name = layer
+            b = O.conv_mask(y.shape, mtype, dtype)
+            s, t = s_t_conv(y * b, b, yl, P, 'model/' + name, spec.num_res_blocks, init)
+            y, ld = O.coupling_forward(y, ld, s, t, b)
+        elif layer[0] == 'squeeze':
+            y = O.space_to_depth(y)
+            if z is not None:
+                z = O.space_to_depth(z)
+        else:
+            split = y.shape[3] // 2
+            new_z, y = y[..., :split], y[..., split:]
+            z = new_z if z is None else torch.cat([z, new_z], 3)
+    y = torch.cat([z, y], 3)                                          # m1:78
+    for mtype, name in spec.dense_layers:
+        b = O.dense_mask(y.shape, mtype, dtype)
+        s, t = s_t_dense(y * b, b, yl, P, 'model/' + name, init)
+        y, ld = O.coupling_forward(y, ld, s, t, b)
+    return y, ld
+
+
+def flow_inverse(spec, P, z_img, yl):
+    """m1:124-135: dense backward, conv backward, then the bare sigmoid (no alpha correction, no x256, no log-det)."""
+    dtype = z_img.dtype
+    z = z_img
+    ld = torch.zeros(z.shape[0], dtype=dtype)
+    for mtype, name in reversed(spec.dense_layers):
+        b = O.dense_mask(z.shape, mtype, dtype)
+        s, t = s_t_dense(z * b, b, yl, P, 'model/' + name, False)
+        z, ld = O.coupling_backward(z, ld, s, t, b)
+    x = None
+    for layer in reversed(spec.conv_layers):
+        if layer[0] == 'conv':
+            _, mtype, name = layer
+            b = O.conv_mask(x.shape, mtype, dtype)
+            s, t = s_t_conv(x * b, b, yl, P, 'model/' + name, spec.num_res_blocks, False)
+            x, ld = O.coupling_backward(x, ld, s, t, b)
+        elif layer[0] == 'squeeze':
+            x = O.depth_to_space(x)
+            if z is not None and z.shape[3] > 0:
+                z = O.depth_to_space(z)
+        else:
+            scale = layer[1]
+            split = z.shape[3] // (2 ** scale) if x is None else x.shape[3]
+            new_y, z = z[..., z.shape[3] - split:], z[..., :z.shape[3] - split]
+            x = new_y if x is None else torch.cat([new_y, x], 3)
+    return torch.sigmoid(x)
+
+
+def build_model(spec, P, x, y_label, n_context=1, init=False):
+    """m1_shapenet.py:46-140, non-sampling branch: log_probs [B, T - n_context] (or [B, T] if n_context == 0)."""
+    B, T = x.shape[0], x.shape[1]
+    yl = label_embedding(y_label.reshape(B * T, -1), P)
+    z, ld = flow_forward(spec, P, x.reshape((B * T,) + tuple(x.shape[2:])), yl, init=init)
+    z_vec = z.reshape(B, T, -1)
+    ld = ld.reshape(B, T)
+    proc = O.GaussOracle(P)
+    proc.reset()
+    out = []
+    if n_context > 0:
+        for i in range(n_context):
+            proc.update_distribution(z_vec[:, i, :])
+        for i in range(n_context, T):                                 # no update after the context (m1:104-109)
+            out.append(proc.get_log_likelihood(z_vec[:, i, :]) + ld[:, i])
+    else:
+        for i in range(T):
+            out.append(proc.get_log_likelihood(z_vec[:, i, :]) + ld[:, i])
+            proc.update_distribution(z_vec[:, i, :])
+    return torch.stack(out, 1), z_vec
+
+
+def build_model_sampling(spec, P, x, y_label, noise, n_context=1):
+    """sampling branch (m1:86-99, 118-138): z_sample per step from the current GP, then the inverse flow."""
+    B, T = x.shape[0], x.shape[1]
+    yl = label_embedding(y_label.reshape(B * T, -1), P)
+    z, _ = flow_forward(spec, P, x.reshape((B * T,) + tuple(x.shape[2:])), yl)
+    zshape = z.shape
+    z_vec = z.reshape(B, T, -1)
+    proc = O.GaussOracle(P)
+    proc.reset()
+    samples = []
+    if n_context > 0:
+        for i in range(n_context):
+            proc.update_distribution(z_vec[:, i, :])
+        for i in range(T):
+            samples.append(proc.sample_from_normals(noise[i]))
+    else:
+        for i in range(T):
+            samples.append(proc.sample_from_normals(noise[i]))
+            proc.update_distribution(z_vec[:, i, :])
+    zs = torch.cat(samples, 1)                                         # each sample [1, B, D] -> cat on axis 1
+    zs = zs.reshape(zshape)
+    xs = flow_inverse(spec, P, zs, yl)
+    return xs
+
+
+def init_params(spec, seed=0, dtype=torch.float64, randomize_heads=True, perturb_process=False):
+    g = torch.Generator().manual_seed(seed)
+    P = OrderedDict()
+
+    def normal(*shape, std=0.05):
+        return (torch.randn(*shape, generator=g, dtype=torch.float64) * std).to(dtype)
+
+    def wn(scope, shape):
+        P[scope + '/V'] = normal(*shape)
+        P[scope + '/g'] = torch.ones(shape[-1], dtype=dtype)
+        P[scope + '/b'] = torch.zeros(shape[-1], dtype=dtype)
+
+    L, Fn = spec.label_units, spec.num_filters
+    P['model/labels_layer/kernel'] = normal(spec.label_dim, L, std=0.5)
+    P['model/labels_layer/bias'] = normal(L, std=0.1)
+    H, W, C = spec.obs_hwc
+    c = C
+    for layer in spec.conv_layers:
+        if layer[0] == 'squeeze':
+            c *= 4
+        elif layer[0] == 'factor':
+            c //= 2
+        else:
+            sc = 'model/%s/function_s_t_wn' % layer[2]
+            convs = [('c1', (1, 1, c, Fn))]
+            for r in range(spec.num_res_blocks):
+                convs += [('c2_%d' % r, (3, 3, Fn, Fn)), ('c3_%d' % r, (3, 3, Fn, Fn))]
+            for nm, shp in convs:
+                wn('%s/%s/label_h' % (sc, nm), (L, Fn))
+                wn('%s/%s/conv_h' % (sc, nm), shp)
+            for nm in ('conv_out_scale', 'conv_out_translation'):
+                P['%s/%s/label_h/kernel' % (sc, nm)] = normal(L, c, std=0.05 if randomize_heads else 0.0)
+                P['%s/%s/%s/kernel' % (sc, nm, nm)] = normal(1, 1, Fn, c) if randomize_heads else torch.zeros(1, 1, Fn, c, dtype=dtype)
+                P['%s/%s/%s/bias' % (sc, nm, nm)] = normal(c) if randomize_heads else torch.zeros(c, dtype=dtype)
+    D, U = spec.ndim, spec.n_units
+    for _, name in spec.dense_layers:
+        sc = 'model/%s/function_s_t_dense_wn' % name
+        for nm, din in (('d1', D), ('d2', U)):
+            wn('%s/%s/label_h' % (sc, nm), (L, din // 2))
+            wn('%s/%s/%s' % (sc, nm, nm), (din // 2 + din, U))
+        for nm in ('d_scale', 'd_translate'):
+            P['%s/%s/label_W1/kernel' % (sc, nm)] = normal(L, U // 2, std=0.3)
+            P['%s/%s/label_W1/bias' % (sc, nm)] = normal(U // 2, std=0.1)
+            P['%s/%s/%s/kernel' % (sc, nm, nm)] = normal(U // 2 + U, D) if randomize_heads else torch.zeros(U // 2 + U, D, dtype=dtype)
+            P['%s/%s/%s/bias' % (sc, nm, nm)] = normal(D) if randomize_heads else torch.zeros(D, dtype=dtype)
+    if perturb_process:
+        u = torch.rand(2, D, generator=g, dtype=torch.float64)
+        var, corr = 0.5 + 1.5 * u[0], 0.01 + 0.89 * u[1]
+    else:
+        var = torch.full((D,), spec.var_init, dtype=torch.float64)
+        corr = torch.full((D,), spec.corr_init, dtype=torch.float64)
+    sq = torch.sqrt(var)
+    P['model/gaussian/prior_var'] = (torch.log(-torch.expm1(-sq)) + sq).view(1, D).to(dtype)
+    P['model/gaussian/prior_corr'] = (torch.log(corr) - torch.log1p(-corr)).view(1, D).to(dtype)
+    return P
+
+
+def data_dependent_init(spec, P, x, y_label, n_context=1):
+    with torch.no_grad():
+        build_model(spec, P, x, y_label, n_context=n_context, init=True)
+    return P
+
+
+def synthetic_batch(spec, batch_size, seq_len, seed=42, dtype=torch.float64):
+    """ShapeNet-shaped stand-in: pixels {0..255} + U[0,1) and labels (sin t, cos t), t in {0,10,...,350} degrees
+    (utils_conditional.py:138-148)."""
+    rs = np.random.RandomState(seed)
+    H, W, C = spec.obs_hwc
+    shape = (batch_size, seq_len, H, W, C)
+    pix = rs.randint(0, 256, size=shape).astype(np.float64)
+    x = pix + np.random.RandomState(317070).uniform(size=shape)
+    ang = np.deg2rad(rs.randint(0, 36, size=(batch_size, seq_len)) * 10.0)
+    y = np.stack([np.sin(ang), np.cos(ang)], -1)
+    return torch.from_numpy(x).to(dtype), torch.from_numpy(y).to(dtype)
