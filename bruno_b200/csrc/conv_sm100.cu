@@ -98,7 +98,7 @@ template <int MODE>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
                const uint8_t* __restrict__ aux1, const uint8_t* __restrict__ aux2, uint8_t* __restrict__ out,
-               SlabGeom g, int ntiles) {
+               SlabGeom g, int ntiles, int bias_img_stride) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int slab_rows = TILE_M + 2 * g.HALO + 8;
@@ -204,9 +204,11 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
     // row bookkeeping without integer division in the loop: q_img = data_row mod IMG advances by a constant per tile
     const int tile_stride = 2 * gridDim.x;
     const int step_mod = (OUT_ROWS * tile_stride) % g.IMG;
+    const int step_div = (OUT_ROWS * tile_stride) / g.IMG;
     int tile = blockIdx.x + grp * gridDim.x;
     int data_row = OUT_ROWS * tile - 1 + row;
     int q_img = ((data_row % g.IMG) + g.IMG) % g.IMG;
+    int n_img = (data_row - q_img) / g.IMG;     // image index of the row (for per-image biases)
     const float inv_p = 1.0f / static_cast<float>(g.P);
     int it = grp;
     for (; tile < ntiles; tile += tile_stride, it += 2) {
@@ -280,8 +282,11 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = acc[jj * 8 + e];
             if (HAS_BIAS) {
-              const float4 b0 = *reinterpret_cast<const float4*>(&cs->bias[j * 8]);
-              const float4 b1 = *reinterpret_cast<const float4*>(&cs->bias[j * 8 + 4]);
+              // shared bias from smem, or the per-image bias table of the label-conditioned layers [N][64]
+              const float* bsrc = bias_img_stride ? bias + static_cast<size_t>(valid ? n_img : 0) * bias_img_stride + j * 8
+                                                  : &cs->bias[j * 8];
+              const float4 b0 = *reinterpret_cast<const float4*>(bsrc);
+              const float4 b1 = *reinterpret_cast<const float4*>(bsrc + 4);
               bj[0] = b0.x; bj[1] = b0.y; bj[2] = b0.z; bj[3] = b0.w; bj[4] = b1.x; bj[5] = b1.y; bj[6] = b1.z; bj[7] = b1.w;
             }
             if (MODE == MODE_ELU || MODE == MODE_LINEAR) {
@@ -316,7 +321,11 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       mbar_arrive(&cs->outready[a]);
       data_row += OUT_ROWS * tile_stride;
       q_img += step_mod;
-      if (q_img >= g.IMG) q_img -= g.IMG;
+      n_img += step_div;
+      if (q_img >= g.IMG) {
+        q_img -= g.IMG;
+        ++n_img;
+      }
     }
   } else {
     // ===== aux / store warp: prefetch the aux tile(s) of tile `it`, then drain the output tile of tile `it - 1` =====
@@ -611,8 +620,8 @@ static int num_sms() {
 }
 
 template <int MODE>
-static int launch_conv(const void* in, const void* w, const float* bias, const void* a1, const void* a2, void* out,
-                       const SlabGeom& g, cudaStream_t st) {
+static int launch_conv(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
+                       const void* a2, void* out, const SlabGeom& g, cudaStream_t st) {
   const size_t smem = conv_smem_bytes(g, MODE);
   static bool configured = false;
   if (!configured) {
@@ -624,7 +633,7 @@ static int launch_conv(const void* in, const void* w, const float* bias, const v
   ProfSpan span(BRUNO_PROF_CONV, st);
   conv3x3_kernel<MODE><<<grid, FWD_THREADS, smem, st>>>(
       static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias, static_cast<const uint8_t*>(a1),
-      static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g, ntiles);
+      static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g, ntiles, bias_img_stride);
   return check_launch("conv3x3_kernel");
 }
 
@@ -664,8 +673,9 @@ int bruno_conv_wn_bwd(const float* V, const float* g, const float* dW, float* dV
   return check_launch("conv_wn_bwd_kernel");
 }
 
-int bruno_conv3x3(int mode, const void* in_slab, const void* wpack, const float* bias, const void* aux1, const void* aux2,
-                  void* out_slab, int N, int H, int W, void* stream) {
+int bruno_conv3x3(int mode, const void* in_slab, const void* wpack, const float* bias, int bias_img_stride,
+                  const void* aux1, const void* aux2, void* out_slab, int N, int H, int W, void* stream) {
+  BRUNO_REQUIRE(bias_img_stride == 0 || bias_img_stride >= 64, "bruno_conv3x3: bias_img_stride must be 0 or >= 64");
   BRUNO_REQUIRE(in_slab && wpack && out_slab && N > 0 && H > 0 && W > 0, "bruno_conv3x3: bad arguments");
   BRUNO_REQUIRE(aligned16(in_slab) && aligned16(wpack) && aligned16(out_slab), "bruno_conv3x3: 16-byte alignment required");
   BRUNO_REQUIRE(in_slab != out_slab, "bruno_conv3x3: in-place convolution is not possible");
@@ -675,19 +685,19 @@ int bruno_conv3x3(int mode, const void* in_slab, const void* wpack, const float*
   switch (mode) {
     case MODE_ELU:
       BRUNO_REQUIRE(bias, "bruno_conv3x3: bias required");
-      return launch_conv<MODE_ELU>(in_slab, wpack, bias, nullptr, nullptr, out_slab, g, st);
+      return launch_conv<MODE_ELU>(in_slab, wpack, bias, bias_img_stride, nullptr, nullptr, out_slab, g, st);
     case MODE_RES_ELU:
       BRUNO_REQUIRE(bias && aux1, "bruno_conv3x3: bias and skip slab required");
-      return launch_conv<MODE_RES_ELU>(in_slab, wpack, bias, aux1, nullptr, out_slab, g, st);
+      return launch_conv<MODE_RES_ELU>(in_slab, wpack, bias, bias_img_stride, aux1, nullptr, out_slab, g, st);
     case MODE_MUL:
       BRUNO_REQUIRE(aux1, "bruno_conv3x3: saved-activation slab required");
-      return launch_conv<MODE_MUL>(in_slab, wpack, nullptr, aux1, nullptr, out_slab, g, st);
+      return launch_conv<MODE_MUL>(in_slab, wpack, nullptr, 0, aux1, nullptr, out_slab, g, st);
     case MODE_ADD_MUL:
       BRUNO_REQUIRE(aux1 && aux2, "bruno_conv3x3: saved-activation and addend slabs required");
-      return launch_conv<MODE_ADD_MUL>(in_slab, wpack, nullptr, aux1, aux2, out_slab, g, st);
+      return launch_conv<MODE_ADD_MUL>(in_slab, wpack, nullptr, 0, aux1, aux2, out_slab, g, st);
     case MODE_LINEAR:
       BRUNO_REQUIRE(bias, "bruno_conv3x3: bias required");
-      return launch_conv<MODE_LINEAR>(in_slab, wpack, bias, nullptr, nullptr, out_slab, g, st);
+      return launch_conv<MODE_LINEAR>(in_slab, wpack, bias, bias_img_stride, nullptr, nullptr, out_slab, g, st);
     default:
       set_last_error("bruno_conv3x3: unknown mode %d", mode);
       return BRUNO_EINVAL;

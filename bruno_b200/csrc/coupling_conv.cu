@@ -11,8 +11,9 @@ size_t bruno_coupling_conv_slabs(int R, int save) { return save ? static_cast<si
 
 int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float* ld_out, int N, int H, int W, int C, int R,
                             int mask_type, int inverse, const float* V1, const float* g1, const float* b1,
-                            const void* wfwd, const float* br, const float* Ks, const float* bs, const float* Kt,
-                            const float* bt, void* slabs, int n_slabs, void* stream) {
+                            const void* wfwd, const float* br, int bias_img_stride, const float* Ks, const float* bs,
+                            const float* Kt, const float* bt, const float* label_s, const float* label_t, void* slabs,
+                            int n_slabs, void* stream) {
   BRUNO_REQUIRE(x && ld_in && y && ld_out && V1 && g1 && b1 && wfwd && br && Ks && bs && Kt && bt && slabs,
                 "bruno_coupling_conv_fwd: null pointer");
   BRUNO_REQUIRE(R >= 1 && (n_slabs >= 3), "bruno_coupling_conv_fwd: need >= 3 slabs (got %d)", n_slabs);
@@ -21,16 +22,19 @@ int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float*
   auto S = [&](int i) { return static_cast<void*>(static_cast<uint8_t*>(slabs) + static_cast<size_t>(i) * sb); };
   auto Wp = [&](int l) { return static_cast<const void*>(static_cast<const uint8_t*>(wfwd) + static_cast<size_t>(l) * wb); };
   int rc;
-  if ((rc = bruno_c1_fwd(x, V1, g1, b1, S(0), N, H, W, C, mask_type, stream))) return rc;
+  // bias_img_stride = 0: b1 [64], br [2R,64];  != 0: label-conditioned per-image tables, image n of layer l at
+  // br + l*64 + n*bias_img_stride (the 2R+1 tables are the columns of one [N, (2R+1)*64] matrix)
+  const size_t bl = 64;
+  if ((rc = bruno_c1_fwd(x, V1, g1, b1, bias_img_stride, S(0), N, H, W, C, mask_type, stream))) return rc;
   int hi = 0;
   for (int r = 0; r < R; ++r) {
     const int ui = save ? 2 * r + 1 : (hi + 1) % 3;
     const int ni = save ? 2 * r + 2 : (hi + 2) % 3;
-    if ((rc = bruno_conv3x3(0, S(hi), Wp(2 * r), br + (2 * r) * 64, nullptr, nullptr, S(ui), N, H, W, stream))) return rc;
-    if ((rc = bruno_conv3x3(1, S(ui), Wp(2 * r + 1), br + (2 * r + 1) * 64, S(hi), nullptr, S(ni), N, H, W, stream))) return rc;
+    if ((rc = bruno_conv3x3(0, S(hi), Wp(2 * r), br + (2 * r) * bl, bias_img_stride, nullptr, nullptr, S(ui), N, H, W, stream))) return rc;
+    if ((rc = bruno_conv3x3(1, S(ui), Wp(2 * r + 1), br + (2 * r + 1) * bl, bias_img_stride, S(hi), nullptr, S(ni), N, H, W, stream))) return rc;
     hi = ni;
   }
-  return bruno_heads_coupling(x, S(hi), Ks, bs, Kt, bt, ld_in, y, ld_out, N, H, W, C, mask_type, inverse, stream);
+  return bruno_heads_coupling(x, S(hi), Ks, bs, Kt, bt, label_s, label_t, ld_in, y, ld_out, N, H, W, C, mask_type, inverse, stream);
 }
 
 int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, int N, int H, int W, int C, int R,
@@ -55,8 +59,8 @@ int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, i
                                      mask_type, stream))) return rc;
   for (int r = R - 1; r >= 0; --r) {
     // g2 = dgrad_c3(g3) * ELU'(u_r);   g3' (or g1) = (dgrad_c2(g2) + g3) * ELU'(block input)
-    if ((rc = bruno_conv3x3(2, GS(2 * r + 2), Wp(2 * r + 1), nullptr, S(2 * r + 1), nullptr, GS(2 * r + 1), N, H, W, stream))) return rc;
-    if ((rc = bruno_conv3x3(3, GS(2 * r + 1), Wp(2 * r), nullptr, S(2 * r), GS(2 * r + 2), GS(2 * r), N, H, W, stream))) return rc;
+    if ((rc = bruno_conv3x3(2, GS(2 * r + 2), Wp(2 * r + 1), nullptr, 0, S(2 * r + 1), nullptr, GS(2 * r + 1), N, H, W, stream))) return rc;
+    if ((rc = bruno_conv3x3(3, GS(2 * r + 1), Wp(2 * r), nullptr, 0, S(2 * r), GS(2 * r + 2), GS(2 * r), N, H, W, stream))) return rc;
   }
   // all 2R weight (and bias) gradients in one launch: conv layer l reads its input slab S(l) and gradient GS(l + 1)
   if ((rc = bruno_conv3x3_wgrad_batched(S(0), GS(1), dVr, dbr, 2 * R, N, H, W, stream))) return rc;

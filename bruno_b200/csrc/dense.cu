@@ -109,6 +109,8 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const fl
       const size_t o = static_cast<size_t>(m) * ldc + n;
       if (ep.pre_out) ep.pre_out[o] = v;
       if (ep.act == 1) v = v > 0.f ? v : expm1f(v);
+      else if (ep.act == 2) v = v > 0.f ? v : 0.2f * v;   // tf.nn.leaky_relu default alpha
+      else if (ep.act == 3) v = tanhf(v);
       if (ep.accumulate) v += C[o];
       C[o] = v;
     }
@@ -311,6 +313,20 @@ int bruno_sgemm(int transA, int transB, int M, int N, int K, const float* A, int
   BRUNO_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bruno_sgemm: bad arguments");
   GemmEpi ep{col_scale, bias, nullptr, act, accumulate, nullptr};
   return gemm(transA != 0, transB != 0, M, N, K, A, lda, B, ldb, C, ldc, ep, static_cast<cudaStream_t>(stream));
+}
+
+int bruno_dense_wn_scale(const float* V, const float* g, float* sc, float* inv_nrm, int K, int N, void* stream) {
+  BRUNO_REQUIRE(V && g && sc && K > 0 && N > 0, "bruno_dense_wn_scale: bad arguments");
+  dense_wn_scale_kernel<<<ceil_div(N, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(V, g, sc, inv_nrm, K, N);
+  return check_launch("dense_wn_scale_kernel");
+}
+
+int bruno_dense_coupling(const float* x, const float* s_pre, const float* t_pre, const float* ld_in, float* y, float* ld_out,
+                         int N, int D, int mask_type, int inverse, void* stream) {
+  BRUNO_REQUIRE(x && s_pre && t_pre && ld_in && y && ld_out && N > 0 && D > 0, "bruno_dense_coupling: bad arguments");
+  BRUNO_REQUIRE(mask_type == BRUNO_MASK_EVEN || mask_type == BRUNO_MASK_ODD, "bruno_dense_coupling: bad mask");
+  dense_coupling_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, s_pre, t_pre, ld_in, y, ld_out, D, mask_type, inverse);
+  return check_launch("dense_coupling_kernel");
 }
 
 int bruno_coupling_dense_fwd(const float* x, const float* ld_in, float* y, float* ld_out, int N, int D, int U, int mask_type,

@@ -143,10 +143,11 @@ __device__ __forceinline__ void c1_weights_to_smem(const float* __restrict__ V1,
 
 __global__ void __launch_bounds__(256)
 c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const float* __restrict__ g1,
-              const float* __restrict__ b1, uint8_t* __restrict__ out, SlabGeom g, int C, int mask_type) {
+              const float* __restrict__ b1, int bias_img_stride, uint8_t* __restrict__ out, SlabGeom g, int C,
+              int mask_type) {
   __shared__ float w_s[MAXC * 64];
   __shared__ float b_s[64];
-  if (threadIdx.x < 64) b_s[threadIdx.x] = b1[threadIdx.x];
+  if (threadIdx.x < 64) b_s[threadIdx.x] = bias_img_stride ? 0.f : b1[threadIdx.x];
   c1_weights_to_smem(V1, g1, C, w_s);
   const int total = g.NT * TILE_M * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -159,7 +160,8 @@ c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
       const float* xp = x + ((static_cast<size_t>(n) * g.H + yy) * g.W + xx) * C;
       float acc[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = b_s[j * 8 + e];
+      for (int e = 0; e < 8; ++e)
+        acc[e] = bias_img_stride ? b1[static_cast<size_t>(n) * bias_img_stride + j * 8 + e] : b_s[j * 8 + e];
       for (int c = 0; c < C; ++c) {
         const float xm = xp[c] * mask_b(mask_type, yy, xx, c, C);
 #pragma unroll
@@ -245,6 +247,7 @@ c1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
 __global__ void __launch_bounds__(256)
 heads_coupling_kernel(const float* __restrict__ xin, const uint8_t* __restrict__ hslab, const float* __restrict__ Ks,
                       const float* __restrict__ bs, const float* __restrict__ Kt, const float* __restrict__ bt,
+                      const float* __restrict__ label_s, const float* __restrict__ label_t,
                       const float* __restrict__ ld_in, float* __restrict__ yout, float* __restrict__ ld_out, SlabGeom g,
                       int C, int mask_type, int inverse) {
   __shared__ float ks_s[64 * MAXC], kt_s[64 * MAXC], bs_s[MAXC], bt_s[MAXC], red[8];
@@ -276,6 +279,10 @@ heads_coupling_kernel(const float* __restrict__ xin, const uint8_t* __restrict__
       float out = xv;
       if (b == 0.f) {
         float sp = bs_s[c], tp = bt_s[c];
+        if (label_s) {        // label-conditioned heads: + dense(y_label)[n, c]   (nn_extra_nvp_conditional.py:382-388)
+          sp += label_s[n * C + c];
+          tp += label_t[n * C + c];
+        }
 #pragma unroll
         for (int k = 0; k < 64; ++k) {
           sp = fmaf(h[k], ks_s[k * C + c], sp);
@@ -456,15 +463,15 @@ int bruno_channel_copy(const float* src, float* dst, long rows, int src_C, int s
   return check_launch("channel_copy_kernel");
 }
 
-int bruno_c1_fwd(const float* x, const float* V1, const float* g1, const float* b1, void* out_slab, int N, int H, int W,
-                 int C, int mask_type, void* stream) {
+int bruno_c1_fwd(const float* x, const float* V1, const float* g1, const float* b1, int bias_img_stride, void* out_slab,
+                 int N, int H, int W, int C, int mask_type, void* stream) {
   BRUNO_REQUIRE(x && V1 && g1 && b1 && out_slab && C >= 1 && C <= MAXC, "bruno_c1_fwd: bad arguments (C <= %d)", MAXC);
   const SlabGeom g = slab_geom(N, H, W);
   const int total = g.NT * TILE_M * 8;
   int blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  c1_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, V1, g1, b1, static_cast<uint8_t*>(out_slab), g, C,
-                                                                        mask_type);
+  c1_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, V1, g1, b1, bias_img_stride,
+                                                                        static_cast<uint8_t*>(out_slab), g, C, mask_type);
   return check_launch("c1_fwd_kernel");
 }
 
@@ -484,13 +491,14 @@ int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g
 }
 
 int bruno_heads_coupling(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
-                         const float* bt, const float* ld_in, float* y, float* ld_out, int N, int H, int W, int C,
-                         int mask_type, int inverse, void* stream) {
+                         const float* bt, const float* label_s, const float* label_t, const float* ld_in, float* y,
+                         float* ld_out, int N, int H, int W, int C, int mask_type, int inverse, void* stream) {
+  BRUNO_REQUIRE((label_s == nullptr) == (label_t == nullptr), "bruno_heads_coupling: label_s / label_t come together");
   BRUNO_REQUIRE(x && h_slab && Ks && bs && Kt && bt && ld_in && y && ld_out && C >= 1 && C <= MAXC,
                 "bruno_heads_coupling: bad arguments");
   const SlabGeom g = slab_geom(N, H, W);
-  heads_coupling_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<const uint8_t*>(h_slab), Ks, bs, Kt,
-                                                                           bt, ld_in, y, ld_out, g, C, mask_type, inverse);
+  heads_coupling_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<const uint8_t*>(h_slab), Ks, bs, Kt, bt, label_s, label_t, ld_in, y, ld_out, g, C, mask_type, inverse);
   return check_launch("heads_coupling_kernel");
 }
 

@@ -28,7 +28,7 @@ def conv_coupling_init(layer, x):
         ld = torch.zeros(N, device=x.device)
         y = torch.empty_like(x)
         _lib.call('bruno_coupling_conv_fwd', x, ld, y, torch.empty_like(ld), N, H, W, C, R, layer.mask_id, 0, layer.V1,
-                  layer.g1, layer.b1, wfwd, layer.br, layer.Ks, layer.bs, layer.Kt, layer.bt, slabs, int(slabs.shape[0]))
+                  layer.g1, layer.b1, wfwd, layer.br, 0, layer.Ks, layer.bs, layer.Kt, layer.bt, None, None, slabs, int(slabs.shape[0]))
         # c1: pre-activation on the masked input
         hh = torch.arange(H, device=x.device).view(H, 1, 1)
         ww = torch.arange(W, device=x.device).view(1, W, 1)
@@ -46,7 +46,7 @@ def conv_coupling_init(layer, x):
         tmp = alloc_slabs(1, N, H, W, x.device)[0]
         pres = []
         for l in range(2 * R):
-            _lib.call('bruno_conv3x3', 4, slabs[l], wfwd[l], layer.br[l].contiguous(), None, None, tmp, N, H, W)
+            _lib.call('bruno_conv3x3', 4, slabs[l], wfwd[l], layer.br[l].contiguous(), 0, None, None, tmp, N, H, W)
             pres.append(slab_to_nhwc(tmp, N, H, W))
         _assign(layer.g1, layer.b1, pre, (0,))
         for l in range(2 * R):

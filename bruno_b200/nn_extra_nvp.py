@@ -140,7 +140,7 @@ class _ConvCouplingFn(torch.autograd.Function):
         y = torch.empty_like(x)
         ld_out = torch.empty_like(ld)
         _lib.call('bruno_coupling_conv_fwd', x, ld, y, ld_out, N, H, W, C, R, layer.mask_id, int(inverse), V1, g1, b1, wfwd,
-                  br, Ks, bs, Kt, bt, slabs, int(slabs.shape[0]))
+                  br, 0, Ks, bs, Kt, bt, None, None, slabs, int(slabs.shape[0]))
         if need_grad:
             if inverse:
                 raise RuntimeError('backward through the inverse pass is not implemented (sampling is inference-only)')

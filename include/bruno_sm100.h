@@ -146,9 +146,11 @@ int bruno_conv_wn_bwd(const float* V, const float* g, const float* dW, float* dV
  *   mode 2: out = conv * ELU'(aux1)                     dgrad through c3, aux1 = saved output of c2
  *   mode 3: out = (conv + aux2) * ELU'(aux1)            dgrad through c2 + skip gradient, aux1 = saved block input
  *   mode 4: out = conv + bias                           (data-dependent init, nvp:394-398)
- * ELU' is evaluated from the saved OUTPUT o of the ELU: 1 if o > 0 else o + 1. */
-int bruno_conv3x3(int mode, const void* in_slab, const void* wpack, const float* bias, const void* aux1, const void* aux2,
-                  void* out_slab, int N, int H, int W, void* stream);
+ * ELU' is evaluated from the saved OUTPUT o of the ELU: 1 if o > 0 else o + 1.
+ * bias_img_stride = 0: bias [64] shared by all images; >= 64: per-image bias table bias[n * stride + c] -- the
+ * label-conditioned layers add dense_wn(y_label)[n, :] to the conv output (nn_extra_nvp_conditional.py:422-433). */
+int bruno_conv3x3(int mode, const void* in_slab, const void* wpack, const float* bias, int bias_img_stride,
+                  const void* aux1, const void* aux2, void* out_slab, int N, int H, int W, void* stream);
 /* dW [3,3,64,64] (HWIO) += sum_pos x[pos + tap] (x) g[pos];  db [64] += sum_pos g[pos]   (fp32, atomically added) */
 int bruno_conv3x3_wgrad(const void* x_slab, const void* g_slab, float* dW, float* db, int N, int H, int W, void* stream);
 /* the same for L layers in ONE launch: layer l uses slab l of x_slab / g_slab (consecutive slabs of bruno_slab_bytes),
@@ -157,17 +159,19 @@ int bruno_conv3x3_wgrad_batched(const void* x_slab, const void* g_slab, float* d
                                 void* stream);
 
 /* c1 (nvp:113-115): out_slab = ELU(conv1x1_wn(x * mask)), x [N,H,W,C] fp32, V1 [C,64], g1, b1 [64]. */
-int bruno_c1_fwd(const float* x, const float* V1, const float* g1, const float* b1, void* out_slab, int N, int H, int W,
-                 int C, int mask_type, void* stream);
+int bruno_c1_fwd(const float* x, const float* V1, const float* g1, const float* b1, int bias_img_stride, void* out_slab,
+                 int N, int H, int W, int C, int mask_type, void* stream);
 /* g_slab = dL/d(pre-activation of c1): dx += mask * (g W1^T); dW1 [C,64] += (x mask)^T g; db1 [64] += sum g. */
 int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g_slab, float* dx, float* dW1, float* db1,
                  int N, int H, int W, int C, int mask_type, void* stream);
 
 /* conv_out_scale / conv_out_translation heads (nvp:129-139) + affine coupling + log-det (forward :162-174, inverse
  * :176-187).  Ks, Kt [64,C]; bs, bt [C]; x, y [N,H,W,C]; ld [N]. */
+/* label_s / label_t (both NULL or both [N,C]): per-image additive terms of the label-conditioned heads
+ * (nn_extra_nvp_conditional.py:382-388). */
 int bruno_heads_coupling(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
-                         const float* bt, const float* ld_in, float* y, float* ld_out, int N, int H, int W, int C,
-                         int mask_type, int inverse, void* stream);
+                         const float* bt, const float* label_s, const float* label_t, const float* ld_in, float* y,
+                         float* ld_out, int N, int H, int W, int C, int mask_type, int inverse, void* stream);
 /* backward of the forward coupling: dx = direct part (the s/t-network part is added by bruno_c1_bwd), g_slab =
  * dL/d(pre-activation of the last residual block); dKs, dbs, dKt, dbt are overwritten (deterministic two-level sum:
  * per-block partials in `scratch` of bruno_heads_bwd_scratch_floats(C) floats, then a fixed-order reduction). */
@@ -181,12 +185,15 @@ int bruno_heads_coupling_bwd(const float* x, const void* h_slab, const float* Ks
  * Stacked parameters: V1 [C,64], g1, b1 [64] (c1); packed residual weights wfwd [2R] (order c2_0, c3_0, c2_1, ...,
  * from bruno_conv_wn_pack), br [2R,64]; Ks, Kt [64,C], bs, bt [C].  `slabs`: n_slabs zero-initialised slabs of
  * bruno_slab_bytes each; n_slabs >= 2R+1 keeps every activation for the backward (slab 0 = c1 output, 2r+1 = c2_r
- * output, 2r+2 = block-r output), n_slabs = 3 ping-pongs (inference). */
+ * output, 2r+2 = block-r output), n_slabs = 3 ping-pongs (inference).
+ * Label-conditioned variant (nn_extra_nvp_conditional.py:422-433): bias_img_stride != 0, b1 / br point into ONE per-image
+ * table (image n of conv layer l at br + l*64 + n*bias_img_stride); label_s / label_t [N,C] as in bruno_heads_coupling. */
 size_t bruno_coupling_conv_slabs(int R, int save);
 int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float* ld_out, int N, int H, int W, int C, int R,
                             int mask_type, int inverse, const float* V1, const float* g1, const float* b1,
-                            const void* wfwd, const float* br, const float* Ks, const float* bs, const float* Kt,
-                            const float* bt, void* slabs, int n_slabs, void* stream);
+                            const void* wfwd, const float* br, int bias_img_stride, const float* Ks, const float* bs,
+                            const float* Kt, const float* bt, const float* label_s, const float* label_t, void* slabs,
+                            int n_slabs, void* stream);
 /* Hand-written backward of the forward coupling: dx [N,H,W,C] and the gradients of every variable of the layer
  * (weight-norm backward included: dVr, dgr are w.r.t. V and g).  saved_slabs = the 2R+1 slabs of the forward;
  * gslabs = 2R+1 zero-initialised scratch slabs (slab 0: gradient w.r.t. the c1 pre-activation, slab l+1: gradient
@@ -211,7 +218,13 @@ int bruno_coupling_dense_bwd(const float* x, const float* dy, const float* dld, 
                              const float* b2, const float* Ks, const float* Kt, const float* ws_fwd, float* ws_bwd,
                              float* dx, float* dV1, float* dg1, float* db1, float* dV2, float* dg2, float* db2, float* dKs,
                              float* dbs, float* dKt, float* dbt, void* stream);
-/* C[M,N] (+)= act(op(A) op(B) * col_scale + bias), row-major fp32 (tf.matmul at nvp:418, tf.layers.dense :262,:268) */
+/* sc[j] = g[j] / ||V[:, j]||, inv_nrm[j] = 1 / ||V[:, j]|| (may be NULL): the scaler of dense_wn (nvp:419) */
+int bruno_dense_wn_scale(const float* V, const float* g, float* sc, float* inv_nrm, int K, int N, void* stream);
+/* the affine coupling + log-det of CouplingLayerDense given the two head outputs s_pre, t_pre [N,D] (nvp:168-186) */
+int bruno_dense_coupling(const float* x, const float* s_pre, const float* t_pre, const float* ld_in, float* y, float* ld_out,
+                         int N, int D, int mask_type, int inverse, void* stream);
+/* C[M,N] (+)= act(op(A) op(B) * col_scale + bias), row-major fp32 (tf.matmul at nvp:418, tf.layers.dense :262,:268);
+ * act: 0 none, 1 ELU, 2 leaky_relu(0.2), 3 tanh */
 int bruno_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
                 int ldc, const float* col_scale, const float* bias, int act, int accumulate, void* stream);
 

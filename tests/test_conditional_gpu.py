@@ -1,0 +1,60 @@
+"""GPU parity of Conditional BRUNO (config_conditional/m1_shapenet.py on nn_extra_nvp_conditional.py), inference path:
+NLL with n_context, and sampling through the inverse flow, against the CPU oracle on identical inputs / weights.
+Tolerance: same stated bf16 bound as the unconditional conv configs (tests/test_flow_gpu.py)."""
+import importlib
+
+import pytest
+import torch
+
+from oracle import bruno_oracle as O
+from oracle import bruno_oracle_cond as OC
+
+pytestmark = pytest.mark.gpu
+
+
+def setup(B, T, seed, n_context=1):
+    spec = OC.CondSpec()
+    P = OC.init_params(spec, seed=seed, dtype=torch.float64, perturb_process=True)
+    x, yl = OC.synthetic_batch(spec, B, T, seed=seed + 1)
+    x, yl = x.float().double(), yl.float().double()
+    OC.data_dependent_init(spec, P, x, yl, n_context=n_context)
+    P = O.cast_params(O.cast_params(P, torch.float32), torch.float64)
+    from bruno_b200.config_conditional import defaults
+    defaults.n_context = n_context
+    defaults.seq_len = T
+    cfg = importlib.reload(importlib.import_module('bruno_b200.config_conditional.m1_shapenet'))
+    xg, ylg = x.float().cuda(), yl.float().cuda()
+    cfg.build_model(xg[:1], ylg[:1])                 # creates the variables
+    cfg.load_tf_variables(P)
+    return spec, P, x, yl, cfg, xg, ylg
+
+
+@pytest.mark.parametrize('n_context', [1, 0])
+def test_conditional_nll_matches_oracle(n_context):
+    B, T = 2, 3
+    spec, P, x, yl, cfg, xg, ylg = setup(B, T, seed=3, n_context=n_context)
+    with torch.no_grad():
+        lp_o, z_o = OC.build_model(spec, P, x, yl, n_context=n_context)
+        with O.emulate_bf16():
+            lp_e, _ = OC.build_model(spec, P, x, yl, n_context=n_context)
+    lp = cfg.build_model(xg, ylg)[0]
+    assert tuple(lp.shape) == tuple(lp_o.shape)
+    rel = lambda a, b: ((a.double().cpu() - b).abs() / b.abs().clamp_min(1.0)).max().item()
+    print('\n[m1_shapenet n_context=%d] per-example log-lik rel err: %.3e vs exact oracle, %.3e vs bf16-emulating oracle' % (
+        n_context, rel(lp, lp_o), rel(lp, lp_e)))
+    assert rel(lp, lp_o) <= 6e-3
+    assert rel(lp, lp_e) <= 3e-3
+
+
+def test_conditional_sampling_matches_oracle():
+    B, T = 2, 3
+    spec, P, x, yl, cfg, xg, ylg = setup(B, T, seed=5, n_context=1)
+    g = torch.Generator().manual_seed(9)
+    noise = [torch.randn(1, B, spec.ndim, generator=g) for _ in range(T)]
+    with torch.no_grad():
+        xs_o = OC.build_model_sampling(spec, P, x, yl, [t.double() for t in noise], n_context=1)
+    xs = cfg.build_model(xg, ylg, sampling_mode=True, noise=[t.cuda() for t in noise])
+    xs = xs.reshape(xs_o.shape)
+    err = (xs.double().cpu() - xs_o).abs().max().item()
+    print('\n[m1_shapenet] sampling: max |x_s - oracle| = %.3e (x in [0,1])' % err)
+    assert err <= 0.08

@@ -63,7 +63,7 @@ def test_conv3x3_all_epilogues(N, H, W):
     ]
     for mode, w, ref in cases:
         out.zero_()
-        _lib.call('bruno_conv3x3', mode, xs, w, b32, a1s, a2s, out, N, H, W)
+        _lib.call('bruno_conv3x3', mode, xs, w, b32, 0, a1s, a2s, out, N, H, W)
         got = slab.slab_to_nhwc(out, N, H, W, check_padding=True).double().cpu()
         err = (got - ref).abs().max().item()
         scale = ref.abs().max().item()

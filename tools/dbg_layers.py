@@ -47,7 +47,7 @@ nrm = torch.sqrt((V[0].float().double() ** 2).sum(dim=(0, 1, 2), keepdim=True))
 Wt = bf(gain[0].float().double().view(1, 1, 1, -1) * V[0].float().double() / nrm)
 xs = slab.nhwc_to_slab(xx.float().cuda())
 out = slab.alloc_slabs(1, N, H, W, 'cuda')[0]
-_lib.call('bruno_conv3x3', 4, xs, wf[0], bias.float().cuda(), None, None, out, N, H, W)
+_lib.call('bruno_conv3x3', 4, xs, wf[0], bias.float().cuda(), 0, None, None, out, N, H, W)
 got = slab.slab_to_nhwc(out, N, H, W).double().cpu()
 ref64 = F.conv2d(bf(xx).permute(0, 3, 1, 2), Wt.permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1) + bias.float().double()
 ref = bf(ref64)

@@ -11,10 +11,10 @@ sl[0].random_(0, 255)   # garbage activations are fine for timing
 bias = torch.zeros(64, device='cuda')
 for mode in (0, 1):
     for _ in range(3):
-        _lib.call('bruno_conv3x3', mode, sl[0], wf[0], bias, sl[2], None, sl[1], N, H, W)
+        _lib.call('bruno_conv3x3', mode, sl[0], wf[0], bias, 0, sl[2], None, sl[1], N, H, W)
     tr = torch.zeros(64 * 16, dtype=torch.int64, device='cuda')
     _lib.load().bruno_debug_conv_trace(tr.data_ptr())
-    _lib.call('bruno_conv3x3', mode, sl[0], wf[0], bias, sl[2], None, sl[1], N, H, W)
+    _lib.call('bruno_conv3x3', mode, sl[0], wf[0], bias, 0, sl[2], None, sl[1], N, H, W)
     torch.cuda.synchronize()
     _lib.load().bruno_debug_conv_trace(None)
     t = tr.view(64, 16).cpu()
