@@ -129,7 +129,7 @@ class CouplingLayerConv(Layer):                                             # co
             ld_in = ld.contiguous() if ld is not None else torch.zeros(N, device=x.device)
             ld_out = torch.empty_like(ld_in)
             _lib.call('bruno_coupling_conv_fwd', x, ld_in, y, ld_out, N, H, W, C, R, self.mask_id, int(inverse), self.V1,
-                      self.g1, tab, wfwd, tab[:, F:], nl * F, self.Ks, self.bs, self.Kt, self.bt, ls, lt, slabs, 3)
+                      self.g1, tab, wfwd, tab.data_ptr() + 4 * F, nl * F, self.Ks, self.bs, self.Kt, self.bt, ls, lt, slabs, 3)
         return y, ld_out
 
     def forward_and_jacobian(self, x, sum_log_det_jacobians, z, y_label=None):      # cond:137-149
