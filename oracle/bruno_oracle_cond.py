@@ -288,7 +288,7 @@ def init_params(spec, seed=0, dtype=torch.float64, randomize_heads=True, perturb
         for nm in ('d_scale', 'd_translate'):
             P['%s/%s/label_W1/kernel' % (sc, nm)] = normal(L, U // 2, std=0.3)
             P['%s/%s/label_W1/bias' % (sc, nm)] = normal(U // 2, std=0.1)
-            P['%s/%s/%s/kernel' % (sc, nm, nm)] = normal(U // 2 + U, D) if randomize_heads else torch.zeros(U // 2 + U, D, dtype=dtype)
+            P['%s/%s/%s/kernel' % (sc, nm, nm)] = normal(U // 2 + U, D, std=0.01) if randomize_heads else torch.zeros(U // 2 + U, D, dtype=dtype)
             P['%s/%s/%s/bias' % (sc, nm, nm)] = normal(D) if randomize_heads else torch.zeros(D, dtype=dtype)
     if perturb_process:
         u = torch.rand(2, D, generator=g, dtype=torch.float64)

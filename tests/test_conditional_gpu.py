@@ -43,7 +43,7 @@ def test_conditional_nll_matches_oracle(n_context):
     print('\n[m1_shapenet n_context=%d] per-example log-lik rel err: %.3e vs exact oracle, %.3e vs bf16-emulating oracle' % (
         n_context, rel(lp, lp_o), rel(lp, lp_e)))
     assert rel(lp, lp_o) <= 6e-3
-    assert rel(lp, lp_e) <= 3e-3
+    assert rel(lp, lp_e) <= 6e-3
 
 
 def test_conditional_sampling_matches_oracle():
