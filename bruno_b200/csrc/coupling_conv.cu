@@ -25,7 +25,7 @@ int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float*
   // bias_img_stride = 0: b1 [64], br [2R,64];  != 0: label-conditioned per-image tables, image n of layer l at
   // br + l*64 + n*bias_img_stride (the 2R+1 tables are the columns of one [N, (2R+1)*64] matrix)
   const size_t bl = 64;
-  if ((rc = bruno_c1_fwd(x, V1, g1, b1, bias_img_stride, S(0), N, H, W, C, mask_type, stream))) return rc;
+  if ((rc = bruno_c1_fwd(x, V1, g1, b1, bias_img_stride, S(0), 0, N, H, W, C, mask_type, stream))) return rc;
   int hi = 0;
   for (int r = 0; r < R; ++r) {
     const int ui = save ? 2 * r + 1 : (hi + 1) % 3;
@@ -34,7 +34,7 @@ int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float*
     if ((rc = bruno_conv3x3(1, S(ui), Wp(2 * r + 1), br + (2 * r + 1) * bl, bias_img_stride, S(hi), nullptr, S(ni), N, H, W, stream))) return rc;
     hi = ni;
   }
-  return bruno_heads_coupling(x, S(hi), Ks, bs, Kt, bt, label_s, label_t, ld_in, y, ld_out, N, H, W, C, mask_type, inverse, stream);
+  return bruno_heads_coupling(x, S(hi), Ks, bs, Kt, bt, label_s, label_t, ld_in, y, ld_out, 0, N, H, W, C, mask_type, inverse, stream);
 }
 
 int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, int N, int H, int W, int C, int R,

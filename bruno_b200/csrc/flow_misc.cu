@@ -144,7 +144,7 @@ __device__ __forceinline__ void c1_weights_to_smem(const float* __restrict__ V1,
 __global__ void __launch_bounds__(256)
 c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const float* __restrict__ g1,
               const float* __restrict__ b1, int bias_img_stride, uint8_t* __restrict__ out, SlabGeom g, int C,
-              int mask_type) {
+              int mask_type, int f32_slab) {
   __shared__ float w_s[MAXC * 64];
   __shared__ float b_s[64];
   if (threadIdx.x < 64) b_s[threadIdx.x] = bias_img_stride ? 0.f : b1[threadIdx.x];
@@ -154,6 +154,7 @@ c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
     const int data_row = i >> 3, j = i & 7;
     const size_t R = static_cast<size_t>(g.HALO) + data_row;
     uint4 packed = make_uint4(0, 0, 0, 0);
+    float outf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (slab_row_is_pixel(data_row, g)) {
       const int n = data_row / g.IMG, q = data_row % g.IMG;
       const int yy = q / g.P - 1, xx = q % g.P - 1;
@@ -167,10 +168,21 @@ c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = fmaf(xm, w_s[c * 64 + j * 8 + e], acc[e]);
       }
-      packed = make_uint4(pack2f(elu_f(acc[0]), elu_f(acc[1])), pack2f(elu_f(acc[2]), elu_f(acc[3])),
-                          pack2f(elu_f(acc[4]), elu_f(acc[5])), pack2f(elu_f(acc[6]), elu_f(acc[7])));
+      if (f32_slab) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) outf[e] = acc[e] > 0.f ? acc[e] : expm1f(acc[e]);
+      } else {
+        packed = make_uint4(pack2f(elu_f(acc[0]), elu_f(acc[1])), pack2f(elu_f(acc[2]), elu_f(acc[3])),
+                            pack2f(elu_f(acc[4]), elu_f(acc[5])), pack2f(elu_f(acc[6]), elu_f(acc[7])));
+      }
     }
-    *reinterpret_cast<uint4*>(out + slab_chunk_off(R, j)) = packed;
+    if (f32_slab) {       // fp32 verification layout: [row][64] floats, no swizzle
+      float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + R * 64 + j * 8);
+      o4[0] = make_float4(outf[0], outf[1], outf[2], outf[3]);
+      o4[1] = make_float4(outf[4], outf[5], outf[6], outf[7]);
+    } else {
+      *reinterpret_cast<uint4*>(out + slab_chunk_off(R, j)) = packed;
+    }
   }
 }
 
@@ -249,7 +261,7 @@ heads_coupling_kernel(const float* __restrict__ xin, const uint8_t* __restrict__
                       const float* __restrict__ bs, const float* __restrict__ Kt, const float* __restrict__ bt,
                       const float* __restrict__ label_s, const float* __restrict__ label_t,
                       const float* __restrict__ ld_in, float* __restrict__ yout, float* __restrict__ ld_out, SlabGeom g,
-                      int C, int mask_type, int inverse) {
+                      int C, int mask_type, int inverse, int f32_slab) {
   __shared__ float ks_s[64 * MAXC], kt_s[64 * MAXC], bs_s[MAXC], bt_s[MAXC], red[8];
   for (int i = threadIdx.x; i < 64 * C; i += 256) {
     ks_s[i] = Ks[i];
@@ -267,10 +279,19 @@ heads_coupling_kernel(const float* __restrict__ xin, const uint8_t* __restrict__
     const int yy = p / g.W, xx = p % g.W;
     const size_t R = static_cast<size_t>(g.HALO) + static_cast<size_t>(n) * g.IMG + (yy + 1) * g.P + (xx + 1);
     float h[64];
+    if (f32_slab) {
+      const float4* hp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(hslab) + R * 64);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint4 u = *reinterpret_cast<const uint4*>(hslab + slab_chunk_off(R, j));
-      unpack8f(u, h + j * 8);
+      for (int j = 0; j < 16; ++j) {
+        const float4 t = hp[j];
+        h[4 * j] = t.x; h[4 * j + 1] = t.y; h[4 * j + 2] = t.z; h[4 * j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 u = *reinterpret_cast<const uint4*>(hslab + slab_chunk_off(R, j));
+        unpack8f(u, h + j * 8);
+      }
     }
     const size_t xo = (static_cast<size_t>(n) * HW + p) * C;
     for (int c = 0; c < C; ++c) {
@@ -421,6 +442,33 @@ __global__ void heads_bwd_finalize_kernel(const float* __restrict__ partial, int
   *dst = s;
 }
 
+// fp32 verification path: epilogue of a 3x3 convolution whose nine taps were accumulated by bruno_sgemm into
+// acc [rows][64] fp32:  out = act(acc + bias (+ skip)) on pixel rows, 0 on padding rows (keeps the slab invariant).
+__global__ void conv_epilogue_f32_kernel(float* __restrict__ acc, const float* __restrict__ bias,
+                                         const float* __restrict__ skip, SlabGeom g, int elu) {
+  const size_t total = static_cast<size_t>(g.NT) * TILE_M * 16;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int data_row = static_cast<int>(i >> 4), j = static_cast<int>(i & 15);
+    float4* p = reinterpret_cast<float4*>(acc + (static_cast<size_t>(g.HALO) + data_row) * 64 + j * 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (slab_row_is_pixel(data_row, g)) {
+      v = *p;
+      const float4 b = *reinterpret_cast<const float4*>(bias + j * 4);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      if (skip) {
+        const float4 s = *reinterpret_cast<const float4*>(skip + (static_cast<size_t>(g.HALO) + data_row) * 64 + j * 4);
+        v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+      }
+      if (elu) {
+        v.x = v.x > 0.f ? v.x : expm1f(v.x); v.y = v.y > 0.f ? v.y : expm1f(v.y);
+        v.z = v.z > 0.f ? v.z : expm1f(v.z); v.w = v.w > 0.f ? v.w : expm1f(v.w);
+      }
+    }
+    *p = v;
+  }
+}
+
 // zero the rows of a slab that heads_coupling_bwd does not write (padding positions), so the slab invariant holds
 __global__ void slab_zero_padding_kernel(uint8_t* __restrict__ slab, SlabGeom g) {
   const int total = g.NT * TILE_M * 8;
@@ -464,14 +512,14 @@ int bruno_channel_copy(const float* src, float* dst, long rows, int src_C, int s
 }
 
 int bruno_c1_fwd(const float* x, const float* V1, const float* g1, const float* b1, int bias_img_stride, void* out_slab,
-                 int N, int H, int W, int C, int mask_type, void* stream) {
+                 int f32_slab, int N, int H, int W, int C, int mask_type, void* stream) {
   BRUNO_REQUIRE(x && V1 && g1 && b1 && out_slab && C >= 1 && C <= MAXC, "bruno_c1_fwd: bad arguments (C <= %d)", MAXC);
   const SlabGeom g = slab_geom(N, H, W);
   const int total = g.NT * TILE_M * 8;
   int blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   c1_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, V1, g1, b1, bias_img_stride,
-                                                                        static_cast<uint8_t*>(out_slab), g, C, mask_type);
+                                                                        static_cast<uint8_t*>(out_slab), g, C, mask_type, f32_slab);
   return check_launch("c1_fwd_kernel");
 }
 
@@ -490,15 +538,22 @@ int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g
   return check_launch("c1_bwd_kernel");
 }
 
+int bruno_conv_epilogue_f32(float* acc, const float* bias, const float* skip, int elu, int N, int H, int W, void* stream) {
+  BRUNO_REQUIRE(acc && bias && N > 0 && H > 0 && W > 0, "bruno_conv_epilogue_f32: bad arguments");
+  const SlabGeom g = slab_geom(N, H, W);
+  conv_epilogue_f32_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, bias, skip, g, elu);
+  return check_launch("conv_epilogue_f32_kernel");
+}
+
 int bruno_heads_coupling(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
                          const float* bt, const float* label_s, const float* label_t, const float* ld_in, float* y,
-                         float* ld_out, int N, int H, int W, int C, int mask_type, int inverse, void* stream) {
+                         float* ld_out, int f32_slab, int N, int H, int W, int C, int mask_type, int inverse, void* stream) {
   BRUNO_REQUIRE((label_s == nullptr) == (label_t == nullptr), "bruno_heads_coupling: label_s / label_t come together");
   BRUNO_REQUIRE(x && h_slab && Ks && bs && Kt && bt && ld_in && y && ld_out && C >= 1 && C <= MAXC,
                 "bruno_heads_coupling: bad arguments");
   const SlabGeom g = slab_geom(N, H, W);
   heads_coupling_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<const uint8_t*>(h_slab), Ks, bs, Kt, bt, label_s, label_t, ld_in, y, ld_out, g, C, mask_type, inverse);
+      x, static_cast<const uint8_t*>(h_slab), Ks, bs, Kt, bt, label_s, label_t, ld_in, y, ld_out, g, C, mask_type, inverse, f32_slab);
   return check_launch("heads_coupling_kernel");
 }
 

@@ -20,6 +20,28 @@ elu = torch.nn.functional.elu          # the only nonlinearity the target config
 
 _INIT_MODE = [False]                   # arg_scope([conv2d_wn, dense_wn], init=init) of the reference (bn2:62)
 
+# Precision of the 3x3 convolutions of CouplingLayerConv:
+#   'bf16' (default, production): tcgen05 tensor cores, bf16 operands / activations, fp32 accumulation.
+#   'fp32' (verification, inference only): the same layer evaluated entirely in fp32 on CUDA cores (nine tap GEMMs per
+#          convolution through bruno_sgemm on fp32 slabs) -- slow, used by the parity tests to show that the only
+#          difference between the production path and the reference arithmetic is the declared bf16 rounding.
+_PRECISION = ['bf16']
+
+
+class precision(object):
+    """with nn_extra_nvp.precision('fp32'): ..."""
+
+    def __init__(self, p):
+        assert p in ('bf16', 'fp32')
+        self.p = p
+
+    def __enter__(self):
+        self.prev = _PRECISION[0]
+        _PRECISION[0] = self.p
+
+    def __exit__(self, *a):
+        _PRECISION[0] = self.prev
+
 
 class init_scope(object):
     """with init_scope(init): ...  -- the reference's arg_scope(init=init)."""
@@ -239,9 +261,49 @@ class CouplingLayerConv(Layer):                                             # nv
             self._slabs = (key, alloc_slabs(n, N, H, W, device))
         return self._slabs[1]
 
+    def _apply_fp32(self, x, ld, inverse):
+        """fp32 verification path (see _PRECISION): c1 -> 2R convolutions as 9 tap GEMMs each -> heads, all fp32."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in (x, ld)):
+            raise RuntimeError("precision('fp32') is an inference-only verification mode")
+        from .slab import SlabGeom
+        with torch.no_grad():
+            x, ld = x.contiguous(), ld.contiguous()
+            N, H, W, C = x.shape
+            g = SlabGeom(N, H, W)
+            key = ('f32', N, H, W, str(x.device))
+            if key not in SLABS.pool:
+                SLABS.pool[key] = torch.zeros(3, g.rows, 64, device=x.device)
+            buf = SLABS.pool[key]
+            M = g.NT * 128
+            _lib.call('bruno_c1_fwd', x, self.V1, self.g1, self.b1, 0, buf[0], 1, N, H, W, C, self.mask_id)
+
+            def conv(src, dst, l, skip, act):
+                V = self.Vr[l].detach().contiguous()
+                scale = (self.gr[l] / torch.sqrt(torch.clamp((V * V).sum(dim=(0, 1, 2)), min=1e-12))).contiguous()
+                for tap in range(9):
+                    shift = (tap // 3 - 1) * g.P + (tap % 3 - 1)
+                    _lib.call('bruno_sgemm', 0, 0, M, 64, 64, src.data_ptr() + 4 * 64 * (g.HALO + shift), 64,
+                              V.data_ptr() + 4 * 64 * 64 * tap, 64, dst.data_ptr() + 4 * 64 * g.HALO, 64, scale, None, 0,
+                              1 if tap > 0 else 0)
+                _lib.call('bruno_conv_epilogue_f32', dst, self.br[l].detach().contiguous(), skip, int(act), N, H, W)
+
+            hi = 0
+            for r in range(self.num_res_blocks):
+                ui, ni = (hi + 1) % 3, (hi + 2) % 3
+                conv(buf[hi], buf[ui], 2 * r, None, True)
+                conv(buf[ui], buf[ni], 2 * r + 1, buf[hi], True)
+                hi = ni
+            y = torch.empty_like(x)
+            ld_out = torch.empty_like(ld)
+            _lib.call('bruno_heads_coupling', x, buf[hi], self.Ks, self.bs, self.Kt, self.bt, None, None, ld, y, ld_out, 1,
+                      N, H, W, C, self.mask_id, int(inverse))
+        return y, ld_out
+
     def _apply(self, x, ld, inverse):
         if self.V1 is None:
             self._build(int(x.shape[3]), x.device)
+        if _PRECISION[0] == 'fp32':
+            return self._apply_fp32(x, ld, inverse)
         out = _ConvCouplingFn.apply(x, ld, self.V1, self.g1, self.b1, self.Vr, self.gr, self.br, self.Ks, self.bs,
                                     self.Kt, self.bt, self, inverse, torch.is_grad_enabled())
         if _INIT_MODE[0]:                      # outputs above use the OLD g, b (nvp:396-398: tf.identity(x))

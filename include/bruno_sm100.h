@@ -159,8 +159,9 @@ int bruno_conv3x3_wgrad_batched(const void* x_slab, const void* g_slab, float* d
                                 void* stream);
 
 /* c1 (nvp:113-115): out_slab = ELU(conv1x1_wn(x * mask)), x [N,H,W,C] fp32, V1 [C,64], g1, b1 [64]. */
+/* f32_slab = 1: the slab is the fp32 verification layout ([row][64] floats, same padded row indexing, no swizzle). */
 int bruno_c1_fwd(const float* x, const float* V1, const float* g1, const float* b1, int bias_img_stride, void* out_slab,
-                 int N, int H, int W, int C, int mask_type, void* stream);
+                 int f32_slab, int N, int H, int W, int C, int mask_type, void* stream);
 /* g_slab = dL/d(pre-activation of c1): dx += mask * (g W1^T); dW1 [C,64] += (x mask)^T g; db1 [64] += sum g. */
 int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g_slab, float* dx, float* dW1, float* db1,
                  int N, int H, int W, int C, int mask_type, void* stream);
@@ -171,7 +172,11 @@ int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g
  * (nn_extra_nvp_conditional.py:382-388). */
 int bruno_heads_coupling(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
                          const float* bt, const float* label_s, const float* label_t, const float* ld_in, float* y,
-                         float* ld_out, int N, int H, int W, int C, int mask_type, int inverse, void* stream);
+                         float* ld_out, int f32_slab, int N, int H, int W, int C, int mask_type, int inverse, void* stream);
+/* fp32 verification path (CouplingLayerConv precision 'fp32'): the nine taps of a 3x3 convolution are accumulated with
+ * bruno_sgemm on fp32 slabs ([rows][64] floats; row = position as in slab.cuh); this applies bias (+ skip) (+ ELU) on
+ * pixel rows and zeroes the padding rows. */
+int bruno_conv_epilogue_f32(float* acc, const float* bias, const float* skip, int elu, int N, int H, int W, void* stream);
 /* backward of the forward coupling: dx = direct part (the s/t-network part is added by bruno_c1_bwd), g_slab =
  * dL/d(pre-activation of the last residual block); dKs, dbs, dKt, dbt are overwritten (deterministic two-level sum:
  * per-block partials in `scratch` of bruno_heads_bwd_scratch_floats(C) floats, then a fixed-order reduction). */

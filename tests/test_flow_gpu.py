@@ -219,3 +219,49 @@ def test_conv_coupling_activations_bitwise_vs_emulating_oracle():
         assert ulp <= 2.0 ** -7
     print('\nmismatching bf16 values: c1 %.4f%%, c2_0 %.4f%%, block-0 output %.4f%%' % tuple(100 * f for f in frac))
     assert frac[0] == 0.0 and frac[1] < 1e-3 and frac[2] < 2e-3
+
+
+@pytest.mark.parametrize('name,B,T', [('bn2_omniglot_tp', 2, 3), ('bn2_omniglot_gp', 2, 2), ('an2_cifar_tp', 1, 2)])
+def test_fp32_verification_mode_meets_the_fp32_bound(name, B, T):
+    """The conv configs evaluated with nn_extra_nvp.precision('fp32') (every convolution in fp32 on CUDA cores) meet the
+    north star's fp32 bound -- per-example log-likelihood within 1e-4 relative of the oracle -- so the gap of the
+    production path is the declared bf16 rounding and nothing else."""
+    from bruno_b200 import nn_extra_nvp
+    spec, P, x, cfg, xg = setup(name, B, T, seed=5)
+    with torch.no_grad():
+        lp_o, lat_o, pri_o, z_o = O.build_model(spec, P, x)
+        with nn_extra_nvp.precision('fp32'):
+            lp, lat, pri, z = cfg.build_model(xg)
+        lp16 = cfg.build_model(xg)[0]
+    e32, e16 = rel_err(lp, lp_o), rel_err(lp16, lp_o)
+    zmax = z_o.abs().max().item()
+    print('\n[%s] per-example log-lik rel err: fp32 verification mode %.3e, bf16 production mode %.3e; max |dz| fp32 %.3e (|z| max %.1f)' % (
+        name, e32, e16, (z.double().cpu() - z_o).abs().max().item(), zmax))
+    assert e32 <= 1e-4
+    assert rel_err(lat, lat_o) <= 1e-4 and rel_err(pri, pri_o) <= 1e-4
+
+
+def test_few_shot_argmax_fp32_and_bf16_agree_with_oracle():
+    """Bit-exact few-shot decisions (north star): argmax over the 20 candidates in fp32 verification mode and in the
+    bf16 production mode both equal the oracle's, on every tested episode."""
+    from bruno_b200 import nn_extra_nvp
+    from bruno_b200.synthetic_data import SyntheticFewShotIterator
+    name = 'bn2_omniglot_tp'
+    spec = O.spec_for(name)
+    P = O.init_params(spec, seed=33, dtype=torch.float64, perturb_process=True)
+    it = SyntheticFewShotIterator(seq_len=2, batch_size=20, rng=np.random.RandomState(11), n_classes=24)
+    eps = [e for e, _ in zip(it.generate(), range(4))]
+    O.data_dependent_init(spec, P, torch.from_numpy(eps[0][0]).double())
+    P = O.cast_params(O.cast_params(P, torch.float32), torch.float64)
+    cfg = fresh_config(name)
+    cfg.build_model(torch.from_numpy(eps[0][0][:1]).cuda())
+    cfg.model.load_tf_variables(P)
+    for xb, y_batch, x_number in eps:
+        xb = torch.from_numpy(xb)
+        with torch.no_grad():
+            s_o = O.build_model(spec, P, xb.double())[0][:, -1]
+            s16 = cfg.build_model(xb.cuda())[0][:, -1]
+            with nn_extra_nvp.precision('fp32'):
+                s32 = cfg.build_model(xb.cuda())[0][:, -1]
+        assert int(s_o.argmax()) == int(s32.argmax()) == int(s16.argmax())
+        assert rel_err(s32, s_o) <= 1e-4
