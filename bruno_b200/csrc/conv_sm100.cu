@@ -223,7 +223,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       const uint32_t st2 = smem_u32(stage2 + a * STG_BYTES + srow * SLAB_ROW_BYTES);
       mbar_wait(&cs->tfull[a], aph);
       tc_fence_after();
-      if (warp == 2 && lane == 0) trace(it, 3);
+      if ((warp == 2 || warp == 10) && lane == 0) trace(it, 3);
 #pragma unroll 1
       for (int p = 0; p < 2; ++p) {
         const int cg = half * 2 + p;
@@ -240,6 +240,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&cs->tempty[a]);
+          if ((warp == 2 || warp == 10) && lane == 0) trace(it, 6);
         }
         const uint32_t xw0 = smem_u32(cs->xch[a][0][q][cg]);   // my dx = -1 block, needed by row + 1 -> written by lane 31
         const uint32_t xw2 = smem_u32(cs->xch[a][1][q][cg]);   // my dx = +1 block, needed by row - 1 -> written by lane 0
@@ -317,7 +318,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         }
       }
       fence_proxy_async_smem();                 // my generic-proxy writes -> visible to the bulk store
-      if (warp == 2 && lane == 0) trace(it, 4);
+      if ((warp == 2 || warp == 10) && lane == 0) trace(it, 4);
       mbar_arrive(&cs->outready[a]);
       data_row += OUT_ROWS * tile_stride;
       q_img += step_mod;

@@ -21,4 +21,4 @@ for mode in (0, 1):
     t0 = int(t[0, 0])
     print('mode', mode, ' columns: load_issued slab_landed mma_issued acc_ready epi_done store_issued store_read_done (cycles since first load)')
     for i in range(30):
-        print(i, 'load %d landed %d mma_done %d | epi: acc %d tmem %d shfl %d bar %d fix %d aux %d math %d fence %d | store %d' % tuple(int(t[i, k] - t0) for k in (0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 4, 5)))
+        print(i, 'load %d landed %d mma_issued %d | epi start %d tmem_free %d done %d | store %d' % tuple(int(t[i, k] - t0) for k in (0, 1, 2, 3, 6, 4, 5)))
