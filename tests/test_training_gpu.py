@@ -1,0 +1,50 @@
+"""GPU: a few full training steps (forward, hand-written backward, student-grad scaling, TF-1.7 RMSProp / Adam kernels on
+the flat parameter buffer) follow the oracle's trajectory.  en2 (fp32 path) -> tight tolerance."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bruno_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('optimizer', ['rmsprop', 'adam'])
+def test_training_trajectory_matches_oracle(optimizer):
+    name = 'en2_noconv_mnist_tp'
+    spec = O.spec_for(name)
+    P = O.init_params(spec, seed=2, dtype=torch.float64, perturb_process=True)
+    xs = [O.synthetic_batch(spec, 4, 5, seed=10 + i).float().double() for i in range(4)]
+    O.data_dependent_init(spec, P, xs[0])
+    P = O.cast_params(O.cast_params(P, torch.float32), torch.float64)
+    cfg = importlib.reload(importlib.import_module('bruno_b200.config_rnn.' + name))
+    cfg.optimizer = optimizer
+    from bruno_b200.trainer import Trainer
+    tr = Trainer(cfg, 'cuda:0')
+    tr.materialize(xs[0].float().cuda(), init=False)
+    cfg.model.load_tf_variables(P)
+    if optimizer == 'adam':
+        tr.slots = (torch.zeros_like(tr.flat), torch.zeros_like(tr.flat))
+    # oracle optimiser state
+    slots = {k: (torch.ones_like(v) if optimizer == 'rmsprop' else (torch.zeros_like(v), torch.zeros_like(v))) for k, v in P.items()}
+    lr, sscale = 1e-3, 0.1
+    for step in range(3):
+        x = xs[step + 1]
+        loss_o, grads = O.loss_and_grads(spec, P, x, student_grad_scale=sscale)
+        for k in P:
+            if optimizer == 'rmsprop':
+                P[k], slots[k] = O.rmsprop_tf17_step(P[k], grads[k], slots[k], lr)
+            else:
+                P[k], m, v = O.adam_tf17_step(P[k], grads[k], slots[k][0], slots[k][1], step + 1, lr)
+                slots[k] = (m, v)
+        loss = tr.train_step(x.float().cuda(), lr, sscale)
+        assert abs(loss.item() - loss_o.item()) <= 2e-4 * abs(loss_o.item()), (step, loss.item(), loss_o.item())
+    worst = 0.0
+    for tfname, view in cfg.model.named_tf_variables():
+        ref = P[tfname]
+        err = (view.detach().double().cpu().reshape(ref.shape) - ref).abs().max().item()
+        worst = max(worst, err / (ref.abs().max().item() + 1e-6))
+    print('\n[%s/%s] worst parameter deviation after 3 steps: %.3e of max' % (name, optimizer, worst))
+    assert worst <= 2e-3
