@@ -166,6 +166,9 @@ __device__ __forceinline__ Vf<VEC> ldv(const float* p) {
   if constexpr (VEC == 4) {
     float4 t = __ldg(reinterpret_cast<const float4*>(p));
     r.x[0] = t.x; r.x[1] = t.y; r.x[2] = t.z; r.x[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r.x[0] = t.x; r.x[1] = t.y;
   } else {
     r.x[0] = __ldg(p);
   }
@@ -179,6 +182,8 @@ __device__ __forceinline__ Vf<VEC> ldv_stream(const float* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x[0]), "=f"(r.x[1]), "=f"(r.x[2]), "=f"(r.x[3])
                  : "l"(p));
+  } else if constexpr (VEC == 2) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x[0]), "=f"(r.x[1]) : "l"(p));
   } else {
     r.x[0] = __ldg(p);
   }
@@ -188,6 +193,8 @@ template <int VEC>
 __device__ __forceinline__ void stv(float* p, const Vf<VEC>& v) {
   if constexpr (VEC == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(v.x[0], v.x[1], v.x[2], v.x[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(v.x[0], v.x[1]);
   } else {
     p[0] = v.x[0];
   }
@@ -263,15 +270,15 @@ __device__ __forceinline__ bool lane_is_writer(int lane) {
 // ------------------------------------------------------------------------------------------------------------
 // forward scan
 // ------------------------------------------------------------------------------------------------------------
-template <int KIND, int VEC, int NB, bool PRIOR, int PF, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template <int KIND, int VEC, int NB, bool PRIOR, int PF, int MINB, int RS, int MAXT>
+__global__ void __launch_bounds__(MAXT, MINB)
 process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, const float* __restrict__ tab,
                    float* __restrict__ s1, float* __restrict__ s2, float* __restrict__ lp,
                    float* __restrict__ lp_prior, float* __restrict__ scratch, int B, int T, int D) {
   constexpr int NCF = ncf_of(KIND);
   constexpr int NV = NB * 2;
-  constexpr int RS = 32 / NV;      // steps whose partial sums are reduced together: ONE 32-value butterfly per RS steps
-  static_assert(RS % PF == 0, "prefetch depth must divide the reduce batch");
+  constexpr int NVAL = NV * RS;    // RS steps' partial sums are reduced together: ONE NVAL-value butterfly per RS steps
+  static_assert(RS % PF == 0 && NVAL <= 32, "prefetch depth must divide the reduce batch");
   extern __shared__ float sred[];  // [T][nwarps][NV]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int d0 = (blockIdx.y * blockDim.x + threadIdx.x) * VEC;
@@ -322,7 +329,7 @@ process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
                      : zerov<VEC>();
 
   for (int n0 = 0; n0 < T; n0 += RS) {
-    float vals[32];
+    float vals[NVAL];
 #pragma unroll
     for (int pp = 0; pp < RS; ++pp) {
       const int n = n0 + pp;
@@ -380,9 +387,9 @@ process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
         vals[pp * NV + 2 * j + 1] = ok ? accp : 0.f;
       }
     }
-    warp_multi_reduce<32>(vals, lane);
-    {
-      const int slot = slot_of_lane<32>(lane);     // = pp * NV + idx
+    warp_multi_reduce<NVAL>(vals, lane);
+    if (lane_is_writer<NVAL>(lane)) {
+      const int slot = slot_of_lane<NVAL>(lane);   // = pp * NV + idx
       const int n = n0 + slot / NV;
       if (n < T) sred[(n * nwarps + warp) * NV + (slot % NV)] = vals[0];
     }
@@ -672,11 +679,25 @@ __global__ void process_sample_kernel(int kind, const float* __restrict__ rvs, c
 struct ScanGeom {
   int vec, threads, nseg;
 };
-static ScanGeom scan_geom(int D, bool ptr_ok) {
+static int fwd_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BRUNO_TP_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+static ScanGeom scan_geom(int D, bool ptr_ok, bool fwd = false) {
   ScanGeom g;
   g.vec = (D % 4 == 0 && ptr_ok) ? 4 : 1;
+  int maxt = 256;
+  if (fwd && fwd_variant() == 1 && D % 4 == 0 && ptr_ok && D / 2 <= 512) {   // 2-wide layout: more, lighter threads
+    g.vec = 2;
+    maxt = 512;
+  }
   const int chunks = D / g.vec;
-  g.threads = chunks >= 256 ? 256 : ((chunks + 31) / 32) * 32;
+  g.threads = chunks >= maxt ? maxt : ((chunks + 31) / 32) * 32;
   g.nseg = (chunks + g.threads - 1) / g.threads;
   return g;
 }
@@ -686,13 +707,13 @@ constexpr int BWD_NB = 2;
 // Variants of the forward scan (rows per thread NB, prefetch depth PF, resident blocks MINB), picked for occupancy /
 // memory-level parallelism: the first version (NB 4, PF 1, 128 registers, 14 warps per SM) reached 72 % of HBM peak for
 // the GP but only 36 % for the TP, whose 3 MUFU + ~17 FP ops per element need more warps to hide latency.
-template <int KIND, int VEC, int NB, int PF, int MINB>
+template <int KIND, int VEC, int NB, int PF, int MINB, int RS, int MAXT>
 static int launch_fwd_variant(const float* z, const float* mu0, const float* table, float* s1, float* s2, float* lp,
                               float* lp_prior, float* scratch, int B, int T, int D, const ScanGeom& g, cudaStream_t st) {
   dim3 grid(ceil_div(B, NB), g.nseg);
   const size_t smem = static_cast<size_t>(T) * (g.threads / 32) * NB * 2 * sizeof(float);
-  auto kp = process_fwd_kernel<KIND, VEC, NB, true, PF, MINB>;
-  auto kn = process_fwd_kernel<KIND, VEC, NB, false, PF, MINB>;
+  auto kp = process_fwd_kernel<KIND, VEC, NB, true, PF, MINB, RS, MAXT>;
+  auto kn = process_fwd_kernel<KIND, VEC, NB, false, PF, MINB, RS, MAXT>;
   auto k = lp_prior ? kp : kn;
   if (smem > 48 * 1024) {
     if (smem > 200 * 1024) {
@@ -715,24 +736,12 @@ static int launch_fwd_variant(const float* z, const float* mu0, const float* tab
   return rc;
 }
 
-static int fwd_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("BRUNO_TP_VARIANT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
 template <int KIND, int VEC>
 static int launch_fwd(const float* z, const float* mu0, const float* table, float* s1, float* s2, float* lp,
                       float* lp_prior, float* scratch, int B, int T, int D, const ScanGeom& g, cudaStream_t st) {
-  switch (fwd_variant()) {
-    case 0: return launch_fwd_variant<KIND, VEC, 4, 1, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
-    case 2: return launch_fwd_variant<KIND, VEC, 2, 2, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
-    case 3: return launch_fwd_variant<KIND, VEC, 2, 4, 3>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
-    default: return launch_fwd_variant<KIND, VEC, 4, 2, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
-  }
+  if (g.threads > 256)   // only the 2-wide layout uses blocks of up to 512 threads
+    return launch_fwd_variant<KIND, VEC, 4, 2, 2, 2, 512>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+  return launch_fwd_variant<KIND, VEC, 4, 1, 2, 4, 256>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
 }
 
 static int bwd_blocks(int B) {
@@ -798,14 +807,17 @@ int bruno_process_fwd(int kind, const float* z, const float* mu0, const float* t
   BRUNO_REQUIRE(z && mu0 && table && lp, "bruno_process_fwd: null pointer");
   BRUNO_REQUIRE((s1 == nullptr) == (s2 == nullptr) || kind == BRUNO_GP, "bruno_process_fwd: s1/s2 must come together");
   const bool ptr_ok = aligned16(z) && aligned16(mu0) && aligned16(table) && (!s1 || aligned16(s1)) && (!s2 || aligned16(s2));
-  ScanGeom g = scan_geom(D, ptr_ok);
+  ScanGeom g = scan_geom(D, ptr_ok, true);
   BRUNO_REQUIRE(g.nseg == 1 || scratch, "bruno_process_fwd: scratch required when D is split (D=%d)", D);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (kind == BRUNO_TP)
-    return g.vec == 4 ? launch_fwd<BRUNO_TP, 4>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st)
-                      : launch_fwd<BRUNO_TP, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
-  return g.vec == 4 ? launch_fwd<BRUNO_GP, 4>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st)
-                    : launch_fwd<BRUNO_GP, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+  if (kind == BRUNO_TP) {
+    if (g.vec == 4) return launch_fwd<BRUNO_TP, 4>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+    if (g.vec == 2) return launch_fwd<BRUNO_TP, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+    return launch_fwd<BRUNO_TP, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+  }
+  if (g.vec == 4) return launch_fwd<BRUNO_GP, 4>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+  if (g.vec == 2) return launch_fwd<BRUNO_GP, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+  return launch_fwd<BRUNO_GP, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
 }
 
 size_t bruno_process_bwd_scratch_floats(int B, int T, int D) {
