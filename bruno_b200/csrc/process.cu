@@ -302,14 +302,6 @@ process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
 #pragma unroll
       for (int i = 0; i < N_PRIOR; ++i) pc[i] = ldv<VEC>(tab + static_cast<size_t>(T * NCF + i) * D + d0);
     }
-    if (KIND == BRUNO_TP) {
-      // e' = 1 / ((v - c)(nu0 - 2)) does not depend on the step; A2_n = A2_0 + n dA, B2_n = A2_n - dA (dA = m ln2 / 2)
-      c_e = ldv<VEC>(tab + static_cast<size_t>(2) * D + d0);
-      c_a0 = ldv<VEC>(tab + static_cast<size_t>(5) * D + d0);
-      const Vf<VEC> b0v = ldv<VEC>(tab + static_cast<size_t>(6) * D + d0);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) c_da.x[e] = c_a0.x[e] - b0v.x[e];
-    }
     if (s1 != nullptr) {
 #pragma unroll
       for (int j = 0; j < NB; ++j)
@@ -325,6 +317,19 @@ process_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
   // 13 FP + 2 MUFU per element, the rest was address math, guards and register moves.)
   const int d0c = active ? d0 : 0;
   const float lane_mask = active ? 1.f : 0.f;
+  if (KIND == BRUNO_TP) {
+    // e' = 1 / ((v - c)(nu0 - 2)) does not depend on the step; A2_n = A2_0 + n dA, B2_n = A2_n - dA (dA = m ln2 / 2).
+    // Inactive lanes take the (consistent) coefficient set of dim 0: their values stay finite and are masked out.
+    c_e = ldv<VEC>(tab + static_cast<size_t>(2) * D + d0c);
+    c_a0 = ldv<VEC>(tab + static_cast<size_t>(5) * D + d0c);
+    const Vf<VEC> b0v = ldv<VEC>(tab + static_cast<size_t>(6) * D + d0c);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) c_da.x[e] = c_a0.x[e] - b0v.x[e];
+  }
+  if (PRIOR && !active) {
+#pragma unroll
+    for (int i = 0; i < N_PRIOR; ++i) pc[i] = ldv<VEC>(tab + static_cast<size_t>(T * NCF + i) * D + d0c);
+  }
   const float* zp[NB];
 #pragma unroll
   for (int j = 0; j < NB; ++j) zp[j] = z + static_cast<size_t>(min(b0 + j, B - 1)) * rowTD + d0c;
