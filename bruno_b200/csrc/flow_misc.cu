@@ -236,9 +236,15 @@ c1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
     int ai = 0;
     for (int o = threadIdx.x; o < nout; o += 256, ++ai) {
       const int co = o & 63, c = o >> 6;
-      float a = 0.f;
-      for (int pp = 0; pp < 256; ++pp) a = fmaf(x_s[pp * (MAXC + 1) + c], g_s[pp * 65 + co], a);
-      acc[ai] += a;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+      for (int pp = 0; pp < 256; pp += 4) {
+        a0 = fmaf(x_s[pp * (MAXC + 1) + c], g_s[pp * 65 + co], a0);
+        a1 = fmaf(x_s[(pp + 1) * (MAXC + 1) + c], g_s[(pp + 1) * 65 + co], a1);
+        a2 = fmaf(x_s[(pp + 2) * (MAXC + 1) + c], g_s[(pp + 2) * 65 + co], a2);
+        a3 = fmaf(x_s[(pp + 3) * (MAXC + 1) + c], g_s[(pp + 3) * 65 + co], a3);
+      }
+      acc[ai] += (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
   }
@@ -416,9 +422,15 @@ heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restri
     int ai = 0;
     for (int o = threadIdx.x; o < nout; o += 256, ++ai) {
       const int k = o % 65, c2 = o / 65;
-      float a = 0.f;
-      for (int pp = 0; pp < 256; ++pp) a = fmaf(h_s[pp * 65 + k], d_s[pp * (2 * MAXC + 1) + c2], a);
-      acc[ai] += a;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // independent chains: the loop is LDS-latency bound otherwise
+#pragma unroll 4
+      for (int pp = 0; pp < 256; pp += 4) {
+        a0 = fmaf(h_s[pp * 65 + k], d_s[pp * (2 * MAXC + 1) + c2], a0);
+        a1 = fmaf(h_s[(pp + 1) * 65 + k], d_s[(pp + 1) * (2 * MAXC + 1) + c2], a1);
+        a2 = fmaf(h_s[(pp + 2) * 65 + k], d_s[(pp + 2) * (2 * MAXC + 1) + c2], a2);
+        a3 = fmaf(h_s[(pp + 3) * 65 + k], d_s[(pp + 3) * (2 * MAXC + 1) + c2], a3);
+      }
+      acc[ai] += (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
   }
@@ -433,8 +445,16 @@ __global__ void heads_bwd_finalize_kernel(const float* __restrict__ partial, int
   const int nout = 65 * 2 * C;
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= nout) return;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partial[static_cast<size_t>(b) * nout + o];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // fixed order, four independent chains
+  int b = 0;
+  for (; b + 3 < nblk; b += 4) {
+    s0 += partial[static_cast<size_t>(b) * nout + o];
+    s1 += partial[static_cast<size_t>(b + 1) * nout + o];
+    s2 += partial[static_cast<size_t>(b + 2) * nout + o];
+    s3 += partial[static_cast<size_t>(b + 3) * nout + o];
+  }
+  for (; b < nblk; ++b) s0 += partial[static_cast<size_t>(b) * nout + o];
+  const float s = (s0 + s1) + (s2 + s3);
   const int k = o % 65, c2 = o / 65;
   const bool is_t = c2 >= C;
   const int c = is_t ? c2 - C : c2;

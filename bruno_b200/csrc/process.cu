@@ -764,7 +764,12 @@ static int launch_fwd(const float* z, const float* mu0, const float* table, floa
                       float* lp_prior, float* scratch, int B, int T, int D, const ScanGeom& g, cudaStream_t st) {
   if (g.threads > 256)   // only the 2-wide layout uses blocks of up to 512 threads
     return launch_fwd_variant<KIND, VEC, 4, 2, 2, 2, 512>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
-  return launch_fwd_variant<KIND, VEC, 4, 1, 2, 4, 256>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+  switch (fwd_variant()) {
+    case 2: return launch_fwd_variant<KIND, VEC, 4, 1, 3, 4, 256>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+    case 3: return launch_fwd_variant<KIND, VEC, 2, 1, 3, 4, 256>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+    case 4: return launch_fwd_variant<KIND, VEC, 2, 1, 4, 8, 256>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+    default: return launch_fwd_variant<KIND, VEC, 4, 1, 2, 4, 256>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
+  }
 }
 
 static int bwd_blocks(int B) {
