@@ -212,6 +212,14 @@ def main():
         few_shot(i)
     fs_steps = max(steps, 10)
     ms_fs = timed(few_shot, fs_steps)
+    graphed = cfg.model.graphed_forward(fs_x[0])            # the same episode as ONE CUDA-graph launch
+
+    def few_shot_graph(i):
+        graphed(fs_x[i % 4])[0][:, -1].argmax()
+
+    for i in range(3):
+        few_shot_graph(i)
+    ms_fsg = timed(few_shot_graph, fs_steps)
 
     # second pass with per-launch CUDA events on the conv kernels (live durations inside the step)
     _lib.query('bruno_profile_enable', 1)
@@ -252,7 +260,8 @@ def main():
                    'l2_note': 'working set per step (6.3 GB of saved bf16 activations) >> 126 MB L2; inputs rotate over %d batches' % n_host},
         'eval_nll': {'value': seqs * steps / (ms_eval * 1e-3), 'unit': 'seqs/s', 'ms_per_step': ms_eval / steps,
                      'what': 'forward NLL (log_probs, latent, prior) of the same batch shape'},
-        'few_shot_20way_1shot': {'value': world * fs_steps / (ms_fs * 1e-3), 'unit': 'episodes/s', 'ms_per_episode': ms_fs / fs_steps,
+        'few_shot_20way_1shot': {'value': world * fs_steps / (ms_fsg * 1e-3), 'unit': 'episodes/s', 'ms_per_episode': ms_fsg / fs_steps,
+                                 'ms_per_episode_eager': ms_fs / fs_steps,
                                  'what': 'test_few_shot_omniglot scoring: 20 candidate sequences x 2 frames, forward + argmax'},
         'e2e': {'value': seqs * steps / (ms_e2e * 1e-3), 'unit': 'seqs/s', 'h2d_bytes_per_step': int(host[0].numel() * 4),
                 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / steps},

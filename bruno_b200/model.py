@@ -103,6 +103,32 @@ class BrunoModel(object):
             return x_samples, log_probs
 
     # ---------------------------------------------------------------------------------------------------
+    # CUDA-graphed inference (latency-bound cases: few-shot episodes of 40 images, test_nll's batch of 1)
+    # ---------------------------------------------------------------------------------------------------
+    def graphed_forward(self, x_example, want_prior=False):
+        """Captures build_model(x) (forward, no grad) for the shape of `x_example` into ONE CUDA graph and returns
+        f(x) -> (log_probs, latent_log_probs, latent_log_probs_prior or None, z_vec).  ~450 kernel launches of a
+        20-way 1-shot episode become one graph launch; outputs are views of static buffers (overwritten by the next call)."""
+        static_x = x_example.clone()
+        with torch.no_grad():
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):                       # warm-up: lazy variable creation, cudaFuncSetAttribute, slab pools
+                    self.build_model(static_x, want_prior=want_prior)
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self.build_model(static_x, want_prior=want_prior)
+
+        def run(x):
+            static_x.copy_(x, non_blocking=True)
+            graph.replay()
+            return static_out
+        run.graph = graph
+        return run
+
+    # ---------------------------------------------------------------------------------------------------
     # parameters
     # ---------------------------------------------------------------------------------------------------
     def layers(self):

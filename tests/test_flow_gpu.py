@@ -265,3 +265,17 @@ def test_few_shot_argmax_fp32_and_bf16_agree_with_oracle():
                 s32 = cfg.build_model(xb.cuda())[0][:, -1]
         assert int(s_o.argmax()) == int(s32.argmax()) == int(s16.argmax())
         assert rel_err(s32, s_o) <= 1e-4
+
+
+def test_cuda_graphed_forward_equals_eager():
+    """The CUDA-graphed few-shot forward (one graph launch per episode) is bit-identical to the eager path."""
+    name = 'bn2_omniglot_tp'
+    spec, P, x, cfg, xg = setup(name, 3, 2, seed=17)
+    with torch.no_grad():
+        ref = cfg.build_model(xg, want_prior=False)[0].clone()
+        f = cfg.model.graphed_forward(xg)
+        out = f(xg)[0].clone()
+        assert torch.equal(out, ref)
+        x2 = xg.flip(0).contiguous()
+        ref2 = cfg.build_model(x2, want_prior=False)[0].clone()
+        assert torch.equal(f(x2)[0], ref2)
