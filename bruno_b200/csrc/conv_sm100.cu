@@ -135,6 +135,9 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = cs->tmem_base;
+  // Programmatic dependent launch: let the next kernel of the stream be scheduled now (its prologue and weight load
+  // overlap our tail); our own reads / writes of activation slabs wait for the previous kernel (griddepcontrol.wait).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // geometry of tile t: computed rows = data rows [126 t - 1, 126 t + 127); stored rows = data rows [126 t, 126 t + 126)
   //   first computed buffer row  Rc = HALO + 126 t - 1;  slab load starts at LS = floor8(Rc - P)
@@ -143,7 +146,8 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
     // ===== producer: weights once, then the activation slab of every tile =====
     if (lane == 0) {
       mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
-      bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);
+      bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);      // weights do not depend on the previous kernel
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % NSTAGE;
@@ -331,6 +335,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
   } else {
     // ===== aux / store warp: prefetch the aux tile(s) of tile `it`, then drain the output tile of tile `it - 1` =====
     if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       int it = 0;
       int prev_tile = -1;
       for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
@@ -632,9 +637,19 @@ static int launch_conv(const void* in, const void* w, const float* bias, int bia
   const int ntiles = (g.data_rows + OUT_ROWS - 1) / OUT_ROWS;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
   ProfSpan span(BRUNO_PROF_CONV, st);
-  conv3x3_kernel<MODE><<<grid, FWD_THREADS, smem, st>>>(
-      static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias, static_cast<const uint8_t*>(a1),
-      static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g, ntiles, bias_img_stride);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(FWD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, conv3x3_kernel<MODE>, static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias,
+                     static_cast<const uint8_t*>(a1), static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g, ntiles,
+                     bias_img_stride);
   return check_launch("conv3x3_kernel");
 }
 
