@@ -117,9 +117,122 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const fl
   }
 }
 
+// Fast path for 16-byte aligned operands (all shapes of the target configs): 128-bit global loads staged through
+// registers one K tile ahead, shared-memory double buffer, one __syncthreads per K tile.  Same 64x64x16 block tile and
+// 4x4 register tile; same epilogue.  Requires lda, ldb % 4 == 0, 16-byte aligned A, B and K % 4 == 0.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+sgemm_fast_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                  float* __restrict__ C, int ldc, GemmEpi ep) {
+  __shared__ __align__(16) float As[2][GK][GB + 4];
+  __shared__ __align__(16) float Bs[2][GK][GB + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // load coordinates (one float4 of A and one of B per thread per K tile)
+  //   A not transposed [M,K]: m = tid / 4, k4 = (tid % 4) * 4 (vector along k);  transposed [K,M]: k = tid / 16, m4 = (tid % 16) * 4
+  //   B not transposed [K,N]: k = tid / 16, n4 = (tid % 16) * 4 (vector along n);  transposed [N,K]: n = tid / 4, k4 = (tid % 4) * 4
+  const int a_r = TA ? (tid >> 4) : (tid >> 2), a_c = TA ? (tid & 15) * 4 : (tid & 3) * 4;
+  const int b_r = TB ? (tid >> 2) : (tid >> 4), b_c = TB ? (tid & 3) * 4 : (tid & 15) * 4;
+  const int nk = (K + GK - 1) / GK;
+  float4 ra, rb;
+  auto gload = [&](int kt) {
+    const int k0 = kt * GK;
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (TA) {
+      if (k0 + a_r < K && m0 + a_c < M) ra = __ldg(reinterpret_cast<const float4*>(A + static_cast<size_t>(k0 + a_r) * lda + m0 + a_c));
+    } else {
+      if (m0 + a_r < M && k0 + a_c < K) ra = __ldg(reinterpret_cast<const float4*>(A + static_cast<size_t>(m0 + a_r) * lda + k0 + a_c));
+    }
+    if (TB) {
+      if (n0 + b_r < N && k0 + b_c < K) rb = __ldg(reinterpret_cast<const float4*>(B + static_cast<size_t>(n0 + b_r) * ldb + k0 + b_c));
+    } else {
+      if (k0 + b_r < K && n0 + b_c < N) rb = __ldg(reinterpret_cast<const float4*>(B + static_cast<size_t>(k0 + b_r) * ldb + n0 + b_c));
+    }
+  };
+  auto sstore = [&](int buf, int kt) {
+    if (ep.a_kscale) {
+      const int k0 = kt * GK;
+      if (TA) {
+        const float sc = k0 + a_r < K ? __ldg(ep.a_kscale + k0 + a_r) : 0.f;
+        ra.x *= sc; ra.y *= sc; ra.z *= sc; ra.w *= sc;
+      } else if (k0 + a_c < K) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(ep.a_kscale + k0 + a_c));
+        ra.x *= sc.x; ra.y *= sc.y; ra.z *= sc.z; ra.w *= sc.w;
+      }
+    }
+    if (TA) {
+      *reinterpret_cast<float4*>(&As[buf][a_r][a_c]) = ra;
+    } else {
+      As[buf][a_c][a_r] = ra.x; As[buf][a_c + 1][a_r] = ra.y; As[buf][a_c + 2][a_r] = ra.z; As[buf][a_c + 3][a_r] = ra.w;
+    }
+    if (TB) {
+      Bs[buf][b_c][b_r] = rb.x; Bs[buf][b_c + 1][b_r] = rb.y; Bs[buf][b_c + 2][b_r] = rb.z; Bs[buf][b_c + 3][b_r] = rb.w;
+    } else {
+      *reinterpret_cast<float4*>(&Bs[buf][b_r][b_c]) = rb;
+    }
+  };
+  gload(0);
+  sstore(0, 0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload(kt + 1);
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1, kt + 1);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (ep.col_scale) v *= ep.col_scale[n];
+      if (ep.bias) v += ep.bias[n];
+      const size_t o = static_cast<size_t>(m) * ldc + n;
+      if (ep.pre_out) ep.pre_out[o] = v;
+      if (ep.act == 1) v = v > 0.f ? v : expm1f(v);
+      else if (ep.act == 2) v = v > 0.f ? v : 0.2f * v;
+      else if (ep.act == 3) v = tanhf(v);
+      if (ep.accumulate) v += C[o];
+      C[o] = v;
+    }
+  }
+}
+
 static int gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 const GemmEpi& ep, cudaStream_t st) {
   dim3 grid(ceil_div(N, GB), ceil_div(M, GB));
+  const bool vec_ok = aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0 && K % 4 == 0 &&
+                      (ta ? M % 4 == 0 : true) && (tb ? true : N % 4 == 0) && (!ep.a_kscale || aligned16(ep.a_kscale));
+  if (vec_ok) {
+    if (!ta && !tb) sgemm_fast_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
+    else if (ta && !tb) sgemm_fast_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
+    else if (!ta && tb) sgemm_fast_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
+    else sgemm_fast_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
+    return check_launch("sgemm_fast_kernel");
+  }
   if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
   else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
   else if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
