@@ -117,95 +117,178 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const fl
   }
 }
 
-// Fast path for 16-byte aligned operands (all shapes of the target configs): 128-bit global loads staged through
-// registers one K tile ahead, shared-memory double buffer, one __syncthreads per K tile.  Same 64x64x16 block tile and
-// 4x4 register tile; same epilogue.  Requires lda, ldb % 4 == 0, 16-byte aligned A, B and K % 4 == 0.
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(256)
-sgemm_fast_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                  float* __restrict__ C, int ldc, GemmEpi ep) {
-  __shared__ __align__(16) float As[2][GK][GB + 4];
-  __shared__ __align__(16) float Bs[2][GK][GB + 4];
+// Fast path for 16-byte aligned operands (all shapes of the target configs).
+//   * both operands are staged in their NATURAL orientation by 16-byte cp.async (LDGSTS.128, zero-fill at the edges)
+//     through a 4-stage ring: the K loop of these skinny GEMMs (640 x 512 x 784; 40 x 512 x 784 for few-shot scoring) is
+//     bound by global-load latency, not FFMA issue, so three K tiles are kept in flight;
+//   * block tile (16 MI) x 64 x 16 with an MI x 4 register tile (MI = 8 for M >= 192, else 4);
+//   * split-K over gridDim.z so that the grid covers ~2 CTAs per SM even when the output has only 8-80 tiles.  Partials
+//     go to a per-tile workspace; the LAST CTA to finish a tile (ticket counter) sums them in z order -- deterministic --
+//     and runs the fused epilogue.  The counter is reset by that CTA, so launches are self-cleaning and graph-safe.
+//     The workspace is shared by all launches of this process: SGEMMs must be issued on one stream (they are).
+// Requires lda, ldb % 4 == 0, 16-byte aligned A, B, K % 4 == 0, and M % 4 (transA) / N % 4 (!transB).
+constexpr int SK_STAGES = 4;
+constexpr int SK_BN = 64;
+
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+template <bool TA, int MI> struct SkShape {
+  static constexpr int BM = 16 * MI;
+  static constexpr int A_FLOATS = TA ? GK * (BM + 4) : BM * (GK + 4);
+};
+template <bool TB> struct SkShapeB {
+  static constexpr int B_FLOATS = TB ? SK_BN * (GK + 4) : GK * (SK_BN + 4);
+};
+
+template <bool TA, bool TB, int MI>
+__global__ void __launch_bounds__(256, 2)
+sgemm_sk_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                float* __restrict__ C, int ldc, GemmEpi ep, int kchunk, float* __restrict__ ws, unsigned* __restrict__ tickets) {
+  constexpr int BM = SkShape<TA, MI>::BM;
+  constexpr int A_FLOATS = SkShape<TA, MI>::A_FLOATS, B_FLOATS = SkShapeB<TB>::B_FLOATS;
+  constexpr int APITCH = TA ? BM + 4 : GK + 4, BPITCH = TB ? GK + 4 : SK_BN + 4;
+  extern __shared__ __align__(16) float sk_smem[];
+  float* As = sk_smem;                          // [SK_STAGES][A_FLOATS]
+  float* Bs = sk_smem + SK_STAGES * A_FLOATS;   // [SK_STAGES][B_FLOATS]
+  __shared__ int s_last;
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.y * GB, n0 = blockIdx.x * GB;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * SK_BN;
   const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
+  const int nk = (K + GK - 1) / GK;
+  const int kt0 = blockIdx.z * kchunk, kt1 = min(nk, kt0 + kchunk);
+
+  float acc[MI][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  // load coordinates (one float4 of A and one of B per thread per K tile)
-  //   A not transposed [M,K]: m = tid / 4, k4 = (tid % 4) * 4 (vector along k);  transposed [K,M]: k = tid / 16, m4 = (tid % 16) * 4
-  //   B not transposed [K,N]: k = tid / 16, n4 = (tid % 16) * 4 (vector along n);  transposed [N,K]: n = tid / 4, k4 = (tid % 4) * 4
-  const int a_r = TA ? (tid >> 4) : (tid >> 2), a_c = TA ? (tid & 15) * 4 : (tid & 3) * 4;
-  const int b_r = TB ? (tid >> 2) : (tid >> 4), b_c = TB ? (tid & 3) * 4 : (tid & 15) * 4;
-  const int nk = (K + GK - 1) / GK;
-  float4 ra, rb;
-  auto gload = [&](int kt) {
-    const int k0 = kt * GK;
-    ra = make_float4(0.f, 0.f, 0.f, 0.f);
-    rb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (TA) {
-      if (k0 + a_r < K && m0 + a_c < M) ra = __ldg(reinterpret_cast<const float4*>(A + static_cast<size_t>(k0 + a_r) * lda + m0 + a_c));
-    } else {
-      if (m0 + a_r < M && k0 + a_c < K) ra = __ldg(reinterpret_cast<const float4*>(A + static_cast<size_t>(m0 + a_r) * lda + k0 + a_c));
-    }
-    if (TB) {
-      if (n0 + b_r < N && k0 + b_c < K) rb = __ldg(reinterpret_cast<const float4*>(B + static_cast<size_t>(n0 + b_r) * ldb + k0 + b_c));
-    } else {
-      if (k0 + b_r < K && n0 + b_c < N) rb = __ldg(reinterpret_cast<const float4*>(B + static_cast<size_t>(k0 + b_r) * ldb + n0 + b_c));
-    }
-  };
-  auto sstore = [&](int buf, int kt) {
-    if (ep.a_kscale) {
-      const int k0 = kt * GK;
-      if (TA) {
-        const float sc = k0 + a_r < K ? __ldg(ep.a_kscale + k0 + a_r) : 0.f;
-        ra.x *= sc; ra.y *= sc; ra.z *= sc; ra.w *= sc;
-      } else if (k0 + a_c < K) {
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(ep.a_kscale + k0 + a_c));
-        ra.x *= sc.x; ra.y *= sc.y; ra.z *= sc.z; ra.w *= sc.w;
+
+  auto load_stage = [&](int kt) {
+    const int st = kt % SK_STAGES, k0 = kt * GK;
+    float* as = As + st * A_FLOATS;
+    float* bs = Bs + st * B_FLOATS;
+#pragma unroll
+    for (int v = tid; v < BM * GK / 4; v += 256) {
+      if (TA) {   // A stored [K, M]: vectors along m
+        const int k = v / (BM / 4), m4 = (v % (BM / 4)) * 4;
+        const bool ok = (k0 + k < K) && (m0 + m4 < M);
+        cp_async16(as + k * APITCH + m4, ok ? A + static_cast<size_t>(k0 + k) * lda + m0 + m4 : A, ok);
+      } else {    // A stored [M, K]: vectors along k
+        const int m = v >> 2, k4 = (v & 3) * 4;
+        const bool ok = (m0 + m < M) && (k0 + k4 < K);
+        cp_async16(as + m * APITCH + k4, ok ? A + static_cast<size_t>(m0 + m) * lda + k0 + k4 : A, ok);
       }
     }
-    if (TA) {
-      *reinterpret_cast<float4*>(&As[buf][a_r][a_c]) = ra;
-    } else {
-      As[buf][a_c][a_r] = ra.x; As[buf][a_c + 1][a_r] = ra.y; As[buf][a_c + 2][a_r] = ra.z; As[buf][a_c + 3][a_r] = ra.w;
-    }
-    if (TB) {
-      Bs[buf][b_c][b_r] = rb.x; Bs[buf][b_c + 1][b_r] = rb.y; Bs[buf][b_c + 2][b_r] = rb.z; Bs[buf][b_c + 3][b_r] = rb.w;
-    } else {
-      *reinterpret_cast<float4*>(&Bs[buf][b_r][b_c]) = rb;
+    {
+      const int v = tid;
+      if (TB) {   // B stored [N, K]
+        const int n = v >> 2, k4 = (v & 3) * 4;
+        const bool ok = (n0 + n < N) && (k0 + k4 < K);
+        cp_async16(bs + n * BPITCH + k4, ok ? B + static_cast<size_t>(n0 + n) * ldb + k0 + k4 : B, ok);
+      } else {    // B stored [K, N]
+        const int k = v >> 4, n4 = (v & 15) * 4;
+        const bool ok = (k0 + k < K) && (n0 + n4 < N);
+        cp_async16(bs + k * BPITCH + n4, ok ? B + static_cast<size_t>(k0 + k) * ldb + n0 + n4 : B, ok);
+      }
     }
   };
-  gload(0);
-  sstore(0, 0);
-  __syncthreads();
-  for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nk) gload(kt + 1);
+
 #pragma unroll
-    for (int k = 0; k < GK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+  for (int s = 0; s < SK_STAGES - 1; ++s) {
+    if (kt0 + s < kt1) load_stage(kt0 + s);
+    cp_async_commit();
+  }
+  for (int kt = kt0; kt < kt1; ++kt) {
+    cp_async_wait<SK_STAGES - 2>();
+    __syncthreads();
+    if (kt + SK_STAGES - 1 < kt1) load_stage(kt + SK_STAGES - 1);
+    cp_async_commit();
+    const float* as = As + (kt % SK_STAGES) * A_FLOATS;
+    const float* bs = Bs + (kt % SK_STAGES) * B_FLOATS;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+    for (int k4 = 0; k4 < GK; k4 += 4) {
+      float a[MI][4], b[4][4];   // [row or col][k within the group of 4]
+      if (TA) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-    if (kt + 1 < nk) {
-      sstore(buf ^ 1, kt + 1);
-      __syncthreads();
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+          for (int h = 0; h < MI / 4; ++h) {
+            const float4 v = *reinterpret_cast<const float4*>(as + (k4 + kk) * APITCH + ty * 4 + 64 * h);
+            a[4 * h][kk] = v.x; a[4 * h + 1][kk] = v.y; a[4 * h + 2][kk] = v.z; a[4 * h + 3][kk] = v.w;
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(as + (ty * 4 + (i & 3) + 64 * (i >> 2)) * APITCH + k4);
+          a[i][0] = v.x; a[i][1] = v.y; a[i][2] = v.z; a[i][3] = v.w;
+        }
+      }
+      if (TB) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(bs + (tx + 16 * j) * BPITCH + k4);
+          b[j][0] = v.x; b[j][1] = v.y; b[j][2] = v.z; b[j][3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 v = *reinterpret_cast<const float4*>(bs + (k4 + kk) * BPITCH + tx * 4);
+          b[0][kk] = v.x; b[1][kk] = v.y; b[2][kk] = v.z; b[3][kk] = v.w;
+        }
+      }
+      if (ep.a_kscale) {   // (A diag(s)) B == A (diag(s) B): scale the 16 b values instead of the 4 MI a values
+        const int kg = kt * GK + k4;
+        float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kg < K) sc = __ldg(reinterpret_cast<const float4*>(ep.a_kscale + kg));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { b[j][0] *= sc.x; b[j][1] *= sc.y; b[j][2] *= sc.z; b[j][3] *= sc.w; }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i][kk], b[j][kk], acc[i][j]);
     }
   }
+  cp_async_wait<0>();
+
+  const int S = gridDim.z;
+  if (S > 1) {
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    float4* wt = reinterpret_cast<float4*>(ws) + static_cast<size_t>(tile) * S * (MI * 256);
+    float4* mine = wt + static_cast<size_t>(blockIdx.z) * (MI * 256);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < MI; ++i) __stcg(mine + i * 256 + tid, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(tickets + tile, 1u) == static_cast<unsigned>(S - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < MI; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int z = 0; z < S; ++z) {
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const float4 v = __ldcg(wt + static_cast<size_t>(z) * (MI * 256) + i * 256 + tid);
+        acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+      }
+    }
+    if (tid == 0) tickets[tile] = 0u;
+  }
+
+#pragma unroll
+  for (int i = 0; i < MI; ++i) {
+    const int m = m0 + ty * 4 + (i & 3) + 64 * (i >> 2);
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+      const int n = n0 + (TB ? tx + 16 * j : tx * 4 + j);
       if (n >= N) continue;
       float v = acc[i][j];
       if (ep.col_scale) v *= ep.col_scale[n];
@@ -221,18 +304,73 @@ sgemm_fast_kernel(int M, int N, int K, const float* __restrict__ A, int lda, con
   }
 }
 
+// split-K workspace (grow-never, allocated on first use outside stream capture)
+constexpr size_t SK_WS_FLOATS = size_t(4) << 20;   // 16 MB
+constexpr int SK_MAX_TILES = 4096;
+static float* g_sk_ws = nullptr;
+static unsigned* g_sk_tickets = nullptr;
+static int g_sk_sms = 0;
+
+static bool sk_workspace(cudaStream_t st) {
+  if (g_sk_ws) return true;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_sk_sms, cudaDevAttrMultiProcessorCount, dev);
+  float* w = nullptr;
+  unsigned* t = nullptr;
+  if (cudaMalloc(&w, SK_WS_FLOATS * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cudaMalloc(&t, SK_MAX_TILES * sizeof(unsigned)) != cudaSuccess || cudaMemset(t, 0, SK_MAX_TILES * sizeof(unsigned)) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(w);
+    return false;
+  }
+  g_sk_ws = w;
+  g_sk_tickets = t;
+  return true;
+}
+
+template <bool TA, bool TB, int MI>
+static int launch_sk(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& ep,
+                     cudaStream_t st) {
+  constexpr int BM = SkShape<TA, MI>::BM;
+  constexpr size_t smem = size_t(SK_STAGES) * (SkShape<TA, MI>::A_FLOATS + SkShapeB<TB>::B_FLOATS) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(sgemm_sk_kernel<TA, TB, MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    attr_done = true;
+  }
+  const int nx = ceil_div(N, SK_BN), ny = ceil_div(M, BM), tiles = nx * ny, nk = ceil_div(K, GK);
+  int S = 1;
+  if (tiles <= SK_MAX_TILES && sk_workspace(st)) {
+    S = (2 * g_sk_sms + tiles / 2) / tiles;
+    S = max(1, min(S, nk / 4));
+    const size_t per_split = static_cast<size_t>(tiles) * BM * SK_BN;
+    while (S > 1 && per_split * S > SK_WS_FLOATS) --S;
+  }
+  const int kchunk = ceil_div(nk, S);
+  S = ceil_div(nk, kchunk);
+  sgemm_sk_kernel<TA, TB, MI><<<dim3(nx, ny, S), 256, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep, kchunk, g_sk_ws, g_sk_tickets);
+  return check_launch("sgemm_sk_kernel");
+}
+
 static int gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 const GemmEpi& ep, cudaStream_t st) {
-  dim3 grid(ceil_div(N, GB), ceil_div(M, GB));
   const bool vec_ok = aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0 && K % 4 == 0 &&
                       (ta ? M % 4 == 0 : true) && (tb ? true : N % 4 == 0) && (!ep.a_kscale || aligned16(ep.a_kscale));
   if (vec_ok) {
-    if (!ta && !tb) sgemm_fast_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
-    else if (ta && !tb) sgemm_fast_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
-    else if (!ta && tb) sgemm_fast_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
-    else sgemm_fast_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
-    return check_launch("sgemm_fast_kernel");
+    const bool big = M >= 192;
+#define SK_DISPATCH(TA_, TB_)                                                                            \
+  return big ? launch_sk<TA_, TB_, 8>(M, N, K, A, lda, B, ldb, C, ldc, ep, st)                           \
+             : launch_sk<TA_, TB_, 4>(M, N, K, A, lda, B, ldb, C, ldc, ep, st)
+    if (!ta && !tb) { SK_DISPATCH(false, false); }
+    else if (ta && !tb) { SK_DISPATCH(true, false); }
+    else if (!ta && tb) { SK_DISPATCH(false, true); }
+    else { SK_DISPATCH(true, true); }
+#undef SK_DISPATCH
   }
+  dim3 grid(ceil_div(N, GB), ceil_div(M, GB));
   if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
   else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
   else if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep);
