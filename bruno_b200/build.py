@@ -17,6 +17,7 @@ SOURCES = ['runtime.cu', 'process.cu', 'flow_misc.cu', 'dense.cu', 'conv_sm100.c
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
+NVCC_FLAGS += os.environ.get('BRUNO_NVCC_EXTRA', '').split()   # experiments: e.g. -DBRUNO_EXP_...
 
 
 def _nvcc():

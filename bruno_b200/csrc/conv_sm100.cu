@@ -49,9 +49,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // Optional pipeline trace (debug): CTA 0 records clock64() at role events into a caller-provided device buffer
 // [tile][16]: 0 slab load issued, 1 slab landed (MMA thread), 2 MMAs issued, 3 accumulator ready (epilogue warp 2),
 // 4 epilogue math done, 5 store issued, 6 store smem-read done.
-__device__ long long* g_conv_trace = nullptr;
-__device__ __forceinline__ void trace(int it, int slot) {
-  if (g_conv_trace != nullptr && blockIdx.x == 0 && it < 64) g_conv_trace[it * 16 + slot] = clock64();
+// The buffer pointer is a kernel parameter (a uniform compare, not a global load on the issue path).
+static long long* g_conv_trace_host = nullptr;
+__device__ __forceinline__ void trace_at(long long* buf, int it, int slot) {
+  if (buf != nullptr && blockIdx.x == 0 && it < 64) buf[it * 16 + slot] = clock64();
 }
 
 constexpr int FWD_EPI_WARPS = 16;            // 4 per TMEM lane quarter: each handles 32 rows x 16 channels
@@ -98,7 +99,7 @@ template <int MODE>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
                const uint8_t* __restrict__ aux1, const uint8_t* __restrict__ aux2, uint8_t* __restrict__ out,
-               SlabGeom g, int ntiles, int bias_img_stride) {
+               SlabGeom g, int ntiles, int bias_img_stride, long long* trace_buf) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int slab_rows = TILE_M + 2 * g.HALO + 8;
@@ -156,7 +157,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         mbar_wait(&cs->empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&cs->full[s], slab_bytes);
         bulk_g2s(slabs + s * slab_bytes, in + static_cast<size_t>(LS) * SLAB_ROW_BYTES, slab_bytes, &cs->full[s]);
-        trace(it, 0);
+        trace_at(trace_buf, it, 0);
       }
     }
   } else if (warp == 1) {
@@ -176,7 +177,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         mbar_wait(&cs->tempty[a], aph ^ 1);
         mbar_wait(&cs->full[s], ph);
         tc_fence_after();
-        trace(it, 1);
+        trace_at(trace_buf, it, 1);
         const uint64_t adesc0 = umma_desc_sw128(smem_u32(slabs + s * slab_bytes), 16, 1024);
         const uint32_t d_tmem = tmem + a * 256;
 #pragma unroll
@@ -190,7 +191,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         }
         umma_commit(&cs->empty[s]);
         umma_commit(&cs->tfull[a]);
-        trace(it, 2);
+        trace_at(trace_buf, it, 2);
       }
     }
   } else if (warp < 2 + FWD_EPI_WARPS) {
@@ -227,7 +228,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
       const uint32_t st2 = smem_u32(stage2 + a * STG_BYTES + srow * SLAB_ROW_BYTES);
       mbar_wait(&cs->tfull[a], aph);
       tc_fence_after();
-      if ((warp == 2 || warp == 10) && lane == 0) trace(it, 3);
+      if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 3);
 #pragma unroll 1
       for (int p = 0; p < 2; ++p) {
         const int cg = half * 2 + p;
@@ -244,7 +245,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&cs->tempty[a]);
-          if ((warp == 2 || warp == 10) && lane == 0) trace(it, 6);
+          if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 6);
         }
         const uint32_t xw0 = smem_u32(cs->xch[a][0][q][cg]);   // my dx = -1 block, needed by row + 1 -> written by lane 31
         const uint32_t xw2 = smem_u32(cs->xch[a][1][q][cg]);   // my dx = +1 block, needed by row - 1 -> written by lane 0
@@ -322,7 +323,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
         }
       }
       fence_proxy_async_smem();                 // my generic-proxy writes -> visible to the bulk store
-      if ((warp == 2 || warp == 10) && lane == 0) trace(it, 4);
+      if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 4);
       mbar_arrive(&cs->outready[a]);
       data_row += OUT_ROWS * tile_stride;
       q_img += step_mod;
@@ -361,7 +362,7 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
           mbar_wait(&cs->outready[pa], (pit >> 1) & 1);
           bulk_s2g(out + static_cast<size_t>(Rf) * SLAB_ROW_BYTES, stage1 + pa * STG_BYTES + (Rf & 7) * SLAB_ROW_BYTES, OUT_BYTES);
           bulk_commit();
-          trace(pit, 5);
+          trace_at(trace_buf, pit, 5);
         }
         if (!live) break;
         prev_tile = tile;
@@ -374,6 +375,274 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
   if (warp == 0) {
     __syncwarp();
     tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---- per-tap implicit GEMM (variant 1) ---------------------------------------------------------------------------
+// Nine row-shifted views x 4 K steps = 36 MMAs of N = 64 accumulate into ONE 64-column accumulator, so the epilogue is
+// a plain row-wise map (no horizontal shuffles, no boundary exchange, no overlapping tiles): a third of the TMEM loads
+// and ~40 % of the instructions of the dx-fused epilogue.  The MMAs themselves are shared-memory-port bound (6 KB per
+// 128x64x16 instruction = 49 cycles, 65 % of the tensor peak), so this variant wins only while the fused kernel is
+// bound by its epilogue; both are kept and selected per process (bruno_debug_conv_variant) so they can be A/B timed.
+// Four 64-column TMEM accumulators decouple the issuer from the two epilogue groups.
+constexpr int TAP_ACC = 4;
+constexpr int TAP_MAX_STAGES = 4;          // slab ring depth: as many as fit next to the staging buffers (host decides)
+
+struct TapSmem {
+  uint64_t full[TAP_MAX_STAGES], empty[TAP_MAX_STAGES], tfull[TAP_ACC], tempty[TAP_ACC], wbar;
+  uint64_t auxfull[2], outready[2];
+  uint32_t tmem_base;
+  alignas(16) float bias[64];
+};
+
+template <int MODE, int NS>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
+                   const uint8_t* __restrict__ aux1, const uint8_t* __restrict__ aux2, uint8_t* __restrict__ out,
+                   SlabGeom g, int ntiles, int bias_img_stride, long long* trace_buf) {
+  constexpr int nstage = NS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int slab_rows = TILE_M + 2 * g.HALO + 8;
+  const uint32_t slab_bytes = static_cast<uint32_t>(slab_rows) * SLAB_ROW_BYTES;
+  uint8_t* wsm = smem;
+  uint8_t* slabs = smem + W_BYTES;
+  uint8_t* stage1 = slabs + nstage * slab_bytes;                       // [2][TILE_BYTES] aux1 in / output out (in place)
+  uint8_t* stage2 = stage1 + 2 * TILE_BYTES;                           // [2][TILE_BYTES] aux2 (MODE_ADD_MUL only)
+  TapSmem* cs = reinterpret_cast<TapSmem*>(stage2 + (mode_has_aux2(MODE) ? 2 * TILE_BYTES : 0));
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
+  constexpr bool HAS_BIAS = MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TAP_MAX_STAGES; ++s) {
+      mbar_init(&cs->full[s], 1);
+      mbar_init(&cs->empty[s], 1);
+    }
+    for (int a = 0; a < TAP_ACC; ++a) {
+      mbar_init(&cs->tfull[a], 1);
+      mbar_init(&cs->tempty[a], FWD_EPI_WARPS / 2);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&cs->auxfull[a], 1);
+      mbar_init(&cs->outready[a], FWD_EPI_WARPS * 16);
+    }
+    mbar_init(&cs->wbar, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) cs->bias[threadIdx.x - 64] = HAS_BIAS ? bias[threadIdx.x - 64] : 0.f;
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(&cs->tmem_base, 64 * TAP_ACC);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = cs->tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // tile t = data rows [128 t, 128 t + 128) = buffer rows from Rf = HALO + 128 t (a multiple of 8); the slab load starts
+  // at LS = floor8(Rf - P - 1) and covers every tap's view.
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
+      bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % nstage;
+        const uint32_t ph = (it / nstage) & 1;
+        const int LS = (g.HALO + TILE_M * tile - g.P - 1) & ~7;
+        mbar_wait(&cs->empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&cs->full[s], slab_bytes);
+        bulk_g2s(slabs + s * slab_bytes, in + static_cast<size_t>(LS) * SLAB_ROW_BYTES, slab_bytes, &cs->full[s]);
+        trace_at(trace_buf, it, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer.  The whole warp runs the loop (uniform control flow: descriptors live in uniform registers and the
+    // issue path is two or three instructions per MMA); one elected lane executes tcgen05.mma / commit.
+    // The tile loop is unrolled over lcm(NS, TAP_ACC) tiles so that the slab stage and the accumulator of every unrolled
+    // body are compile-time: no descriptor or TMEM address is recomputed between tiles (rewriting a uniform register that
+    // queued MMAs still read stalls the issuer until the tensor pipe has drained -- a bubble per tile). =====
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr int U = (NS == 3) ? 12 : 4;
+    mbar_wait(&cs->wbar, 0);
+    const uint64_t bdesc0 = umma_desc_sw128(smem_u32(wsm), 16, 1024);
+    uint64_t adesc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) adesc[s] = umma_desc_sw128(smem_u32(slabs + s * slab_bytes), 16, 1024);
+    // Rf - LS is the same for every tile (HALO and 128 t are multiples of 8)
+    const uint32_t a_base = static_cast<uint32_t>(g.HALO - ((g.HALO - g.P - 1) & ~7)) * 8u;
+    const uint32_t p8 = static_cast<uint32_t>(g.P) * 8u;
+    // The barrier waits of tile it+1 (each a ~100-cycle round trip even when the barrier completed long ago) are taken
+    // by the elected lane BETWEEN the last taps of tile it, while the tensor pipe still holds queued MMAs.
+    int tile = blockIdx.x;
+    bool more = tile < ntiles;
+    const bool leader = elect_one();
+    if (more && leader) {
+      mbar_wait(&cs->tempty[0], 1u);
+      mbar_wait(&cs->full[0], 0u);
+      tc_fence_after();
+    }
+    for (uint32_t r = 0; more; ++r) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (more) {
+          const int s = u % NS, a = u % TAP_ACC;
+          const int sn = (u + 1) % NS, an = (u + 1) % TAP_ACC;
+          const int it = static_cast<int>(r) * U + u;
+          tile += gridDim.x;
+          more = tile < ntiles;
+          if (leader) {
+            trace_at(trace_buf, it, 1);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              const uint32_t a_off = a_base + static_cast<uint32_t>(dy) * p8 + static_cast<uint32_t>(dx * 8);
+              if (more) {
+                if (tap == 5) mbar_wait(&cs->tempty[an], ((r * (U / TAP_ACC) + (u + 1) / TAP_ACC) & 1u) ^ 1u);
+                if (tap == 6) mbar_wait(&cs->full[sn], (r * (U / NS) + (u + 1) / NS) & 1u);
+                if (tap == 7) tc_fence_after();
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(tmem + a * 64, adesc[s] + (a_off + 2u * k),
+                          bdesc0 + static_cast<uint32_t>((tap * W_TAP_BYTES + k * 32) >> 4), idesc, (tap | k) != 0);
+              }
+            }
+            umma_commit(&cs->empty[s]);
+            umma_commit(&cs->tfull[a]);
+            trace_at(trace_buf, it, 2);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 2 + FWD_EPI_WARPS) {
+    // two groups of 8 warps alternate tiles (group = staging buffer); warp -> TMEM lane quarter and 32-channel half
+    const int grp = (warp - 2) >> 3;
+    const int q = warp & 3;
+    const int half = ((warp - 2) >> 2) & 1;
+    const int row = q * 32 + lane;
+    const int R7 = lane & 7;                    // HALO and the tile origin are multiples of 8
+    const int tile_stride = 2 * gridDim.x;
+    const int step_mod = (TILE_M * tile_stride) % g.IMG;
+    const int step_div = (TILE_M * tile_stride) / g.IMG;
+    int tile = blockIdx.x + grp * gridDim.x;
+    int data_row = TILE_M * tile + row;
+    int q_img = data_row % g.IMG;
+    int n_img = data_row / g.IMG;
+    const float inv_p = 1.0f / static_cast<float>(g.P);
+    const uint32_t st1 = smem_u32(stage1 + grp * TILE_BYTES + row * SLAB_ROW_BYTES);
+    const uint32_t st2 = smem_u32(stage2 + grp * TILE_BYTES + row * SLAB_ROW_BYTES);
+    int it = grp;
+    for (; tile < ntiles; tile += tile_stride, it += 2) {
+      const int a = it % TAP_ACC;
+      const int yy = static_cast<int>((static_cast<float>(q_img) + 0.5f) * inv_p);
+      const int xx = q_img - yy * g.P;
+      const bool valid = data_row < g.data_rows && yy >= 1 && xx >= 1;
+      mbar_wait(&cs->tfull[a], (it / TAP_ACC) & 1);
+      tc_fence_after();
+      if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 3);
+      const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 64 + half * 32;
+      uint32_t acc[4][8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld8(tbase + c * 8, acc[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cs->tempty[a]);
+      if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 6);
+      mbar_wait(&cs->auxfull[grp], (it >> 1) & 1);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = half * 4 + jj;
+        const int pos = (j ^ R7) << 4;
+        float o[8], bj[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(acc[jj][e]);
+        if (HAS_BIAS) {
+          const float* bsrc = bias_img_stride ? bias + static_cast<size_t>(valid ? n_img : 0) * bias_img_stride + j * 8
+                                              : &cs->bias[j * 8];
+          const float4 b0 = *reinterpret_cast<const float4*>(bsrc);
+          const float4 b1 = *reinterpret_cast<const float4*>(bsrc + 4);
+          bj[0] = b0.x; bj[1] = b0.y; bj[2] = b0.z; bj[3] = b0.w; bj[4] = b1.x; bj[5] = b1.y; bj[6] = b1.z; bj[7] = b1.w;
+        }
+        if (MODE == MODE_ELU || MODE == MODE_LINEAR) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float t = o[e] + bj[e];
+            o[e] = MODE == MODE_ELU ? elu_fast(t) : t;
+          }
+        } else if (MODE == MODE_RES_ELU) {
+          float sk[8];
+          unpack8(lds_u4(st1 + pos), sk);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = elu_fast(o[e] + bj[e] + sk[e]);
+        } else if (MODE == MODE_MUL) {
+          float sk[8];
+          unpack8(lds_u4(st1 + pos), sk);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(sk[e]);
+        } else {
+          float sk[8], t[8];
+          unpack8(lds_u4(st1 + pos), sk);
+          unpack8(lds_u4(st2 + pos), t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
+        }
+        sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
+      }
+      fence_proxy_async_smem();
+      if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 4);
+      mbar_arrive(&cs->outready[grp]);
+      data_row += TILE_M * tile_stride;
+      q_img += step_mod;
+      n_img += step_div;
+      if (q_img >= g.IMG) {
+        q_img -= g.IMG;
+        ++n_img;
+      }
+    }
+  } else {
+    if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      int it = 0;
+      int prev_tile = -1;
+      for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
+        const bool live = tile < ntiles;
+        if (live) {
+          const int b = it & 1;
+          bulk_wait_read<0>();                  // the store of tile it-2 has finished reading this staging buffer
+          if (mode_has_aux1(MODE)) {
+            const size_t off = static_cast<size_t>(g.HALO + TILE_M * tile) * SLAB_ROW_BYTES;
+            mbar_arrive_expect_tx(&cs->auxfull[b], mode_has_aux2(MODE) ? 2 * TILE_BYTES : TILE_BYTES);
+            bulk_g2s(stage1 + b * TILE_BYTES, aux1 + off, TILE_BYTES, &cs->auxfull[b]);
+            if (mode_has_aux2(MODE)) bulk_g2s(stage2 + b * TILE_BYTES, aux2 + off, TILE_BYTES, &cs->auxfull[b]);
+          } else {
+            mbar_arrive(&cs->auxfull[b]);
+          }
+        }
+        if (prev_tile >= 0) {
+          const int pit = it - 1;
+          const int pa = pit & 1;
+          mbar_wait(&cs->outready[pa], (pit >> 1) & 1);
+          bulk_s2g(out + static_cast<size_t>(g.HALO + TILE_M * prev_tile) * SLAB_ROW_BYTES, stage1 + pa * TILE_BYTES, TILE_BYTES);
+          bulk_commit();
+          trace_at(trace_buf, pit, 5);
+        }
+        if (!live) break;
+        prev_tile = tile;
+      }
+      bulk_wait_all<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem, 64 * TAP_ACC);
   }
 }
 
@@ -625,9 +894,59 @@ static int num_sms() {
   return cached[dev];
 }
 
+static int g_conv_variant = 1;   // 0: dx-fused N=192 kernel, 1: per-tap N=64 kernel
+
+template <int MODE, int NS>
+static int launch_conv_tap_ns(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
+                              const void* a2, void* out, const SlabGeom& g, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv3x3_tap_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
+  const int ntiles = g.NT;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  ProfSpan span(BRUNO_PROF_CONV, st);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(FWD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, conv3x3_tap_kernel<MODE, NS>, static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias,
+                     static_cast<const uint8_t*>(a1), static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g, ntiles,
+                     bias_img_stride, g_conv_trace_host);
+  return check_launch("conv3x3_tap_kernel");
+}
+
+static size_t tap_fixed_smem(int mode) { return 1024 + W_BYTES + (mode_has_aux2(mode) ? 4 : 2) * TILE_BYTES + sizeof(TapSmem) + 64; }
+static int tap_stages(const SlabGeom& g, int mode) {
+  const size_t slab = static_cast<size_t>(TILE_M + 2 * g.HALO + 8) * SLAB_ROW_BYTES;
+  const size_t fixed = tap_fixed_smem(mode);
+  if (fixed + 2 * slab > 227 * 1024) return 0;
+  const int n = static_cast<int>((227 * 1024 - fixed) / slab);
+  return n > TAP_MAX_STAGES ? TAP_MAX_STAGES : n;
+}
+
+template <int MODE>
+static int launch_conv_tap(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
+                           const void* a2, void* out, const SlabGeom& g, cudaStream_t st) {
+  const int ns = tap_stages(g, MODE);
+  BRUNO_REQUIRE(ns >= 2, "bruno_conv3x3: W=%d too wide for the shared-memory slab ring", g.W);
+  const size_t smem = tap_fixed_smem(MODE) + static_cast<size_t>(ns) * (TILE_M + 2 * g.HALO + 8) * SLAB_ROW_BYTES;
+  if (ns == 4) return launch_conv_tap_ns<MODE, 4>(in, w, bias, bias_img_stride, a1, a2, out, g, smem, st);
+  if (ns == 3) return launch_conv_tap_ns<MODE, 3>(in, w, bias, bias_img_stride, a1, a2, out, g, smem, st);
+  return launch_conv_tap_ns<MODE, 2>(in, w, bias, bias_img_stride, a1, a2, out, g, smem, st);
+}
+
 template <int MODE>
 static int launch_conv(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
                        const void* a2, void* out, const SlabGeom& g, cudaStream_t st) {
+  if (g_conv_variant == 1) return launch_conv_tap<MODE>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
   const size_t smem = conv_smem_bytes(g, MODE);
   static bool configured = false;
   if (!configured) {
@@ -649,7 +968,7 @@ static int launch_conv(const void* in, const void* w, const float* bias, int bia
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, conv3x3_kernel<MODE>, static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias,
                      static_cast<const uint8_t*>(a1), static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g, ntiles,
-                     bias_img_stride);
+                     bias_img_stride, g_conv_trace_host);
   return check_launch("conv3x3_kernel");
 }
 
@@ -667,11 +986,14 @@ size_t bruno_slab_bytes(int N, int H, int W) {
 size_t bruno_conv_wpack_bytes(void) { return W_BYTES; }
 
 int bruno_debug_conv_trace(long long* device_buffer) {
-  cudaError_t e = cudaMemcpyToSymbol(g_conv_trace, &device_buffer, sizeof(device_buffer));
-  if (e != cudaSuccess) {
-    set_last_error("bruno_debug_conv_trace: %s", cudaGetErrorString(e));
-    return BRUNO_ECUDA;
-  }
+  g_conv_trace_host = device_buffer;
+  return BRUNO_OK;
+}
+
+int bruno_debug_conv_variant(int variant) {
+  if (variant < 0) return g_conv_variant;
+  BRUNO_REQUIRE(variant == 0 || variant == 1, "bruno_debug_conv_variant: 0 (dx-fused) or 1 (per-tap)");
+  g_conv_variant = variant;
   return BRUNO_OK;
 }
 
@@ -696,7 +1018,7 @@ int bruno_conv3x3(int mode, const void* in_slab, const void* wpack, const float*
   BRUNO_REQUIRE(aligned16(in_slab) && aligned16(wpack) && aligned16(out_slab), "bruno_conv3x3: 16-byte alignment required");
   BRUNO_REQUIRE(in_slab != out_slab, "bruno_conv3x3: in-place convolution is not possible");
   const SlabGeom g = slab_geom(N, H, W);
-  BRUNO_REQUIRE(conv_smem_bytes(g) <= 227 * 1024, "bruno_conv3x3: W=%d too wide for the shared-memory slab", W);
+  BRUNO_REQUIRE(g_conv_variant == 1 || conv_smem_bytes(g) <= 227 * 1024, "bruno_conv3x3: W=%d too wide for the shared-memory slab", W);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (mode) {
     case MODE_ELU:

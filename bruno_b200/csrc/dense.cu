@@ -272,12 +272,18 @@ sgemm_sk_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const
     __threadfence();
 #pragma unroll
     for (int i = 0; i < MI; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    for (int z = 0; z < S; ++z) {
+    constexpr int ZU = MI == 4 ? 4 : 2;   // partials fetched per round trip (loads first, then the ordered adds)
+    for (int z = 0; z < S; z += ZU) {
+      float4 v[ZU][MI];
 #pragma unroll
-      for (int i = 0; i < MI; ++i) {
-        const float4 v = __ldcg(wt + static_cast<size_t>(z) * (MI * 256) + i * 256 + tid);
-        acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
-      }
+      for (int u = 0; u < ZU; ++u)
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+          v[u][i] = z + u < S ? __ldcg(wt + static_cast<size_t>(z + u) * (MI * 256) + i * 256 + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < ZU; ++u)
+#pragma unroll
+        for (int i = 0; i < MI; ++i) { acc[i][0] += v[u][i].x; acc[i][1] += v[u][i].y; acc[i][2] += v[u][i].z; acc[i][3] += v[u][i].w; }
     }
     if (tid == 0) tickets[tile] = 0u;
   }

@@ -110,7 +110,8 @@ def test_forward_and_backward_match_oracle(name, B, T):
         name, e_emu, worst[0], worst[1]))
     assert e_emu <= TOL_LL_EMU
     # an2 with B=1, T=2 on uniform-noise 'bytes' is the extreme regime (|z| ~ 3e4, log p ~ -2e6): gradients chaotic
-    assert worst[0] <= (0.5 if name.startswith('an2') else TOL_GRAD_EMU), worst
+    # (kernel and emulating oracle are two realisations of that chaos: same bound as against the exact oracle)
+    assert worst[0] <= (TOL_GRAD[name] if name.startswith('an2') else TOL_GRAD_EMU), worst
 
 
 @pytest.mark.parametrize('name', ['en2_noconv_mnist_tp', 'bn2_omniglot_tp', 'an2_cifar_tp'])

@@ -9,12 +9,14 @@ _lib.call('bruno_conv_wn_pack', V.cuda(), torch.ones(1, 64, device='cuda'), wf, 
 sl = slab.alloc_slabs(3, N, H, W, 'cuda')
 sl[0].random_(0, 255)   # garbage activations are fine for timing
 bias = torch.zeros(64, device='cuda')
-for mode in (0, 1):
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+_lib.load().bruno_debug_conv_variant(variant)
+for mode in (0, 3):
     for _ in range(3):
-        _lib.call('bruno_conv3x3', mode, sl[0], wf[0], bias, 0, sl[2], None, sl[1], N, H, W)
+        _lib.call('bruno_conv3x3', mode, sl[0], wf[0], bias if mode < 2 else None, 0, sl[2] if mode else None, sl[2] if mode == 3 else None, sl[1], N, H, W)
     tr = torch.zeros(64 * 16, dtype=torch.int64, device='cuda')
     _lib.load().bruno_debug_conv_trace(tr.data_ptr())
-    _lib.call('bruno_conv3x3', mode, sl[0], wf[0], bias, 0, sl[2], None, sl[1], N, H, W)
+    _lib.call('bruno_conv3x3', mode, sl[0], wf[0], bias if mode < 2 else None, 0, sl[2] if mode else None, sl[2] if mode == 3 else None, sl[1], N, H, W)
     torch.cuda.synchronize()
     _lib.load().bruno_debug_conv_trace(None)
     t = tr.view(64, 16).cpu()
