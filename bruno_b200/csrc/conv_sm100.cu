@@ -682,7 +682,7 @@ conv3x3_wgrad_kernel(const uint8_t* __restrict__ x_base, const uint8_t* __restri
   uint8_t* stages = smem;
   uint8_t* ones = smem + WG_STAGES * stage_bytes;         // 1024-aligned, AFTER the stages (positive LBO)
   WgradSmem* ws = reinterpret_cast<WgradSmem*>(ones + ONES_BYTES);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
 
   // constant operand: logical channel 0 of every row = 1.0, everything else 0 (swizzled like a slab row)
   for (int i = threadIdx.x; i < ONES_BYTES / 16; i += blockDim.x) {
@@ -728,40 +728,63 @@ conv3x3_wgrad_kernel(const uint8_t* __restrict__ x_base, const uint8_t* __restri
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
-      const uint32_t ones_addr = smem_u32(ones);
-      int it = 0;
-      for (int tile = t0; tile < t1; ++tile, ++it) {
-        const int s = it % WG_STAGES;
-        const uint32_t ph = (it / WG_STAGES) & 1;
-        mbar_wait(&ws->full[s], ph);
-        tc_fence_after();
-        const uint32_t xs_addr = smem_u32(stages + s * stage_bytes);
-        const uint32_t gs_addr = xs_addr + xs_bytes;
-#pragma unroll 1
-        for (int ks = 0; ks < TILE_M / 16; ++ks) {
-          const uint64_t bdesc = umma_desc_sw128(gs_addr + ks * 16 * SLAB_ROW_BYTES, 16, 1024);
+    // MMA issuer: uniform control flow for the whole warp, one elected lane issues.  Stage, K step and tap pair are all
+    // compile-time in the unrolled body and every descriptor is (loop-invariant base) + constant: the issue path is a
+    // couple of uniform-datapath instructions per MMA.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+    const uint32_t ones_lo = (smem_u32(ones) & 0x3FFFFu) >> 4;
+    uint32_t a_lo[WG_STAGES][5], b_lo[WG_STAGES];   // low descriptor words at K step 0: address | LBO << 16
 #pragma unroll
-          for (int c = 0; c < 5; ++c) {
-            const int tapA = 2 * c;
-            const int offA = g.HALO + (tapA / 3 - 1) * g.P + (tapA % 3 - 1) + ks * 16;
-            const uint32_t a_addr = xs_addr + offA * SLAB_ROW_BYTES;
-            uint32_t lbo;
-            if (c < 4) {
-              const int tapB = tapA + 1;
-              const int offB = g.HALO + (tapB / 3 - 1) * g.P + (tapB % 3 - 1) + ks * 16;
-              lbo = static_cast<uint32_t>(offB - offA) * SLAB_ROW_BYTES;
-            } else {
-              lbo = ones_addr - a_addr;
-            }
-            umma_bf16(tmem + c * 64, umma_desc_sw128(a_addr, lbo, 1024), bdesc, idesc, (it | ks) != 0);
-          }
-        }
-        umma_commit(&ws->empty[s]);
+    for (int s = 0; s < WG_STAGES; ++s) {
+      const uint32_t xs_lo = (smem_u32(stages + s * stage_bytes) & 0x3FFFFu) >> 4;
+      b_lo[s] = (xs_lo + (xs_bytes >> 4)) | (1u << 16);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const int tapA = 2 * c, tapB = 2 * c + 1;
+        const int offA = g.HALO + (tapA / 3 - 1) * g.P + (tapA % 3 - 1);
+        const int offB = g.HALO + (tapB / 3 - 1) * g.P + (tapB % 3 - 1);
+        const uint32_t lo = xs_lo + static_cast<uint32_t>(offA) * 8u;
+        // LBO (16-byte units): distance from the tap A atom to the tap B atom; for the ninth tap, to the "ones" atom
+        // (that distance shrinks by 128 units per K step, see below)
+        const uint32_t lbo = c < 4 ? static_cast<uint32_t>(offB - offA) * 8u : ones_lo - lo;
+        a_lo[s][c] = lo | (lbo << 16);
       }
-      umma_commit(&ws->done);
     }
+    const bool leader = elect_one();
+    int tile = t0;
+    bool more = tile < t1;
+    for (uint32_t r = 0; more; ++r) {
+#pragma unroll
+      for (int s = 0; s < WG_STAGES; ++s) {
+        if (more) {
+          if (leader) {
+            mbar_wait(&ws->full[s], r & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < TILE_M / 16; ++ks) {
+              const uint64_t bdesc = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo[s] + ks * 128u);
+#pragma unroll
+              for (int c = 0; c < 5; ++c) {
+                // address += 128 units per K step; the ones atom stays put, so its LBO shrinks by the same amount
+                const uint32_t lo = a_lo[s][c] + (c < 4 ? ks * 128u : ks * 128u - ((ks * 128u) << 16));
+                umma_bf16(tmem + c * 64, (static_cast<uint64_t>(DESC_HI) << 32) | lo, bdesc, idesc, (r | s | ks) != 0);
+              }
+            }
+            umma_commit(&ws->empty[s]);
+          }
+          ++tile;
+          more = tile < t1;
+        }
+      }
+    }
+    // the issuer itself waits for the last commit: no asynchronous mbarrier arrive may still be in flight when the CTA
+    // exits (it would land in the shared memory of whichever CTA gets this SM next)
+    if (leader && t1 > t0) {
+      umma_commit(&ws->done);
+      mbar_wait(&ws->done, 0);
+    }
+    __syncwarp();
   } else if (t1 > t0) {
     const int q = warp & 3;
     const int m = q * 32 + lane;  // accumulator row: [0,64) = tap A channels, [64,128) = tap B channels

@@ -95,6 +95,28 @@ def test_conv3x3_wgrad(N, H, W):
     assert (dW.double().cpu() - 2 * ref).abs().max().item() <= 4e-4 * scale + 2e-4
 
 
+@pytest.mark.parametrize('L,N,H,W', [(4, 6, 28, 28), (16, 6, 14, 14)])
+def test_conv3x3_wgrad_batched(L, N, H, W):
+    """One launch for L stacked layers (the grid is split among them) == L single-layer launches."""
+    from bruno_b200 import _lib, slab
+    g = torch.Generator().manual_seed(11 + L)
+    xs = slab.alloc_slabs(L, N, H, W, 'cuda')
+    gs = slab.alloc_slabs(L, N, H, W, 'cuda')
+    for l in range(L):
+        xs[l].copy_(slab.nhwc_to_slab((torch.randn(N, H, W, 64, generator=g)).cuda()))
+        gs[l].copy_(slab.nhwc_to_slab((torch.randn(N, H, W, 64, generator=g) * 0.1).cuda()))
+    dW = torch.zeros(L, 3, 3, 64, 64, device='cuda')
+    db = torch.zeros(L, 64, device='cuda')
+    _lib.call('bruno_conv3x3_wgrad_batched', xs, gs, dW, db, L, N, H, W)
+    for l in range(L):
+        dW1 = torch.zeros(3, 3, 64, 64, device='cuda')
+        db1 = torch.zeros(64, device='cuda')
+        _lib.call('bruno_conv3x3_wgrad', xs[l], gs[l], dW1, db1, N, H, W)
+        scale = dW1.abs().max().item()
+        assert (dW[l] - dW1).abs().max().item() <= 1e-5 * scale + 1e-6, l
+        assert (db[l] - db1).abs().max().item() <= 1e-5 * db1.abs().max().item() + 1e-6, l
+
+
 def test_wn_backward():
     from bruno_b200 import _lib
     g = torch.Generator().manual_seed(3)
