@@ -313,6 +313,8 @@ sgemm_sk_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const
 // split-K workspace (grow-never, allocated on first use outside stream capture)
 constexpr size_t SK_WS_FLOATS = size_t(4) << 20;   // 16 MB
 constexpr int SK_MAX_TILES = 4096;
+constexpr size_t CR_WS_FLOATS = size_t(64) << 10;  // column-reduction partials, after the split-K region
+constexpr int CR_MAX_GROUPS = 1024;                // column-reduction tickets, after the split-K tickets
 static float* g_sk_ws = nullptr;
 static unsigned* g_sk_tickets = nullptr;
 static int g_sk_sms = 0;
@@ -326,8 +328,9 @@ static bool sk_workspace(cudaStream_t st) {
   cudaDeviceGetAttribute(&g_sk_sms, cudaDevAttrMultiProcessorCount, dev);
   float* w = nullptr;
   unsigned* t = nullptr;
-  if (cudaMalloc(&w, SK_WS_FLOATS * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return false; }
-  if (cudaMalloc(&t, SK_MAX_TILES * sizeof(unsigned)) != cudaSuccess || cudaMemset(t, 0, SK_MAX_TILES * sizeof(unsigned)) != cudaSuccess) {
+  if (cudaMalloc(&w, (SK_WS_FLOATS + CR_WS_FLOATS) * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cudaMalloc(&t, (SK_MAX_TILES + CR_MAX_GROUPS) * sizeof(unsigned)) != cudaSuccess ||
+      cudaMemset(t, 0, (SK_MAX_TILES + CR_MAX_GROUPS) * sizeof(unsigned)) != cudaSuccess) {
     cudaGetLastError();
     cudaFree(w);
     return false;
@@ -494,24 +497,77 @@ __global__ void elu_bwd_kernel(const float* __restrict__ pre, const float* __res
 }
 
 // out1[j] = sum_m A[m,j];  out2[j] = sum_m A[m,j] * Bm[m,j] (if Bm)
+// grid (N/32, MS): block (x, y) reduces rows [y M/MS, (y+1) M/MS) of 32 columns with four loads in flight per thread;
+// with MS > 1 the partials go to the workspace and the last block of a column group (ticket) adds them in y order.
+constexpr int CR_MAX_SPLIT = 16;
 __global__ void __launch_bounds__(256)
 col_reduce_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ out1,
-                  float* __restrict__ out2, int M, int N) {
+                  float* __restrict__ out2, int M, int N, float* __restrict__ part, unsigned* __restrict__ tickets) {
   __shared__ float sh[8][33];
-  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
-  float a = 0.f, b = 0.f;
-  if (j < N)
-    for (int m = threadIdx.x >> 5; m < M; m += 8) {
-      const float v = A[static_cast<size_t>(m) * N + j];
-      a += v;
-      if (Bm) b = fmaf(v, Bm[static_cast<size_t>(m) * N + j], b);
+  __shared__ int s_last;
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + c;
+  const int MS = gridDim.y;
+  const int rows = (M + MS - 1) / MS;
+  const int m_begin = blockIdx.y * rows, m_end = min(M, m_begin + rows);
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (j < N) {
+    for (int m = m_begin + rg; m < m_end; m += 32) {
+      float v[4], w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int mm = m + 8 * u;
+        v[u] = mm < m_end ? A[static_cast<size_t>(mm) * N + j] : 0.f;
+        w[u] = (Bm && mm < m_end) ? Bm[static_cast<size_t>(mm) * N + j] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] += v[u];
+        b[u] = fmaf(v[u], w[u], b[u]);
+      }
     }
-  a = col_block_reduce(a, sh);
-  if (Bm) b = col_block_reduce(b, sh);
-  if (j < N && threadIdx.x < 32) {
-    out1[j] = a;
-    if (out2) out2[j] = b;
   }
+  float sa = col_block_reduce((a[0] + a[1]) + (a[2] + a[3]), sh);
+  float sb = Bm ? col_block_reduce((b[0] + b[1]) + (b[2] + b[3]), sh) : 0.f;
+  if (MS > 1) {
+    // partial layout [column group][y][2][32]
+    float* mine = part + (static_cast<size_t>(blockIdx.x) * MS + blockIdx.y) * 64;
+    if (threadIdx.x < 32) {
+      __stcg(mine + c, sa);
+      __stcg(mine + 32 + c, sb);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(tickets + blockIdx.x, 1u) == static_cast<unsigned>(MS - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+      sa = 0.f;
+      sb = 0.f;
+      const float* base = part + static_cast<size_t>(blockIdx.x) * MS * 64;
+      for (int y = 0; y < MS; ++y) {
+        sa += __ldcg(base + y * 64 + c);
+        sb += __ldcg(base + y * 64 + 32 + c);
+      }
+      if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
+    }
+  }
+  if (j < N && threadIdx.x < 32) {
+    out1[j] = sa;
+    if (out2) out2[j] = sb;
+  }
+}
+
+static void col_reduce(const float* A, const float* Bm, float* out1, float* out2, int M, int N, cudaStream_t st) {
+  const int groups = ceil_div(N, 32);
+  int ms = 1;
+  if (groups <= CR_MAX_GROUPS && sk_workspace(st)) {
+    ms = max(1, min(CR_MAX_SPLIT, min(M / 32, (2 * g_sk_sms) / groups)));
+    while (ms > 1 && static_cast<size_t>(groups) * ms * 64 > CR_WS_FLOATS) --ms;
+  }
+  col_reduce_kernel<<<dim3(groups, ms), 256, 0, st>>>(A, Bm, out1, out2, M, N, g_sk_ws ? g_sk_ws + SK_WS_FLOATS : nullptr,
+                                                      g_sk_tickets ? g_sk_tickets + SK_MAX_TILES : nullptr);
 }
 
 // weight-norm backward for dense_wn.  dVraw = x^T dpre;  r1 = colsum(dpre * pre);  db = colsum(dpre).
@@ -634,13 +690,13 @@ int bruno_coupling_dense_bwd(const float* x, const float* dy, const float* dld, 
   // heads
   if ((rc = gemm(true, false, U, D, N, w.h2, U, ds_pre, D, dKs, D, plain, st))) return rc;
   if ((rc = gemm(true, false, U, D, N, w.h2, U, dt_pre, D, dKt, D, plain, st))) return rc;
-  col_reduce_kernel<<<ceil_div(D, 32), 256, 0, st>>>(ds_pre, nullptr, dbs, nullptr, N, D);
-  col_reduce_kernel<<<ceil_div(D, 32), 256, 0, st>>>(dt_pre, nullptr, dbt, nullptr, N, D);
+  col_reduce(ds_pre, nullptr, dbs, nullptr, N, D, st);
+  col_reduce(dt_pre, nullptr, dbt, nullptr, N, D, st);
   if ((rc = gemm(false, true, N, U, D, ds_pre, D, Ks, D, dh, U, plain, st))) return rc;
   if ((rc = gemm(false, true, N, U, D, dt_pre, D, Kt, D, dh, U, accum, st))) return rc;
   // d2
   elu_bwd_kernel<<<nblk(NU), 256, 0, st>>>(w.pre2, dh, dpre, NU);
-  col_reduce_kernel<<<ceil_div(U, 32), 256, 0, st>>>(dpre, w.pre2, db2, r1, N, U);
+  col_reduce(dpre, w.pre2, db2, r1, N, U, st);
   if ((rc = gemm(true, false, U, U, N, w.h1, U, dpre, U, dV2, U, plain, st))) return rc;
   dense_wn_bwd_kernel<<<nblk(static_cast<size_t>(U) * U), 256, 0, st>>>(V2, g2, b2, w.sc2, w.in2, r1, db2, dV2, dg2, U, U);
   {
@@ -650,7 +706,7 @@ int bruno_coupling_dense_bwd(const float* x, const float* dy, const float* dld, 
   }
   // d1
   elu_bwd_kernel<<<nblk(NU), 256, 0, st>>>(w.pre1, dh, dpre, NU);
-  col_reduce_kernel<<<ceil_div(U, 32), 256, 0, st>>>(dpre, w.pre1, db1, r1, N, U);
+  col_reduce(dpre, w.pre1, db1, r1, N, U, st);
   if ((rc = gemm(true, false, D, U, N, w.xm, D, dpre, U, dV1, U, plain, st))) return rc;
   dense_wn_bwd_kernel<<<nblk(static_cast<size_t>(D) * U), 256, 0, st>>>(V1, g1, b1, w.sc1, w.in1, r1, db1, dV1, dg1, D, U);
   {

@@ -83,6 +83,32 @@ class _SlabPool(object):
 
 SLABS = _SlabPool()
 
+# Direct gradient sinks.  After BrunoModel.flatten_parameters every variable owns a preset .grad view into the flat
+# gradient buffer; letting autograd accumulate into it costs one elementwise add launch per variable per step (166 for
+# bn2_omniglot).  With direct sinks on, the backward kernels WRITE the variable gradients straight into those views and
+# hand autograd None.  Valid only under the trainer's contract: the buffer is zeroed every step and every variable is
+# used once per backward (no micro-batch accumulation) -- the trainer switches it on, everything else leaves it off.
+_DIRECT_GRADS = [False]
+
+
+def direct_grads(on):
+    _DIRECT_GRADS[0] = bool(on)
+
+
+def _grad_sinks(layer, names):
+    """-> (buffers the kernel writes, values returned to autograd) for the variables `names` of `layer`."""
+    bufs, rets = [], []
+    for n in names:
+        p = getattr(layer, n)
+        if _DIRECT_GRADS[0] and p.grad is not None and p.grad.is_contiguous() and p.grad.shape == p.shape:
+            bufs.append(p.grad)
+            rets.append(None)
+        else:
+            t = torch.empty_like(p)
+            bufs.append(t)
+            rets.append(t)
+    return bufs, rets
+
 
 class Layer(object):                                                        # nvp:14-19
     def forward_and_jacobian(self, x, z, sum_log_det_jacobian):
@@ -182,13 +208,11 @@ class _ConvCouplingFn(torch.autograd.Function):
         dld = dld.contiguous()
         gsl = SLABS.get('grad', 2 * R + 1, N, H, W, x.device)
         dx = torch.empty_like(x)
-        dV1, dg1, db1 = torch.empty_like(V1), torch.empty_like(g1), torch.empty_like(g1)
-        dVr, dgr, dbr = torch.empty_like(Vr), torch.empty_like(gr), torch.empty_like(gr)
-        dKs, dbs, dKt, dbt = torch.empty_like(Ks), torch.empty_like(bs), torch.empty_like(Kt), torch.empty_like(bt)
+        (dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt), rets = _grad_sinks(layer, layer._PNAMES)
         scratch = _new_like(x, _lib.query('bruno_heads_bwd_scratch_floats', C))
         _lib.call('bruno_coupling_conv_bwd', x, dy, dld, N, H, W, C, R, layer.mask_id, V1, g1, Vr, gr, ctx.wbwd, Ks, bs, Kt, bt,
                   ctx.slabs, gsl, scratch, dx, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt)
-        return dx, dld, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt, None, None, None
+        return (dx, dld) + tuple(rets) + (None, None, None)
 
 
 class CouplingLayerConv(Layer):                                             # nvp:58-187
@@ -350,14 +374,10 @@ class _DenseCouplingFn(torch.autograd.Function):
         N, D, U = xs[0], int(np.prod(xs[1:])), V1.shape[1]
         ws2 = _new_like(x, _lib.query('bruno_coupling_dense_bwd_ws_floats', N, D, U))
         dx = torch.empty_like(x)
-        outs = [torch.empty_like(t) for t in (V1, g1, b1, V2, g2, b2, Ks)]
-        dbs = _new_like(x, D)
-        dKt = torch.empty_like(Kt)
-        dbt = _new_like(x, D)
-        dV1, dg1, db1, dV2, dg2, db2, dKs = outs
+        (dV1, dg1, db1, dV2, dg2, db2, dKs, dbs, dKt, dbt), rets = _grad_sinks(ctx.layer, ctx.layer._PNAMES)
         _lib.call('bruno_coupling_dense_bwd', x, dy.contiguous(), dld.contiguous(), N, D, U, ctx.layer.mask_id, V1, g1, b1,
                   V2, g2, b2, Ks, Kt, ws, ws2, dx, dV1, dg1, db1, dV2, dg2, db2, dKs, dbs, dKt, dbt)
-        return dx, dld, dV1, dg1, db1, dV2, dg2, db2, dKs, dbs, dKt, dbt, None, None, None
+        return (dx, dld) + tuple(rets) + (None, None, None)
 
 
 class CouplingLayerDense(Layer):                                            # nvp:190-274

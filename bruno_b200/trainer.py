@@ -8,7 +8,7 @@ and divided by nr_gpu (:96-105), gradients of the prior_* variables multiplied b
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, nn_extra_nvp
 
 
 class Trainer(object):
@@ -51,7 +51,12 @@ class Trainer(object):
         self.flat_grad.zero_()
         log_probs = self.cfg.build_model(x, want_prior=False)[0]
         loss = self.cfg.loss(log_probs)
-        loss.backward()
+        # the coupling backward kernels write straight into the (just zeroed) flat gradient views
+        nn_extra_nvp.direct_grads(True)
+        try:
+            loss.backward()
+        finally:
+            nn_extra_nvp.direct_grads(False)
         return loss.detach()
 
     def apply_gradients(self, lr, student_scale=1.0):
