@@ -13,7 +13,7 @@ LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libbruno_sm100.so')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
-SOURCES = ['runtime.cu', 'process.cu', 'flow_misc.cu', 'dense.cu', 'conv_sm100.cu', 'coupling_conv.cu', 'optim.cu']
+SOURCES = ['runtime.cu', 'process.cu', 'flow_misc.cu', 'dense.cu', 'gemm_tf32.cu', 'conv_sm100.cu', 'coupling_conv.cu', 'optim.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']

@@ -5,20 +5,12 @@
 // en2 config): a register-tiled CUDA-core SGEMM with fused column-scale / bias / ELU epilogue, plus the elementwise
 // coupling kernels and the hand-written backward, orchestrated in C so that one coupling is ONE host call.
 #include "common.cuh"
+#include "dense_gemm.cuh"
 
 namespace bruno {
 
 constexpr int GB = 64;   // block tile M and N
 constexpr int GK = 16;
-
-struct GemmEpi {
-  const float* col_scale;  // out = acc * col_scale[n]          (may be null)
-  const float* bias;       // + bias[n]                         (may be null)
-  float* pre_out;          // store the pre-activation here too (may be null)
-  int act;                 // 0 none, 1 ELU
-  int accumulate;          // C += result
-  const float* a_kscale;   // A[m,k] *= a_kscale[k]             (may be null)
-};
 
 __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool valid) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
@@ -319,6 +311,8 @@ static float* g_sk_ws = nullptr;
 static unsigned* g_sk_tickets = nullptr;
 static int g_sk_sms = 0;
 
+static int g_gemm_variant = 1;   // 0: CUDA-core SGEMM, 1: tcgen05 3xTF32 (gemm_tf32.cu)
+
 static bool sk_workspace(cudaStream_t st) {
   if (g_sk_ws) return true;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -368,6 +362,12 @@ static int gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, 
                 const GemmEpi& ep, cudaStream_t st) {
   const bool vec_ok = aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0 && K % 4 == 0 &&
                       (ta ? M % 4 == 0 : true) && (tb ? true : N % 4 == 0) && (!ep.a_kscale || aligned16(ep.a_kscale));
+  if (vec_ok && g_gemm_variant == 1 && sk_workspace(st)) {
+    int taken = 0;
+    const int rc = gemm_tf32x3(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, ep, g_sk_ws, SK_WS_FLOATS, g_sk_tickets, SK_MAX_TILES,
+                               g_sk_sms, st, &taken);
+    if (taken) return rc;
+  }
   if (vec_ok) {
     const bool big = M >= 192;
 #define SK_DISPATCH(TA_, TB_)                                                                            \
@@ -619,6 +619,18 @@ size_t bruno_coupling_dense_ws_floats(int N, int D, int U) {
 }
 size_t bruno_coupling_dense_bwd_ws_floats(int N, int D, int U) {
   return 3 * (static_cast<size_t>(N) * D + 4) + 2 * (static_cast<size_t>(N) * U + 4) + 4 * (static_cast<size_t>(U) + 4);
+}
+
+int bruno_debug_gemm_variant(int variant) {
+  if (variant < 0) return g_gemm_variant;
+  BRUNO_REQUIRE(variant == 0 || variant == 1, "bruno_debug_gemm_variant: 0 (CUDA-core SGEMM) or 1 (tcgen05 3xTF32)");
+  g_gemm_variant = variant;
+  return BRUNO_OK;
+}
+
+int bruno_debug_gemm_trace(long long* device_buffer) {
+  gemm_tf32x3_set_trace(device_buffer);
+  return BRUNO_OK;
 }
 
 int bruno_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,

@@ -1,0 +1,455 @@
+// fp32-accurate GEMM on the tensor cores for the dense coupling layers (CouplingLayerDense, nn_extra_nvp.py:190-274;
+// dense_wn :408-432): C[M,N] = op(A)[M,K] op(B)[K,N] with the fused prologue / epilogue of GemmEpi.
+//
+// The dense s/t networks are the parity-critical fp32 part of the flow (en2_noconv_mnist is dense only, tolerance 1e-4),
+// but their GEMMs are skinny (640 x 512 x 784 in training, 40 x 512 x 784 when scoring a few-shot episode): on CUDA cores
+// they are bound by FFMA issue and shared-memory traffic at ~19 % of the fp32 peak.  Here every operand is split on the
+// fly into two TF32 terms, a = hi + lo (hi = tf32(a), lo = tf32(a - hi), |a - hi - lo| <= 2^-22 |a|), and the product is
+// accumulated as  hi*hi + lo*hi + hi*lo  by three tcgen05.mma.kind::tf32 per K step into one fp32 TMEM accumulator
+// (the dropped lo*lo term is 2^-22 relative: the result is as accurate as an fp32 FFMA chain of length K).
+//
+//   * no transposes: a row-major [M,K] / [N,K] source is a K-major UMMA operand, a row-major [K,M] / [K,N] source an
+//     MN-major one; both are written by the loader warps straight into the 128-byte-swizzled canonical layouts;
+//   * 128 x 128 output tile per CTA, K tiles of 32 through a 3-stage ring (4 loader warps -> 1 issuer warp);
+//   * split-K over gridDim.z so that ~one CTA per SM is busy even for 8..20 output tiles; partials go to a workspace
+//     and the last CTA of a tile (ticket) adds them in z order (deterministic) and runs the epilogue.
+#include "dense_gemm.cuh"
+#include <stdlib.h>
+
+#include <type_traits>
+
+#include "ptx.cuh"
+
+namespace bruno {
+
+namespace {
+
+constexpr int TG_BM = 128, TG_BK = 32, TG_STAGES = 3;
+constexpr int TG_TILE_BYTES = 128 * TG_BK * 4;            // 16 KB: one 128-row operand term of one stage
+constexpr int TG_LOADER_WARPS = 4 * TG_STAGES;            // one group of 4 warps per ring stage: three K tiles in flight
+constexpr int TG_THREADS = 32 * (TG_LOADER_WARPS + 1);    // + issuer warp; warps 0..3 also run the epilogue
+constexpr int TG_MAX_SPLIT = 8;
+
+struct TgSmem {
+  uint64_t full[TG_STAGES], empty[TG_STAGES], done;
+  uint32_t tmem_base;
+  int last;
+};
+
+// a = hi + lo with hi = a rounded to TF32 (11 significant bits) and lo = a - hi (exact, <= 13 significant bits).
+// cvt.rna.tf32.f32 issues at a fraction of the ALU rate and made the loaders the bottleneck; the same rounding is two
+// integer ops: add half an ulp of the TF32 mantissa to the magnitude bits, clear the 13 low bits.  lo is stored as it is:
+// the tensor core ignores its 13 low mantissa bits, |error| <= 2^-10 |lo| <= 2^-21 |a|.
+__device__ __forceinline__ void split_store(uint32_t hi_addr, uint32_t lo_addr, const float4& v) {
+  uint4 h, l;
+  h.x = (__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u;
+  h.y = (__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u;
+  h.z = (__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u;
+  h.w = (__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u;
+  l.x = __float_as_uint(v.x - __uint_as_float(h.x));
+  l.y = __float_as_uint(v.y - __uint_as_float(h.y));
+  l.z = __float_as_uint(v.z - __uint_as_float(h.z));
+  l.w = __float_as_uint(v.w - __uint_as_float(h.w));
+  sts_u4(hi_addr, h);
+  sts_u4(lo_addr, l);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// kind::tf32 instruction descriptor: TF32 A/B (format 2), fp32 D, M = 128
+__host__ __device__ constexpr uint32_t idesc_tf32(int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+// One 128 x 32 operand tile (rows = M or N index r0.., K tile at k0) of a row-major source, held in registers between the
+// global loads (fetch) and the split into two TF32 terms written in the canonical swizzled layout (store).  128 loader
+// threads, 8 x float4 each.
+//   KMAJOR  (source [rows, K], K contiguous): smem row r (128 B = 32 k), 16-byte chunk c at (c ^ (r & 7)); a warp
+//            instruction covers 4 full 128-byte source lines.
+//   MNMAJOR (source [K, rows], rows contiguous): 32-bit MN-major operands use the "128-byte swizzle with 32-byte
+//            atomicity" (descriptor layout type 1, cute Layout_MN_SW128_32B_Atom: Swizzle<2,5,2>): four 32-row atom
+//            columns 4 KB apart (LBO); inside one, smem row k (128 B = 32 consecutive rows), atoms of 4 k rows
+//            (SBO = 512 B), 32-BYTE chunk cc at (cc ^ (k & 3)); a warp instruction covers 512 contiguous source bytes.
+// Rows beyond `rows_total` are neither loaded nor stored: accumulator row m (column n) depends only on A row m (B row
+// n), and those outputs are never read.  The K tail IS zero-filled (it feeds every output).
+template <bool MNMAJOR, int ROWS>
+struct OperandTile {
+  float4 v[8];
+  uint32_t mask;    // bit i: element i is stored
+
+  __device__ __forceinline__ static uint32_t offset(int i, int tid) {
+    const int w = tid >> 5, l = tid & 31;
+    if (!MNMAJOR) {
+      const int r = w * 32 + i * 4 + (l >> 3), c = l & 7;
+      return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4));
+    }
+    const int k = w * 8 + i, a = l >> 3, c = l & 7;
+    return static_cast<uint32_t>(a * 4096 + k * 128 + (((((c >> 1) ^ (k & 3)) << 1) | (c & 1)) << 4));
+  }
+
+  __device__ __forceinline__ void fetch(const float* __restrict__ src, int ld, int rows_total, int K, int r0, int k0,
+                                        const float* __restrict__ kscale, int tid) {
+    const int w = tid >> 5, l = tid & 31;
+    mask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!MNMAJOR) {
+        const int r = w * 32 + i * 4 + (l >> 3), c = l & 7;
+        const int gr = r0 + r, gk = k0 + 4 * c;
+        if (r < ROWS && gr < rows_total) {
+          mask |= 1u << i;
+          if (gk < K) v[i] = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(gr) * ld + gk));
+        }
+      } else {
+        const int k = w * 8 + i, a = l >> 3, c = l & 7;
+        const int gr = r0 + a * 32 + 4 * c, gk = k0 + k;
+        if (a * 32 < ROWS && gr < rows_total) {
+          mask |= 1u << i;
+          if (gk < K) v[i] = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(gk) * ld + gr));
+        }
+      }
+    }
+    if (kscale) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!MNMAJOR) {
+          const int gk = k0 + 4 * (l & 7);
+          if (gk < K) {
+            const float4 s = __ldg(reinterpret_cast<const float4*>(kscale + gk));
+            v[i].x *= s.x; v[i].y *= s.y; v[i].z *= s.z; v[i].w *= s.w;
+          }
+        } else {
+          const int gk = k0 + w * 8 + i;
+          const float s = gk < K ? __ldg(kscale + gk) : 0.f;
+          v[i].x *= s; v[i].y *= s; v[i].z *= s; v[i].w *= s;
+        }
+      }
+    }
+  }
+
+  __device__ __forceinline__ void store(uint32_t hi_base, uint32_t lo_base, int tid) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (mask & (1u << i)) {
+        const uint32_t off = offset(i, tid);
+        split_store(hi_base + off, lo_base + off, v[i]);
+      }
+  }
+};
+
+// debug timeline (bruno_debug_gemm_trace): CTA 0 records clock64() per K tile [64][8]:
+// 0 stage free (loader), 1 tile stored, 2 arrived, 3 issuer saw it, 4 MMAs issued; row 63: 5 accumulator done, 6 epilogue end
+static long long* g_gemm_trace_host = nullptr;
+__device__ __forceinline__ void gtrace(long long* buf, int it, int slot) {
+  if (buf != nullptr && blockIdx.x + blockIdx.y + blockIdx.z == 0 && it < 64) buf[it * 8 + slot] = clock64();
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_apply(float x) {
+  if (ACT == 1) return x > 0.f ? x : expm1f(x);
+  if (ACT == 2) return x > 0.f ? x : 0.2f * x;      // tf.nn.leaky_relu default alpha
+  if (ACT == 3) return tanhf(x);
+  return x;
+}
+// runs f(integral_constant<ACT>) for the runtime activation code: the activation is compile-time inside the row loops
+// (left as a runtime test there, both transcendental paths are evaluated for every element: ~250 cycles per row)
+template <class F>
+__device__ __forceinline__ void with_act(int act, F f) {
+  if (act == 1) f(std::integral_constant<int, 1>{});
+  else if (act == 2) f(std::integral_constant<int, 2>{});
+  else if (act == 3) f(std::integral_constant<int, 3>{});
+  else f(std::integral_constant<int, 0>{});
+}
+
+template <bool TA, bool TB, int BN>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                   float* __restrict__ C, int ldc, GemmEpi ep, int kchunk, float* __restrict__ ws, unsigned* __restrict__ tickets,
+                   long long* trace_buf) {
+  constexpr int B_TILE_BYTES = BN * TG_BK * 4;
+  constexpr int STAGE_BYTES = 2 * TG_TILE_BYTES + 2 * B_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
+  extern __shared__ uint8_t tg_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tg_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  TgSmem* cs = reinterpret_cast<TgSmem*>(smem + TG_STAGES * STAGE_BYTES);
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * BN;
+  const int nk = (K + TG_BK - 1) / TG_BK;
+  const int kt0 = blockIdx.z * kchunk, kt1 = min(nk, kt0 + kchunk);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TG_STAGES; ++s) {
+      mbar_init(&cs->full[s], 128);
+      mbar_init(&cs->empty[s], 1);
+    }
+    mbar_init(&cs->done, 1);
+    fence_mbar_init();
+  }
+  if (warp == TG_LOADER_WARPS) {
+    __syncwarp();
+    tmem_alloc(&cs->tmem_base, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = cs->tmem_base;
+  const uint32_t stage0 = smem_u32(smem);
+
+  if (warp < TG_LOADER_WARPS) {
+    // ===== loaders: group g owns ring stage g and K tiles kt0 + g, kt0 + g + 3, ... =====
+    const int grp = warp >> 2;
+    const int tid = threadIdx.x & 127;
+    const uint32_t st = stage0 + grp * STAGE_BYTES;
+    // A is stored [K, M] when transposed (M contiguous -> MN-major), B is stored [K, N] when NOT transposed.
+    // The loads of the group's NEXT tile are issued right after the current one is stored, so they are in flight while
+    // the tensor core works on this stage and while the group waits for it to drain.
+    OperandTile<TA, TG_BM> ta_;
+    OperandTile<!TB, BN> tb_;
+    int kt = kt0 + grp;
+    if (kt < kt1) {
+      ta_.fetch(A, lda, M, K, m0, kt * TG_BK, ep.a_kscale, tid);
+      tb_.fetch(B, ldb, N, K, n0, kt * TG_BK, nullptr, tid);
+    }
+    uint32_t j = 0;
+    for (; kt < kt1; kt += TG_STAGES, ++j) {
+      mbar_wait(&cs->empty[grp], (j & 1u) ^ 1u);
+      if (tid == 0) gtrace(trace_buf, kt - kt0, 0);
+      ta_.store(st, st + TG_TILE_BYTES, tid);
+      tb_.store(st + 2 * TG_TILE_BYTES, st + 2 * TG_TILE_BYTES + B_TILE_BYTES, tid);
+      if (tid == 0) gtrace(trace_buf, kt - kt0, 1);
+      fence_proxy_async_smem();
+      mbar_arrive(&cs->full[grp]);
+      if (tid == 0) gtrace(trace_buf, kt - kt0, 2);
+      if (kt + TG_STAGES < kt1) {
+        ta_.fetch(A, lda, M, K, m0, (kt + TG_STAGES) * TG_BK, ep.a_kscale, tid);
+        tb_.fetch(B, ldb, N, K, n0, (kt + TG_STAGES) * TG_BK, nullptr, tid);
+      }
+    }
+  } else {
+    // ===== issuer: uniform loop, one elected lane issues =====
+    constexpr uint32_t idesc = idesc_tf32(BN, TA ? 1 : 0, TB ? 0 : 1);
+    constexpr uint32_t HI_K = (1024u >> 4) | (1u << 14) | (2u << 29);        // SBO 1024 B, version, SWIZZLE_128B
+    constexpr uint32_t HI_MN = (512u >> 4) | (1u << 14) | (1u << 29);        // SBO 512 B, version, SWIZZLE_128B_BASE32B
+    constexpr uint32_t A_HI = TA ? HI_MN : HI_K, B_HI = TB ? HI_K : HI_MN;
+    constexpr uint32_t A_LBO = TA ? (4096u >> 4) : 1u, B_LBO = TB ? 1u : (4096u >> 4);
+    constexpr uint32_t A_STEP = TA ? 64u : 2u, B_STEP = TB ? 2u : 64u;       // per K = 8: 8 smem rows / 32 bytes
+    const bool leader = elect_one();
+    int it = 0;
+    for (int kt = kt0; kt < kt1; ++kt, ++it) {
+      const int s = it % TG_STAGES;
+      if (leader) {
+        mbar_wait(&cs->full[s], (it / TG_STAGES) & 1);
+        tc_fence_after();
+        gtrace(trace_buf, it, 3);
+        const uint32_t st = (stage0 + s * STAGE_BYTES) >> 4;
+        const uint32_t ahi = (st & 0x3FFFu) | (A_LBO << 16), alo = ((st + (TG_TILE_BYTES >> 4)) & 0x3FFFu) | (A_LBO << 16);
+        const uint32_t bhi = ((st + 2 * (TG_TILE_BYTES >> 4)) & 0x3FFFu) | (B_LBO << 16);
+        const uint32_t blo = ((st + 2 * (TG_TILE_BYTES >> 4) + (B_TILE_BYTES >> 4)) & 0x3FFFu) | (B_LBO << 16);
+#pragma unroll
+        for (int kk = 0; kk < TG_BK / 8; ++kk) {
+          const uint64_t dah = (static_cast<uint64_t>(A_HI) << 32) | (ahi + kk * A_STEP);
+          const uint64_t dal = (static_cast<uint64_t>(A_HI) << 32) | (alo + kk * A_STEP);
+          const uint64_t dbh = (static_cast<uint64_t>(B_HI) << 32) | (bhi + kk * B_STEP);
+          const uint64_t dbl = (static_cast<uint64_t>(B_HI) << 32) | (blo + kk * B_STEP);
+          umma_tf32(tmem, dal, dbh, idesc, (it | kk) != 0);     // small terms first
+          umma_tf32(tmem, dah, dbl, idesc, 1u);
+          umma_tf32(tmem, dah, dbh, idesc, 1u);
+        }
+        umma_commit(&cs->empty[s]);
+        gtrace(trace_buf, it, 4);
+      }
+    }
+    if (leader) {
+      umma_commit(&cs->done);
+      mbar_wait(&cs->done, 0);           // no asynchronous arrive may outlive the CTA
+    }
+    __syncwarp();
+  }
+
+  if (warp < TG_LOADER_WARPS) {
+    // ===== epilogue.  Warps 0..3 read their TMEM lane quarter 32 columns at a time and transpose it through shared
+    // memory (the ring is idle once `done` fired), so that a warp instruction writes 32 consecutive columns of one row.
+    // With split-K the tile goes to the workspace and the LAST CTA of the tile (ticket) reduces it with all 12 warps.
+    const int S = gridDim.z;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    constexpr int NCH = BN / 32;
+    float* wt = ws + static_cast<size_t>(tile) * S * (TG_BM * BN);        // [z][row][BN]
+    // phase A: warps 0..3 copy their TMEM lane quarter into a row-major shared tile (pitch BN + 1: conflict-free both ways)
+    float* T = reinterpret_cast<float*>(smem);
+    constexpr int TP = BN + 1;
+    if (warp < 4) {
+      mbar_wait(&cs->done, 0);
+      tc_fence_after();
+      if (threadIdx.x == 0) gtrace(trace_buf, 63, 5);
+#pragma unroll 1
+      for (int ch = 0; ch < NCH; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + ch * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) T[(warp * 32 + lane) * TP + ch * 32 + e] = __uint_as_float(v[e]);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * TG_LOADER_WARPS) : "memory");
+    if (threadIdx.x == 0) gtrace(trace_buf, 60, 5);
+    // phase B: all 12 warps write rows (a warp instruction = 32 consecutive columns of one row)
+    const int rows = min(TG_BM, M - m0);
+    float* mine = wt + static_cast<size_t>(blockIdx.z) * (TG_BM * BN);
+    if (S > 1) {
+      for (int task = warp; task < rows * NCH; task += 2 * TG_LOADER_WARPS) {
+        const int t2 = task + TG_LOADER_WARPS;
+        const int r_a = task / NCH, c_a = task % NCH, r_b = t2 / NCH, c_b = t2 % NCH;
+        const float va = T[r_a * TP + c_a * 32 + lane];
+        const float vb = t2 < rows * NCH ? T[r_b * TP + c_b * 32 + lane] : 0.f;
+        __stcg(mine + r_a * BN + c_a * 32 + lane, va);
+        if (t2 < rows * NCH) __stcg(mine + r_b * BN + c_b * 32 + lane, vb);
+      }
+    } else {
+      with_act(ep.act, [&](auto act) {
+        constexpr int TU = 4;
+        const int ntask = rows * NCH;
+        for (int task0 = warp; task0 < ntask; task0 += TU * TG_LOADER_WARPS) {
+          float val[TU], old[TU];
+#pragma unroll
+          for (int u = 0; u < TU; ++u) {
+            const int task = task0 + u * TG_LOADER_WARPS;
+            const int row = task / NCH, ch = task % NCH;
+            const bool on = task < ntask && n0 + ch * 32 + lane < N;
+            val[u] = on ? T[row * TP + ch * 32 + lane] : 0.f;
+            old[u] = (on && ep.accumulate) ? C[static_cast<size_t>(m0 + row) * ldc + n0 + ch * 32 + lane] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < TU; ++u) {
+            const int task = task0 + u * TG_LOADER_WARPS;
+            const int row = task / NCH, ch = task % NCH;
+            const int n = n0 + ch * 32 + lane;
+            if (task < ntask && n < N) {
+              const size_t o = static_cast<size_t>(m0 + row) * ldc + n;
+              float x = val[u];
+              if (ep.col_scale) x = __fmul_rn(x, ep.col_scale[n]);
+              if (ep.bias) x = __fadd_rn(x, ep.bias[n]);
+              if (ep.pre_out) ep.pre_out[o] = x;
+              C[o] = act_apply<decltype(act)::value>(x) + old[u];
+            }
+          }
+        }
+      });
+    }
+    if (threadIdx.x == 0) gtrace(trace_buf, 60, 6);
+    if (S > 1) {
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TG_LOADER_WARPS) : "memory");
+      if (threadIdx.x == 0) cs->last = (atomicAdd(tickets + tile, 1u) == static_cast<unsigned>(S - 1));
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TG_LOADER_WARPS) : "memory");
+      if (cs->last) {
+        __threadfence();
+        // task = (row, 32-column chunk); each lane adds the S partials of its column in z order.  Four tasks per
+        // iteration: all their partial loads are in flight together (one L2 round trip per iteration, not per task).
+        with_act(ep.act, [&](auto act) {
+          constexpr int TU = 4;
+          const int ntask = rows * NCH;
+          for (int task0 = warp; task0 < ntask; task0 += TU * TG_LOADER_WARPS) {
+            float part[TU][TG_MAX_SPLIT];
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+              const int task = task0 + u * TG_LOADER_WARPS;
+              const float* src = wt + (task / NCH) * BN + (task % NCH) * 32 + lane;
+#pragma unroll
+              for (int z = 0; z < TG_MAX_SPLIT; ++z)
+                part[u][z] = (task < ntask && z < S) ? __ldcg(src + static_cast<size_t>(z) * (TG_BM * BN)) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+              const int task = task0 + u * TG_LOADER_WARPS;
+              if (task >= ntask) break;
+              const int row = task / NCH, ch = task % NCH;
+              const int n = n0 + ch * 32 + lane;
+              float x = 0.f;
+#pragma unroll
+              for (int z = 0; z < TG_MAX_SPLIT; ++z) x += part[u][z];
+              if (n < N) {
+                const size_t o = static_cast<size_t>(m0 + row) * ldc + n;
+                if (ep.col_scale) x = __fmul_rn(x, ep.col_scale[n]);
+                if (ep.bias) x = __fadd_rn(x, ep.bias[n]);
+                if (ep.pre_out) ep.pre_out[o] = x;
+                x = act_apply<decltype(act)::value>(x);
+                if (ep.accumulate) x += C[o];
+                C[o] = x;
+              }
+            }
+          }
+        });
+        if (threadIdx.x == 0) tickets[tile] = 0u;
+      }
+    }
+    if (threadIdx.x == 0) gtrace(trace_buf, 63, 6);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TG_LOADER_WARPS) {
+    __syncwarp();
+    tmem_dealloc(tmem, BN);
+  }
+}
+
+template <bool TA, bool TB, int BN>
+int launch_tf32_bn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& ep,
+                   float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, cudaStream_t st) {
+  constexpr size_t smem = 1024 + TG_STAGES * (2 * TG_TILE_BYTES + 2 * BN * TG_BK * 4) + sizeof(TgSmem) + 64;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(tf32x3_gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = true;
+  }
+  const int nx = ceil_div(N, BN), ny = ceil_div(M, TG_BM), tiles = nx * ny, nk = ceil_div(K, TG_BK);
+  int S = 1;
+  static const char* force_s = getenv("BRUNO_TF32_SPLIT");
+  if (ws && tickets && tiles <= max_tiles) {
+    S = force_s ? atoi(force_s) : sms / tiles;
+    const int smax = nk / 2 < TG_MAX_SPLIT ? nk / 2 : TG_MAX_SPLIT;      // at least two K tiles per CTA
+    S = S > smax ? smax : S;
+    S = S < 1 ? 1 : S;
+    while (S > 1 && static_cast<size_t>(tiles) * S * TG_BM * BN > ws_floats) --S;
+  }
+  const int kchunk = ceil_div(nk, S);
+  S = ceil_div(nk, kchunk);
+  tf32x3_gemm_kernel<TA, TB, BN><<<dim3(nx, ny, S), TG_THREADS, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep, kchunk, ws, tickets,
+                                                                                g_gemm_trace_host);
+  return check_launch("tf32x3_gemm_kernel");
+}
+
+template <bool TA, bool TB>
+int launch_tf32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& ep,
+                float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, cudaStream_t st, int* taken) {
+  *taken = 1;
+  // 64-column tiles while 128-column tiles would leave most SMs without work
+  const int tiles128 = ceil_div(N, 128) * ceil_div(M, TG_BM);
+  if (tiles128 * 2 <= sms || N <= 64)
+    return launch_tf32_bn<TA, TB, 64>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st);
+  return launch_tf32_bn<TA, TB, 128>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st);
+}
+
+}  // namespace
+
+void gemm_tf32x3_set_trace(long long* device_buffer) { g_gemm_trace_host = device_buffer; }
+
+int gemm_tf32x3(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                const GemmEpi& ep, float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, cudaStream_t st,
+                int* taken) {
+  *taken = 0;
+  if (!ta && !tb) return launch_tf32<false, false>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st, taken);
+  if (ta && !tb) return launch_tf32<true, false>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st, taken);
+  if (!ta && tb) return launch_tf32<false, true>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st, taken);
+  return launch_tf32<true, true>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st, taken);
+}
+
+}  // namespace bruno

@@ -231,6 +231,13 @@ int bruno_dense_wn_scale(const float* V, const float* g, float* sc, float* inv_n
 /* the affine coupling + log-det of CouplingLayerDense given the two head outputs s_pre, t_pre [N,D] (nvp:168-186) */
 int bruno_dense_coupling(const float* x, const float* s_pre, const float* t_pre, const float* ld_in, float* y, float* ld_out,
                          int N, int D, int mask_type, int inverse, void* stream);
+/* debug / A-B timing: which kernel the dense-path GEMMs (bruno_sgemm and the dense couplings) use when the operands are
+ * 16-byte aligned: 0 = CUDA-core SGEMM (strict fp32 FFMA), 1 = tcgen05 3xTF32 split (fp32-accurate, default).
+ * variant < 0 queries. */
+int bruno_debug_gemm_variant(int variant);
+/* debug: CTA (0,0,0) of the tcgen05 GEMM records clock64() of its pipeline events into device_buffer [64][8] (NULL = off) */
+int bruno_debug_gemm_trace(long long* device_buffer);
+
 /* C[M,N] (+)= act(op(A) op(B) * col_scale + bias), row-major fp32 (tf.matmul at nvp:418, tf.layers.dense :262,:268);
  * act: 0 none, 1 ELU, 2 leaky_relu(0.2), 3 tanh */
 int bruno_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
