@@ -248,6 +248,15 @@ def main():
     # forward convs + dgrad convs: 2 x the forward count per step, `steps` steps in the profiled region
     flops_total = 2.0 * conv_launch_flops(n_img) * steps
     achieved = flops_total / (conv['total_ms'] * 1e-3) / 1e12 if conv['total_ms'] > 0 else None
+    traffic, traffic_note = None, None
+    tj = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')
+    if os.path.exists(tj):
+        tinfo = json.load(open(tj))
+        traffic = tinfo['avg_bytes_per_launch']
+        traffic_note = ('dram read+write bytes per launch, ncu --set full capture of the 28x28 layers (%s); algorithmic bytes of '
+                        'such a launch: %.0f (in + out slab) to %.0f (in + skip + out)' % (
+                            tinfo['source'], tinfo['algorithmic_bytes_per_launch']['mode0 (in+out slab)'],
+                            tinfo['algorithmic_bytes_per_launch']['mode1 (in+skip+out)']))
     seqs = B * world
     line = {
         'metric': 'bn2_omniglot_tp_train_seqs_per_sec', 'value': seqs * steps / (ms_train * 1e-3), 'unit': 'seqs/s',
@@ -266,9 +275,10 @@ def main():
         'e2e': {'value': seqs * steps / (ms_e2e * 1e-3), 'unit': 'seqs/s', 'h2d_bytes_per_step': int(host[0].numel() * 4),
                 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / steps},
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_kernel (tcgen05 implicit GEMM, fwd + dgrad launches)',
+        'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_tap_kernel (tcgen05 implicit GEMM, fwd + dgrad launches)',
                      'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                     'frac': (achieved / peak_tf) if achieved else None, 'traffic': None, 'peak_source': peak_src,
+                     'frac': (achieved / peak_tf) if achieved else None, 'traffic': traffic, 'traffic_note': traffic_note,
+                     'peak_source': peak_src,
                      'launches': conv['launches'], 'avg_launch_us': 1e3 * conv['total_ms'] / max(conv['launches'], 1),
                      'share_of_step': conv['total_ms'] / (ms_train) if ms_train else None},
         'kernel_time_ms_per_step': {k: v['total_ms'] / steps for k, v in prof.items()},
