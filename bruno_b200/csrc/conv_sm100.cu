@@ -646,6 +646,327 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
   }
 }
 
+// ---- pair-fused implicit GEMM (variant 2) ------------------------------------------------------------------------
+// The per-tap kernel is bound by the shared-memory port: 36 MMAs x 6 KB of operand reads + ~58 KB of slab / staging
+// traffic per 128-row tile = 2140 cycles at 128 B/clk (measured: 2100).  Here the taps (dy, 0) and (dy, +1) share ONE
+// activation view in an N = 128 MMA (8 KB per instruction, at the port limit AND the tensor rate), and the tap (dy, -1)
+// is an N = 64 MMA on the view shifted by one row that accumulates into the same 64 columns as (dy, 0):
+//     D0[q] = sum_dy in[q + dy P - 1] W[dy,-1] + in[q + dy P] W[dy,0]        (columns 0..63)
+//     D1[q] = sum_dy in[q + dy P]     W[dy,+1]                               (columns 64..127)
+//     out[p] = D0[p] + D1[p + 1]
+// 24 MMAs / 168 KB per tile instead of 36 / 216 KB; the epilogue pays ONE warp shuffle per value (half of the dx-fused
+// kernel, a third fewer TMEM loads) and tiles overlap by one row (128 computed, 127 stored).
+// Measured (tools/bench_conv.py, 640 x 28 x 28): the issuer needs 1250 cycles per tile (per-tap: 1700) but the two-pass
+// shuffle epilogue needs ~3700 cycles per tile and group, so the kernel is epilogue-bound at ~1950 cycles per tile:
+// 38.8 us in mode 0 (per-tap 39.7) and SLOWER in the modes with auxiliary tiles (44-55 us vs 40-46).  Kept as variant 2
+// for A/B work on its epilogue; the per-tap kernel stays the default.
+constexpr int PR_OUT_ROWS = 127;
+constexpr int PR_OUT_BYTES = PR_OUT_ROWS * SLAB_ROW_BYTES;
+constexpr int PR_ACC = 4;                    // 4 x 128 TMEM columns
+
+struct PairSmem {
+  uint64_t full[TAP_MAX_STAGES], empty[TAP_MAX_STAGES], tfull[PR_ACC], tempty[PR_ACC], wbar;
+  uint64_t auxfull[2], outready[2];
+  uint32_t tmem_base;
+  alignas(16) float bias[64];
+  alignas(16) float xch[2][4][4][EPI_CH];    // [group][lane quarter][channel group][channels]: D1 of the quarter's row 0
+};
+
+template <int MODE, int NS>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+conv3x3_pair_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
+                    const uint8_t* __restrict__ aux1, const uint8_t* __restrict__ aux2, uint8_t* __restrict__ out,
+                    SlabGeom g, int ntiles, int bias_img_stride, long long* trace_buf) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int slab_rows = TILE_M + 2 * g.HALO + 8;
+  const uint32_t slab_bytes = static_cast<uint32_t>(slab_rows) * SLAB_ROW_BYTES;
+  uint8_t* wsm = smem;
+  uint8_t* slabs = smem + W_BYTES;
+  uint8_t* stage1 = slabs + NS * slab_bytes;                           // [2][STG_BYTES] aux1 in / output out (in place)
+  uint8_t* stage2 = stage1 + 2 * STG_BYTES;                            // [2][STG_BYTES] aux2 (MODE_ADD_MUL only)
+  PairSmem* cs = reinterpret_cast<PairSmem*>(stage2 + (mode_has_aux2(MODE) ? 2 * STG_BYTES : 0));
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  constexpr bool HAS_BIAS = MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TAP_MAX_STAGES; ++s) {
+      mbar_init(&cs->full[s], 1);
+      mbar_init(&cs->empty[s], 1);
+    }
+    for (int a = 0; a < PR_ACC; ++a) {
+      mbar_init(&cs->tfull[a], 1);
+      mbar_init(&cs->tempty[a], FWD_EPI_WARPS / 2);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&cs->auxfull[a], 1);
+      mbar_init(&cs->outready[a], FWD_EPI_WARPS * 16);
+    }
+    mbar_init(&cs->wbar, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) cs->bias[threadIdx.x - 64] = HAS_BIAS ? bias[threadIdx.x - 64] : 0.f;
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(&cs->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = cs->tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // tile t: computed rows = data rows [127 t, 127 t + 128), stored rows [127 t, 127 t + 127).  First computed = first
+  // stored buffer row Rf = HALO + 127 t; slab load starts at LS = floor8(Rf - P - 1); staging row 0 <-> floor8(Rf).
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
+      bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % NS;
+        const uint32_t ph = (it / NS) & 1;
+        const int LS = (g.HALO + PR_OUT_ROWS * tile - g.P - 1) & ~7;
+        mbar_wait(&cs->empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&cs->full[s], slab_bytes);
+        bulk_g2s(slabs + s * slab_bytes, in + static_cast<size_t>(LS) * SLAB_ROW_BYTES, slab_bytes, &cs->full[s]);
+        trace_at(trace_buf, it, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (uniform loop, elected lane issues; stage / accumulator compile-time, see the per-tap kernel) =====
+    constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr int U = (NS == 3) ? 12 : 4;
+    mbar_wait(&cs->wbar, 0);
+    const uint64_t bdesc0 = umma_desc_sw128(smem_u32(wsm), 16, 1024);
+    uint64_t adesc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) adesc[s] = umma_desc_sw128(smem_u32(slabs + s * slab_bytes), 16, 1024);
+    const uint32_t p8 = static_cast<uint32_t>(g.P) * 8u;
+    int tile = blockIdx.x;
+    bool more = tile < ntiles;
+    const bool leader = elect_one();
+    if (more && leader) {
+      mbar_wait(&cs->tempty[0], 1u);
+      mbar_wait(&cs->full[0], 0u);
+      tc_fence_after();
+    }
+    for (uint32_t r = 0; more; ++r) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (more) {
+          const int s = u % NS, a = u % PR_ACC;
+          const int sn = (u + 1) % NS, an = (u + 1) % PR_ACC;
+          const int it = static_cast<int>(r) * U + u;
+          const int Rf = g.HALO + PR_OUT_ROWS * tile;
+          const uint32_t a_base = static_cast<uint32_t>(Rf - ((Rf - g.P - 1) & ~7)) * 8u;
+          tile += gridDim.x;
+          more = tile < ntiles;
+          if (leader) {
+            trace_at(trace_buf, it, 1);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint32_t a_off = a_base + static_cast<uint32_t>(dy - 1) * p8;
+              if (more) {
+                if (dy == 1) mbar_wait(&cs->tempty[an], ((r * (U / PR_ACC) + (u + 1) / PR_ACC) & 1u) ^ 1u);
+                if (dy == 2) {
+                  mbar_wait(&cs->full[sn], (r * (U / NS) + (u + 1) / NS) & 1u);
+                  tc_fence_after();
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k)      // taps (dy, 0) | (dy, +1): columns 0..127
+                umma_bf16(tmem + a * 128, adesc[s] + (a_off + 2u * k),
+                          bdesc0 + static_cast<uint32_t>(((dy * 3 + 1) * W_TAP_BYTES + k * 32) >> 4), idesc128, (dy | k) != 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)      // tap (dy, -1) on the view one row up: columns 0..63
+                umma_bf16(tmem + a * 128, adesc[s] + (a_off - 8u + 2u * k),
+                          bdesc0 + static_cast<uint32_t>(((dy * 3) * W_TAP_BYTES + k * 32) >> 4), idesc64, 1u);
+            }
+            umma_commit(&cs->empty[s]);
+            umma_commit(&cs->tfull[a]);
+            trace_at(trace_buf, it, 2);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 2 + FWD_EPI_WARPS) {
+    // ===== epilogue: two groups of 8 warps alternate tiles; warp -> TMEM lane quarter and 32-channel half, processed as
+    // two passes of 16 channels =====
+    const int grp = (warp - 2) >> 3;
+    const int q = warp & 3;
+    const int half = ((warp - 2) >> 2) & 1;
+    const int row = q * 32 + lane;              // computed row inside the tile; rows 0..126 are stored
+    constexpr int NCH = EPI_CH / 8;
+    const float m_dn = lane < 31 ? 1.f : 0.f;   // lane 31 takes row + 1 from the next lane quarter through smem
+    const bool stored = row < PR_OUT_ROWS;
+    const int tile_stride = 2 * gridDim.x;
+    const int step_mod = (PR_OUT_ROWS * tile_stride) % g.IMG;
+    const int step_div = (PR_OUT_ROWS * tile_stride) / g.IMG;
+    int tile = blockIdx.x + grp * gridDim.x;
+    int data_row = PR_OUT_ROWS * tile + row;
+    int q_img = data_row % g.IMG;
+    int n_img = data_row / g.IMG;
+    const float inv_p = 1.0f / static_cast<float>(g.P);
+    int it = grp;
+    for (; tile < ntiles; tile += tile_stride, it += 2) {
+      const int a = it % PR_ACC;
+      const int yy = static_cast<int>((static_cast<float>(q_img) + 0.5f) * inv_p);
+      const int xx = q_img - yy * g.P;
+      const bool valid = stored && data_row < g.data_rows && yy >= 1 && xx >= 1;
+      const int Rf = g.HALO + PR_OUT_ROWS * tile;
+      const int srow = (Rf & 7) + row;
+      const int R7 = (Rf + row) & 7;
+      const uint32_t st1 = smem_u32(stage1 + grp * STG_BYTES + srow * SLAB_ROW_BYTES);
+      const uint32_t st2 = smem_u32(stage2 + grp * STG_BYTES + srow * SLAB_ROW_BYTES);
+      mbar_wait(&cs->tfull[a], (it / PR_ACC) & 1);
+      tc_fence_after();
+      if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 3);
+#pragma unroll 1
+      for (int p = 0; p < 2; ++p) {
+        const int cg = half * 2 + p;
+        const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 128 + cg * EPI_CH;
+        uint32_t d0[NCH][8], d1[NCH][8];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          tmem_ld8(tbase + c * 8, d0[c]);
+          tmem_ld8(tbase + 64 + c * 8, d1[c]);
+        }
+        tmem_ld_wait();
+        if (p == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cs->tempty[a]);
+          if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 6);
+        }
+        const uint32_t xw = smem_u32(cs->xch[grp][q][cg]);
+        float acc[EPI_CH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          if (lane == 0) {
+            sts_u4(xw + c * 32, make_uint4(d1[c][0], d1[c][1], d1[c][2], d1[c][3]));
+            sts_u4(xw + c * 32 + 16, make_uint4(d1[c][4], d1[c][5], d1[c][6], d1[c][7]));
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[c][e]), 1);    // dx = +1 term of row + 1
+            acc[c * 8 + e] = fmaf(dn, m_dn, __uint_as_float(d0[c][e]));
+          }
+        }
+        // the last row of a lane quarter takes row + 1 from the next quarter (another warp): group barrier, then read
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
+        if (lane == 31 && q < 3) {
+          const uint32_t xr = smem_u32(cs->xch[grp][q + 1][cg]);
+#pragma unroll
+          for (int e = 0; e < EPI_CH / 4; ++e) {
+            const uint4 t = lds_u4(xr + e * 16);
+            acc[4 * e] += __uint_as_float(t.x); acc[4 * e + 1] += __uint_as_float(t.y);
+            acc[4 * e + 2] += __uint_as_float(t.z); acc[4 * e + 3] += __uint_as_float(t.w);
+          }
+        }
+        if (p == 0) mbar_wait(&cs->auxfull[grp], (it >> 1) & 1);
+        if (stored) {
+#pragma unroll
+          for (int jj = 0; jj < NCH; ++jj) {
+            const int j = cg * NCH + jj;
+            const int pos = (j ^ R7) << 4;
+            float o[8], bj[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = acc[jj * 8 + e];
+            if (HAS_BIAS) {
+              const float* bsrc = bias_img_stride ? bias + static_cast<size_t>(valid ? n_img : 0) * bias_img_stride + j * 8
+                                                  : &cs->bias[j * 8];
+              const float4 b0 = *reinterpret_cast<const float4*>(bsrc);
+              const float4 b1 = *reinterpret_cast<const float4*>(bsrc + 4);
+              bj[0] = b0.x; bj[1] = b0.y; bj[2] = b0.z; bj[3] = b0.w; bj[4] = b1.x; bj[5] = b1.y; bj[6] = b1.z; bj[7] = b1.w;
+            }
+            if (MODE == MODE_ELU || MODE == MODE_LINEAR) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float t = o[e] + bj[e];
+                o[e] = MODE == MODE_ELU ? elu_fast(t) : t;
+              }
+            } else if (MODE == MODE_RES_ELU) {
+              float sk[8];
+              unpack8(lds_u4(st1 + pos), sk);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = elu_fast(o[e] + bj[e] + sk[e]);
+            } else if (MODE == MODE_MUL) {
+              float sk[8];
+              unpack8(lds_u4(st1 + pos), sk);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(sk[e]);
+            } else {
+              float sk[8], t[8];
+              unpack8(lds_u4(st1 + pos), sk);
+              unpack8(lds_u4(st2 + pos), t);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
+            }
+            sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 4);
+      mbar_arrive(&cs->outready[grp]);
+      data_row += PR_OUT_ROWS * tile_stride;
+      q_img += step_mod;
+      n_img += step_div;
+      if (q_img >= g.IMG) {
+        q_img -= g.IMG;
+        ++n_img;
+      }
+    }
+  } else {
+    // ===== aux / store warp =====
+    if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      int it = 0;
+      int prev_tile = -1;
+      for (int tile = blockIdx.x;; tile += gridDim.x, ++it) {
+        const bool live = tile < ntiles;
+        if (live) {
+          const int b = it & 1;
+          const int Rf = g.HALO + PR_OUT_ROWS * tile;
+          bulk_wait_read<0>();
+          if (mode_has_aux1(MODE)) {
+            const size_t off = static_cast<size_t>(Rf) * SLAB_ROW_BYTES;
+            const uint32_t soff = static_cast<uint32_t>(Rf & 7) * SLAB_ROW_BYTES;
+            mbar_arrive_expect_tx(&cs->auxfull[b], mode_has_aux2(MODE) ? 2 * PR_OUT_BYTES : PR_OUT_BYTES);
+            bulk_g2s(stage1 + b * STG_BYTES + soff, aux1 + off, PR_OUT_BYTES, &cs->auxfull[b]);
+            if (mode_has_aux2(MODE)) bulk_g2s(stage2 + b * STG_BYTES + soff, aux2 + off, PR_OUT_BYTES, &cs->auxfull[b]);
+          } else {
+            mbar_arrive(&cs->auxfull[b]);
+          }
+        }
+        if (prev_tile >= 0) {
+          const int pit = it - 1;
+          const int pa = pit & 1;
+          const int Rf = g.HALO + PR_OUT_ROWS * prev_tile;
+          mbar_wait(&cs->outready[pa], (pit >> 1) & 1);
+          bulk_s2g(out + static_cast<size_t>(Rf) * SLAB_ROW_BYTES, stage1 + pa * STG_BYTES + (Rf & 7) * SLAB_ROW_BYTES, PR_OUT_BYTES);
+          bulk_commit();
+          trace_at(trace_buf, pit, 5);
+        }
+        if (!live) break;
+        prev_tile = tile;
+      }
+      bulk_wait_all<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // wgrad
 // ------------------------------------------------------------------------------------------------------------
@@ -917,7 +1238,7 @@ static int num_sms() {
   return cached[dev];
 }
 
-static int g_conv_variant = 1;   // 0: dx-fused N=192 kernel, 1: per-tap N=64 kernel
+static int g_conv_variant = 1;   // 0: dx-fused N=192 kernel, 1: per-tap N=64 kernel, 2: pair-fused N=128 + N=64 kernel
 
 template <int MODE, int NS>
 static int launch_conv_tap_ns(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
@@ -966,10 +1287,52 @@ static int launch_conv_tap(const void* in, const void* w, const float* bias, int
   return launch_conv_tap_ns<MODE, 2>(in, w, bias, bias_img_stride, a1, a2, out, g, smem, st);
 }
 
+template <int MODE, int NS>
+static int launch_conv_pair_ns(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
+                               const void* a2, void* out, const SlabGeom& g, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv3x3_pair_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
+  const int ntiles = (g.data_rows + PR_OUT_ROWS - 1) / PR_OUT_ROWS;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  ProfSpan span(BRUNO_PROF_CONV, st);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(FWD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel<MODE, NS>, static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias,
+                     static_cast<const uint8_t*>(a1), static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g, ntiles,
+                     bias_img_stride, g_conv_trace_host);
+  return check_launch("conv3x3_pair_kernel");
+}
+
+template <int MODE>
+static int launch_conv_pair(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
+                            const void* a2, void* out, const SlabGeom& g, cudaStream_t st) {
+  const size_t fixed = 1024 + W_BYTES + (mode_has_aux2(MODE) ? 4 : 2) * STG_BYTES + sizeof(PairSmem) + 64;
+  const size_t slab = static_cast<size_t>(TILE_M + 2 * g.HALO + 8) * SLAB_ROW_BYTES;
+  int ns = fixed + 2 * slab > 227 * 1024 ? 0 : static_cast<int>((227 * 1024 - fixed) / slab);
+  if (ns > TAP_MAX_STAGES) ns = TAP_MAX_STAGES;
+  BRUNO_REQUIRE(ns >= 2, "bruno_conv3x3: W=%d too wide for the shared-memory slab ring", g.W);
+  const size_t smem = fixed + static_cast<size_t>(ns) * slab;
+  if (ns == 4) return launch_conv_pair_ns<MODE, 4>(in, w, bias, bias_img_stride, a1, a2, out, g, smem, st);
+  if (ns == 3) return launch_conv_pair_ns<MODE, 3>(in, w, bias, bias_img_stride, a1, a2, out, g, smem, st);
+  return launch_conv_pair_ns<MODE, 2>(in, w, bias, bias_img_stride, a1, a2, out, g, smem, st);
+}
+
 template <int MODE>
 static int launch_conv(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
                        const void* a2, void* out, const SlabGeom& g, cudaStream_t st) {
   if (g_conv_variant == 1) return launch_conv_tap<MODE>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
+  if (g_conv_variant == 2) return launch_conv_pair<MODE>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
   const size_t smem = conv_smem_bytes(g, MODE);
   static bool configured = false;
   if (!configured) {
@@ -1015,7 +1378,7 @@ int bruno_debug_conv_trace(long long* device_buffer) {
 
 int bruno_debug_conv_variant(int variant) {
   if (variant < 0) return g_conv_variant;
-  BRUNO_REQUIRE(variant == 0 || variant == 1, "bruno_debug_conv_variant: 0 (dx-fused) or 1 (per-tap)");
+  BRUNO_REQUIRE(variant >= 0 && variant <= 2, "bruno_debug_conv_variant: 0 (dx-fused), 1 (per-tap) or 2 (pair-fused)");
   g_conv_variant = variant;
   return BRUNO_OK;
 }
@@ -1041,7 +1404,7 @@ int bruno_conv3x3(int mode, const void* in_slab, const void* wpack, const float*
   BRUNO_REQUIRE(aligned16(in_slab) && aligned16(wpack) && aligned16(out_slab), "bruno_conv3x3: 16-byte alignment required");
   BRUNO_REQUIRE(in_slab != out_slab, "bruno_conv3x3: in-place convolution is not possible");
   const SlabGeom g = slab_geom(N, H, W);
-  BRUNO_REQUIRE(g_conv_variant == 1 || conv_smem_bytes(g) <= 227 * 1024, "bruno_conv3x3: W=%d too wide for the shared-memory slab", W);
+  BRUNO_REQUIRE(g_conv_variant != 0 || conv_smem_bytes(g) <= 227 * 1024, "bruno_conv3x3: W=%d too wide for the shared-memory slab", W);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (mode) {
     case MODE_ELU:

@@ -134,7 +134,8 @@ size_t bruno_conv_wpack_bytes(void);
 /* debug: CTA 0 of bruno_conv3x3 records clock64() of its pipeline events into device_buffer [64 tiles][8] (NULL = off) */
 int bruno_debug_conv_trace(long long* device_buffer);
 /* debug / A-B timing: which forward/dgrad kernel bruno_conv3x3 launches: 0 = dx-fused (three horizontal taps per N=192
- * MMA, shuffle epilogue), 1 = per-tap (36 MMAs of N=64 into one accumulator, plain epilogue).  variant < 0 queries. */
+ * MMA, shuffle epilogue), 1 = per-tap (36 MMAs of N=64 into one accumulator, plain epilogue; default), 2 = pair-fused
+ * (taps (dy,0),(dy,+1) in one N=128 MMA, (dy,-1) as an N=64 MMA on the shifted view).  variant < 0 queries. */
 int bruno_debug_conv_variant(int variant);
 
 /* conv2d_wn weight normalisation (nvp:389) of L stacked 3x3 64->64 kernels V [L,3,3,64,64] (HWIO), g [L,64] into the

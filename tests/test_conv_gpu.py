@@ -41,8 +41,20 @@ def _setup(N, H, W, seed):
     return V, gain, bias, x, a1, a2, wf, wbw
 
 
+@pytest.fixture
+def conv_variant(request):
+    """Selects the forward/dgrad kernel (0 dx-fused, 1 per-tap = default, 2 pair-fused) for one test, then restores it."""
+    from bruno_b200 import _lib
+    lib = _lib.load()
+    prev = lib.bruno_debug_conv_variant(-1)
+    assert lib.bruno_debug_conv_variant(request.param) == 0
+    yield request.param
+    lib.bruno_debug_conv_variant(prev)
+
+
+@pytest.mark.parametrize('conv_variant', [0, 1, 2], indirect=True)
 @pytest.mark.parametrize('N,H,W', [(3, 28, 28), (5, 14, 14), (2, 32, 32), (1, 16, 16), (40, 14, 14)])
-def test_conv3x3_all_epilogues(N, H, W):
+def test_conv3x3_all_epilogues(N, H, W, conv_variant):
     from bruno_b200 import _lib, slab
     V, gain, bias, x, a1, a2, wf, wbw = _setup(N, H, W, seed=N * H)
     Wt = bf(wn(V[0].float().double(), gain[0].float().double()))   # the kernel rounds the normalised weights to bf16
