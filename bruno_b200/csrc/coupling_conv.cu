@@ -42,6 +42,18 @@ int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, i
                             const void* wbwd, const float* Ks, const float* bs, const float* Kt, const float* bt,
                             const void* saved_slabs, void* gslabs, float* scratch, float* dx, float* dV1, float* dg1, float* db1,
                             float* dVr, float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt, void* stream) {
+  return bruno_coupling_conv_bwd_cond(x, dy, dld, N, H, W, C, R, mask_type, V1, g1, Vr, gr, wbwd, Ks, bs, Kt, bt, saved_slabs,
+                                      gslabs, scratch, dx, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt, nullptr, nullptr, 0,
+                                      nullptr, nullptr, stream);
+}
+
+int bruno_coupling_conv_bwd_cond(const float* x, const float* dy, const float* dld, int N, int H, int W, int C, int R,
+                                 int mask_type, const float* V1, const float* g1, const float* Vr, const float* gr,
+                                 const void* wbwd, const float* Ks, const float* bs, const float* Kt, const float* bt,
+                                 const void* saved_slabs, void* gslabs, float* scratch, float* dx, float* dV1, float* dg1,
+                                 float* db1, float* dVr, float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt,
+                                 const float* label_s, float* dtab, int dtab_stride, float* dlabel_s, float* dlabel_t,
+                                 void* stream) {
   BRUNO_REQUIRE(x && dy && dld && V1 && g1 && Vr && gr && wbwd && Ks && bs && Kt && bt && saved_slabs && gslabs && scratch && dx && dV1 &&
                     dg1 && db1 && dVr && dgr && dbr && dKs && dbs && dKt && dbt, "bruno_coupling_conv_bwd: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -55,8 +67,8 @@ int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, i
   cudaMemsetAsync(dV1, 0, static_cast<size_t>(C) * 64 * sizeof(float), st);
   cudaMemsetAsync(db1, 0, 64 * sizeof(float), st);
   int rc;
-  if ((rc = bruno_heads_coupling_bwd(x, S(2 * R), Ks, bs, Kt, bt, dy, dld, dx, GS(2 * R), dKs, dbs, dKt, dbt, scratch, N, H, W, C,
-                                     mask_type, stream))) return rc;
+  if ((rc = bruno_heads_coupling_bwd_cond(x, S(2 * R), Ks, bs, Kt, bt, dy, dld, dx, GS(2 * R), dKs, dbs, dKt, dbt, scratch, N, H,
+                                          W, C, mask_type, label_s, dlabel_s, dlabel_t, stream))) return rc;
   for (int r = R - 1; r >= 0; --r) {
     // g2 = dgrad_c3(g3) * ELU'(u_r);   g3' (or g1) = (dgrad_c2(g2) + g3) * ELU'(block input)
     if ((rc = bruno_conv3x3(2, GS(2 * r + 2), Wp(2 * r + 1), nullptr, 0, S(2 * r + 1), nullptr, GS(2 * r + 1), N, H, W, stream))) return rc;
@@ -65,6 +77,8 @@ int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, i
   // all 2R weight (and bias) gradients in one launch: conv layer l reads its input slab S(l) and gradient GS(l + 1)
   if ((rc = bruno_conv3x3_wgrad_batched(S(0), GS(1), dVr, dbr, 2 * R, N, H, W, stream))) return rc;
   if ((rc = bruno_c1_bwd(x, V1, g1, GS(0), dx, dV1, db1, N, H, W, C, mask_type, stream))) return rc;
+  // label-conditioned layers: gradient of the per-image bias tables = per-image channel sums of the 2R+1 gradient slabs
+  if (dtab && (rc = bruno_slab_image_colsum(gslabs, 2 * R + 1, dtab, dtab_stride, N, H, W, stream))) return rc;
   // weight-norm backward, in place over the raw weight gradients
   if ((rc = bruno_conv_wn_bwd(Vr, gr, dVr, dVr, dgr, 2 * R, 9 * 64, stream))) return rc;
   return bruno_conv_wn_bwd(V1, g1, dV1, dV1, dg1, 1, C, stream);

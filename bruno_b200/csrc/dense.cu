@@ -654,6 +654,16 @@ int bruno_dense_coupling(const float* x, const float* s_pre, const float* t_pre,
   return check_launch("dense_coupling_kernel");
 }
 
+int bruno_dense_coupling_bwd(const float* x, const float* s_pre, const float* dy, const float* dld, float* dx, float* ds_pre,
+                             float* dt_pre, int N, int D, int mask_type, void* stream) {
+  BRUNO_REQUIRE(x && s_pre && dy && dld && dx && ds_pre && dt_pre && N > 0 && D > 0, "bruno_dense_coupling_bwd: bad arguments");
+  BRUNO_REQUIRE(mask_type == BRUNO_MASK_EVEN || mask_type == BRUNO_MASK_ODD, "bruno_dense_coupling_bwd: bad mask");
+  const size_t ND = static_cast<size_t>(N) * D;
+  dense_coupling_bwd_kernel<<<nblk(ND), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, s_pre, dy, dld, dx, ds_pre, dt_pre, ND, D,
+                                                                                      mask_type);
+  return check_launch("dense_coupling_bwd_kernel");
+}
+
 int bruno_coupling_dense_fwd(const float* x, const float* ld_in, float* y, float* ld_out, int N, int D, int U, int mask_type,
                              int inverse, const float* V1, const float* g1, const float* b1, const float* V2,
                              const float* g2, const float* b2, const float* Ks, const float* bs, const float* Kt,

@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(256)
 heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restrict__ hslab, const float* __restrict__ Ks,
                           const float* __restrict__ bs, const float* __restrict__ Kt, const float* __restrict__ bt,
                           const float* __restrict__ dy, const float* __restrict__ dld, float* __restrict__ dx,
-                          uint8_t* __restrict__ gslab, float* __restrict__ partial, SlabGeom g, int C, int mask_type) {
+                          uint8_t* __restrict__ gslab, float* __restrict__ partial, SlabGeom g, int C, int mask_type,
+                          const float* __restrict__ label_s, float* __restrict__ dlabel_s, float* __restrict__ dlabel_t) {
   extern __shared__ float sm[];
   float* ks_s = sm;                        // [64][C]
   float* kt_s = ks_s + 64 * MAXC;
@@ -363,6 +364,13 @@ heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restri
   // leave as ONE partial vector per block (640 blocks x same-address atomics serialised for ~200 us at L2 before)
   for (int n = blockIdx.x; n < g.N; n += gridDim.x) {
   const float dl = dld[n];
+  // label-conditioned heads (nn_extra_nvp_conditional.py:382-388): the per-image terms label_s/t[n, c] enter the
+  // pre-activations, their gradients are the per-image sums of d(s_pre), d(t_pre)
+  float lsum[2 * MAXC];
+  if (dlabel_s) {
+#pragma unroll
+    for (int c = 0; c < 2 * MAXC; ++c) lsum[c] = 0.f;
+  }
   for (int p0 = 0; p0 < HW; p0 += 256) {
     const int p = p0 + threadIdx.x;
     const bool ok = p < HW;
@@ -382,7 +390,7 @@ heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restri
         const float g_y = dy[xo + c];
         float dsp = 0.f, dtp = 0.f, dxv = g_y;
         if (b == 0.f) {
-          float sp = bs_s[c];
+          float sp = bs_s[c] + (label_s ? label_s[n * C + c] : 0.f);
 #pragma unroll
           for (int k = 0; k < 64; ++k) sp = fmaf(h[k], ks_s[k * C + c], sp);
           const float s = tanhf(sp);
@@ -394,6 +402,14 @@ heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restri
         dx[xo + c] = dxv;
         dpre[c] = dsp;
         dpre[C + c] = dtp;
+      }
+      if (dlabel_s) {
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+          if (c < C) {
+            lsum[c] += dpre[c];
+            lsum[MAXC + c] += dpre[C + c];
+          }
       }
       // dh and the gradient w.r.t. the pre-activation of the last residual block
       uint32_t packed[32];
@@ -434,9 +450,56 @@ heads_coupling_bwd_kernel(const float* __restrict__ xin, const uint8_t* __restri
     }
     __syncthreads();
   }
+  if (dlabel_s) {
+    // fixed shuffle tree + fixed-order sum of the 8 warp totals (h_s is free between images)
+#pragma unroll
+    for (int c = 0; c < 2 * MAXC; ++c) {
+      float v = lsum[c];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) h_s[(threadIdx.x >> 5) * (2 * MAXC) + c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * MAXC) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += h_s[w * (2 * MAXC) + threadIdx.x];
+      const int c = threadIdx.x & (MAXC - 1);
+      if (c < C) (threadIdx.x < MAXC ? dlabel_s : dlabel_t)[n * C + c] = t;
+    }
+    __syncthreads();
+  }
   }
   int ai = 0;
   for (int o = threadIdx.x; o < nout; o += 256, ++ai) partial[static_cast<size_t>(blockIdx.x) * nout + o] = acc[ai];
+}
+
+// Per-image channel sums of L stacked gradient slabs: out[n, l*64 + c] = sum over the rows of image n of slab l.
+// (gradient of the label-conditioned per-image bias tables, nn_extra_nvp_conditional.py:422-433.)  grid (N, L).
+__global__ void __launch_bounds__(256)
+slab_image_colsum_kernel(const uint8_t* __restrict__ slabs, size_t slab_stride, SlabGeom g, float* __restrict__ out, int out_stride) {
+  __shared__ float red[32][65];
+  const int n = blockIdx.x, l = blockIdx.y;
+  const uint8_t* slab = slabs + static_cast<size_t>(l) * slab_stride;
+  const int j = threadIdx.x & 7, rg = threadIdx.x >> 3;       // 16-byte chunk (8 channels), row group
+  float a[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = 0.f;
+  for (int q = rg; q < g.IMG; q += 32) {
+    const size_t R = static_cast<size_t>(g.HALO) + static_cast<size_t>(n) * g.IMG + q;
+    float v[8];
+    unpack8f(*reinterpret_cast<const uint4*>(slab + slab_chunk_off(R, j)), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] += v[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rg][j * 8 + e] = a[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+    for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
+    out[static_cast<size_t>(n) * out_stride + l * 64 + threadIdx.x] = t;
+  }
 }
 
 // fixed-order sum of the per-block partials -> dKs, dbs, dKt, dbt (overwritten)
@@ -583,6 +646,23 @@ int bruno_heads_coupling_bwd(const float* x, const void* h_slab, const float* Ks
                              const float* bt, const float* dy, const float* dld, float* dx, void* g_slab, float* dKs,
                              float* dbs, float* dKt, float* dbt, float* scratch, int N, int H, int W, int C, int mask_type,
                              void* stream) {
+  return bruno_heads_coupling_bwd_cond(x, h_slab, Ks, bs, Kt, bt, dy, dld, dx, g_slab, dKs, dbs, dKt, dbt, scratch, N, H, W, C,
+                                       mask_type, nullptr, nullptr, nullptr, stream);
+}
+
+int bruno_slab_image_colsum(const void* slabs, int L, float* out, int out_stride, int N, int H, int W, void* stream) {
+  BRUNO_REQUIRE(slabs && out && L >= 1 && out_stride >= L * 64, "bruno_slab_image_colsum: bad arguments");
+  const SlabGeom g = slab_geom(N, H, W);
+  slab_image_colsum_kernel<<<dim3(N, L), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(slabs), static_cast<size_t>(g.rows) * SLAB_ROW_BYTES, g, out, out_stride);
+  return check_launch("slab_image_colsum_kernel");
+}
+
+int bruno_heads_coupling_bwd_cond(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
+                                  const float* bt, const float* dy, const float* dld, float* dx, void* g_slab, float* dKs,
+                                  float* dbs, float* dKt, float* dbt, float* scratch, int N, int H, int W, int C,
+                                  int mask_type, const float* label_s, float* dlabel_s, float* dlabel_t, void* stream) {
+  BRUNO_REQUIRE((dlabel_s == nullptr) == (dlabel_t == nullptr), "bruno_heads_coupling_bwd: dlabel_s and dlabel_t go together");
   BRUNO_REQUIRE(x && h_slab && Ks && bs && Kt && bt && dy && dld && dx && g_slab && dKs && dbs && dKt && dbt && scratch &&
                     C >= 1 && C <= MAXC, "bruno_heads_coupling_bwd: bad arguments");
   const SlabGeom g = slab_geom(N, H, W);
@@ -596,7 +676,8 @@ int bruno_heads_coupling_bwd(const float* x, const void* h_slab, const float* Ks
   slab_zero_padding_kernel<<<148 * 4, 256, 0, st>>>(static_cast<uint8_t*>(g_slab), g);
   const int nblk = N < HEADS_BWD_BLOCKS ? N : HEADS_BWD_BLOCKS;
   heads_coupling_bwd_kernel<<<nblk, 256, smem, st>>>(x, static_cast<const uint8_t*>(h_slab), Ks, bs, Kt, bt, dy, dld, dx,
-                                                     static_cast<uint8_t*>(g_slab), scratch, g, C, mask_type);
+                                                     static_cast<uint8_t*>(g_slab), scratch, g, C, mask_type, label_s, dlabel_s,
+                                                     dlabel_t);
   int rc = check_launch("heads_coupling_bwd_kernel");
   if (rc) return rc;
   heads_bwd_finalize_kernel<<<ceil_div(65 * 2 * C, 128), 128, 0, st>>>(scratch, nblk, C, dKs, dbs, dKt, dbt);

@@ -4,15 +4,22 @@ config_conditional/m1_shapenet.py).  Layer protocol of the reference (:27-31):
     backward(y, z, y_label) -> (x, z)
 Every weight-normalised conv adds dense_wn(y_label)[:, None, None, :] to its output (:422-433) -- on the GPU that is a
 per-image bias table consumed by the tensor-core conv epilogue; every dense layer is fed concat(dense(y_label), x)
-(:461-471, :350-369).  Round 1 implements the INFERENCE path (NLL evaluation and sampling, forward + inverse); the
-hand-written backward of the conditional layers is not built yet and training raises NotImplementedError.
+(:461-471, :350-369).
+Inference (NLL evaluation, sampling: forward + inverse) runs through the fused kernels.  Training: the conv coupling has a
+hand-written backward (bruno_coupling_conv_bwd_cond: the unconditional backward + per-image gradients of the bias tables
+and head terms); the small label paths and the dense coupling are composed from differentiable primitives whose matrix
+products and coupling arithmetic are C-ABI calls (_MatmulFn, _DenseCouplingElemFn) and whose per-column scale / bias /
+activation are elementwise torch ops on [N, units] tensors.
 """
 import numpy as np
 import torch
 
+import torch.nn.functional as F
+
 from . import _lib
 from .nn_extra_nvp import (MASKS, SLABS, Layer as _BaseLayer, elu, int_shape, _new_like, _pre, _SpaceToDepthFn,  # noqa: F401
                            channel_slice, channel_concat)
+from .slab import alloc_slabs
 
 LEAKY, TANH, ELU, NONE = 2, 3, 1, 0
 
@@ -50,6 +57,133 @@ def dense_wn_apply(x, V, g, b, act=NONE, extra_bias=None):
     return _sgemm(x, V, N, sc, bias.contiguous(), act)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# differentiable primitives of the training path
+# ------------------------------------------------------------------------------------------------------------------
+class _MatmulFn(torch.autograd.Function):
+    """a [M,K] @ b [K,N] and its two gradient products, all through bruno_sgemm."""
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        M, K = a.shape
+        N = b.shape[1]
+        c = _new_like(a, M, N)
+        _lib.call('bruno_sgemm', 0, 0, M, N, K, a, K, b, N, c, N, None, None, 0, 0)
+        ctx.save_for_backward(a, b)
+        return c
+
+    @staticmethod
+    def backward(ctx, dc):
+        a, b = ctx.saved_tensors
+        dc = dc.contiguous()
+        M, K = a.shape
+        N = b.shape[1]
+        da = db = None
+        if ctx.needs_input_grad[0]:                      # da = dc @ b^T   (b is stored [K, N] = op(B)^T stored [N', K'])
+            da = _new_like(a, M, K)
+            _lib.call('bruno_sgemm', 0, 1, M, K, N, dc, N, b, N, da, K, None, None, 0, 0)
+        if ctx.needs_input_grad[1]:                      # db = a^T @ dc   (a is stored [M, K] = op(A)^T stored [K', M'])
+            db = _new_like(a, K, N)
+            _lib.call('bruno_sgemm', 1, 0, K, N, M, a, K, dc, N, db, N, None, None, 0, 0)
+        return da, db
+
+
+def _act(pre, act):
+    if act == ELU:
+        return F.elu(pre)
+    if act == LEAKY:
+        return F.leaky_relu(pre, 0.2)
+    if act == TANH:
+        return torch.tanh(pre)
+    return pre
+
+
+def dense_wn_train(x, V, g, b, act=NONE, extra_bias=None):
+    """dense_wn (cond:437-459), differentiable: (x @ V) * g / ||V|| + b."""
+    pre = _MatmulFn.apply(x, V) * (g / torch.sqrt((V * V).sum(0))) + b
+    if extra_bias is not None:
+        pre = pre + extra_bias
+    return _act(pre, act)
+
+
+def dense_train(x, K, bias=None, act=NONE):
+    pre = _MatmulFn.apply(x, K)
+    if bias is not None:
+        pre = pre + bias
+    return _act(pre, act)
+
+
+def _grad_mode(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+class _CondConvCouplingFn(torch.autograd.Function):
+    """Label-conditioned CouplingLayerConv: forward = bruno_coupling_conv_fwd with per-image bias tables and head terms,
+    backward = bruno_coupling_conv_bwd_cond (gradients of the variables AND of tab / ls / lt, which autograd carries on
+    into the label paths)."""
+    @staticmethod
+    def forward(ctx, x, ld, V1, g1, Vr, gr, Ks, bs, Kt, bt, tab, ls, lt, layer):
+        x, ld, tab, ls, lt = x.contiguous(), ld.contiguous(), tab.contiguous(), ls.contiguous(), lt.contiguous()
+        N, H, W, C = x.shape
+        R, Fl = layer.num_res_blocks, layer.num_filters
+        nl = 2 * R + 1
+        wb = _lib.query('bruno_conv_wpack_bytes')
+        wfwd = torch.empty(2 * R, wb, dtype=torch.uint8, device=x.device)
+        wbwd = torch.empty(2 * R, wb, dtype=torch.uint8, device=x.device)
+        _lib.call('bruno_conv_wn_pack', Vr, gr, wfwd, wbwd, 2 * R)
+        slabs = layer._saved_slabs(N, H, W, x.device)
+        y = torch.empty_like(x)
+        ld_out = torch.empty_like(ld)
+        _lib.call('bruno_coupling_conv_fwd', x, ld, y, ld_out, N, H, W, C, R, layer.mask_id, 0, V1, g1, tab, wfwd,
+                  tab.data_ptr() + 4 * Fl, nl * Fl, Ks, bs, Kt, bt, ls, lt, slabs, int(slabs.shape[0]))
+        ctx.layer, ctx.slabs, ctx.wbwd = layer, slabs, wbwd
+        ctx.save_for_backward(x, V1, g1, Vr, gr, Ks, bs, Kt, bt, ls)
+        return y, ld_out
+
+    @staticmethod
+    def backward(ctx, dy, dld):
+        x, V1, g1, Vr, gr, Ks, bs, Kt, bt, ls = ctx.saved_tensors
+        layer = ctx.layer
+        N, H, W, C = x.shape
+        R, Fl = layer.num_res_blocks, layer.num_filters
+        nl = 2 * R + 1
+        dy, dld = dy.contiguous(), dld.contiguous()
+        gsl = SLABS.get('grad', nl, N, H, W, x.device)
+        dx = torch.empty_like(x)
+        dV1, dg1, db1 = torch.empty_like(V1), torch.empty_like(g1), torch.empty_like(g1)
+        dVr, dgr, dbr = torch.empty_like(Vr), torch.empty_like(gr), torch.empty_like(gr)
+        dKs, dbs, dKt, dbt = torch.empty_like(Ks), torch.empty_like(bs), torch.empty_like(Kt), torch.empty_like(bt)
+        dtab = _new_like(x, N, nl * Fl)
+        dls, dlt = _new_like(x, N, C), _new_like(x, N, C)
+        scratch = _new_like(x, _lib.query('bruno_heads_bwd_scratch_floats', C))
+        _lib.call('bruno_coupling_conv_bwd_cond', x, dy, dld, N, H, W, C, R, layer.mask_id, V1, g1, Vr, gr, ctx.wbwd, Ks, bs,
+                  Kt, bt, ctx.slabs, gsl, scratch, dx, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt, ls, dtab, nl * Fl,
+                  dls, dlt)
+        # the conv biases live inside `tab` (tab = label term + conv bias): db1 / dbr reach them through dtab
+        return dx, dld, dV1, dg1, dVr, dgr, dKs, dbs, dKt, dbt, dtab, dls, dlt, None
+
+
+class _DenseCouplingElemFn(torch.autograd.Function):
+    """The affine coupling itself for the dense layers: y = x b + (1-b)(x e^s + t), ld += sum s, s = tanh(s_pre)(1-b)."""
+    @staticmethod
+    def forward(ctx, x, s_pre, t_pre, ld, mask_id):
+        x, s_pre, t_pre, ld = x.contiguous(), s_pre.contiguous(), t_pre.contiguous(), ld.contiguous()
+        N, D = x.shape
+        y, ld_out = torch.empty_like(x), torch.empty_like(ld)
+        _lib.call('bruno_dense_coupling', x, s_pre, t_pre, ld, y, ld_out, N, D, mask_id, 0)
+        ctx.mask_id = mask_id
+        ctx.save_for_backward(x, s_pre)
+        return y, ld_out
+
+    @staticmethod
+    def backward(ctx, dy, dld):
+        x, s_pre = ctx.saved_tensors
+        N, D = x.shape
+        dx, ds, dt = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        _lib.call('bruno_dense_coupling_bwd', x, s_pre, dy.contiguous(), dld.contiguous(), dx, ds, dt, N, D, ctx.mask_id)
+        return dx, ds, dt, dld, None
+
+
 class Layer(object):                                                        # cond:26-31
     def forward_and_jacobian(self, x, sum_log_det_jacobians, z, y_label):
         raise NotImplementedError(str(type(self)))
@@ -74,6 +208,20 @@ class CouplingLayerConv(Layer):                                             # co
         self.nonlinearity, self.weight_norm = nonlinearity, weight_norm
         self.num_filters, self.num_res_blocks = num_filters, num_res_blocks
         self.V1 = None
+        self._slabs = None
+
+    # trainable variables (the label_h bias of a conv is created with use_bias=False -> not trainable, cond:426)
+    _TRAINABLE = ('V1', 'g1', 'b1', 'Vr', 'gr', 'br', 'LV', 'Lg', 'Ks', 'bs', 'Kt', 'bt', 'LKs', 'LKt')
+
+    def parameters(self):
+        return [] if self.V1 is None else [getattr(self, n) for n in self._TRAINABLE]
+
+    def _saved_slabs(self, N, H, W, device):
+        n = 2 * self.num_res_blocks + 1
+        key = (N, H, W, str(device))
+        if self._slabs is None or self._slabs[0] != key:
+            self._slabs = (key, alloc_slabs(n, N, H, W, device))
+        return self._slabs[1]
 
     def _build(self, C, L, device):
         F, R = self.num_filters, self.num_res_blocks
@@ -89,36 +237,52 @@ class CouplingLayerConv(Layer):                                             # co
         self.Kt, self.bt = torch.zeros(F, C, device=device), torch.zeros(C, device=device)
         self.LKs, self.LKt = _normal(L, C, device=device, std=0.3), _normal(L, C, device=device, std=0.3)
 
-    def named_tf_variables(self, prefix='model/'):
+    def named_tf_variables(self, prefix='model/', grad=False):
+        """(TF variable name, view) pairs; grad=True: the same views of the gradients (None where there is none)."""
         sc = '%s%s/function_s_t_wn/' % (prefix, self.name)
         F, R, C = self.num_filters, self.num_res_blocks, self.V1.shape[0]
         names = ['c1'] + [n for r in range(R) for n in ('c2_%d' % r, 'c3_%d' % r)]
+
+        def T(n):
+            t = getattr(self, n)
+            return t.grad if grad else t
+
+        def V(t, f):
+            return None if t is None else f(t)
         out = []
         for i, nm in enumerate(names):
-            out += [(sc + nm + '/label_h/V', self.LV[:, i * F:(i + 1) * F]), (sc + nm + '/label_h/g', self.Lg[i * F:(i + 1) * F]),
-                    (sc + nm + '/label_h/b', self.Lb[i * F:(i + 1) * F])]
+            out += [(sc + nm + '/label_h/V', V(T('LV'), lambda t: t[:, i * F:(i + 1) * F])),
+                    (sc + nm + '/label_h/g', V(T('Lg'), lambda t: t[i * F:(i + 1) * F])),
+                    (sc + nm + '/label_h/b', V(T('Lb'), lambda t: t[i * F:(i + 1) * F]))]
             if i == 0:
-                out += [(sc + 'c1/conv_h/V', self.V1.view(1, 1, C, F)), (sc + 'c1/conv_h/g', self.g1), (sc + 'c1/conv_h/b', self.b1)]
+                out += [(sc + 'c1/conv_h/V', V(T('V1'), lambda t: t.view(1, 1, C, F))), (sc + 'c1/conv_h/g', T('g1')),
+                        (sc + 'c1/conv_h/b', T('b1'))]
             else:
-                out += [(sc + nm + '/conv_h/V', self.Vr[i - 1]), (sc + nm + '/conv_h/g', self.gr[i - 1]),
-                        (sc + nm + '/conv_h/b', self.br[i - 1])]
-        for nm, K, b, LK in (('conv_out_scale', self.Ks, self.bs, self.LKs), ('conv_out_translation', self.Kt, self.bt, self.LKt)):
-            out += [('%s%s/label_h/kernel' % (sc, nm), LK), ('%s%s/%s/kernel' % (sc, nm, nm), K.view(1, 1, F, C)),
-                    ('%s%s/%s/bias' % (sc, nm, nm), b)]
+                out += [(sc + nm + '/conv_h/V', V(T('Vr'), lambda t: t[i - 1])), (sc + nm + '/conv_h/g', V(T('gr'), lambda t: t[i - 1])),
+                        (sc + nm + '/conv_h/b', V(T('br'), lambda t: t[i - 1]))]
+        for nm, K, b, LK in (('conv_out_scale', 'Ks', 'bs', 'LKs'), ('conv_out_translation', 'Kt', 'bt', 'LKt')):
+            out += [('%s%s/label_h/kernel' % (sc, nm), T(LK)), ('%s%s/%s/kernel' % (sc, nm, nm), V(T(K), lambda t: t.view(1, 1, F, C))),
+                    ('%s%s/%s/bias' % (sc, nm, nm), T(b))]
         return out
 
     def _apply(self, x, ld, y_label, inverse):
-        if torch.is_grad_enabled() and (x.requires_grad or (ld is not None and ld.requires_grad)):
-            raise NotImplementedError('conditional layers: backward (training) is not built in round 1')
         x = x.contiguous()
         N, H, W, C = x.shape
         if self.V1 is None:
             self._build(C, int(y_label.shape[1]), x.device)
         F, R = self.num_filters, self.num_res_blocks
         nl = 2 * R + 1
+        conv_b = torch.cat([self.b1.view(1, F), self.br], 0).reshape(-1)
+        if _grad_mode(x, ld, y_label, *self.parameters()):
+            if inverse:
+                raise RuntimeError('backward through the inverse pass is not implemented (sampling is inference-only)')
+            tab = dense_wn_train(y_label, self.LV, self.Lg, self.Lb, NONE, extra_bias=conv_b)
+            ls = dense_train(y_label, self.LKs)
+            lt = dense_train(y_label, self.LKt)
+            return _CondConvCouplingFn.apply(x, ld, self.V1, self.g1, self.Vr, self.gr, self.Ks, self.bs, self.Kt, self.bt,
+                                             tab, ls, lt, self)
         with torch.no_grad():
             # per-image bias tables [N, (2R+1)*64]: dense_wn(y_label) + b of the conv (cond:422-433)
-            conv_b = torch.cat([self.b1.view(1, F), self.br], 0).reshape(-1)
             tab = dense_wn_apply(y_label, self.LV, self.Lg, self.Lb, NONE, extra_bias=conv_b)
             ls = _sgemm(y_label, self.LKs, C)
             lt = _sgemm(y_label, self.LKt, C)
@@ -167,22 +331,38 @@ class CouplingLayerDense(Layer):                                            # co
             P['%s/%s/bias' % (nm, nm)] = torch.zeros(D, device=device)
         self.P = P
 
-    def named_tf_variables(self, prefix='model/'):
+    def named_tf_variables(self, prefix='model/', grad=False):
         sc = '%s%s/function_s_t_dense_wn/' % (prefix, self.name)
-        return [(sc + k, v) for k, v in self.P.items()]
+        return [(sc + k, (v.grad if grad else v)) for k, v in self.P.items()]
+
+    def parameters(self):
+        return [] if self.P is None else list(self.P.values())      # every variable of the dense path is trainable
 
     def _apply(self, x, ld, y_label, inverse):
-        if torch.is_grad_enabled() and (x.requires_grad or (ld is not None and ld.requires_grad)):
-            raise NotImplementedError('conditional layers: backward (training) is not built in round 1')
         xs = x.shape
         x = x.contiguous()
         N, D = xs[0], int(np.prod(xs[1:]))
         if self.P is None:
             self._build(D, int(y_label.shape[1]), x.device)
         P = self.P
+        idx = torch.arange(D, device=x.device) % 2
+        b = (idx if self.mask_type == 'even' else 1 - idx).to(torch.float32)
+        if _grad_mode(x, ld, y_label, *self.parameters()):
+            if inverse:
+                raise RuntimeError('backward through the inverse pass is not implemented (sampling is inference-only)')
+            x2 = x.reshape(N, D)
+            y = x2 * b
+            for nm in ('d1', 'd2'):
+                h = dense_wn_train(y_label, P[nm + '/label_h/V'], P[nm + '/label_h/g'], P[nm + '/label_h/b'], LEAKY)
+                y = dense_wn_train(torch.cat([h, y], 1), P['%s/%s/V' % (nm, nm)], P['%s/%s/g' % (nm, nm)],
+                                   P['%s/%s/b' % (nm, nm)], ELU)
+            pre = []
+            for nm in ('d_scale', 'd_translate'):
+                h = dense_train(y_label, P[nm + '/label_W1/kernel'], P[nm + '/label_W1/bias'], LEAKY)
+                pre.append(dense_train(torch.cat([h, y], 1), P['%s/%s/kernel' % (nm, nm)], P['%s/%s/bias' % (nm, nm)]))
+            out, ld_out = _DenseCouplingElemFn.apply(x2, pre[0], pre[1], ld, self.mask_id)
+            return out.reshape(xs), ld_out
         with torch.no_grad():
-            idx = torch.arange(D, device=x.device) % 2
-            b = (idx if self.mask_type == 'even' else 1 - idx).to(torch.float32)
             y = x.view(N, D) * b                                                       # x1 = x * mask
             for nm in ('d1', 'd2'):                                                    # cond:461-471
                 h = dense_wn_apply(y_label, P[nm + '/label_h/V'], P[nm + '/label_h/g'], P[nm + '/label_h/b'], LEAKY)

@@ -79,3 +79,41 @@ class SyntheticFewShotIterator(object):
             y = np.repeat(np.asarray(classes)[:, None], self.seq_len, axis=1)
             y[:, -1] = true_cls
             yield x, y, true_cls
+
+
+class SyntheticShapenetIterator(object):
+    """Shape / range contract of the reference's ShapenetConditionalNPDataIterator (utils_conditional.py:100-160) for
+    Conditional BRUNO: x [batch, seq_len, 32, 32, 1] = pixel + U[0,1), y_label [batch, seq_len, 2] = (sin, cos) of a view
+    angle in {0, 10, ..., 350} degrees.  One object prototype per sequence, shifted horizontally with the angle: the
+    frames of a sequence are exchangeable given their labels."""
+    def __init__(self, seq_len, batch_size, obs_shape=(32, 32, 1), rng=None, noise_rng=None, n_batches=None, **kwargs):
+        self.seq_len, self.batch_size, self.obs_shape = seq_len, batch_size, tuple(obs_shape)
+        self.rng = rng if rng is not None else np.random.RandomState(42)
+        self.noise_rng = noise_rng if noise_rng is not None else np.random.RandomState(317070)
+        self.nsamples = n_batches
+
+    def get_observation_size(self):
+        return (self.seq_len,) + self.obs_shape
+
+    def get_label_size(self):
+        return (self.seq_len, 2)
+
+    def _batch(self):
+        B, T = self.batch_size, self.seq_len
+        H, W, C = self.obs_shape
+        proto = (self.rng.uniform(size=(B, H, W, C)) < 0.15).astype(np.float32) * 255.0
+        angles = self.rng.randint(0, 36, size=(B, T)) * 10.0
+        x = np.empty((B, T, H, W, C), dtype=np.float32)
+        for b in range(B):
+            for t in range(T):
+                x[b, t] = np.roll(proto[b], int(angles[b, t] / 360.0 * W), axis=1)
+        x = np.minimum(x + self.noise_rng.uniform(size=x.shape).astype(np.float32), np.float32(255.99998))
+        rad = np.deg2rad(angles)
+        y = np.stack([np.sin(rad), np.cos(rad)], -1).astype(np.float32)
+        return x, y
+
+    def generate(self, **kwargs):
+        i = 0
+        while self.nsamples is None or i < self.nsamples:
+            yield self._batch()
+            i += 1

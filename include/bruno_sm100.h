@@ -189,6 +189,14 @@ int bruno_heads_coupling_bwd(const float* x, const void* h_slab, const float* Ks
                              const float* bt, const float* dy, const float* dld, float* dx, void* g_slab, float* dKs,
                              float* dbs, float* dKt, float* dbt, float* scratch, int N, int H, int W, int C, int mask_type,
                              void* stream);
+/* label-conditioned heads (nn_extra_nvp_conditional.py:372-392): label_s [N,C] is the per-image term of the scale head's
+ * pre-activation; dlabel_s, dlabel_t [N,C] receive the per-image sums of d(s_pre), d(t_pre).  NULLs = the call above. */
+int bruno_heads_coupling_bwd_cond(const float* x, const void* h_slab, const float* Ks, const float* bs, const float* Kt,
+                                  const float* bt, const float* dy, const float* dld, float* dx, void* g_slab, float* dKs,
+                                  float* dbs, float* dKt, float* dbt, float* scratch, int N, int H, int W, int C,
+                                  int mask_type, const float* label_s, float* dlabel_s, float* dlabel_t, void* stream);
+/* out[n, l*64 + c] = sum over the positions of image n of slab l (L stacked slabs): gradient of per-image bias tables */
+int bruno_slab_image_colsum(const void* slabs, int L, float* out, int out_stride, int N, int H, int W, void* stream);
 
 /* The whole CouplingLayerConv in one call.  forward_and_jacobian (nvp:162-174) / backward (:176-187, inverse = 1).
  * Stacked parameters: V1 [C,64], g1, b1 [64] (c1); packed residual weights wfwd [2R] (order c2_0, c3_0, c2_1, ...,
@@ -213,6 +221,16 @@ int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, i
                             const void* wbwd, const float* Ks, const float* bs, const float* Kt, const float* bt,
                             const void* saved_slabs, void* gslabs, float* scratch, float* dx, float* dV1, float* dg1, float* db1,
                             float* dVr, float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt, void* stream);
+/* the same for the label-conditioned coupling (nn_extra_nvp_conditional.py:34-159): label_s as in the forward call;
+ * dtab [N, dtab_stride >= (2R+1)*64] receives the gradient of the per-image bias tables (column block l = conv layer l,
+ * block 0 = c1), dlabel_s / dlabel_t [N,C] the gradients of the per-image head terms. */
+int bruno_coupling_conv_bwd_cond(const float* x, const float* dy, const float* dld, int N, int H, int W, int C, int R,
+                                 int mask_type, const float* V1, const float* g1, const float* Vr, const float* gr,
+                                 const void* wbwd, const float* Ks, const float* bs, const float* Kt, const float* bt,
+                                 const void* saved_slabs, void* gslabs, float* scratch, float* dx, float* dV1, float* dg1,
+                                 float* db1, float* dVr, float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt,
+                                 const float* label_s, float* dtab, int dtab_stride, float* dlabel_s, float* dlabel_t,
+                                 void* stream);
 
 /* --- dense coupling layer, CouplingLayerDense (nvp:190-274) with dense_wn (:408-432), fp32 ---------------------- */
 size_t bruno_coupling_dense_ws_floats(int N, int D, int U);
@@ -232,6 +250,10 @@ int bruno_dense_wn_scale(const float* V, const float* g, float* sc, float* inv_n
 /* the affine coupling + log-det of CouplingLayerDense given the two head outputs s_pre, t_pre [N,D] (nvp:168-186) */
 int bruno_dense_coupling(const float* x, const float* s_pre, const float* t_pre, const float* ld_in, float* y, float* ld_out,
                          int N, int D, int mask_type, int inverse, void* stream);
+/* backward of the forward coupling above: dx = dy (b + (1-b) e^s) (direct part only; the s/t network adds its own through
+ * ds_pre, dt_pre), ds_pre = (dy (1-b) x e^s + dld[n]) (1 - tanh^2), dt_pre = dy (1-b). */
+int bruno_dense_coupling_bwd(const float* x, const float* s_pre, const float* dy, const float* dld, float* dx, float* ds_pre,
+                             float* dt_pre, int N, int D, int mask_type, void* stream);
 /* debug / A-B timing: which kernel the dense-path GEMMs (bruno_sgemm and the dense couplings) use when the operands are
  * 16-byte aligned: 0 = CUDA-core SGEMM (strict fp32 FFMA), 1 = tcgen05 3xTF32 split (fp32-accurate, default).
  * variant < 0 queries. */

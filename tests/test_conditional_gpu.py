@@ -3,6 +3,8 @@ NLL with n_context, and sampling through the inverse flow, against the CPU oracl
 Tolerance: same stated bf16 bound as the unconditional conv configs (tests/test_flow_gpu.py)."""
 import importlib
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -61,3 +63,126 @@ def test_conditional_sampling_matches_oracle():
     err = (xs.double().cpu() - xs_o).abs().max().item()
     print('\n[m1_shapenet] sampling: max |x_s - oracle| = %.3e (x in [0,1])' % err)
     assert err <= 0.2       # bf16 s/t nets in the inverse pass; mid-range pixels sit on the steep part of the sigmoid
+
+
+def _oracle_grads(spec, P, x, yl, n_context, names):
+    Pg = {k: (v.clone().requires_grad_(True) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in P.items()}
+    lp, _ = OC.build_model(spec, Pg, x, yl, n_context=n_context)
+    loss = -lp.mean()
+    keys = [k for k in names if k in Pg and torch.is_tensor(Pg[k]) and Pg[k].requires_grad]
+    grads = torch.autograd.grad(loss, [Pg[k] for k in keys], allow_unused=True)
+    return loss.item(), dict(zip(keys, grads))
+
+
+@pytest.mark.parametrize('n_context', [1, 0])
+def test_conditional_training_gradients_match_oracle(n_context):
+    """Training graph of Conditional BRUNO: loss and the gradient of every trainable variable (label paths included)
+    against autograd on the oracle.  Same stated bf16 bounds as the unconditional conv configs."""
+    B, T = 2, 3
+    spec, P, x, yl, cfg, xg, ylg = setup(B, T, seed=3, n_context=n_context)
+    cfg.set_trainable(True)
+    try:
+        lp = cfg.build_model(xg, ylg)[0]
+        loss = cfg.loss(lp)
+        loss.backward()
+        named = cfg.named_tf_gradients()
+        loss_o, g_o = _oracle_grads(spec, P, x, yl, n_context, [n for n, _ in named])
+        assert abs(loss.item() - loss_o) <= 6e-3 * abs(loss_o)
+        worst, checked = (0.0, None), 0
+        gmax = max(v.abs().max().item() for v in g_o.values() if v is not None)
+        for name, g in named:
+            go = g_o.get(name)
+            if go is None:
+                continue
+            if name.endswith('label_h/b') and '/function_s_t_wn/' in name:
+                assert g is None                  # created with use_bias=False: exists, is added, is NOT trained (cond:426)
+                continue
+            assert g is not None, name
+            gg = g.detach().double().cpu().reshape(go.shape)
+            # (c1 with one input channel: W = g sign(V), the true gradient w.r.t. V is 0 -> absolute floor)
+            scale = max(go.abs().max().item(), 1e-5 * gmax)
+            err = (gg - go).abs().max().item() / scale
+            checked += 1
+            if err > worst[0]:
+                worst = (err, name)
+            assert err <= 1e-1, (name, err, scale)
+        print('\n[m1_shapenet n_context=%d] loss %.6f (oracle %.6f); %d variables, worst gradient error %.3e of max at %s' % (
+            n_context, loss.item(), loss_o, checked, worst[0], worst[1]))
+        assert checked > 300
+    finally:
+        cfg.set_trainable(False)
+
+
+def test_conditional_data_dependent_init_matches_oracle():
+    """build_model(init=True): g and b of every weight-normalised conv / dense (conv_h AND label_h) after the init pass."""
+    B, T = 2, 3
+    spec = OC.CondSpec()
+    P = OC.init_params(spec, seed=11, dtype=torch.float64)
+    x, yl = OC.synthetic_batch(spec, B, T, seed=12)
+    x, yl = x.float().double(), yl.float().double()
+    P = O.cast_params(O.cast_params(P, torch.float32), torch.float64)
+    from bruno_b200.config_conditional import defaults
+    defaults.n_context, defaults.seq_len = 1, T
+    cfg = importlib.reload(importlib.import_module('bruno_b200.config_conditional.m1_shapenet'))
+    xg, ylg = x.float().cuda(), yl.float().cuda()
+    cfg.build_model(xg[:1], ylg[:1])
+    cfg.load_tf_variables(P)
+    cfg.build_model(xg, ylg, init=True)
+    OC.data_dependent_init(spec, P, x, yl, n_context=1)
+    worst, worst_dense = (0.0, None), (0.0, None)
+    n = 0
+    for name, view in cfg.named_tf_variables():
+        if not (name.endswith('/g') or name.endswith('/b')):
+            continue
+        ref = P[name].double()
+        got = view.detach().double().cpu().reshape(ref.shape)
+        assert torch.isfinite(got).all(), name
+        err = (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
+        n += 1
+        if 'function_s_t_dense_wn' in name:
+            worst_dense = max(worst_dense, (err, name))
+        else:
+            worst = max(worst, (err, name))
+    print('\n[m1_shapenet] data-dependent init: %d g/b tensors; conv couplings worst relative error %.3e at %s; dense couplings '
+          '(fed by the un-normalised bf16 conv stack of the init pass, 6 samples) %.3e' % (n, worst[0], worst[1], worst_dense[0]))
+    assert n > 200
+    # the init pass runs the 14 conv couplings UN-normalised (old g = 1, b = 0): activations grow layer by layer and the
+    # bf16 rounding noise with them -- 4e-3 at the first scale, 1e-1 at the last
+    assert worst[0] <= 0.25
+    # the dense couplings see that amplified noise through moments over B*T = 6 samples: their init is checked exactly on
+    # identical inputs below
+
+
+def test_conditional_dense_init_exact_on_identical_inputs():
+    from bruno_b200 import nn_extra_nvp_conditional as C, ddinit
+    torch.manual_seed(0)
+    N, D, L = 6, 1024, 32
+    layer = C.CouplingLayerDense('even', name='even_0', n_units=256)
+    x = torch.randn(N, 4, 4, 64, device='cuda')
+    yl = torch.randn(N, L, device='cuda')
+    layer._build(D, L, x.device)
+    for k, v in layer.P.items():
+        if k.endswith('kernel'):
+            v.normal_(0, 0.05)
+    P = {n: v.detach().double().cpu().clone() for n, v in layer.named_tf_variables(prefix='')}
+    ddinit.cond_dense_coupling_init(layer, x, torch.zeros(N, device='cuda'), yl)
+    mask = (torch.arange(D) % 2).double().view(4, 4, 64).expand(N, 4, 4, 64)
+    OC.s_t_dense(x.double().cpu() * mask, mask, yl.double().cpu(), P, 'even_0', True)
+    for n, v in layer.named_tf_variables(prefix=''):
+        if n.endswith('/g') or n.endswith('/b'):
+            ref = P[n]
+            assert (v.detach().double().cpu() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item(), n
+
+
+def test_conditional_train_driver_runs(tmp_path):
+    """config_conditional/train.py end to end: init pass at iteration 0, then RMSProp steps through the flat buffers."""
+    from bruno_b200.config_conditional import defaults, train
+    defaults.n_context, defaults.seq_len = 1, 4
+    importlib.reload(importlib.import_module('bruno_b200.config_conditional.m1_shapenet'))
+    trainer, avg = train.main(['--config_name', 'm1_shapenet', '--max_iter', '7', '--print_every', '2',
+                               '--metadata_dir', str(tmp_path)])
+    assert trainer.opt_steps == 6 and len(avg) == 3
+    assert all(np.isfinite(a) for a in avg)
+    assert avg[-1] < avg[0]                      # the loss of the untrained flow drops within a few RMSProp steps
+    import os
+    assert any(f == 'params.pt' for _, _, fs in os.walk(str(tmp_path)) for f in fs)
