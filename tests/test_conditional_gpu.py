@@ -186,3 +186,11 @@ def test_conditional_train_driver_runs(tmp_path):
     assert avg[-1] < avg[0]                      # the loss of the untrained flow drops within a few RMSProp steps
     import os
     assert any(f == 'params.pt' for _, _, fs in os.walk(str(tmp_path)) for f in fs)
+    # the evaluation and sampling drivers restore that checkpoint
+    from bruno_b200.config_conditional import test_nll, test_samples
+    test, tr = test_nll.main(['--config_name', 'm1_shapenet', '--seq_len', '4', '--n_context', '1', '--n_batches', '2',
+                              '--metadata_dir', str(tmp_path)])
+    assert np.isfinite(test[0]) and np.isfinite(tr[0])
+    out = test_samples.main(['--config_name', 'm1_shapenet', '--seq_len', '4', '--n_context', '1', '--n_samples', '1',
+                             '--metadata_dir', str(tmp_path)])
+    assert out[0]['samples'].shape[-3:] == (32, 32, 1)
