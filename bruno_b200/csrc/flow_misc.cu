@@ -25,6 +25,13 @@ __device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
   return s;
 }
 
+// a / d for 0 <= a < 2^22 through one FMUL + F2I (exact: (a + 0.5) / d is at least 0.5 / d away from an integer and the
+// float product is off by less than that); a runtime-divisor integer division costs ~25 instructions, and the
+// row -> (image, line, column) decomposition needs three of them per 16 bytes moved.
+__device__ __forceinline__ int fdiv22(int a, int d, float inv_d, bool small) {
+  return small ? static_cast<int>((static_cast<float>(a) + 0.5f) * inv_d) : a / d;
+}
+
 __device__ __forceinline__ float mask_b(int mask_type, int y, int x, int c, int C) {
   // nn_extra_nvp.py:143-160.  b = 1: pass-through / conditioning half.
   switch (mask_type) {
@@ -150,14 +157,17 @@ c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
   if (threadIdx.x < 64) b_s[threadIdx.x] = bias_img_stride ? 0.f : b1[threadIdx.x];
   c1_weights_to_smem(V1, g1, C, w_s);
   const int total = g.NT * TILE_M * 8;
+  const bool small = g.NT * TILE_M < (1 << 22);
+  const float inv_img = 1.0f / static_cast<float>(g.IMG), inv_p = 1.0f / static_cast<float>(g.P);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int data_row = i >> 3, j = i & 7;
     const size_t R = static_cast<size_t>(g.HALO) + data_row;
     uint4 packed = make_uint4(0, 0, 0, 0);
     float outf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (slab_row_is_pixel(data_row, g)) {
-      const int n = data_row / g.IMG, q = data_row % g.IMG;
-      const int yy = q / g.P - 1, xx = q % g.P - 1;
+    const int n = fdiv22(data_row, g.IMG, inv_img, small), q = data_row - n * g.IMG;
+    const int y1 = fdiv22(q, g.P, inv_p, small);
+    const int yy = y1 - 1, xx = q - y1 * g.P - 1;
+    if (data_row < g.data_rows && yy >= 0 && xx >= 0) {
       const float* xp = x + ((static_cast<size_t>(n) * g.H + yy) * g.W + xx) * C;
       float acc[8];
 #pragma unroll
@@ -253,6 +263,95 @@ c1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
     const int co = o & 63, c = o >> 6;
     if (c < C) atomicAdd(dW1 + c * 64 + co, acc[ai]);
     else atomicAdd(db1 + co, acc[ai]);
+  }
+}
+
+// c1 backward for C <= 4, eight lanes per pixel (lane j owns the 16-byte chunk j of the gradient slab row): coalesced
+// 512-byte warp reads, dx through 8-channel partials + xor-shuffles, dW1 / db1 in registers over all pixels of the thread
+// and ONE fixed-order block reduction + atomics at the end (see heads_coupling_bwd8_kernel).
+template <int C>
+__global__ void __launch_bounds__(256, 2)
+c1_bwd8_kernel(const float* __restrict__ x, const float* __restrict__ V1, const float* __restrict__ g1w,
+               const uint8_t* __restrict__ gslab, float* __restrict__ dx, float* __restrict__ dW1, float* __restrict__ db1,
+               SlabGeom g, int mask_type) {
+  __shared__ float w_s[MAXC * 64];
+  __shared__ float red[8][64][C + 2];         // [warp][channel][c or bias]
+  c1_weights_to_smem(V1, g1w, C, w_s);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = lane & 7;
+  float w[C][8];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[c][e] = w_s[c * 64 + 8 * j + e];
+  float acc[C + 1][8];
+#pragma unroll
+  for (int c = 0; c <= C; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+  const int HW = g.H * g.W;
+  const int NP = g.N * HW;
+  const int ngroups = gridDim.x * 32;
+  const bool small = NP < (1 << 22);
+  const float inv_hw = 1.0f / static_cast<float>(HW), inv_w = 1.0f / static_cast<float>(g.W);
+  // the inputs of the NEXT pixel are fetched before the current one is processed: with one 16-byte load per thread and
+  // iteration the kernel sat at ~1 TB/s (latency x 16 warps / SM)
+  struct In { uint4 gq; float xv[C]; int yy, xx, q; };
+  auto fetch = [&](int q) {
+    In r;
+    r.q = q;
+    const int n = fdiv22(q, HW, inv_hw, small), p = q - n * HW;
+    r.yy = fdiv22(p, g.W, inv_w, small);
+    r.xx = p - r.yy * g.W;
+    const size_t R = static_cast<size_t>(g.HALO) + static_cast<size_t>(n) * g.IMG + (r.yy + 1) * g.P + (r.xx + 1);
+    r.gq = *reinterpret_cast<const uint4*>(gslab + slab_chunk_off(R, j));
+#pragma unroll
+    for (int c = 0; c < C; ++c) r.xv[c] = x[static_cast<size_t>(q) * C + c];
+    return r;
+  };
+  int q0 = (blockIdx.x * 256 + threadIdx.x) >> 3;
+  In cur;
+  if (q0 < NP) cur = fetch(q0);
+  for (int q = q0; q < NP; q += ngroups) {
+    In nxt = cur;
+    if (q + ngroups < NP) nxt = fetch(q + ngroups);
+    float gv[8];
+    unpack8f(cur.gq, gv);
+    const size_t xo = static_cast<size_t>(q) * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float b = mask_b(mask_type, cur.yy, cur.xx, c, C);
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(gv[e], w[c][e], d);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      const float xm = cur.xv[c] * b;
+      if (j == c) dx[xo + c] += b * d;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[c][e] = fmaf(xm, gv[e], acc[c][e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[C][e] += gv[e];
+    cur = nxt;
+  }
+#pragma unroll
+  for (int c = 0; c <= C; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = acc[c][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 8) red[warp][8 * j + e][c] = v;
+    }
+  __syncthreads();
+  for (int o = threadIdx.x; o < (C + 1) * 64; o += 256) {
+    const int co = o & 63, c = o >> 6;
+    float t = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) t += red[wq][co][c];
+    if (c < C) atomicAdd(dW1 + c * 64 + co, t);
+    else atomicAdd(db1 + co, t);
   }
 }
 
@@ -502,6 +601,162 @@ slab_image_colsum_kernel(const uint8_t* __restrict__ slabs, size_t slab_stride, 
   }
 }
 
+// The same backward for C <= 4 (all layers of bn2 / en2; the coupling at C channels has 2C head outputs), eight lanes per
+// pixel: lane j of a pixel's group owns the 16-byte chunk j (8 channels) of the slab row.
+//   * a warp instruction reads / writes 4 consecutive rows = 512 contiguous bytes (thread-per-pixel touched 32 lines
+//     with 16 bytes each: LSU-bound at ~10 us per 256 pixels);
+//   * the head dot products are 8-channel partials + three xor-shuffles;
+//   * the head-weight gradients dK[k][c2] = sum_p h[p][k] d[p][c2] stay in REGISTERS (8 channels x 2C per thread) over
+//     all pixels of the thread: the shared-memory transpose + dot-product phase of the generic kernel (19 us of LDS per
+//     14x14 layer) is gone.  One fixed-order reduction per block at the end -> `partial`, same layout as above.
+template <int C>
+__global__ void __launch_bounds__(256, 2)
+heads_coupling_bwd8_kernel(const float* __restrict__ xin, const uint8_t* __restrict__ hslab, const float* __restrict__ Ks,
+                           const float* __restrict__ bs, const float* __restrict__ Kt, const float* __restrict__ dy,
+                           const float* __restrict__ dld, float* __restrict__ dx, uint8_t* __restrict__ gslab,
+                           float* __restrict__ partial, SlabGeom g, int mask_type, const float* __restrict__ label_s,
+                           float* __restrict__ dlabel_acc /* [N, 2C], zeroed, or null */) {
+  __shared__ float red[8][64][2 * C + 1];   // per-warp sums: [warp][channel][c2]; column 2C unused (bank spread)
+  __shared__ float redb[8][2 * C];
+  // head kernels by chunk: [j][e][c] with an odd pitch per chunk (the 8 chunk lanes of a pixel hit 8 different banks)
+  constexpr int KP = 8 * C + 1;
+  __shared__ float ks_s[8 * KP], kt_s[8 * KP];
+  for (int i = threadIdx.x; i < 64 * C; i += 256) {
+    const int k = i / C, c = i % C;
+    ks_s[(k >> 3) * KP + (k & 7) * C + c] = Ks[i];
+    kt_s[(k >> 3) * KP + (k & 7) * C + c] = Kt[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = lane & 7;                     // chunk = channels 8j .. 8j+7
+  const float* ks = ks_s + j * KP;            // ks[e * C + c]
+  const float* kt = kt_s + j * KP;
+  float bsv[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) bsv[c] = bs[c];
+  float acc[8][2 * C], accb[2 * C];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int c = 0; c < 2 * C; ++c) acc[e][c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 2 * C; ++c) accb[c] = 0.f;
+
+  const int HW = g.H * g.W;
+  const int NP = g.N * HW;                    // < 2^31 (the slab geometry already requires it)
+  const int ngroups = gridDim.x * 32;
+  const bool small = NP < (1 << 22);
+  const float inv_hw = 1.0f / static_cast<float>(HW), inv_w = 1.0f / static_cast<float>(g.W);
+  // inputs of the NEXT pixel are fetched before the current one is processed (see c1_bwd8_kernel)
+  struct In { uint4 hq; float gy[C], xv[C], ls[C], dl; int n, yy, xx; size_t R; };
+  auto fetch = [&](int q) {
+    In r;
+    r.n = fdiv22(q, HW, inv_hw, small);
+    const int p = q - r.n * HW;
+    r.yy = fdiv22(p, g.W, inv_w, small);
+    r.xx = p - r.yy * g.W;
+    r.R = static_cast<size_t>(g.HALO) + static_cast<size_t>(r.n) * g.IMG + (r.yy + 1) * g.P + (r.xx + 1);
+    r.hq = *reinterpret_cast<const uint4*>(hslab + slab_chunk_off(r.R, j));
+    r.dl = dld[r.n];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      r.gy[c] = dy[static_cast<size_t>(q) * C + c];
+      r.xv[c] = xin[static_cast<size_t>(q) * C + c];
+      r.ls[c] = label_s ? label_s[r.n * C + c] : 0.f;
+    }
+    return r;
+  };
+  const int q0 = (blockIdx.x * 256 + threadIdx.x) >> 3;
+  In cur;
+  if (q0 < NP) cur = fetch(q0);
+  for (int q = q0; q < NP; q += ngroups) {
+    In nxt = cur;
+    if (q + ngroups < NP) nxt = fetch(q + ngroups);
+    const int n = cur.n, yy = cur.yy, xx = cur.xx;
+    const size_t R = cur.R;
+    float h[8];
+    unpack8f(cur.hq, h);
+    const size_t xo = static_cast<size_t>(q) * C;
+    const float dl = cur.dl;
+    // scale-head pre-activation: 8-channel partial, summed over the 8 lanes of the pixel
+    float sp[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float v = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v = fmaf(h[e], ks[e * C + c], v);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      sp[c] = v + bsv[c] + cur.ls[c];
+    }
+    float d[2 * C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float b = mask_b(mask_type, yy, xx, c, C);
+      const float g_y = cur.gy[c];
+      float dsp = 0.f, dtp = 0.f, dxv = g_y;
+      if (b == 0.f) {
+        const float s_ = tanhf(sp[c]);
+        const float es = expf(s_);
+        dxv = g_y * es;
+        dtp = g_y;
+        dsp = (g_y * cur.xv[c] * es + dl) * (1.f - s_ * s_);
+      }
+      if (j == c) dx[xo + c] = dxv;
+      d[c] = dsp;
+      d[C + c] = dtp;
+    }
+    if (dlabel_acc && j == 0) {
+#pragma unroll
+      for (int c = 0; c < 2 * C; ++c) atomicAdd(dlabel_acc + static_cast<size_t>(n) * 2 * C + c, d[c]);
+    }
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) v = fmaf(d[c], ks[e * C + c], fmaf(d[C + c], kt[e * C + c], v));
+      o[e] = v * elu_grad_from_out(h[e]);
+#pragma unroll
+      for (int c = 0; c < 2 * C; ++c) acc[e][c] = fmaf(h[e], d[c], acc[e][c]);
+    }
+    if (j == 0) {
+#pragma unroll
+      for (int c = 0; c < 2 * C; ++c) accb[c] += d[c];
+    }
+    *reinterpret_cast<uint4*>(gslab + slab_chunk_off(R, j)) =
+        make_uint4(pack2f(o[0], o[1]), pack2f(o[2], o[3]), pack2f(o[4], o[5]), pack2f(o[6], o[7]));
+    cur = nxt;
+  }
+  // block reduction in a fixed order: the 4 pixel groups of a warp (xor 8, 16), then the 8 warps through shared memory
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int c = 0; c < 2 * C; ++c) {
+      float v = acc[e][c];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 8) red[warp][8 * j + e][c] = v;
+    }
+#pragma unroll
+  for (int c = 0; c < 2 * C; ++c) {
+    float v = accb[c];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (lane == 0) redb[warp][c] = v;
+  }
+  __syncthreads();
+  const int nout = 65 * 2 * C;
+  for (int o = threadIdx.x; o < nout; o += 256) {
+    const int k = o % 65, c2 = o / 65;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += k < 64 ? red[w][k][c2] : redb[w][c2];
+    partial[static_cast<size_t>(blockIdx.x) * nout + o] = t;
+  }
+}
+
 // fixed-order sum of the per-block partials -> dKs, dbs, dKt, dbt (overwritten)
 __global__ void heads_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dKs,
                                           float* __restrict__ dbs, float* __restrict__ dKt, float* __restrict__ dbt) {
@@ -616,6 +871,16 @@ int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g
     cudaFuncSetAttribute(c1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = true;
   }
+  if (C <= 4) {
+    cudaStream_t st8 = static_cast<cudaStream_t>(stream);
+    const SlabGeom g8 = slab_geom(N, H, W);
+    const uint8_t* gs8 = static_cast<const uint8_t*>(g_slab);
+    if (C == 1) c1_bwd8_kernel<1><<<296, 256, 0, st8>>>(x, V1, g1, gs8, dx, dW1, db1, g8, mask_type);
+    else if (C == 2) c1_bwd8_kernel<2><<<296, 256, 0, st8>>>(x, V1, g1, gs8, dx, dW1, db1, g8, mask_type);
+    else if (C == 3) c1_bwd8_kernel<3><<<296, 256, 0, st8>>>(x, V1, g1, gs8, dx, dW1, db1, g8, mask_type);
+    else c1_bwd8_kernel<4><<<296, 256, 0, st8>>>(x, V1, g1, gs8, dx, dW1, db1, g8, mask_type);
+    return check_launch("c1_bwd8_kernel");
+  }
   c1_bwd_kernel<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, V1, g1, static_cast<const uint8_t*>(g_slab), dx, dW1,
                                                                       db1, g, C, mask_type);
   return check_launch("c1_bwd_kernel");
@@ -674,6 +939,31 @@ int bruno_heads_coupling_bwd_cond(const float* x, const void* h_slab, const floa
     configured = true;
   }
   slab_zero_padding_kernel<<<148 * 4, 256, 0, st>>>(static_cast<uint8_t*>(g_slab), g);
+  if (C <= 4 && !dlabel_s) {
+    // eight lanes per pixel, head-weight gradients in registers (see heads_coupling_bwd8_kernel)
+    int nb = 0;
+#define HB8(CC)                                                                                                           \
+  do {                                                                                                                    \
+    static int per_sm = 0;                                                                                                \
+    if (per_sm == 0) {                                                                                                    \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heads_coupling_bwd8_kernel<CC>, 256, 0);                     \
+      if (per_sm < 1) per_sm = 1;                                                                                         \
+    }                                                                                                                     \
+    nb = 148 * per_sm < HEADS_BWD_BLOCKS ? 148 * per_sm : HEADS_BWD_BLOCKS;                                               \
+    heads_coupling_bwd8_kernel<CC><<<nb, 256, 0, st>>>(x, static_cast<const uint8_t*>(h_slab), Ks, bs, Kt, dy, dld, dx,   \
+                                                       static_cast<uint8_t*>(g_slab), scratch, g, mask_type, label_s,     \
+                                                       nullptr);                                                          \
+  } while (0)
+    if (C == 1) HB8(1);
+    else if (C == 2) HB8(2);
+    else if (C == 3) HB8(3);
+    else HB8(4);
+#undef HB8
+    int rc8 = check_launch("heads_coupling_bwd8_kernel");
+    if (rc8) return rc8;
+    heads_bwd_finalize_kernel<<<ceil_div(65 * 2 * C, 128), 128, 0, st>>>(scratch, nb, C, dKs, dbs, dKt, dbt);
+    return check_launch("heads_bwd_finalize_kernel");
+  }
   const int nblk = N < HEADS_BWD_BLOCKS ? N : HEADS_BWD_BLOCKS;
   heads_coupling_bwd_kernel<<<nblk, 256, smem, st>>>(x, static_cast<const uint8_t*>(h_slab), Ks, bs, Kt, bt, dy, dld, dx,
                                                      static_cast<uint8_t*>(g_slab), scratch, g, C, mask_type, label_s, dlabel_s,
