@@ -758,21 +758,20 @@ heads_coupling_bwd8_kernel(const float* __restrict__ xin, const uint8_t* __restr
 }
 
 // fixed-order sum of the per-block partials -> dKs, dbs, dKt, dbt (overwritten)
-__global__ void heads_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dKs,
-                                          float* __restrict__ dbs, float* __restrict__ dKt, float* __restrict__ dbt) {
+__global__ void __launch_bounds__(256)
+heads_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dKs,
+                          float* __restrict__ dbs, float* __restrict__ dKt, float* __restrict__ dbt) {
+  // one warp per output: lane l adds blocks l, l+32, ... in order, then a fixed xor-shuffle tree (deterministic; a single
+  // thread per output walked the ~300 partials as 74 dependent L2 round trips = 15 us)
   const int nout = 65 * 2 * C;
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (o >= nout) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // fixed order, four independent chains
-  int b = 0;
-  for (; b + 3 < nblk; b += 4) {
-    s0 += partial[static_cast<size_t>(b) * nout + o];
-    s1 += partial[static_cast<size_t>(b + 1) * nout + o];
-    s2 += partial[static_cast<size_t>(b + 2) * nout + o];
-    s3 += partial[static_cast<size_t>(b + 3) * nout + o];
-  }
-  for (; b < nblk; ++b) s0 += partial[static_cast<size_t>(b) * nout + o];
-  const float s = (s0 + s1) + (s2 + s3);
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int b = lane; b < nblk; b += 32) s += partial[static_cast<size_t>(b) * nout + o];
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (lane != 0) return;
   const int k = o % 65, c2 = o / 65;
   const bool is_t = c2 >= C;
   const int c = is_t ? c2 - C : c2;
@@ -961,7 +960,7 @@ int bruno_heads_coupling_bwd_cond(const float* x, const void* h_slab, const floa
 #undef HB8
     int rc8 = check_launch("heads_coupling_bwd8_kernel");
     if (rc8) return rc8;
-    heads_bwd_finalize_kernel<<<ceil_div(65 * 2 * C, 128), 128, 0, st>>>(scratch, nb, C, dKs, dbs, dKt, dbt);
+    heads_bwd_finalize_kernel<<<ceil_div(65 * 2 * C, 8), 256, 0, st>>>(scratch, nb, C, dKs, dbs, dKt, dbt);
     return check_launch("heads_bwd_finalize_kernel");
   }
   const int nblk = N < HEADS_BWD_BLOCKS ? N : HEADS_BWD_BLOCKS;
@@ -970,7 +969,7 @@ int bruno_heads_coupling_bwd_cond(const float* x, const void* h_slab, const floa
                                                      dlabel_t);
   int rc = check_launch("heads_coupling_bwd_kernel");
   if (rc) return rc;
-  heads_bwd_finalize_kernel<<<ceil_div(65 * 2 * C, 128), 128, 0, st>>>(scratch, nblk, C, dKs, dbs, dKt, dbt);
+  heads_bwd_finalize_kernel<<<ceil_div(65 * 2 * C, 8), 256, 0, st>>>(scratch, nblk, C, dKs, dbs, dKt, dbt);
   return check_launch("heads_bwd_finalize_kernel");
 }
 
