@@ -433,7 +433,9 @@ int launch_tf32(int M, int N, int K, const float* A, int lda, const float* B, in
   *taken = 1;
   // 64-column tiles while 128-column tiles would leave most SMs without work
   const int tiles128 = ceil_div(N, 128) * ceil_div(M, TG_BM);
-  if (tiles128 * 2 <= sms || N <= 64)
+  static const char* force_bn = getenv("BRUNO_TF32_BN");
+  const bool want64 = force_bn ? atoi(force_bn) == 64 : (tiles128 * 2 <= sms || N <= 64);
+  if (want64)
     return launch_tf32_bn<TA, TB, 64>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st);
   return launch_tf32_bn<TA, TB, 128>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st);
 }
