@@ -406,20 +406,30 @@ __device__ __forceinline__ float col_block_reduce(float v, float (*sh)[33]) {
 }
 
 // sc[j] = g[j] / ||V[:, j]||_2   (tf.norm, no epsilon: nvp:419);  inv_nrm[j] = 1 / ||V[:, j]||
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 dense_wn_scale_kernel(const float* __restrict__ V, const float* __restrict__ g, float* __restrict__ sc,
                       float* __restrict__ inv_nrm, int K, int N) {
-  __shared__ float sh[8][33];
-  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
-  float n2 = 0.f;
-  if (j < N)
-    for (int k = threadIdx.x >> 5; k < K; k += 8) {
-      const float t = V[static_cast<size_t>(k) * N + j];
-      n2 = fmaf(t, t, n2);
+  // 32 columns x 32 row groups per block, four loads in flight per thread, fixed-order combine
+  __shared__ float sh[32][33];
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + c;
+  float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+  if (j < N) {
+    for (int k = rg; k < K; k += 128) {
+      const float t0 = V[static_cast<size_t>(k) * N + j];
+      const float t1 = k + 32 < K ? V[static_cast<size_t>(k + 32) * N + j] : 0.f;
+      const float t2 = k + 64 < K ? V[static_cast<size_t>(k + 64) * N + j] : 0.f;
+      const float t3 = k + 96 < K ? V[static_cast<size_t>(k + 96) * N + j] : 0.f;
+      n0 = fmaf(t0, t0, n0); n1 = fmaf(t1, t1, n1); n2 = fmaf(t2, t2, n2); n3 = fmaf(t3, t3, n3);
     }
-  n2 = col_block_reduce(n2, sh);
+  }
+  sh[rg][c] = (n0 + n1) + (n2 + n3);
+  __syncthreads();
   if (j < N && threadIdx.x < 32) {
-    const float inv = rsqrtf(n2);
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += sh[r][c];
+    const float inv = rsqrtf(t);
     sc[j] = g[j] * inv;
     if (inv_nrm) inv_nrm[j] = inv;
   }
@@ -642,7 +652,7 @@ int bruno_sgemm(int transA, int transB, int M, int N, int K, const float* A, int
 
 int bruno_dense_wn_scale(const float* V, const float* g, float* sc, float* inv_nrm, int K, int N, void* stream) {
   BRUNO_REQUIRE(V && g && sc && K > 0 && N > 0, "bruno_dense_wn_scale: bad arguments");
-  dense_wn_scale_kernel<<<ceil_div(N, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(V, g, sc, inv_nrm, K, N);
+  dense_wn_scale_kernel<<<ceil_div(N, 32), 1024, 0, static_cast<cudaStream_t>(stream)>>>(V, g, sc, inv_nrm, K, N);
   return check_launch("dense_wn_scale_kernel");
 }
 
@@ -675,8 +685,8 @@ int bruno_coupling_dense_fwd(const float* x, const float* ld_in, float* y, float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DenseWs w = carve(ws, N, D, U);
   const size_t ND = static_cast<size_t>(N) * D;
-  dense_wn_scale_kernel<<<ceil_div(U, 32), 256, 0, st>>>(V1, g1, w.sc1, w.in1, D, U);
-  dense_wn_scale_kernel<<<ceil_div(U, 32), 256, 0, st>>>(V2, g2, w.sc2, w.in2, U, U);
+  dense_wn_scale_kernel<<<ceil_div(U, 32), 1024, 0, st>>>(V1, g1, w.sc1, w.in1, D, U);
+  dense_wn_scale_kernel<<<ceil_div(U, 32), 1024, 0, st>>>(V2, g2, w.sc2, w.in2, U, U);
   dense_mask_mul_kernel<<<nblk(ND), 256, 0, st>>>(x, w.xm, ND, D, mask_type);
   int rc;
   if ((rc = gemm(false, false, N, U, D, w.xm, D, V1, U, w.h1, U, GemmEpi{w.sc1, b1, w.pre1, 1, 0, nullptr}, st))) return rc;
