@@ -1,34 +1,44 @@
-"""Mutable test-time overrides, same names and semantics as the reference's config_rnn/defaults.py:1-33 (they must be
-set BEFORE the config module is imported, test_nll.py:19,27)."""
-# do not change these parameters here
-seq_len = 20
-seq_len_few_shot = 2
-batch_size_few_shot = 20
-eval_only_last = False
-eps_corr = None
-mask_dims = False
+"""Test-time overrides of the config_rnn modules.
+
+The reference keeps a handful of module-level knobs (sequence length, few-shot batch size, correlation mask) that its
+test drivers overwrite from the command line BEFORE importing a config module (config_rnn/defaults.py, used at
+test_nll.py:19,27).  Same names and semantics here; the assignment logic is table driven.
+"""
+
+# name -> value; every entry is also published as a module attribute (defaults.seq_len, ...)
+_VALUES = {
+    'seq_len': 20,
+    'seq_len_few_shot': 2,
+    'batch_size_few_shot': 20,
+    'eval_only_last': False,
+    'eps_corr': None,
+    'mask_dims': False,
+}
+
+# command-line flag -> [(attribute, conversion)].  batch_size really is cast to bool in the reference (defaults.py:21);
+# the few-shot configs only test its truthiness.
+_FLAGS = {
+    'seq_len': [('seq_len', None), ('seq_len_few_shot', None)],
+    'batch_size': [('batch_size_few_shot', bool)],
+    'eval_only_last': [('eval_only_last', bool)],
+    'eps_corr': [('eps_corr', None)],
+    'mask_dims': [('mask_dims', bool)],
+}
+
+
+def _publish():
+    globals().update(_VALUES)
 
 
 def set_parameters(args):
-    params_dict = vars(args)
-    global seq_len
-    global seq_len_few_shot
-    if 'seq_len' in params_dict:
-        seq_len = params_dict['seq_len']
-        seq_len_few_shot = params_dict['seq_len']
+    """Copy the recognised fields of an argparse namespace into the module attributes."""
+    given = vars(args)
+    for flag, targets in _FLAGS.items():
+        if flag not in given:
+            continue
+        for attr, conv in targets:
+            _VALUES[attr] = conv(given[flag]) if conv is not None else given[flag]
+    _publish()
 
-    global batch_size_few_shot
-    if 'batch_size' in params_dict:
-        batch_size_few_shot = bool(params_dict['batch_size'])   # sic: defaults.py:21 casts to bool in the reference
 
-    global eval_only_last
-    if 'eval_only_last' in params_dict:
-        eval_only_last = bool(params_dict['eval_only_last'])
-
-    global eps_corr
-    if 'eps_corr' in params_dict:
-        eps_corr = params_dict['eps_corr']
-
-    global mask_dims
-    if 'mask_dims' in params_dict:
-        mask_dims = bool(params_dict['mask_dims'])
+_publish()

@@ -1,10 +1,13 @@
-"""k-way n-shot classification -- counterpart of the reference's config_rnn/test_few_shot_omniglot.py: the score of a
-candidate class is log_probs[:, -1] (the test image given the n shots of that class), decision = argmax (:64-80)."""
+"""k-way n-shot classification driver (reference: config_rnn/test_few_shot_omniglot.py, same flags and prints).
+
+An episode holds k candidate sequences: n shots of class j followed by the SAME query image.  The score of class j is
+the predictive log-probability of the last frame, log_probs[j, -1]; scores of repeated presentations of a query are
+averaged and the decision is the argmax (reference :64-80).
+"""
 import argparse
 import importlib
 import json
 import os
-from collections import defaultdict
 
 import numpy as np
 import torch
@@ -15,6 +18,23 @@ from . import defaults
 np.set_printoptions(suppress=True)
 
 
+class _Query(object):
+    """Accumulates the class scores of one query image over its presentations."""
+    __slots__ = ('scores', 'truth', 'candidates')
+
+    def __init__(self, truth, candidates):
+        self.scores, self.truth, self.candidates = [], truth, candidates
+
+    def correct(self):
+        return self.candidates[int(np.argmax(np.mean(np.asarray(self.scores), axis=0)))] == self.truth
+
+
+def _score_episode(config, x_batch, k, device):
+    with torch.no_grad():
+        log_probs = config.build_model(torch.from_numpy(x_batch).to(device), want_prior=False)[0]
+    return log_probs.reshape(k, config.seq_len)[:, -1].cpu().numpy()
+
+
 def classify(config_name, seq_len, n_trials, batch_size, metadata_dir='metadata', max_episodes=None, restore=True):
     config = importlib.import_module('bruno_b200.config_rnn.%s' % config_name)
     device = torch.device('cuda', 0)
@@ -23,39 +43,27 @@ def classify(config_name, seq_len, n_trials, batch_size, metadata_dir='metadata'
         save_dir = utils.find_model_metadata(metadata_dir + '/', config_name)
         print('Building the model', os.path.dirname(save_dir).split('/')[-1])
         utils.load_checkpoint_into(config, save_dir, device)
-    data_iter = config.test_data_iter2
-    data_iter.batch_size = batch_size
-    trial_accuracies = []
+    episodes = config.test_data_iter2
+    episodes.batch_size = batch_size
+    accuracies = []
     for trial in range(n_trials):
-        n_correct = n_total = 0
-        x_number2scores = defaultdict(list)
-        x_number2true_y, x_number2ys = {}, {}
-        for iteration, (x_batch, y_batch, x_number) in enumerate(data_iter.generate(trial=trial)):
-            if max_episodes is not None and iteration >= max_episodes:
+        queries = {}
+        for count, (x_batch, y_batch, query_id) in enumerate(episodes.generate(trial=trial)):
+            if max_episodes is not None and count >= max_episodes:
                 break
-            y_true = int(y_batch[0, -1])
-            with torch.no_grad():
-                log_p = config.build_model(torch.from_numpy(x_batch).to(device), want_prior=False)[0].cpu().numpy()
-            log_p = log_p.reshape((data_iter.batch_size, config.seq_len))[:, -1]
-            x_number2scores[x_number].append(log_p)
-            x_number2true_y[x_number] = y_true
-            x_number2ys[x_number] = y_batch[:, 0]
-        for k, v in x_number2scores.items():
-            avg_score = np.mean(np.asarray(v), axis=0)
-            max_idx = np.argmax(avg_score)
-            if x_number2ys[k][max_idx] == x_number2true_y[k]:
-                n_correct += 1
-            n_total += 1
-        acc = n_correct / n_total
-        print(trial, 'accuracy', acc)
-        print('n test examples', n_total)
-        trial_accuracies.append(acc)
+            if query_id not in queries:
+                queries[query_id] = _Query(truth=int(y_batch[0, -1]), candidates=y_batch[:, 0])
+            queries[query_id].scores.append(_score_episode(config, x_batch, episodes.batch_size, device))
+        hits = sum(1 for q in queries.values() if q.correct())
+        accuracies.append(hits / len(queries))
+        print(trial, 'accuracy', accuracies[-1])
+        print('n test examples', len(queries))
     print('---------------------------------------------')
     print(n_trials, config.seq_len)
-    print(trial_accuracies)
-    print('average accuracy over trials', np.mean(trial_accuracies))
-    print('std accuracy over trials', np.std(trial_accuracies))
-    return trial_accuracies
+    print(accuracies)
+    print('average accuracy over trials', np.mean(accuracies))
+    print('std accuracy over trials', np.std(accuracies))
+    return accuracies
 
 
 def main(argv=None):
@@ -71,8 +79,8 @@ def main(argv=None):
     args, _ = parser.parse_known_args(argv)
     defaults.set_parameters(args)
     print('input args:\n', json.dumps(vars(args), indent=4, separators=(',', ':')))
-    if args.mask_dims == 0:
-        assert args.eps_corr == 0.
+    if not args.mask_dims:
+        assert args.eps_corr == 0., '--eps_corr needs --mask_dims 1'
     return classify(config_name=args.config_name, seq_len=args.seq_len, n_trials=args.n_trials,
                     batch_size=args.batch_size, metadata_dir=args.metadata_dir)
 
