@@ -86,7 +86,7 @@ def cpu_reference_line(args, steps, warmup, as_reference_arm):
     if not as_reference_arm:
         return cb
     return {'metric': 'bn2_omniglot_tp_train_seqs_per_sec', 'value': val, 'unit': 'seqs/s', 'n_gpus': args.gpus,
-            'steps': steps, 'warmup': warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'steps': steps, 'warmup': warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
             'config': {'workload': 'bn2_omniglot_tp training step (fwd+bwd), 28x28x1, seq_len %d' % args.seq_len,
                        'per_step_sample_seqs': sample_b},
@@ -103,6 +103,9 @@ def main():
     ap.add_argument('--seq_len', type=int, default=20)
     ap.add_argument('--cpu_sample_seqs', type=int, default=1)
     ap.add_argument('--no_cpu_baseline', action='store_true')
+    ap.add_argument('--config_name', default=CONFIG, help='config_rnn module; the headline metric is quoted on the default')
+    ap.add_argument('--strong', action='store_true', help='strong scaling: --batch is the GLOBAL batch, split over the ranks (train.py:184)')
+    ap.add_argument('--data_kind', default=None, help="synthetic pixel distribution: 'strokes' (Omniglot-like) or 'bytes' (uniform)")
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -135,14 +138,20 @@ def main():
     from bruno_b200.config_rnn import defaults
     from bruno_b200.trainer import Trainer
     defaults.seq_len = args.seq_len
-    cfg = importlib.import_module('bruno_b200.config_rnn.' + CONFIG)
-    cfg.batch_size = args.batch * world                      # reference semantics: global batch, split over towers
-    B, T = args.batch, args.seq_len
+    cfg = importlib.import_module('bruno_b200.config_rnn.' + args.config_name)
+    if args.strong:
+        assert args.batch % world == 0, '--strong: the global batch must be divisible by the number of GPUs'
+        per_gpu = args.batch // world
+    else:
+        per_gpu = args.batch
+    cfg.batch_size = per_gpu * world                         # reference semantics: global batch, split over towers
+    B, T = per_gpu, args.seq_len
     H, W, C = cfg.obs_shape[1:]
 
     from bruno_b200.synthetic_data import SyntheticExchSeqDataIterator
     import numpy as np
-    it = SyntheticExchSeqDataIterator(seq_len=T, batch_size=B, obs_shape=(H, W, C), kind='strokes',
+    kind = args.data_kind or ('bytes' if 'cifar' in args.config_name else 'strokes')
+    it = SyntheticExchSeqDataIterator(seq_len=T, batch_size=B, obs_shape=(H, W, C), kind=kind,
                                       rng=np.random.RandomState(42 + rank), noise_rng=np.random.RandomState(317070 + rank))
     gen = it.generate()
     n_host = 4
@@ -151,7 +160,8 @@ def main():
 
     tr = Trainer(cfg, dev, world_size=world, rank=rank).materialize(devx[0], init=True)
     # the reference's heads are zero-initialised (flow = identity at step 0); a few real steps move them off zero
-    lr = cfg.learning_rate_schedule[200]
+    sched = getattr(cfg, 'learning_rate_schedule', None)
+    lr = sched[200] if sched and 200 in sched else cfg.learning_rate
 
     def barrier():
         if world > 1:
@@ -246,7 +256,16 @@ def main():
     n_img = B * T
     conv = prof['conv3x3_fwd_dgrad']
     # forward convs + dgrad convs: 2 x the forward count per step, `steps` steps in the profiled region
-    flops_total = 2.0 * conv_launch_flops(n_img) * steps
+    if args.config_name == CONFIG:
+        fwd_flops = conv_launch_flops(n_img)
+    else:                                                    # 2R convolutions per conv coupling at the coupling's resolution
+        fwd_flops = 0.0
+        for layer in cfg.nvp_layers:
+            sl = getattr(layer, '_slabs', None)
+            if sl is not None:
+                (n_, h_, w_, _), R_ = sl[0], layer.num_res_blocks
+                fwd_flops += 2.0 * R_ * 2 * 9 * FILTERS * FILTERS * n_ * h_ * w_
+    flops_total = 2.0 * fwd_flops * steps
     achieved = flops_total / (conv['total_ms'] * 1e-3) / 1e12 if conv['total_ms'] > 0 else None
     traffic, traffic_note = None, None
     tj = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')
@@ -259,14 +278,16 @@ def main():
                             tinfo['algorithmic_bytes_per_launch']['mode1 (in+skip+out)']))
     seqs = B * world
     line = {
-        'metric': 'bn2_omniglot_tp_train_seqs_per_sec', 'value': seqs * steps / (ms_train * 1e-3), 'unit': 'seqs/s',
+        'metric': '%s_train_seqs_per_sec' % args.config_name, 'value': seqs * steps / (ms_train * 1e-3), 'unit': 'seqs/s',
         'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms_train / steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': 'bn2_omniglot_tp training step: conv Real NVP (10 conv + 6 dense couplings) + recurrent '
-                               't-process, fwd + hand-written bwd + NCCL allreduce + RMSProp(TF-1.7)',
+        'config': {'workload': '%s training step: Real NVP (%d conv + %d dense couplings) + recurrent '
+                               'process, fwd + hand-written bwd + NCCL allreduce + optimiser (TF-1.7 semantics)' % (
+                                   args.config_name, sum(1 for l in cfg.nvp_layers if hasattr(l, 'num_res_blocks')), len(cfg.nvp_dense_layers)),
                    'obs_shape': [H, W, C], 'seq_len': T, 'seqs_per_gpu': B, 'global_batch': seqs, 'parallelism': 'dp%d' % world,
                    'params': tr.n_params,
-                   'l2_note': 'working set per step (6.3 GB of saved bf16 activations) >> 126 MB L2; inputs rotate over %d batches' % n_host},
+                   'l2_note': 'working set per step (%.1f GB of saved bf16 activations) >> 126 MB L2; inputs rotate over %d batches' % (
+                       sum(l._slabs[1].numel() for l in cfg.nvp_layers if getattr(l, '_slabs', None) is not None) / 1e9, n_host)},
         'eval_nll': {'value': seqs * steps / (ms_eval * 1e-3), 'unit': 'seqs/s', 'ms_per_step': ms_eval / steps,
                      'what': 'forward NLL (log_probs, latent, prior) of the same batch shape'},
         'few_shot_20way_1shot': {'value': world * fs_steps / (ms_fsg * 1e-3), 'unit': 'episodes/s', 'ms_per_episode': ms_fsg / fs_steps,
