@@ -280,7 +280,7 @@ def main():
     line = {
         'metric': '%s_train_seqs_per_sec' % args.config_name, 'value': seqs * steps / (ms_train * 1e-3), 'unit': 'seqs/s',
         'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms_train / steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': '%s training step: Real NVP (%d conv + %d dense couplings) + recurrent '
                                'process, fwd + hand-written bwd + NCCL allreduce + optimiser (TF-1.7 semantics)' % (
                                    args.config_name, sum(1 for l in cfg.nvp_layers if hasattr(l, 'num_res_blocks')), len(cfg.nvp_dense_layers)),
