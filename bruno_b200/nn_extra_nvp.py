@@ -95,6 +95,20 @@ def direct_grads(on):
     _DIRECT_GRADS[0] = bool(on)
 
 
+# Called by the coupling backward once the kernels that write a layer's variable gradients have been enqueued (the trainer
+# uses it to start the NCCL allreduce of that layer's slice of the flat gradient buffer while the backward goes on).
+_GRADS_READY_HOOK = [None]
+
+
+def on_layer_grads_ready(fn):
+    _GRADS_READY_HOOK[0] = fn
+
+
+def _notify_grads_ready(layer):
+    if _GRADS_READY_HOOK[0] is not None:
+        _GRADS_READY_HOOK[0](layer)
+
+
 def _grad_sinks(layer, names):
     """-> (buffers the kernel writes, values returned to autograd) for the variables `names` of `layer`."""
     bufs, rets = [], []
@@ -212,6 +226,7 @@ class _ConvCouplingFn(torch.autograd.Function):
         scratch = _new_like(x, _lib.query('bruno_heads_bwd_scratch_floats', C))
         _lib.call('bruno_coupling_conv_bwd', x, dy, dld, N, H, W, C, R, layer.mask_id, V1, g1, Vr, gr, ctx.wbwd, Ks, bs, Kt, bt,
                   ctx.slabs, gsl, scratch, dx, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt)
+        _notify_grads_ready(layer)
         return (dx, dld) + tuple(rets) + (None, None, None)
 
 
@@ -377,6 +392,7 @@ class _DenseCouplingFn(torch.autograd.Function):
         (dV1, dg1, db1, dV2, dg2, db2, dKs, dbs, dKt, dbt), rets = _grad_sinks(ctx.layer, ctx.layer._PNAMES)
         _lib.call('bruno_coupling_dense_bwd', x, dy.contiguous(), dld.contiguous(), N, D, U, ctx.layer.mask_id, V1, g1, b1,
                   V2, g2, b2, Ks, Kt, ws, ws2, dx, dV1, dg1, db1, dV2, dg2, db2, dKs, dbs, dKt, dbt)
+        _notify_grads_ready(ctx.layer)
         return (dx, dld) + tuple(rets) + (None, None, None)
 
 

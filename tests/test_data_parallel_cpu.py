@@ -99,3 +99,14 @@ def test_trainer_student_ranges_and_flat_layout():
     assert len(rng) == 3 and all(n == 5 for _, n in rng)
     flat.mul_(0.5)                                       # an optimiser update of the flat buffer is seen through the views
     assert torch.allclose(after[0].detach(), 0.5 * before[0])
+
+
+def test_uncovered_ranges_of_the_bucketed_allreduce():
+    """Host logic of the overlapped allreduce (trainer.py): what the per-layer calls did not cover is reduced last, once."""
+    from bruno_b200.trainer import uncovered_ranges
+    assert uncovered_ranges([], 10) == [(0, 10)]
+    assert uncovered_ranges([(0, 10)], 10) == []
+    assert uncovered_ranges([(6, 2), (2, 2)], 10) == [(0, 2), (4, 2), (8, 2)]
+    assert uncovered_ranges([(0, 4), (4, 4)], 12) == [(8, 4)]
+    covered = sorted([(2, 2), (6, 2)] + uncovered_ranges([(6, 2), (2, 2)], 10))
+    assert sum(n for _, n in covered) == 10 and all(covered[i][0] + covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
