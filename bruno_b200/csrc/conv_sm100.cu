@@ -646,6 +646,347 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
   }
 }
 
+// ---- layer chain: the 2R convolutions of a coupling's s/t ResNet (or of its backward) in ONE persistent launch --------
+// A 14x14 layer is 7.6 tiles per CTA = 8.4 us of pipeline, but a launch costs ~17 us: barrier / TMEM set-up, the wait for
+// the previous kernel's flush, the first slab's latency, and the drain of the last tile (tools/dbg_trace.py).  The chain
+// kernel keeps the CTA, its barriers, its TMEM and its pipeline state alive across layers.  Tile t of every layer belongs
+// to CTA t mod grid; tile t of layer l needs the tiles t-1, t, t+1 of layer l-1 (halo < 128 rows), which are published
+// through per-tile EPOCH flags in global memory (set after the tile's bulk store has completed, read with acquire by the
+// slab producer).  All CTAs are co-resident (grid <= #SMs, one CTA per SM), and a CTA only ever waits for tiles of the
+// PREVIOUS layer, so the waits cannot cycle.  The weights (one 72 KB buffer) are reloaded at each layer boundary as soon
+// as the CTA's last MMA of the previous layer has completed.
+// Same arithmetic as conv3x3_tap_kernel (bit-identical results, tests/test_conv_gpu.py).
+// STATUS: correct but NOT yet faster -- bn2_omniglot_tp step 15.8-16.6 ms with the chain vs 14.4 ms with one launch per
+// layer (619 -> 218 launches per step), few-shot episode 1.8 vs 1.33 ms.  Ruled out by measurement: serial acquire polls
+// in the producer (now three relaxed loads hidden behind the ring-stage wait), the per-tile gpu-scope / proxy fences
+// (removing them changes nothing), one store in flight vs two.  Not yet traced: the layer-boundary bubble (the producer
+// cannot prefetch the next layer's slabs until the last MMA of the layer has retired and the weights have been swapped).
+// Off by default (bruno_debug_conv_chain); kept because per-launch overhead is 40 % of the 14x14 layers' time.
+constexpr int CHAIN_MAX_LAYERS = 16;
+struct ChainLayer {
+  const uint8_t* in;
+  const uint8_t* w;
+  const float* bias;
+  const uint8_t* aux1;
+  const uint8_t* aux2;
+  uint8_t* out;
+  int mode;
+  int pad_;
+};
+struct ChainArgs {
+  ChainLayer layer[CHAIN_MAX_LAYERS];
+  int L;
+  int bias_img_stride;
+  unsigned epoch;           // value the flags of THIS launch take (monotonic over launches: no clearing)
+  unsigned* flags;          // [L][ntiles]
+  unsigned* error;          // set to 1 if a flag wait gave up (never in a correct run; avoids a hung GPU)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool BWD, int NS>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+conv3x3_chain_kernel(const __grid_constant__ ChainArgs args, SlabGeom g, int ntiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int slab_rows = TILE_M + 2 * g.HALO + 8;
+  const uint32_t slab_bytes = static_cast<uint32_t>(slab_rows) * SLAB_ROW_BYTES;
+  uint8_t* wsm = smem;
+  uint8_t* slabs = smem + W_BYTES;
+  uint8_t* stage1 = slabs + NS * slab_bytes;                           // [2][TILE_BYTES] aux1 in / output out (in place)
+  uint8_t* stage2 = stage1 + 2 * TILE_BYTES;                           // [2][TILE_BYTES] aux2 (backward only)
+  TapSmem* cs = reinterpret_cast<TapSmem*>(stage2 + (BWD ? 2 * TILE_BYTES : 0));
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int L = args.L;
+  const int grid = gridDim.x;
+  const int cnt = (ntiles - static_cast<int>(blockIdx.x) + grid - 1) / grid;     // tiles of this CTA per layer (>= 1)
+  const int total = L * cnt;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TAP_MAX_STAGES; ++s) {
+      mbar_init(&cs->full[s], 1);
+      mbar_init(&cs->empty[s], 1);
+    }
+    for (int a = 0; a < TAP_ACC; ++a) {
+      mbar_init(&cs->tfull[a], 1);
+      mbar_init(&cs->tempty[a], FWD_EPI_WARPS / 2);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&cs->auxfull[a], 1);
+      mbar_init(&cs->outready[a], FWD_EPI_WARPS * 16);
+    }
+    mbar_init(&cs->wbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(&cs->tmem_base, 64 * TAP_ACC);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = cs->tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == 0) {
+    // ===== producer: per layer the weights, per tile the activation slab (after the neighbours' flags) =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
+      bulk_g2s(wsm, args.layer[0].w, W_BYTES, &cs->wbar);           // weights do not depend on the previous kernel
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      int l = 0, j = 0;
+      for (int it = 0; it < total; ++it) {
+        const int tile = blockIdx.x + j * grid;
+        const int s = it % NS;
+        if (j == 0 && l > 0) {
+          // every MMA of layer l-1 in this CTA has completed -> the weight buffer may be overwritten
+          mbar_wait(&cs->empty[(it - 1) % NS], ((it - 1) / NS) & 1);
+          mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
+          bulk_g2s(wsm, args.layer[l].w, W_BYTES, &cs->wbar);
+        }
+        // the three neighbour flags are fetched (relaxed, in parallel) BEFORE the wait for a free ring stage, which
+        // normally takes about a tile period: their L2 round trip hides behind it.  Serial acquire loads (~0.7 us each)
+        // made the producer slower than the tensor pipe.
+        const unsigned* f = args.flags + static_cast<size_t>(l > 0 ? l - 1 : 0) * ntiles;
+        const int t0 = tile > 0 ? tile - 1 : 0, t1 = tile + 1 < ntiles ? tile + 1 : ntiles - 1;
+        unsigned f0 = args.epoch, f1 = args.epoch, f2 = args.epoch;
+        if (l > 0) {
+          f0 = ld_relaxed_u32(f + t0);
+          f1 = ld_relaxed_u32(f + tile);
+          f2 = ld_relaxed_u32(f + t1);
+        }
+        mbar_wait(&cs->empty[s], ((it / NS) & 1) ^ 1);
+        if (l > 0) {
+          unsigned spins = 0;
+          while (f0 != args.epoch || f1 != args.epoch || f2 != args.epoch) {
+            f0 = ld_relaxed_u32(f + t0);
+            f1 = ld_relaxed_u32(f + tile);
+            f2 = ld_relaxed_u32(f + t1);
+            if (++spins > (1u << 21)) {
+              *args.error = 1u;
+              break;
+            }
+          }
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");          // relaxed loads that saw the release stores + fence = acquire
+          asm volatile("fence.proxy.async;" ::: "memory");          // the tiles were written / are read by the async proxy
+        }
+        const int LS = (g.HALO + TILE_M * tile - g.P - 1) & ~7;
+        mbar_arrive_expect_tx(&cs->full[s], slab_bytes);
+        bulk_g2s(slabs + s * slab_bytes, args.layer[l].in + static_cast<size_t>(LS) * SLAB_ROW_BYTES, slab_bytes, &cs->full[s]);
+        if (++j == cnt) {
+          j = 0;
+          ++l;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (see conv3x3_tap_kernel); the iteration counter runs on across layers =====
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr int U = (NS == 3) ? 12 : 4;
+    const uint64_t bdesc0 = umma_desc_sw128(smem_u32(wsm), 16, 1024);
+    uint64_t adesc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) adesc[s] = umma_desc_sw128(smem_u32(slabs + s * slab_bytes), 16, 1024);
+    const uint32_t a_base = static_cast<uint32_t>(g.HALO - ((g.HALO - g.P - 1) & ~7)) * 8u;
+    const uint32_t p8 = static_cast<uint32_t>(g.P) * 8u;
+    const bool leader = elect_one();
+    int j = 0, l = 0;                                 // position of iteration `it` inside its layer
+    if (leader) {
+      mbar_wait(&cs->wbar, 0u);
+      mbar_wait(&cs->tempty[0], 1u);
+      mbar_wait(&cs->full[0], 0u);
+      tc_fence_after();
+    }
+    bool more = total > 0;
+    for (uint32_t r = 0; more; ++r) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (more) {
+          const int s = u % NS, a = u % TAP_ACC;
+          const int sn = (u + 1) % NS, an = (u + 1) % TAP_ACC;
+          const int it = static_cast<int>(r) * U + u;
+          more = it + 1 < total;
+          const bool next_new_layer = (j + 1 == cnt);
+          if (leader) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              const uint32_t a_off = a_base + static_cast<uint32_t>(dy) * p8 + static_cast<uint32_t>(dx * 8);
+              if (more && !next_new_layer) {
+                if (tap == 5) mbar_wait(&cs->tempty[an], ((r * (U / TAP_ACC) + (u + 1) / TAP_ACC) & 1u) ^ 1u);
+                if (tap == 6) mbar_wait(&cs->full[sn], (r * (U / NS) + (u + 1) / NS) & 1u);
+                if (tap == 7) tc_fence_after();
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(tmem + a * 64, adesc[s] + (a_off + 2u * k),
+                          bdesc0 + static_cast<uint32_t>((tap * W_TAP_BYTES + k * 32) >> 4), idesc, (tap | k) != 0);
+              }
+            }
+            umma_commit(&cs->empty[s]);
+            umma_commit(&cs->tfull[a]);
+            if (more && next_new_layer) {
+              // layer boundary: the new weights land only after these MMAs have completed (the producer waits for them)
+              mbar_wait(&cs->wbar, static_cast<uint32_t>(l + 1) & 1u);
+              mbar_wait(&cs->tempty[an], ((r * (U / TAP_ACC) + (u + 1) / TAP_ACC) & 1u) ^ 1u);
+              mbar_wait(&cs->full[sn], (r * (U / NS) + (u + 1) / NS) & 1u);
+              tc_fence_after();
+            }
+          }
+          if (++j == cnt) {
+            j = 0;
+            ++l;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 2 + FWD_EPI_WARPS) {
+    // ===== epilogue: two groups of 8 warps alternate iterations; warp -> TMEM lane quarter and 32-channel half =====
+    const int grp = (warp - 2) >> 3;
+    const int q = warp & 3;
+    const int half = ((warp - 2) >> 2) & 1;
+    const int row = q * 32 + lane;
+    const int R7 = lane & 7;
+    const float inv_p = 1.0f / static_cast<float>(g.P), inv_img = 1.0f / static_cast<float>(g.IMG);
+    const bool small = g.NT * TILE_M < (1 << 22);
+    const uint32_t st1 = smem_u32(stage1 + grp * TILE_BYTES + row * SLAB_ROW_BYTES);
+    const uint32_t st2 = smem_u32(stage2 + grp * TILE_BYTES + row * SLAB_ROW_BYTES);
+    for (int it = grp; it < total; it += 2) {
+      const int l = it / cnt, j = it - l * cnt;
+      const int tile = blockIdx.x + j * grid;
+      const int mode = args.layer[l].mode;
+      const float* __restrict__ bias = args.layer[l].bias;
+      const int a = it % TAP_ACC;
+      const int data_row = TILE_M * tile + row;
+      const int n_img = small ? static_cast<int>((static_cast<float>(data_row) + 0.5f) * inv_img) : data_row / g.IMG;
+      const int q_img = data_row - n_img * g.IMG;
+      const int yy = static_cast<int>((static_cast<float>(q_img) + 0.5f) * inv_p);
+      const int xx = q_img - yy * g.P;
+      const bool valid = data_row < g.data_rows && yy >= 1 && xx >= 1;
+      mbar_wait(&cs->tfull[a], (it / TAP_ACC) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 64 + half * 32;
+      uint32_t acc[4][8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld8(tbase + c * 8, acc[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cs->tempty[a]);
+      mbar_wait(&cs->auxfull[grp], (it >> 1) & 1);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int jc = half * 4 + jj;
+        const int pos = (jc ^ R7) << 4;
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(acc[jj][e]);
+        if (!BWD) {
+          float bj[8];
+          const float* bsrc = bias + (args.bias_img_stride ? static_cast<size_t>(valid ? n_img : 0) * args.bias_img_stride : 0) + jc * 8;
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bsrc));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bsrc + 4));
+          bj[0] = b0.x; bj[1] = b0.y; bj[2] = b0.z; bj[3] = b0.w; bj[4] = b1.x; bj[5] = b1.y; bj[6] = b1.z; bj[7] = b1.w;
+          if (mode == MODE_ELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = elu_fast(o[e] + bj[e]);
+          } else {        // MODE_RES_ELU
+            float sk[8];
+            unpack8(lds_u4(st1 + pos), sk);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = elu_fast(o[e] + bj[e] + sk[e]);
+          }
+        } else {
+          float sk[8];
+          unpack8(lds_u4(st1 + pos), sk);
+          if (mode == MODE_MUL) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(sk[e]);
+          } else {        // MODE_ADD_MUL
+            float t[8];
+            unpack8(lds_u4(st2 + pos), t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
+          }
+        }
+        sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&cs->outready[grp]);
+    }
+  } else {
+    // ===== aux / store warp: aux tiles in, output tile out, and the tile's flag once its store has COMPLETED =====
+    if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      auto publish = [&](int it) {                     // the store of iteration `it` is complete
+        const int l = it / cnt, j = it - l * cnt;
+        __threadfence();
+        st_release_u32(args.flags + static_cast<size_t>(l) * ntiles + blockIdx.x + j * grid, args.epoch);
+      };
+      // loop iteration k: prefetch the aux tile(s) of iteration k, publish iteration k-2 (its store, issued one loop
+      // iteration ago, is the only one outstanding), then drain iteration k-1.  A flag must never wait for a LATER
+      // iteration's epilogue: the next layer's producers are waiting for it.
+      for (int it = 0; it <= total; ++it) {
+        if (it < total) {
+          const int l = it / cnt, j = it - l * cnt;
+          const int tile = blockIdx.x + j * grid;
+          const int b = it & 1;
+          const int mode = args.layer[l].mode;
+          // staging buffer b was the source of the store of iteration it-2.  With one tile per layer the aux tile of
+          // iteration it was WRITTEN by that store (same tile, two layers up): it must have landed, not just been read.
+          if (cnt < 2) bulk_wait_all<0>();
+          else bulk_wait_read<0>();
+          const bool a1 = mode == MODE_RES_ELU || mode == MODE_MUL || mode == MODE_ADD_MUL, a2 = mode == MODE_ADD_MUL;
+          if (a1) {
+            const size_t off = static_cast<size_t>(g.HALO + TILE_M * tile) * SLAB_ROW_BYTES;
+            mbar_arrive_expect_tx(&cs->auxfull[b], a2 ? 2 * TILE_BYTES : TILE_BYTES);
+            bulk_g2s(stage1 + b * TILE_BYTES, args.layer[l].aux1 + off, TILE_BYTES, &cs->auxfull[b]);
+            if (a2) bulk_g2s(stage2 + b * TILE_BYTES, args.layer[l].aux2 + off, TILE_BYTES, &cs->auxfull[b]);
+          } else {
+            mbar_arrive(&cs->auxfull[b]);
+          }
+        }
+        if (it >= 2) {
+          bulk_wait_all<0>();
+          publish(it - 2);
+        }
+        if (it >= 1) {
+          const int pit = it - 1;
+          const int pl = pit / cnt, pj = pit - pl * cnt;
+          const int ptile = blockIdx.x + pj * grid;
+          const int pa = pit & 1;
+          mbar_wait(&cs->outready[pa], (pit >> 1) & 1);
+          bulk_s2g(args.layer[pl].out + static_cast<size_t>(g.HALO + TILE_M * ptile) * SLAB_ROW_BYTES, stage1 + pa * TILE_BYTES,
+                   TILE_BYTES);
+          bulk_commit();
+        }
+      }
+      bulk_wait_all<0>();
+      if (total >= 1) publish(total - 1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem, 64 * TAP_ACC);
+  }
+}
+
 // ---- pair-fused implicit GEMM (variant 2) ------------------------------------------------------------------------
 // The per-tap kernel is bound by the shared-memory port: 36 MMAs x 6 KB of operand reads + ~58 KB of slab / staging
 // traffic per 128-row tile = 2140 cycles at 128 B/clk (measured: 2100).  Here the taps (dy, 0) and (dy, +1) share ONE
@@ -1335,6 +1676,111 @@ static int launch_conv_pair(const void* in, const void* w, const float* bias, in
   return launch_conv_pair_ns<MODE, 2>(in, w, bias, bias_img_stride, a1, a2, out, g, smem, st);
 }
 
+// ---- chain launcher ----------------------------------------------------------------------------------------------
+static int g_conv_chain = 0;                 // bruno_debug_conv_chain: OFF by default (measured slower, see above)
+static unsigned* g_chain_flags = nullptr;    // [CHAIN_MAX_LAYERS][g_chain_tiles] epoch flags + 1 error word
+static int g_chain_tiles = 0;
+static unsigned g_chain_epoch = 0;
+static unsigned* g_chain_error_host = nullptr;   // pinned copy of the error word of the previous launch
+
+template <bool BWD, int NS>
+static int launch_chain_ns(const ChainArgs& a, const SlabGeom& g, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv3x3_chain_kernel<BWD, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
+  const int ntiles = g.NT;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  ProfSpan span(BRUNO_PROF_CONV, st);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(FWD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, conv3x3_chain_kernel<BWD, NS>, a, g, ntiles);
+  return check_launch("conv3x3_chain_kernel");
+}
+
+// L stacked convolutions of one geometry in one launch.  Returns BRUNO_OK, an error, or +1 when the chain path is not
+// available (switched off, too many layers, flags cannot be allocated under stream capture, slab too wide): the caller
+// then issues the layers one by one.
+int conv3x3_chain(bool backward, int L, const void* const* in, const void* const* w, const float* const* bias,
+                  const void* const* aux1, const void* const* aux2, void* const* out, const int* mode, int bias_img_stride,
+                  int N, int H, int W, cudaStream_t st) {
+  if (!g_conv_chain || g_conv_variant != 1 || L < 1 || L > CHAIN_MAX_LAYERS) return 1;
+  const SlabGeom g = slab_geom(N, H, W);
+  // with fewer than two tiles per CTA every layer is one lock-step round of flag hand-offs: mode 1 leaves those shapes to
+  // separate launches, mode 2 chains everything (tests)
+  if (g_conv_chain == 1 && g.NT < 2 * num_sms()) return 1;
+  if (g_chain_flags == nullptr || g.NT > g_chain_tiles) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return 1;
+    }
+    cudaDeviceSynchronize();                 // the old buffer may still be in use
+    if (g_chain_flags) cudaFree(g_chain_flags);
+    g_chain_tiles = g.NT > 8192 ? g.NT : 8192;
+    const size_t words = static_cast<size_t>(CHAIN_MAX_LAYERS) * g_chain_tiles + 1;
+    if (cudaMalloc(&g_chain_flags, words * sizeof(unsigned)) != cudaSuccess) {
+      cudaGetLastError();
+      g_chain_flags = nullptr;
+      g_chain_tiles = 0;
+      return 1;
+    }
+    cudaMemset(g_chain_flags, 0, words * sizeof(unsigned));
+    if (!g_chain_error_host) {
+      cudaMallocHost(&g_chain_error_host, sizeof(unsigned));
+      *g_chain_error_host = 0u;
+    }
+  }
+  if (g_chain_error_host && *g_chain_error_host) {
+    set_last_error("conv3x3_chain: a tile-flag wait of an earlier launch gave up (inter-layer dependency never published)");
+    return BRUNO_ECUDA;
+  }
+  const size_t fixed = 1024 + W_BYTES + (backward ? 4 : 2) * TILE_BYTES + sizeof(TapSmem) + 64;
+  const size_t slab = static_cast<size_t>(TILE_M + 2 * g.HALO + 8) * SLAB_ROW_BYTES;
+  if (fixed + 2 * slab > 227 * 1024) return 1;
+  int ns = static_cast<int>((227 * 1024 - fixed) / slab);
+  if (ns > TAP_MAX_STAGES) ns = TAP_MAX_STAGES;
+  ChainArgs a{};
+  for (int l = 0; l < L; ++l) {
+    a.layer[l].in = static_cast<const uint8_t*>(in[l]);
+    a.layer[l].w = static_cast<const uint8_t*>(w[l]);
+    a.layer[l].bias = bias ? bias[l] : nullptr;
+    a.layer[l].aux1 = aux1 ? static_cast<const uint8_t*>(aux1[l]) : nullptr;
+    a.layer[l].aux2 = aux2 ? static_cast<const uint8_t*>(aux2[l]) : nullptr;
+    a.layer[l].out = static_cast<uint8_t*>(out[l]);
+    a.layer[l].mode = mode[l];
+  }
+  a.L = L;
+  a.bias_img_stride = bias_img_stride;
+  a.epoch = ++g_chain_epoch;
+  if (g_chain_epoch == 0xFFFFFFFFu) {        // wrap: clear the flags once every 4 billion launches
+    cudaMemsetAsync(g_chain_flags, 0, (static_cast<size_t>(CHAIN_MAX_LAYERS) * g_chain_tiles) * sizeof(unsigned), st);
+    g_chain_epoch = 0;
+    a.epoch = ++g_chain_epoch;
+  }
+  a.flags = g_chain_flags;
+  a.error = g_chain_flags + static_cast<size_t>(CHAIN_MAX_LAYERS) * g_chain_tiles;
+  // the flag rows are [L][ntiles] with the CURRENT ntiles as pitch (a launch only reads what it wrote)
+  const size_t smem = fixed + static_cast<size_t>(ns) * slab;
+  int rc;
+  if (backward) rc = ns >= 4 ? launch_chain_ns<true, 4>(a, g, smem, st) : ns == 3 ? launch_chain_ns<true, 3>(a, g, smem, st)
+                                                                                  : launch_chain_ns<true, 2>(a, g, smem, st);
+  else rc = ns >= 4 ? launch_chain_ns<false, 4>(a, g, smem, st) : ns == 3 ? launch_chain_ns<false, 3>(a, g, smem, st)
+                                                                         : launch_chain_ns<false, 2>(a, g, smem, st);
+  // the error word is looked at by the NEXT call (no synchronisation here)
+  if (rc == BRUNO_OK) cudaMemcpyAsync(g_chain_error_host, a.error, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+  return rc;
+}
+
 template <int MODE>
 static int launch_conv(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
                        const void* a2, void* out, const SlabGeom& g, cudaStream_t st) {
@@ -1380,6 +1826,12 @@ size_t bruno_conv_wpack_bytes(void) { return W_BYTES; }
 
 int bruno_debug_conv_trace(long long* device_buffer) {
   g_conv_trace_host = device_buffer;
+  return BRUNO_OK;
+}
+
+int bruno_debug_conv_chain(int on) {
+  if (on < 0) return g_conv_chain;
+  g_conv_chain = on > 2 ? 1 : on;            // 0 off, 1 on for >= 2 tiles per CTA (default), 2 on for every shape (tests)
   return BRUNO_OK;
 }
 

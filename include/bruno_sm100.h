@@ -137,6 +137,10 @@ int bruno_debug_conv_trace(long long* device_buffer);
  * MMA, shuffle epilogue), 1 = per-tap (36 MMAs of N=64 into one accumulator, plain epilogue; default), 2 = pair-fused
  * (taps (dy,0),(dy,+1) in one N=128 MMA, (dy,-1) as an N=64 MMA on the shifted view).  variant < 0 queries. */
 int bruno_debug_conv_variant(int variant);
+/* experimental: 1 = the 2R convolutions of a coupling's s/t network (and of its backward) run as ONE persistent launch
+ * with per-tile inter-layer flags (conv3x3_chain_kernel) when there are at least two tiles per SM, 2 = for every shape
+ * (tests), 0 (default: the chain is bit-identical but not yet faster) = one launch per layer.  on < 0 queries. */
+int bruno_debug_conv_chain(int on);
 
 /* conv2d_wn weight normalisation (nvp:389) of L stacked 3x3 64->64 kernels V [L,3,3,64,64] (HWIO), g [L,64] into the
  * packed bf16 tensor-core operands: wfwd [L] (forward) and wbwd [L] (dgrad: transposed + flipped; may be NULL). */

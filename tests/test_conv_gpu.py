@@ -143,3 +143,35 @@ def test_wn_backward():
               dW.float().cuda().contiguous(), dV, dg, 2, 576)
     assert torch.allclose(dV.double().cpu().view(2, 3, 3, 64, 64), V.grad, rtol=1e-4, atol=1e-5)
     assert torch.allclose(dg.double().cpu(), gain.grad, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('N,H,W,C', [(3, 28, 28, 1), (40, 14, 14, 4), (1, 16, 16, 2), (130, 14, 14, 4), (500, 14, 14, 2)])
+def test_layer_chain_is_bit_identical_to_per_layer_launches(N, H, W, C):
+    """The 2R convolutions of a coupling as ONE persistent launch (per-tile inter-layer flags) == 2R launches: forward
+    output, log-det and (backward) the input gradient, bit for bit; both the 3-slab inference ring and the saved slabs."""
+    from bruno_b200 import _lib, nn_extra_nvp
+    lib = _lib.load()
+    torch.manual_seed(N + H)
+    layer = nn_extra_nvp.CouplingLayerConv('checkerboard0' if C == 1 else 'channel1', name='chain_test')
+    x = torch.randn(N, H, W, C, device='cuda')
+    ld = torch.zeros(N, device='cuda')
+    with torch.no_grad():
+        layer.forward_and_jacobian(x[:1], None, ld[:1])              # creates the variables
+        for p in (layer.Ks, layer.Kt):
+            p.normal_(0, 0.05)
+    res = {}
+    try:
+        for chain in (2, 0):
+            assert lib.bruno_debug_conv_chain(chain) == 0
+            with torch.no_grad():
+                y_inf, _, ld_inf = layer.forward_and_jacobian(x, None, ld)
+            xg = x.clone().requires_grad_(True)
+            y, _, l2 = layer.forward_and_jacobian(xg, None, ld)
+            (y.square().sum() + l2.sum()).backward()
+            res[chain] = (y_inf.clone(), ld_inf.clone(), y.detach().clone(), xg.grad.clone())
+            for p in layer.parameters():
+                p.grad = None
+    finally:
+        lib.bruno_debug_conv_chain(1)
+    for a, b in zip(res[2], res[0]):
+        assert torch.equal(a, b)

@@ -1,7 +1,7 @@
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from bruno_b200 import _lib, slab
-N, H, W = 640, 28, 28
+N, H, W = (int(a) for a in sys.argv[2:5]) if len(sys.argv) > 4 else (640, 28, 28)
 g = torch.Generator().manual_seed(0)
 V = torch.randn(1, 3, 3, 64, 64, generator=g) * 0.05
 wf = torch.empty(1, _lib.query('bruno_conv_wpack_bytes'), dtype=torch.uint8, device='cuda')
