@@ -391,6 +391,8 @@ constexpr int TAP_MAX_STAGES = 4;          // slab ring depth: as many as fit ne
 struct TapSmem {
   uint64_t full[TAP_MAX_STAGES], empty[TAP_MAX_STAGES], tfull[TAP_ACC], tempty[TAP_ACC], wbar;
   uint64_t auxfull[2], outready[2];
+  uint64_t flagok[8];                        // chain kernel: neighbour flags of iteration it seen (ring of 8)
+  volatile int prod_it;                      // chain kernel: iterations whose slab load the producer has issued
   uint32_t tmem_base;
   alignas(16) float bias[64];
 };
@@ -656,13 +658,17 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
 // PREVIOUS layer, so the waits cannot cycle.  The weights (one 72 KB buffer) are reloaded at each layer boundary as soon
 // as the CTA's last MMA of the previous layer has completed.
 // Same arithmetic as conv3x3_tap_kernel (bit-identical results, tests/test_conv_gpu.py).
-// STATUS: correct but NOT yet faster -- bn2_omniglot_tp step 15.8-16.6 ms with the chain vs 14.4 ms with one launch per
-// layer (619 -> 218 launches per step), few-shot episode 1.8 vs 1.33 ms.  Ruled out by measurement: serial acquire polls
-// in the producer (now three relaxed loads hidden behind the ring-stage wait), the per-tile gpu-scope / proxy fences
-// (removing them changes nothing), one store in flight vs two.  Not yet traced: the layer-boundary bubble (the producer
-// cannot prefetch the next layer's slabs until the last MMA of the layer has retired and the weights have been swapped).
-// Off by default (bruno_debug_conv_chain); kept because per-launch overhead is 40 % of the 14x14 layers' time.
+// STATUS: correct, within 3.5 % of the per-layer launches but NOT faster yet -- bn2_omniglot_tp step 15.0 ms with the chain vs
+// 14.5 ms with one launch per layer on the same box (619 -> 218 launches per step).  What the timeline (tools/
+// dbg_trace_chain.py) showed and what was fixed: (i) ONE aux/store thread that waits for each store to land before the
+// next is issued runs at 3000 cycles per tile (store latency ~1.4 us) against 2150 for the tensor pipe -> two store
+// threads, one per staging buffer; (ii) a gpu-scope fence issued by the PRODUCER after the flag poll waits for its slab
+// loads in flight (~2500 cycles per tile, loads serialised) -> a separate flag warp that owns no asynchronous copies polls,
+// fences and releases the producer through an mbarrier ring; (iii) serial acquire polls -> three relaxed loads + one fence.
+// Left: the tile period inside a layer is ~2230 cycles (per-tap kernel: 2100) and every layer boundary costs ~2200 cycles
+// (the weights are swapped only after the layer's last MMA has retired).  Off by default (bruno_debug_conv_chain).
 constexpr int CHAIN_MAX_LAYERS = 16;
+constexpr int CHAIN_THREADS = FWD_THREADS + 64;   // + second aux / store warp + flag warp
 struct ChainLayer {
   const uint8_t* in;
   const uint8_t* w;
@@ -680,6 +686,7 @@ struct ChainArgs {
   unsigned epoch;           // value the flags of THIS launch take (monotonic over launches: no clearing)
   unsigned* flags;          // [L][ntiles]
   unsigned* error;          // set to 1 if a flag wait gave up (never in a correct run; avoids a hung GPU)
+  long long* trace;         // debug timeline of CTA 0 (bruno_debug_conv_trace), or null
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -697,7 +704,7 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 }
 
 template <bool BWD, int NS>
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+__global__ void __launch_bounds__(CHAIN_THREADS, 1)
 conv3x3_chain_kernel(const __grid_constant__ ChainArgs args, SlabGeom g, int ntiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -728,6 +735,8 @@ conv3x3_chain_kernel(const __grid_constant__ ChainArgs args, SlabGeom g, int nti
       mbar_init(&cs->outready[a], FWD_EPI_WARPS * 16);
     }
     mbar_init(&cs->wbar, 1);
+    for (int f = 0; f < 8; ++f) mbar_init(&cs->flagok[f], 1);
+    cs->prod_it = 0;
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -757,35 +766,17 @@ conv3x3_chain_kernel(const __grid_constant__ ChainArgs args, SlabGeom g, int nti
           mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
           bulk_g2s(wsm, args.layer[l].w, W_BYTES, &cs->wbar);
         }
-        // the three neighbour flags are fetched (relaxed, in parallel) BEFORE the wait for a free ring stage, which
-        // normally takes about a tile period: their L2 round trip hides behind it.  Serial acquire loads (~0.7 us each)
-        // made the producer slower than the tensor pipe.
-        const unsigned* f = args.flags + static_cast<size_t>(l > 0 ? l - 1 : 0) * ntiles;
-        const int t0 = tile > 0 ? tile - 1 : 0, t1 = tile + 1 < ntiles ? tile + 1 : ntiles - 1;
-        unsigned f0 = args.epoch, f1 = args.epoch, f2 = args.epoch;
-        if (l > 0) {
-          f0 = ld_relaxed_u32(f + t0);
-          f1 = ld_relaxed_u32(f + tile);
-          f2 = ld_relaxed_u32(f + t1);
-        }
         mbar_wait(&cs->empty[s], ((it / NS) & 1) ^ 1);
-        if (l > 0) {
-          unsigned spins = 0;
-          while (f0 != args.epoch || f1 != args.epoch || f2 != args.epoch) {
-            f0 = ld_relaxed_u32(f + t0);
-            f1 = ld_relaxed_u32(f + tile);
-            f2 = ld_relaxed_u32(f + t1);
-            if (++spins > (1u << 21)) {
-              *args.error = 1u;
-              break;
-            }
-          }
-          asm volatile("fence.acq_rel.gpu;" ::: "memory");          // relaxed loads that saw the release stores + fence = acquire
-          asm volatile("fence.proxy.async;" ::: "memory");          // the tiles were written / are read by the async proxy
-        }
+        trace_at(args.trace, it, 7);
+        // the neighbour tiles of the previous layer have been seen published by the flag warp (which holds no
+        // outstanding asynchronous copies: a gpu-scope fence issued HERE waited for the slab loads in flight, ~2500 cycles
+        // per tile, and serialised them)
+        mbar_wait(&cs->flagok[it & 7], (it >> 3) & 1);            // (arrives for layer 0 too: uniform phases)
         const int LS = (g.HALO + TILE_M * tile - g.P - 1) & ~7;
         mbar_arrive_expect_tx(&cs->full[s], slab_bytes);
         bulk_g2s(slabs + s * slab_bytes, args.layer[l].in + static_cast<size_t>(LS) * SLAB_ROW_BYTES, slab_bytes, &cs->full[s]);
+        trace_at(args.trace, it, 0);
+        cs->prod_it = it + 1;
         if (++j == cnt) {
           j = 0;
           ++l;
@@ -821,6 +812,7 @@ conv3x3_chain_kernel(const __grid_constant__ ChainArgs args, SlabGeom g, int nti
           more = it + 1 < total;
           const bool next_new_layer = (j + 1 == cnt);
           if (leader) {
+            trace_at(args.trace, it, 1);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -838,6 +830,7 @@ conv3x3_chain_kernel(const __grid_constant__ ChainArgs args, SlabGeom g, int nti
             }
             umma_commit(&cs->empty[s]);
             umma_commit(&cs->tfull[a]);
+            trace_at(args.trace, it, 2);
             if (more && next_new_layer) {
               // layer boundary: the new weights land only after these MMAs have completed (the producer waits for them)
               mbar_wait(&cs->wbar, static_cast<uint32_t>(l + 1) & 1u);
@@ -879,6 +872,7 @@ conv3x3_chain_kernel(const __grid_constant__ ChainArgs args, SlabGeom g, int nti
       const bool valid = data_row < g.data_rows && yy >= 1 && xx >= 1;
       mbar_wait(&cs->tfull[a], (it / TAP_ACC) & 1);
       tc_fence_after();
+      if ((warp == 2 || warp == 10) && lane == 0) trace_at(args.trace, it, 3);
       const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 64 + half * 32;
       uint32_t acc[4][8];
 #pragma unroll
@@ -888,6 +882,7 @@ conv3x3_chain_kernel(const __grid_constant__ ChainArgs args, SlabGeom g, int nti
       __syncwarp();
       if (lane == 0) mbar_arrive(&cs->tempty[a]);
       mbar_wait(&cs->auxfull[grp], (it >> 1) & 1);
+      if ((warp == 2 || warp == 10) && lane == 0) trace_at(args.trace, it, 6);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const int jc = half * 4 + jj;
@@ -926,57 +921,87 @@ conv3x3_chain_kernel(const __grid_constant__ ChainArgs args, SlabGeom g, int nti
         sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
       }
       fence_proxy_async_smem();
+      if ((warp == 2 || warp == 10) && lane == 0) trace_at(args.trace, it, 4);
       mbar_arrive(&cs->outready[grp]);
     }
-  } else {
-    // ===== aux / store warp: aux tiles in, output tile out, and the tile's flag once its store has COMPLETED =====
+  } else if (warp < 2 + FWD_EPI_WARPS + 2) {
+    // ===== two aux / store threads, one per staging buffer (iteration parity): aux tiles in, output tile out, and the
+    // tile's flag once its store has LANDED.  One thread doing all three waited ~1.4 us for every store before issuing
+    // the next: 3000 cycles per tile against 2150 for the tensor pipe.  Per thread and iteration:
+    //   staging buffer free (own store of it-2 read) -> prefetch aux(it) -> store(it-2) landed -> publish(it-2)
+    //   -> epilogue(it) done -> store(it).
+    // A flag never waits for a later iteration's epilogue: the next layer's producers are waiting for it. =====
     if (lane == 0) {
+      const int par = warp - (2 + FWD_EPI_WARPS);
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      auto publish = [&](int it) {                     // the store of iteration `it` is complete
+      auto publish = [&](int it) {
         const int l = it / cnt, j = it - l * cnt;
         __threadfence();
         st_release_u32(args.flags + static_cast<size_t>(l) * ntiles + blockIdx.x + j * grid, args.epoch);
       };
-      // loop iteration k: prefetch the aux tile(s) of iteration k, publish iteration k-2 (its store, issued one loop
-      // iteration ago, is the only one outstanding), then drain iteration k-1.  A flag must never wait for a LATER
-      // iteration's epilogue: the next layer's producers are waiting for it.
-      for (int it = 0; it <= total; ++it) {
-        if (it < total) {
-          const int l = it / cnt, j = it - l * cnt;
-          const int tile = blockIdx.x + j * grid;
-          const int b = it & 1;
-          const int mode = args.layer[l].mode;
-          // staging buffer b was the source of the store of iteration it-2.  With one tile per layer the aux tile of
-          // iteration it was WRITTEN by that store (same tile, two layers up): it must have landed, not just been read.
-          if (cnt < 2) bulk_wait_all<0>();
-          else bulk_wait_read<0>();
-          const bool a1 = mode == MODE_RES_ELU || mode == MODE_MUL || mode == MODE_ADD_MUL, a2 = mode == MODE_ADD_MUL;
-          if (a1) {
-            const size_t off = static_cast<size_t>(g.HALO + TILE_M * tile) * SLAB_ROW_BYTES;
-            mbar_arrive_expect_tx(&cs->auxfull[b], a2 ? 2 * TILE_BYTES : TILE_BYTES);
-            bulk_g2s(stage1 + b * TILE_BYTES, args.layer[l].aux1 + off, TILE_BYTES, &cs->auxfull[b]);
-            if (a2) bulk_g2s(stage2 + b * TILE_BYTES, args.layer[l].aux2 + off, TILE_BYTES, &cs->auxfull[b]);
-          } else {
-            mbar_arrive(&cs->auxfull[b]);
-          }
+      int last = -1;
+      for (int it = par; it < total; it += 2) {
+        const int l = it / cnt, j = it - l * cnt;
+        const int tile = blockIdx.x + j * grid;
+        const int mode = args.layer[l].mode;
+        // with one tile per layer the aux tile of iteration it was WRITTEN by the store of it-2: it must have landed
+        if (cnt < 2) bulk_wait_all<0>();
+        else bulk_wait_read<0>();
+        const bool a1 = mode == MODE_RES_ELU || mode == MODE_MUL || mode == MODE_ADD_MUL, a2 = mode == MODE_ADD_MUL;
+        if (a1) {
+          const size_t off = static_cast<size_t>(g.HALO + TILE_M * tile) * SLAB_ROW_BYTES;
+          mbar_arrive_expect_tx(&cs->auxfull[par], a2 ? 2 * TILE_BYTES : TILE_BYTES);
+          bulk_g2s(stage1 + par * TILE_BYTES, args.layer[l].aux1 + off, TILE_BYTES, &cs->auxfull[par]);
+          if (a2) bulk_g2s(stage2 + par * TILE_BYTES, args.layer[l].aux2 + off, TILE_BYTES, &cs->auxfull[par]);
+        } else {
+          mbar_arrive(&cs->auxfull[par]);
         }
-        if (it >= 2) {
+        if (last >= 0) {
           bulk_wait_all<0>();
-          publish(it - 2);
+          publish(last);
         }
-        if (it >= 1) {
-          const int pit = it - 1;
-          const int pl = pit / cnt, pj = pit - pl * cnt;
-          const int ptile = blockIdx.x + pj * grid;
-          const int pa = pit & 1;
-          mbar_wait(&cs->outready[pa], (pit >> 1) & 1);
-          bulk_s2g(args.layer[pl].out + static_cast<size_t>(g.HALO + TILE_M * ptile) * SLAB_ROW_BYTES, stage1 + pa * TILE_BYTES,
-                   TILE_BYTES);
-          bulk_commit();
-        }
+        mbar_wait(&cs->outready[par], (it >> 1) & 1);
+        bulk_s2g(args.layer[l].out + static_cast<size_t>(g.HALO + TILE_M * tile) * SLAB_ROW_BYTES, stage1 + par * TILE_BYTES,
+                 TILE_BYTES);
+        bulk_commit();
+        trace_at(args.trace, it, 5);
+        last = it;
       }
       bulk_wait_all<0>();
-      if (total >= 1) publish(total - 1);
+      if (last >= 0) publish(last);
+    }
+  } else {
+    // ===== flag warp: sees the three neighbour tiles of the previous layer published, then releases the producer =====
+    if (lane == 0) {
+      int l = 0, j = 0;
+      for (int it = 0; it < total; ++it) {
+        // ring of 8: this warp runs up to 8 iterations ahead of the producer, whose loads must not wait for the poll +
+        // fences (~2000 cycles).  Entry it & 7 may be re-armed once the producer has consumed it for iteration it - 8.
+        // (Not an mbarrier parity wait on empty[]: eight iterations are two phases of a 4-stage ring -- parity aliases.)
+        while (it - cs->prod_it >= 8) {
+        }
+        if (l > 0) {
+          const int tile = blockIdx.x + j * grid;
+          const unsigned* f = args.flags + static_cast<size_t>(l - 1) * ntiles;
+          const int t0 = tile > 0 ? tile - 1 : 0, t1 = tile + 1 < ntiles ? tile + 1 : ntiles - 1;
+          unsigned spins = 0;
+          for (;;) {
+            const unsigned f0 = ld_relaxed_u32(f + t0), f1 = ld_relaxed_u32(f + tile), f2 = ld_relaxed_u32(f + t1);
+            if (f0 == args.epoch && f1 == args.epoch && f2 == args.epoch) break;
+            if (++spins > (1u << 21)) {
+              *args.error = 1u;
+              break;
+            }
+          }
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");          // relaxed loads that saw the release stores + fence = acquire
+          asm volatile("fence.proxy.async;" ::: "memory");          // the tiles were written / will be read by the async proxy
+        }
+        mbar_arrive(&cs->flagok[it & 7]);
+        if (++j == cnt) {
+          j = 0;
+          ++l;
+        }
+      }
     }
   }
   tc_fence_before();
@@ -1695,7 +1720,7 @@ static int launch_chain_ns(const ChainArgs& a, const SlabGeom& g, size_t smem, c
   ProfSpan span(BRUNO_PROF_CONV, st);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(FWD_THREADS);
+  cfg.blockDim = dim3(CHAIN_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1769,6 +1794,7 @@ int conv3x3_chain(bool backward, int L, const void* const* in, const void* const
   }
   a.flags = g_chain_flags;
   a.error = g_chain_flags + static_cast<size_t>(CHAIN_MAX_LAYERS) * g_chain_tiles;
+  a.trace = g_conv_trace_host;
   // the flag rows are [L][ntiles] with the CURRENT ntiles as pitch (a launch only reads what it wrote)
   const size_t smem = fixed + static_cast<size_t>(ns) * slab;
   int rc;
