@@ -666,7 +666,9 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
 // loads in flight (~2500 cycles per tile, loads serialised) -> a separate flag warp that owns no asynchronous copies polls,
 // fences and releases the producer through an mbarrier ring; (iii) serial acquire polls -> three relaxed loads + one fence.
 // Left: the tile period inside a layer is ~2230 cycles (per-tap kernel: 2100) and every layer boundary costs ~2200 cycles
-// (the weights are swapped only after the layer's last MMA has retired).  Off by default (bruno_debug_conv_chain).
+// (the weights are swapped only after the layer's last MMA has retired).  Chaining ONLY the 14x14 layers
+// (BRUNO_CHAIN_MAX_TILES=2000) gives 14.17 vs 14.25 ms per step and 4.83 vs 4.91 ms per evaluation: inside the noise.
+// Off by default (bruno_debug_conv_chain).
 constexpr int CHAIN_MAX_LAYERS = 16;
 constexpr int CHAIN_THREADS = FWD_THREADS + 64;   // + second aux / store warp + flag warp
 struct ChainLayer {
@@ -1743,6 +1745,8 @@ int conv3x3_chain(bool backward, int L, const void* const* in, const void* const
   // with fewer than two tiles per CTA every layer is one lock-step round of flag hand-offs: mode 1 leaves those shapes to
   // separate launches, mode 2 chains everything (tests)
   if (g_conv_chain == 1 && g.NT < 2 * num_sms()) return 1;
+  static const char* max_tiles_env = getenv("BRUNO_CHAIN_MAX_TILES");     // experiment: chain only the small layers
+  if (g_conv_chain == 1 && max_tiles_env && g.NT > atoi(max_tiles_env)) return 1;
   if (g_chain_flags == nullptr || g.NT > g_chain_tiles) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {

@@ -1,9 +1,11 @@
 // Dense (fully connected) coupling layers: CouplingLayerDense (nn_extra_nvp.py:190-274) with dense_wn (:408-432).
 //   h1 = ELU((x b) V1 * g1/|V1| + b1);  h2 = ELU(h1 V2 * g2/|V2| + b2)
 //   s = tanh(h2 Ks + bs)(1-b);  t = (h2 Kt + bt)(1-b);  y = x b + (1-b)(x e^s + t);  ld += sum s
-// fp32 throughout (these layers carry 0.4 % of the FLOPs of bn2_omniglot and all of the parity budget of the dense
-// en2 config): a register-tiled CUDA-core SGEMM with fused column-scale / bias / ELU epilogue, plus the elementwise
-// coupling kernels and the hand-written backward, orchestrated in C so that one coupling is ONE host call.
+// fp32 accuracy throughout (these layers carry 0.4 % of the FLOPs of bn2_omniglot and all of the parity budget of the
+// dense en2 config).  GEMMs: the tcgen05 3xTF32 kernel of gemm_tf32.cu by default (fp32-accurate split on the tensor
+// cores), or the register-tiled CUDA-core SGEMM below (strict fp32 FFMA; bruno_debug_gemm_variant(0), and the fallback for
+// unaligned operands), both with the fused column-scale / bias / activation epilogue; plus the elementwise coupling
+// kernels and the hand-written backward, orchestrated in C so that one coupling is ONE host call.
 #include "common.cuh"
 #include "dense_gemm.cuh"
 

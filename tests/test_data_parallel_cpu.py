@@ -110,3 +110,21 @@ def test_uncovered_ranges_of_the_bucketed_allreduce():
     assert uncovered_ranges([(0, 4), (4, 4)], 12) == [(8, 4)]
     covered = sorted([(2, 2), (6, 2)] + uncovered_ranges([(6, 2), (2, 2)], 10))
     assert sum(n for _, n in covered) == 10 and all(covered[i][0] + covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+
+
+def test_test_time_defaults_follow_the_reference_semantics():
+    """config_rnn/defaults.py and config_conditional/defaults.py: which command-line fields override which knobs."""
+    import argparse
+    import importlib
+    d = importlib.reload(importlib.import_module('bruno_b200.config_rnn.defaults'))
+    assert (d.seq_len, d.seq_len_few_shot, d.batch_size_few_shot, d.eval_only_last, d.eps_corr, d.mask_dims) == (20, 2, 20, False, None, False)
+    d.set_parameters(argparse.Namespace(seq_len=6, batch_size=5, mask_dims=1, eps_corr=0.25, unrelated=3))
+    assert d.seq_len == 6 and d.seq_len_few_shot == 6            # one flag feeds both (defaults.py:14-17)
+    assert d.batch_size_few_shot is True                         # (sic) cast to bool in the reference (defaults.py:21)
+    assert d.mask_dims is True and d.eps_corr == 0.25 and d.eval_only_last is False
+    importlib.reload(d)
+    c = importlib.reload(importlib.import_module('bruno_b200.config_conditional.defaults'))
+    assert (c.seq_len, c.n_context) == (16, 1)
+    c.set_parameters(argparse.Namespace(n_context=3))
+    assert (c.seq_len, c.n_context) == (16, 3)
+    importlib.reload(c)
