@@ -79,6 +79,12 @@ class ConditionalTrainer(object):
         return {'variables': {n: v.detach().cpu().clone() for n, v in self.cfg.named_tf_variables()},
                 'slots': [s.cpu() for s in self.slots], 'opt_steps': self.opt_steps}
 
+    def load_state_dict(self, sd):
+        self.cfg.load_tf_variables(sd['variables'])             # the variables are views into the flat buffer
+        for s, t in zip(self.slots, sd['slots']):
+            s.copy_(t.to(self.device))
+        self.opt_steps = sd['opt_steps']
+
 
 def main(argv=None):
     parser = argparse.ArgumentParser()
@@ -92,8 +98,6 @@ def main(argv=None):
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     assert args.nr_gpu == world, '--nr_gpu must equal the number of launched ranks (train.py:22)'
-    if args.resume:
-        raise NotImplementedError('resume of the conditional driver: load the torch checkpoint with config.load_tf_variables')
     if rank == 0:
         print('input args:\n', json.dumps(vars(args), indent=4, separators=(',', ':')))
     np.random.seed(seed=42)
@@ -106,11 +110,24 @@ def main(argv=None):
     config = importlib.import_module('bruno_b200.config_conditional.%s' % args.config_name)
     assert config.batch_size % world == 0
     max_iter = args.max_iter or config.max_iter
-    experiment_id = '%s-%s' % (args.config_name.split('.')[-1], time.strftime("%Y_%m_%d", time.localtime()))
-    save_dir = os.path.join(args.metadata_dir, experiment_id)
+    last_iteration, resumed = 0, None
+    if args.resume:                                        # train.py:31-41
+        save_dir = utils.find_model_metadata(args.metadata_dir + '/', args.config_name)
+        experiment_id = os.path.dirname(save_dir).split('/')[-1]
+        resumed = torch.load(os.path.join(save_dir, 'params.pt'), map_location='cpu', weights_only=False)
+        last_iteration = resumed['iteration']
+        if rank == 0:
+            print('Last iteration', last_iteration)
+            print('Last learning rate', resumed['lr'])
+    else:
+        experiment_id = '%s-%s' % (args.config_name.split('.')[-1], time.strftime("%Y_%m_%d", time.localtime()))
+        save_dir = os.path.join(args.metadata_dir, experiment_id)
+        if rank == 0:
+            utils.autodir(save_dir)
     if rank == 0:
-        utils.autodir(save_dir)
         print('exp_id', experiment_id)
+        if args.resume:
+            print('Resuming training')
     trainer = ConditionalTrainer(config, device, world, rank)
     lr = config.learning_rate
     student_grad_scale = config.scale_student_grad
@@ -127,9 +144,15 @@ def main(argv=None):
         if iteration == 0:                                  # the init pass, no weight update (train.py:178-183)
             if rank == 0:
                 print('initializing the model...')
-            trainer.materialize(torch.from_numpy(x_batch).to(device), torch.from_numpy(y_batch).to(device), init=True)
+            trainer.materialize(torch.from_numpy(x_batch).to(device), torch.from_numpy(y_batch).to(device), init=not args.resume)
+            if resumed is not None:
+                trainer.load_state_dict(resumed)
             if rank == 0:
                 print('Number of parameters', trainer.n_params)
+            continue
+        if args.resume and iteration < last_iteration:      # fast-forward schedules and data (train.py:172-175)
+            if rank == 0 and iteration % (args.print_every * 10) == 0:
+                print(iteration, 'skipping training')
             continue
         xs, ys = np.split(x_batch, world)[rank], np.split(y_batch, world)[rank]
         loss = trainer.train_step(torch.from_numpy(np.ascontiguousarray(xs)).to(device),

@@ -190,6 +190,10 @@ def test_conditional_train_driver_runs(tmp_path):
     assert avg[-1] < avg[0]                      # the loss of the untrained flow drops within a few RMSProp steps
     import os
     assert any(f == 'params.pt' for _, _, fs in os.walk(str(tmp_path)) for f in fs)
+    # resume: restores variables and optimiser slots, fast-forwards to the saved iteration, continues
+    trainer2, avg2 = train.main(['--config_name', 'm1_shapenet', '--max_iter', '9', '--print_every', '2', '--resume', '1',
+                                 '--metadata_dir', str(tmp_path)])
+    assert trainer2.opt_steps == 6 + 2 and all(np.isfinite(a) for a in avg2)
     # the evaluation and sampling drivers restore that checkpoint
     from bruno_b200.config_conditional import test_nll, test_samples
     test, tr = test_nll.main(['--config_name', 'm1_shapenet', '--seq_len', '4', '--n_context', '1', '--n_batches', '2',
