@@ -67,7 +67,7 @@ def build(force=False, verbose=False):
         fh.write('\n'.join(log))
     if verbose:
         print('\n'.join(log))
-    cmd = [_nvcc(), '-shared', '-o', LIB] + objs + ['-lcudart']
+    cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs + ['-lcudart']
     subprocess.check_call(cmd)
     with open(stamp, 'w') as fh:
         fh.write(dig)
