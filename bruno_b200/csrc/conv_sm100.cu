@@ -386,6 +386,14 @@ conv3x3_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack
 // bound by its epilogue; both are kept and selected per process (bruno_debug_conv_variant) so they can be A/B timed.
 // Four 64-column TMEM accumulators decouple the issuer from the two epilogue groups.
 constexpr int TAP_ACC = 4;
+// (dgrad + addend) epilogue: take the addend tile global -> registers instead of staging it through shared memory?  On paper
+// it saves 32 KB of port traffic per tile and frees a slab stage; measured it DOUBLES the 28x28 launch (83.9 vs 45.7 us):
+// a warp's 16-byte loads touch 32 different lines, the LSU path costs the tensor pipe far more than the staging did.
+#ifdef BRUNO_TAP_AUX2_DIRECT
+constexpr bool TAP_AUX2_DIRECT = true;
+#else
+constexpr bool TAP_AUX2_DIRECT = false;
+#endif
 constexpr int TAP_MAX_STAGES = 4;          // slab ring depth: as many as fit next to the staging buffers (host decides)
 
 struct TapSmem {
@@ -411,7 +419,7 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
   uint8_t* slabs = smem + W_BYTES;
   uint8_t* stage1 = slabs + nstage * slab_bytes;                       // [2][TILE_BYTES] aux1 in / output out (in place)
   uint8_t* stage2 = stage1 + 2 * TILE_BYTES;                           // [2][TILE_BYTES] aux2 (MODE_ADD_MUL only)
-  TapSmem* cs = reinterpret_cast<TapSmem*>(stage2 + (mode_has_aux2(MODE) ? 2 * TILE_BYTES : 0));
+  TapSmem* cs = reinterpret_cast<TapSmem*>(stage2 + ((mode_has_aux2(MODE) && !TAP_AUX2_DIRECT) ? 2 * TILE_BYTES : 0));
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   constexpr bool HAS_BIAS = MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR;
 
@@ -538,9 +546,18 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
     const float inv_p = 1.0f / static_cast<float>(g.P);
     const uint32_t st1 = smem_u32(stage1 + grp * TILE_BYTES + row * SLAB_ROW_BYTES);
     const uint32_t st2 = smem_u32(stage2 + grp * TILE_BYTES + row * SLAB_ROW_BYTES);
+    if (mode_has_aux2(MODE) && TAP_AUX2_DIRECT) asm volatile("griddepcontrol.wait;" ::: "memory");   // reads aux2 from global
     int it = grp;
     for (; tile < ntiles; tile += tile_stride, it += 2) {
       const int a = it % TAP_ACC;
+      // the addend tile (aux2) goes global -> registers: staging it costs 32 KB of shared-memory port traffic per tile and
+      // a fourth pair of staging buffers (= one slab stage).  Issued before the accumulator wait: its latency hides there.
+      uint4 t2[4];
+      if (mode_has_aux2(MODE) && TAP_AUX2_DIRECT) {
+        const uint8_t* arow = aux2 + static_cast<size_t>(g.HALO + TILE_M * tile + row) * SLAB_ROW_BYTES;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) t2[jj] = ldg_nc_u4(arow + (((half * 4 + jj) ^ R7) << 4));
+      }
       const int yy = static_cast<int>((static_cast<float>(q_img) + 0.5f) * inv_p);
       const int xx = q_img - yy * g.P;
       const bool valid = data_row < g.data_rows && yy >= 1 && xx >= 1;
@@ -590,7 +607,7 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
         } else {
           float sk[8], t[8];
           unpack8(lds_u4(st1 + pos), sk);
-          unpack8(lds_u4(st2 + pos), t);
+          unpack8(TAP_AUX2_DIRECT ? t2[jj] : lds_u4(st2 + pos), t);
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
         }
@@ -619,9 +636,10 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
           bulk_wait_read<0>();                  // the store of tile it-2 has finished reading this staging buffer
           if (mode_has_aux1(MODE)) {
             const size_t off = static_cast<size_t>(g.HALO + TILE_M * tile) * SLAB_ROW_BYTES;
-            mbar_arrive_expect_tx(&cs->auxfull[b], mode_has_aux2(MODE) ? 2 * TILE_BYTES : TILE_BYTES);
+            constexpr bool STAGE_AUX2 = mode_has_aux2(MODE) && !TAP_AUX2_DIRECT;
+            mbar_arrive_expect_tx(&cs->auxfull[b], STAGE_AUX2 ? 2 * TILE_BYTES : TILE_BYTES);
             bulk_g2s(stage1 + b * TILE_BYTES, aux1 + off, TILE_BYTES, &cs->auxfull[b]);
-            if (mode_has_aux2(MODE)) bulk_g2s(stage2 + b * TILE_BYTES, aux2 + off, TILE_BYTES, &cs->auxfull[b]);
+            if (STAGE_AUX2) bulk_g2s(stage2 + b * TILE_BYTES, aux2 + off, TILE_BYTES, &cs->auxfull[b]);
           } else {
             mbar_arrive(&cs->auxfull[b]);
           }
@@ -1642,7 +1660,9 @@ static int launch_conv_tap_ns(const void* in, const void* w, const float* bias, 
   return check_launch("conv3x3_tap_kernel");
 }
 
-static size_t tap_fixed_smem(int mode) { return 1024 + W_BYTES + (mode_has_aux2(mode) ? 4 : 2) * TILE_BYTES + sizeof(TapSmem) + 64; }
+static size_t tap_fixed_smem(int mode) {
+  return 1024 + W_BYTES + ((mode_has_aux2(mode) && !TAP_AUX2_DIRECT) ? 4 : 2) * TILE_BYTES + sizeof(TapSmem) + 64;
+}
 static int tap_stages(const SlabGeom& g, int mode) {
   const size_t slab = static_cast<size_t>(TILE_M + 2 * g.HALO + 8) * SLAB_ROW_BYTES;
   const size_t fixed = tap_fixed_smem(mode);

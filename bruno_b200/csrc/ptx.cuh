@@ -169,6 +169,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// read-only 128-bit global load that does not allocate in L1 (streamed once)
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* gptr) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(gptr));
+  return r;
+}
+
 // explicit shared-space 128-bit accesses (a generic LD/ST on a shared address pays the generic->shared translation)
 __device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
   uint4 r;
