@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace bruno {
 
@@ -455,6 +456,287 @@ __global__ void process_fwd_finalize(const float* __restrict__ scratch, float* _
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// forward scan, persistent + bulk-copy ring (the default when D % 4 == 0 and the pointers are 16-byte aligned)
+// ------------------------------------------------------------------------------------------------------------
+// The register-staged kernel above is latency-bound (ncu: 38 % issue utilisation, long-scoreboard the top stall, 14
+// warps per SM at 128 registers, and a block lives for only T / RS = 5 loop iterations, so its prologue -- dependent
+// L2 loads of the coefficients -- and its epilogue -- block barrier, cross-warp reduce -- leave the memory pipe idle for
+// a sizeable share of its life).  This variant keeps HBM busy independently of what the math warps are doing:
+//   * persistent blocks (grid.x = resident blocks), each walking row groups g = blockIdx.x, += gridDim.x;
+//   * one producer warp: an elected lane streams z[rows of the group][step][segment] with 1-D bulk copies (UBLKCP; a
+//     row's step is one contiguous D*4-byte run) into an NSTAGE-deep shared-memory ring, full/empty mbarriers per
+//     stage, running ahead across group boundaries so the next group's first steps land while this group reduces;
+//   * consumer warps: same thread <-> (4 dims x NB rows) mapping, same butterfly and same cross-warp order as the
+//     kernel above (results are bit-identical for equal NB / RS), z from LDS.128, the per-step coefficients prefetched
+//     one step ahead with LDG (L1/L2-resident table), the [T][warps][NV] partials double-buffered by group parity so
+//     one consumer-only named barrier per group suffices.
+template <int KIND, int NB, bool PRIOR, int NSTAGE, int RS, int MINB, bool CPF, bool STATE>
+__global__ void __launch_bounds__(256, MINB)
+process_fwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ mu0, const float* __restrict__ tab,
+                        float* __restrict__ s1, float* __restrict__ s2, float* __restrict__ lp,
+                        float* __restrict__ lp_prior, float* __restrict__ scratch, int B, int T, int D) {
+  constexpr int VEC = 4;
+  constexpr int NCF = ncf_of(KIND);
+  constexpr int NV = PRIOR ? NB * 2 : NB;
+  constexpr int NVAL = NV * RS;
+  static_assert(NVAL <= 32, "at most 32 values per butterfly");
+  extern __shared__ __align__(16) unsigned char ring_smem[];
+  const int ncons = blockDim.x - 32, ncw = ncons >> 5;       // consumer threads / warps; the last warp produces
+  const int seg_cap = ncons * VEC;                            // dims per segment (row slot length in the ring)
+  const int seg_d0 = blockIdx.y * seg_cap;
+  const int seg_len = min(D - seg_d0, seg_cap);
+  float* stage = reinterpret_cast<float*>(ring_smem);                                  // [NSTAGE][NB][seg_cap]
+  float* sred = stage + static_cast<size_t>(NSTAGE) * NB * seg_cap;                     // [2][T][ncw][NV]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sred + static_cast<size_t>(2) * T * ncw * NV);
+  uint64_t* empty = full + NSTAGE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int groups = ceil_div(B, NB);
+  const size_t rowTD = static_cast<size_t>(T) * D;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], ncw);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == ncw) {                                          // ---------------- producer warp
+    if (lane == 0) {
+      const uint32_t seg_bytes = static_cast<uint32_t>(seg_len) * 4u;
+      int s = 0;
+      uint32_t ph = 1;                                        // fresh barrier: waiting on parity 1 falls through
+      for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+        const float* src[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) src[j] = z + static_cast<size_t>(min(g * NB + j, B - 1)) * rowTD + seg_d0;
+        for (int n = 0; n < T; ++n) {
+          mbar_wait(&empty[s], ph);
+          mbar_arrive_expect_tx(&full[s], seg_bytes * NB);
+          float* dst = stage + static_cast<size_t>(s) * NB * seg_cap;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            bulk_g2s(dst + j * seg_cap, src[j], seg_bytes, &full[s]);
+            src[j] += D;
+          }
+          if (++s == NSTAGE) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps
+  const int dl = threadIdx.x * VEC;                           // dim inside the segment
+  const bool active = dl < seg_len;
+  const int d0 = seg_d0 + dl;
+  const int d0c = active ? d0 : seg_d0;                       // inactive lanes compute on dim seg_d0 and are masked
+  const int dlc = active ? dl : 0;
+  const float lane_mask = active ? 1.f : 0.f;
+
+  Vf<VEC> pc[N_PRIOR];
+  Vf<VEC> c_e = zerov<VEC>(), c_f0 = zerov<VEC>(), c_a0 = zerov<VEC>(), c_da = zerov<VEC>();
+  const Vf<VEC> mu = ldv<VEC>(mu0 + d0c);
+#pragma unroll
+  for (int i = 0; i < N_PRIOR; ++i) pc[i] = PRIOR ? ldv<VEC>(tab + static_cast<size_t>(T * NCF + i) * D + d0c) : zerov<VEC>();
+  if (KIND == BRUNO_TP) {
+    c_a0 = ldv<VEC>(tab + static_cast<size_t>(5) * D + d0c);
+    const Vf<VEC> b0v = ldv<VEC>(tab + static_cast<size_t>(6) * D + d0c);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) c_da.x[e] = c_a0.x[e] - b0v.x[e];
+  }
+  const bool mu_zero = __all_sync(0xffffffffu, [&] { bool zr = true;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) zr = zr && (mu.x[e] == 0.f);
+    return zr; }());
+
+  struct Coef {
+    Vf<VEC> w, dd, C;                                         // TP: w, dd w, C;   GP: dd, I, C
+  };
+  const float* const tp0 = tab + d0c;
+  const size_t tstep = static_cast<size_t>(NCF) * D;
+  auto load_coef = [&](const float* tp) {
+    Coef c;
+    c.w = ldv<VEC>(tp);
+    c.dd = ldv<VEC>(tp + D);
+    c.C = ldv<VEC>(tp + (KIND == BRUNO_TP ? 4 : 2) * static_cast<size_t>(D));
+    return c;
+  };
+  const float* tpn = tp0;                                     // table row of the NEXT step (CPF) / of this step
+  Coef cn;
+  if (CPF) cn = load_coef(tpn);
+  int s = 0;
+  uint32_t ph = 0;
+  int par = 0;
+
+  // The Student-t scan carries q_n = 1 + beta_n / (nu0 - 2) recursively: the Mahalanobis term of the posterior obeys
+  // beta_{n+1} = beta_n + (x - mu_n)^2 / sigma_n (the literal update of student:100-106), i.e. q_{n+1} = q_n + r_n^2 = u_n,
+  // so lg2(q_n) is the previous step's lg2(u_{n-1}): ONE MUFU and 6 FP instructions per element instead of 2 + 11 for
+  // the closed form q_n = 1 + e S2 + f_n S1^2, no S2 in the hot loop, and none of the closed form's cancellation.
+  // STATE = running prefix sums are read and written back (the reference's step-by-step API); the model builders'
+  // sequence-at-once path runs the !STATE instantiation, which never touches S2.
+  {
+    constexpr bool FAST = !STATE;
+    Vf<VEC> S1[NB], S2[NB], Q[NB], LQ[NB];
+    for (int g = blockIdx.x; g < groups; g += gridDim.x, par ^= 1) {
+      const int b0 = g * NB;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        S1[j] = zerov<VEC>();
+        S2[j] = zerov<VEC>();
+        LQ[j] = zerov<VEC>();
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) Q[j].x[e] = 1.f;
+      }
+      if (STATE) {
+        if (KIND == BRUNO_TP) {
+          c_e = ldv<VEC>(tab + static_cast<size_t>(2) * D + d0c);
+          c_f0 = ldv<VEC>(tab + static_cast<size_t>(3) * D + d0c);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (active && b0 + j < B) {
+            S1[j] = ldv<VEC>(s1 + static_cast<size_t>(b0 + j) * D + d0);
+            if (KIND == BRUNO_TP) {
+              S2[j] = ldv<VEC>(s2 + static_cast<size_t>(b0 + j) * D + d0);
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) {
+                Q[j].x[e] = fmaf(c_f0.x[e], S1[j].x[e] * S1[j].x[e], fmaf(c_e.x[e], S2[j].x[e], 1.f));
+                LQ[j].x[e] = fast_lg2(Q[j].x[e]);
+              }
+            }
+          }
+      }
+      float* sr = sred + static_cast<size_t>(par) * T * ncw * NV;
+
+      auto do_step = [&](int n, float* vals_pp) {
+        Coef c;
+        if (CPF) {                                            // coefficients one step ahead (12 more registers)
+          c = cn;
+          tpn = (n + 1 == T) ? tp0 : tpn + tstep;
+          cn = load_coef(tpn);
+        } else {
+          c = load_coef(tpn);
+          tpn = (n + 1 == T) ? tp0 : tpn + tstep;
+        }
+        mbar_wait(&full[s], ph);
+        const float* xs = stage + static_cast<size_t>(s) * NB * seg_cap + dlc;
+        Vf<VEC> x[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const float4 t = *reinterpret_cast<const float4*>(xs + j * seg_cap);
+          x[j].x[0] = t.x; x[j].x[1] = t.y; x[j].x[2] = t.z; x[j].x[3] = t.w;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == NSTAGE) {
+          s = 0;
+          ph ^= 1u;
+        }
+        if (!mu_zero) {                                       // warp-uniform; mu0 is 0 in every reference config
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) x[j].x[e] -= mu.x[e];
+        }
+        const float fn = static_cast<float>(n);
+        Vf<VEC> a2, b2;
+        float csum = 0.f, psum = 0.f;                         // the batch-independent additive constants of this step
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          if (KIND == BRUNO_TP) {
+            a2.x[e] = fmaf(fn, c_da.x[e], c_a0.x[e]);
+            b2.x[e] = a2.x[e] - c_da.x[e];
+          }
+          csum += c.C.x[e];
+          if (PRIOR) psum += pc[1].x[e];
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          float acc = csum, accp = psum;
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const float xz = x[j].x[e];
+            if constexpr (KIND == BRUNO_TP) {
+              const float r = fmaf(-c.dd.x[e], S1[j].x[e], c.w.x[e] * xz);
+              const float u = fmaf(r, r, Q[j].x[e]);
+              const float lu = fast_lg2(u);
+              acc = fmaf(-a2.x[e], lu, fmaf(b2.x[e], LQ[j].x[e], acc));
+              if (PRIOR) accp = fmaf(-pc[2].x[e], fast_lg2(fmaf(xz * xz, pc[0].x[e], 1.f)), accp);
+              S1[j].x[e] += xz;
+              if (!FAST) S2[j].x[e] = fmaf(xz, xz, S2[j].x[e]);
+              Q[j].x[e] = u;
+              LQ[j].x[e] = lu;
+            } else {
+              const float r = fmaf(-c.w.x[e], S1[j].x[e], xz);
+              acc = fmaf(-c.dd.x[e], r * r, acc);
+              if (PRIOR) accp = fmaf(-pc[0].x[e], xz * xz, accp);
+              S1[j].x[e] += xz;
+            }
+          }
+          if (PRIOR) {
+            vals_pp[2 * j] = acc;
+            vals_pp[2 * j + 1] = accp;
+          } else {
+            vals_pp[j] = acc;
+          }
+        }
+      };
+
+      int n0 = 0;
+      for (; n0 + RS <= T; n0 += RS) {
+        float vals[NVAL];
+#pragma unroll
+        for (int pp = 0; pp < RS; ++pp) do_step(n0 + pp, vals + pp * NV);
+#pragma unroll
+        for (int i = 0; i < NVAL; ++i) vals[i] *= lane_mask;
+        warp_multi_reduce<NVAL>(vals, lane);
+        if (lane_is_writer<NVAL>(lane)) {
+          const int slot = slot_of_lane<NVAL>(lane);
+          sr[((n0 + slot / NV) * ncw + warp) * NV + (slot % NV)] = vals[0];
+        }
+      }
+      for (; n0 < T; ++n0) {
+        float vals[NV];
+        do_step(n0, vals);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) vals[i] *= lane_mask;
+        warp_multi_reduce<NV>(vals, lane);
+        if (lane_is_writer<NV>(lane)) sr[(n0 * ncw + warp) * NV + slot_of_lane<NV>(lane)] = vals[0];
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");   // consumers only; the producer keeps streaming
+      const int nseg = gridDim.y;
+      for (int i = threadIdx.x; i < T * NV; i += ncons) {
+        const int n = i / NV, idx = i % NV, j = PRIOR ? idx >> 1 : idx, which = PRIOR ? idx & 1 : 0;
+        if (b0 + j >= B) continue;
+        float sum = 0.f;
+        for (int w = 0; w < ncw; ++w) sum += sr[(n * ncw + w) * NV + idx];
+        if (nseg == 1) {
+          if (which == 0) lp[static_cast<size_t>(b0 + j) * T + n] = sum;
+          else lp_prior[static_cast<size_t>(b0 + j) * T + n] = sum;
+        } else {
+          scratch[((static_cast<size_t>(blockIdx.y) * B + b0 + j) * T + n) * 2 + which] = sum;
+        }
+      }
+      if (STATE && active) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (b0 + j < B) {
+            stv<VEC>(s1 + static_cast<size_t>(b0 + j) * D + d0, S1[j]);
+            if (KIND == BRUNO_TP) stv<VEC>(s2 + static_cast<size_t>(b0 + j) * D + d0, S2[j]);
+          }
+      }
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
 // backward scan
 // ------------------------------------------------------------------------------------------------------------
 // double-single accumulation of S2 = sum (x - mu0)^2 in the backward: the reverse pass recovers the prefix sums by
@@ -702,13 +984,16 @@ __global__ void process_sample_kernel(int kind, const float* __restrict__ rvs, c
 struct ScanGeom {
   int vec, threads, nseg;
 };
+// Forward-scan variant: 0 = default (bulk-copy ring kernel when D % 4 == 0 and the pointers are aligned, else the
+// register-staged kernel), 1-4 / 9 = register-staged variants (9 = its default shape), 10-13 = ring variants.
+// BRUNO_TP_VARIANT in the environment or bruno_process_set_fwd_variant() at run time (A/B benches and tests).
+static int g_fwd_variant = -1;
 static int fwd_variant() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_fwd_variant < 0) {
     const char* e = getenv("BRUNO_TP_VARIANT");
-    v = e ? atoi(e) : 0;
+    g_fwd_variant = e ? atoi(e) : 0;
   }
-  return v;
+  return g_fwd_variant;
 }
 
 static ScanGeom scan_geom(int D, bool ptr_ok, bool fwd = false) {
@@ -759,9 +1044,83 @@ static int launch_fwd_variant(const float* z, const float* mu0, const float* tab
   return rc;
 }
 
+// Ring kernel launch.  Returns +1 when this shape cannot take the ring path (caller falls back to the register-staged
+// kernel): T too long for the shared-memory partials.
+constexpr int RING_CONS = 224;   // consumer threads per block at most (7 warps + 1 producer warp = 256 threads)
+static ScanGeom ring_geom(int D) {
+  ScanGeom g;
+  g.vec = 4;
+  const int chunks = D / 4;
+  g.threads = chunks >= RING_CONS ? RING_CONS : ((chunks + 31) / 32) * 32;
+  g.nseg = (chunks + g.threads - 1) / g.threads;
+  return g;
+}
+template <int KIND, int NB, int NSTAGE, int RS, int MINB, bool CPF>
+static int launch_fwd_ring(const float* z, const float* mu0, const float* table, float* s1, float* s2, float* lp,
+                           float* lp_prior, float* scratch, int B, int T, int D, cudaStream_t st) {
+  const ScanGeom g = ring_geom(D);
+  const int ncw = g.threads / 32;
+  const size_t smem = static_cast<size_t>(NSTAGE) * NB * g.threads * 4 * sizeof(float) +
+                      static_cast<size_t>(2) * T * ncw * NB * 2 * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
+  if (smem > 112 * 1024 || (g.nseg > 1 && scratch == nullptr)) return 1;
+  auto k = s1 ? (lp_prior ? process_fwd_ring_kernel<KIND, NB, true, NSTAGE, RS, MINB, CPF, true>
+                          : process_fwd_ring_kernel<KIND, NB, false, NSTAGE, RS, MINB, CPF, true>)
+              : (lp_prior ? process_fwd_ring_kernel<KIND, NB, true, NSTAGE, RS, MINB, CPF, false>
+                          : process_fwd_ring_kernel<KIND, NB, false, NSTAGE, RS, MINB, CPF, false>);
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  // resident blocks per SM of this instantiation at this (threads, smem): queried once per change, not per launch
+  static struct { size_t smem; int threads, per_sm; } cache[4] = {};
+  auto& ce = cache[(s1 ? 2 : 0) + (lp_prior ? 1 : 0)];
+  if (ce.smem != smem || ce.threads != g.threads) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, g.threads + 32, smem);
+    ce.smem = smem;
+    ce.threads = g.threads;
+    ce.per_sm = per_sm;
+  }
+  const int per_sm = ce.per_sm;
+  if (per_sm < 1) return 1;
+  const int groups = ceil_div(B, NB);
+  const int resident = ceil_div(per_sm * sm_count, g.nseg);
+  dim3 grid(groups < resident ? groups : resident, g.nseg);
+  int rc;
+  {
+    ProfSpan span(BRUNO_PROF_PROCESS_FWD, st);
+    k<<<grid, g.threads + 32, smem, st>>>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D);
+    rc = check_launch("process_fwd_ring_kernel");
+  }
+  if (rc) return rc;
+  if (g.nseg > 1) {
+    process_fwd_finalize<<<ceil_div(B * T, 256), 256, 0, st>>>(scratch, lp, lp_prior, g.nseg, B * T);
+    rc = check_launch("process_fwd_finalize");
+  }
+  return rc;
+}
+
 template <int KIND, int VEC>
 static int launch_fwd(const float* z, const float* mu0, const float* table, float* s1, float* s2, float* lp,
                       float* lp_prior, float* scratch, int B, int T, int D, const ScanGeom& g, cudaStream_t st) {
+  if constexpr (VEC == 4) {
+    const int v = fwd_variant();
+    if (v == 0 || v >= 10) {
+      int rc;
+      switch (v) {
+        case 11: rc = launch_fwd_ring<KIND, 2, 8, 2, 3, true>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 12: rc = launch_fwd_ring<KIND, 2, 8, 4, 3, false>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 13: rc = launch_fwd_ring<KIND, 2, 8, 2, 4, false>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 14: rc = launch_fwd_ring<KIND, 4, 6, 2, 2, true>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 15: rc = launch_fwd_ring<KIND, 4, 4, 2, 2, false>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        default: rc = launch_fwd_ring<KIND, 4, 4, 4, 2, true>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+      }
+      if (rc <= 0) return rc;
+    }
+  }
   if (g.threads > 256)   // only the 2-wide layout uses blocks of up to 512 threads
     return launch_fwd_variant<KIND, VEC, 4, 2, 2, 2, 512>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, g, st);
   switch (fwd_variant()) {
@@ -823,8 +1182,10 @@ int bruno_process_table(int kind, const float* var_vbl, const float* nu_vbl, con
   return check_launch("process_table_kernel");
 }
 
+void bruno_process_set_fwd_variant(int variant) { g_fwd_variant = variant < 0 ? 0 : variant; }
+
 size_t bruno_process_scratch_floats(int B, int T, int D) {
-  const int nseg = scan_geom(D, false).nseg;  // worst case: the scalar (unaligned) path
+  const int nseg = scan_geom(D, false).nseg;  // worst case: the scalar (unaligned) path (>= the ring kernel's segments)
   return nseg > 1 ? static_cast<size_t>(nseg) * B * T * 2 : 0;
 }
 

@@ -75,6 +75,10 @@ int bruno_process_table(int kind, const float* var_vbl, const float* nu_vbl, con
  * `table` comes from bruno_process_table(kind, ..., n0, T, D).  `scratch` holds >= bruno_process_scratch_floats
  * floats (only used when D is split across blocks). */
 size_t bruno_process_scratch_floats(int B, int T, int D);
+/* Picks the forward-scan kernel for A/B measurements and the variant-equivalence test: 0 = default (persistent
+ * bulk-copy ring kernel when D % 4 == 0 and all pointers are 16-byte aligned, register-staged kernel otherwise),
+ * 9 = always the register-staged kernel, 10-14 = ring shapes.  Same results for every value. */
+void bruno_process_set_fwd_variant(int variant);
 int bruno_process_fwd(int kind, const float* z, const float* mu0, const float* table, float* s1, float* s2,
                       float* lp, float* lp_prior, float* scratch, int B, int T, int D, void* stream);
 

@@ -190,3 +190,50 @@ def test_backward_is_finite_for_huge_latents(kind):
         a = a.double().cpu()
         assert torch.isfinite(a).all()
         assert (a - b).abs().max().item() <= 5e-3 * (b.abs().max().item() + 1e-12)
+
+
+@pytest.mark.parametrize('kind', ['tp', 'gp'])
+@pytest.mark.parametrize('B,T,D,mu', [(7, 20, 784, 0.), (5, 7, 3600, 0.), (9, 3, 40, 0.4), (1030, 20, 784, 0.)])
+def test_forward_scan_variants_agree(kind, B, T, D, mu):
+    """The persistent bulk-copy ring kernel (default, shapes 10-15) against the register-staged scan (9) and the
+    oracle: ragged row groups, a ragged last segment (3600 = 4 x 896 + 16), non-zero mu0, more groups than resident
+    blocks, and the running-state entry (s1/s2 read and written back)."""
+    from bruno_b200 import _lib
+    from bruno_b200.process import build_table
+    layer, P = _layer(kind, D, seed=3, mu=mu)
+    g = torch.Generator().manual_seed(B + D)
+    z = (torch.randn(B, T, D, generator=g) * 1.3 + 0.5 * torch.randn(B, 1, D, generator=g)).float().cuda()
+    out = {}
+    try:
+        for v in (9, 0, 10, 11, 12, 13, 14, 15):
+            _lib.query('bruno_process_set_fwd_variant', v)
+            lp, pr = layer.sequence_log_likelihoods(z)
+            out[v] = (lp.detach().clone(), pr.detach().clone())
+        for v in (0, 10, 11, 12, 13, 14, 15):
+            assert torch.allclose(out[v][0], out[9][0], rtol=3e-5, atol=1e-3), (v, (out[v][0] - out[9][0]).abs().max().item())
+            assert torch.allclose(out[v][1], out[9][1], rtol=3e-5, atol=1e-3), v
+        if B <= 16:
+            lp_o, pr_o = O.process_log_probs(_oracle_proc(kind, P, mu=mu), z.double().cpu())
+            _close(out[0][0], lp_o)
+            _close(out[0][1], pr_o)
+        # running state: the first T1 steps, then the rest from the stored prefix sums
+        T1 = T // 2
+        if T1 > 0:
+            nu = layer.nu_vbl.detach() if kind == 'tp' else None
+            for v in (9, 0):
+                _lib.query('bruno_process_set_fwd_variant', v)
+                s1 = torch.zeros(B, D, device='cuda')
+                s2 = torch.zeros(B, D, device='cuda')
+                lps = []
+                for n0, zz in ((0, z[:, :T1].contiguous()), (T1, z[:, T1:].contiguous())):
+                    Tn = zz.shape[1]
+                    tab = build_table(layer.kind, layer.var_vbl.detach(), nu, layer.corr_vbl.detach(), layer.mu, None,
+                                      layer.min_nu, n0, Tn, False)
+                    lp = torch.empty(B, Tn, device='cuda')
+                    scratch = torch.empty(max(_lib.query('bruno_process_scratch_floats', B, Tn, D), 1), device='cuda')
+                    _lib.call('bruno_process_fwd', layer.kind, zz, layer.mu, tab, s1, s2, lp, None, scratch, B, Tn, D)
+                    lps.append(lp)
+                lp_cat = torch.cat(lps, 1)
+                assert torch.allclose(lp_cat, out[9][0], rtol=3e-5, atol=2e-3), (v, (lp_cat - out[9][0]).abs().max().item())
+    finally:
+        _lib.query('bruno_process_set_fwd_variant', 0)

@@ -25,11 +25,33 @@ def timeit(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters * 1e-3
 
 
+def sweep_variants(variants, Bs, T, D, peak):
+    for kind, layer in (('tp', StudentRecurrentLayer((D,))), ('gp', GaussianRecurrentLayer((D,)))):
+        for B in Bs:
+            z = torch.randn(B, T, D, device='cuda')
+            nu = layer.nu_vbl.detach() if kind == 'tp' else None
+            tab = build_table(layer.kind, layer.var_vbl.detach(), nu, layer.corr_vbl.detach(), layer.mu, None, 2.0, 0, T, False)
+            lp = torch.empty(B, T, device='cuda')
+            lpp = torch.empty(B, T, device='cuda')
+            scratch = torch.empty(max(_lib.query('bruno_process_scratch_floats', B, T, D), 1), device='cuda')
+            for v in variants:
+                _lib.query('bruno_process_set_fwd_variant', v)
+                for name, prior, nbytes in (('fwd', None, 4 * B * T * D + 4 * B * T), ('fwd+prior', lpp, 4 * B * T * D + 8 * B * T)):
+                    t = timeit(lambda: _lib.call('bruno_process_fwd', layer.kind, z, layer.mu, tab, None, None, lp, prior, scratch, B, T, D))
+                    gbs = nbytes / t * 1e-9
+                    print('variant %2d %s %-9s B=%6d T=%d D=%d  %8.1f us  %7.1f GB/s  (%.1f%% of measured %.0f GB/s)' % (
+                        v, kind, name, B, T, D, t * 1e6, gbs, 100 * gbs / peak, peak), flush=True)
+            _lib.query('bruno_process_set_fwd_variant', 0)
+
+
 def main():
     peaks = json.load(open(os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json'))) if os.path.exists(
         os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json')) else {'hbm_gbs': 6650.0}
     Bs = [int(a) for a in sys.argv[1:]] or [32, 4096, 16384, 65536]
     T, D = 20, 784
+    if os.environ.get('BENCH_VARIANTS'):          # forward-scan A/B: BENCH_VARIANTS=9,10,14 python tools/bench_process.py 65536
+        sweep_variants([int(v) for v in os.environ['BENCH_VARIANTS'].split(',')], Bs, T, D, peaks['hbm_gbs'])
+        return
     for kind, layer in (('tp', StudentRecurrentLayer((D,))), ('gp', GaussianRecurrentLayer((D,)))):
         for B in Bs:
             z = torch.randn(B, T, D, device='cuda')
