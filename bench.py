@@ -276,6 +276,44 @@ def main():
                         'such a launch: %.0f (in + out slab) to %.0f (in + skip + out)' % (
                             tinfo['source'], tinfo['algorithmic_bytes_per_launch']['mode0 (in+out slab)'],
                             tinfo['algorithmic_bytes_per_launch']['mode1 (in+skip+out)']))
+    # t-process forward scan against the HBM roofline: the training shape (B = 32) is launch-bound, so the scan is also
+    # timed alone on a batch far larger than L2 (16384 sequences = 1.03 GB of latents), CUDA events on the launch stream
+    scan = None
+    try:
+        from bruno_b200.process import build_table
+        from bruno_b200.nn_extra_student import StudentRecurrentLayer
+        from bruno_b200.nn_extra_gauss import GaussianRecurrentLayer
+        Dz, Bz = H * W * C, 16384
+        lay = GaussianRecurrentLayer((Dz,)) if args.config_name.endswith('_gp') else StudentRecurrentLayer((Dz,))
+        zz = torch.randn(Bz, T, Dz, device=dev)
+        nu = lay.nu_vbl.detach() if lay.nu_vbl is not None else None
+        tab = build_table(lay.kind, lay.var_vbl.detach(), nu, lay.corr_vbl.detach(), lay.mu, None, lay.min_nu, 0, T, False)
+        lpz = torch.empty(Bz, T, device=dev)
+        scr = torch.empty(max(_lib.query('bruno_process_scratch_floats', Bz, T, Dz), 1), device=dev)
+
+        def scan_once():
+            _lib.call('bruno_process_fwd', lay.kind, zz, lay.mu, tab, None, None, lpz, None, scr, Bz, T, Dz)
+        for _ in range(3):
+            scan_once()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            scan_once()
+        e1.record()
+        torch.cuda.synchronize()
+        t_scan = e0.elapsed_time(e1) * 1e-3 / 10
+        alg = 4.0 * Bz * T * Dz + 4.0 * Bz * T                # z read once + log-probs written
+        hbm = peaks.get('hbm_gbs', 6550.0)
+        scan = {'bound': 'hbm', 'kernel': 'process_fwd_ring_kernel (%s forward scan, persistent bulk-copy ring)' % (
+                    'GP' if lay.nu_vbl is None else 'TP'),
+                'achieved': alg / t_scan * 1e-9, 'peak': hbm, 'unit': 'GB/s', 'frac': alg / t_scan * 1e-9 / hbm,
+                'traffic': None, 'us_per_launch': t_scan * 1e6, 'shape': [Bz, T, Dz],
+                'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback'}
+        del zz
+    except Exception as exc:                                   # the bench line must not die on the side measurement
+        scan = {'error': repr(exc)}
+
     seqs = B * world
     line = {
         'metric': '%s_train_seqs_per_sec' % args.config_name, 'value': seqs * steps / (ms_train * 1e-3), 'unit': 'seqs/s',
@@ -302,6 +340,7 @@ def main():
                      'peak_source': peak_src,
                      'launches': conv['launches'], 'avg_launch_us': 1e3 * conv['total_ms'] / max(conv['launches'], 1),
                      'share_of_step': conv['total_ms'] / (ms_train) if ms_train else None},
+        'roofline_process_scan': scan,
         'kernel_time_ms_per_step': {k: v['total_ms'] / steps for k, v in prof.items()},
         'clocks': sampler.summary() if sampler else None,
         'final_loss': float(losses[-1]) if losses else None,
