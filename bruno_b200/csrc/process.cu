@@ -896,6 +896,306 @@ process_bwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
   for (int p = 0; p < 3; ++p) stv<VEC>(partial + (static_cast<size_t>(blockIdx.x) * 3 + p) * D + d0, pg[p]);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// backward scan, persistent + bulk-copy ring (default when D % 4 == 0 and the pointers are 16-byte aligned)
+// ------------------------------------------------------------------------------------------------------------
+// Same arithmetic per element as process_bwd_kernel.  What changes is where the bytes come from:
+//   * z through the producer warp's bulk-copy ring, forward for the totals and again in reverse (the second read of a
+//     group is an L2 hit: NB * T * D * 4 bytes per block are in flight);
+//   * the coefficient tables were the real bound (28 vector loads per thread-step for NB * 4 elements, ~14x the z bytes
+//     through L2): e, A2 and B2 have step-independent derivatives, so their accumulators run over all steps and groups of
+//     the block and are chained to the raw variables ONCE at the end; A2_n / B2_n themselves are a0 + n da; C's
+//     accumulator is a scalar per step.  Per step: 3 coefficient + 12 derivative vectors (TP), 2 + 6 (GP);
+//   * coefficients and dlp one step ahead in registers.
+template <int KIND, int NB, bool PRIOR, int NSTAGE, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+process_bwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ mu0, const float* __restrict__ tab,
+                        const float* __restrict__ dlp, const float* __restrict__ dlpp, float* __restrict__ dz,
+                        float* __restrict__ partial, int B, int T, int D) {
+  constexpr int VEC = 4;
+  constexpr int NCF = ncf_of(KIND);
+  constexpr float INV_LN2 = 1.4426950408889634f;
+  extern __shared__ __align__(16) unsigned char ring_smem[];
+  const int ncons = blockDim.x - 32, ncw = ncons >> 5;
+  const int seg_cap = ncons * VEC;
+  const int seg_d0 = blockIdx.y * seg_cap;
+  const int seg_len = min(D - seg_d0, seg_cap);
+  float* stage = reinterpret_cast<float*>(ring_smem);                                  // [NSTAGE][NB][seg_cap]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage + static_cast<size_t>(NSTAGE) * NB * seg_cap);
+  uint64_t* empty = full + NSTAGE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int groups = ceil_div(B, NB);
+  const size_t rowTD = static_cast<size_t>(T) * D;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], ncw);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == ncw) {                                          // ---------------- producer warp
+    if (lane == 0) {
+      const uint32_t seg_bytes = static_cast<uint32_t>(seg_len) * 4u;
+      int s = 0;
+      uint32_t ph = 1;
+      for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+        const float* src[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) src[j] = z + static_cast<size_t>(min(g * NB + j, B - 1)) * rowTD + seg_d0;
+        for (int it = 0; it < 2 * T; ++it) {                  // steps 0..T-1 (totals), then T-1..0 (reverse pass)
+          const int n = it < T ? it : 2 * T - 1 - it;
+          mbar_wait(&empty[s], ph);
+          mbar_arrive_expect_tx(&full[s], seg_bytes * NB);
+          float* dst = stage + static_cast<size_t>(s) * NB * seg_cap;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) bulk_g2s(dst + j * seg_cap, src[j] + static_cast<size_t>(n) * D, seg_bytes, &full[s]);
+          if (++s == NSTAGE) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps
+  const int dl_ = threadIdx.x * VEC;
+  const bool active = dl_ < seg_len;
+  const int d0 = seg_d0 + dl_;
+  const int d0c = active ? d0 : seg_d0;
+  const int dlc = active ? dl_ : 0;
+  const float* gtab = tab + static_cast<size_t>(T * NCF + N_PRIOR) * D;
+  const Vf<VEC> mu = ldv<VEC>(mu0 + d0c);
+  Vf<VEC> pc[N_PRIOR], pcg[N_PRIOR], pg[3];
+#pragma unroll
+  for (int i = 0; i < N_PRIOR; ++i) {
+    pc[i] = PRIOR ? ldv<VEC>(tab + static_cast<size_t>(T * NCF + i) * D + d0c) : zerov<VEC>();
+    pcg[i] = zerov<VEC>();
+  }
+#pragma unroll
+  for (int p = 0; p < 3; ++p) pg[p] = zerov<VEC>();
+  Vf<VEC> c_e = zerov<VEC>(), c_a0 = zerov<VEC>(), c_da = zerov<VEC>();
+  Vf<VEC> cgE = zerov<VEC>(), cg5 = zerov<VEC>(), cg6 = zerov<VEC>();      // step-independent derivatives: chained at the end
+  if (KIND == BRUNO_TP) {
+    c_e = ldv<VEC>(tab + static_cast<size_t>(2) * D + d0c);
+    c_a0 = ldv<VEC>(tab + static_cast<size_t>(5) * D + d0c);
+    const Vf<VEC> b0v = ldv<VEC>(tab + static_cast<size_t>(6) * D + d0c);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) c_da.x[e] = c_a0.x[e] - b0v.x[e];
+  }
+  struct Coef {
+    Vf<VEC> a, b, f;                                          // TP: w, dd w, f';   GP: dd, I, -
+  };
+  auto load_coef = [&](int n) {
+    const float* tp = tab + static_cast<size_t>(n) * NCF * D + d0c;
+    Coef c;
+    c.a = ldv<VEC>(tp);
+    c.b = ldv<VEC>(tp + D);
+    c.f = KIND == BRUNO_TP ? ldv<VEC>(tp + 3 * static_cast<size_t>(D)) : zerov<VEC>();
+    return c;
+  };
+  int s = 0;
+  uint32_t ph = 0;
+  auto next_stage = [&]() -> const float* {
+    mbar_wait(&full[s], ph);
+    return stage + static_cast<size_t>(s) * NB * seg_cap + dlc;
+  };
+  auto release_stage = [&]() {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (++s == NSTAGE) {
+      s = 0;
+      ph ^= 1u;
+    }
+  };
+
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int b0 = g * NB;
+    Vf<VEC> S1[NB], S2[NB], S2lo[NB], G1[NB], G2[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      S1[j] = zerov<VEC>(); S2[j] = zerov<VEC>(); S2lo[j] = zerov<VEC>(); G1[j] = zerov<VEC>(); G2[j] = zerov<VEC>();
+    }
+    // coefficients and upstream gradients of the LAST step: in flight while pass 1 runs
+    Coef cn = load_coef(T - 1);
+    float dln[NB], dqn[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const bool valid = b0 + j < B;
+      dln[j] = valid ? __ldg(dlp + static_cast<size_t>(b0 + j) * T + (T - 1)) : 0.f;
+      dqn[j] = (PRIOR && valid) ? __ldg(dlpp + static_cast<size_t>(b0 + j) * T + (T - 1)) : 0.f;
+    }
+    // pass 1: totals
+    for (int n = 0; n < T; ++n) {
+      const float* xs = next_stage();
+      Vf<VEC> x[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(xs + j * seg_cap);
+        x[j].x[0] = t.x; x[j].x[1] = t.y; x[j].x[2] = t.z; x[j].x[3] = t.w;
+      }
+      release_stage();
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float xz = x[j].x[e] - mu.x[e];
+          S1[j].x[e] += xz;
+          if (KIND == BRUNO_TP) {
+            const float p2 = xz * xz;
+            ds_add(S2[j].x[e], S2lo[j].x[e], p2, fmaf(xz, xz, -p2));
+          }
+        }
+    }
+    // pass 2: reverse
+    for (int n = T - 1; n >= 0; --n) {
+      const Coef c = cn;
+      float dlv[NB], dqv[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        dlv[j] = dln[j];
+        dqv[j] = dqn[j];
+      }
+      if (n > 0) {
+        cn = load_coef(n - 1);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const bool valid = b0 + j < B;
+          dln[j] = valid ? __ldg(dlp + static_cast<size_t>(b0 + j) * T + (n - 1)) : 0.f;
+          dqn[j] = (PRIOR && valid) ? __ldg(dlpp + static_cast<size_t>(b0 + j) * T + (n - 1)) : 0.f;
+        }
+      }
+      const float* xs = next_stage();
+      Vf<VEC> x[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(xs + j * seg_cap);
+        x[j].x[0] = t.x; x[j].x[1] = t.y; x[j].x[2] = t.z; x[j].x[3] = t.w;
+      }
+      release_stage();
+      const float fn = static_cast<float>(n);
+      Vf<VEC> a2 = zerov<VEC>(), b2 = zerov<VEC>();           // the table's A2_n, B2_n
+      if (KIND == BRUNO_TP) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          a2.x[e] = fmaf(fn, c_da.x[e], c_a0.x[e]);
+          b2.x[e] = a2.x[e] - c_da.x[e];
+        }
+      }
+      Vf<VEC> cga = zerov<VEC>(), cgb = zerov<VEC>(), cgf = zerov<VEC>();
+      float cgC = 0.f;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const float dl = dlv[j], dlq = dqv[j];                // 0 for rows past B: no gradient contribution
+        cgC += dl;
+        Vf<VEC> gx;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float xz = x[j].x[e] - mu.x[e];
+          float dxz, dS1, dS2 = 0.f;
+          if constexpr (KIND == BRUNO_TP) {
+            const float s1v = S1[j].x[e] - xz;
+            const float p2 = xz * xz;
+            ds_add(S2[j].x[e], S2lo[j].x[e], -p2, -fmaf(xz, xz, -p2));
+            const float s2v = fmaxf(S2[j].x[e] + S2lo[j].x[e], 0.f);
+            S1[j].x[e] = s1v;
+            const float s1sq = s1v * s1v;
+            const float r = fmaf(-c.b.x[e], s1v, c.a.x[e] * xz);
+            const float q = fmaf(c.f.x[e], s1sq, fmaf(c_e.x[e], s2v, 1.f));
+            const float u = fmaf(r, r, q);
+            const float gu = -a2.x[e] * INV_LN2 * fast_rcp(u) * dl;
+            const float gq = fmaf(b2.x[e] * INV_LN2 * dl, fast_rcp(q), gu);
+            const float gr = 2.f * r * gu;
+            dxz = gr * c.a.x[e];
+            dS1 = fmaf(gq * c.f.x[e], 2.f * s1v, -gr * c.b.x[e]);
+            dS2 = gq * c_e.x[e];
+            cga.x[e] = fmaf(gr, xz, cga.x[e]);
+            cgb.x[e] = fmaf(-gr, s1v, cgb.x[e]);
+            cgE.x[e] = fmaf(gq, s2v, cgE.x[e]);
+            cgf.x[e] = fmaf(gq, s1sq, cgf.x[e]);
+            cg5.x[e] = fmaf(-fast_lg2(u), dl, cg5.x[e]);
+            cg6.x[e] = fmaf(fast_lg2(q), dl, cg6.x[e]);
+            if (PRIOR) {
+              const float x2 = xz * xz;
+              const float up = fmaf(x2, pc[0].x[e], 1.f);
+              const float gup = -pc[2].x[e] * INV_LN2 * fast_rcp(up) * dlq;
+              dxz = fmaf(gup * 2.f * pc[0].x[e], xz, dxz);
+              pcg[0].x[e] = fmaf(gup, x2, pcg[0].x[e]);
+              pcg[1].x[e] += dlq;
+              pcg[2].x[e] = fmaf(-fast_lg2(up), dlq, pcg[2].x[e]);
+            }
+          } else {
+            const float s1v = S1[j].x[e] - xz;
+            S1[j].x[e] = s1v;
+            const float r = fmaf(-c.a.x[e], s1v, xz);
+            const float gr = -2.f * c.b.x[e] * r * dl;
+            dxz = gr;
+            dS1 = -gr * c.a.x[e];
+            cga.x[e] = fmaf(-gr, s1v, cga.x[e]);
+            cgb.x[e] = fmaf(-r * r, dl, cgb.x[e]);
+            if (PRIOR) {
+              dxz = fmaf(-2.f * pc[0].x[e] * dlq, xz, dxz);
+              pcg[0].x[e] = fmaf(-xz * xz, dlq, pcg[0].x[e]);
+              pcg[1].x[e] += dlq;
+            }
+          }
+          gx.x[e] = dxz + G1[j].x[e] + 2.f * xz * G2[j].x[e];
+          G1[j].x[e] += dS1;
+          G2[j].x[e] += dS2;
+        }
+        if (active && b0 + j < B) stv<VEC>(dz + static_cast<size_t>(b0 + j) * rowTD + static_cast<size_t>(n) * D + d0, gx);
+      }
+      // chain this step's accumulators (the coefficients whose derivatives depend on the step) to the raw variables
+      const float* gt = gtab + static_cast<size_t>(n) * NCF * 3 * D + d0c;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        if (KIND == BRUNO_GP && p == 1) continue;
+        const Vf<VEC> da_ = ldv<VEC>(gt + static_cast<size_t>(0 * 3 + p) * D);
+        const Vf<VEC> db_ = ldv<VEC>(gt + static_cast<size_t>(1 * 3 + p) * D);
+        const Vf<VEC> dC_ = ldv<VEC>(gt + static_cast<size_t>((KIND == BRUNO_TP ? 4 : 2) * 3 + p) * D);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          pg[p].x[e] = fmaf(cgC, dC_.x[e], fmaf(cgb.x[e], db_.x[e], fmaf(cga.x[e], da_.x[e], pg[p].x[e])));
+        if (KIND == BRUNO_TP) {
+          const Vf<VEC> df_ = ldv<VEC>(gt + static_cast<size_t>(3 * 3 + p) * D);
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) pg[p].x[e] = fmaf(cgf.x[e], df_.x[e], pg[p].x[e]);
+        }
+      }
+    }
+  }
+  if (KIND == BRUNO_TP) {                                     // e, A2, B2: d/d(raw variable) does not depend on the step
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const Vf<VEC> dE = ldv<VEC>(gtab + static_cast<size_t>(2 * 3 + p) * D + d0c);
+      const Vf<VEC> d5 = ldv<VEC>(gtab + static_cast<size_t>(5 * 3 + p) * D + d0c);
+      const Vf<VEC> d6 = ldv<VEC>(gtab + static_cast<size_t>(6 * 3 + p) * D + d0c);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e)
+        pg[p].x[e] = fmaf(cg6.x[e], d6.x[e], fmaf(cg5.x[e], d5.x[e], fmaf(cgE.x[e], dE.x[e], pg[p].x[e])));
+    }
+  }
+  if (PRIOR) {
+#pragma unroll
+    for (int i = 0; i < N_PRIOR; ++i)
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        const Vf<VEC> dc = ldv<VEC>(gtab + (static_cast<size_t>(T * NCF + i) * 3 + p) * D + d0c);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) pg[p].x[e] = fmaf(pcg[i].x[e], dc.x[e], pg[p].x[e]);
+      }
+  }
+  if (active) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) stv<VEC>(partial + (static_cast<size_t>(blockIdx.x) * 3 + p) * D + d0, pg[p]);
+  }
+}
+
 __global__ void process_bwd_finalize(const float* __restrict__ partial, int nblk, int D, float* __restrict__ dvar,
                                      float* __restrict__ dnu, float* __restrict__ dcorr) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1136,10 +1436,73 @@ static int bwd_blocks(int B) {
   return groups < 592 ? groups : 592;
 }
 
+// Backward variant: 0 = default (ring kernel when eligible), 9 = always the register-staged kernel, 10/11 = ring shapes.
+static int g_bwd_variant = -1;
+static int bwd_variant() {
+  if (g_bwd_variant < 0) {
+    const char* e = getenv("BRUNO_TP_BWD_VARIANT");
+    g_bwd_variant = e ? atoi(e) : 0;
+  }
+  return g_bwd_variant;
+}
+
+template <int KIND, int NB, int NSTAGE, int MINB>
+static int launch_bwd_ring(const float* z, const float* mu0, const float* table, const float* dlp, const float* dlpp,
+                           float* dz, float* dvar, float* dnu, float* dcorr, float* scratch, int B, int T, int D,
+                           cudaStream_t st) {
+  const ScanGeom g = ring_geom(D);
+  const size_t smem = static_cast<size_t>(NSTAGE) * NB * g.threads * 4 * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
+  auto k = dlpp ? process_bwd_ring_kernel<KIND, NB, true, NSTAGE, MINB> : process_bwd_ring_kernel<KIND, NB, false, NSTAGE, MINB>;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static struct { size_t smem; int threads, per_sm; } cache[2] = {};
+  auto& ce = cache[dlpp ? 1 : 0];
+  if (ce.smem != smem || ce.threads != g.threads) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, g.threads + 32, smem);
+    ce.smem = smem;
+    ce.threads = g.threads;
+    ce.per_sm = per_sm;
+  }
+  if (ce.per_sm < 1) return 1;
+  const int groups = ceil_div(B, NB);
+  int nblk = ceil_div(ce.per_sm * sm_count, g.nseg);
+  if (nblk > groups) nblk = groups;
+  if (nblk > bwd_blocks(B)) nblk = bwd_blocks(B);             // the scratch holds bwd_blocks(B) partial rows
+  dim3 grid(nblk, g.nseg);
+  int rc;
+  {
+    ProfSpan span(BRUNO_PROF_PROCESS_BWD, st);
+    k<<<grid, g.threads + 32, smem, st>>>(z, mu0, table, dlp, dlpp, dz, scratch, B, T, D);
+    rc = check_launch("process_bwd_ring_kernel");
+  }
+  if (rc) return rc;
+  process_bwd_finalize<<<ceil_div(D, 256), 256, 0, st>>>(scratch, nblk, D, dvar, KIND == BRUNO_TP ? dnu : nullptr, dcorr);
+  return check_launch("process_bwd_finalize");
+}
+
 template <int KIND, int VEC>
 static int launch_bwd(const float* z, const float* mu0, const float* table, const float* dlp, const float* dlpp,
                       float* dz, float* dvar, float* dnu, float* dcorr, float* scratch, int B, int T, int D,
                       const ScanGeom& g, cudaStream_t st) {
+  if constexpr (VEC == 4) {
+    const int v = bwd_variant();
+    if (v != 9) {
+      int rc;
+      switch (v) {
+        case 10: rc = launch_bwd_ring<KIND, 2, 4, 2>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        case 11: rc = launch_bwd_ring<KIND, 2, 8, 1>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        case 12: rc = launch_bwd_ring<KIND, 4, 4, 1>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        default: rc = launch_bwd_ring<KIND, 2, 8, 2>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+      }
+      if (rc <= 0) return rc;
+    }
+  }
   const int groups = ceil_div(B, BWD_NB);
   const int nblk = bwd_blocks(B);
   const int gpb = ceil_div(groups, nblk);
@@ -1183,6 +1546,7 @@ int bruno_process_table(int kind, const float* var_vbl, const float* nu_vbl, con
 }
 
 void bruno_process_set_fwd_variant(int variant) { g_fwd_variant = variant < 0 ? 0 : variant; }
+void bruno_process_set_bwd_variant(int variant) { g_bwd_variant = variant < 0 ? 0 : variant; }
 
 size_t bruno_process_scratch_floats(int B, int T, int D) {
   const int nseg = scan_geom(D, false).nseg;  // worst case: the scalar (unaligned) path (>= the ring kernel's segments)

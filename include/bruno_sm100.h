@@ -79,6 +79,8 @@ size_t bruno_process_scratch_floats(int B, int T, int D);
  * bulk-copy ring kernel when D % 4 == 0 and all pointers are 16-byte aligned, register-staged kernel otherwise),
  * 9 = always the register-staged kernel, 10-14 = ring shapes.  Same results for every value. */
 void bruno_process_set_fwd_variant(int variant);
+/* Same switch for bruno_process_bwd: 0 = default (ring kernel when eligible), 9 = register-staged, 10-12 = ring shapes. */
+void bruno_process_set_bwd_variant(int variant);
 int bruno_process_fwd(int kind, const float* z, const float* mu0, const float* table, float* s1, float* s2,
                       float* lp, float* lp_prior, float* scratch, int B, int T, int D, void* stream);
 

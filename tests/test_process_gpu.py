@@ -237,3 +237,32 @@ def test_forward_scan_variants_agree(kind, B, T, D, mu):
                 assert torch.allclose(lp_cat, out[9][0], rtol=3e-5, atol=2e-3), (v, (lp_cat - out[9][0]).abs().max().item())
     finally:
         _lib.query('bruno_process_set_fwd_variant', 0)
+
+
+@pytest.mark.parametrize('kind', ['tp', 'gp'])
+@pytest.mark.parametrize('B,T,D,mu,with_prior', [(7, 20, 784, 0., False), (5, 7, 3600, 0., True), (9, 3, 40, 0.4, True),
+                                                 (1190, 6, 784, 0., False), (3, 1, 784, 0., True)])
+def test_backward_scan_variants_agree(kind, B, T, D, mu, with_prior):
+    """The bulk-copy ring backward (default, shapes 10-12) against the register-staged kernel (9): ragged groups, a
+    ragged last segment, non-zero mu0, more groups than persistent blocks, T = 1, with and without the prior term."""
+    from bruno_b200 import _lib
+    layer, P = _layer(kind, D, seed=4, mu=mu)
+    g = torch.Generator().manual_seed(B * 7 + D)
+    z = (torch.randn(B, T, D, generator=g) * 1.2 + 0.4 * torch.randn(B, 1, D, generator=g)).float().cuda()
+    wl = torch.randn(B, T, generator=g).cuda()
+    wp = torch.randn(B, T, generator=g).cuda()
+    params = [layer.var_vbl, layer.nu_vbl, layer.corr_vbl] if kind == 'tp' else [layer.var_vbl, layer.corr_vbl]
+    out = {}
+    try:
+        for v in (9, 0, 10, 11, 12):
+            _lib.query('bruno_process_set_bwd_variant', v)
+            zg = z.clone().requires_grad_(True)
+            lp, pr = layer.sequence_log_likelihoods(zg, want_prior=with_prior)
+            obj = (lp * wl).sum() + ((pr * wp).sum() if with_prior else 0.)
+            out[v] = [t.detach().clone() for t in torch.autograd.grad(obj, [zg] + params)]
+        for v in (0, 10, 11, 12):
+            for a, b in zip(out[v], out[9]):
+                scale = b.abs().max().item() + 1e-12
+                assert (a - b).abs().max().item() <= 1e-4 * scale, (v, (a - b).abs().max().item(), scale)
+    finally:
+        _lib.query('bruno_process_set_bwd_variant', 0)

@@ -42,6 +42,22 @@ def sweep_variants(variants, Bs, T, D, peak):
                     print('variant %2d %s %-9s B=%6d T=%d D=%d  %8.1f us  %7.1f GB/s  (%.1f%% of measured %.0f GB/s)' % (
                         v, kind, name, B, T, D, t * 1e6, gbs, 100 * gbs / peak, peak), flush=True)
             _lib.query('bruno_process_set_fwd_variant', 0)
+            if os.environ.get('BENCH_BWD_VARIANTS'):
+                tabg = build_table(layer.kind, layer.var_vbl.detach(), nu, layer.corr_vbl.detach(), layer.mu, None, 2.0, 0, T, True)
+                dz = torch.empty_like(z)
+                dv = [torch.empty(1, D, device='cuda') for _ in range(3)]
+                bscr = torch.empty(max(_lib.query('bruno_process_bwd_scratch_floats', B, T, D), 1), device='cuda')
+                dlp = torch.randn(B, T, device='cuda')
+                for v in [int(x) for x in os.environ['BENCH_BWD_VARIANTS'].split(',')]:
+                    _lib.query('bruno_process_set_bwd_variant', v)
+                    for name, prior in (('bwd', None), ('bwd+prior', dlp)):
+                        t = timeit(lambda: _lib.call('bruno_process_bwd', layer.kind, z, layer.mu, tabg, dlp, prior, dz, dv[0],
+                                                     dv[1] if kind == 'tp' else None, dv[2], bscr, B, T, D), iters=10)
+                        gbs = (8 * B * T * D + 4 * B * T) / t * 1e-9
+                        print('bwd variant %2d %s %-9s B=%6d T=%d D=%d  %8.1f us  %7.1f GB/s  (%.1f%% of measured %.0f GB/s)' % (
+                            v, kind, name, B, T, D, t * 1e6, gbs, 100 * gbs / peak, peak), flush=True)
+                _lib.query('bruno_process_set_bwd_variant', 0)
+                del dz
 
 
 def main():
