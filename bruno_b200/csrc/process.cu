@@ -1496,9 +1496,11 @@ static int launch_bwd(const float* z, const float* mu0, const float* table, cons
       int rc;
       switch (v) {
         case 10: rc = launch_bwd_ring<KIND, 2, 4, 2>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
-        case 11: rc = launch_bwd_ring<KIND, 2, 8, 1>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        case 11: rc = launch_bwd_ring<KIND, 2, 8, 2>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
         case 12: rc = launch_bwd_ring<KIND, 4, 4, 1>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
-        default: rc = launch_bwd_ring<KIND, 2, 8, 2>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        // measured (profiles/r01_process_bwd_ring_sweep.log): one 254-register block per SM without spills beats two
+        // 128-register blocks with 48 spilled values per thread (TP 5.5 vs 6.9 ms at B = 65536; GP equal)
+        default: rc = launch_bwd_ring<KIND, 2, 8, 1>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
       }
       if (rc <= 0) return rc;
     }
