@@ -467,10 +467,11 @@ __global__ void process_fwd_finalize(const float* __restrict__ scratch, float* _
 //     row's step is one contiguous D*4-byte run) into an NSTAGE-deep shared-memory ring, full/empty mbarriers per
 //     stage, running ahead across group boundaries so the next group's first steps land while this group reduces;
 //   * consumer warps: same thread <-> (4 dims x NB rows) mapping, same butterfly and same cross-warp order as the
-//     kernel above (results are bit-identical for equal NB / RS), z from LDS.128, the per-step coefficients prefetched
-//     one step ahead with LDG (L1/L2-resident table), the [T][warps][NV] partials double-buffered by group parity so
-//     one consumer-only named barrier per group suffices.
-template <int KIND, int NB, bool PRIOR, int NSTAGE, int RS, int MINB, bool CPF, bool STATE>
+//     kernel above, z from LDS.128; the three per-step coefficient rows either ride in the same ring stage (CPF = 2,
+//     default: three more bulk copies per stage from the L2-resident table, no LDG in the hot loop) or are prefetched
+//     one step ahead with LDG (CPF = 1) / loaded in place (CPF = 0); the [T][warps][NV] partials are double-buffered
+//     by group parity so one consumer-only named barrier per group suffices.
+template <int KIND, int NB, bool PRIOR, int NSTAGE, int RS, int MINB, int CPF, bool STATE>
 __global__ void __launch_bounds__(256, MINB)
 process_fwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ mu0, const float* __restrict__ tab,
                         float* __restrict__ s1, float* __restrict__ s2, float* __restrict__ lp,
@@ -485,8 +486,9 @@ process_fwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
   const int seg_cap = ncons * VEC;                            // dims per segment (row slot length in the ring)
   const int seg_d0 = blockIdx.y * seg_cap;
   const int seg_len = min(D - seg_d0, seg_cap);
-  float* stage = reinterpret_cast<float*>(ring_smem);                                  // [NSTAGE][NB][seg_cap]
-  float* sred = stage + static_cast<size_t>(NSTAGE) * NB * seg_cap;                     // [2][T][ncw][NV]
+  constexpr int NROW = CPF == 2 ? NB + 3 : NB;               // CPF == 2: the step's 3 coefficient rows ride in the stage
+  float* stage = reinterpret_cast<float*>(ring_smem);                                  // [NSTAGE][NROW][seg_cap]
+  float* sred = stage + static_cast<size_t>(NSTAGE) * NROW * seg_cap;                   // [2][T][ncw][NV]
   uint64_t* full = reinterpret_cast<uint64_t*>(sred + static_cast<size_t>(2) * T * ncw * NV);
   uint64_t* empty = full + NSTAGE;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -514,12 +516,18 @@ process_fwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
         for (int j = 0; j < NB; ++j) src[j] = z + static_cast<size_t>(min(g * NB + j, B - 1)) * rowTD + seg_d0;
         for (int n = 0; n < T; ++n) {
           mbar_wait(&empty[s], ph);
-          mbar_arrive_expect_tx(&full[s], seg_bytes * NB);
-          float* dst = stage + static_cast<size_t>(s) * NB * seg_cap;
+          mbar_arrive_expect_tx(&full[s], seg_bytes * NROW);
+          float* dst = stage + static_cast<size_t>(s) * NROW * seg_cap;
 #pragma unroll
           for (int j = 0; j < NB; ++j) {
             bulk_g2s(dst + j * seg_cap, src[j], seg_bytes, &full[s]);
             src[j] += D;
+          }
+          if (CPF == 2) {                                     // w / dd, dd w / I, C of this step (L2-resident table)
+            const float* trow = tab + static_cast<size_t>(n) * NCF * D + seg_d0;
+            bulk_g2s(dst + (NB + 0) * seg_cap, trow, seg_bytes, &full[s]);
+            bulk_g2s(dst + (NB + 1) * seg_cap, trow + D, seg_bytes, &full[s]);
+            bulk_g2s(dst + (NB + 2) * seg_cap, trow + (KIND == BRUNO_TP ? 4 : 2) * static_cast<size_t>(D), seg_bytes, &full[s]);
           }
           if (++s == NSTAGE) {
             s = 0;
@@ -554,6 +562,9 @@ process_fwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
 #pragma unroll
     for (int e = 0; e < VEC; ++e) zr = zr && (mu.x[e] == 0.f);
     return zr; }());
+  float psum = 0.f;                                           // the prior's additive constant over this thread's dims
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) psum += pc[1].x[e];
 
   struct Coef {
     Vf<VEC> w, dd, C;                                         // TP: w, dd w, C;   GP: dd, I, C
@@ -569,7 +580,7 @@ process_fwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
   };
   const float* tpn = tp0;                                     // table row of the NEXT step (CPF) / of this step
   Coef cn;
-  if (CPF) cn = load_coef(tpn);
+  if (CPF == 1) cn = load_coef(tpn);
   int s = 0;
   uint32_t ph = 0;
   int par = 0;
@@ -616,21 +627,29 @@ process_fwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
 
       auto do_step = [&](int n, float* vals_pp) {
         Coef c;
-        if (CPF) {                                            // coefficients one step ahead (12 more registers)
+        if (CPF == 1) {                                       // coefficients one step ahead (12 more registers)
           c = cn;
           tpn = (n + 1 == T) ? tp0 : tpn + tstep;
           cn = load_coef(tpn);
-        } else {
+        } else if (CPF == 0) {
           c = load_coef(tpn);
           tpn = (n + 1 == T) ? tp0 : tpn + tstep;
         }
         mbar_wait(&full[s], ph);
-        const float* xs = stage + static_cast<size_t>(s) * NB * seg_cap + dlc;
+        const float* xs = stage + static_cast<size_t>(s) * NROW * seg_cap + dlc;
         Vf<VEC> x[NB];
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
           const float4 t = *reinterpret_cast<const float4*>(xs + j * seg_cap);
           x[j].x[0] = t.x; x[j].x[1] = t.y; x[j].x[2] = t.z; x[j].x[3] = t.w;
+        }
+        if (CPF == 2) {                                       // the step's coefficients came with the stage
+          const float4 t0 = *reinterpret_cast<const float4*>(xs + (NB + 0) * seg_cap);
+          const float4 t1 = *reinterpret_cast<const float4*>(xs + (NB + 1) * seg_cap);
+          const float4 t2 = *reinterpret_cast<const float4*>(xs + (NB + 2) * seg_cap);
+          c.w.x[0] = t0.x; c.w.x[1] = t0.y; c.w.x[2] = t0.z; c.w.x[3] = t0.w;
+          c.dd.x[0] = t1.x; c.dd.x[1] = t1.y; c.dd.x[2] = t1.z; c.dd.x[3] = t1.w;
+          c.C.x[0] = t2.x; c.C.x[1] = t2.y; c.C.x[2] = t2.z; c.C.x[3] = t2.w;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -646,7 +665,7 @@ process_fwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
         }
         const float fn = static_cast<float>(n);
         Vf<VEC> a2, b2;
-        float csum = 0.f, psum = 0.f;                         // the batch-independent additive constants of this step
+        float csum = 0.f;                                     // the batch-independent additive constant of this step
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           if (KIND == BRUNO_TP) {
@@ -654,7 +673,6 @@ process_fwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
             b2.x[e] = a2.x[e] - c_da.x[e];
           }
           csum += c.C.x[e];
-          if (PRIOR) psum += pc[1].x[e];
         }
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
@@ -1355,12 +1373,12 @@ static ScanGeom ring_geom(int D) {
   g.nseg = (chunks + g.threads - 1) / g.threads;
   return g;
 }
-template <int KIND, int NB, int NSTAGE, int RS, int MINB, bool CPF>
+template <int KIND, int NB, int NSTAGE, int RS, int MINB, int CPF>
 static int launch_fwd_ring(const float* z, const float* mu0, const float* table, float* s1, float* s2, float* lp,
                            float* lp_prior, float* scratch, int B, int T, int D, cudaStream_t st) {
   const ScanGeom g = ring_geom(D);
   const int ncw = g.threads / 32;
-  const size_t smem = static_cast<size_t>(NSTAGE) * NB * g.threads * 4 * sizeof(float) +
+  const size_t smem = static_cast<size_t>(NSTAGE) * (CPF == 2 ? NB + 3 : NB) * g.threads * 4 * sizeof(float) +
                       static_cast<size_t>(2) * T * ncw * NB * 2 * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
   if (smem > 112 * 1024 || (g.nseg > 1 && scratch == nullptr)) return 1;
   auto k = s1 ? (lp_prior ? process_fwd_ring_kernel<KIND, NB, true, NSTAGE, RS, MINB, CPF, true>
@@ -1411,12 +1429,18 @@ static int launch_fwd(const float* z, const float* mu0, const float* table, floa
     if (v == 0 || v >= 10) {
       int rc;
       switch (v) {
-        case 11: rc = launch_fwd_ring<KIND, 2, 8, 2, 3, true>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
-        case 12: rc = launch_fwd_ring<KIND, 2, 8, 4, 3, false>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
-        case 13: rc = launch_fwd_ring<KIND, 2, 8, 2, 4, false>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
-        case 14: rc = launch_fwd_ring<KIND, 4, 6, 2, 2, true>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
-        case 15: rc = launch_fwd_ring<KIND, 4, 4, 2, 2, false>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
-        default: rc = launch_fwd_ring<KIND, 4, 4, 4, 2, true>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 11: rc = launch_fwd_ring<KIND, 2, 8, 2, 3, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 12: rc = launch_fwd_ring<KIND, 2, 8, 4, 3, 0>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 13: rc = launch_fwd_ring<KIND, 2, 8, 2, 4, 0>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 14: rc = launch_fwd_ring<KIND, 4, 6, 2, 2, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 16: rc = launch_fwd_ring<KIND, 4, 4, 4, 2, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 17: rc = launch_fwd_ring<KIND, 4, 4, 2, 2, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 18: rc = launch_fwd_ring<KIND, 4, 3, 4, 2, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 15: rc = launch_fwd_ring<KIND, 4, 4, 2, 2, 0>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        case 10: rc = launch_fwd_ring<KIND, 4, 4, 4, 2, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
+        // default: the step's coefficient rows ride in the ring stage (CPF = 2): no LDG in the hot loop, 648 vs 689 us
+        // for the TP scan at B = 65536 (profiles/r01_process_ring_sweep_v6.log)
+        default: rc = launch_fwd_ring<KIND, 4, 4, 4, 2, 2>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
       }
       if (rc <= 0) return rc;
     }

@@ -205,11 +205,11 @@ def test_forward_scan_variants_agree(kind, B, T, D, mu):
     z = (torch.randn(B, T, D, generator=g) * 1.3 + 0.5 * torch.randn(B, 1, D, generator=g)).float().cuda()
     out = {}
     try:
-        for v in (9, 0, 10, 11, 12, 13, 14, 15):
+        for v in (9, 0, 10, 11, 12, 13, 14, 15, 16, 17, 18):
             _lib.query('bruno_process_set_fwd_variant', v)
             lp, pr = layer.sequence_log_likelihoods(z)
             out[v] = (lp.detach().clone(), pr.detach().clone())
-        for v in (0, 10, 11, 12, 13, 14, 15):
+        for v in (0, 10, 11, 12, 13, 14, 15, 16, 17, 18):
             assert torch.allclose(out[v][0], out[9][0], rtol=3e-5, atol=1e-3), (v, (out[v][0] - out[9][0]).abs().max().item())
             assert torch.allclose(out[v][1], out[9][1], rtol=3e-5, atol=1e-3), v
         if B <= 16:

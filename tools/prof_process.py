@@ -8,8 +8,9 @@ layer = StudentRecurrentLayer((D,))
 z = torch.randn(B, T, D, device='cuda')
 tab = build_table(0, layer.var_vbl.detach(), layer.nu_vbl.detach(), layer.corr_vbl.detach(), layer.mu, None, 2.0, 0, T, False)
 lp = torch.empty(B, T, device='cuda')
+lpp = torch.empty(B, T, device='cuda') if 'prior' in sys.argv[1:] else None   # python tools/prof_process.py prior
 sc = torch.empty(1, device='cuda')
 for _ in range(3):
-    _lib.call('bruno_process_fwd', 0, z, layer.mu, tab, None, None, lp, None, sc, B, T, D)
+    _lib.call('bruno_process_fwd', 0, z, layer.mu, tab, None, None, lp, lpp, sc, B, T, D)
 torch.cuda.synchronize()
 print('ok')
