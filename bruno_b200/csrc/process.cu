@@ -925,7 +925,7 @@ process_bwd_kernel(const float* __restrict__ z, const float* __restrict__ mu0, c
 //     the block and are chained to the raw variables ONCE at the end; A2_n / B2_n themselves are a0 + n da; C's
 //     accumulator is a scalar per step.  Per step: 3 coefficient + 12 derivative vectors (TP), 2 + 6 (GP);
 //   * coefficients and dlp one step ahead in registers.
-template <int KIND, int NB, bool PRIOR, int NSTAGE, int MINB>
+template <int KIND, int NB, bool PRIOR, int NSTAGE, int MINB, bool CT>
 __global__ void __launch_bounds__(256, MINB)
 process_bwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ mu0, const float* __restrict__ tab,
                         const float* __restrict__ dlp, const float* __restrict__ dlpp, float* __restrict__ dz,
@@ -938,8 +938,12 @@ process_bwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
   const int seg_cap = ncons * VEC;
   const int seg_d0 = blockIdx.y * seg_cap;
   const int seg_len = min(D - seg_d0, seg_cap);
-  float* stage = reinterpret_cast<float*>(ring_smem);                                  // [NSTAGE][NB][seg_cap]
-  uint64_t* full = reinterpret_cast<uint64_t*>(stage + static_cast<size_t>(NSTAGE) * NB * seg_cap);
+  // CT: the reverse pass's stages also carry the step's coefficient rows (TP w, dd w, f'; GP dd, I) and the derivative
+  // rows of its step-dependent chains (TP 4 x 3, GP 3 x 2): no LDG and no 64-bit address arithmetic in the hot loop
+  constexpr int NCO = KIND == BRUNO_TP ? 3 : 2, NDE = KIND == BRUNO_TP ? 12 : 6;
+  constexpr int NROW = CT ? NB + NCO + NDE : NB;
+  float* stage = reinterpret_cast<float*>(ring_smem);                                  // [NSTAGE][NROW][seg_cap]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage + static_cast<size_t>(NSTAGE) * NROW * seg_cap);
   uint64_t* empty = full + NSTAGE;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = ceil_div(B, NB);
@@ -967,10 +971,29 @@ process_bwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
         for (int it = 0; it < 2 * T; ++it) {                  // steps 0..T-1 (totals), then T-1..0 (reverse pass)
           const int n = it < T ? it : 2 * T - 1 - it;
           mbar_wait(&empty[s], ph);
-          mbar_arrive_expect_tx(&full[s], seg_bytes * NB);
-          float* dst = stage + static_cast<size_t>(s) * NB * seg_cap;
+          const bool tables = CT && it >= T;
+          mbar_arrive_expect_tx(&full[s], seg_bytes * (tables ? NROW : NB));
+          float* dst = stage + static_cast<size_t>(s) * NROW * seg_cap;
 #pragma unroll
           for (int j = 0; j < NB; ++j) bulk_g2s(dst + j * seg_cap, src[j] + static_cast<size_t>(n) * D, seg_bytes, &full[s]);
+          if (tables) {
+            const float* trow = tab + static_cast<size_t>(n) * NCF * D + seg_d0;
+            const float* grow = tab + static_cast<size_t>(T * NCF + N_PRIOR) * D + static_cast<size_t>(n) * NCF * 3 * D + seg_d0;
+            bulk_g2s(dst + (NB + 0) * seg_cap, trow, seg_bytes, &full[s]);
+            bulk_g2s(dst + (NB + 1) * seg_cap, trow + D, seg_bytes, &full[s]);
+            if (KIND == BRUNO_TP) bulk_g2s(dst + (NB + 2) * seg_cap, trow + 3 * static_cast<size_t>(D), seg_bytes, &full[s]);
+            int r = NB + NCO;
+#pragma unroll
+            for (int k = 0; k < (KIND == BRUNO_TP ? 4 : 3); ++k) {
+              const int ci = KIND == BRUNO_TP ? (k < 2 ? k : k + 1) : k;       // TP: w, dd w, f', C = rows 0, 1, 3, 4
+#pragma unroll
+              for (int p = 0; p < 3; ++p) {
+                if (KIND == BRUNO_GP && p == 1) continue;
+                bulk_g2s(dst + r * seg_cap, grow + static_cast<size_t>(ci * 3 + p) * D, seg_bytes, &full[s]);
+                ++r;
+              }
+            }
+          }
           if (++s == NSTAGE) {
             s = 0;
             ph ^= 1u;
@@ -1021,7 +1044,13 @@ process_bwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
   uint32_t ph = 0;
   auto next_stage = [&]() -> const float* {
     mbar_wait(&full[s], ph);
-    return stage + static_cast<size_t>(s) * NB * seg_cap + dlc;
+    return stage + static_cast<size_t>(s) * NROW * seg_cap + dlc;
+  };
+  auto lds4 = [](const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    Vf<VEC> r;
+    r.x[0] = t.x; r.x[1] = t.y; r.x[2] = t.z; r.x[3] = t.w;
+    return r;
   };
   auto release_stage = [&]() {
     __syncwarp();
@@ -1040,7 +1069,8 @@ process_bwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
       S1[j] = zerov<VEC>(); S2[j] = zerov<VEC>(); S2lo[j] = zerov<VEC>(); G1[j] = zerov<VEC>(); G2[j] = zerov<VEC>();
     }
     // coefficients and upstream gradients of the LAST step: in flight while pass 1 runs
-    Coef cn = load_coef(T - 1);
+    Coef cn;
+    if (!CT) cn = load_coef(T - 1);
     float dln[NB], dqn[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
@@ -1072,7 +1102,8 @@ process_bwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
     }
     // pass 2: reverse
     for (int n = T - 1; n >= 0; --n) {
-      const Coef c = cn;
+      Coef c;
+      if (!CT) c = cn;
       float dlv[NB], dqv[NB];
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
@@ -1080,7 +1111,7 @@ process_bwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
         dqv[j] = dqn[j];
       }
       if (n > 0) {
-        cn = load_coef(n - 1);
+        if (!CT) cn = load_coef(n - 1);
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
           const bool valid = b0 + j < B;
@@ -1095,7 +1126,13 @@ process_bwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
         const float4 t = *reinterpret_cast<const float4*>(xs + j * seg_cap);
         x[j].x[0] = t.x; x[j].x[1] = t.y; x[j].x[2] = t.z; x[j].x[3] = t.w;
       }
-      release_stage();
+      if (CT) {
+        c.a = lds4(xs + (NB + 0) * seg_cap);
+        c.b = lds4(xs + (NB + 1) * seg_cap);
+        c.f = KIND == BRUNO_TP ? lds4(xs + (NB + 2) * seg_cap) : zerov<VEC>();
+      } else {
+        release_stage();
+      }
       const float fn = static_cast<float>(n);
       Vf<VEC> a2 = zerov<VEC>(), b2 = zerov<VEC>();           // the table's A2_n, B2_n
       if (KIND == BRUNO_TP) {
@@ -1170,21 +1207,26 @@ process_bwd_ring_kernel(const float* __restrict__ z, const float* __restrict__ m
       }
       // chain this step's accumulators (the coefficients whose derivatives depend on the step) to the raw variables
       const float* gt = gtab + static_cast<size_t>(n) * NCF * 3 * D + d0c;
+      constexpr int NP = KIND == BRUNO_TP ? 3 : 2;            // derivative rows per coefficient in the stage
+      const float* gs = xs + (NB + NCO) * seg_cap;            // [k][pi] rows of the stage (CT)
 #pragma unroll
       for (int p = 0; p < 3; ++p) {
         if (KIND == BRUNO_GP && p == 1) continue;
-        const Vf<VEC> da_ = ldv<VEC>(gt + static_cast<size_t>(0 * 3 + p) * D);
-        const Vf<VEC> db_ = ldv<VEC>(gt + static_cast<size_t>(1 * 3 + p) * D);
-        const Vf<VEC> dC_ = ldv<VEC>(gt + static_cast<size_t>((KIND == BRUNO_TP ? 4 : 2) * 3 + p) * D);
+        const int pi = KIND == BRUNO_TP ? p : (p >> 1);
+        const Vf<VEC> da_ = CT ? lds4(gs + (0 * NP + pi) * seg_cap) : ldv<VEC>(gt + static_cast<size_t>(0 * 3 + p) * D);
+        const Vf<VEC> db_ = CT ? lds4(gs + (1 * NP + pi) * seg_cap) : ldv<VEC>(gt + static_cast<size_t>(1 * 3 + p) * D);
+        const Vf<VEC> dC_ = CT ? lds4(gs + ((KIND == BRUNO_TP ? 3 : 2) * NP + pi) * seg_cap)
+                               : ldv<VEC>(gt + static_cast<size_t>((KIND == BRUNO_TP ? 4 : 2) * 3 + p) * D);
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
           pg[p].x[e] = fmaf(cgC, dC_.x[e], fmaf(cgb.x[e], db_.x[e], fmaf(cga.x[e], da_.x[e], pg[p].x[e])));
         if (KIND == BRUNO_TP) {
-          const Vf<VEC> df_ = ldv<VEC>(gt + static_cast<size_t>(3 * 3 + p) * D);
+          const Vf<VEC> df_ = CT ? lds4(gs + (2 * NP + pi) * seg_cap) : ldv<VEC>(gt + static_cast<size_t>(3 * 3 + p) * D);
 #pragma unroll
           for (int e = 0; e < VEC; ++e) pg[p].x[e] = fmaf(cgf.x[e], df_.x[e], pg[p].x[e]);
         }
       }
+      if (CT) release_stage();
     }
   }
   if (KIND == BRUNO_TP) {                                     // e, A2, B2: d/d(raw variable) does not depend on the step
@@ -1470,13 +1512,15 @@ static int bwd_variant() {
   return g_bwd_variant;
 }
 
-template <int KIND, int NB, int NSTAGE, int MINB>
+template <int KIND, int NB, int NSTAGE, int MINB, bool CT>
 static int launch_bwd_ring(const float* z, const float* mu0, const float* table, const float* dlp, const float* dlpp,
                            float* dz, float* dvar, float* dnu, float* dcorr, float* scratch, int B, int T, int D,
                            cudaStream_t st) {
   const ScanGeom g = ring_geom(D);
-  const size_t smem = static_cast<size_t>(NSTAGE) * NB * g.threads * 4 * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
-  auto k = dlpp ? process_bwd_ring_kernel<KIND, NB, true, NSTAGE, MINB> : process_bwd_ring_kernel<KIND, NB, false, NSTAGE, MINB>;
+  constexpr int NROW = CT ? NB + (KIND == BRUNO_TP ? 15 : 8) : NB;
+  const size_t smem = static_cast<size_t>(NSTAGE) * NROW * g.threads * 4 * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
+  if (smem > 226 * 1024) return 1;
+  auto k = dlpp ? process_bwd_ring_kernel<KIND, NB, true, NSTAGE, MINB, CT> : process_bwd_ring_kernel<KIND, NB, false, NSTAGE, MINB, CT>;
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
@@ -1519,12 +1563,14 @@ static int launch_bwd(const float* z, const float* mu0, const float* table, cons
     if (v != 9) {
       int rc;
       switch (v) {
-        case 10: rc = launch_bwd_ring<KIND, 2, 4, 2>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
-        case 11: rc = launch_bwd_ring<KIND, 2, 8, 2>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
-        case 12: rc = launch_bwd_ring<KIND, 4, 4, 1>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        case 10: rc = launch_bwd_ring<KIND, 2, 4, 2, false>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        case 11: rc = launch_bwd_ring<KIND, 2, 8, 2, false>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        case 13: rc = launch_bwd_ring<KIND, 2, 3, 1, true>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        case 14: rc = launch_bwd_ring<KIND, 2, 2, 1, true>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        case 12: rc = launch_bwd_ring<KIND, 4, 4, 1, false>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
         // measured (profiles/r01_process_bwd_ring_sweep.log): one 254-register block per SM without spills beats two
         // 128-register blocks with 48 spilled values per thread (TP 5.5 vs 6.9 ms at B = 65536; GP equal)
-        default: rc = launch_bwd_ring<KIND, 2, 8, 1>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        default: rc = launch_bwd_ring<KIND, 2, 8, 1, false>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
       }
       if (rc <= 0) return rc;
     }
