@@ -1564,13 +1564,21 @@ static int launch_bwd(const float* z, const float* mu0, const float* table, cons
       int rc;
       switch (v) {
         case 10: rc = launch_bwd_ring<KIND, 2, 4, 2, false>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        case 15: rc = launch_bwd_ring<KIND, 2, 8, 1, false>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
         case 11: rc = launch_bwd_ring<KIND, 2, 8, 2, false>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
         case 13: rc = launch_bwd_ring<KIND, 2, 3, 1, true>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
         case 14: rc = launch_bwd_ring<KIND, 2, 2, 1, true>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
         case 12: rc = launch_bwd_ring<KIND, 4, 4, 1, false>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
         // measured (profiles/r01_process_bwd_ring_sweep.log): one 254-register block per SM without spills beats two
         // 128-register blocks with 48 spilled values per thread (TP 5.5 vs 6.9 ms at B = 65536; GP equal)
-        default: rc = launch_bwd_ring<KIND, 2, 8, 1, false>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st); break;
+        // default: the reverse pass's coefficient and derivative rows ride in the ring stage (TP 5.0 vs 5.5 ms, TP + prior
+        // 5.5 vs 6.9, GP 2.2 vs 2.65 at B = 65536); GP + prior is the one case measured slower that way (3.5 vs 2.8 ms)
+        default:
+          if (KIND == BRUNO_TP || dlpp == nullptr)
+            rc = launch_bwd_ring<KIND, 2, 3, 1, true>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st);
+          else
+            rc = launch_bwd_ring<KIND, 2, 8, 1, false>(z, mu0, table, dlp, dlpp, dz, dvar, dnu, dcorr, scratch, B, T, D, st);
+          break;
       }
       if (rc <= 0) return rc;
     }

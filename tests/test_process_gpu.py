@@ -254,13 +254,13 @@ def test_backward_scan_variants_agree(kind, B, T, D, mu, with_prior):
     params = [layer.var_vbl, layer.nu_vbl, layer.corr_vbl] if kind == 'tp' else [layer.var_vbl, layer.corr_vbl]
     out = {}
     try:
-        for v in (9, 0, 10, 11, 12, 13, 14):
+        for v in (9, 0, 10, 11, 12, 13, 14, 15):
             _lib.query('bruno_process_set_bwd_variant', v)
             zg = z.clone().requires_grad_(True)
             lp, pr = layer.sequence_log_likelihoods(zg, want_prior=with_prior)
             obj = (lp * wl).sum() + ((pr * wp).sum() if with_prior else 0.)
             out[v] = [t.detach().clone() for t in torch.autograd.grad(obj, [zg] + params)]
-        for v in (0, 10, 11, 12, 13, 14):
+        for v in (0, 10, 11, 12, 13, 14, 15):
             for a, b in zip(out[v], out[9]):
                 scale = b.abs().max().item() + 1e-12
                 assert (a - b).abs().max().item() <= 1e-4 * scale, (v, (a - b).abs().max().item(), scale)
