@@ -305,10 +305,14 @@ def main():
         t_scan = e0.elapsed_time(e1) * 1e-3 / 10
         alg = 4.0 * Bz * T * Dz + 4.0 * Bz * T                # z read once + log-probs written
         hbm = peaks.get('hbm_gbs', 6550.0)
+        traffic_scan = None                                   # measured DRAM bytes per latent element (ncu --set full) x elements
+        tpj = os.path.join(ROOT, 'profiles', 'r01_process_traffic.json')
+        if os.path.exists(tpj) and lay.nu_vbl is not None:
+            traffic_scan = json.load(open(tpj))['bytes_per_latent_element'] * Bz * T * Dz
         scan = {'bound': 'hbm', 'kernel': 'process_fwd_ring_kernel (%s forward scan, persistent bulk-copy ring)' % (
                     'GP' if lay.nu_vbl is None else 'TP'),
                 'achieved': alg / t_scan * 1e-9, 'peak': hbm, 'unit': 'GB/s', 'frac': alg / t_scan * 1e-9 / hbm,
-                'traffic': None, 'us_per_launch': t_scan * 1e6, 'shape': [Bz, T, Dz],
+                'traffic': traffic_scan, 'us_per_launch': t_scan * 1e6, 'shape': [Bz, T, Dz],
                 'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback'}
         del zz
     except Exception as exc:                                   # the bench line must not die on the side measurement
