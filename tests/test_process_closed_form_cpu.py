@@ -118,3 +118,50 @@ def test_tp_recursive_q_scan_matches_reference_golden_vector(golden_dir):
     assert np.allclose(lp[0], g['tp_recursive'], atol=1e-8, rtol=1e-8)
     lg = _gp_scan_closed_form(x, g['var'].astype(np.float64), g['corr'].astype(np.float64), np.zeros(1))
     assert np.allclose(lg[0][1:], g['gp_joint'][1:], atol=1e-3, rtol=1e-3)
+
+
+def _tp_backward_dz(z, dlp, var, nu0, corr, mu):
+    """dz of sum(lp * dlp) with the two-pass scheme of process_bwd_ring_kernel (TP): totals forward, then the sequence in
+    reverse, recovering the prefix sums by subtraction and carrying the suffix sums G1 / G2 of dL/dS1, dL/dS2."""
+    B, T, D = z.shape
+    c = corr * var
+    e = 1.0 / ((var - c) * (nu0 - 2.0))
+    xz_all = z - mu
+    S1 = xz_all.sum(1)
+    S2 = (xz_all * xz_all).sum(1)
+    G1 = np.zeros((B, D))
+    G2 = np.zeros((B, D))
+    dz = np.zeros_like(z)
+    for n in range(T - 1, -1, -1):
+        dd = c / (var + c * (n - 1.0))
+        w = 1.0 / np.sqrt((var - dd * c * n) * (nu0 - 2.0))
+        ddw = dd * w
+        f = -c / ((var - c) * (c * (n - 1.0) + var) * (nu0 - 2.0))
+        A = (nu0 + n + 1.0) / 2.0
+        xz = xz_all[:, n, :]
+        dl = dlp[:, n:n + 1]
+        S1 = S1 - xz                                           # prefix sums BEFORE observation n
+        S2 = S2 - xz * xz
+        r = w * xz - ddw * S1
+        q = 1.0 + e * S2 + f * S1 * S1
+        u = r * r + q
+        gu = -A / u * dl                                       # d/du of -A ln u
+        gq = (A - 0.5) / q * dl + gu                           # q enters directly and through u = r^2 + q
+        gr = 2.0 * r * gu
+        dz[:, n, :] = gr * w + G1 + 2.0 * xz * G2
+        G1 = G1 + (gq * f * 2.0 * S1 - gr * ddw)
+        G2 = G2 + gq * e
+    return dz
+
+
+@pytest.mark.parametrize('B,T,D,mu', [(3, 9, 6, 0.0), (2, 5, 4, 0.3)])
+def test_tp_two_pass_backward_equals_oracle_autograd(B, T, D, mu):
+    proc = _setup('tp', D, seed=T, mu=mu)
+    g = torch.Generator().manual_seed(B + D)
+    z = (torch.randn(B, T, D, generator=g, dtype=torch.float64) * 1.3).requires_grad_(True)
+    dlp = torch.randn(B, T, generator=g, dtype=torch.float64)
+    lp_o, _ = O.process_log_probs(proc, z)
+    (dz_o,) = torch.autograd.grad((lp_o * dlp).sum(), [z])
+    var, nu0, corr = (t.numpy()[0] for t in (proc.var, proc.nu, proc.corr))
+    dz = _tp_backward_dz(z.detach().numpy(), dlp.numpy(), var, nu0, corr, np.full(D, mu))
+    assert np.allclose(dz, dz_o.numpy(), rtol=1e-8, atol=1e-9)
