@@ -12,6 +12,12 @@
 //   * hand-written backward: pass 1 re-reads z to form the total sums, pass 2 walks the sequence in reverse,
 //     carrying the suffix sums of dL/dS1, dL/dS2; coefficient gradients are chained to the raw variables with the
 //     fp64 forward-mode derivatives stored by the table kernel.
+//   * default kernels (process_fwd_ring_kernel / process_bwd_ring_kernel, D % 4 == 0 and aligned pointers): persistent
+//     blocks, a producer warp streaming z -- and the step's table rows -- through a cp.async.bulk + mbarrier
+//     shared-memory ring, the same thread <-> (4 dims x NB rows) mapping in the consumer warps; the forward carries
+//     q_n = 1 + beta_n / (nu0 - 2) recursively (q_{n+1} = q_n + r_n^2: one lg2 per element).  The register-staged
+//     kernels below them in this file are the fallback for other shapes and the A/B partners
+//     (bruno_process_set_fwd_variant / _bwd_variant).  Measured: forward 97 % of the HBM copy peak (was 44.5 %).
 #include <math.h>
 #include <stdlib.h>
 
