@@ -1,9 +1,11 @@
 """CPU oracle for CONDITIONAL BRUNO (config_conditional/m1_shapenet.py on nn_extra_nvp_conditional.py) -- TEST
 INFRASTRUCTURE ONLY, same rules as bruno_oracle.py (never imported by the product package).
 
-Pinning status: "parity unpinned" -- the reference ships no test / golden vector for the conditional path; pinned by the
-same self-consistency checks as the unconditional flow (invertibility; the GP recurrence itself is pinned through
-bruno_oracle.GaussOracle against tests_gp_tp/utils_stats.py).
+Pinning status: PINNED -- tests/golden/ref_flow_m1_shapenet.npz holds what the reference's own unmodified
+nn_extra_nvp_conditional.py + config_conditional/m1_shapenet.py compute (executed over tests/tf_shim/, see
+bruno_oracle.py) for data-dependent init, log-probs, loss gradients of all 1262 variables and the sampling branch;
+tests/test_reference_pinning_cpu.py requires this module to reproduce them to 1e-9.  That pinning corrected one
+misreading: the conditional 'c1' is a 3x3 convolution (init_params below).
 
 Restates, with the reference file:line next to each function (paths relative to /root/reference):
   * label-conditioned weight-normalised conv / dense layers      nn_extra_nvp_conditional.py:396-471
@@ -269,7 +271,10 @@ def init_params(spec, seed=0, dtype=torch.float64, randomize_heads=True, perturb
             c //= 2
         else:
             sc = 'model/%s/function_s_t_wn' % layer[2]
-            convs = [('c1', (1, 1, c, Fn))]
+            # c1: the label branch of conv2d_wn (:427) calls the inner conv2d_wn WITHOUT forwarding filter_size, so the
+            # 'c1' of a conditional coupling is a 3x3 convolution (default filter_size=[3, 3], :397), not the 1x1 the
+            # call site (:89) asks for.  Pinned by tests/golden/ref_flow_m1_shapenet.npz (reference code executed).
+            convs = [('c1', (3, 3, c, Fn))]
             for r in range(spec.num_res_blocks):
                 convs += [('c2_%d' % r, (3, 3, Fn, Fn)), ('c3_%d' % r, (3, 3, Fn, Fn))]
             for nm, shp in convs:
