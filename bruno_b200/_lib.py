@@ -85,13 +85,20 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+_ABI_DTYPES = (torch.float32, torch.uint8)      # fp32 data; uint8 = packed bf16 weights / activation slabs (opaque bytes)
+
+
 def call(name, *args):
-    """Invoke an int-returning entry point; tensors are passed as device pointers; appends the current stream."""
+    """Invoke an int-returning entry point; tensors are passed as device pointers; appends the current stream.
+    Only float32 tensors and opaque uint8 byte buffers cross the ABI: anything else (a float64 batch from a user
+    iterator, an int tensor) would be reinterpreted silently, so it raises here."""
     lib = load()
     fn = getattr(lib, name)
     conv = []
     for a in args:
         if isinstance(a, torch.Tensor):
+            if a.dtype not in _ABI_DTYPES:
+                raise RuntimeError('%s: tensor of dtype %s passed to the C ABI (float32 / uint8 buffers only)' % (name, a.dtype))
             conv.append(ptr(a, None))
         else:
             conv.append(a)

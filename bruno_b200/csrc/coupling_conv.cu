@@ -13,7 +13,7 @@ int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float*
                             int mask_type, int inverse, const float* V1, const float* g1, const float* b1,
                             const void* wfwd, const float* br, int bias_img_stride, const float* Ks, const float* bs,
                             const float* Kt, const float* bt, const float* label_s, const float* label_t, void* slabs,
-                            int n_slabs, void* stream) {
+                            int n_slabs, int c1_ks, void* stream) {
   BRUNO_REQUIRE(x && ld_in && y && ld_out && V1 && g1 && b1 && wfwd && br && Ks && bs && Kt && bt && slabs,
                 "bruno_coupling_conv_fwd: null pointer");
   BRUNO_REQUIRE(R >= 1 && (n_slabs >= 3), "bruno_coupling_conv_fwd: need >= 3 slabs (got %d)", n_slabs);
@@ -25,7 +25,7 @@ int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float*
   // bias_img_stride = 0: b1 [64], br [2R,64];  != 0: label-conditioned per-image tables, image n of layer l at
   // br + l*64 + n*bias_img_stride (the 2R+1 tables are the columns of one [N, (2R+1)*64] matrix)
   const size_t bl = 64;
-  if ((rc = bruno_c1_fwd(x, V1, g1, b1, bias_img_stride, S(0), 0, N, H, W, C, mask_type, stream))) return rc;
+  if ((rc = bruno_c1_fwd(x, V1, g1, b1, bias_img_stride, S(0), 0, N, H, W, C, mask_type, c1_ks, stream))) return rc;
   int hi = 0;
   if (2 * R <= 16) {
     // the 2R convolutions as one persistent launch (conv3x3_chain_kernel); falls through to per-layer launches if the
@@ -62,7 +62,7 @@ int bruno_coupling_conv_bwd(const float* x, const float* dy, const float* dld, i
                             float* dVr, float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt, void* stream) {
   return bruno_coupling_conv_bwd_cond(x, dy, dld, N, H, W, C, R, mask_type, V1, g1, Vr, gr, wbwd, Ks, bs, Kt, bt, saved_slabs,
                                       gslabs, scratch, dx, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt, nullptr, nullptr, 0,
-                                      nullptr, nullptr, stream);
+                                      nullptr, nullptr, 1, stream);
 }
 
 int bruno_coupling_conv_bwd_cond(const float* x, const float* dy, const float* dld, int N, int H, int W, int C, int R,
@@ -71,7 +71,7 @@ int bruno_coupling_conv_bwd_cond(const float* x, const float* dy, const float* d
                                  const void* saved_slabs, void* gslabs, float* scratch, float* dx, float* dV1, float* dg1,
                                  float* db1, float* dVr, float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt,
                                  const float* label_s, float* dtab, int dtab_stride, float* dlabel_s, float* dlabel_t,
-                                 void* stream) {
+                                 int c1_ks, void* stream) {
   BRUNO_REQUIRE(x && dy && dld && V1 && g1 && Vr && gr && wbwd && Ks && bs && Kt && bt && saved_slabs && gslabs && scratch && dx && dV1 &&
                     dg1 && db1 && dVr && dgr && dbr && dKs && dbs && dKt && dbt, "bruno_coupling_conv_bwd: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -82,7 +82,7 @@ int bruno_coupling_conv_bwd_cond(const float* x, const float* dy, const float* d
   auto GS = [&](int i) { return static_cast<void*>(static_cast<uint8_t*>(gslabs) + static_cast<size_t>(i) * sb); };
   cudaMemsetAsync(dVr, 0, static_cast<size_t>(2 * R) * 9 * 64 * 64 * sizeof(float), st);
   cudaMemsetAsync(dbr, 0, static_cast<size_t>(2 * R) * 64 * sizeof(float), st);
-  cudaMemsetAsync(dV1, 0, static_cast<size_t>(C) * 64 * sizeof(float), st);
+  cudaMemsetAsync(dV1, 0, static_cast<size_t>(c1_ks * c1_ks * C) * 64 * sizeof(float), st);
   cudaMemsetAsync(db1, 0, 64 * sizeof(float), st);
   int rc;
   if ((rc = bruno_heads_coupling_bwd_cond(x, S(2 * R), Ks, bs, Kt, bt, dy, dld, dx, GS(2 * R), dKs, dbs, dKt, dbt, scratch, N, H,
@@ -106,12 +106,12 @@ int bruno_coupling_conv_bwd_cond(const float* x, const float* dy, const float* d
   }
   // all 2R weight (and bias) gradients in one launch: conv layer l reads its input slab S(l) and gradient GS(l + 1)
   if ((rc = bruno_conv3x3_wgrad_batched(S(0), GS(1), dVr, dbr, 2 * R, N, H, W, stream))) return rc;
-  if ((rc = bruno_c1_bwd(x, V1, g1, GS(0), dx, dV1, db1, N, H, W, C, mask_type, stream))) return rc;
+  if ((rc = bruno_c1_bwd(x, V1, g1, GS(0), dx, dV1, db1, N, H, W, C, mask_type, c1_ks, stream))) return rc;
   // label-conditioned layers: gradient of the per-image bias tables = per-image channel sums of the 2R+1 gradient slabs
   if (dtab && (rc = bruno_slab_image_colsum(gslabs, 2 * R + 1, dtab, dtab_stride, N, H, W, stream))) return rc;
   // weight-norm backward, in place over the raw weight gradients
   if ((rc = bruno_conv_wn_bwd(Vr, gr, dVr, dVr, dgr, 2 * R, 9 * 64, stream))) return rc;
-  return bruno_conv_wn_bwd(V1, g1, dV1, dV1, dg1, 1, C, stream);
+  return bruno_conv_wn_bwd(V1, g1, dV1, dV1, dg1, 1, c1_ks * c1_ks * C, stream);
 }
 
 }  // extern "C"

@@ -134,11 +134,14 @@ __global__ void channel_copy_kernel(const float* __restrict__ src, float* __rest
 // c1: 1x1 weight-normalised conv C -> 64 on the masked input + ELU, written as a swizzled bf16 slab.  nvp:113-115
 // ------------------------------------------------------------------------------------------------------------
 constexpr int MAXC = 16;
+// rows of the c1 weight matrix: ks*ks*C.  ks = 1 everywhere (nvp:113) except the label-conditioned couplings, whose c1 is a
+// 3x3 convolution (nn_extra_nvp_conditional.py:427 calls the inner conv2d_wn without forwarding filter_size) with C <= 8.
+constexpr int MAXK = 72;
 constexpr int HEADS_BWD_BLOCKS = 296;   // 2 resident blocks per SM
 
 __device__ __forceinline__ void c1_weights_to_smem(const float* __restrict__ V1, const float* __restrict__ g1, int C,
                                                    float* w_s /*[C][64]*/) {
-  // W1[c][co] = g1[co] * V1[c][co] / sqrt(max(sum_c V1^2, 1e-12))
+  // W1[c][co] = g1[co] * V1[c][co] / sqrt(max(sum_c V1^2, 1e-12));  C = all rows (ks*ks*Cin)
   for (int i = threadIdx.x; i < 64; i += blockDim.x) {
     float n2 = 0.f;
     for (int c = 0; c < C; ++c) n2 = fmaf(V1[c * 64 + i], V1[c * 64 + i], n2);
@@ -151,11 +154,11 @@ __device__ __forceinline__ void c1_weights_to_smem(const float* __restrict__ V1,
 __global__ void __launch_bounds__(256)
 c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const float* __restrict__ g1,
               const float* __restrict__ b1, int bias_img_stride, uint8_t* __restrict__ out, SlabGeom g, int C,
-              int mask_type, int f32_slab) {
-  __shared__ float w_s[MAXC * 64];
+              int mask_type, int f32_slab, int KS) {
+  __shared__ float w_s[MAXK * 64];
   __shared__ float b_s[64];
   if (threadIdx.x < 64) b_s[threadIdx.x] = bias_img_stride ? 0.f : b1[threadIdx.x];
-  c1_weights_to_smem(V1, g1, C, w_s);
+  c1_weights_to_smem(V1, g1, KS * KS * C, w_s);
   const int total = g.NT * TILE_M * 8;
   const bool small = g.NT * TILE_M < (1 << 22);
   const float inv_img = 1.0f / static_cast<float>(g.IMG), inv_p = 1.0f / static_cast<float>(g.P);
@@ -173,10 +176,23 @@ c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
 #pragma unroll
       for (int e = 0; e < 8; ++e)
         acc[e] = bias_img_stride ? b1[static_cast<size_t>(n) * bias_img_stride + j * 8 + e] : b_s[j * 8 + e];
-      for (int c = 0; c < C; ++c) {
-        const float xm = xp[c] * mask_b(mask_type, yy, xx, c, C);
+      if (KS == 1) {
+        for (int c = 0; c < C; ++c) {
+          const float xm = xp[c] * mask_b(mask_type, yy, xx, c, C);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(xm, w_s[c * 64 + j * 8 + e], acc[e]);
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(xm, w_s[c * 64 + j * 8 + e], acc[e]);
+        }
+      } else {                               // 3x3, zero 'SAME' padding, rows of V1 ordered (kh, kw, cin) like HWIO
+        for (int t = 0; t < 9; ++t) {
+          const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
+          if (y2 < 0 || y2 >= g.H || x2 < 0 || x2 >= g.W) continue;
+          const float* xq = x + ((static_cast<size_t>(n) * g.H + y2) * g.W + x2) * C;
+          for (int c = 0; c < C; ++c) {
+            const float xm = xq[c] * mask_b(mask_type, y2, x2, c, C);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(xm, w_s[(t * C + c) * 64 + j * 8 + e], acc[e]);
+          }
+        }
       }
       if (f32_slab) {
 #pragma unroll
@@ -201,18 +217,20 @@ c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
 __global__ void __launch_bounds__(256)
 c1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const float* __restrict__ g1w,
               const uint8_t* __restrict__ gslab, float* __restrict__ dx, float* __restrict__ dW1, float* __restrict__ db1,
-              SlabGeom g, int C, int mask_type) {
+              SlabGeom g, int C, int mask_type, int KS) {
   extern __shared__ float sm[];
-  float* w_s = sm;                       // [C][64]
-  float* g_s = w_s + MAXC * 64;          // [256][65]
-  float* x_s = g_s + 256 * 65;           // [256][MAXC+1]
-  c1_weights_to_smem(V1, g1w, C, w_s);
+  const int K = KS * KS * C;             // rows of the weight matrix
+  const int KP = K + 1;                  // + the constant-one column that yields db1
+  float* w_s = sm;                       // [K][64]
+  float* g_s = w_s + MAXK * 64;          // [256][65]
+  float* x_s = g_s + 256 * 65;           // [256][KP]
+  c1_weights_to_smem(V1, g1w, K, w_s);
   const int n = blockIdx.x;
   const int HW = g.H * g.W;
-  const int nout = (C + 1) * 64;
-  float acc[(MAXC + 1) * 64 / 256 + 1];
+  const int nout = KP * 64;
+  float acc[(MAXK + 1) * 64 / 256 + 1];
 #pragma unroll
-  for (int i = 0; i < (MAXC + 1) * 64 / 256 + 1; ++i) acc[i] = 0.f;
+  for (int i = 0; i < (MAXK + 1) * 64 / 256 + 1; ++i) acc[i] = 0.f;
   for (int p0 = 0; p0 < HW; p0 += 256) {
     const int p = p0 + threadIdx.x;
     const bool ok = p < HW;
@@ -220,25 +238,60 @@ c1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
     if (ok) {
       const int yy = p / g.W, xx = p % g.W;
       const size_t R = static_cast<size_t>(g.HALO) + static_cast<size_t>(n) * g.IMG + (yy + 1) * g.P + (xx + 1);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint4 u = *reinterpret_cast<const uint4*>(gslab + slab_chunk_off(R, j));
-        unpack8f(u, gv + j * 8);
-      }
       const size_t xo = (static_cast<size_t>(n) * HW + p) * C;
-      for (int c = 0; c < C; ++c) {
-        const float b = mask_b(mask_type, yy, xx, c, C);
-        float d = 0.f;
+      if (KS == 1) {
 #pragma unroll
-        for (int k = 0; k < 64; ++k) d = fmaf(gv[k], w_s[c * 64 + k], d);
-        dx[xo + c] += b * d;
-        x_s[threadIdx.x * (MAXC + 1) + c] = x[xo + c] * b;
+        for (int j = 0; j < 8; ++j) {
+          const uint4 u = *reinterpret_cast<const uint4*>(gslab + slab_chunk_off(R, j));
+          unpack8f(u, gv + j * 8);
+        }
+        for (int c = 0; c < C; ++c) {
+          const float b = mask_b(mask_type, yy, xx, c, C);
+          float d = 0.f;
+#pragma unroll
+          for (int k = 0; k < 64; ++k) d = fmaf(gv[k], w_s[c * 64 + k], d);
+          dx[xo + c] += b * d;
+          x_s[threadIdx.x * KP + c] = x[xo + c] * b;
+        }
+      } else {
+        // 3x3: the pre-activation at q = p - shift(t) read input pixel p through tap t, so
+        //   dx[p][c] = b(p,c) sum_t sum_co g[p - shift(t)][co] W1[t*C + c][co]
+        // (gather: deterministic; rows of the gradient slab outside the image are its zero padding), and the row of the
+        // im2col matrix for dW1 is xm at p + shift(t) (zero outside the image).
+        float d[MAXC];
+        for (int c = 0; c < C; ++c) d[c] = 0.f;
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3 - 1, dxx = t % 3 - 1;
+          const size_t Rn = R - static_cast<size_t>(dy * g.P + dxx) ;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(gslab + slab_chunk_off(Rn, j));
+            unpack8f(u, gv + j * 8);
+          }
+          for (int c = 0; c < C; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 64; ++k) a = fmaf(gv[k], w_s[(t * C + c) * 64 + k], a);
+            d[c] += a;
+          }
+          const int y2 = yy + dy, x2 = xx + dxx;
+          const bool in = y2 >= 0 && y2 < g.H && x2 >= 0 && x2 < g.W;
+          for (int c = 0; c < C; ++c)
+            x_s[threadIdx.x * KP + t * C + c] =
+                in ? x[((static_cast<size_t>(n) * g.H + y2) * g.W + x2) * C + c] * mask_b(mask_type, y2, x2, c, C) : 0.f;
+        }
+        for (int c = 0; c < C; ++c) dx[xo + c] += mask_b(mask_type, yy, xx, c, C) * d[c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 u = *reinterpret_cast<const uint4*>(gslab + slab_chunk_off(R, j));
+          unpack8f(u, gv + j * 8);
+        }
       }
-      x_s[threadIdx.x * (MAXC + 1) + C] = 1.f;
+      x_s[threadIdx.x * KP + K] = 1.f;
     } else {
 #pragma unroll
       for (int k = 0; k < 64; ++k) gv[k] = 0.f;
-      for (int c = 0; c <= C; ++c) x_s[threadIdx.x * (MAXC + 1) + c] = 0.f;
+      for (int c = 0; c <= K; ++c) x_s[threadIdx.x * KP + c] = 0.f;
     }
 #pragma unroll
     for (int k = 0; k < 64; ++k) g_s[threadIdx.x * 65 + k] = gv[k];
@@ -249,10 +302,10 @@ c1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
       for (int pp = 0; pp < 256; pp += 4) {
-        a0 = fmaf(x_s[pp * (MAXC + 1) + c], g_s[pp * 65 + co], a0);
-        a1 = fmaf(x_s[(pp + 1) * (MAXC + 1) + c], g_s[(pp + 1) * 65 + co], a1);
-        a2 = fmaf(x_s[(pp + 2) * (MAXC + 1) + c], g_s[(pp + 2) * 65 + co], a2);
-        a3 = fmaf(x_s[(pp + 3) * (MAXC + 1) + c], g_s[(pp + 3) * 65 + co], a3);
+        a0 = fmaf(x_s[pp * KP + c], g_s[pp * 65 + co], a0);
+        a1 = fmaf(x_s[(pp + 1) * KP + c], g_s[(pp + 1) * 65 + co], a1);
+        a2 = fmaf(x_s[(pp + 2) * KP + c], g_s[(pp + 2) * 65 + co], a2);
+        a3 = fmaf(x_s[(pp + 3) * KP + c], g_s[(pp + 3) * 65 + co], a3);
       }
       acc[ai] += (a0 + a1) + (a2 + a3);
     }
@@ -261,7 +314,7 @@ c1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
   int ai = 0;
   for (int o = threadIdx.x; o < nout; o += 256, ++ai) {
     const int co = o & 63, c = o >> 6;
-    if (c < C) atomicAdd(dW1 + c * 64 + co, acc[ai]);
+    if (c < K) atomicAdd(dW1 + c * 64 + co, acc[ai]);
     else atomicAdd(db1 + co, acc[ai]);
   }
 }
@@ -849,28 +902,31 @@ int bruno_channel_copy(const float* src, float* dst, long rows, int src_C, int s
 }
 
 int bruno_c1_fwd(const float* x, const float* V1, const float* g1, const float* b1, int bias_img_stride, void* out_slab,
-                 int f32_slab, int N, int H, int W, int C, int mask_type, void* stream) {
-  BRUNO_REQUIRE(x && V1 && g1 && b1 && out_slab && C >= 1 && C <= MAXC, "bruno_c1_fwd: bad arguments (C <= %d)", MAXC);
+                 int f32_slab, int N, int H, int W, int C, int mask_type, int ks, void* stream) {
+  BRUNO_REQUIRE(x && V1 && g1 && b1 && out_slab && C >= 1 && C <= MAXC && (ks == 1 || ks == 3) && ks * ks * C <= MAXK,
+                "bruno_c1_fwd: bad arguments (C <= %d, ks in {1,3}, ks*ks*C <= %d)", MAXC, MAXK);
   const SlabGeom g = slab_geom(N, H, W);
   const int total = g.NT * TILE_M * 8;
   int blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   c1_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, V1, g1, b1, bias_img_stride,
-                                                                        static_cast<uint8_t*>(out_slab), g, C, mask_type, f32_slab);
+                                                                        static_cast<uint8_t*>(out_slab), g, C, mask_type, f32_slab, ks);
   return check_launch("c1_fwd_kernel");
 }
 
 int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g_slab, float* dx, float* dW1, float* db1,
-                 int N, int H, int W, int C, int mask_type, void* stream) {
-  BRUNO_REQUIRE(x && V1 && g1 && g_slab && dx && dW1 && db1 && C >= 1 && C <= MAXC, "bruno_c1_bwd: bad arguments");
+                 int N, int H, int W, int C, int mask_type, int ks, void* stream) {
+  BRUNO_REQUIRE(x && V1 && g1 && g_slab && dx && dW1 && db1 && C >= 1 && C <= MAXC && (ks == 1 || ks == 3) &&
+                    ks * ks * C <= MAXK, "bruno_c1_bwd: bad arguments");
   const SlabGeom g = slab_geom(N, H, W);
-  const size_t smem = (MAXC * 64 + 256 * 65 + 256 * (MAXC + 1)) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(c1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    configured = true;
+  const size_t smem = (MAXK * 64 + 256 * 65 + 256 * (ks * ks * C + 1)) * sizeof(float);
+  {
+    // the opt-in is per device: set it on every call (a few hundred ns) instead of caching a per-process flag
+    const cudaError_t e = cudaFuncSetAttribute(c1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>((MAXK * 64 + 256 * 65 + 256 * (MAXK + 1)) * sizeof(float)));
+    BRUNO_REQUIRE(e == cudaSuccess, "bruno_c1_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
   }
-  if (C <= 4) {
+  if (C <= 4 && ks == 1) {
     cudaStream_t st8 = static_cast<cudaStream_t>(stream);
     const SlabGeom g8 = slab_geom(N, H, W);
     const uint8_t* gs8 = static_cast<const uint8_t*>(g_slab);
@@ -881,7 +937,7 @@ int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g
     return check_launch("c1_bwd8_kernel");
   }
   c1_bwd_kernel<<<N, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, V1, g1, static_cast<const uint8_t*>(g_slab), dx, dW1,
-                                                                      db1, g, C, mask_type);
+                                                                      db1, g, C, mask_type, ks);
   return check_launch("c1_bwd_kernel");
 }
 

@@ -28,7 +28,7 @@ def conv_coupling_init(layer, x):
         ld = torch.zeros(N, device=x.device)
         y = torch.empty_like(x)
         _lib.call('bruno_coupling_conv_fwd', x, ld, y, torch.empty_like(ld), N, H, W, C, R, layer.mask_id, 0, layer.V1,
-                  layer.g1, layer.b1, wfwd, layer.br, 0, layer.Ks, layer.bs, layer.Kt, layer.bt, None, None, slabs, int(slabs.shape[0]))
+                  layer.g1, layer.b1, wfwd, layer.br, 0, layer.Ks, layer.bs, layer.Kt, layer.bt, None, None, slabs, int(slabs.shape[0]), 1)
         # c1: pre-activation on the masked input
         hh = torch.arange(H, device=x.device).view(H, 1, 1)
         ww = torch.arange(W, device=x.device).view(1, W, 1)
@@ -103,6 +103,7 @@ def _conv_mask(mt, H, W, C, device):
 
 def cond_conv_coupling_init(layer, x, ld, y_label):
     from .nn_extra_nvp_conditional import _sgemm
+    import torch.nn.functional as Fn
     with torch.no_grad():
         x = x.contiguous()
         N, H, W, C = x.shape
@@ -124,11 +125,13 @@ def cond_conv_coupling_init(layer, x, ld, y_label):
         ld_out = torch.empty_like(ld)
         _lib.call('bruno_coupling_conv_fwd', x, ld.contiguous(), y, ld_out, N, H, W, C, R, layer.mask_id, 0, layer.V1, layer.g1,
                   tab, wfwd, tab.data_ptr() + 4 * F, nl * F, layer.Ks, layer.bs, layer.Kt, layer.bt, ls, lt, slabs,
-                  int(slabs.shape[0]))
+                  int(slabs.shape[0]), 3)
         # conv_h pre-activations: the convolution with the conv's own bias only
         b = _conv_mask(layer.mask_type, H, W, C, x.device)
         nrm = torch.sqrt(torch.clamp((layer.V1 ** 2).sum(0), min=1e-12))
-        pre1 = (x * b).reshape(-1, C) @ (layer.V1 * (layer.g1 / nrm)) + layer.b1
+        # the conditional c1 is a 3x3 convolution (cond:427): V1 [9*C, F], rows ordered (kh, kw, cin)
+        W1 = (layer.V1 * (layer.g1 / nrm)).view(3, 3, C, F).permute(3, 2, 0, 1)
+        pre1 = Fn.conv2d((x * b).permute(0, 3, 1, 2), W1, padding=1).permute(0, 2, 3, 1).reshape(-1, F) + layer.b1
         tmp = alloc_slabs(1, N, H, W, x.device)[0]
         pres = []
         for l in range(2 * R):

@@ -124,6 +124,17 @@ def _grad_sinks(layer, names):
     return bufs, rets
 
 
+def _check_generation(ctx, layer):
+    """The activations a conv coupling saves for its backward are kept in one buffer per layer (6.3 GB per model at
+    B=32, T=20: not duplicated per call).  A second grad-enabled forward through the same layer before the backward of
+    the first (gradient accumulation over micro-batches, two losses, autograd.grad on an older graph) has overwritten
+    them -- fail loudly instead of returning gradients of the wrong activations."""
+    if ctx.generation != layer._generation:
+        raise RuntimeError('%s: backward of a stale graph -- the layer ran %d grad-enabled forward(s) after the one being '
+                           'differentiated and its saved activations were overwritten; call backward before the next '
+                           'forward' % (layer.name, layer._generation - ctx.generation))
+
+
 class Layer(object):                                                        # nvp:14-19
     def forward_and_jacobian(self, x, z, sum_log_det_jacobian):
         raise NotImplementedError(str(type(self)))
@@ -202,13 +213,16 @@ class _ConvCouplingFn(torch.autograd.Function):
         y = torch.empty_like(x)
         ld_out = torch.empty_like(ld)
         _lib.call('bruno_coupling_conv_fwd', x, ld, y, ld_out, N, H, W, C, R, layer.mask_id, int(inverse), V1, g1, b1, wfwd,
-                  br, 0, Ks, bs, Kt, bt, None, None, slabs, int(slabs.shape[0]))
+                  br, 0, Ks, bs, Kt, bt, None, None, slabs, int(slabs.shape[0]), 1)
         if need_grad:
             if inverse:
                 raise RuntimeError('backward through the inverse pass is not implemented (sampling is inference-only)')
             ctx.layer = layer
             ctx.slabs = slabs
             ctx.wbwd = wbwd
+            # the saved activations live in ONE per-layer buffer: a later grad-enabled forward overwrites them
+            layer._generation += 1
+            ctx.generation = layer._generation
             ctx.save_for_backward(x, V1, g1, Vr, gr, Ks, bs, Kt, bt)
         return y, ld_out
 
@@ -216,6 +230,7 @@ class _ConvCouplingFn(torch.autograd.Function):
     def backward(ctx, dy, dld):
         x, V1, g1, Vr, gr, Ks, bs, Kt, bt = ctx.saved_tensors
         layer = ctx.layer
+        _check_generation(ctx, layer)
         N, H, W, C = x.shape
         R = layer.num_res_blocks
         dy = dy.contiguous()
@@ -251,6 +266,7 @@ class CouplingLayerConv(Layer):                                             # nv
         self.num_res_blocks = num_res_blocks
         self.V1 = None
         self._slabs = None
+        self._generation = 0
 
     # ---- variables (created on first use, like tf.get_variable under make_template) --------------------
     def _build(self, C, device):
@@ -314,7 +330,7 @@ class CouplingLayerConv(Layer):                                             # nv
                 SLABS.pool[key] = torch.zeros(3, g.rows, 64, device=x.device)
             buf = SLABS.pool[key]
             M = g.NT * 128
-            _lib.call('bruno_c1_fwd', x, self.V1, self.g1, self.b1, 0, buf[0], 1, N, H, W, C, self.mask_id)
+            _lib.call('bruno_c1_fwd', x, self.V1, self.g1, self.b1, 0, buf[0], 1, N, H, W, C, self.mask_id, 1)
 
             def conv(src, dst, l, skip, act):
                 V = self.Vr[l].detach().contiguous()

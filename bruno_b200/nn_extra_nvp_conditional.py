@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from .nn_extra_nvp import (MASKS, SLABS, Layer as _BaseLayer, elu, int_shape, _new_like, _pre, _SpaceToDepthFn,  # noqa: F401
+from .nn_extra_nvp import (MASKS, SLABS, _check_generation, Layer as _BaseLayer, elu, int_shape, _new_like, _pre, _SpaceToDepthFn,  # noqa: F401
                            channel_slice, channel_concat)
 from .slab import alloc_slabs
 
@@ -135,8 +135,10 @@ class _CondConvCouplingFn(torch.autograd.Function):
         y = torch.empty_like(x)
         ld_out = torch.empty_like(ld)
         _lib.call('bruno_coupling_conv_fwd', x, ld, y, ld_out, N, H, W, C, R, layer.mask_id, 0, V1, g1, tab, wfwd,
-                  tab.data_ptr() + 4 * Fl, nl * Fl, Ks, bs, Kt, bt, ls, lt, slabs, int(slabs.shape[0]))
+                  tab.data_ptr() + 4 * Fl, nl * Fl, Ks, bs, Kt, bt, ls, lt, slabs, int(slabs.shape[0]), 3)
         ctx.layer, ctx.slabs, ctx.wbwd = layer, slabs, wbwd
+        layer._generation += 1
+        ctx.generation = layer._generation
         ctx.save_for_backward(x, V1, g1, Vr, gr, Ks, bs, Kt, bt, ls)
         return y, ld_out
 
@@ -144,6 +146,7 @@ class _CondConvCouplingFn(torch.autograd.Function):
     def backward(ctx, dy, dld):
         x, V1, g1, Vr, gr, Ks, bs, Kt, bt, ls = ctx.saved_tensors
         layer = ctx.layer
+        _check_generation(ctx, layer)
         N, H, W, C = x.shape
         R, Fl = layer.num_res_blocks, layer.num_filters
         nl = 2 * R + 1
@@ -158,7 +161,7 @@ class _CondConvCouplingFn(torch.autograd.Function):
         scratch = _new_like(x, _lib.query('bruno_heads_bwd_scratch_floats', C))
         _lib.call('bruno_coupling_conv_bwd_cond', x, dy, dld, N, H, W, C, R, layer.mask_id, V1, g1, Vr, gr, ctx.wbwd, Ks, bs,
                   Kt, bt, ctx.slabs, gsl, scratch, dx, dV1, dg1, db1, dVr, dgr, dbr, dKs, dbs, dKt, dbt, ls, dtab, nl * Fl,
-                  dls, dlt)
+                  dls, dlt, 3)
         # the conv biases live inside `tab` (tab = label term + conv bias): db1 / dbr reach them through dtab
         return dx, dld, dV1, dg1, dVr, dgr, dKs, dbs, dKt, dbt, dtab, dls, dlt, None
 
@@ -209,6 +212,7 @@ class CouplingLayerConv(Layer):                                             # co
         self.num_filters, self.num_res_blocks = num_filters, num_res_blocks
         self.V1 = None
         self._slabs = None
+        self._generation = 0
 
     # trainable variables (the label_h bias of a conv is created with use_bias=False -> not trainable, cond:426)
     _TRAINABLE = ('V1', 'g1', 'b1', 'Vr', 'gr', 'br', 'LV', 'Lg', 'Ks', 'bs', 'Kt', 'bt', 'LKs', 'LKt')
@@ -226,7 +230,8 @@ class CouplingLayerConv(Layer):                                             # co
     def _build(self, C, L, device):
         F, R = self.num_filters, self.num_res_blocks
         nl = 2 * R + 1
-        self.V1 = _normal(C, F, device=device)
+        # c1 of a conditional coupling is 3x3 in the reference (cond:427 drops filter_size): V1 = HWIO [3,3,C,F] flattened
+        self.V1 = _normal(9 * C, F, device=device)
         self.g1, self.b1 = torch.ones(F, device=device), torch.zeros(F, device=device)
         self.Vr = _normal(2 * R, 3, 3, F, F, device=device)
         self.gr, self.br = torch.ones(2 * R, F, device=device), torch.zeros(2 * R, F, device=device)
@@ -240,7 +245,7 @@ class CouplingLayerConv(Layer):                                             # co
     def named_tf_variables(self, prefix='model/', grad=False):
         """(TF variable name, view) pairs; grad=True: the same views of the gradients (None where there is none)."""
         sc = '%s%s/function_s_t_wn/' % (prefix, self.name)
-        F, R, C = self.num_filters, self.num_res_blocks, self.V1.shape[0]
+        F, R, C = self.num_filters, self.num_res_blocks, self.V1.shape[0] // 9
         names = ['c1'] + [n for r in range(R) for n in ('c2_%d' % r, 'c3_%d' % r)]
 
         def T(n):
@@ -255,7 +260,7 @@ class CouplingLayerConv(Layer):                                             # co
                     (sc + nm + '/label_h/g', V(T('Lg'), lambda t: t[i * F:(i + 1) * F])),
                     (sc + nm + '/label_h/b', V(T('Lb'), lambda t: t[i * F:(i + 1) * F]))]
             if i == 0:
-                out += [(sc + 'c1/conv_h/V', V(T('V1'), lambda t: t.view(1, 1, C, F))), (sc + 'c1/conv_h/g', T('g1')),
+                out += [(sc + 'c1/conv_h/V', V(T('V1'), lambda t: t.view(3, 3, C, F))), (sc + 'c1/conv_h/g', T('g1')),
                         (sc + 'c1/conv_h/b', T('b1'))]
             else:
                 out += [(sc + nm + '/conv_h/V', V(T('Vr'), lambda t: t[i - 1])), (sc + nm + '/conv_h/g', V(T('gr'), lambda t: t[i - 1])),
@@ -293,7 +298,7 @@ class CouplingLayerConv(Layer):                                             # co
             ld_in = ld.contiguous() if ld is not None else torch.zeros(N, device=x.device)
             ld_out = torch.empty_like(ld_in)
             _lib.call('bruno_coupling_conv_fwd', x, ld_in, y, ld_out, N, H, W, C, R, self.mask_id, int(inverse), self.V1,
-                      self.g1, tab, wfwd, tab.data_ptr() + 4 * F, nl * F, self.Ks, self.bs, self.Kt, self.bt, ls, lt, slabs, 3)
+                      self.g1, tab, wfwd, tab.data_ptr() + 4 * F, nl * F, self.Ks, self.bs, self.Kt, self.bt, ls, lt, slabs, 3, 3)
         return y, ld_out
 
     def forward_and_jacobian(self, x, sum_log_det_jacobians, z, y_label=None):      # cond:137-149

@@ -46,7 +46,7 @@ class Trainer(object):
         self.flat, self.flat_grad = self.model.flatten_parameters()
         if self.world_size > 1:
             dist.broadcast(self.flat, 0)
-        opt = getattr(cfg, 'optimizer', 'rmsprop')
+        opt = getattr(cfg, 'optimizer', 'adam')                        # train.py:122-131: RMSProp only if asked for
         if opt == 'rmsprop':
             self.slots = (torch.ones_like(self.flat),)                  # TF initialises the rms slot to 1
         else:

@@ -175,10 +175,13 @@ int bruno_conv3x3_wgrad_batched(const void* x_slab, const void* g_slab, float* d
 /* c1 (nvp:113-115): out_slab = ELU(conv1x1_wn(x * mask)), x [N,H,W,C] fp32, V1 [C,64], g1, b1 [64]. */
 /* f32_slab = 1: the slab is the fp32 verification layout ([row][64] floats, same padded row indexing, no swizzle). */
 int bruno_c1_fwd(const float* x, const float* V1, const float* g1, const float* b1, int bias_img_stride, void* out_slab,
-                 int f32_slab, int N, int H, int W, int C, int mask_type, void* stream);
-/* g_slab = dL/d(pre-activation of c1): dx += mask * (g W1^T); dW1 [C,64] += (x mask)^T g; db1 [64] += sum g. */
+                 int f32_slab, int N, int H, int W, int C, int mask_type, int ks, void* stream);
+/* g_slab = dL/d(pre-activation of c1): dx += mask * (g W1^T); dW1 [ks*ks*C,64] += (x mask)^T g; db1 [64] += sum g.
+ * ks = 1: the 1x1 c1 of nn_extra_nvp.py:113; ks = 3: the c1 of a label-conditioned coupling, which the reference
+ * evaluates as a 3x3 convolution (nn_extra_nvp_conditional.py:427 does not forward filter_size); V1 [ks*ks*C, 64] rows
+ * ordered (kh, kw, cin) = the HWIO variable flattened. */
 int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g_slab, float* dx, float* dW1, float* db1,
-                 int N, int H, int W, int C, int mask_type, void* stream);
+                 int N, int H, int W, int C, int mask_type, int ks, void* stream);
 
 /* conv_out_scale / conv_out_translation heads (nvp:129-139) + affine coupling + log-det (forward :162-174, inverse
  * :176-187).  Ks, Kt [64,C]; bs, bt [C]; x, y [N,H,W,C]; ld [N]. */
@@ -220,7 +223,7 @@ int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float*
                             int mask_type, int inverse, const float* V1, const float* g1, const float* b1,
                             const void* wfwd, const float* br, int bias_img_stride, const float* Ks, const float* bs,
                             const float* Kt, const float* bt, const float* label_s, const float* label_t, void* slabs,
-                            int n_slabs, void* stream);
+                            int n_slabs, int c1_ks, void* stream);
 /* Hand-written backward of the forward coupling: dx [N,H,W,C] and the gradients of every variable of the layer
  * (weight-norm backward included: dVr, dgr are w.r.t. V and g).  saved_slabs = the 2R+1 slabs of the forward;
  * gslabs = 2R+1 zero-initialised scratch slabs (slab 0: gradient w.r.t. the c1 pre-activation, slab l+1: gradient
@@ -240,7 +243,7 @@ int bruno_coupling_conv_bwd_cond(const float* x, const float* dy, const float* d
                                  const void* saved_slabs, void* gslabs, float* scratch, float* dx, float* dV1, float* dg1,
                                  float* db1, float* dVr, float* dgr, float* dbr, float* dKs, float* dbs, float* dKt, float* dbt,
                                  const float* label_s, float* dtab, int dtab_stride, float* dlabel_s, float* dlabel_t,
-                                 void* stream);
+                                 int c1_ks, void* stream);
 
 /* --- dense coupling layer, CouplingLayerDense (nvp:190-274) with dense_wn (:408-432), fp32 ---------------------- */
 size_t bruno_coupling_dense_ws_floats(int N, int D, int U);

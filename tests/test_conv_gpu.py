@@ -175,3 +175,63 @@ def test_layer_chain_is_bit_identical_to_per_layer_launches(N, H, W, C):
         lib.bruno_debug_conv_chain(1)
     for a, b in zip(res[2], res[0]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('conv_variant', [1, 0, 2], indirect=True)
+@pytest.mark.parametrize('N,H,W', [(640, 28, 28), (640, 14, 14), (320, 32, 32)])
+def test_conv3x3_all_epilogues_at_benchmark_shapes(N, H, W, conv_variant):
+    """The shapes bench.py runs (bn2_omniglot_tp B=32 x T=20 -> 640 images at 28x28 and 14x14; an2_cifar B=16 x T=20 at
+    32x32): ~4200 / ~1100 / ~2700 tiles = 7..28 tiles per persistent CTA, so the slab-ring wrap-around, the four rotating
+    TMEM accumulators, the lcm-unrolled stage/accumulator loop and the two alternating epilogue groups are all checked
+    against float64 F.conv2d on bf16-rounded operands (reference computed on the GPU in float64), every epilogue mode."""
+    from bruno_b200 import _lib, slab
+    V, gain, bias, x, a1, a2, wf, wbw = _setup(N, H, W, seed=N + H)
+    dev = 'cuda'
+    Wt = bf(wn(V[0].float().double(), gain[0].float().double())).to(dev)
+    xs, a1s, a2s = [slab.nhwc_to_slab(t.float().cuda()) for t in (x, a1, a2)]
+    xq, a1q, a2q = bf(x).to(dev), bf(a1).to(dev), bf(a2).to(dev)
+    out = slab.alloc_slabs(1, N, H, W, 'cuda')[0]
+    b32 = bias.float().cuda()
+    bd = bias.float().double().to(dev)
+    conv = conv_ref(xq, Wt)
+    dconv = conv_ref(xq, Wt.flip(0, 1).permute(0, 1, 3, 2))
+    cases = [
+        (0, wf[0], lambda: F.elu(conv + bd)),
+        (1, wf[0], lambda: F.elu(conv + bd + a1q)),
+        (2, wbw[0], lambda: dconv * elu_grad_from_out(a1q)),
+        (3, wbw[0], lambda: (dconv + a2q) * elu_grad_from_out(a1q)),
+        (4, wf[0], lambda: conv + bd),
+    ]
+    for mode, w, ref_fn in cases:
+        ref = ref_fn()
+        out.zero_()
+        _lib.call('bruno_conv3x3', mode, xs, w, b32, 0, a1s, a2s, out, N, H, W)
+        got = slab.slab_to_nhwc(out, N, H, W, check_padding=True).double()
+        d = (got - ref).abs()
+        scale = ref.abs().max().item()
+        assert d.max().item() <= 2.0 ** -7 * scale + 1e-3, (mode, d.max().item(), scale)
+        assert d.mean().item() <= 3e-3 * scale, (mode, d.mean().item())
+        # per-image check: a wrong tile anywhere (ring wrap-around, tail tile) shows up as one bad image
+        per_img = d.reshape(N, -1).max(dim=1).values
+        assert int((per_img > 2.0 ** -7 * scale + 1e-3).sum()) == 0
+        del ref, got, d
+
+
+def test_conv3x3_wgrad_at_benchmark_shape():
+    """wgrad at 640 x 14 x 14 and 640 x 28 x 28 (the bench shapes) against float64 autograd on the GPU."""
+    from bruno_b200 import _lib, slab
+    for N, H, W in ((640, 14, 14), (640, 28, 28)):
+        g = torch.Generator().manual_seed(N + H)
+        x = torch.randn(N, H, W, 64, generator=g)
+        gr = torch.randn(N, H, W, 64, generator=g) * 0.1
+        xs, gs = slab.nhwc_to_slab(x.cuda()), slab.nhwc_to_slab(gr.cuda())
+        dW = torch.zeros(3, 3, 64, 64, device='cuda')
+        db = torch.zeros(64, device='cuda')
+        _lib.call('bruno_conv3x3_wgrad', xs, gs, dW, db, N, H, W)
+        xq, gq = bf(x.double()).cuda(), bf(gr.double()).cuda()
+        w = torch.zeros(3, 3, 64, 64, dtype=torch.float64, device='cuda', requires_grad=True)
+        (conv_ref(xq, w) * gq).sum().backward()
+        scale = w.grad.abs().max().item()
+        assert (dW.double() - w.grad).abs().max().item() <= 2e-4 * scale + 1e-4
+        refb = gq.sum(dim=(0, 1, 2))
+        assert (db.double() - refb).abs().max().item() <= 2e-4 * refb.abs().max().item() + 1e-4

@@ -211,7 +211,7 @@ def test_conv_coupling_activations_bitwise_vs_emulating_oracle():
     yg = yin.float().cuda()
     ld = torch.zeros(N, device='cuda')
     _lib.call('bruno_coupling_conv_fwd', yg, ld, torch.empty_like(yg), torch.empty_like(ld), N, H, W, C, R, layer.mask_id, 0,
-              layer.V1, layer.g1, layer.b1, wf, layer.br, 0, layer.Ks, layer.bs, layer.Kt, layer.bt, None, None, slabs, 2 * R + 1)
+              layer.V1, layer.g1, layer.b1, wf, layer.br, 0, layer.Ks, layer.bs, layer.Kt, layer.bt, None, None, slabs, 2 * R + 1, 1)
     frac = []
     for i, a in enumerate(acts):
         got = slab.slab_to_nhwc(slabs[i], N, H, W, check_padding=True).double().cpu()

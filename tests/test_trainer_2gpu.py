@@ -1,0 +1,35 @@
+"""GPU x 2 (run with `gpurun --gpus 2`; skipped on a single-GPU box): the N-rank NCCL Trainer equals the 1-GPU
+full-batch step -- row a19 of SURVEY.md section 8, config_rnn/train.py:83-111.  Two ranks, each on its np.split shard,
+allreduce-sum of the flat gradient buffer, /nr_gpu, student-grad scale, TF-1.7 RMSProp; compared with one rank on the
+whole batch: the averaged gradient buffer after step 1 and the flat parameter buffer after two steps, for the dense
+(fp32) config and the conv (bf16 tensor-core) config, with the single allreduce and with the per-layer overlapped one."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+def test_two_rank_trainer_equals_single_gpu_full_batch(tmp_path):
+    out = os.path.join(str(tmp_path), 'dp.pt')
+    port = 29500 + os.getpid() % 400
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', str(port), os.path.join(ROOT, 'tests', '_dp_worker.py'), out]
+    p = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-4000:]
+    res = torch.load(out)
+    for name, tol_g, tol_p in (('en2_noconv_mnist_tp', 1e-5, 1e-5), ('bn2_omniglot_tp', 2e-3, 2e-3)):
+        flat1, g1 = res[(name, 'single')]
+        for overlap in (False, True):
+            flat2, g2 = res[(name, overlap)]
+            eg = ((g2 - g1).norm() / g1.norm()).item()
+            ep = ((flat2 - flat1).norm() / flat1.norm()).item()
+            print('\n[%s overlap=%s] 2-rank vs 1-rank: gradient buffer rel L2 %.3e, parameters after 2 steps rel L2 %.3e' % (
+                name, overlap, eg, ep))
+            # sums over shards are re-associated (and the conv wgrad accumulates with atomics): not bit-equal
+            assert eg <= tol_g and ep <= tol_p

@@ -42,7 +42,7 @@ _lib.call('bruno_conv_wn_pack', layer.Vr, layer.gr, wf, None, 2 * R)
 slabs = slab.alloc_slabs(2 * R + 1, N, H, W, 'cuda')
 ld = torch.zeros(N, device='cuda'); out = torch.empty_like(yg); ldo = torch.empty_like(ld)
 _lib.call('bruno_coupling_conv_fwd', yg, ld, out, ldo, N, H, W, C, R, layer.mask_id, 0, layer.V1, layer.g1, layer.b1, wf,
-          layer.br, 0, layer.Ks, layer.bs, layer.Kt, layer.bt, None, None, slabs, 2 * R + 1)
+          layer.br, 0, layer.Ks, layer.bs, layer.Kt, layer.bt, None, None, slabs, 2 * R + 1, 1)
 for i, a in enumerate(acts):
     got = slab.slab_to_nhwc(slabs[i], N, H, W, check_padding=True).double().cpu()
     mism = (got != a).double().mean().item()
