@@ -64,33 +64,112 @@ class ClockSampler(threading.Thread):
                 'samples': len(s)}
 
 
+def host_threads():
+    """Host threads the CPU arm may use: every core this process is allowed on.  torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which silently made the round-1 reference arm 13x slower at N > 1; the arm sets its thread count itself."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_line(args, steps, warmup, as_reference_arm):
     """The reference's own CPU path cannot run (TF-1.7 absent): time the oracle restatement (PyTorch-CPU fp32, all host
-    threads) on a bounded sample of the same workload: `sample_b` sequences of 20 frames, forward + backward."""
+    threads) on a bounded sample of the same workload -- `sample_b` sequences of `seq_len` frames per step, one step =
+    forward + backward + TF-1.7 RMSProp update of all variables, i.e. the same work per sequence as our arm's step."""
+    n_thr = host_threads()
+    os.environ['OMP_NUM_THREADS'] = str(n_thr)
+    os.environ['MKL_NUM_THREADS'] = str(n_thr)
     import torch
+    torch.set_num_threads(n_thr)
     from oracle import bruno_oracle as O
-    spec = O.spec_for(CONFIG)
+    name = args.config_name if args.config_name != 'm1_shapenet' else CONFIG
+    spec = O.spec_for(name)
     sample_b = args.cpu_sample_seqs
     P = O.init_params(spec, seed=0, dtype=torch.float32)
-    x = O.synthetic_batch(spec, sample_b, args.seq_len, seed=1, dtype=torch.float32)
+    slots = {k: torch.ones_like(v) for k, v in P.items()}
+    xs = [O.synthetic_batch(spec, sample_b, args.seq_len, seed=1 + i, dtype=torch.float32) for i in range(2)]
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.loss_and_grads(spec, P, x)
+        _, grads = O.loss_and_grads(spec, P, xs[i % 2], student_grad_scale=0.1)
+        for k in P:
+            P[k], slots[k] = O.rmsprop_tf17_step(P[k], grads[k], slots[k], 1e-5)
         times.append(time.perf_counter() - t0)
-    t = sum(times[warmup:]) / max(steps, 1)
+    timed = sorted(times[warmup:])
+    t = sum(timed) / max(steps, 1)
     val = sample_b / t
     cb = {'value': val, 'unit': 'seqs/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-          'sample': '%d sequence(s) x %d frames 28x28, forward+backward of bn2_omniglot_tp (oracle restatement, '
-                    'PyTorch-CPU fp32, no optimiser step), %d timed repetition(s)' % (sample_b, args.seq_len, steps)}
+          'median_ms_per_step': 1e3 * timed[len(timed) // 2],
+          'sample': '%d sequences x %d frames per step, forward + backward + RMSProp of %s (oracle restatement of the '
+                    'reference, PyTorch-CPU fp32, %d threads), %d timed steps after %d warm-up' % (
+                        sample_b, args.seq_len, name, torch.get_num_threads(), steps, warmup)}
     if not as_reference_arm:
         return cb
-    return {'metric': 'bn2_omniglot_tp_train_seqs_per_sec', 'value': val, 'unit': 'seqs/s', 'n_gpus': args.gpus,
+    return {'metric': '%s_train_seqs_per_sec' % name, 'value': val, 'unit': 'seqs/s', 'n_gpus': args.gpus,
             'steps': steps, 'warmup': warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': 'bn2_omniglot_tp training step (fwd+bwd), 28x28x1, seq_len %d' % args.seq_len,
-                       'per_step_sample_seqs': sample_b},
+            'config': {'workload': '%s training step (fwd + bwd + RMSProp), seq_len %d, CPU restatement of the reference' % (name, args.seq_len),
+                       'per_step_sample_seqs': sample_b, 'host_threads': torch.get_num_threads()},
             'cpu_baseline': cb, 'e2e': {'value': val, 'unit': 'seqs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+
+
+def bench_conditional(args, dev, world, rank):
+    """Conditional BRUNO (config_conditional/m1_shapenet: B=4, T=16, 32x32x1, label dim 2, GP with n_context=1), BASELINE.json
+    config C5: training step + NLL evaluation through the same public calls a user of the config module makes."""
+    import torch
+    import torch.distributed as dist
+    from bruno_b200 import _lib
+    from bruno_b200.config_conditional import defaults
+    defaults.seq_len, defaults.n_context = 16, 1
+    cfg = importlib.import_module('bruno_b200.config_conditional.m1_shapenet')
+    from bruno_b200.config_conditional.train import ConditionalTrainer
+    it = cfg.train_data_iter.generate()
+    batches = [next(it) for _ in range(4)]
+    hx = [torch.from_numpy(b[0]).pin_memory() for b in batches]
+    hy = [torch.from_numpy(b[1]).pin_memory() for b in batches]
+    xs, ys = [h.to(dev) for h in hx], [h.to(dev) for h in hy]
+    tr = ConditionalTrainer(cfg, dev, world_size=world, rank=rank).materialize(xs[0], ys[0], init=True)
+    warmup, steps = max(args.warmup, 3), args.steps
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    losses = []
+
+    def e2e(i):
+        x, y = hx[i % 4].to(dev, non_blocking=True), hy[i % 4].to(dev, non_blocking=True)
+        losses.append(tr.train_step(x, y, 1e-3, 0.5).item())
+    for i in range(warmup):
+        tr.train_step(xs[i % 4], ys[i % 4], 1e-3, 0.5)
+    l0 = _lib.query('bruno_launch_count')
+    ms_train = timed(lambda i: tr.train_step(xs[i % 4], ys[i % 4], 1e-3, 0.5), steps)
+    launches = _lib.query('bruno_launch_count') - l0
+    ms_e2e = timed(e2e, steps)
+    ms_eval = timed(lambda i: tr.eval_step(xs[i % 4], ys[i % 4]), steps)
+    B = cfg.batch_size * world
+    return {'metric': 'm1_shapenet_train_seqs_per_sec', 'value': B * steps / (ms_train * 1e-3), 'unit': 'seqs/s', 'n_gpus': world,
+            'steps': steps, 'warmup': warmup, 'ms_per_step': ms_train / steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'Conditional BRUNO m1_shapenet training step: 14 label-conditioned conv couplings (R=6, 3x3 c1) + 6 '
+                                   'label-conditioned dense couplings, GP, n_context 1; fwd + bwd + RMSProp',
+                       'obs_shape': list(cfg.obs_shape[1:]), 'seq_len': cfg.seq_len, 'seqs_per_gpu': cfg.batch_size, 'params': tr.n_params},
+            'eval_nll': {'value': B * steps / (ms_eval * 1e-3), 'unit': 'seqs/s', 'ms_per_step': ms_eval / steps},
+            'e2e': {'value': B * steps / (ms_e2e * 1e-3), 'unit': 'seqs/s', 'ms_per_step': ms_e2e / steps,
+                    'h2d_bytes_per_step': int(hx[0].numel() * 4 + hy[0].numel() * 4), 'd2h_bytes_per_step': 4},
+            'gpu_launches': int(launches), 'final_loss': losses[-1] if losses else None}
 
 
 def main():
@@ -101,9 +180,10 @@ def main():
     ap.add_argument('--impl', default='bruno_b200')
     ap.add_argument('--batch', type=int, default=32, help='sequences per GPU')
     ap.add_argument('--seq_len', type=int, default=20)
-    ap.add_argument('--cpu_sample_seqs', type=int, default=1)
+    ap.add_argument('--cpu_sample_seqs', type=int, default=2, help='sequences per CPU step (BASELINE.md section 5: B = 2)')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--config_name', default=CONFIG, help='config_rnn module; the headline metric is quoted on the default')
+    ap.add_argument('--no_graph', action='store_true', help='time the training step with eager launches instead of the CUDA graph')
     ap.add_argument('--strong', action='store_true', help='strong scaling: --batch is the GLOBAL batch, split over the ranks (train.py:184)')
     ap.add_argument('--data_kind', default=None, help="synthetic pixel distribution: 'strokes' (Omniglot-like) or 'bytes' (uniform)")
     args = ap.parse_args()
@@ -121,7 +201,7 @@ def main():
 
     if args.impl == 'reference':
         if rank == 0:
-            emit(cpu_reference_line(args, min(args.steps, 3), min(args.warmup, 1), True))
+            emit(cpu_reference_line(args, args.steps, args.warmup, True))
         return
 
     import torch
@@ -135,6 +215,13 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     from bruno_b200 import _lib
+    if args.config_name == 'm1_shapenet':
+        line = bench_conditional(args, dev, world, rank)
+        if rank == 0:
+            emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     from bruno_b200.config_rnn import defaults
     from bruno_b200.trainer import Trainer
     defaults.seq_len = args.seq_len
@@ -196,12 +283,20 @@ def main():
 
     for i in range(warmup):
         train_resident(i)
+    torch.cuda.synchronize()
+    l0 = _lib.query('bruno_launch_count')
+    train_resident(0)                                       # one eager step: how many of our kernels a step launches
+    launches_per_step = _lib.query('bruno_launch_count') - l0
+    if not args.no_graph:
+        # forward + hand-written backward as ONE CUDA-graph launch (Trainer.enable_cuda_graph); allreduce + optimiser eager
+        tr.enable_cuda_graph(devx[0])
+        for i in range(2):
+            train_resident(i)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    l0 = _lib.query('bruno_launch_count')
     ms_train = timed(train_resident, steps)
-    launches = _lib.query('bruno_launch_count') - l0
+    launches = launches_per_step * steps
     ms_e2e = timed(train_e2e, steps)
     if sampler:
         sampler.stop_flag = True
@@ -232,8 +327,9 @@ def main():
     ms_fsg = timed(few_shot_graph, fs_steps)
 
     # second pass with per-launch CUDA events on the conv kernels (live durations inside the step)
+    tr.disable_cuda_graph()                                  # per-launch CUDA events need eager launches
     _lib.query('bruno_profile_enable', 1)
-    timed(train_resident, steps)
+    ms_train_eager = timed(train_resident, steps)
     import ctypes
     tot, cnt = ctypes.c_double(), ctypes.c_long()
     prof = {}
@@ -241,6 +337,28 @@ def main():
         _lib.load().bruno_profile_read(kind, ctypes.byref(tot), ctypes.byref(cnt))
         prof[name] = {'total_ms': tot.value, 'launches': cnt.value}
     _lib.query('bruno_profile_enable', 0)
+
+    # The reference's own nr_gpu semantics (config_rnn/train.py:184: ONE batch of `batch_size` sequences, np.split over the
+    # GPUs) = strong scaling: measured in the same run with the global batch of --batch sequences split over the ranks.
+    strong = None
+    if world > 1 and not args.strong and args.batch % world == 0:
+        per = args.batch // world
+        xs_small = [d[:per].contiguous() for d in devx]
+
+        def train_small(i):
+            tr.train_step(xs_small[i % n_host], lr, 0.1)
+        for i in range(3):
+            train_small(i)
+        if not args.no_graph:
+            tr.enable_cuda_graph(xs_small[0])
+            for i in range(2):
+                train_small(i)
+        ms_small = timed(train_small, steps)
+        tr.disable_cuda_graph()
+        strong = {'global_batch': args.batch, 'seqs_per_gpu': per, 'value': args.batch * steps / (ms_small * 1e-3), 'unit': 'seqs/s',
+                  'ms_per_step': ms_small / steps,
+                  'what': 'ONE batch of %d sequences split over %d GPUs (np.split, config_rnn/train.py:184) -- the reference\'s '
+                          'nr_gpu semantics; speed-up over 1 GPU = this value / the 1-GPU bench value' % (args.batch, world)}
 
     if rank != 0:
         if world > 1:
@@ -251,8 +369,17 @@ def main():
     pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(pk):
         peaks = json.load(open(pk))
-    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
-    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback'
+    # Two measured denominators (MEASURED_PEAKS.json): the burst figure (a kernel timed alone / a short region at full
+    # clocks) and the sustained one (inside a long, power-limited step).  Both fractions are reported; `peak` / `frac` use
+    # the one that matches the SM clock sampled DURING the timed region (>= 90 % of max -> burst regime).
+    peak_burst = peaks.get('bf16_tflops', 1660.8)
+    peak_sust = peaks.get('bf16_tflops_sustained', 1396.3)
+    clk = sampler.summary() if sampler else {}
+    burst_regime = bool(clk.get('sm_mhz') and clk.get('sm_max_mhz') and clk['sm_mhz'] >= 0.9 * clk['sm_max_mhz'])
+    peak_tf = peak_burst if burst_regime else peak_sust
+    peak_src = ('measured (MEASURED_PEAKS.json %s; SM clock under load %s of %s MHz -> %s regime)' % (
+        'bf16_tflops' if burst_regime else 'bf16_tflops_sustained', clk.get('sm_mhz'), clk.get('sm_max_mhz'),
+        'burst' if burst_regime else 'sustained')) if peaks else 'fallback (B200_PROFILING.md)'
     n_img = B * T
     conv = prof['conv3x3_fwd_dgrad']
     # forward convs + dgrad convs: 2 x the forward count per step, `steps` steps in the profiled region
@@ -291,29 +418,49 @@ def main():
         lpz = torch.empty(Bz, T, device=dev)
         scr = torch.empty(max(_lib.query('bruno_process_scratch_floats', Bz, T, Dz), 1), device=dev)
 
-        def scan_once():
-            _lib.call('bruno_process_fwd', lay.kind, zz, lay.mu, tab, None, None, lpz, None, scr, Bz, T, Dz)
-        for _ in range(3):
-            scan_once()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(10):
-            scan_once()
-        e1.record()
-        torch.cuda.synchronize()
-        t_scan = e0.elapsed_time(e1) * 1e-3 / 10
-        alg = 4.0 * Bz * T * Dz + 4.0 * Bz * T                # z read once + log-probs written
+        lppz = torch.empty(Bz, T, device=dev)
+        tab_g = build_table(lay.kind, lay.var_vbl.detach(), nu, lay.corr_vbl.detach(), lay.mu, None, lay.min_nu, 0, T, True)
+        dlp = torch.randn(Bz, T, device=dev)
+        dz = torch.empty_like(zz)
+        dvar, dnu, dcorr = torch.empty(1, Dz, device=dev), (torch.empty(1, Dz, device=dev) if nu is not None else None), torch.empty(1, Dz, device=dev)
+        scr_b = torch.empty(max(_lib.query('bruno_process_bwd_scratch_floats', Bz, T, Dz), 1), device=dev)
+
+        def time_it(fn):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e-3 / 10
+
         hbm = peaks.get('hbm_gbs', 6550.0)
+        kname = 'GP' if lay.nu_vbl is None else 'TP'
+        # algorithmic bytes (DESIGN 5.3 / SURVEY 8d3): fwd = z once + log-probs; fwd+prior adds the prior log-probs;
+        # bwd = z read + dz written + dlp read
+        t_f = time_it(lambda: _lib.call('bruno_process_fwd', lay.kind, zz, lay.mu, tab, None, None, lpz, None, scr, Bz, T, Dz))
+        t_fp = time_it(lambda: _lib.call('bruno_process_fwd', lay.kind, zz, lay.mu, tab, None, None, lpz, lppz, scr, Bz, T, Dz))
+        t_b = time_it(lambda: _lib.call('bruno_process_bwd', lay.kind, zz, lay.mu, tab_g, dlp, None, dz, dvar, dnu, dcorr, scr_b, Bz, T, Dz))
+        alg = 4.0 * Bz * T * Dz + 4.0 * Bz * T
+        alg_fp = 4.0 * Bz * T * Dz + 8.0 * Bz * T
+        alg_b = 8.0 * Bz * T * Dz + 4.0 * Bz * T
+        t_scan = t_f
         traffic_scan = None                                   # measured DRAM bytes per latent element (ncu --set full) x elements
         tpj = os.path.join(ROOT, 'profiles', 'r01_process_traffic.json')
         if os.path.exists(tpj) and lay.nu_vbl is not None:
             traffic_scan = json.load(open(tpj))['bytes_per_latent_element'] * Bz * T * Dz
-        scan = {'bound': 'hbm', 'kernel': 'process_fwd_ring_kernel (%s forward scan, persistent bulk-copy ring)' % (
-                    'GP' if lay.nu_vbl is None else 'TP'),
+        scan = {'bound': 'hbm', 'kernel': 'process_fwd_ring_kernel (%s forward scan, persistent bulk-copy ring)' % kname,
                 'achieved': alg / t_scan * 1e-9, 'peak': hbm, 'unit': 'GB/s', 'frac': alg / t_scan * 1e-9 / hbm,
                 'traffic': traffic_scan, 'us_per_launch': t_scan * 1e6, 'shape': [Bz, T, Dz],
+                'fwd_prior': {'what': 'forward scan with the prior log-probs (the NLL-eval path, want_prior=True)',
+                              'achieved': alg_fp / t_fp * 1e-9, 'frac': alg_fp / t_fp * 1e-9 / hbm, 'us_per_launch': t_fp * 1e6},
+                'bwd': {'what': 'hand-written backward scan (dz + parameter gradients)',
+                        'achieved': alg_b / t_b * 1e-9, 'frac': alg_b / t_b * 1e-9 / hbm, 'us_per_launch': t_b * 1e6},
                 'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback'}
+        del dz
         del zz
     except Exception as exc:                                   # the bench line must not die on the side measurement
         scan = {'error': repr(exc)}
@@ -338,19 +485,27 @@ def main():
         'e2e': {'value': seqs * steps / (ms_e2e * 1e-3), 'unit': 'seqs/s', 'h2d_bytes_per_step': int(host[0].numel() * 4),
                 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / steps},
         'gpu_launches': int(launches),
+        'gpu_launches_note': 'kernels of libbruno_sm100.so per step (%d, counted on an eager step) x steps; in the timed region '
+                             'the forward + backward kernels are replayed from ONE CUDA graph (%s)' % (
+                                 launches_per_step, 'off: --no_graph' if args.no_graph else 'on'),
+        'strong_scaling': strong,
+        'ms_per_step_eager': ms_train_eager / steps,
         'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_tap_kernel (tcgen05 implicit GEMM, fwd + dgrad launches)',
                      'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                     'frac': (achieved / peak_tf) if achieved else None, 'traffic': traffic, 'traffic_note': traffic_note,
+                     'frac': (achieved / peak_tf) if achieved else None,
+                     'frac_burst': (achieved / peak_burst) if achieved else None,
+                     'frac_sustained': (achieved / peak_sust) if achieved else None,
+                     'traffic': traffic, 'traffic_note': traffic_note,
                      'peak_source': peak_src,
                      'launches': conv['launches'], 'avg_launch_us': 1e3 * conv['total_ms'] / max(conv['launches'], 1),
-                     'share_of_step': conv['total_ms'] / (ms_train) if ms_train else None},
+                     'share_of_step': conv['total_ms'] / (ms_train_eager) if ms_train_eager else None},
         'roofline_process_scan': scan,
         'kernel_time_ms_per_step': {k: v['total_ms'] / steps for k, v in prof.items()},
         'clocks': sampler.summary() if sampler else None,
         'final_loss': float(losses[-1]) if losses else None,
     }
     if not args.no_cpu_baseline and world == 1:
-        line['cpu_baseline'] = cpu_reference_line(args, 2, 1, False)
+        line['cpu_baseline'] = cpu_reference_line(args, 8, 2, False)
     emit(line)
     if world > 1:
         dist.destroy_process_group()

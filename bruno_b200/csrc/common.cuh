@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "../../include/bruno_sm100.h"
 
@@ -44,6 +45,27 @@ inline int check_launch(const char* what) {
       return BRUNO_EINVAL;            \
     }                                 \
   } while (0)
+
+// Runs `f` once per (call site, CUDA device), under a lock: kernel attributes such as the dynamic-shared-memory opt-in are
+// per device, and two host threads (e.g. the autograd thread and the main thread) may reach a call site at the same time.
+class OncePerDevice {
+ public:
+  template <class F>
+  void run(F f) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0;
+    if (bit && (done_.load(std::memory_order_acquire) & bit)) return;
+    std::lock_guard<std::mutex> lock(mu_);
+    if (bit && (done_.load(std::memory_order_relaxed) & bit)) return;
+    f();
+    done_.fetch_or(bit, std::memory_order_release);
+  }
+
+ private:
+  std::atomic<uint64_t> done_{0};
+  std::mutex mu_;
+};
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

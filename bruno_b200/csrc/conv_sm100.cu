@@ -1636,11 +1636,10 @@ static int g_conv_variant = 1;   // 0: dx-fused N=192 kernel, 1: per-tap N=64 ke
 template <int MODE, int NS>
 static int launch_conv_tap_ns(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
                               const void* a2, void* out, const SlabGeom& g, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice once;
+  once.run([&] {
     cudaFuncSetAttribute(conv3x3_tap_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured = true;
-  }
+  });
   const int ntiles = g.NT;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
   ProfSpan span(BRUNO_PROF_CONV, st);
@@ -1685,11 +1684,10 @@ static int launch_conv_tap(const void* in, const void* w, const float* bias, int
 template <int MODE, int NS>
 static int launch_conv_pair_ns(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
                                const void* a2, void* out, const SlabGeom& g, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice once;
+  once.run([&] {
     cudaFuncSetAttribute(conv3x3_pair_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured = true;
-  }
+  });
   const int ntiles = (g.data_rows + PR_OUT_ROWS - 1) / PR_OUT_ROWS;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
   ProfSpan span(BRUNO_PROF_CONV, st);
@@ -1732,11 +1730,10 @@ static unsigned* g_chain_error_host = nullptr;   // pinned copy of the error wor
 
 template <bool BWD, int NS>
 static int launch_chain_ns(const ChainArgs& a, const SlabGeom& g, size_t smem, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice once;
+  once.run([&] {
     cudaFuncSetAttribute(conv3x3_chain_kernel<BWD, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured = true;
-  }
+  });
   const int ntiles = g.NT;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
   ProfSpan span(BRUNO_PROF_CONV, st);
@@ -1837,11 +1834,10 @@ static int launch_conv(const void* in, const void* w, const float* bias, int bia
   if (g_conv_variant == 1) return launch_conv_tap<MODE>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
   if (g_conv_variant == 2) return launch_conv_pair<MODE>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
   const size_t smem = conv_smem_bytes(g, MODE);
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice once;
+  once.run([&] {
     cudaFuncSetAttribute(conv3x3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured = true;
-  }
+  });
   const int ntiles = (g.data_rows + OUT_ROWS - 1) / OUT_ROWS;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
   ProfSpan span(BRUNO_PROF_CONV, st);
@@ -1948,11 +1944,10 @@ int bruno_conv3x3_wgrad_batched(const void* x_slab, const void* g_slab, float* d
   const SlabGeom g = slab_geom(N, H, W);
   const size_t smem = wgrad_smem_bytes(g);
   BRUNO_REQUIRE(smem <= 227 * 1024, "bruno_conv3x3_wgrad: W=%d too wide", W);
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice once;
+  once.run([&] {
     cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured = true;
-  }
+  });
   int per_layer = num_sms() / L;
   if (per_layer < 1) per_layer = 1;
   if (per_layer > g.NT) per_layer = g.NT;

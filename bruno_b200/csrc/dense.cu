@@ -341,11 +341,10 @@ static int launch_sk(int M, int N, int K, const float* A, int lda, const float* 
                      cudaStream_t st) {
   constexpr int BM = SkShape<TA, MI>::BM;
   constexpr size_t smem = size_t(SK_STAGES) * (SkShape<TA, MI>::A_FLOATS + SkShapeB<TB>::B_FLOATS) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static OncePerDevice once;
+  once.run([&] {
     cudaFuncSetAttribute(sgemm_sk_kernel<TA, TB, MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    attr_done = true;
-  }
+  });
   const int nx = ceil_div(N, SK_BN), ny = ceil_div(M, BM), tiles = nx * ny, nk = ceil_div(K, GK);
   int S = 1;
   if (tiles <= SK_MAX_TILES && sk_workspace(st)) {

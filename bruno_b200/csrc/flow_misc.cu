@@ -920,12 +920,11 @@ int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g
                     ks * ks * C <= MAXK, "bruno_c1_bwd: bad arguments");
   const SlabGeom g = slab_geom(N, H, W);
   const size_t smem = (MAXK * 64 + 256 * 65 + 256 * (ks * ks * C + 1)) * sizeof(float);
-  {
-    // the opt-in is per device: set it on every call (a few hundred ns) instead of caching a per-process flag
-    const cudaError_t e = cudaFuncSetAttribute(c1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               static_cast<int>((MAXK * 64 + 256 * 65 + 256 * (MAXK + 1)) * sizeof(float)));
-    BRUNO_REQUIRE(e == cudaSuccess, "bruno_c1_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-  }
+  static OncePerDevice once;      // the opt-in is per device; not per call (the call may run under stream capture)
+  once.run([&] {
+    cudaFuncSetAttribute(c1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>((MAXK * 64 + 256 * 65 + 256 * (MAXK + 1)) * sizeof(float)));
+  });
   if (C <= 4 && ks == 1) {
     cudaStream_t st8 = static_cast<cudaStream_t>(stream);
     const SlabGeom g8 = slab_geom(N, H, W);
@@ -988,11 +987,10 @@ int bruno_heads_coupling_bwd_cond(const float* x, const void* h_slab, const floa
   const SlabGeom g = slab_geom(N, H, W);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = (2 * 64 * MAXC + 2 * MAXC + 256 * 65 + 256 * (2 * MAXC + 1)) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice once;
+  once.run([&] {
     cudaFuncSetAttribute(heads_coupling_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    configured = true;
-  }
+  });
   slab_zero_padding_kernel<<<148 * 4, 256, 0, st>>>(static_cast<uint8_t*>(g_slab), g);
   if (C <= 4 && !dlabel_s) {
     // eight lanes per pixel, head-weight gradients in registers (see heads_coupling_bwd8_kernel)

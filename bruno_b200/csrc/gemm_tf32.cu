@@ -405,11 +405,10 @@ template <bool TA, bool TB, int BN>
 int launch_tf32_bn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& ep,
                    float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, cudaStream_t st) {
   constexpr size_t smem = 1024 + TG_STAGES * (2 * TG_TILE_BYTES + 2 * BN * TG_BK * 4) + sizeof(TgSmem) + 64;
-  static bool configured = false;
-  if (!configured) {
+  static OncePerDevice once;
+  once.run([&] {
     cudaFuncSetAttribute(tf32x3_gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    configured = true;
-  }
+  });
   const int nx = ceil_div(N, BN), ny = ceil_div(M, TG_BM), tiles = nx * ny, nk = ceil_div(K, TG_BK);
   int S = 1;
   static const char* force_s = getenv("BRUNO_TF32_SPLIT");

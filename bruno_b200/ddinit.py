@@ -16,6 +16,18 @@ def _assign(g, b, pre, dims):
     b.add_(-m * scale_init)                              # b.assign_add(-m_init * scale_init)
 
 
+def assign_from_moments(g, b, m, v):
+    """g.assign(g * scale_init); b.assign_add(-m_init * scale_init) with scale_init = 1 / sqrt(v_init + 1e-10) (nvp:396-397)."""
+    scale_init = (1.0 / torch.sqrt(v + 1e-10)).to(g.dtype)
+    g.mul_(scale_init)
+    b.add_(-(m.to(g.dtype)) * scale_init)
+
+
+def conv_mask(mt, H, W, C, device):
+    """b of CouplingLayerConv.get_mask (nvp:143-160) as an [H, W, C] float tensor."""
+    return _conv_mask(mt, H, W, C, device)
+
+
 def conv_coupling_init(layer, x):
     with torch.no_grad():
         x = x.contiguous()

@@ -317,10 +317,14 @@ class CouplingLayerConv(Layer):                                             # nv
         return self._slabs[1]
 
     def _apply_fp32(self, x, ld, inverse):
-        """fp32 verification path (see _PRECISION): c1 -> 2R convolutions as 9 tap GEMMs each -> heads, all fp32."""
+        """fp32 verification path (see _PRECISION): c1 -> 2R convolutions as 9 tap GEMMs each -> heads, all fp32.
+        Under init_scope(True) it also performs the data-dependent init (nvp:394-398) from the fp32 pre-activations, so
+        that the init can be compared with the reference's at fp32 accuracy (the production init uses the moments of the
+        bf16 path's own activations, bruno_b200/ddinit.py)."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in (x, ld)):
             raise RuntimeError("precision('fp32') is an inference-only verification mode")
-        from .slab import SlabGeom
+        from .slab import SlabGeom, _pixel_rows
+        init = _INIT_MODE[0]
         with torch.no_grad():
             x, ld = x.contiguous(), ld.contiguous()
             N, H, W, C = x.shape
@@ -331,6 +335,8 @@ class CouplingLayerConv(Layer):                                             # nv
             buf = SLABS.pool[key]
             M = g.NT * 128
             _lib.call('bruno_c1_fwd', x, self.V1, self.g1, self.b1, 0, buf[0], 1, N, H, W, C, self.mask_id, 1)
+            moments = []
+            rows = _pixel_rows(g, x.device) if init else None
 
             def conv(src, dst, l, skip, act):
                 V = self.Vr[l].detach().contiguous()
@@ -340,6 +346,9 @@ class CouplingLayerConv(Layer):                                             # nv
                     _lib.call('bruno_sgemm', 0, 0, M, 64, 64, src.data_ptr() + 4 * 64 * (g.HALO + shift), 64,
                               V.data_ptr() + 4 * 64 * 64 * tap, 64, dst.data_ptr() + 4 * 64 * g.HALO, 64, scale, None, 0,
                               1 if tap > 0 else 0)
+                if init:                                   # moments of the pre-activation conv + b over (N, H, W)
+                    pre = dst[rows].double() + self.br[l].double()
+                    moments.append((pre.mean(0), pre.var(0, unbiased=False)))
                 _lib.call('bruno_conv_epilogue_f32', dst, self.br[l].detach().contiguous(), skip, int(act), N, H, W)
 
             hi = 0
@@ -352,13 +361,21 @@ class CouplingLayerConv(Layer):                                             # nv
             ld_out = torch.empty_like(ld)
             _lib.call('bruno_heads_coupling', x, buf[hi], self.Ks, self.bs, self.Kt, self.bt, None, None, ld, y, ld_out, 1,
                       N, H, W, C, self.mask_id, int(inverse))
+            if init:
+                from .ddinit import conv_mask, assign_from_moments
+                b = conv_mask(self.mask_type, H, W, C, x.device)
+                nrm = torch.sqrt(torch.clamp((self.V1.double() ** 2).sum(0), min=1e-12))
+                pre1 = (x * b).reshape(-1, C).double() @ (self.V1.double() * (self.g1.double() / nrm)) + self.b1.double()
+                assign_from_moments(self.g1, self.b1, pre1.mean(0), pre1.var(0, unbiased=False))
+                for l, (m, v) in enumerate(moments):
+                    assign_from_moments(self.gr[l], self.br[l], m, v)
         return y, ld_out
 
     def _apply(self, x, ld, inverse):
         if self.V1 is None:
             self._build(int(x.shape[3]), x.device)
         if _PRECISION[0] == 'fp32':
-            return self._apply_fp32(x, ld, inverse)
+            return self._apply_fp32(x, ld, inverse)          # handles init_scope itself
         out = _ConvCouplingFn.apply(x, ld, self.V1, self.g1, self.b1, self.Vr, self.gr, self.br, self.Ks, self.bs,
                                     self.Kt, self.bt, self, inverse, torch.is_grad_enabled())
         if _INIT_MODE[0]:                      # outputs above use the OLD g, b (nvp:396-398: tf.identity(x))

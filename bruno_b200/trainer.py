@@ -80,7 +80,42 @@ class Trainer(object):
         return sum(p.numel() for p in self.model.parameters())
 
     # -- one step ------------------------------------------------------------------------------------------
+    def enable_cuda_graph(self, x_example):
+        """Captures forward + hand-written backward of ONE batch shape (everything between the input copy and the gradient
+        allreduce: ~600 kernel launches for bn2_omniglot_tp) into a CUDA graph; train_step then replays it with one launch.
+        The allreduce and the optimiser stay outside (learning rate and student-grad scale change every iteration,
+        train.py:165-170, and are kernel arguments).  What it buys: at 32 sequences per GPU the step is GPU-bound either way;
+        in the reference's own nr_gpu semantics (ONE batch of 32 split over 8 GPUs = 80 images per GPU, train.py:184) the
+        host cannot issue 600 launches in the ~3 ms the kernels take -- the graph removes that bound."""
+        if self.overlap_allreduce:
+            raise RuntimeError('the per-layer overlapped allreduce issues NCCL calls from inside the backward: not capturable')
+        self._graph = None
+        static_x = x_example.clone()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                   # warm-up: slab pools, one-time kernel attributes, autograd buffers
+                self._forward_backward_eager(static_x)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = self._forward_backward_eager(static_x)
+        self._graph, self._graph_x, self._graph_loss = graph, static_x, static_loss
+        return self
+
+    def disable_cuda_graph(self):
+        self._graph = None
+
     def forward_backward(self, x):
+        g = getattr(self, '_graph', None)
+        if g is not None and tuple(x.shape) == tuple(self._graph_x.shape):
+            self._graph_x.copy_(x, non_blocking=True)
+            g.replay()
+            self._reduced = []
+            return self._graph_loss                   # static buffer: overwritten by the next replay
+        return self._forward_backward_eager(x)
+
+    def _forward_backward_eager(self, x):
         self.flat_grad.zero_()
         log_probs = self.cfg.build_model(x, want_prior=False)[0]
         loss = self.cfg.loss(log_probs)

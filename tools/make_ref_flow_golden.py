@@ -9,8 +9,9 @@ tests/tf_shim/ (TF-1.7 cannot be installed here).  Full-size networks (64 filter
 units); only batch and sequence length are reduced.
 
 Per config the fixture holds what the reference computes on seeded inputs / weights:
-  * `init_*`    g and b of every weight-normalised layer after `build_model(x, init=True)` (nn_extra_nvp.py:394-398,
-                422-426) -- the data-dependent initialisation;
+  * `init/*`    g and b of every weight-normalised layer after `build_model(x, init=True)` (nn_extra_nvp.py:394-398,
+                422-426) -- the data-dependent initialisation -- from weights with RANDOMISED heads (so that s, t != 0 in
+                the outputs / gradients below); `init0/*` the same from the reference's real iteration-0 state (heads = 0);
   * `log_probs`, `latent`, `prior`, `z_vec`   the four outputs of `build_model(x)` (bn2_omniglot_tp.py:59-168);
   * `loss`, `grad_*`   `config.loss(log_probs)` and d loss / d variable for every trainable variable through torch
                 autograd over the reference code (what `tf.gradients(train_loss, all_params)` returns,
@@ -96,6 +97,18 @@ def run_unconditional(name):
     for k in P0:
         if k not in wn_names(P0):
             assert torch.equal(P1[k], P0[k]), k            # init touches only g and b
+
+    # (1b) the same init pass from the reference's REAL iteration-0 state: zero-initialised heads (nvp:129-138), i.e. the
+    #      flow is the identity and every coupling's s/t network sees the exact logit-transformed input
+    Pz = O.init_params(spec, seed=seed, dtype=torch.float64, randomize_heads=False, perturb_process=True)
+    with ref_loader.reference_modules() as tf:
+        tf.preload_variables({k: v.numpy() for k, v in Pz.items()})
+        cfg = ref_loader.import_config('config_rnn', name, seq_len=T)
+        with torch.no_grad(), tf.variable_scope('model'):
+            cfg.build_model(tf._f(x), init=True)
+            for k, v in tf.variables_by_name().items():
+                if k.endswith('/g') or k.endswith('/b'):
+                    fix['init0/' + k] = v.detach().numpy().copy()
 
     # (2) forward + loss + gradients with the initialised weights (fresh graph: the student layer derives var/nu/corr
     #     from its variables at construction)
