@@ -92,9 +92,13 @@ def report_process(layer):
         print('nu median-min-max:', np.median(nu), np.min(nu), np.max(nu))
 
 
-def validate(config, trainer, device):
-    losses = [config.loss(trainer.eval_step(torch.from_numpy(xb).to(device))[0]).item()
-              for _, xb in zip(range(config.n_valid_batches), config.valid_data_iter.generate())]
+def validate(config, trainer, device, data_iter, n_batches):
+    """train.py:201-223: `eval_loss` if the config defines it (else `loss`), averaged over `n_batches` batches drawn with a
+    FRESH RandomState(42) -- every validation sees the same batches and the iterators' own rng state is untouched."""
+    loss_fn = getattr(config, 'eval_loss', config.loss)
+    rng = np.random.RandomState(42)
+    losses = [loss_fn(trainer.eval_step(torch.from_numpy(np.ascontiguousarray(xb)).to(device))[0]).item()
+              for _, xb in zip(range(n_batches), data_iter.generate(rng))]
     return float(np.mean(losses))
 
 
@@ -171,8 +175,10 @@ def main(argv=None):
             print('%d/%d train_loss=%6.8f bits/value=%.3f' % (done, max_iter, mean, mean / config.ndim / np.log(2.)))
         if hasattr(config, 'validate_every') and done % config.validate_every == 0:
             print('\n Validating ...')
-            run.history['losses_eval_valid'].append(validate(config, trainer, device))
+            run.history['losses_eval_valid'].append(validate(config, trainer, device, config.valid_data_iter, config.n_valid_batches))
             print('valid loss', run.history['losses_eval_valid'][-1])
+            run.history['losses_eval_train'].append(validate(config, trainer, device, config.train_data_iter, config.n_valid_batches * 10))
+            print('train loss', run.history['losses_eval_train'][-1])
         if done % config.save_every == 0 or done == max_iter:
             now = time.time()
             eta = (max_iter - iteration) / config.save_every * (now - last_save)

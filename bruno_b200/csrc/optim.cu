@@ -47,6 +47,45 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   p[i] = p[i] - lr_t * mn / (sqrtf(vn) + eps);
 }
 
+// Episodic fine-tuning loss (config_rnn/bn2_omniglot_tp_ft_1s_20w.py:222-226): log_probs [M*B, T] -> per episode m a
+// softmax over the B candidate sequences of the LAST element's log-prob; loss = -mean_m log softmax_m[0].  One warp per
+// episode (B <= 1024), one block; writes the loss and (optionally) its gradient d loss / d log_probs in the same launch:
+//   d loss / d lp[m, b, T-1] = (softmax_m[b] - [b == 0]) / M, zero for the other columns.
+__global__ void __launch_bounds__(1024)
+episode_softmax_loss_kernel(const float* __restrict__ lp, int M, int B, int T, float* __restrict__ loss,
+                            float* __restrict__ dlp) {
+  __shared__ float partial[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  float acc = 0.f;
+  for (int m = warp; m < M; m += nwarp) {
+    const float* row = lp + static_cast<size_t>(m) * B * T + (T - 1);
+    float mx = -INFINITY;
+    for (int b = lane; b < B; b += 32) mx = fmaxf(mx, row[static_cast<size_t>(b) * T]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int b = lane; b < B; b += 32) se += expf(row[static_cast<size_t>(b) * T] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const float lse = mx + logf(se);
+    if (lane == 0) acc += lse - row[0];                 // -log softmax[0]
+    if (dlp) {
+      float* drow = dlp + static_cast<size_t>(m) * B * T;
+      for (int i = lane; i < B * T; i += 32) {
+        const int b = i / T, t = i - b * T;
+        drow[i] = t == T - 1 ? (expf(row[static_cast<size_t>(b) * T] - lse) - (b == 0 ? 1.f : 0.f)) / static_cast<float>(M) : 0.f;
+      }
+    }
+  }
+  if (lane == 0) partial[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < nwarp; ++w) t += partial[w];    // fixed order: deterministic
+    *loss = t / static_cast<float>(M);
+  }
+}
+
 }  // namespace bruno
 
 using namespace bruno;
@@ -71,6 +110,13 @@ int bruno_adam_tf17(float* p, const float* g, float* m, float* v, size_t n, floa
   adam_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, n, static_cast<float>(lr_t), beta1, beta2, eps, grad_scale);
   return check_launch("adam_kernel");
+}
+
+int bruno_episode_softmax_loss(const float* log_probs, int M, int B, int T, float* loss, float* dlog_probs, void* stream) {
+  BRUNO_REQUIRE(log_probs && loss && M >= 1 && B >= 1 && T >= 1, "bruno_episode_softmax_loss: bad arguments");
+  const int warps = M < 32 ? M : 32;
+  episode_softmax_loss_kernel<<<1, 32 * warps, 0, static_cast<cudaStream_t>(stream)>>>(log_probs, M, B, T, loss, dlog_probs);
+  return check_launch("episode_softmax_loss_kernel");
 }
 
 }  // extern "C"

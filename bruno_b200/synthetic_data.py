@@ -20,22 +20,28 @@ class SyntheticExchSeqDataIterator(object):
     def get_observation_size(self):
         return (self.seq_len,) + self.obs_shape
 
-    def _batch(self):
+    def _batch(self, rng=None, noise_rng=None):
+        rng = self.rng if rng is None else rng
+        noise_rng = self.noise_rng if noise_rng is None else noise_rng
         shape = (self.batch_size, self.seq_len) + self.obs_shape
         if self.kind == 'strokes':
             # one "class" prototype per sequence + per-frame jitter: frames of a sequence are exchangeable, not iid
-            proto = self.rng.uniform(size=(self.batch_size, 1) + self.obs_shape) < 0.1
-            flip = self.rng.uniform(size=shape) < 0.03
+            proto = rng.uniform(size=(self.batch_size, 1) + self.obs_shape) < 0.1
+            flip = rng.uniform(size=shape) < 0.03
             pix = np.logical_xor(np.broadcast_to(proto, shape), flip).astype(np.float32) * 255.0
         else:
-            pix = self.rng.randint(0, 256, size=shape).astype(np.float32)
-        noise = self.noise_rng.uniform(size=shape).astype(np.float32)
+            pix = rng.randint(0, 256, size=shape).astype(np.float32)
+        noise = noise_rng.uniform(size=shape).astype(np.float32)
         return np.minimum(pix + noise, np.float32(255.99998))
 
     def generate(self, rng=None, noise_rng=None):
+        """data_iter.py:56-58: an explicit `rng` replaces the iterator's own (train.py:204 re-seeds it for validation; the
+        dequantisation noise then comes from the same stream, like the reference's noise_rng = self.rng default)."""
+        if rng is not None and noise_rng is None:
+            noise_rng = rng
         i = 0
         while self.nsamples is None or i < self.nsamples:
-            yield self._batch()
+            yield self._batch(rng, noise_rng)
             i += 1
 
     def generate_each_digit(self, **kwargs):
@@ -79,6 +85,37 @@ class SyntheticFewShotIterator(object):
             y = np.repeat(np.asarray(classes)[:, None], self.seq_len, axis=1)
             y[:, -1] = true_cls
             yield x, y, true_cls
+
+
+class SyntheticEpisodesIterator(SyntheticFewShotIterator):
+    """Shape contract of OmniglotEpisodesDataIterator.generate (data_iter.py:244-296), the training stream of the episodic
+    fine-tuning configs: an endless stream of meta-batches of `meta_batch_size` k-way n-shot episodes,
+    x [meta_batch_size * k, n + 1, ...]; inside an episode row 0 is the TRUE class (n shots + the test image) and rows
+    1..k-1 are other classes whose last element is overwritten with the same test image (:282); one noise sequence per
+    episode is added to every row (:284-286)."""
+
+    def __init__(self, seq_len, batch_size, meta_batch_size, obs_shape=(28, 28, 1), rng=None, n_classes=50, **kwargs):
+        super(SyntheticEpisodesIterator, self).__init__(seq_len, batch_size, obs_shape=obs_shape, rng=rng, n_classes=n_classes)
+        self.meta_batch_size = meta_batch_size
+
+    def generate(self, trial=0, rng=None):
+        rng = self.rng if rng is None else rng
+        k, T = self.batch_size, self.seq_len
+        while True:
+            x = np.zeros((self.meta_batch_size, k, T) + self.obs_shape, dtype=np.float32)
+            y = np.zeros((self.meta_batch_size, k, T), dtype=np.float32)
+            for m in range(self.meta_batch_size):
+                true_cls = int(rng.choice(self.n_classes))
+                others = [c for c in range(self.n_classes) if c != true_cls]
+                classes = [true_cls] + [int(c) for c in rng.choice(others, k - 1, replace=False)]
+                for j, c in enumerate(classes):
+                    for s in range(T):
+                        x[m, j, s] = self._draw(c)
+                    y[m, j] = c
+                x[m, 1:, -1] = x[m, 0, -1][None]                       # the same test image closes every candidate row
+                noise = rng.uniform(size=(1, T) + self.obs_shape).astype(np.float32)
+                x[m] = np.minimum(x[m] + noise, np.float32(255.99998))
+            yield (x.reshape((self.meta_batch_size * k, T) + self.obs_shape), y.reshape(self.meta_batch_size * k, T))
 
 
 class SyntheticShapenetIterator(object):

@@ -283,6 +283,11 @@ int bruno_sgemm(int transA, int transB, int M, int N, int K, const float* A, int
  * Optimiser steps with TF-1.7 semantics (config_rnn/train.py:121-131) over a flat fp32 buffer; grad_scale folds the
  * 1/nr_gpu tower average (train.py:103-105) and the student-grad schedule (train.py:108-111).
  * ---------------------------------------------------------------------------------------------------------- */
+/* Episodic fine-tuning loss (config_rnn/bn2_omniglot_tp_ft_1s_20w.py:222-226): log_probs [M*B, T] (M episodes of B candidate
+ * sequences, candidate 0 = the true class); loss[0] = -mean_m log softmax_b(log_probs[m, b, T-1])[0]; dlog_probs (optional,
+ * [M*B, T]) receives d loss / d log_probs. */
+int bruno_episode_softmax_loss(const float* log_probs, int M, int B, int T, float* loss, float* dlog_probs, void* stream);
+
 int bruno_rmsprop_tf17(float* p, const float* g, float* ms, size_t n, float lr, float decay, float eps, float grad_scale,
                        void* stream);
 int bruno_adam_tf17(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
