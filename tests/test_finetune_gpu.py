@@ -23,9 +23,11 @@ def test_episode_loss_kernel_matches_reference_loss(golden_dir):
     loss = losses.episode_softmax_loss(lp, M, B, T)
     loss.backward()
     ref_loss = float(g['loss'])
-    assert abs(loss.item() - ref_loss) <= 1e-5 * abs(ref_loss)
+    # the fixture's log-probs are float64 values around -900: their float32 copies are off by up to 3e-5 absolute, which
+    # is a 3e-5 RELATIVE change of every softmax term
+    assert abs(loss.item() - ref_loss) <= 1e-4 * abs(ref_loss)
     gr = lp.grad.double().cpu().numpy()
-    assert np.abs(gr - g['grad']).max() <= 1e-5 * np.abs(g['grad']).max()
+    assert np.abs(gr - g['grad']).max() <= 1e-4 * np.abs(g['grad']).max()
     assert np.all(gr[:, :-1] == 0.0)                      # only the last element of every sequence carries gradient
 
 
@@ -55,8 +57,9 @@ def test_finetune_config_surface_and_gradient_flow():
     with torch.no_grad():
         cfg.build_model(x[:1])
         for layer in cfg.model.layers():
-            layer.Ks.normal_(0, 0.05)
-            layer.Kt.normal_(0, 0.05)
+            if hasattr(layer, 'Ks'):
+                layer.Ks.normal_(0, 0.05)
+                layer.Kt.normal_(0, 0.05)
     loss = cfg.loss(cfg.build_model(x)[0])
     grads = torch.autograd.grad(loss, cfg.model.parameters())
     assert np.isfinite(loss.item()) and 0.0 < loss.item()

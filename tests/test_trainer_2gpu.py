@@ -23,7 +23,7 @@ def test_two_rank_trainer_equals_single_gpu_full_batch(tmp_path):
     p = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-4000:]
     res = torch.load(out)
-    for name, tol_g, tol_p in (('en2_noconv_mnist_tp', 1e-5, 1e-5), ('bn2_omniglot_tp', 2e-3, 2e-3)):
+    for name, tol_g, tol_p in (('en2_noconv_mnist_tp', 1e-5, 1e-5), ('bn2_omniglot_tp', 1e-4, 1e-4)):
         flat1, g1 = res[(name, 'single')]
         for overlap in (False, True):
             flat2, g2 = res[(name, overlap)]
@@ -32,4 +32,5 @@ def test_two_rank_trainer_equals_single_gpu_full_batch(tmp_path):
             print('\n[%s overlap=%s] 2-rank vs 1-rank: gradient buffer rel L2 %.3e, parameters after 2 steps rel L2 %.3e' % (
                 name, overlap, eg, ep))
             # sums over shards are re-associated (and the conv wgrad accumulates with atomics): not bit-equal
+            # (measured on 2 B200: en2 1.3e-7 / 6.8e-9, bn2 1.3e-6 / 1.8e-6)
             assert eg <= tol_g and ep <= tol_p
