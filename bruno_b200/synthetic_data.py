@@ -48,6 +48,45 @@ class SyntheticExchSeqDataIterator(object):
         for x in self.generate():
             yield x, np.zeros((self.batch_size,), dtype='int32')
 
+    def _class_sequence(self, rng, proto=None, same_image=False):
+        """seq_len frames of one synthetic class (prototype + per-frame flips), pixels in {0, 255}, no noise yet."""
+        shape = (self.seq_len,) + self.obs_shape
+        if self.kind == 'strokes':
+            proto = (rng.uniform(size=self.obs_shape) < 0.1) if proto is None else proto
+            flip = rng.uniform(size=shape) < 0.03
+            if same_image:
+                flip = np.broadcast_to(flip[:1], shape)
+            return np.logical_xor(np.broadcast_to(proto, shape), flip).astype(np.float32) * 255.0
+        seq = rng.randint(0, 256, size=shape).astype(np.float32)
+        return np.broadcast_to(seq[:1], shape).copy() if same_image else seq
+
+    def generate_anomaly(self, noise_rng=None):
+        """Contract of data_iter.py:398-422: ONE sequence of a class whose element seq_len - 5 is replaced by an image of
+        another class; y marks the class of every element.  Yields (x [1, seq_len, ...], y [1, seq_len])."""
+        noise_rng = np.random.RandomState(42) if noise_rng is None else noise_rng
+        while True:
+            x = self._class_sequence(self.rng)[None].copy()
+            y = np.zeros((1, self.seq_len), dtype=np.float32)
+            x[0, self.seq_len - 5] = self._class_sequence(self.rng)[0]
+            y[0, self.seq_len - 5] = 1.0
+            yield np.minimum(x + noise_rng.uniform(size=x.shape).astype(np.float32), np.float32(255.99998)), y
+
+    def generate_diagonal_roll(self, same_class=True, same_image=False, black_image=False, rng=None, noise_rng=None):
+        """Contract of data_iter.py:424-463: a batch of seq_len copies of ONE sequence, copy i rolled by i positions, so
+        that the diagonal of a [seq_len, seq_len] output follows frame 0 through every position of the sequence."""
+        rng = self.rng if rng is None else rng
+        noise_rng = self.rng if noise_rng is None else noise_rng
+        while True:
+            seq = self._class_sequence(rng, same_image=same_image)[None].copy()
+            if black_image:
+                seq[0, 0] *= 0.
+            if black_image and same_image:
+                seq *= 0.
+            if not same_class:
+                seq[0, 0] = self._class_sequence(rng)[0]
+            seq = np.minimum(seq + noise_rng.uniform(size=seq.shape).astype(np.float32), np.float32(255.99998))
+            yield np.concatenate([np.roll(seq, i, axis=1) for i in range(self.seq_len)], 0)
+
 
 class SyntheticFewShotIterator(object):
     """Shape contract of OmniglotTestBatchSeqDataIterator.generate (data_iter.py:204-241): k-way n-shot episodes as
