@@ -604,6 +604,59 @@ __global__ void masked_accumulate_kernel(float* __restrict__ dx, const float* __
 
 static inline unsigned nblk(size_t total) { return static_cast<unsigned>((total + 255) / 256); }
 
+// ---- label-conditioned dense coupling (nn_extra_nvp_conditional.py:162-266, 350-369, 437-471) -----------------------
+// dst[m, off + j] = src[m, j] (* dense mask b(j) if mask_type >= 0), dst row pitch ld
+__global__ void copy_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t total, int n, int ld, int off,
+                                 int mask_type) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t m = i / n;
+  const int j = static_cast<int>(i - m * n);
+  const float b = mask_type >= 0 ? dense_mask_b(mask_type, j) : 1.f;
+  dst[m * ld + off + j] = src[i] * b;
+}
+// dst[m, j] = src[m, off + j], src row pitch ld
+__global__ void slice_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t total, int n, int ld, int off) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t m = i / n;
+  dst[i] = src[m * ld + off + static_cast<int>(i - m * n)];
+}
+// dpre = dh * leaky_relu'(h): the sign of the output is the sign of the pre-activation (alpha = 0.2)
+__global__ void leaky_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dh, float* __restrict__ dpre, size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < total) dpre[i] = dh[i] * (h[i] > 0.f ? 1.f : 0.2f);
+}
+__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < total) a[i] += b[i];
+}
+
+struct CondDenseWs {
+  float *scL1, *inL1, *scL2, *inL2, *sc1, *in1, *sc2, *in2;
+  float *hL1, *preL1, *o1, *h1, *pre1, *hL2, *preL2, *o2, *h2, *pre2, *hs, *ht, *s_pre, *t_pre;
+};
+static size_t cond_dense_ws_floats(int N, int D, int U, int L) {
+  const size_t n = N, nh1 = D / 2, nh2 = U / 2;
+  auto r4 = [](size_t v) { return (v + 3) / 4 * 4; };
+  return 2 * r4(nh1) + 2 * r4(nh2) + 4 * r4(U) + 2 * r4(n * nh1) + r4(n * (nh1 + D)) + 2 * r4(n * U) + 2 * r4(n * nh2) +
+         r4(n * (nh2 + U)) + 2 * r4(n * U) + 2 * r4(n * nh2) + 2 * r4(n * D);
+}
+static CondDenseWs cond_carve(float* ws, int N, int D, int U) {
+  CondDenseWs w;
+  const size_t n = N, nh1 = D / 2, nh2 = U / 2;
+  size_t o = 0;
+  auto take = [&](size_t v) { float* p = ws + o; o += (v + 3) / 4 * 4; return p; };
+  w.scL1 = take(nh1); w.inL1 = take(nh1); w.scL2 = take(nh2); w.inL2 = take(nh2);
+  w.sc1 = take(U); w.in1 = take(U); w.sc2 = take(U); w.in2 = take(U);
+  w.hL1 = take(n * nh1); w.preL1 = take(n * nh1); w.o1 = take(n * (nh1 + D)); w.h1 = take(n * U); w.pre1 = take(n * U);
+  w.hL2 = take(n * nh2); w.preL2 = take(n * nh2); w.o2 = take(n * (nh2 + U)); w.h2 = take(n * U); w.pre2 = take(n * U);
+  w.hs = take(n * nh2); w.ht = take(n * nh2); w.s_pre = take(n * D); w.t_pre = take(n * D);
+  return w;
+}
+// order of the 20 variables of a label-conditioned dense coupling (construction order of the reference graph)
+enum CondVar { cLV1, cLg1, cLb1, cV1, cg1, cb1, cLV2, cLg2, cLb2, cV2, cg2, cb2, cWs, cbws, cKs, cbs, cWt, cbwt, cKt, cbt, cNVAR };
+
 struct DenseWs {
   float *sc1, *sc2, *in1, *in2, *xm, *pre1, *pre2, *h1, *h2, *s_pre, *t_pre;
 };
@@ -749,6 +802,134 @@ int bruno_coupling_dense_bwd(const float* x, const float* dy, const float* dld, 
   }
   masked_accumulate_kernel<<<nblk(ND), 256, 0, st>>>(dx, dxm, ND, D, mask_type);
   return check_launch("bruno_coupling_dense_bwd");
+}
+
+size_t bruno_coupling_dense_cond_ws_floats(int N, int D, int U, int L) { return cond_dense_ws_floats(N, D, U, L); }
+size_t bruno_coupling_dense_cond_bwd_ws_floats(int N, int D, int U, int L) {
+  const size_t n = N, k1 = D / 2 + D, k2 = U / 2 + U;
+  auto r4 = [](size_t v) { return (v + 3) / 4 * 4; };
+  return 2 * r4(n * D) + r4(n * (k1 > k2 ? k1 : k2)) + 2 * r4(n * U) + 2 * r4(n * (D / 2 > U / 2 ? D / 2 : U / 2)) +
+         r4(n * L) + r4(U > D / 2 ? U : D / 2) + 16;
+}
+
+int bruno_coupling_dense_cond_fwd(const float* x, const float* yl, const float* ld_in, float* y, float* ld_out, int N, int D,
+                                  int U, int L, int mask_type, int inverse, const float* const* vars, float* ws, void* stream) {
+  BRUNO_REQUIRE(x && yl && ld_in && y && ld_out && vars && ws, "bruno_coupling_dense_cond_fwd: null pointer");
+  BRUNO_REQUIRE(N > 0 && D > 0 && U > 0 && L > 0 && D % 2 == 0 && U % 2 == 0 &&
+                    (mask_type == BRUNO_MASK_EVEN || mask_type == BRUNO_MASK_ODD), "bruno_coupling_dense_cond_fwd: bad sizes / mask");
+  for (int i = 0; i < cNVAR; ++i) BRUNO_REQUIRE(vars[i] != nullptr, "bruno_coupling_dense_cond_fwd: variable %d is null", i);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nh1 = D / 2, nh2 = U / 2, K1 = nh1 + D, K2 = nh2 + U;
+  const size_t n = N;
+  CondDenseWs w = cond_carve(ws, N, D, U);
+  dense_wn_scale_kernel<<<ceil_div(nh1, 32), 1024, 0, st>>>(vars[cLV1], vars[cLg1], w.scL1, w.inL1, L, nh1);
+  dense_wn_scale_kernel<<<ceil_div(nh2, 32), 1024, 0, st>>>(vars[cLV2], vars[cLg2], w.scL2, w.inL2, L, nh2);
+  dense_wn_scale_kernel<<<ceil_div(U, 32), 1024, 0, st>>>(vars[cV1], vars[cg1], w.sc1, w.in1, K1, U);
+  dense_wn_scale_kernel<<<ceil_div(U, 32), 1024, 0, st>>>(vars[cV2], vars[cg2], w.sc2, w.in2, K2, U);
+  int rc;
+  // d1 = dense_wn(concat(leaky(dense_wn(y_label)), x * b))   (cond:461-471)
+  if ((rc = gemm(false, false, N, nh1, L, yl, L, vars[cLV1], nh1, w.hL1, nh1, GemmEpi{w.scL1, vars[cLb1], w.preL1, 2, 0, nullptr}, st))) return rc;
+  copy_cols_kernel<<<nblk(n * nh1), 256, 0, st>>>(w.hL1, w.o1, n * nh1, nh1, K1, 0, -1);
+  copy_cols_kernel<<<nblk(n * D), 256, 0, st>>>(x, w.o1, n * D, D, K1, nh1, mask_type);
+  if ((rc = gemm(false, false, N, U, K1, w.o1, K1, vars[cV1], U, w.h1, U, GemmEpi{w.sc1, vars[cb1], w.pre1, 1, 0, nullptr}, st))) return rc;
+  // d2
+  if ((rc = gemm(false, false, N, nh2, L, yl, L, vars[cLV2], nh2, w.hL2, nh2, GemmEpi{w.scL2, vars[cLb2], w.preL2, 2, 0, nullptr}, st))) return rc;
+  copy_cols_kernel<<<nblk(n * nh2), 256, 0, st>>>(w.hL2, w.o2, n * nh2, nh2, K2, 0, -1);
+  copy_cols_kernel<<<nblk(n * U), 256, 0, st>>>(w.h1, w.o2, n * U, U, K2, nh2, -1);
+  if ((rc = gemm(false, false, N, U, K2, w.o2, K2, vars[cV2], U, w.h2, U, GemmEpi{w.sc2, vars[cb2], w.pre2, 1, 0, nullptr}, st))) return rc;
+  // heads: plain dense(concat(leaky(dense(y_label)), h2))   (cond:350-369) = hs Ks[:nh2] + h2 Ks[nh2:] + bs
+  if ((rc = gemm(false, false, N, nh2, L, yl, L, vars[cWs], nh2, w.hs, nh2, GemmEpi{nullptr, vars[cbws], nullptr, 2, 0, nullptr}, st))) return rc;
+  if ((rc = gemm(false, false, N, nh2, L, yl, L, vars[cWt], nh2, w.ht, nh2, GemmEpi{nullptr, vars[cbwt], nullptr, 2, 0, nullptr}, st))) return rc;
+  if ((rc = gemm(false, false, N, D, nh2, w.hs, nh2, vars[cKs], D, w.s_pre, D, GemmEpi{nullptr, vars[cbs], nullptr, 0, 0, nullptr}, st))) return rc;
+  if ((rc = gemm(false, false, N, D, U, w.h2, U, vars[cKs] + static_cast<size_t>(nh2) * D, D, w.s_pre, D, GemmEpi{nullptr, nullptr, nullptr, 0, 1, nullptr}, st))) return rc;
+  if ((rc = gemm(false, false, N, D, nh2, w.ht, nh2, vars[cKt], D, w.t_pre, D, GemmEpi{nullptr, vars[cbt], nullptr, 0, 0, nullptr}, st))) return rc;
+  if ((rc = gemm(false, false, N, D, U, w.h2, U, vars[cKt] + static_cast<size_t>(nh2) * D, D, w.t_pre, D, GemmEpi{nullptr, nullptr, nullptr, 0, 1, nullptr}, st))) return rc;
+  dense_coupling_kernel<<<N, 256, 0, st>>>(x, w.s_pre, w.t_pre, ld_in, y, ld_out, D, mask_type, inverse);
+  return check_launch("bruno_coupling_dense_cond_fwd");
+}
+
+int bruno_coupling_dense_cond_bwd(const float* x, const float* yl, const float* dy, const float* dld, int N, int D, int U, int L,
+                                  int mask_type, const float* const* vars, const float* ws_fwd, float* ws_bwd, float* dx,
+                                  float* dyl, float* const* grads, void* stream) {
+  BRUNO_REQUIRE(x && yl && dy && dld && vars && ws_fwd && ws_bwd && dx && dyl && grads, "bruno_coupling_dense_cond_bwd: null pointer");
+  for (int i = 0; i < cNVAR; ++i) BRUNO_REQUIRE(vars[i] && grads[i], "bruno_coupling_dense_cond_bwd: variable / gradient %d is null", i);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nh1 = D / 2, nh2 = U / 2, K1 = nh1 + D, K2 = nh2 + U;
+  const size_t n = N, ND = n * D, NU = n * U;
+  CondDenseWs w = cond_carve(const_cast<float*>(ws_fwd), N, D, U);
+  size_t o = 0;
+  auto take = [&](size_t v) { float* p = ws_bwd + o; o += (v + 3) / 4 * 4; return p; };
+  float* ds_pre = take(ND);
+  float* dt_pre = take(ND);
+  float* dob = take(n * (K1 > K2 ? K1 : K2));      // gradient of a concat buffer
+  float* dh = take(NU);
+  float* dpre = take(NU);
+  float* dhl = take(n * (nh1 > nh2 ? nh1 : nh2));  // gradient of a label branch output
+  float* dprel = take(n * (nh1 > nh2 ? nh1 : nh2));
+  float* dyl_t = take(n * L);
+  float* r1 = take(U > nh1 ? U : nh1);
+  int rc;
+  const GemmEpi plain{nullptr, nullptr, nullptr, 0, 0, nullptr};
+  const GemmEpi accum{nullptr, nullptr, nullptr, 0, 1, nullptr};
+  bool dyl_set = false;
+  // dyl (+)= dpre_label @ W^T (optionally with the weight-norm column scale folded into the rows of dpre_label)
+  auto label_back = [&](const float* dpl, const float* W, int ncol, const float* kscale) -> int {
+    GemmEpi e = dyl_set ? accum : plain;
+    e.a_kscale = kscale;
+    dyl_set = true;
+    return gemm(false, true, N, L, ncol, dpl, ncol, W, ncol, dyl, L, e, st);
+  };
+  (void)dyl_t;
+  dense_coupling_bwd_kernel<<<nblk(ND), 256, 0, st>>>(x, w.s_pre, dy, dld, dx, ds_pre, dt_pre, ND, D, mask_type);
+  // ---- heads
+  struct Head { const float* dpre_out; int W, bw, K, b; const float* hl; };
+  const Head heads[2] = {{ds_pre, cWs, cbws, cKs, cbs, w.hs}, {dt_pre, cWt, cbwt, cKt, cbt, w.ht}};
+  for (int hidx = 0; hidx < 2; ++hidx) {
+    const Head& H = heads[hidx];
+    if ((rc = gemm(true, false, nh2, D, N, H.hl, nh2, H.dpre_out, D, grads[H.K], D, plain, st))) return rc;
+    if ((rc = gemm(true, false, U, D, N, w.h2, U, H.dpre_out, D, grads[H.K] + static_cast<size_t>(nh2) * D, D, plain, st))) return rc;
+    col_reduce(H.dpre_out, nullptr, grads[H.b], nullptr, N, D, st);
+    if ((rc = gemm(false, true, N, U, D, H.dpre_out, D, vars[H.K] + static_cast<size_t>(nh2) * D, D, dh, U, hidx ? accum : plain, st))) return rc;
+    // label branch of the head: plain dense + leaky_relu
+    if ((rc = gemm(false, true, N, nh2, D, H.dpre_out, D, vars[H.K], D, dhl, nh2, plain, st))) return rc;
+    leaky_bwd_kernel<<<nblk(n * nh2), 256, 0, st>>>(H.hl, dhl, dprel, n * nh2);
+    if ((rc = gemm(true, false, L, nh2, N, yl, L, dprel, nh2, grads[H.W], nh2, plain, st))) return rc;
+    col_reduce(dprel, nullptr, grads[H.bw], nullptr, N, nh2, st);
+    if ((rc = label_back(dprel, vars[H.W], nh2, nullptr))) return rc;
+  }
+  // ---- d2 then d1: dense_wn(concat(label branch, input))
+  struct Lay { int LV, Lg, Lb, V, g, b, nh, K, din; const float *scL, *inL, *sc, *in, *hL, *preL, *o, *pre; };
+  const Lay lays[2] = {{cLV2, cLg2, cLb2, cV2, cg2, cb2, nh2, K2, U, w.scL2, w.inL2, w.sc2, w.in2, w.hL2, w.preL2, w.o2, w.pre2},
+                       {cLV1, cLg1, cLb1, cV1, cg1, cb1, nh1, K1, D, w.scL1, w.inL1, w.sc1, w.in1, w.hL1, w.preL1, w.o1, w.pre1}};
+  for (int li = 0; li < 2; ++li) {
+    const Lay& Y = lays[li];
+    elu_bwd_kernel<<<nblk(NU), 256, 0, st>>>(Y.pre, dh, dpre, NU);
+    col_reduce(dpre, Y.pre, grads[Y.b], r1, N, U, st);
+    if ((rc = gemm(true, false, Y.K, U, N, Y.o, Y.K, dpre, U, grads[Y.V], U, plain, st))) return rc;
+    dense_wn_bwd_kernel<<<nblk(static_cast<size_t>(Y.K) * U), 256, 0, st>>>(vars[Y.V], vars[Y.g], vars[Y.b], Y.sc, Y.in, r1, grads[Y.b],
+                                                                          grads[Y.V], grads[Y.g], Y.K, U);
+    {
+      GemmEpi e = plain;
+      e.a_kscale = Y.sc;
+      if ((rc = gemm(false, true, N, Y.K, U, dpre, U, vars[Y.V], U, dob, Y.K, e, st))) return rc;
+    }
+    // label branch: dense_wn + leaky_relu
+    slice_cols_kernel<<<nblk(n * Y.nh), 256, 0, st>>>(dob, dhl, n * Y.nh, Y.nh, Y.K, 0);
+    leaky_bwd_kernel<<<nblk(n * Y.nh), 256, 0, st>>>(Y.hL, dhl, dprel, n * Y.nh);
+    col_reduce(dprel, Y.preL, grads[Y.Lb], r1, N, Y.nh, st);
+    if ((rc = gemm(true, false, L, Y.nh, N, yl, L, dprel, Y.nh, grads[Y.LV], Y.nh, plain, st))) return rc;
+    dense_wn_bwd_kernel<<<nblk(static_cast<size_t>(L) * Y.nh), 256, 0, st>>>(vars[Y.LV], vars[Y.Lg], vars[Y.Lb], Y.scL, Y.inL, r1,
+                                                                            grads[Y.Lb], grads[Y.LV], grads[Y.Lg], L, Y.nh);
+    if ((rc = label_back(dprel, vars[Y.LV], Y.nh, Y.scL))) return rc;
+    // input branch
+    if (li == 0) {
+      slice_cols_kernel<<<nblk(NU), 256, 0, st>>>(dob, dh, NU, U, Y.K, Y.nh);           // gradient of h1
+    } else {
+      slice_cols_kernel<<<nblk(ND), 256, 0, st>>>(dob, ds_pre, ND, D, Y.K, Y.nh);        // gradient of x * b (ds_pre is free now)
+      masked_accumulate_kernel<<<nblk(ND), 256, 0, st>>>(dx, ds_pre, ND, D, mask_type);
+    }
+  }
+  return check_launch("bruno_coupling_dense_cond_bwd");
 }
 
 }  // extern "C"

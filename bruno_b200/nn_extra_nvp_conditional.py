@@ -187,6 +187,47 @@ class _DenseCouplingElemFn(torch.autograd.Function):
         return dx, ds, dt, dld, None
 
 
+def _ptr_array(tensors):
+    """`const float* const*` argument of the C ABI: a host array of device pointers (kept alive by the caller)."""
+    import ctypes
+    for t in tensors:
+        _lib.ptr(t)                                        # CUDA / float32 / contiguous checks
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class _CondDenseCouplingFn(torch.autograd.Function):
+    """Label-conditioned CouplingLayerDense (cond:162-266): forward = bruno_coupling_dense_cond_fwd, backward =
+    bruno_coupling_dense_cond_bwd -- hand-written: the gradients of the 20 variables, of x and of the label embedding
+    come from one C-ABI call each way (GEMMs on the tcgen05 3xTF32 path, fused scale / bias / activation epilogues)."""
+    @staticmethod
+    def forward(ctx, x, ld, yl, layer, inverse, *vs):
+        xs = x.shape
+        x, ld, yl = x.contiguous(), ld.contiguous(), yl.contiguous()
+        N, D, U, L = xs[0], int(np.prod(xs[1:])), layer.n_units, yl.shape[1]
+        vs = [v.contiguous() for v in vs]
+        ws = _new_like(x, _lib.query('bruno_coupling_dense_cond_ws_floats', N, D, U, L))
+        y, ld_out = torch.empty_like(x), torch.empty_like(ld)
+        _lib.call('bruno_coupling_dense_cond_fwd', x, yl, ld, y, ld_out, N, D, U, L, layer.mask_id, int(inverse), _ptr_array(vs), ws)
+        if any(ctx.needs_input_grad):
+            if inverse:
+                raise RuntimeError('backward through the inverse pass is not implemented (sampling is inference-only)')
+            ctx.dims = (N, D, U, L, layer.mask_id)
+            ctx.save_for_backward(x, yl, ws, *vs)
+        return y, ld_out
+
+    @staticmethod
+    def backward(ctx, dy, dld):
+        x, yl, ws = ctx.saved_tensors[:3]
+        vs = list(ctx.saved_tensors[3:])
+        N, D, U, L, mask_id = ctx.dims
+        ws2 = _new_like(x, _lib.query('bruno_coupling_dense_cond_bwd_ws_floats', N, D, U, L))
+        dx, dyl = torch.empty_like(x), torch.empty_like(yl)
+        grads = [torch.empty_like(v) for v in vs]
+        _lib.call('bruno_coupling_dense_cond_bwd', x, yl, dy.contiguous(), dld.contiguous(), N, D, U, L, mask_id, _ptr_array(vs), ws,
+                  ws2, dx, dyl, _ptr_array(grads))
+        return (dx, dld, dyl, None, None) + tuple(grads)
+
+
 class Layer(object):                                                        # cond:26-31
     def forward_and_jacobian(self, x, sum_log_det_jacobians, z, y_label):
         raise NotImplementedError(str(type(self)))
@@ -349,39 +390,13 @@ class CouplingLayerDense(Layer):                                            # co
         N, D = xs[0], int(np.prod(xs[1:]))
         if self.P is None:
             self._build(D, int(y_label.shape[1]), x.device)
-        P = self.P
-        idx = torch.arange(D, device=x.device) % 2
-        b = (idx if self.mask_type == 'even' else 1 - idx).to(torch.float32)
-        if _grad_mode(x, ld, y_label, *self.parameters()):
-            if inverse:
-                raise RuntimeError('backward through the inverse pass is not implemented (sampling is inference-only)')
-            x2 = x.reshape(N, D)
-            y = x2 * b
-            for nm in ('d1', 'd2'):
-                h = dense_wn_train(y_label, P[nm + '/label_h/V'], P[nm + '/label_h/g'], P[nm + '/label_h/b'], LEAKY)
-                y = dense_wn_train(torch.cat([h, y], 1), P['%s/%s/V' % (nm, nm)], P['%s/%s/g' % (nm, nm)],
-                                   P['%s/%s/b' % (nm, nm)], ELU)
-            pre = []
-            for nm in ('d_scale', 'd_translate'):
-                h = dense_train(y_label, P[nm + '/label_W1/kernel'], P[nm + '/label_W1/bias'], LEAKY)
-                pre.append(dense_train(torch.cat([h, y], 1), P['%s/%s/kernel' % (nm, nm)], P['%s/%s/bias' % (nm, nm)]))
-            out, ld_out = _DenseCouplingElemFn.apply(x2, pre[0], pre[1], ld, self.mask_id)
-            return out.reshape(xs), ld_out
-        with torch.no_grad():
-            y = x.view(N, D) * b                                                       # x1 = x * mask
-            for nm in ('d1', 'd2'):                                                    # cond:461-471
-                h = dense_wn_apply(y_label, P[nm + '/label_h/V'], P[nm + '/label_h/g'], P[nm + '/label_h/b'], LEAKY)
-                y = dense_wn_apply(torch.cat([h, y], 1), P['%s/%s/V' % (nm, nm)], P['%s/%s/g' % (nm, nm)],
-                                   P['%s/%s/b' % (nm, nm)], ELU)
-            pre = []
-            for nm in ('d_scale', 'd_translate'):                                      # cond:350-369
-                h = _sgemm(y_label, P[nm + '/label_W1/kernel'], self.n_units // 2, None, P[nm + '/label_W1/bias'], LEAKY)
-                pre.append(_sgemm(torch.cat([h, y], 1), P['%s/%s/kernel' % (nm, nm)], D, None, P['%s/%s/bias' % (nm, nm)], NONE))
-            out = torch.empty_like(x)
-            ld_in = ld.contiguous() if ld is not None else torch.zeros(N, device=x.device)
-            ld_out = torch.empty_like(ld_in)
-            _lib.call('bruno_dense_coupling', x, pre[0], pre[1], ld_in, out, ld_out, N, D, self.mask_id, int(inverse))
-        return out, ld_out
+        vs = list(self.P.values())
+        assert len(vs) == 20
+        ld_in = ld if ld is not None else torch.zeros(N, device=x.device)
+        if inverse and _grad_mode(x, ld, y_label, *vs):
+            raise RuntimeError('backward through the inverse pass is not implemented (sampling is inference-only)')
+        out, ld_out = _CondDenseCouplingFn.apply(x, ld_in, y_label, self, bool(inverse), *vs)
+        return out.reshape(xs), ld_out
 
     def forward_and_jacobian(self, x, sum_log_det_jacobians, z, y_label=None):
         y, ld = self._apply(x, sum_log_det_jacobians, y_label, False)

@@ -283,6 +283,22 @@ int bruno_sgemm(int transA, int transB, int M, int N, int K, const float* A, int
  * Optimiser steps with TF-1.7 semantics (config_rnn/train.py:121-131) over a flat fp32 buffer; grad_scale folds the
  * 1/nr_gpu tower average (train.py:103-105) and the student-grad schedule (train.py:108-111).
  * ---------------------------------------------------------------------------------------------------------- */
+/* Label-conditioned dense coupling (nn_extra_nvp_conditional.py:162-266): every weight-normalised dense layer is
+ * dense_wn(concat(leaky_relu(dense_wn(y_label)), input)) (:461-471), every head dense(concat(leaky_relu(dense(y_label)), h))
+ * (:350-369).  yl [N, L] = the label embedding; `vars` = 20 device pointers in the reference's construction order:
+ *   d1/label_h/{V [L,D/2], g, b}, d1/d1/{V [D/2+D,U], g, b}, d2/label_h/{V [L,U/2], g, b}, d2/d2/{V [U/2+U,U], g, b},
+ *   d_scale/label_W1/{kernel [L,U/2], bias}, d_scale/d_scale/{kernel [U/2+U,D], bias}, d_translate/... (same shapes).
+ * fwd: y, ld_out as bruno_coupling_dense_fwd; `ws` (bruno_coupling_dense_cond_ws_floats floats) keeps the activations.
+ * bwd: dx [N,D], dyl [N,L] (gradient w.r.t. the label embedding), grads = 20 device pointers shaped like vars (overwritten;
+ * weight-norm backward included); ws_bwd: bruno_coupling_dense_cond_bwd_ws_floats floats. */
+size_t bruno_coupling_dense_cond_ws_floats(int N, int D, int U, int L);
+size_t bruno_coupling_dense_cond_bwd_ws_floats(int N, int D, int U, int L);
+int bruno_coupling_dense_cond_fwd(const float* x, const float* yl, const float* ld_in, float* y, float* ld_out, int N, int D,
+                                  int U, int L, int mask_type, int inverse, const float* const* vars, float* ws, void* stream);
+int bruno_coupling_dense_cond_bwd(const float* x, const float* yl, const float* dy, const float* dld, int N, int D, int U, int L,
+                                  int mask_type, const float* const* vars, const float* ws_fwd, float* ws_bwd, float* dx,
+                                  float* dyl, float* const* grads, void* stream);
+
 /* Episodic fine-tuning loss (config_rnn/bn2_omniglot_tp_ft_1s_20w.py:222-226): log_probs [M*B, T] (M episodes of B candidate
  * sequences, candidate 0 = the true class); loss[0] = -mean_m log softmax_b(log_probs[m, b, T-1])[0]; dlog_probs (optional,
  * [M*B, T]) receives d loss / d log_probs. */
