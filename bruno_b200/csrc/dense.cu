@@ -932,4 +932,53 @@ int bruno_coupling_dense_cond_bwd(const float* x, const float* yl, const float* 
   return check_launch("bruno_coupling_dense_cond_bwd");
 }
 
+// ---- one dense layer, forward + hand-written backward (label paths of the conditional model) --------------------------
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (a ? a[i] : 0.f) + (b ? b[i] : 0.f);
+}
+
+size_t bruno_dense_layer_bwd_ws_floats(int N, int U) { return static_cast<size_t>(N) * U + U + 8; }
+
+int bruno_dense_layer_fwd(const float* x, const float* W, const float* g, const float* b, const float* extra_bias, int N, int K,
+                          int U, int act, float* out, float* pre, float* sc, float* inv_nrm, float* btot, void* stream) {
+  BRUNO_REQUIRE(x && W && out && btot && N > 0 && K > 0 && U > 0 && act >= 0 && act <= 3, "bruno_dense_layer_fwd: bad arguments");
+  BRUNO_REQUIRE(!g || (sc && inv_nrm), "bruno_dense_layer_fwd: weight-norm needs the sc / inv_nrm outputs");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  add_vec_kernel<<<ceil_div(U, 256), 256, 0, st>>>(b, extra_bias, btot, U);
+  if (g) dense_wn_scale_kernel<<<ceil_div(U, 32), 1024, 0, st>>>(W, g, sc, inv_nrm, K, U);
+  return gemm(false, false, N, U, K, x, K, W, U, out, U, GemmEpi{g ? sc : nullptr, btot, pre, act, 0, nullptr}, st);
+}
+
+int bruno_dense_layer_bwd(const float* x, const float* W, const float* g, const float* btot, const float* sc,
+                          const float* inv_nrm, const float* pre, const float* out, const float* dout, int N, int K, int U,
+                          int act, float* ws, float* dx, float* dW, float* dg, float* db, void* stream) {
+  BRUNO_REQUIRE(x && W && dout && ws && dW && db && N > 0 && K > 0 && U > 0, "bruno_dense_layer_bwd: bad arguments");
+  BRUNO_REQUIRE(!g || (btot && sc && inv_nrm && pre && dg), "bruno_dense_layer_bwd: weight-norm needs btot / sc / inv_nrm / pre / dg");
+  BRUNO_REQUIRE(act == 0 || (act == 1 && pre) || (act == 2 && out), "bruno_dense_layer_bwd: act 1 needs pre, act 2 needs out");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t NU = static_cast<size_t>(N) * U;
+  float* dpre_buf = ws;
+  float* r1 = ws + (NU + 3) / 4 * 4;
+  const float* dpre = dout;
+  if (act == 1) {
+    elu_bwd_kernel<<<nblk(NU), 256, 0, st>>>(pre, dout, dpre_buf, NU);
+    dpre = dpre_buf;
+  } else if (act == 2) {
+    leaky_bwd_kernel<<<nblk(NU), 256, 0, st>>>(out, dout, dpre_buf, NU);
+    dpre = dpre_buf;
+  }
+  col_reduce(dpre, g ? pre : nullptr, db, g ? r1 : nullptr, N, U, st);
+  int rc;
+  const GemmEpi plain{nullptr, nullptr, nullptr, 0, 0, nullptr};
+  if ((rc = gemm(true, false, K, U, N, x, K, dpre, U, dW, U, plain, st))) return rc;
+  if (g) dense_wn_bwd_kernel<<<nblk(static_cast<size_t>(K) * U), 256, 0, st>>>(W, g, btot, sc, inv_nrm, r1, db, dW, dg, K, U);
+  if (dx) {
+    GemmEpi e = plain;
+    e.a_kscale = g ? sc : nullptr;
+    if ((rc = gemm(false, true, N, K, U, dpre, U, W, U, dx, K, e, st))) return rc;
+  }
+  return check_launch("bruno_dense_layer_bwd");
+}
+
 }  // extern "C"

@@ -5,16 +5,14 @@ config_conditional/m1_shapenet.py).  Layer protocol of the reference (:27-31):
 Every weight-normalised conv adds dense_wn(y_label)[:, None, None, :] to its output (:422-433) -- on the GPU that is a
 per-image bias table consumed by the tensor-core conv epilogue; every dense layer is fed concat(dense(y_label), x)
 (:461-471, :350-369).
-Inference (NLL evaluation, sampling: forward + inverse) runs through the fused kernels.  Training: the conv coupling has a
-hand-written backward (bruno_coupling_conv_bwd_cond: the unconditional backward + per-image gradients of the bias tables
-and head terms); the small label paths and the dense coupling are composed from differentiable primitives whose matrix
-products and coupling arithmetic are C-ABI calls (_MatmulFn, _DenseCouplingElemFn) and whose per-column scale / bias /
-activation are elementwise torch ops on [N, units] tensors.
+Inference (NLL evaluation, sampling: forward + inverse) and training run through the fused kernels; every backward is
+hand-written: the conv coupling (bruno_coupling_conv_bwd_cond: the unconditional backward + per-image gradients of the
+bias tables and head terms), the dense coupling (bruno_coupling_dense_cond_bwd: one call for all 20 variables, x and the
+label embedding) and the label paths (bruno_dense_layer_bwd per dense layer).  torch only carries the autograd graph
+between those calls.
 """
 import numpy as np
 import torch
-
-import torch.nn.functional as F
 
 from . import _lib
 from .nn_extra_nvp import (MASKS, SLABS, _check_generation, Layer as _BaseLayer, elu, int_shape, _new_like, _pre, _SpaceToDepthFn,  # noqa: F401
@@ -60,57 +58,45 @@ def dense_wn_apply(x, V, g, b, act=NONE, extra_bias=None):
 # ------------------------------------------------------------------------------------------------------------------
 # differentiable primitives of the training path
 # ------------------------------------------------------------------------------------------------------------------
-class _MatmulFn(torch.autograd.Function):
-    """a [M,K] @ b [K,N] and its two gradient products, all through bruno_sgemm."""
+class _DenseLayerFn(torch.autograd.Function):
+    """One dense layer of a label path -- dense_wn (g given) or plain dense -- with fused scale / bias / activation; the
+    backward (dx, dW or dV, dg, db) is the hand-written bruno_dense_layer_bwd, not autograd of torch ops."""
     @staticmethod
-    def forward(ctx, a, b):
-        a, b = a.contiguous(), b.contiguous()
-        M, K = a.shape
-        N = b.shape[1]
-        c = _new_like(a, M, N)
-        _lib.call('bruno_sgemm', 0, 0, M, N, K, a, K, b, N, c, N, None, None, 0, 0)
-        ctx.save_for_backward(a, b)
-        return c
+    def forward(ctx, x, W, g, b, extra_bias, act):
+        x, W = x.contiguous(), W.contiguous()
+        N, K = x.shape
+        U = W.shape[1]
+        out, pre = _new_like(x, N, U), _new_like(x, N, U)
+        sc = _new_like(x, U) if g is not None else None
+        inv = _new_like(x, U) if g is not None else None
+        btot = _new_like(x, U)
+        _lib.call('bruno_dense_layer_fwd', x, W, g, b, extra_bias, N, K, U, int(act), out, pre, sc, inv, btot)
+        ctx.act, ctx.has = int(act), (g is not None, b is not None, extra_bias is not None)
+        ctx.save_for_backward(x, W, g, btot, sc, inv, pre, out)
+        return out
 
     @staticmethod
-    def backward(ctx, dc):
-        a, b = ctx.saved_tensors
-        dc = dc.contiguous()
-        M, K = a.shape
-        N = b.shape[1]
-        da = db = None
-        if ctx.needs_input_grad[0]:                      # da = dc @ b^T   (b is stored [K, N] = op(B)^T stored [N', K'])
-            da = _new_like(a, M, K)
-            _lib.call('bruno_sgemm', 0, 1, M, K, N, dc, N, b, N, da, K, None, None, 0, 0)
-        if ctx.needs_input_grad[1]:                      # db = a^T @ dc   (a is stored [M, K] = op(A)^T stored [K', M'])
-            db = _new_like(a, K, N)
-            _lib.call('bruno_sgemm', 1, 0, K, N, M, a, K, dc, N, db, N, None, None, 0, 0)
-        return da, db
-
-
-def _act(pre, act):
-    if act == ELU:
-        return F.elu(pre)
-    if act == LEAKY:
-        return F.leaky_relu(pre, 0.2)
-    if act == TANH:
-        return torch.tanh(pre)
-    return pre
+    def backward(ctx, dout):
+        x, W, g, btot, sc, inv, pre, out = ctx.saved_tensors
+        N, K = x.shape
+        U = W.shape[1]
+        ws = _new_like(x, _lib.query('bruno_dense_layer_bwd_ws_floats', N, U))
+        dx = _new_like(x, N, K) if ctx.needs_input_grad[0] else None
+        dW, db = torch.empty_like(W), _new_like(x, U)
+        dg = _new_like(x, U) if g is not None else None
+        _lib.call('bruno_dense_layer_bwd', x, W, g, btot, sc, inv, pre, out, dout.contiguous(), N, K, U, ctx.act, ws, dx, dW, dg, db)
+        has_g, has_b, has_e = ctx.has
+        return dx, dW, dg, (db if has_b else None), (db if has_e else None), None
 
 
 def dense_wn_train(x, V, g, b, act=NONE, extra_bias=None):
-    """dense_wn (cond:437-459), differentiable: (x @ V) * g / ||V|| + b."""
-    pre = _MatmulFn.apply(x, V) * (g / torch.sqrt((V * V).sum(0))) + b
-    if extra_bias is not None:
-        pre = pre + extra_bias
-    return _act(pre, act)
+    """dense_wn (cond:437-459), differentiable: (x @ V) * g / ||V|| + b (+ extra_bias)."""
+    return _DenseLayerFn.apply(x, V, g, b, extra_bias, act)
 
 
 def dense_train(x, K, bias=None, act=NONE):
-    pre = _MatmulFn.apply(x, K)
-    if bias is not None:
-        pre = pre + bias
-    return _act(pre, act)
+    """plain tf.layers.dense, differentiable."""
+    return _DenseLayerFn.apply(x, K, None, bias, None, act)
 
 
 def _grad_mode(*tensors):
@@ -164,27 +150,6 @@ class _CondConvCouplingFn(torch.autograd.Function):
                   dls, dlt, 3)
         # the conv biases live inside `tab` (tab = label term + conv bias): db1 / dbr reach them through dtab
         return dx, dld, dV1, dg1, dVr, dgr, dKs, dbs, dKt, dbt, dtab, dls, dlt, None
-
-
-class _DenseCouplingElemFn(torch.autograd.Function):
-    """The affine coupling itself for the dense layers: y = x b + (1-b)(x e^s + t), ld += sum s, s = tanh(s_pre)(1-b)."""
-    @staticmethod
-    def forward(ctx, x, s_pre, t_pre, ld, mask_id):
-        x, s_pre, t_pre, ld = x.contiguous(), s_pre.contiguous(), t_pre.contiguous(), ld.contiguous()
-        N, D = x.shape
-        y, ld_out = torch.empty_like(x), torch.empty_like(ld)
-        _lib.call('bruno_dense_coupling', x, s_pre, t_pre, ld, y, ld_out, N, D, mask_id, 0)
-        ctx.mask_id = mask_id
-        ctx.save_for_backward(x, s_pre)
-        return y, ld_out
-
-    @staticmethod
-    def backward(ctx, dy, dld):
-        x, s_pre = ctx.saved_tensors
-        N, D = x.shape
-        dx, ds, dt = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
-        _lib.call('bruno_dense_coupling_bwd', x, s_pre, dy.contiguous(), dld.contiguous(), dx, ds, dt, N, D, ctx.mask_id)
-        return dx, ds, dt, dld, None
 
 
 def _ptr_array(tensors):

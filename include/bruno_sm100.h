@@ -299,6 +299,20 @@ int bruno_coupling_dense_cond_bwd(const float* x, const float* yl, const float* 
                                   int mask_type, const float* const* vars, const float* ws_fwd, float* ws_bwd, float* dx,
                                   float* dyl, float* const* grads, void* stream);
 
+/* One dense layer with its hand-written backward (the label paths of the conditional model: labels_layer m1:66-67,
+ * label_h of every weight-normalised conv cond:422-433, label_h of the conv heads cond:382-388).
+ *   g != NULL: dense_wn -- out = act((x W) g / ||W||_col + b + extra_bias)   (cond:437-459);   g == NULL: plain dense.
+ *   act: 0 none, 1 ELU, 2 leaky_relu(0.2), 3 tanh (forward only).  fwd outputs: out [N,U], pre [N,U] (may be NULL when
+ *   act == 0 or 2 and g == NULL), sc / inv_nrm [U] (weight norm), btot [U] = b + extra_bias.
+ *   bwd: dW [K,U] (w.r.t. V for weight norm), dg [U], db [U] (= gradient of b AND of extra_bias), dx [N,K] (may be NULL);
+ *   ws: bruno_dense_layer_bwd_ws_floats(N, U) floats. */
+size_t bruno_dense_layer_bwd_ws_floats(int N, int U);
+int bruno_dense_layer_fwd(const float* x, const float* W, const float* g, const float* b, const float* extra_bias, int N, int K,
+                          int U, int act, float* out, float* pre, float* sc, float* inv_nrm, float* btot, void* stream);
+int bruno_dense_layer_bwd(const float* x, const float* W, const float* g, const float* btot, const float* sc,
+                          const float* inv_nrm, const float* pre, const float* out, const float* dout, int N, int K, int U,
+                          int act, float* ws, float* dx, float* dW, float* dg, float* db, void* stream);
+
 /* Episodic fine-tuning loss (config_rnn/bn2_omniglot_tp_ft_1s_20w.py:222-226): log_probs [M*B, T] (M episodes of B candidate
  * sequences, candidate 0 = the true class); loss[0] = -mean_m log softmax_b(log_probs[m, b, T-1])[0]; dlog_probs (optional,
  * [M*B, T]) receives d loss / d log_probs. */
