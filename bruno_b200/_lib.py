@@ -57,6 +57,8 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     _protos = declared_prototypes()
     for name, (restype, argtypes) in _protos.items():
+        if not hasattr(lib, name) and (name.startswith('bruno_debug_') or '_set_' in name):
+            continue                     # a library built with -DBRUNO_NO_DEBUG has no A/B switches
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes
@@ -85,6 +87,26 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+_workspaces = {}     # (device index, stream handle) -> the caller-owned GEMM workspace bound to that stream
+
+
+def ensure_workspace():
+    """The library never allocates: the split-K / column-reduction workspace of the dense-path GEMMs is allocated here
+    (once per device and stream, zero-filled) and bound with bruno_workspace_bind.  Under stream capture nothing can be
+    allocated: capture on a stream that has been warmed up (Trainer.enable_cuda_graph / BrunoModel.graphed_forward do);
+    without a bound workspace the GEMMs run un-split."""
+    st = torch.cuda.current_stream()
+    key = (st.device.index, st.cuda_stream)
+    if key in _workspaces or torch.cuda.is_current_stream_capturing():
+        return
+    lib = load()
+    ws = torch.zeros(lib.bruno_workspace_bytes(), dtype=torch.uint8, device=st.device)
+    rc = lib.bruno_workspace_bind(st.cuda_stream, ws.data_ptr(), ws.numel())
+    if rc != 0:
+        raise RuntimeError('bruno_workspace_bind failed (%d): %s' % (rc, last_error()))
+    _workspaces[key] = ws
+
+
 _ABI_DTYPES = (torch.float32, torch.uint8)      # fp32 data; uint8 = packed bf16 weights / activation slabs (opaque bytes)
 
 
@@ -94,6 +116,7 @@ def call(name, *args):
     iterator, an int tensor) would be reinterpreted silently, so it raises here."""
     lib = load()
     fn = getattr(lib, name)
+    ensure_workspace()
     conv = []
     for a in args:
         if isinstance(a, torch.Tensor):

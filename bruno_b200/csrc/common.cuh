@@ -71,11 +71,4 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// conv_sm100.cu: L stacked 3x3 convolutions of one geometry as ONE persistent launch (modes per layer: forward
-// 0 = bias+ELU / 1 = bias+skip+ELU, backward 2 = dgrad*ELU' / 3 = (dgrad+addend)*ELU').  Returns BRUNO_OK, a negative
-// error code, or +1 when the chain path is unavailable and the caller must launch the layers one by one.
-int conv3x3_chain(bool backward, int L, const void* const* in, const void* const* w, const float* const* bias,
-                  const void* const* aux1, const void* const* aux2, void* const* out, const int* mode, int bias_img_stride,
-                  int N, int H, int W, cudaStream_t st);
-
 }  // namespace bruno

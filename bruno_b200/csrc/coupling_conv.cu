@@ -27,24 +27,6 @@ int bruno_coupling_conv_fwd(const float* x, const float* ld_in, float* y, float*
   const size_t bl = 64;
   if ((rc = bruno_c1_fwd(x, V1, g1, b1, bias_img_stride, S(0), 0, N, H, W, C, mask_type, c1_ks, stream))) return rc;
   int hi = 0;
-  if (2 * R <= 16) {
-    // the 2R convolutions as one persistent launch (conv3x3_chain_kernel); falls through to per-layer launches if the
-    // chain path is unavailable
-    const void* cin[16]; const void* cw[16]; const float* cb[16]; const void* ca1[16]; void* cout[16]; int cm[16];
-    int h = 0;
-    for (int r = 0; r < R; ++r) {
-      const int ui = save ? 2 * r + 1 : (h + 1) % 3;
-      const int ni = save ? 2 * r + 2 : (h + 2) % 3;
-      cin[2 * r] = S(h); cw[2 * r] = Wp(2 * r); cb[2 * r] = br + (2 * r) * bl; ca1[2 * r] = nullptr; cout[2 * r] = S(ui); cm[2 * r] = 0;
-      cin[2 * r + 1] = S(ui); cw[2 * r + 1] = Wp(2 * r + 1); cb[2 * r + 1] = br + (2 * r + 1) * bl; ca1[2 * r + 1] = S(h);
-      cout[2 * r + 1] = S(ni); cm[2 * r + 1] = 1;
-      h = ni;
-    }
-    rc = conv3x3_chain(false, 2 * R, cin, cw, cb, ca1, nullptr, cout, cm, bias_img_stride, N, H, W, static_cast<cudaStream_t>(stream));
-    if (rc < 0) return rc;
-    if (rc == 0)
-      return bruno_heads_coupling(x, S(h), Ks, bs, Kt, bt, label_s, label_t, ld_in, y, ld_out, 0, N, H, W, C, mask_type, inverse, stream);
-  }
   for (int r = 0; r < R; ++r) {
     const int ui = save ? 2 * r + 1 : (hi + 1) % 3;
     const int ni = save ? 2 * r + 2 : (hi + 2) % 3;
@@ -87,19 +69,7 @@ int bruno_coupling_conv_bwd_cond(const float* x, const float* dy, const float* d
   int rc;
   if ((rc = bruno_heads_coupling_bwd_cond(x, S(2 * R), Ks, bs, Kt, bt, dy, dld, dx, GS(2 * R), dKs, dbs, dKt, dbt, scratch, N, H,
                                           W, C, mask_type, label_s, dlabel_s, dlabel_t, stream))) return rc;
-  bool chained = false;
-  if (2 * R <= 16) {
-    const void* cin[16]; const void* cw[16]; const void* ca1[16]; const void* ca2[16]; void* cout[16]; int cm[16];
-    int k = 0;
-    for (int r = R - 1; r >= 0; --r) {
-      cin[k] = GS(2 * r + 2); cw[k] = Wp(2 * r + 1); ca1[k] = S(2 * r + 1); ca2[k] = nullptr; cout[k] = GS(2 * r + 1); cm[k] = 2; ++k;
-      cin[k] = GS(2 * r + 1); cw[k] = Wp(2 * r); ca1[k] = S(2 * r); ca2[k] = GS(2 * r + 2); cout[k] = GS(2 * r); cm[k] = 3; ++k;
-    }
-    rc = conv3x3_chain(true, 2 * R, cin, cw, nullptr, ca1, ca2, cout, cm, 0, N, H, W, st);
-    if (rc < 0) return rc;
-    chained = rc == 0;
-  }
-  for (int r = R - 1; r >= 0 && !chained; --r) {
+  for (int r = R - 1; r >= 0; --r) {
     // g2 = dgrad_c3(g3) * ELU'(u_r);   g3' (or g1) = (dgrad_c2(g2) + g3) * ELU'(block input)
     if ((rc = bruno_conv3x3(2, GS(2 * r + 2), Wp(2 * r + 1), nullptr, 0, S(2 * r + 1), nullptr, GS(2 * r + 1), N, H, W, stream))) return rc;
     if ((rc = bruno_conv3x3(3, GS(2 * r + 1), Wp(2 * r), nullptr, 0, S(2 * r), GS(2 * r + 2), GS(2 * r), N, H, W, stream))) return rc;

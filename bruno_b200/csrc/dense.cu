@@ -304,37 +304,41 @@ sgemm_sk_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const
   }
 }
 
-// split-K workspace (grow-never, allocated on first use outside stream capture)
+// Split-K / column-reduction workspace.  The library never allocates device memory: the caller allocates
+// bruno_workspace_bytes() zero-initialised bytes and binds them to the stream it launches on (bruno_workspace_bind).  A launch
+// on a stream without a bound workspace runs un-split (correct, slower).  One workspace per stream: the tickets and the
+// partial tiles of two GEMMs in flight must not alias.
 constexpr size_t SK_WS_FLOATS = size_t(4) << 20;   // 16 MB
 constexpr int SK_MAX_TILES = 4096;
 constexpr size_t CR_WS_FLOATS = size_t(64) << 10;  // column-reduction partials, after the split-K region
 constexpr int CR_MAX_GROUPS = 1024;                // column-reduction tickets, after the split-K tickets
-static float* g_sk_ws = nullptr;
-static unsigned* g_sk_tickets = nullptr;
-static int g_sk_sms = 0;
+constexpr size_t WS_BYTES = (SK_WS_FLOATS + CR_WS_FLOATS) * sizeof(float) + (SK_MAX_TILES + CR_MAX_GROUPS) * sizeof(unsigned);
 
-static int g_gemm_variant = 1;   // 0: CUDA-core SGEMM, 1: tcgen05 3xTF32 (gemm_tf32.cu)
+struct Workspace {
+  float* ws = nullptr;           // [SK_WS_FLOATS + CR_WS_FLOATS]
+  unsigned* tickets = nullptr;   // [SK_MAX_TILES + CR_MAX_GROUPS], zero between launches
+  int sms = 0;
+  explicit operator bool() const { return ws != nullptr; }
+};
+struct WsEntry { cudaStream_t stream; int device; Workspace w; bool used; };
+constexpr int WS_MAX_BOUND = 64;
+static WsEntry g_ws_table[WS_MAX_BOUND];         // caller-owned buffers, keyed by (device, stream)
+static std::mutex g_ws_mutex;
 
-static bool sk_workspace(cudaStream_t st) {
-  if (g_sk_ws) return true;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
+static Workspace sk_workspace(cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_sk_sms, cudaDevAttrMultiProcessorCount, dev);
-  float* w = nullptr;
-  unsigned* t = nullptr;
-  if (cudaMalloc(&w, (SK_WS_FLOATS + CR_WS_FLOATS) * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return false; }
-  if (cudaMalloc(&t, (SK_MAX_TILES + CR_MAX_GROUPS) * sizeof(unsigned)) != cudaSuccess ||
-      cudaMemset(t, 0, (SK_MAX_TILES + CR_MAX_GROUPS) * sizeof(unsigned)) != cudaSuccess) {
-    cudaGetLastError();
-    cudaFree(w);
-    return false;
-  }
-  g_sk_ws = w;
-  g_sk_tickets = t;
-  return true;
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  for (int i = 0; i < WS_MAX_BOUND; ++i)
+    if (g_ws_table[i].used && g_ws_table[i].stream == st && g_ws_table[i].device == dev) return g_ws_table[i].w;
+  return Workspace{};
 }
+
+#ifndef BRUNO_NO_DEBUG
+static int g_gemm_variant = 1;   // 0: CUDA-core SGEMM, 1: tcgen05 3xTF32 (gemm_tf32.cu)
+#else
+constexpr int g_gemm_variant = 1;
+#endif
 
 template <bool TA, bool TB, int MI>
 static int launch_sk(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& ep,
@@ -347,15 +351,16 @@ static int launch_sk(int M, int N, int K, const float* A, int lda, const float* 
   });
   const int nx = ceil_div(N, SK_BN), ny = ceil_div(M, BM), tiles = nx * ny, nk = ceil_div(K, GK);
   int S = 1;
-  if (tiles <= SK_MAX_TILES && sk_workspace(st)) {
-    S = (2 * g_sk_sms + tiles / 2) / tiles;
+  const Workspace wk = sk_workspace(st);
+  if (tiles <= SK_MAX_TILES && wk) {
+    S = (2 * wk.sms + tiles / 2) / tiles;
     S = max(1, min(S, nk / 4));
     const size_t per_split = static_cast<size_t>(tiles) * BM * SK_BN;
     while (S > 1 && per_split * S > SK_WS_FLOATS) --S;
   }
   const int kchunk = ceil_div(nk, S);
   S = ceil_div(nk, kchunk);
-  sgemm_sk_kernel<TA, TB, MI><<<dim3(nx, ny, S), 256, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep, kchunk, g_sk_ws, g_sk_tickets);
+  sgemm_sk_kernel<TA, TB, MI><<<dim3(nx, ny, S), 256, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep, kchunk, wk.ws, wk.tickets);
   return check_launch("sgemm_sk_kernel");
 }
 
@@ -363,10 +368,11 @@ static int gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, 
                 const GemmEpi& ep, cudaStream_t st) {
   const bool vec_ok = aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0 && K % 4 == 0 &&
                       (ta ? M % 4 == 0 : true) && (tb ? true : N % 4 == 0) && (!ep.a_kscale || aligned16(ep.a_kscale));
-  if (vec_ok && g_gemm_variant == 1 && sk_workspace(st)) {
+  const Workspace wk = sk_workspace(st);
+  if (vec_ok && g_gemm_variant == 1 && wk) {
     int taken = 0;
-    const int rc = gemm_tf32x3(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, ep, g_sk_ws, SK_WS_FLOATS, g_sk_tickets, SK_MAX_TILES,
-                               g_sk_sms, st, &taken);
+    const int rc = gemm_tf32x3(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, ep, wk.ws, SK_WS_FLOATS, wk.tickets, SK_MAX_TILES,
+                               wk.sms, st, &taken);
     if (taken) return rc;
   }
   if (vec_ok) {
@@ -573,12 +579,13 @@ col_reduce_kernel(const float* __restrict__ A, const float* __restrict__ Bm, flo
 static void col_reduce(const float* A, const float* Bm, float* out1, float* out2, int M, int N, cudaStream_t st) {
   const int groups = ceil_div(N, 32);
   int ms = 1;
-  if (groups <= CR_MAX_GROUPS && sk_workspace(st)) {
-    ms = max(1, min(CR_MAX_SPLIT, min(M / 32, (2 * g_sk_sms) / groups)));
+  const Workspace wk = sk_workspace(st);
+  if (groups <= CR_MAX_GROUPS && wk) {
+    ms = max(1, min(CR_MAX_SPLIT, min(M / 32, (2 * wk.sms) / groups)));
     while (ms > 1 && static_cast<size_t>(groups) * ms * 64 > CR_WS_FLOATS) --ms;
   }
-  col_reduce_kernel<<<dim3(groups, ms), 256, 0, st>>>(A, Bm, out1, out2, M, N, g_sk_ws ? g_sk_ws + SK_WS_FLOATS : nullptr,
-                                                      g_sk_tickets ? g_sk_tickets + SK_MAX_TILES : nullptr);
+  col_reduce_kernel<<<dim3(groups, ms), 256, 0, st>>>(A, Bm, out1, out2, M, N, wk ? wk.ws + SK_WS_FLOATS : nullptr,
+                                                      wk ? wk.tickets + SK_MAX_TILES : nullptr);
 }
 
 // weight-norm backward for dense_wn.  dVraw = x^T dpre;  r1 = colsum(dpre * pre);  db = colsum(dpre).
@@ -685,6 +692,7 @@ size_t bruno_coupling_dense_bwd_ws_floats(int N, int D, int U) {
   return 3 * (static_cast<size_t>(N) * D + 4) + 2 * (static_cast<size_t>(N) * U + 4) + 4 * (static_cast<size_t>(U) + 4);
 }
 
+#ifndef BRUNO_NO_DEBUG
 int bruno_debug_gemm_variant(int variant) {
   if (variant < 0) return g_gemm_variant;
   BRUNO_REQUIRE(variant == 0 || variant == 1, "bruno_debug_gemm_variant: 0 (CUDA-core SGEMM) or 1 (tcgen05 3xTF32)");
@@ -694,6 +702,41 @@ int bruno_debug_gemm_variant(int variant) {
 
 int bruno_debug_gemm_trace(long long* device_buffer) {
   gemm_tf32x3_set_trace(device_buffer);
+  return BRUNO_OK;
+}
+#endif
+
+size_t bruno_workspace_bytes(void) { return WS_BYTES; }
+
+int bruno_workspace_bind(void* stream, void* workspace, size_t bytes) {
+  BRUNO_REQUIRE(workspace && bytes >= WS_BYTES && aligned16(workspace), "bruno_workspace_bind: need >= %zu zero-initialised, 16-byte aligned bytes",
+                WS_BYTES);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  int slot = -1;
+  for (int i = 0; i < WS_MAX_BOUND; ++i) {
+    if (g_ws_table[i].used && g_ws_table[i].stream == st && g_ws_table[i].device == dev) { slot = i; break; }
+    if (!g_ws_table[i].used && slot < 0) slot = i;
+  }
+  BRUNO_REQUIRE(slot >= 0, "bruno_workspace_bind: more than %d bound workspaces", WS_MAX_BOUND);
+  Workspace w;
+  w.ws = static_cast<float*>(workspace);
+  w.tickets = reinterpret_cast<unsigned*>(w.ws + SK_WS_FLOATS + CR_WS_FLOATS);
+  w.sms = sms;
+  g_ws_table[slot] = WsEntry{st, dev, w, true};
+  return BRUNO_OK;
+}
+
+int bruno_workspace_unbind(void* stream) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  for (int i = 0; i < WS_MAX_BOUND; ++i)
+    if (g_ws_table[i].used && g_ws_table[i].stream == static_cast<cudaStream_t>(stream) && g_ws_table[i].device == dev)
+      g_ws_table[i].used = false;
   return BRUNO_OK;
 }
 

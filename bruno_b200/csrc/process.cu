@@ -1631,8 +1631,10 @@ int bruno_process_table(int kind, const float* var_vbl, const float* nu_vbl, con
   return check_launch("process_table_kernel");
 }
 
+#ifndef BRUNO_NO_DEBUG
 void bruno_process_set_fwd_variant(int variant) { g_fwd_variant = variant < 0 ? 0 : variant; }
 void bruno_process_set_bwd_variant(int variant) { g_bwd_variant = variant < 0 ? 0 : variant; }
+#endif
 
 size_t bruno_process_scratch_floats(int B, int T, int D) {
   const int nseg = scan_geom(D, false).nseg;  // worst case: the scalar (unaligned) path (>= the ring kernel's segments)

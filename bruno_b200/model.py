@@ -118,7 +118,7 @@ class BrunoModel(object):
                     self.build_model(static_x, want_prior=want_prior)
             torch.cuda.current_stream().wait_stream(s)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=s):             # the warmed-up stream: its GEMM workspace is bound
                 static_out = self.build_model(static_x, want_prior=want_prior)
 
         def run(x):

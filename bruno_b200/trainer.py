@@ -98,7 +98,7 @@ class Trainer(object):
                 self._forward_backward_eager(static_x)
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=side):          # the warmed-up stream: its GEMM workspace is bound
             static_loss = self._forward_backward_eager(static_x)
         self._graph, self._graph_x, self._graph_loss = graph, static_x, static_loss
         return self

@@ -8,10 +8,18 @@
  *
  * Conventions
  *   - every function returns 0 (BRUNO_OK) or a negative BRUNO_E* code; bruno_last_error() gives the message
- *   - all data pointers are DEVICE pointers owned by the caller; nothing here allocates device memory
+ *   - all data pointers are DEVICE pointers owned by the caller.  The library never allocates or frees device (or
+ *     pinned host) memory: every buffer, including scratch, is an argument sized by a *_bytes / *_floats query; the one
+ *     buffer that is not an argument of each call -- the split-K / column-reduction workspace of the dense-path GEMMs --
+ *     is caller-owned too and bound per stream with bruno_workspace_bind (below)
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
  *   - float tensors are contiguous fp32; images are NHWC like the reference
- *   - entry points are re-entrant across streams and devices (no mutable global state)
+ *   - entry points may be called concurrently from several host threads on different streams / devices.  Process-wide
+ *     state, all of it listed here: (1) the launch counter and the optional CUDA-event profile (bruno_profile_*);
+ *     (2) the table of caller-bound workspaces (mutex-protected); (3) one-time per-device kernel attributes
+ *     (dynamic shared-memory opt-in, mutex-protected); (4) the A/B switches of the DEBUG section at the end of each
+ *     group (bruno_debug_*, bruno_process_set_*_variant): not thread-safe, never touched by the product path, compiled
+ *     out with -DBRUNO_NO_DEBUG.
  */
 #ifndef BRUNO_SM100_H_
 #define BRUNO_SM100_H_
@@ -32,6 +40,15 @@ const char* bruno_last_error(void);
 int bruno_abi_version(void);
 /* number of CUDA kernels this library has launched in this process (evidence for bench.py's gpu_launches) */
 long bruno_launch_count(void);
+
+/* Workspace of the dense-path GEMMs (bruno_sgemm, bruno_coupling_dense_*, bruno_dense_layer_*): split-K partial tiles,
+ * column-reduction partials and their ticket counters.  The caller allocates bruno_workspace_bytes() bytes of device
+ * memory, ZERO-FILLS them once (the kernels leave the tickets at zero), and binds them to the stream it launches on.
+ * One workspace per stream: two streams that run GEMMs concurrently need two.  Launches on a stream without a bound
+ * workspace run un-split (same results up to summation order, slower).  Unbind before freeing the memory. */
+size_t bruno_workspace_bytes(void);
+int bruno_workspace_bind(void* stream, void* workspace, size_t bytes);
+int bruno_workspace_unbind(void* stream);
 
 /* Optional CUDA-event timing of every launch of a kernel family on its own stream (off by default; bench.py turns it
  * on for a second pass over the timed region to get the live per-launch duration of the dominant kernel). */
@@ -75,12 +92,14 @@ int bruno_process_table(int kind, const float* var_vbl, const float* nu_vbl, con
  * `table` comes from bruno_process_table(kind, ..., n0, T, D).  `scratch` holds >= bruno_process_scratch_floats
  * floats (only used when D is split across blocks). */
 size_t bruno_process_scratch_floats(int B, int T, int D);
-/* Picks the forward-scan kernel for A/B measurements and the variant-equivalence test: 0 = default (persistent
- * bulk-copy ring kernel when D % 4 == 0 and all pointers are 16-byte aligned, register-staged kernel otherwise),
- * 9 = always the register-staged kernel, 10-14 = ring shapes.  Same results for every value. */
+#ifndef BRUNO_NO_DEBUG
+/* DEBUG (process-wide, not thread-safe).  Picks the forward-scan kernel for A/B measurements and the variant-equivalence
+ * test: 0 = default (persistent bulk-copy ring kernel when D % 4 == 0 and all pointers are 16-byte aligned,
+ * register-staged kernel otherwise), 9 = always the register-staged kernel, 10-14 = ring shapes.  Same results for every value. */
 void bruno_process_set_fwd_variant(int variant);
 /* Same switch for bruno_process_bwd: 0 = default (ring kernel when eligible), 9 = register-staged, 10-12 = ring shapes. */
 void bruno_process_set_bwd_variant(int variant);
+#endif
 int bruno_process_fwd(int kind, const float* z, const float* mu0, const float* table, float* s1, float* s2,
                       float* lp, float* lp_prior, float* scratch, int B, int T, int D, void* stream);
 
@@ -137,16 +156,11 @@ int bruno_channel_copy(const float* src, float* dst, long rows, int src_C, int s
  * the size of one, which the caller allocates ZERO-INITIALISED once (kernels keep the padding rows zero). */
 size_t bruno_slab_bytes(int N, int H, int W);
 size_t bruno_conv_wpack_bytes(void);
-/* debug: CTA 0 of bruno_conv3x3 records clock64() of its pipeline events into device_buffer [64 tiles][8] (NULL = off) */
+#ifndef BRUNO_NO_DEBUG
+/* DEBUG (process-wide, not thread-safe): CTA 0 of bruno_conv3x3 records clock64() of its pipeline events into
+ * device_buffer [64 tiles][16] (NULL = off) */
 int bruno_debug_conv_trace(long long* device_buffer);
-/* debug / A-B timing: which forward/dgrad kernel bruno_conv3x3 launches: 0 = dx-fused (three horizontal taps per N=192
- * MMA, shuffle epilogue), 1 = per-tap (36 MMAs of N=64 into one accumulator, plain epilogue; default), 2 = pair-fused
- * (taps (dy,0),(dy,+1) in one N=128 MMA, (dy,-1) as an N=64 MMA on the shifted view).  variant < 0 queries. */
-int bruno_debug_conv_variant(int variant);
-/* experimental: 1 = the 2R convolutions of a coupling's s/t network (and of its backward) run as ONE persistent launch
- * with per-tile inter-layer flags (conv3x3_chain_kernel) when there are at least two tiles per SM, 2 = for every shape
- * (tests), 0 (default: the chain is bit-identical but not yet faster) = one launch per layer.  on < 0 queries. */
-int bruno_debug_conv_chain(int on);
+#endif
 
 /* conv2d_wn weight normalisation (nvp:389) of L stacked 3x3 64->64 kernels V [L,3,3,64,64] (HWIO), g [L,64] into the
  * packed bf16 tensor-core operands: wfwd [L] (forward) and wbwd [L] (dgrad: transposed + flipped; may be NULL). */
@@ -267,12 +281,14 @@ int bruno_dense_coupling(const float* x, const float* s_pre, const float* t_pre,
  * ds_pre, dt_pre), ds_pre = (dy (1-b) x e^s + dld[n]) (1 - tanh^2), dt_pre = dy (1-b). */
 int bruno_dense_coupling_bwd(const float* x, const float* s_pre, const float* dy, const float* dld, float* dx, float* ds_pre,
                              float* dt_pre, int N, int D, int mask_type, void* stream);
-/* debug / A-B timing: which kernel the dense-path GEMMs (bruno_sgemm and the dense couplings) use when the operands are
- * 16-byte aligned: 0 = CUDA-core SGEMM (strict fp32 FFMA), 1 = tcgen05 3xTF32 split (fp32-accurate, default).
- * variant < 0 queries. */
+#ifndef BRUNO_NO_DEBUG
+/* DEBUG (process-wide, not thread-safe) / A-B timing: which kernel the dense-path GEMMs (bruno_sgemm and the dense couplings)
+ * use when the operands are 16-byte aligned: 0 = CUDA-core SGEMM (strict fp32 FFMA), 1 = tcgen05 3xTF32 split
+ * (fp32-accurate, default).  variant < 0 queries. */
 int bruno_debug_gemm_variant(int variant);
-/* debug: CTA (0,0,0) of the tcgen05 GEMM records clock64() of its pipeline events into device_buffer [64][8] (NULL = off) */
+/* DEBUG: CTA (0,0,0) of the tcgen05 GEMM records clock64() of its pipeline events into device_buffer [64][8] (NULL = off) */
 int bruno_debug_gemm_trace(long long* device_buffer);
+#endif
 
 /* C[M,N] (+)= act(op(A) op(B) * col_scale + bias), row-major fp32 (tf.matmul at nvp:418, tf.layers.dense :262,:268);
  * act: 0 none, 1 ELU, 2 leaky_relu(0.2), 3 tanh */

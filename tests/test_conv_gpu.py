@@ -41,20 +41,8 @@ def _setup(N, H, W, seed):
     return V, gain, bias, x, a1, a2, wf, wbw
 
 
-@pytest.fixture
-def conv_variant(request):
-    """Selects the forward/dgrad kernel (0 dx-fused, 1 per-tap = default, 2 pair-fused) for one test, then restores it."""
-    from bruno_b200 import _lib
-    lib = _lib.load()
-    prev = lib.bruno_debug_conv_variant(-1)
-    assert lib.bruno_debug_conv_variant(request.param) == 0
-    yield request.param
-    lib.bruno_debug_conv_variant(prev)
-
-
-@pytest.mark.parametrize('conv_variant', [0, 1, 2], indirect=True)
 @pytest.mark.parametrize('N,H,W', [(3, 28, 28), (5, 14, 14), (2, 32, 32), (1, 16, 16), (40, 14, 14)])
-def test_conv3x3_all_epilogues(N, H, W, conv_variant):
+def test_conv3x3_all_epilogues(N, H, W):
     from bruno_b200 import _lib, slab
     V, gain, bias, x, a1, a2, wf, wbw = _setup(N, H, W, seed=N * H)
     Wt = bf(wn(V[0].float().double(), gain[0].float().double()))   # the kernel rounds the normalised weights to bf16
@@ -145,41 +133,8 @@ def test_wn_backward():
     assert torch.allclose(dg.double().cpu(), gain.grad, rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize('N,H,W,C', [(3, 28, 28, 1), (40, 14, 14, 4), (1, 16, 16, 2), (130, 14, 14, 4), (500, 14, 14, 2)])
-def test_layer_chain_is_bit_identical_to_per_layer_launches(N, H, W, C):
-    """The 2R convolutions of a coupling as ONE persistent launch (per-tile inter-layer flags) == 2R launches: forward
-    output, log-det and (backward) the input gradient, bit for bit; both the 3-slab inference ring and the saved slabs."""
-    from bruno_b200 import _lib, nn_extra_nvp
-    lib = _lib.load()
-    torch.manual_seed(N + H)
-    layer = nn_extra_nvp.CouplingLayerConv('checkerboard0' if C == 1 else 'channel1', name='chain_test')
-    x = torch.randn(N, H, W, C, device='cuda')
-    ld = torch.zeros(N, device='cuda')
-    with torch.no_grad():
-        layer.forward_and_jacobian(x[:1], None, ld[:1])              # creates the variables
-        for p in (layer.Ks, layer.Kt):
-            p.normal_(0, 0.05)
-    res = {}
-    try:
-        for chain in (2, 0):
-            assert lib.bruno_debug_conv_chain(chain) == 0
-            with torch.no_grad():
-                y_inf, _, ld_inf = layer.forward_and_jacobian(x, None, ld)
-            xg = x.clone().requires_grad_(True)
-            y, _, l2 = layer.forward_and_jacobian(xg, None, ld)
-            (y.square().sum() + l2.sum()).backward()
-            res[chain] = (y_inf.clone(), ld_inf.clone(), y.detach().clone(), xg.grad.clone())
-            for p in layer.parameters():
-                p.grad = None
-    finally:
-        lib.bruno_debug_conv_chain(1)
-    for a, b in zip(res[2], res[0]):
-        assert torch.equal(a, b)
-
-
-@pytest.mark.parametrize('conv_variant', [1, 0, 2], indirect=True)
 @pytest.mark.parametrize('N,H,W', [(640, 28, 28), (640, 14, 14), (320, 32, 32)])
-def test_conv3x3_all_epilogues_at_benchmark_shapes(N, H, W, conv_variant):
+def test_conv3x3_all_epilogues_at_benchmark_shapes(N, H, W):
     """The shapes bench.py runs (bn2_omniglot_tp B=32 x T=20 -> 640 images at 28x28 and 14x14; an2_cifar B=16 x T=20 at
     32x32): ~4200 / ~1100 / ~2700 tiles = 7..28 tiles per persistent CTA, so the slab-ring wrap-around, the four rotating
     TMEM accumulators, the lcm-unrolled stage/accumulator loop and the two alternating epilogue groups are all checked

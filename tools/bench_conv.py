@@ -1,6 +1,7 @@
-"""A/B timing of the two forward/dgrad conv kernels (bruno_debug_conv_variant) on the bn2_omniglot_tp layer shape."""
+"""Per-mode timing of the forward/dgrad conv kernel on one layer shape (default: the bn2_omniglot_tp 28x28 layer)."""
 import sys, torch
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bruno_b200 import _lib, slab
 N, H, W = 640, 28, 28
 if len(sys.argv) > 1: N, H, W = (int(a) for a in sys.argv[1:4])
@@ -11,9 +12,7 @@ _lib.call('bruno_conv_wn_pack', V.cuda(), torch.ones(1, 64, device='cuda'), wf, 
 sl = slab.alloc_slabs(4, N, H, W, 'cuda')
 bias = torch.zeros(64, device='cuda')
 flops = 2.0 * N * H * W * 9 * 64 * 64
-lib = _lib.load()
 for variant in (1,):
-    lib.bruno_debug_conv_variant(variant)
     for mode in (0, 1, 2, 3):
         def run():
             _lib.call('bruno_conv3x3', mode, sl[0], wf[0], bias if mode in (0, 1) else None, 0, sl[2] if mode else None,
@@ -25,4 +24,4 @@ for variant in (1,):
         for _ in range(40): run()
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 40 * 1e3
-        print('variant %d mode %d: %.1f us  %.0f TFLOP/s' % (variant, mode, us, flops / us * 1e-6))
+        print('mode %d: %.1f us  %.0f TFLOP/s' % (mode, us, flops / us * 1e-6))
