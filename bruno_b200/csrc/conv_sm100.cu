@@ -111,6 +111,7 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
   TapSmem* cs = reinterpret_cast<TapSmem*>(stage2 + ((mode_has_aux2(MODE) && !TAP_AUX2_DIRECT) ? 2 * TILE_BYTES : 0));
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   constexpr bool HAS_BIAS = MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR;
+  if (threadIdx.x == 0) trace_at(trace_buf, 0, 8);                       // kernel entry
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TAP_MAX_STAGES; ++s) {
@@ -139,6 +140,7 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
   tc_fence_after();
   const uint32_t tmem = cs->tmem_base;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) trace_at(trace_buf, 0, 9);                       // barriers + TMEM set up
 
   // tile t = data rows [128 t, 128 t + 128) = buffer rows from Rf = HALO + 128 t (a multiple of 8); the slab load starts
   // at LS = floor8(Rf - P - 1) and covers every tap's view.
@@ -147,6 +149,7 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
       mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
       bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);
       asm volatile("griddepcontrol.wait;" ::: "memory");
+      trace_at(trace_buf, 0, 10);                                        // previous grid complete
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % nstage;
@@ -167,6 +170,7 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
     constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
     constexpr int U = (NS == 3) ? 12 : 4;
     mbar_wait(&cs->wbar, 0);
+    if (lane == 0) trace_at(trace_buf, 0, 11);                           // weights landed
     const uint64_t bdesc0 = umma_desc_sw128(smem_u32(wsm), 16, 1024);
     uint64_t adesc[NS];
 #pragma unroll
@@ -344,11 +348,14 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
         if (!live) break;
         prev_tile = tile;
       }
+      // (waiting only for the staging-buffer READS here, cp.async.bulk.wait_group.read, was measured: no change -- the
+      // dependent grid's griddepcontrol.wait waits for the writes anyway)
       bulk_wait_all<0>();
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_at(trace_buf, 0, 12);                      // every role done (stores landed)
   if (warp == 0) {
     __syncwarp();
     tmem_dealloc(tmem, 64 * TAP_ACC);
