@@ -114,7 +114,7 @@ def cpu_reference_line(args, steps, warmup, as_reference_arm):
             'cpu_baseline': cb, 'e2e': {'value': val, 'unit': 'seqs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
 
 
-def conv_sequence_graph_ms(cfg, dev, reps=10):
+def conv_sequence_graph_ms(cfg, dev, reps=10, direction=None, height=None):
     """GPU time of the 3x3 conv launches of ONE training step in the regime the timed region runs them in: the same
     kernels, modes, shapes and data dependencies (per coupling: 2R forward launches as a dependent chain, then 2R dgrad
     launches with their saved-activation / addend tiles), captured into one CUDA graph and replayed; CUDA events on the
@@ -132,11 +132,13 @@ def conv_sequence_graph_ms(cfg, dev, reps=10):
         wf = torch.empty(2 * R, wb, dtype=torch.uint8, device=dev)
         wbw = torch.empty(2 * R, wb, dtype=torch.uint8, device=dev)
         _lib.call('bruno_conv_wn_pack', layer.Vr.detach(), layer.gr.detach(), wf, wbw, 2 * R)
+        if height is not None and H != height:                   # tools/bench_conv_step.py: one resolution at a time
+            continue
         plan.append((N, H, W, R, sl[1], wf, wbw, layer.br.detach(), slab.alloc_slabs(3, N, H, W, dev)))
 
     def run():
         n = 0
-        for N, H, W, R, saved, wf, wbw, br, tmp in plan:          # forward: h -> c2 -> c3 (+ skip) -> h', a dependent chain
+        for N, H, W, R, saved, wf, wbw, br, tmp in (plan if direction != 'bwd' else []):   # forward: h -> c2 -> c3 (+ skip) -> h'
             hi = 0
             for r in range(R):
                 ui, ni = (hi + 1) % 3, (hi + 2) % 3
@@ -144,7 +146,7 @@ def conv_sequence_graph_ms(cfg, dev, reps=10):
                 _lib.call('bruno_conv3x3', 1, tmp[ui], wf[2 * r + 1], br[2 * r + 1].contiguous(), 0, tmp[hi], None, tmp[ni], N, H, W)
                 hi = ni
                 n += 2
-        for N, H, W, R, saved, wf, wbw, br, tmp in reversed(plan):  # backward: dgrad chain g3 -> g2 -> g1 per block
+        for N, H, W, R, saved, wf, wbw, br, tmp in (reversed(plan) if direction != 'fwd' else []):  # backward: dgrad chain per block
             for r in range(R - 1, -1, -1):
                 # g2 = dgrad_c3(g3) * ELU'(u_r);  g3' = (dgrad_c2(g2) + g3) * ELU'(h_r): saved activations as aux tiles
                 g3, g2, g1 = (0, 1, 2) if r % 2 == 0 else (2, 1, 0)

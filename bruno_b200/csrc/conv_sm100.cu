@@ -21,6 +21,11 @@ namespace bruno {
 
 constexpr int W_TAP_BYTES = 64 * 128;        // one tap: 64 rows (N) x 64 bf16 (K)
 constexpr int W_BYTES = 9 * W_TAP_BYTES;     // 73728
+// Packed operand order: tap (dy, dx) = (tap / 3 - 1, tap % 3 - 1) lives in 8 KB block (dx + 1) * 3 + (1 - dy), i.e. the
+// three vertical taps of one horizontal offset are 192 consecutive operand rows ordered dy = +1, 0, -1: the line-tile
+// kernel multiplies one input line by all three in ONE N = 192 instruction (output lines y-1, y, y+1 = ascending
+// accumulator slots).
+__host__ __device__ constexpr int wpack_block(int tap) { return (tap % 3) * 3 + (2 - tap / 3); }
 constexpr int CONV_THREADS = 192;
 
 enum ConvMode { MODE_ELU = 0, MODE_RES_ELU = 1, MODE_MUL = 2, MODE_ADD_MUL = 3, MODE_LINEAR = 4 };
@@ -51,7 +56,14 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // The buffer pointer is a kernel parameter (a uniform compare, not a global load on the issue path).
 static long long* g_conv_trace_host = nullptr;
 __device__ __forceinline__ void trace_at(long long* buf, int it, int slot) {
-  if (buf != nullptr && blockIdx.x == 0 && it < 64) buf[it * 16 + slot] = clock64();
+  if (buf != nullptr && blockIdx.x == 0 && it < 64) {
+    buf[it * 16 + slot] = clock64();
+    if (slot == 8 || slot == 12) {      // kernel entry / end also in ns: (cycles / ns) = the SM clock the launch really ran at
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      buf[it * 16 + (slot == 8 ? 13 : 14)] = static_cast<long long>(ns);
+    }
+  }
 }
 
 constexpr int FWD_EPI_WARPS = 16;            // 4 per TMEM lane quarter: each handles 32 rows x 16 channels
@@ -211,7 +223,7 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 umma_bf16(tmem + a * 64, adesc[s] + (a_off + 2u * k),
-                          bdesc0 + static_cast<uint32_t>((tap * W_TAP_BYTES + k * 32) >> 4), idesc, (tap | k) != 0);
+                          bdesc0 + static_cast<uint32_t>((wpack_block(tap) * W_TAP_BYTES + k * 32) >> 4), idesc, (tap | k) != 0);
               }
             }
             umma_commit(&cs->empty[s]);
@@ -253,7 +265,7 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
       }
       const int yy = static_cast<int>((static_cast<float>(q_img) + 0.5f) * inv_p);
       const int xx = q_img - yy * g.P;
-      const bool valid = data_row < g.data_rows && yy >= 1 && xx >= 1;
+      const bool valid = data_row < g.data_rows && yy >= 1 && xx >= 1 && xx <= g.W;
       mbar_wait(&cs->tfull[a], (it / TAP_ACC) & 1);
       tc_fence_after();
       if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 3);
@@ -359,6 +371,332 @@ conv3x3_tap_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ w
   if (warp == 0) {
     __syncwarp();
     tmem_dealloc(tmem, 64 * TAP_ACC);
+  }
+}
+
+// ---- line-tile implicit GEMM (default) ----------------------------------------------------------------------------
+// The per-tap kernel above is bound by the shared-memory port: every M128 x N64 x K16 instruction re-reads 4 KB of A and
+// 2 KB of B for 32 cycles of tensor work, and N cannot grow because Cout = 64 -- unless several TAPS share one A view.
+// Taps that share a view produce outputs for DIFFERENT positions, which the earlier fused variants paid for with warp
+// shuffles in the epilogue.  Here the shift is absorbed by the tile geometry instead:
+//   * an MMA tile is ONE IMAGE LINE of G = 128 / P consecutive images (P = slab row pitch, a multiple of 8: G bulk copies
+//     of P rows each land at rows i * P of the stage, swizzle phase preserved), so "one line down" is "the next tile, same
+//     TMEM lanes";
+//   * input line y times the 192-row operand [W(dy=+1, dx); W(dy=0, dx); W(dy=-1, dx)] is ONE N = 192 instruction whose
+//     three 64-column blocks are the contributions to output lines y-1, y, y+1;
+//   * output lines own consecutive 64-column TMEM slots (ring of 8), so those three blocks land in three consecutive
+//     slots: each slot accumulates its line from the three input lines around it, in the order dy = -1, 0, +1, dx, k --
+//     the SAME summation order as the per-tap kernel (the two kernels agree bit for bit), and the epilogue stays a plain
+//     row-wise map.
+// 12 instructions of N = 192 (96 tensor cycles, 10 KB of operands = 80 port cycles each) replace 36 of N = 64 (32 tensor
+// cycles, 6 KB = 48 port cycles): the MMAs of a tile are tensor-bound, no slab halo is loaded (a line needs only its
+// left / right neighbour rows = the zero padding columns), and zero padding lines cost no MMA at all.
+// A CTA walks a contiguous range of output lines; where its range starts / ends inside an image group it also multiplies
+// the neighbouring input line by the one block it needs (N = 64).  The first instruction of an input line is split where
+// a slot sees its first contribution (overwrite) next to slots that accumulate, and where the slot ring wraps.
+constexpr int LT_SLOTS = 8;                                       // 64-column accumulators = all 512 TMEM columns
+constexpr int LT_GUARD = 8;                                       // zero rows before / after the 128 tile rows of a stage
+constexpr int LT_STAGE_BYTES = (TILE_M + 2 * LT_GUARD) * SLAB_ROW_BYTES;   // 18 KB
+constexpr int LT_MAX_STAGES = 4;
+
+struct LineSmem {
+  uint64_t full[LT_MAX_STAGES], empty[LT_MAX_STAGES], tfull[LT_SLOTS], tempty[LT_SLOTS], wbar;
+  uint64_t auxfull[2], outready[2];
+  uint32_t tmem_base;
+  alignas(16) float bias[64];
+};
+
+// This CTA's share [t, t1) of the output line tiles (linear index = image group * H + data line - 1), walked segment by
+// segment; a segment = consecutive output lines yo0..yo1 (1-based data lines) of ONE image group j.  Its input lines are
+// yi0()..yi1(): one more on either side unless that side is the zero padding line.
+struct LineWalk {
+  int H, t, t1, j, yo0, yo1;
+  __device__ LineWalk(int H_, int t0_, int t1_) : H(H_), t(t0_), t1(t1_), j(0), yo0(0), yo1(0) {}
+  __device__ bool next() {
+    if (t >= t1) return false;
+    j = t / H;
+    yo0 = t - j * H + 1;
+    const int n = min(H - yo0 + 1, t1 - t);
+    yo1 = yo0 + n - 1;
+    t += n;
+    return true;
+  }
+  __device__ int yi0() const { return max(1, yo0 - 1); }
+  __device__ int yi1() const { return min(H, yo1 + 1); }
+};
+
+template <int MODE, int NS>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
+                    const uint8_t* __restrict__ aux1, const uint8_t* __restrict__ aux2, uint8_t* __restrict__ out,
+                    SlabGeom g, int G, int n_lines, int bias_img_stride, long long* trace_buf) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* wsm = smem;
+  uint8_t* slabs = smem + W_BYTES;                                     // [NS][guard | 128 tile rows | guard]
+  uint8_t* stage1 = slabs + NS * LT_STAGE_BYTES;                       // [2][TILE_BYTES] aux1 in / output out (in place)
+  uint8_t* stage2 = stage1 + 2 * TILE_BYTES;                           // [2][TILE_BYTES] aux2 (MODE_ADD_MUL only)
+  LineSmem* cs = reinterpret_cast<LineSmem*>(stage2 + (mode_has_aux2(MODE) ? 2 * TILE_BYTES : 0));
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
+  constexpr bool HAS_BIAS = MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR;
+  if (threadIdx.x == 0) trace_at(trace_buf, 0, 8);                       // kernel entry
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LT_MAX_STAGES; ++s) {
+      mbar_init(&cs->full[s], 1);
+      mbar_init(&cs->empty[s], 1);
+    }
+    for (int a = 0; a < LT_SLOTS; ++a) {
+      mbar_init(&cs->tfull[a], 1);
+      mbar_init(&cs->tempty[a], FWD_EPI_WARPS / 2);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&cs->auxfull[a], 1);
+      mbar_init(&cs->outready[a], FWD_EPI_WARPS * 16);
+    }
+    mbar_init(&cs->wbar, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) cs->bias[threadIdx.x - 64] = HAS_BIAS ? bias[threadIdx.x - 64] : 0.f;
+  // rows of a stage that no copy ever writes stay zero: the two guards and the rows past the last image segment
+  {
+    const int used = G * g.P;                                            // tile rows the G segments cover (<= 128)
+    const int zrows = 2 * LT_GUARD + (TILE_M - used);
+    for (int i = threadIdx.x; i < NS * zrows * 8; i += blockDim.x) {
+      const int s = i / (zrows * 8), r = (i / 8) % zrows, c = i & 7;
+      const int row = r < LT_GUARD ? r : LT_GUARD + used + (r - LT_GUARD);
+      reinterpret_cast<uint4*>(slabs + s * LT_STAGE_BYTES)[row * 8 + c] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(&cs->tmem_base, 64 * LT_SLOTS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = cs->tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) trace_at(trace_buf, 0, 9);                       // barriers + TMEM set up
+
+  const int t0 = static_cast<int>(static_cast<long long>(blockIdx.x) * n_lines / gridDim.x);
+  const int t1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * n_lines / gridDim.x);
+  const uint32_t seg_bytes = static_cast<uint32_t>(g.P) * SLAB_ROW_BYTES;
+  // byte offset of line `line` (0 = the zero line above the image) of image n in a slab
+  auto line_off = [&](int n, int line) {
+    return (static_cast<size_t>(g.HALO) + static_cast<size_t>(n) * g.IMG + static_cast<size_t>(line) * g.P) * SLAB_ROW_BYTES;
+  };
+
+  if (warp == 0) {
+    // ===== producer: one input line of G images per stage = G bulk copies of P rows =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
+      bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      trace_at(trace_buf, 0, 10);                                        // previous grid complete
+      LineWalk w(g.H, t0, t1);
+      int ii = 0;
+      while (w.next()) {
+        for (int yi = w.yi0(); yi <= w.yi1(); ++yi, ++ii) {
+          const int s = ii % NS;
+          mbar_wait(&cs->empty[s], ((ii / NS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&cs->full[s], static_cast<uint32_t>(G) * seg_bytes);
+          trace_at(trace_buf, ii, 0);
+          // a segment past the last image reads the slab's leading guard rows (zeros): its rows are the right-hand
+          // neighbours of the last real image's line
+          for (int i = 0; i < G; ++i) {
+            const int n = w.j * G + i;
+            bulk_g2s(slabs + s * LT_STAGE_BYTES + (LT_GUARD + i * g.P) * SLAB_ROW_BYTES,
+                     n < g.N ? in + line_off(n, yi) : in, seg_bytes, &cs->full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one elected lane =====
+    constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 0, 0), idesc128 = umma_idesc_bf16(128, 128, 0, 0),
+                       idesc192 = umma_idesc_bf16(128, 192, 0, 0);
+    mbar_wait(&cs->wbar, 0);
+    if (lane == 0) trace_at(trace_buf, 0, 11);                           // weights landed
+    const uint64_t bdesc0 = umma_desc_sw128(smem_u32(wsm), 16, 1024);
+    const uint64_t adesc0 = umma_desc_sw128(smem_u32(slabs + LT_GUARD * SLAB_ROW_BYTES), 16, 1024);
+    if (elect_one()) {
+      LineWalk w(g.H, t0, t1);
+      int ii = 0, it_seg = 0;
+      while (w.next()) {
+        for (int yi = w.yi0(); yi <= w.yi1(); ++yi, ++ii) {
+          const int s = ii % NS;
+          // block b of the 192-row operand = output line yi - 1 + b; valid if that line is in this segment
+          const int b_lo = yi - 1 >= w.yo0 ? 0 : (yi >= w.yo0 ? 1 : 2);
+          const int b_hi = yi + 1 <= w.yo1 ? 2 : (yi <= w.yo1 ? 1 : 0);
+          const int bf = yi == 1 ? 1 : 2;                                // blocks >= bf see their FIRST contribution here
+          const int it0 = it_seg + (yi - 1 - w.yo0);                     // output-tile index (within the CTA) of block 0
+          mbar_wait(&cs->full[s], (ii / NS) & 1);
+          for (int b = max(bf, b_lo); b <= b_hi; ++b)                    // a fresh slot: its previous line has been drained
+            mbar_wait(&cs->tempty[(it0 + b) & 7], (((it0 + b) >> 3) & 1) ^ 1);
+          tc_fence_after();
+          trace_at(trace_buf, ii, 1);
+          const uint64_t adesc = adesc0 + static_cast<uint32_t>((s * LT_STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int dxi = 0; dxi < 3; ++dxi) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const bool first = (dxi | k) == 0;
+              // A view: the line shifted by dx = dxi - 1 rows (8 descriptor units), K step = 32 bytes (2 units)
+              const uint64_t a = adesc + static_cast<uint64_t>(static_cast<int64_t>((dxi - 1) * 8 + 2 * k));
+              const uint64_t bk = bdesc0 + static_cast<uint32_t>((dxi * 3 * W_TAP_BYTES + k * 32) >> 4);
+              int b = b_lo;
+              while (b <= b_hi) {
+                int e = b;                                               // extend the run [b, e]
+                while (e < b_hi && ((it0 + e) & 7) != 7 && !(first && e + 1 == bf)) ++e;
+                const int nb = e - b + 1;
+                const uint32_t idesc = nb == 3 ? idesc192 : (nb == 2 ? idesc128 : idesc64);
+                umma_bf16(tmem + static_cast<uint32_t>(((it0 + b) & 7) * 64), a, bk + static_cast<uint32_t>(b * (W_TAP_BYTES >> 4)),
+                          idesc, first ? (b < bf ? 1u : 0u) : 1u);
+                b = e + 1;
+              }
+            }
+          }
+          umma_commit(&cs->empty[s]);
+          if (b_lo == 0) umma_commit(&cs->tfull[it0 & 7]);               // line yi - 1 has all three contributions
+          if (yi == g.H && b_lo <= 1 && b_hi >= 1) umma_commit(&cs->tfull[(it0 + 1) & 7]);   // last line of the image
+          trace_at(trace_buf, ii, 2);
+        }
+        it_seg += w.yo1 - w.yo0 + 1;
+      }
+    }
+    __syncwarp();
+    // no asynchronous mbarrier arrive may still be in flight when the CTA exits: the last commit is a tfull that an
+    // epilogue warp waits for before the final __syncthreads, and commits complete in order
+  } else if (warp < 2 + FWD_EPI_WARPS) {
+    // ===== epilogue: two groups of 8 warps alternate output tiles (group = staging buffer) =====
+    const int grp = (warp - 2) >> 3;
+    const int q = warp & 3;
+    const int half = ((warp - 2) >> 2) & 1;
+    const int row = q * 32 + lane;                                       // tile row = TMEM lane
+    const int R7 = lane & 7;                                             // P and the segment origins are multiples of 8
+    const int img_i = row / g.P, x1 = row - img_i * g.P;                 // image within the group, column + 1
+    const bool valid_x = img_i < G && x1 >= 1 && x1 <= g.W;
+    const uint32_t st1 = smem_u32(stage1 + grp * TILE_BYTES + row * SLAB_ROW_BYTES);
+    const uint32_t st2 = smem_u32(stage2 + grp * TILE_BYTES + row * SLAB_ROW_BYTES);
+    LineWalk w(g.H, t0, t1);
+    int it = 0;
+    while (w.next()) {
+      const int n_img = w.j * G + img_i;
+      const bool valid = valid_x && n_img < g.N;
+      for (int yo = w.yo0; yo <= w.yo1; ++yo, ++it) {
+        if ((it & 1) != grp) continue;
+        const int a = it & 7;
+        mbar_wait(&cs->tfull[a], (it >> 3) & 1);
+        tc_fence_after();
+        if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 3);
+        const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 64 + half * 32;
+        uint32_t acc[4][8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld8(tbase + c * 8, acc[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cs->tempty[a]);
+        mbar_wait(&cs->auxfull[grp], (it >> 1) & 1);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = half * 4 + jj;
+          const int pos = (j ^ R7) << 4;
+          float o[8], bj[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(acc[jj][e]);
+          if (HAS_BIAS) {
+            const float* bsrc = bias_img_stride ? bias + static_cast<size_t>(valid ? n_img : 0) * bias_img_stride + j * 8
+                                                : &cs->bias[j * 8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bsrc);
+            const float4 b1 = *reinterpret_cast<const float4*>(bsrc + 4);
+            bj[0] = b0.x; bj[1] = b0.y; bj[2] = b0.z; bj[3] = b0.w; bj[4] = b1.x; bj[5] = b1.y; bj[6] = b1.z; bj[7] = b1.w;
+          }
+          if (MODE == MODE_ELU || MODE == MODE_LINEAR) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float t = o[e] + bj[e];
+              o[e] = MODE == MODE_ELU ? elu_fast(t) : t;
+            }
+          } else if (MODE == MODE_RES_ELU) {
+            float sk[8];
+            unpack8(lds_u4(st1 + pos), sk);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = elu_fast(o[e] + bj[e] + sk[e]);
+          } else if (MODE == MODE_MUL) {
+            float sk[8];
+            unpack8(lds_u4(st1 + pos), sk);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = o[e] * elu_grad_from_out(sk[e]);
+          } else {
+            float sk[8], t[8];
+            unpack8(lds_u4(st1 + pos), sk);
+            unpack8(lds_u4(st2 + pos), t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
+          }
+          sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
+        }
+        fence_proxy_async_smem();
+        if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 4);
+        mbar_arrive(&cs->outready[grp]);
+      }
+    }
+  } else {
+    // ===== aux prefetch / output drain: G bulk copies per tile each way =====
+    if (lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      LineWalk w(g.H, t0, t1);
+      int it = 0;
+      int prev_j = 0, prev_line = -1;                                    // image group / line of the previous output tile
+      bool more = w.next();
+      int yo = more ? w.yo0 : 0;
+      for (;; ++it) {
+        if (more) {
+          const int b = it & 1;
+          const int geff = min(G, g.N - w.j * G);
+          bulk_wait_read<0>();                // the store of tile it-2 has finished reading staging buffer b
+          if (mode_has_aux1(MODE)) {
+            mbar_arrive_expect_tx(&cs->auxfull[b], static_cast<uint32_t>(geff) * seg_bytes * (mode_has_aux2(MODE) ? 2u : 1u));
+            for (int i = 0; i < geff; ++i) {
+              const size_t off = line_off(w.j * G + i, yo);
+              bulk_g2s(stage1 + b * TILE_BYTES + i * seg_bytes, aux1 + off, seg_bytes, &cs->auxfull[b]);
+              if (mode_has_aux2(MODE)) bulk_g2s(stage2 + b * TILE_BYTES + i * seg_bytes, aux2 + off, seg_bytes, &cs->auxfull[b]);
+            }
+          } else {
+            mbar_arrive(&cs->auxfull[b]);
+          }
+        }
+        if (prev_line >= 0) {
+          const int pit = it - 1;
+          const int pb = pit & 1;
+          const int geff = min(G, g.N - prev_j * G);
+          mbar_wait(&cs->outready[pb], (pit >> 1) & 1);
+          for (int i = 0; i < geff; ++i)
+            bulk_s2g(out + line_off(prev_j * G + i, prev_line), stage1 + pb * TILE_BYTES + i * seg_bytes, seg_bytes);
+          bulk_commit();
+          trace_at(trace_buf, pit, 5);
+        }
+        if (!more) break;
+        prev_j = w.j;
+        prev_line = yo;
+        if (++yo > w.yo1) {
+          more = w.next();
+          yo = more ? w.yo0 : 0;
+        }
+      }
+      bulk_wait_all<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) trace_at(trace_buf, 0, 12);                      // every role done (stores landed)
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem, 64 * LT_SLOTS);
   }
 }
 
@@ -569,13 +907,13 @@ conv_wn_pack_kernel(const float* __restrict__ V, const float* __restrict__ gain,
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = v[(tap * 64 + (j * 8 + e)) * 64 + rowi] * scale[rowi];
-    *reinterpret_cast<uint4*>(wf + tap * W_TAP_BYTES + rowi * 128 + ((j ^ (rowi & 7)) << 4)) = pack8(f);
+    *reinterpret_cast<uint4*>(wf + wpack_block(tap) * W_TAP_BYTES + rowi * 128 + ((j ^ (rowi & 7)) << 4)) = pack8(f);
     if (wb) {
       // dgrad operand: tap' = 8 - tap, [row = ci][k = co]
       float h[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) h[e] = v[(tap * 64 + rowi) * 64 + (j * 8 + e)] * scale[j * 8 + e];
-      *reinterpret_cast<uint4*>(wb + (8 - tap) * W_TAP_BYTES + rowi * 128 + ((j ^ (rowi & 7)) << 4)) = pack8(h);
+      *reinterpret_cast<uint4*>(wb + wpack_block(8 - tap) * W_TAP_BYTES + rowi * 128 + ((j ^ (rowi & 7)) << 4)) = pack8(h);
     }
   }
 }
@@ -684,9 +1022,48 @@ static int launch_conv_tap(const void* in, const void* w, const float* bias, int
   return launch_conv_tap_ns<MODE, 2>(in, w, bias, bias_img_stride, a1, a2, out, g, smem, st);
 }
 
+static size_t line_fixed_smem(int mode) {
+  return 1024 + W_BYTES + (mode_has_aux2(mode) ? 4 : 2) * TILE_BYTES + sizeof(LineSmem) + 64;
+}
+
+template <int MODE, int NS>
+static int launch_conv_line_ns(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
+                               const void* a2, void* out, const SlabGeom& g, cudaStream_t st) {
+  static OncePerDevice once;
+  once.run([&] {
+    cudaFuncSetAttribute(conv3x3_line_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  const int G = TILE_M / g.P;                                   // images per line tile
+  const int n_groups = (g.N + G - 1) / G;
+  const long long n_lines = static_cast<long long>(n_groups) * g.H;
+  BRUNO_REQUIRE(n_lines < (1ll << 30), "bruno_conv3x3: too many line tiles");
+  const int grid = n_lines < num_sms() ? static_cast<int>(n_lines) : num_sms();
+  const size_t smem = line_fixed_smem(MODE) + static_cast<size_t>(NS) * LT_STAGE_BYTES;
+  ProfSpan span(BRUNO_PROF_CONV, st);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(FWD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, conv3x3_line_kernel<MODE, NS>, static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias,
+                     static_cast<const uint8_t*>(a1), static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g, G,
+                     static_cast<int>(n_lines), bias_img_stride, g_conv_trace_host);
+  return check_launch("conv3x3_line_kernel");
+}
+
+// 0 = line-tile kernel (default; needs the row pitch P <= 128), 1 = per-tap kernel (any width the slab ring fits)
+static int g_conv_variant = 0;
+
 template <int MODE>
 static int launch_conv(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
                        const void* a2, void* out, const SlabGeom& g, cudaStream_t st) {
+  if (g_conv_variant == 0 && g.P <= TILE_M)
+    return launch_conv_line_ns<MODE, LT_MAX_STAGES>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
   return launch_conv_tap<MODE>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
 }
 
@@ -706,6 +1083,11 @@ size_t bruno_conv_wpack_bytes(void) { return W_BYTES; }
 #ifndef BRUNO_NO_DEBUG
 int bruno_debug_conv_trace(long long* device_buffer) {
   g_conv_trace_host = device_buffer;
+  return BRUNO_OK;
+}
+int bruno_debug_conv_variant(int variant) {
+  BRUNO_REQUIRE(variant == 0 || variant == 1, "bruno_debug_conv_variant: 0 = line-tile kernel, 1 = per-tap kernel");
+  g_conv_variant = variant;
   return BRUNO_OK;
 }
 #endif

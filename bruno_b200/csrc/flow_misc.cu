@@ -170,7 +170,7 @@ c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
     const int n = fdiv22(data_row, g.IMG, inv_img, small), q = data_row - n * g.IMG;
     const int y1 = fdiv22(q, g.P, inv_p, small);
     const int yy = y1 - 1, xx = q - y1 * g.P - 1;
-    if (data_row < g.data_rows && yy >= 0 && xx >= 0) {
+    if (data_row < g.data_rows && yy >= 0 && xx >= 0 && xx < g.W) {
       const float* xp = x + ((static_cast<size_t>(n) * g.H + yy) * g.W + xx) * C;
       float acc[8];
 #pragma unroll

@@ -4,9 +4,12 @@
 // (16-byte chunk j of buffer row R lives at chunk j ^ (R & 7)), so a contiguous run of rows can be brought into shared
 // memory with ONE 1-D bulk async copy and used directly as a K-major SW128 tcgen05 operand.
 //
-// Zero padding is part of the layout: images are laid out with a row pitch of P = W + 1 (one shared zero column between
-// the right edge of a line and the left edge of the next) and H + 1 lines per image (the zero line above image n is the
-// zero line below image n - 1).  Pixel (n, y, x) sits at data row  n * IMG + (y + 1) * P + (x + 1),  IMG = (H + 1) * P,
+// Zero padding is part of the layout: images are laid out with a row pitch of P = round_up(W + 1, 8) (at least one shared
+// zero column between the right edge of a line and the left edge of the next; a multiple of 8 so that every image line
+// starts at the same swizzle phase and a line can be copied to any 8-row-aligned place in shared memory -- the line-tile
+// convolution kernel gathers one line of several images into one 128-row MMA tile) and H + 1 lines per image (the zero
+// line above image n is the zero line below image n - 1).
+// Pixel (n, y, x) sits at data row  n * IMG + (y + 1) * P + (x + 1),  IMG = (H + 1) * P,
 // and its 3x3 neighbour (dy, dx) at  +dy * P + dx  -- always inside the slab, always zero where the reference's SAME
 // padding reads zero.  The 3x3 implicit GEMM therefore needs no im2col: the nine taps are nine row-shifted views of the
 // same shared-memory slab.  Buffer row = HALO + data row; HALO = round_up(P + 1, 8) guard rows at both ends stay zero.
@@ -32,7 +35,7 @@ struct SlabGeom {
 __host__ __device__ inline SlabGeom slab_geom(int N, int H, int W) {
   SlabGeom g;
   g.N = N; g.H = H; g.W = W;
-  g.P = W + 1;
+  g.P = ((W + 1 + 7) / 8) * 8;
   g.IMG = (H + 1) * g.P;
   g.HALO = ((g.P + 1 + 7) / 8) * 8;
   g.data_rows = N * g.IMG;
@@ -50,7 +53,7 @@ __host__ __device__ inline size_t slab_chunk_off(size_t R, int j) {
 __host__ __device__ inline bool slab_row_is_pixel(int data_row, const SlabGeom& g) {
   if (data_row >= g.data_rows) return false;
   const int q = data_row % g.IMG;
-  return (q / g.P) >= 1 && (q % g.P) >= 1;
+  return (q / g.P) >= 1 && (q % g.P) >= 1 && (q % g.P) <= g.W;
 }
 
 }  // namespace bruno

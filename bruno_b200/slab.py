@@ -11,7 +11,7 @@ TILE_M = 128
 class SlabGeom(object):
     def __init__(self, N, H, W):
         self.N, self.H, self.W = N, H, W
-        self.P = W + 1
+        self.P = ((W + 1 + 7) // 8) * 8
         self.IMG = (H + 1) * self.P
         self.HALO = ((self.P + 1 + 7) // 8) * 8
         self.data_rows = N * self.IMG

@@ -160,6 +160,8 @@ size_t bruno_conv_wpack_bytes(void);
 /* DEBUG (process-wide, not thread-safe): CTA 0 of bruno_conv3x3 records clock64() of its pipeline events into
  * device_buffer [64 tiles][16] (NULL = off) */
 int bruno_debug_conv_trace(long long* device_buffer);
+/* DEBUG (process-wide): 0 = line-tile conv kernel (default), 1 = per-tap kernel (the fallback for row pitch > 128). */
+int bruno_debug_conv_variant(int variant);
 #endif
 
 /* conv2d_wn weight normalisation (nvp:389) of L stacked 3x3 64->64 kernels V [L,3,3,64,64] (HWIO), g [L,64] into the

@@ -41,7 +41,8 @@ def _setup(N, H, W, seed):
     return V, gain, bias, x, a1, a2, wf, wbw
 
 
-@pytest.mark.parametrize('N,H,W', [(3, 28, 28), (5, 14, 14), (2, 32, 32), (1, 16, 16), (40, 14, 14)])
+@pytest.mark.parametrize('N,H,W', [(3, 28, 28), (5, 14, 14), (2, 32, 32), (1, 16, 16), (40, 14, 14), (1, 15, 15), (11, 7, 7),
+                                   (9, 1, 5), (2, 3, 39), (13, 31, 31), (3, 5, 127)])
 def test_conv3x3_all_epilogues(N, H, W):
     from bruno_b200 import _lib, slab
     V, gain, bias, x, a1, a2, wf, wbw = _setup(N, H, W, seed=N * H)
@@ -190,3 +191,28 @@ def test_conv3x3_wgrad_at_benchmark_shape():
         assert (dW.double() - w.grad).abs().max().item() <= 2e-4 * scale + 1e-4
         refb = gq.sum(dim=(0, 1, 2))
         assert (db.double() - refb).abs().max().item() <= 2e-4 * refb.abs().max().item() + 1e-4
+
+
+@pytest.mark.parametrize('N,H,W', [(3, 28, 28), (41, 14, 14), (2, 32, 32), (1, 15, 15), (300, 14, 14), (150, 28, 28), (13, 31, 31)])
+def test_line_tile_kernel_is_bit_identical_to_per_tap_kernel(N, H, W):
+    """The default line-tile kernel (one image line of several images per MMA tile, the three vertical taps as one N = 192
+    instruction into three consecutive TMEM accumulator slots) sums every output in the same order as the per-tap kernel
+    (the fallback for very wide images): the two must agree bit for bit, in every epilogue mode, including partial image
+    groups, widths with and without a spare padding column, and CTA ranges that start / end inside an image."""
+    from bruno_b200 import _lib, slab
+    V, gain, bias, x, a1, a2, wf, wbw = _setup(N, H, W, seed=3 * N + H)
+    xs, a1s, a2s = [slab.nhwc_to_slab(t.float().cuda()) for t in (x, a1, a2)]
+    b32 = bias.float().cuda()
+    out = slab.alloc_slabs(2, N, H, W, 'cuda')
+    lib = _lib.load()
+    try:
+        for mode in range(5):
+            w = wf[0] if mode in (0, 1, 4) else wbw[0]
+            for variant in (0, 1):
+                assert lib.bruno_debug_conv_variant(variant) == 0
+                out[variant].zero_()
+                _lib.call('bruno_conv3x3', mode, xs, w, b32, 0, a1s, a2s, out[variant], N, H, W)
+            torch.cuda.synchronize()
+            assert torch.equal(out[0], out[1]), (mode, int((out[0] != out[1]).sum()))
+    finally:
+        lib.bruno_debug_conv_variant(0)
