@@ -11,7 +11,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), 'include', 'bruno_sm100.h')
-LIB_PATH = os.path.join(HERE, 'lib', 'libbruno_sm100.so')
+LIB_PATH = os.environ.get('BRUNO_SM100_LIB') or os.path.join(HERE, 'lib', 'libbruno_sm100.so')   # override: A/B builds of the same ABI
 
 TP, GP = 0, 1
 

@@ -399,12 +399,25 @@ constexpr int LT_GUARD = 8;                                       // zero rows b
 constexpr int LT_STAGE_BYTES = (TILE_M + 2 * LT_GUARD) * SLAB_ROW_BYTES;   // 18 KB
 constexpr int LT_MAX_STAGES = 4;
 
+constexpr int LT_THREADS = 32 * (2 + FWD_EPI_WARPS + 3);   // producer, MMA issuer, epilogue warps, aux loader, output drain, gatekeeper
+constexpr int LT_GATES = 4;
+constexpr int LT_MAX_NB = 4;                                // ring of "tile may be issued" barriers (gatekeeper -> issuer)
+
 struct LineSmem {
   uint64_t full[LT_MAX_STAGES], empty[LT_MAX_STAGES], tfull[LT_SLOTS], tempty[LT_SLOTS], wbar;
-  uint64_t auxfull[2], outready[2];
+  uint64_t auxfull[LT_MAX_NB], outready[LT_MAX_NB], outfree[LT_MAX_NB], go[LT_GATES];
   uint32_t tmem_base;
   alignas(16) float bias[64];
 };
+// Staging ring: NB buffers of one tile per stream (aux1 / output IN PLACE, aux2).  An aux tile is requested as soon as the
+// store of the tile NB back has read the buffer, i.e. NB - 1 tile periods before its epilogue needs it: with the HBM
+// latency at 2-3 tile periods, NB = 2 (one buffer per epilogue group) exposes it in every epilogue.
+// (MODE_ADD_MUL: three input stages + two staging buffers per stream.  Three of each also fits in shared memory, but that
+// configuration -- and only that one -- fails on back-to-back 640 x 28 x 28 launches (launch failure / hang) for a reason
+// not yet understood; the protocol is deadlock-free on paper and every other combination runs the chains bit-exactly.)
+__host__ __device__ constexpr int line_nb(int mode) { return mode_has_aux2(mode) ? 2 : (mode_has_aux1(mode) ? 4 : 2); }
+__host__ __device__ constexpr int line_ns(int mode) { return mode_has_aux2(mode) ? 3 : LT_MAX_STAGES; }
+__host__ __device__ constexpr int line_stage_tiles(int mode) { return line_nb(mode) * (mode_has_aux2(mode) ? 2 : 1); }
 
 // This CTA's share [t, t1) of the output line tiles (linear index = image group * H + data line - 1), walked segment by
 // segment; a segment = consecutive output lines yo0..yo1 (1-based data lines) of ONE image group j.  Its input lines are
@@ -426,17 +439,18 @@ struct LineWalk {
 };
 
 template <int MODE, int NS>
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+__global__ void __launch_bounds__(LT_THREADS, 1)
 conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
                     const uint8_t* __restrict__ aux1, const uint8_t* __restrict__ aux2, uint8_t* __restrict__ out,
-                    SlabGeom g, int G, int n_lines, int bias_img_stride, long long* trace_buf) {
+                    SlabGeom g, int G, int n_lines, int bias_img_stride, long long* trace_buf, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* wsm = smem;
   uint8_t* slabs = smem + W_BYTES;                                     // [NS][guard | 128 tile rows | guard]
-  uint8_t* stage1 = slabs + NS * LT_STAGE_BYTES;                       // [2][TILE_BYTES] aux1 in / output out (in place)
-  uint8_t* stage2 = stage1 + 2 * TILE_BYTES;                           // [2][TILE_BYTES] aux2 (MODE_ADD_MUL only)
-  LineSmem* cs = reinterpret_cast<LineSmem*>(stage2 + (mode_has_aux2(MODE) ? 2 * TILE_BYTES : 0));
+  constexpr int NB = line_nb(MODE);
+  uint8_t* stage1 = slabs + NS * LT_STAGE_BYTES;                       // [NB][TILE_BYTES] aux1 tile in / output tile out (in place)
+  uint8_t* stage2 = stage1 + NB * TILE_BYTES;                          // [NB][TILE_BYTES] aux2 tiles (MODE_ADD_MUL only)
+  LineSmem* cs = reinterpret_cast<LineSmem*>(stage1 + line_stage_tiles(MODE) * TILE_BYTES);
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   constexpr bool HAS_BIAS = MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR;
   if (threadIdx.x == 0) trace_at(trace_buf, 0, 8);                       // kernel entry
@@ -450,25 +464,20 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
       mbar_init(&cs->tfull[a], 1);
       mbar_init(&cs->tempty[a], FWD_EPI_WARPS / 2);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < LT_MAX_NB; ++a) {
       mbar_init(&cs->auxfull[a], 1);
       mbar_init(&cs->outready[a], FWD_EPI_WARPS * 16);
+      mbar_init(&cs->outfree[a], 1);
     }
+    for (int a = 0; a < LT_GATES; ++a) mbar_init(&cs->go[a], 1);
     mbar_init(&cs->wbar, 1);
     fence_mbar_init();
   }
   if (threadIdx.x >= 64 && threadIdx.x < 128) cs->bias[threadIdx.x - 64] = HAS_BIAS ? bias[threadIdx.x - 64] : 0.f;
-  // rows of a stage that no copy ever writes stay zero: the two guards and the rows past the last image segment
-  {
-    const int used = G * g.P;                                            // tile rows the G segments cover (<= 128)
-    const int zrows = 2 * LT_GUARD + (TILE_M - used);
-    for (int i = threadIdx.x; i < NS * zrows * 8; i += blockDim.x) {
-      const int s = i / (zrows * 8), r = (i / 8) % zrows, c = i & 7;
-      const int row = r < LT_GUARD ? r : LT_GUARD + used + (r - LT_GUARD);
-      reinterpret_cast<uint4*>(slabs + s * LT_STAGE_BYTES)[row * 8 + c] = make_uint4(0, 0, 0, 0);
-    }
-    fence_proxy_async_smem();
-  }
+  // Rows of a stage that no copy ever writes stay zero for the whole kernel: the guards, the padding columns past W + 1
+  // of every image segment (only the rows a line's neighbours can read are copied) and the rows past the last segment.
+  for (int i = threadIdx.x; i < NS * (LT_STAGE_BYTES / 16); i += blockDim.x) reinterpret_cast<uint4*>(slabs)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
   if (warp == 0) {
     __syncwarp();
     tmem_alloc(&cs->tmem_base, 64 * LT_SLOTS);
@@ -484,6 +493,11 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
   const int t0 = static_cast<int>(static_cast<long long>(blockIdx.x) * n_lines / gridDim.x);
   const int t1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * n_lines / gridDim.x);
   const uint32_t seg_bytes = static_cast<uint32_t>(g.P) * SLAB_ROW_BYTES;
+  // HBM traffic: an input line needs its W pixels and one padding row on either side (rows 0 .. W + 1 of the segment);
+  // aux tiles and the output need the W pixel rows only (the padding rows of a slab are never written: they stay zero)
+  const uint32_t in_bytes = static_cast<uint32_t>(min(g.P, g.W + 2)) * SLAB_ROW_BYTES;
+  const uint32_t px_bytes = static_cast<uint32_t>(g.W) * SLAB_ROW_BYTES;
+  const size_t img_bytes = static_cast<size_t>(g.IMG) * SLAB_ROW_BYTES;
   // byte offset of line `line` (0 = the zero line above the image) of image n in a slab
   auto line_off = [&](int n, int line) {
     return (static_cast<size_t>(g.HALO) + static_cast<size_t>(n) * g.IMG + static_cast<size_t>(line) * g.P) * SLAB_ROW_BYTES;
@@ -502,69 +516,128 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
         for (int yi = w.yi0(); yi <= w.yi1(); ++yi, ++ii) {
           const int s = ii % NS;
           mbar_wait(&cs->empty[s], ((ii / NS) & 1) ^ 1);
-          mbar_arrive_expect_tx(&cs->full[s], static_cast<uint32_t>(G) * seg_bytes);
+          const int geff = min(G, g.N - w.j * G);
+          mbar_arrive_expect_tx(&cs->full[s], static_cast<uint32_t>(geff) * in_bytes + (geff < G ? seg_bytes : 0u));
           trace_at(trace_buf, ii, 0);
-          // a segment past the last image reads the slab's leading guard rows (zeros): its rows are the right-hand
-          // neighbours of the last real image's line
-          for (int i = 0; i < G; ++i) {
-            const int n = w.j * G + i;
-            bulk_g2s(slabs + s * LT_STAGE_BYTES + (LT_GUARD + i * g.P) * SLAB_ROW_BYTES,
-                     n < g.N ? in + line_off(n, yi) : in, seg_bytes, &cs->full[s]);
+          uint8_t* dst = slabs + s * LT_STAGE_BYTES + LT_GUARD * SLAB_ROW_BYTES;
+          const uint8_t* src = in + line_off(w.j * G, yi);
+          if (dbg & 2) {
+            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&cs->full[s])),
+                         "r"(static_cast<uint32_t>(geff) * in_bytes + (geff < G ? seg_bytes : 0u)) : "memory");
+          } else {
+            for (int i = 0; i < geff; ++i, dst += seg_bytes, src += img_bytes) bulk_g2s(dst, src, in_bytes, &cs->full[s]);
+            // the segment after the last image of a partial group holds that image's right-hand neighbours: zeros (the
+            // slab's leading guard rows), whatever an earlier full group left there
+            if (geff < G) bulk_g2s(dst, in, seg_bytes, &cs->full[s]);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one elected lane =====
-    constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 0, 0), idesc128 = umma_idesc_bf16(128, 128, 0, 0),
-                       idesc192 = umma_idesc_bf16(128, 192, 0, 0);
+    // ===== MMA issuer: one elected lane.  Measured (tools/umma_bench.cu): the MMAs of a tile take 1250 cycles in
+    // isolation and every instruction the issuing thread executes between them adds its full latency (branches ~8 cycles)
+    // -- the tensor pipe does not run ahead of the issuer far enough to hide them.  So the issuer does the bare minimum:
+    // ONE barrier wait per tile (the gatekeeper thread has already waited for the input line and for the accumulator
+    // slots), incremental uniform-register bookkeeping, and for the common case -- a line with both neighbours inside this
+    // CTA's segment -- straight-line code per accumulator-ring position class (no wrap / wrap after two blocks / wrap
+    // after one). =====
     mbar_wait(&cs->wbar, 0);
     if (lane == 0) trace_at(trace_buf, 0, 11);                           // weights landed
-    const uint64_t bdesc0 = umma_desc_sw128(smem_u32(wsm), 16, 1024);
-    const uint64_t adesc0 = umma_desc_sw128(smem_u32(slabs + LT_GUARD * SLAB_ROW_BYTES), 16, 1024);
     if (elect_one()) {
-      LineWalk w(g.H, t0, t1);
-      int ii = 0, it_seg = 0;
-      while (w.next()) {
-        for (int yi = w.yi0(); yi <= w.yi1(); ++yi, ++ii) {
-          const int s = ii % NS;
-          // block b of the 192-row operand = output line yi - 1 + b; valid if that line is in this segment
-          const int b_lo = yi - 1 >= w.yo0 ? 0 : (yi >= w.yo0 ? 1 : 2);
-          const int b_hi = yi + 1 <= w.yo1 ? 2 : (yi <= w.yo1 ? 1 : 0);
-          const int bf = yi == 1 ? 1 : 2;                                // blocks >= bf see their FIRST contribution here
-          const int it0 = it_seg + (yi - 1 - w.yo0);                     // output-tile index (within the CTA) of block 0
-          mbar_wait(&cs->full[s], (ii / NS) & 1);
-          for (int b = max(bf, b_lo); b <= b_hi; ++b)                    // a fresh slot: its previous line has been drained
-            mbar_wait(&cs->tempty[(it0 + b) & 7], (((it0 + b) >> 3) & 1) ^ 1);
-          tc_fence_after();
-          trace_at(trace_buf, ii, 1);
-          const uint64_t adesc = adesc0 + static_cast<uint32_t>((s * LT_STAGE_BYTES) >> 4);
+      constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 0, 0), idesc128 = umma_idesc_bf16(128, 128, 0, 0),
+                         idesc192 = umma_idesc_bf16(128, 192, 0, 0);
+      constexpr uint32_t BLK = W_TAP_BYTES >> 4;                         // one 64-row operand block in descriptor units
+      const uint64_t bdesc0 = umma_desc_sw128(smem_u32(wsm), 16, 1024);
+      const uint64_t adesc0 = umma_desc_sw128(smem_u32(slabs + LT_GUARD * SLAB_ROW_BYTES), 16, 1024);
+      const uint32_t empty0 = smem_u32(&cs->empty[0]), tfull0 = smem_u32(&cs->tfull[0]), go0 = smem_u32(&cs->go[0]);
+      auto commit_addr = [](uint32_t bar) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+      };
+      auto wait_addr = [](uint32_t bar, uint32_t parity) {
+        uint32_t ok;
+        do {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t}"
+              : "=r"(ok)
+              : "r"(bar), "r"(parity)
+              : "memory");
+        } while (!ok);
+      };
+      // steps 1..11 of a tile: (dx, k) = A view shifted by dx rows (8 descriptor units) at K offset 32 k bytes (2 units)
+      // times the operand of dx at the same K offset; run 0 = n0 blocks from block b_lo into d0, run 1 (n1 > 0: the slot
+      // ring wrapped) = the following n1 blocks into slot 0
+      auto steps = [&](uint64_t adesc, uint64_t bq, uint32_t d0, uint32_t id0, uint32_t n0, uint32_t id1, bool two) {
 #pragma unroll
-          for (int dxi = 0; dxi < 3; ++dxi) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const bool first = (dxi | k) == 0;
-              // A view: the line shifted by dx = dxi - 1 rows (8 descriptor units), K step = 32 bytes (2 units)
-              const uint64_t a = adesc + static_cast<uint64_t>(static_cast<int64_t>((dxi - 1) * 8 + 2 * k));
-              const uint64_t bk = bdesc0 + static_cast<uint32_t>((dxi * 3 * W_TAP_BYTES + k * 32) >> 4);
-              int b = b_lo;
-              while (b <= b_hi) {
-                int e = b;                                               // extend the run [b, e]
-                while (e < b_hi && ((it0 + e) & 7) != 7 && !(first && e + 1 == bf)) ++e;
-                const int nb = e - b + 1;
-                const uint32_t idesc = nb == 3 ? idesc192 : (nb == 2 ? idesc128 : idesc64);
-                umma_bf16(tmem + static_cast<uint32_t>(((it0 + b) & 7) * 64), a, bk + static_cast<uint32_t>(b * (W_TAP_BYTES >> 4)),
-                          idesc, first ? (b < bf ? 1u : 0u) : 1u);
-                b = e + 1;
-              }
-            }
-          }
-          umma_commit(&cs->empty[s]);
-          if (b_lo == 0) umma_commit(&cs->tfull[it0 & 7]);               // line yi - 1 has all three contributions
-          if (yi == g.H && b_lo <= 1 && b_hi >= 1) umma_commit(&cs->tfull[(it0 + 1) & 7]);   // last line of the image
-          trace_at(trace_buf, ii, 2);
+        for (int st = 1; st < 12; ++st) {
+          const int dxi = st >> 2, k = st & 3;
+          const uint64_t a = adesc + static_cast<uint64_t>(static_cast<int64_t>((dxi - 1) * 8 + 2 * k));
+          const uint32_t bo = static_cast<uint32_t>((dxi * 3 * W_TAP_BYTES + k * 32) >> 4);
+          umma_bf16(d0, a, bq + bo, id0, 1u);
+          if (two) umma_bf16(tmem, a, bq + (bo + n0 * BLK), id1, 1u);
         }
-        it_seg += w.yo1 - w.yo0 + 1;
+      };
+      LineWalk w(g.H, t0, t1);
+      int ii = 0, it_seg = 0, sidx = 0, tr_i = 0;
+      uint32_t a_off = 0;                                                // descriptor offset of the current stage
+      while (w.next()) {
+        const int yo0 = w.yo0, yo1 = w.yo1, yi1 = w.yi1();
+        int yi = w.yi0();
+        int it0 = it_seg + (yi - 1 - yo0);                               // output-tile index (within the CTA) of block 0
+        for (; yi <= yi1; ++yi, ++it0, ++ii) {
+          wait_addr(go0 + 8u * (ii & (LT_GATES - 1)), (ii / LT_GATES) & 1);
+          tc_fence_after();
+          trace_at(trace_buf, tr_i, 1);
+          const uint64_t adesc = adesc0 + a_off;
+          const uint64_t a1 = adesc - 8u;                                // first step: dx = -1, k = 0
+          const uint32_t slot = it0 & 7;
+          const uint32_t d0 = tmem + slot * 64;
+          if (yi > yo0 && yi < yo1 && yi > 1) {
+            // interior line: blocks 0, 1 accumulate, block 2 opens a fresh slot; all three valid; line yi - 1 completes
+            if (slot <= 5) {
+              umma_bf16(d0, a1, bdesc0, idesc128, 1u);
+              umma_bf16(d0 + 128, a1, bdesc0 + 2 * BLK, idesc64, 0u);
+              steps(adesc, bdesc0, d0, idesc192, 3, 0, false);
+            } else if (slot == 6) {
+              umma_bf16(d0, a1, bdesc0, idesc128, 1u);
+              umma_bf16(tmem, a1, bdesc0 + 2 * BLK, idesc64, 0u);
+              steps(adesc, bdesc0, d0, idesc128, 2, idesc64, true);
+            } else {
+              umma_bf16(d0, a1, bdesc0, idesc64, 1u);
+              umma_bf16(tmem, a1, bdesc0 + BLK, idesc64, 1u);
+              umma_bf16(tmem + 64, a1, bdesc0 + 2 * BLK, idesc64, 0u);
+              steps(adesc, bdesc0, d0, idesc64, 1, idesc128, true);
+            }
+            commit_addr(empty0 + 8u * sidx);
+            commit_addr(tfull0 + 8u * slot);
+          } else {
+            // edge line: block b = output line yi - 1 + b is valid if that line is in this segment
+            const int b_lo = yi - 1 >= yo0 ? 0 : (yi >= yo0 ? 1 : 2);
+            const int b_hi = yi + 1 <= yo1 ? 2 : (yi <= yo1 ? 1 : 0);
+            const int bf = yi == 1 ? 1 : 2;                              // blocks >= bf see their FIRST contribution here
+            const uint32_t slot0 = (it0 + b_lo) & 7, nbt = b_hi - b_lo + 1;
+            const uint32_t n0 = min(nbt, 8u - slot0), n1 = nbt - n0;     // blocks before / after the slot ring wraps
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+              if (b >= b_lo && b <= b_hi)
+                umma_bf16(tmem + static_cast<uint32_t>(((it0 + b) & 7) * 64), a1, bdesc0 + b * BLK, idesc64, b < bf ? 1u : 0u);
+            steps(adesc, bdesc0 + b_lo * BLK, tmem + slot0 * 64, idesc64 + (n0 - 1) * (8u << 17), n0, idesc64 + (n1 - 1) * (8u << 17),
+                  n1 != 0);
+            commit_addr(empty0 + 8u * sidx);
+            if (b_lo == 0) commit_addr(tfull0 + 8u * slot);              // line yi - 1 has all three contributions
+            if (yi == g.H && b_lo <= 1 && b_hi >= 1) commit_addr(tfull0 + 8u * ((it0 + 1) & 7));   // last line of the image
+          }
+          trace_at(trace_buf, tr_i, 2);
+          ++tr_i;
+          if (++sidx == NS) {
+            sidx = 0;
+            a_off = 0;
+          } else {
+            a_off += LT_STAGE_BYTES >> 4;
+          }
+        }
+        it_seg += yo1 - yo0 + 1;
       }
     }
     __syncwarp();
@@ -579,8 +652,8 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
     const int R7 = lane & 7;                                             // P and the segment origins are multiples of 8
     const int img_i = row / g.P, x1 = row - img_i * g.P;                 // image within the group, column + 1
     const bool valid_x = img_i < G && x1 >= 1 && x1 <= g.W;
-    const uint32_t st1 = smem_u32(stage1 + grp * TILE_BYTES + row * SLAB_ROW_BYTES);
-    const uint32_t st2 = smem_u32(stage2 + grp * TILE_BYTES + row * SLAB_ROW_BYTES);
+    const uint32_t st1_0 = smem_u32(stage1 + row * SLAB_ROW_BYTES);
+    const uint32_t st2_0 = smem_u32(stage2 + row * SLAB_ROW_BYTES);
     LineWalk w(g.H, t0, t1);
     int it = 0;
     while (w.next()) {
@@ -595,12 +668,15 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
         const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 64 + half * 32;
         uint32_t acc[4][8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld8(tbase + c * 8, acc[c]);
+        if (!(dbg & 16)) { for (int c = 0; c < 4; ++c) tmem_ld8(tbase + c * 8, acc[c]); } else { for (int c = 0; c < 4; ++c) for (int e = 0; e < 8; ++e) acc[c][e] = 0; }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&cs->tempty[a]);
-        mbar_wait(&cs->auxfull[grp], (it >> 1) & 1);
+        const int sb = it % NB;                                          // staging buffer of this tile
+        const uint32_t st1 = st1_0 + sb * TILE_BYTES, st2 = st2_0 + sb * TILE_BYTES;
+        if (mode_has_aux1(MODE)) mbar_wait(&cs->auxfull[sb], (it / NB) & 1);           // (the loader waited for the buffer)
+        else mbar_wait(&cs->outfree[sb], ((it / NB) & 1) ^ 1);           // the store of tile it - NB has read the buffer
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int j = half * 4 + jj;
@@ -638,57 +714,76 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
           }
-          sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
+          if (!(dbg & 8)) sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
         }
         fence_proxy_async_smem();
         if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 4);
-        mbar_arrive(&cs->outready[grp]);
+        mbar_arrive(&cs->outready[sb]);
       }
     }
-  } else {
-    // ===== aux prefetch / output drain: G bulk copies per tile each way =====
-    if (lane == 0) {
+  } else if (warp == 2 + FWD_EPI_WARPS) {
+    // ===== aux loader: the saved-activation / addend tiles of output tile it, up to NB - 1 tiles ahead of its epilogue =====
+    if (mode_has_aux1(MODE) && lane == 0) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
       LineWalk w(g.H, t0, t1);
       int it = 0;
-      int prev_j = 0, prev_line = -1;                                    // image group / line of the previous output tile
-      bool more = w.next();
-      int yo = more ? w.yo0 : 0;
-      for (;; ++it) {
-        if (more) {
-          const int b = it & 1;
-          const int geff = min(G, g.N - w.j * G);
-          bulk_wait_read<0>();                // the store of tile it-2 has finished reading staging buffer b
-          if (mode_has_aux1(MODE)) {
-            mbar_arrive_expect_tx(&cs->auxfull[b], static_cast<uint32_t>(geff) * seg_bytes * (mode_has_aux2(MODE) ? 2u : 1u));
-            for (int i = 0; i < geff; ++i) {
-              const size_t off = line_off(w.j * G + i, yo);
-              bulk_g2s(stage1 + b * TILE_BYTES + i * seg_bytes, aux1 + off, seg_bytes, &cs->auxfull[b]);
-              if (mode_has_aux2(MODE)) bulk_g2s(stage2 + b * TILE_BYTES + i * seg_bytes, aux2 + off, seg_bytes, &cs->auxfull[b]);
-            }
-          } else {
-            mbar_arrive(&cs->auxfull[b]);
+      while (w.next()) {
+        const int geff = min(G, g.N - w.j * G);
+        for (int yo = w.yo0; yo <= w.yo1; ++yo, ++it) {
+          const int b = it % NB;
+          if (it >= NB) mbar_wait(&cs->outfree[b], ((it / NB) - 1) & 1);   // the store of tile it - NB has read buffer b
+          mbar_arrive_expect_tx(&cs->auxfull[b], static_cast<uint32_t>(geff) * px_bytes * (mode_has_aux2(MODE) ? 2u : 1u));
+          size_t off = line_off(w.j * G, yo) + SLAB_ROW_BYTES;          // pixel rows 1 .. W of each segment
+          uint32_t so = b * TILE_BYTES + SLAB_ROW_BYTES;
+          for (int i = 0; i < geff; ++i, off += img_bytes, so += seg_bytes) {
+            bulk_g2s(stage1 + so, aux1 + off, px_bytes, &cs->auxfull[b]);
+            if (mode_has_aux2(MODE)) bulk_g2s(stage2 + so, aux2 + off, px_bytes, &cs->auxfull[b]);
           }
         }
-        if (prev_line >= 0) {
-          const int pit = it - 1;
-          const int pb = pit & 1;
-          const int geff = min(G, g.N - prev_j * G);
-          mbar_wait(&cs->outready[pb], (pit >> 1) & 1);
-          for (int i = 0; i < geff; ++i)
-            bulk_s2g(out + line_off(prev_j * G + i, prev_line), stage1 + pb * TILE_BYTES + i * seg_bytes, seg_bytes);
+      }
+    }
+  } else if (warp == 2 + FWD_EPI_WARPS + 1) {
+    // ===== output drain: G bulk stores per tile =====
+    if (lane == 0) {
+      LineWalk w(g.H, t0, t1);
+      int it = 0;
+      while (w.next()) {
+        const int geff = min(G, g.N - w.j * G);
+        for (int yo = w.yo0; yo <= w.yo1; ++yo, ++it) {
+          const int b = it % NB;
+          mbar_wait(&cs->outready[b], (it / NB) & 1);
+          uint8_t* dst = out + line_off(w.j * G, yo) + SLAB_ROW_BYTES;   // pixel rows 1 .. W of each segment
+          const uint8_t* src = stage1 + b * TILE_BYTES + SLAB_ROW_BYTES;
+          if (!(dbg & 4)) for (int i = 0; i < geff; ++i, dst += img_bytes, src += seg_bytes) bulk_s2g(dst, src, px_bytes);
           bulk_commit();
-          trace_at(trace_buf, pit, 5);
-        }
-        if (!more) break;
-        prev_j = w.j;
-        prev_line = yo;
-        if (++yo > w.yo1) {
-          more = w.next();
-          yo = more ? w.yo0 : 0;
+          trace_at(trace_buf, it, 5);
+          bulk_wait_read<0>();                // the store has read its staging buffer (a few hundred cycles; the next
+          mbar_arrive(&cs->outfree[b]);       // tile's outready is a tile period away): free it for tile it + NB
         }
       }
       bulk_wait_all<0>();
+    }
+  } else {
+    // ===== gatekeeper: takes the barrier waits of the issuer (input line landed, fresh accumulator slots drained) and
+    // opens ONE gate per input tile.  A gate of the ring is reused LT_GATES tiles later; by then its tile has been issued
+    // and completed (this tile's input stage was freed by the commit of a tile at most LT_GATES - 1 back). =====
+    if (lane == 0) {
+      LineWalk w(g.H, t0, t1);
+      int ii = 0, it_seg = 0;
+      while (w.next()) {
+        const int yo0 = w.yo0, yo1 = w.yo1;
+        for (int yi = w.yi0(); yi <= w.yi1(); ++yi, ++ii) {
+          const int b_lo = yi - 1 >= yo0 ? 0 : (yi >= yo0 ? 1 : 2);
+          const int b_hi = yi + 1 <= yo1 ? 2 : (yi <= yo1 ? 1 : 0);
+          const int bf = yi == 1 ? 1 : 2;
+          const int it0 = it_seg + (yi - 1 - yo0);
+          mbar_wait(&cs->full[ii % NS], (ii / NS) & 1);
+          for (int b = max(bf, b_lo); b <= b_hi; ++b)
+            mbar_wait(&cs->tempty[(it0 + b) & 7], (((it0 + b) >> 3) & 1) ^ 1);
+          mbar_arrive(&cs->go[ii & (LT_GATES - 1)]);
+        }
+        it_seg += yo1 - yo0 + 1;
+      }
     }
   }
   tc_fence_before();
@@ -1023,7 +1118,7 @@ static int launch_conv_tap(const void* in, const void* w, const float* bias, int
 }
 
 static size_t line_fixed_smem(int mode) {
-  return 1024 + W_BYTES + (mode_has_aux2(mode) ? 4 : 2) * TILE_BYTES + sizeof(LineSmem) + 64;
+  return 1024 + W_BYTES + line_stage_tiles(mode) * TILE_BYTES + sizeof(LineSmem) + 64;
 }
 
 template <int MODE, int NS>
@@ -1042,7 +1137,7 @@ static int launch_conv_line_ns(const void* in, const void* w, const float* bias,
   ProfSpan span(BRUNO_PROF_CONV, st);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(FWD_THREADS);
+  cfg.blockDim = dim3(LT_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1052,18 +1147,23 @@ static int launch_conv_line_ns(const void* in, const void* w, const float* bias,
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, conv3x3_line_kernel<MODE, NS>, static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias,
                      static_cast<const uint8_t*>(a1), static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g, G,
-                     static_cast<int>(n_lines), bias_img_stride, g_conv_trace_host);
+                     static_cast<int>(n_lines), bias_img_stride, g_conv_trace_host, getenv("BRUNO_DBG_LINE") ? atoi(getenv("BRUNO_DBG_LINE")) : 0);
   return check_launch("conv3x3_line_kernel");
 }
 
-// 0 = line-tile kernel (default; needs the row pitch P <= 128), 1 = per-tap kernel (any width the slab ring fits)
+// 0 = automatic: the line-tile kernel when every CTA gets at least a few output lines (its per-CTA set-up -- 704 threads,
+// 8 TMEM slots, zeroed stages -- and the halo lines of a range that starts / ends inside an image do not pay off on a
+// 40-image few-shot episode: 1.61 vs 1.33 ms per episode), else the per-tap kernel; 1 = per-tap kernel (also the fallback
+// for a row pitch P > 128); 2 = line-tile kernel
 static int g_conv_variant = 0;
 
 template <int MODE>
 static int launch_conv(const void* in, const void* w, const float* bias, int bias_img_stride, const void* a1,
                        const void* a2, void* out, const SlabGeom& g, cudaStream_t st) {
-  if (g_conv_variant == 0 && g.P <= TILE_M)
-    return launch_conv_line_ns<MODE, LT_MAX_STAGES>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
+  const int G = g.P <= TILE_M ? TILE_M / g.P : 1;
+  const long long n_lines = static_cast<long long>((g.N + G - 1) / G) * g.H;
+  const bool line = g.P <= TILE_M && (g_conv_variant == 2 || (g_conv_variant == 0 && n_lines >= 3ll * num_sms()));
+  if (line) return launch_conv_line_ns<MODE, line_ns(MODE)>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
   return launch_conv_tap<MODE>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
 }
 
@@ -1086,7 +1186,7 @@ int bruno_debug_conv_trace(long long* device_buffer) {
   return BRUNO_OK;
 }
 int bruno_debug_conv_variant(int variant) {
-  BRUNO_REQUIRE(variant == 0 || variant == 1, "bruno_debug_conv_variant: 0 = line-tile kernel, 1 = per-tap kernel");
+  BRUNO_REQUIRE(variant >= 0 && variant <= 2, "bruno_debug_conv_variant: 0 = automatic, 1 = per-tap kernel, 2 = line-tile kernel");
   g_conv_variant = variant;
   return BRUNO_OK;
 }

@@ -160,7 +160,8 @@ size_t bruno_conv_wpack_bytes(void);
 /* DEBUG (process-wide, not thread-safe): CTA 0 of bruno_conv3x3 records clock64() of its pipeline events into
  * device_buffer [64 tiles][16] (NULL = off) */
 int bruno_debug_conv_trace(long long* device_buffer);
-/* DEBUG (process-wide): 0 = line-tile conv kernel (default), 1 = per-tap kernel (the fallback for row pitch > 128). */
+/* DEBUG (process-wide): 0 = automatic (line-tile kernel for >= 3 output lines per SM, else per-tap), 1 = per-tap kernel
+ * (also the fallback for a row pitch > 128), 2 = line-tile kernel. */
 int bruno_debug_conv_variant(int variant);
 #endif
 

@@ -62,15 +62,23 @@ def test_conv3x3_all_epilogues(N, H, W):
         (3, wbw[0], (dconv + a2q) * elu_grad_from_out(a1q)),
         (4, wf[0], conv + bias.float().double()),
     ]
-    for mode, w, ref in cases:
-        out.zero_()
-        _lib.call('bruno_conv3x3', mode, xs, w, b32, 0, a1s, a2s, out, N, H, W)
-        got = slab.slab_to_nhwc(out, N, H, W, check_padding=True).double().cpu()
-        err = (got - ref).abs().max().item()
-        scale = ref.abs().max().item()
-        assert err <= 2.0 ** -7 * scale + 1e-3, (mode, err, scale)
-        # mean error must be far below the bf16 output quantum (catches systematic tap/channel mix-ups)
-        assert (got - ref).abs().mean().item() <= 3e-3 * scale, (mode, (got - ref).abs().mean().item())
+    lib = _lib.load()
+    try:
+        for variant in (1, 2):          # per-tap kernel, line-tile kernel (the automatic choice depends on the size)
+            if variant == 2 and W + 1 > 128:
+                continue
+            assert lib.bruno_debug_conv_variant(variant) == 0
+            for mode, w, ref in cases:
+                out.zero_()
+                _lib.call('bruno_conv3x3', mode, xs, w, b32, 0, a1s, a2s, out, N, H, W)
+                got = slab.slab_to_nhwc(out, N, H, W, check_padding=True).double().cpu()
+                err = (got - ref).abs().max().item()
+                scale = ref.abs().max().item()
+                assert err <= 2.0 ** -7 * scale + 1e-3, (variant, mode, err, scale)
+                # mean error must be far below the bf16 output quantum (catches systematic tap/channel mix-ups)
+                assert (got - ref).abs().mean().item() <= 3e-3 * scale, (variant, mode, (got - ref).abs().mean().item())
+    finally:
+        lib.bruno_debug_conv_variant(0)
 
 
 @pytest.mark.parametrize('N,H,W', [(3, 28, 28), (5, 14, 14), (2, 32, 32), (300, 14, 14)])
@@ -208,10 +216,10 @@ def test_line_tile_kernel_is_bit_identical_to_per_tap_kernel(N, H, W):
     try:
         for mode in range(5):
             w = wf[0] if mode in (0, 1, 4) else wbw[0]
-            for variant in (0, 1):
+            for variant in (2, 1):
                 assert lib.bruno_debug_conv_variant(variant) == 0
-                out[variant].zero_()
-                _lib.call('bruno_conv3x3', mode, xs, w, b32, 0, a1s, a2s, out[variant], N, H, W)
+                out[variant - 1].zero_()
+                _lib.call('bruno_conv3x3', mode, xs, w, b32, 0, a1s, a2s, out[variant - 1], N, H, W)
             torch.cuda.synchronize()
             assert torch.equal(out[0], out[1]), (mode, int((out[0] != out[1]).sum()))
     finally:

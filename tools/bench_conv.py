@@ -70,11 +70,12 @@ for (N, H, W) in shapes:
             N, H, W, tiles, tiles / 148.0, mode, us_eager, us_graph, flops / us_graph * 1e-6), flush=True)
         keep.append(graph)
         if first_graph is None:
-            first_graph = (graph, flops, (N, H, W), chain)
+            first_graph = []
+        if len(first_graph) < 4:
+            first_graph.append((graph, flops, (N, H, W), chain, mode))
 
-if sustain > 0:
-    graph, flops, shape, chain = first_graph
-    print('sustained replay of mode 0 %s for %.1f s; idle: %s' % (shape, sustain, smi()))
+for graph, flops, shape, chain, gmode in (first_graph if sustain > 0 else []):
+    print('sustained replay of mode %d %s for %.1f s; idle: %s' % (gmode, shape, sustain, smi()))
     t_end = time.time() + sustain
     w = 0
     while time.time() < t_end:
@@ -82,7 +83,7 @@ if sustain > 0:
         tr = torch.zeros(64 * 16, dtype=torch.int64, device='cuda')
         if hasattr(lib, 'bruno_debug_conv_trace'):
             lib.bruno_debug_conv_trace(tr.data_ptr())
-            chain(0)
+            chain(gmode)
             torch.cuda.synchronize()
             lib.bruno_debug_conv_trace(None)
             t = tr.view(64, 16).cpu()

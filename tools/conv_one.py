@@ -12,9 +12,9 @@ xs, a1, a2 = [slab.nhwc_to_slab(torch.randn(N, H, W, 64, generator=g).cuda()) fo
 bias = torch.randn(64, generator=g).cuda()
 out = slab.alloc_slabs(2, N, H, W, 'cuda')
 lib = _lib.load()
-for v in (1, 0):
+for v in (1, 2):
     lib.bruno_debug_conv_variant(v)
-    _lib.call('bruno_conv3x3', mode, xs, wf[0] if mode in (0, 1, 4) else wbw[0], bias, 0, a1, a2, out[v], N, H, W)
+    _lib.call('bruno_conv3x3', mode, xs, wf[0] if mode in (0, 1, 4) else wbw[0], bias, 0, a1, a2, out[v - 1], N, H, W)
     torch.cuda.synchronize()
     print('variant', v, 'ok', flush=True)
 a, b = slab.slab_to_nhwc(out[0], N, H, W, check_padding=True), slab.slab_to_nhwc(out[1], N, H, W, check_padding=True)

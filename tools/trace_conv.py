@@ -1,6 +1,6 @@
 """Pipeline timeline of CTA 0 of the forward/dgrad conv kernel (bruno_debug_conv_trace; DEBUG build only):
-kernel entry, set-up, previous-grid-complete, weights landed, then per tile: slab load issued / landed, MMAs issued,
-accumulator ready, epilogue done, store issued, and the kernel's end.  Cycles of SM 0's clock64().
+kernel entry, set-up, previous-grid-complete, weights landed, then per input tile: load issued, issuer past its waits,
+MMAs issued, and per output tile: accumulator ready, epilogue done, store issued; and the kernel's end.  Cycles of SM 0's clock64().
 Usage: python tools/trace_conv.py [N H W]      (default 640 14 14: the launch-overhead-bound layer shape)"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -21,7 +21,7 @@ def launch(mode):
               sl[2] if mode == 3 else None, sl[1], N, H, W)
 
 
-for mode in (0, 3):
+for mode in (0, 1, 2, 3):
     for _ in range(3):
         launch(mode)
     tr = torch.zeros(64 * 16, dtype=torch.int64, device='cuda')
@@ -36,8 +36,10 @@ for mode in (0, 3):
     print('mode %d  %dx%dx%d   (cycles since kernel entry of CTA 0; second of two back-to-back launches)' % (mode, N, H, W))
     print('  setup done %d | previous grid complete %d | weights landed %d | kernel end %d' % (
         rel(t[0, 9]), rel(t[0, 10]), rel(t[0, 11]), rel(t[0, 12])))
-    for i in range(32):
+    cyc, ns = int(t[0, 12] - t[0, 8]), int(t[0, 14] - t[0, 13])
+    print('  CTA 0 lifetime: %d cycles in %d ns = %.0f MHz effective SM clock' % (cyc, ns, 1e3 * cyc / max(ns, 1)))
+    for i in range(int(os.environ.get('TRACE_TILES', '32'))):
         if int(t[i, 0]) == 0:
             break
-        print('  tile %2d: load issued %6d landed %6d | mma issued %6d | acc ready %6d tmem free %6d epi done %6d | store issued %6d' % (
-            (i,) + tuple(rel(t[i, k]) for k in (0, 1, 2, 3, 6, 4, 5))))
+        print('  tile %2d: load issued %6d | mma start %6d issued %6d | acc ready %6d epi done %6d | store issued %6d' % (
+            (i,) + tuple(rel(t[i, k]) for k in (0, 1, 2, 3, 4, 5))))
