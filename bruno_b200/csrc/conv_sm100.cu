@@ -399,7 +399,7 @@ constexpr int LT_GUARD = 8;                                       // zero rows b
 constexpr int LT_STAGE_BYTES = (TILE_M + 2 * LT_GUARD) * SLAB_ROW_BYTES;   // 18 KB
 constexpr int LT_MAX_STAGES = 4;
 
-constexpr int LT_THREADS = 32 * (2 + FWD_EPI_WARPS + 3);   // producer, MMA issuer, epilogue warps, aux loader, output drain, gatekeeper
+constexpr int LT_THREADS = 32 * (2 + FWD_EPI_WARPS + 4);   // producer, MMA issuer, epilogue warps, aux1 loader, output drain, gatekeeper, aux2 loader
 constexpr int LT_GATES = 4;
 constexpr int LT_MAX_NB = 4;                                // ring of "tile may be issued" barriers (gatekeeper -> issuer)
 
@@ -722,7 +722,9 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
       }
     }
   } else if (warp == 2 + FWD_EPI_WARPS) {
-    // ===== aux loader: the saved-activation / addend tiles of output tile it, up to NB - 1 tiles ahead of its epilogue =====
+    // ===== aux1 loader: the saved-activation tile of output tile it, up to NB - 1 tiles ahead of its epilogue.  (One bulk
+    // copy costs its issuing thread ~110 cycles -- 8 segments per tile at 14x14 are most of a tile period -- so the second
+    // stream of MODE_ADD_MUL has its own thread, below; both complete the same barrier, this one arms it.) =====
     if (mode_has_aux1(MODE) && lane == 0) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
       LineWalk w(g.H, t0, t1);
@@ -735,10 +737,24 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
           mbar_arrive_expect_tx(&cs->auxfull[b], static_cast<uint32_t>(geff) * px_bytes * (mode_has_aux2(MODE) ? 2u : 1u));
           size_t off = line_off(w.j * G, yo) + SLAB_ROW_BYTES;          // pixel rows 1 .. W of each segment
           uint32_t so = b * TILE_BYTES + SLAB_ROW_BYTES;
-          for (int i = 0; i < geff; ++i, off += img_bytes, so += seg_bytes) {
-            bulk_g2s(stage1 + so, aux1 + off, px_bytes, &cs->auxfull[b]);
-            if (mode_has_aux2(MODE)) bulk_g2s(stage2 + so, aux2 + off, px_bytes, &cs->auxfull[b]);
-          }
+          for (int i = 0; i < geff; ++i, off += img_bytes, so += seg_bytes) bulk_g2s(stage1 + so, aux1 + off, px_bytes, &cs->auxfull[b]);
+        }
+      }
+    }
+  } else if (warp == 2 + FWD_EPI_WARPS + 3) {
+    // ===== aux2 loader (MODE_ADD_MUL): the addend tile; same buffer hand-shake, bytes counted by the aux1 loader =====
+    if (mode_has_aux2(MODE) && lane == 0) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      LineWalk w(g.H, t0, t1);
+      int it = 0;
+      while (w.next()) {
+        const int geff = min(G, g.N - w.j * G);
+        for (int yo = w.yo0; yo <= w.yo1; ++yo, ++it) {
+          const int b = it % NB;
+          if (it >= NB) mbar_wait(&cs->outfree[b], ((it / NB) - 1) & 1);
+          size_t off = line_off(w.j * G, yo) + SLAB_ROW_BYTES;
+          uint32_t so = b * TILE_BYTES + SLAB_ROW_BYTES;
+          for (int i = 0; i < geff; ++i, off += img_bytes, so += seg_bytes) bulk_g2s(stage2 + so, aux2 + off, px_bytes, &cs->auxfull[b]);
         }
       }
     }
@@ -763,7 +779,7 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
       }
       bulk_wait_all<0>();
     }
-  } else {
+  } else if (warp == 2 + FWD_EPI_WARPS + 2) {
     // ===== gatekeeper: takes the barrier waits of the issuer (input line landed, fresh accumulator slots drained) and
     // opens ONE gate per input tile.  A gate of the ring is reused LT_GATES tiles later; by then its tile has been issued
     // and completed (this tile's input stage was freed by the commit of a tile at most LT_GATES - 1 back). =====
@@ -961,6 +977,261 @@ conv3x3_wgrad_kernel(const uint8_t* __restrict__ x_base, const uint8_t* __restri
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---- line-tile wgrad (default) --------------------------------------------------------------------------------------
+// Same tile geometry as the line-tile forward kernel: a tile = one image line of G images = 128 contraction rows.
+//   dW[dy][dx][ci][co] = sum over tiles  X_line(y + dy)[row + dx][ci] * G_line(y)[row][co]
+// For the X line yi ONE N = 192 instruction pairs two horizontal views of it (M = 128: dx = -1, 0; second instruction:
+// dx = +1 and the constant "ones" atom whose row 64 collects the bias gradient) with the THREE gradient lines yi-1, yi,
+// yi+1 -- three 64-column atoms LBO = one ring slot apart -- so the accumulator block b is the vertical tap dy = 1 - b:
+// 16 instructions of 96 tensor cycles per tile (10 KB of operands each: tensor-bound) instead of 40 of N = 64 at 49
+// port-bound cycles, the zero padding lines are never touched, and every X / G line is loaded exactly once per CTA
+// range.  Gradient lines live in a ring of WL_GSLOTS slots; where three consecutive lines wrap around the ring the
+// instruction is split in two.  Accumulators (2 x 192 columns) are zeroed once and summed over all tiles of the CTA.
+constexpr int WL_XSTAGES = 3;
+constexpr int WL_GSLOTS = 6;
+constexpr int WL_GATES = 4;
+constexpr int WL_THREADS = 32 * 8;      // X producer, issuer, 4 epilogue warps (one per TMEM lane quarter), gatekeeper, G producer
+
+struct WlineSmem {
+  uint64_t xfull[WL_XSTAGES], xempty[WL_XSTAGES], gfull[WL_GSLOTS], gempty[WL_GSLOTS], go[WL_GATES], done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(WL_THREADS, 1)
+conv3x3_wgrad_line_kernel(const uint8_t* __restrict__ x_base, const uint8_t* __restrict__ gr_base, float* __restrict__ dW_base,
+                          float* __restrict__ db_base, SlabGeom g, size_t slab_stride, int ctas_per_layer, int G, int n_lines) {
+  const int layer = blockIdx.x / ctas_per_layer;
+  const int part = blockIdx.x % ctas_per_layer;
+  const uint8_t* __restrict__ x = x_base + static_cast<size_t>(layer) * slab_stride;
+  const uint8_t* __restrict__ gr = gr_base + static_cast<size_t>(layer) * slab_stride;
+  float* __restrict__ dW = dW_base + static_cast<size_t>(layer) * 9 * 64 * 64;
+  float* __restrict__ db = db_base + static_cast<size_t>(layer) * 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* xst = smem;                                                  // [WL_XSTAGES][guard | 128 rows | guard]
+  uint8_t* gst = xst + WL_XSTAGES * LT_STAGE_BYTES;                     // [WL_GSLOTS][128 rows]
+  uint8_t* ones = gst + WL_GSLOTS * TILE_BYTES;                         // AFTER every X stage (positive LBO)
+  WlineSmem* ws = reinterpret_cast<WlineSmem*>(ones + ONES_BYTES);
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
+
+  // everything no copy writes stays zero: guards, padding columns, rows past the last segment
+  for (int i = threadIdx.x; i < (WL_XSTAGES * LT_STAGE_BYTES + WL_GSLOTS * TILE_BYTES) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(xst)[i] = make_uint4(0, 0, 0, 0);
+  // constant operand: logical channel 0 of every row = 1.0, everything else 0 (swizzled like a slab row)
+  for (int i = threadIdx.x; i < ONES_BYTES / 16; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (c == (r & 7)) val.x = 0x00003f80u;  // bf16 1.0 in element 0
+    reinterpret_cast<uint4*>(ones)[i] = val;
+  }
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WL_XSTAGES; ++s) {
+      mbar_init(&ws->xfull[s], 1);
+      mbar_init(&ws->xempty[s], 1);
+    }
+    for (int s = 0; s < WL_GSLOTS; ++s) {
+      mbar_init(&ws->gfull[s], 1);
+      mbar_init(&ws->gempty[s], 1);
+    }
+    for (int s = 0; s < WL_GATES; ++s) mbar_init(&ws->go[s], 1);
+    mbar_init(&ws->done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&ws->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ws->tmem_base;
+  if (warp >= 2 && warp < 6) {                                           // zero the two 192-column accumulators
+    const uint32_t tl = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    for (int c = 0; c < 384; c += 8) tmem_st8_fill(tl + c, 0u);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // contiguous range of X line tiles per CTA (keeps the fp32 accumulation order fixed for a given grid)
+  const int t0 = static_cast<int>(static_cast<long long>(part) * n_lines / ctas_per_layer);
+  const int t1 = static_cast<int>(static_cast<long long>(part + 1) * n_lines / ctas_per_layer);
+  const uint32_t seg_bytes = static_cast<uint32_t>(g.P) * SLAB_ROW_BYTES;
+  const uint32_t in_bytes = static_cast<uint32_t>(min(g.P, g.W + 2)) * SLAB_ROW_BYTES;   // pixels + one padding row either side
+  const uint32_t px_bytes = static_cast<uint32_t>(g.W) * SLAB_ROW_BYTES;
+  const size_t img_bytes = static_cast<size_t>(g.IMG) * SLAB_ROW_BYTES;
+  auto line_off = [&](int n, int line) {
+    return (static_cast<size_t>(g.HALO) + static_cast<size_t>(n) * g.IMG + static_cast<size_t>(line) * g.P) * SLAB_ROW_BYTES;
+  };
+
+  if (warp == 0) {
+    // ===== X producer: one X line of G images per stage =====
+    if (lane == 0) {
+      LineWalk w(g.H, t0, t1);
+      int xi = 0;
+      while (w.next()) {
+        const int geff = min(G, g.N - w.j * G);
+        for (int yi = w.yo0; yi <= w.yo1; ++yi, ++xi) {
+          const int s = xi % WL_XSTAGES;
+          mbar_wait(&ws->xempty[s], ((xi / WL_XSTAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&ws->xfull[s], static_cast<uint32_t>(G) * in_bytes);
+          uint8_t* dst = xst + s * LT_STAGE_BYTES + LT_GUARD * SLAB_ROW_BYTES;
+          const uint8_t* src = x + line_off(w.j * G, yi);
+          for (int i = 0; i < geff; ++i, dst += seg_bytes, src += img_bytes) bulk_g2s(dst, src, in_bytes, &ws->xfull[s]);
+          for (int i = geff; i < G; ++i, dst += seg_bytes) bulk_g2s(dst, x, in_bytes, &ws->xfull[s]);       // zeros (slab guard rows)
+        }
+      }
+    }
+  } else if (warp == 7) {
+    // ===== G producer: the gradient lines of every segment, each once, into the slot ring =====
+    if (lane == 0) {
+      LineWalk w(g.H, t0, t1);
+      int gc = 0;
+      while (w.next()) {
+        const int geff = min(G, g.N - w.j * G);
+        const int gb = min(g.H, w.yo1 + 1);
+        for (int y = max(1, w.yo0 - 1); y <= gb; ++y, ++gc) {
+          const int sl = gc % WL_GSLOTS;
+          mbar_wait(&ws->gempty[sl], ((gc / WL_GSLOTS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&ws->gfull[sl], static_cast<uint32_t>(G) * px_bytes);
+          uint8_t* dst = gst + sl * TILE_BYTES + SLAB_ROW_BYTES;          // pixel rows 1 .. W of each segment
+          const uint8_t* src = gr + line_off(w.j * G, y) + SLAB_ROW_BYTES;
+          for (int i = 0; i < geff; ++i, dst += seg_bytes, src += img_bytes) bulk_g2s(dst, src, px_bytes, &ws->gfull[sl]);
+          for (int i = geff; i < G; ++i, dst += seg_bytes) bulk_g2s(dst, gr, px_bytes, &ws->gfull[sl]);     // zeros
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one wait per tile (the gatekeeper has seen the X line and its gradient lines land) =====
+    if (elect_one()) {
+      constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+      constexpr uint32_t GSLOT = TILE_BYTES >> 4;                          // one gradient-line slot in descriptor units
+      const uint32_t x_lo0 = ((smem_u32(xst) & 0x3FFFFu) >> 4) + LT_GUARD * 8;   // tile row 0 of X stage 0
+      const uint32_t g_lo0 = (smem_u32(gst) & 0x3FFFFu) >> 4;
+      const uint32_t ones_lo = (smem_u32(ones) & 0x3FFFFu) >> 4;
+      const uint32_t go0 = smem_u32(&ws->go[0]), xempty0 = smem_u32(&ws->xempty[0]), gempty0 = smem_u32(&ws->gempty[0]);
+      auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(DESC_HI) << 32) | lo; };
+      auto commit_addr = [](uint32_t bar) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+      };
+      LineWalk w(g.H, t0, t1);
+      int xi = 0, gc_seg = 0, sidx = 0;
+      uint32_t x_off = 0;
+      while (w.next()) {
+        const int ga = max(1, w.yo0 - 1), gb = min(g.H, w.yo1 + 1);
+        for (int yi = w.yo0; yi <= w.yo1; ++yi, ++xi) {
+          mbar_wait(&ws->go[xi & (WL_GATES - 1)], (xi / WL_GATES) & 1);
+          tc_fence_after();
+          // accumulator block b = gradient line yi - 1 + b = vertical tap dy = 1 - b
+          const int b_lo = yi - 1 >= 1 ? 0 : 1, b_hi = yi + 1 <= g.H ? 2 : 1;
+          const int gcnt = gc_seg + (yi - 1 + b_lo - ga);                  // ring counter of the first gradient line used
+          const uint32_t slot0 = static_cast<uint32_t>(gcnt % WL_GSLOTS), nbt = b_hi - b_lo + 1;
+          const uint32_t n0 = min(nbt, WL_GSLOTS - slot0), n1 = nbt - n0;  // lines before / after the ring wraps
+          const uint32_t d1 = tmem + b_lo * 64, d2 = tmem + 192 + b_lo * 64;
+          const uint32_t id0 = idesc64 + (n0 - 1) * (8u << 17), id1 = idesc64 + (n1 - 1) * (8u << 17);
+          // A: two atoms LBO apart.  dx = -1, 0: rows -1 and 0 of the tile (LBO = one row = 8 units);  dx = +1 and "ones":
+          // LBO = distance to the constant atom, shrinking by the 128 units the address advances per K step
+          const uint32_t xa = x_lo0 + x_off;
+          const uint32_t a1 = (xa - 8u) | (8u << 16);
+          const uint32_t a2 = (xa + 8u) | ((ones_lo - (xa + 8u)) << 16);
+          const uint64_t A1 = desc(a1), A2 = desc(a2);
+          const uint64_t B0 = desc((g_lo0 + slot0 * GSLOT) | (GSLOT << 16)), B1 = desc(g_lo0 | (GSLOT << 16));
+          // per K step (16 rows = 128 descriptor units): every address + 128 ks; the LBO of A2 - 128 ks (constant atom)
+          if (n1 == 0) {
+#pragma unroll
+            for (int ks = 0; ks < TILE_M / 16; ++ks) {
+              const uint64_t k = ks * 128u;
+              umma_bf16(d1, A1 + k, B0 + k, id0, 1u);
+              umma_bf16(d2, A2 + k - (k << 16), B0 + k, id0, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < TILE_M / 16; ++ks) {
+              const uint64_t k = ks * 128u;
+              umma_bf16(d1, A1 + k, B0 + k, id0, 1u);
+              umma_bf16(d1 + n0 * 64, A1 + k, B1 + k, id1, 1u);
+              umma_bf16(d2, A2 + k - (k << 16), B0 + k, id0, 1u);
+              umma_bf16(d2 + n0 * 64, A2 + k - (k << 16), B1 + k, id1, 1u);
+            }
+          }
+          commit_addr(xempty0 + 8u * sidx);
+          // gradient line yi - 1 is not needed after this tile; the last tile of a segment frees the rest
+          if (yi - 1 >= ga) commit_addr(gempty0 + 8u * ((gc_seg + (yi - 1 - ga)) % WL_GSLOTS));
+          if (yi == w.yo1)
+            for (int y = yi; y <= gb; ++y) commit_addr(gempty0 + 8u * ((gc_seg + (y - ga)) % WL_GSLOTS));
+          if (++sidx == WL_XSTAGES) {
+            sidx = 0;
+            x_off = 0;
+          } else {
+            x_off += LT_STAGE_BYTES >> 4;
+          }
+        }
+        gc_seg += gb - ga + 1;
+      }
+      // the issuer itself waits for the last commit: no asynchronous mbarrier arrive may still be in flight when the CTA
+      // exits (it would land in the shared memory of whichever CTA gets this SM next)
+      umma_commit(&ws->done);
+      mbar_wait(&ws->done, 0);
+    }
+    __syncwarp();
+  } else if (warp >= 2 && warp < 6) {
+    // ===== final epilogue: the accumulated gradient of this CTA's range -> global (fp32 atomics) =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                // accumulator row: view (m >> 6) x input channel (m & 63)
+    mbar_wait(&ws->done, 0);
+    tc_fence_after();
+    if (t1 > t0) {
+      const int ci = m & 63;
+      for (int half = 0; half < 2; ++half) {    // 0: dx = -1 / 0 (rows 0..63 / 64..127);  1: dx = +1 (rows 0..63), bias (row 64)
+        const int dx = half == 0 ? (m >> 6) - 1 : 1;
+        for (int b = 0; b < 3; ++b) {
+          const int tap = (2 - b) * 3 + (dx + 1);                          // dy = 1 - b
+          for (int h32 = 0; h32 < 2; ++h32) {
+            uint32_t v[32];
+            tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + half * 192 + b * 64 + h32 * 32, v);
+            tmem_ld_wait();
+            float* dst = nullptr;
+            if (half == 0 || m < 64) dst = dW + (static_cast<size_t>(tap) * 64 + ci) * 64 + h32 * 32;
+            else if (m == 64 && b == 1) dst = db + h32 * 32;               // sum of the gradient line itself (dy = 0 block)
+            if (dst) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4)
+                red_add_v4(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                           __uint_as_float(v[e + 3]));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===== gatekeeper: waits for the X line and for the gradient lines it needs, opens one gate per tile =====
+    if (lane == 0) {
+      LineWalk w(g.H, t0, t1);
+      int xi = 0, gc = 0;
+      while (w.next()) {
+        const int gb = min(g.H, w.yo1 + 1);
+        int gnext = max(1, w.yo0 - 1);
+        for (int yi = w.yo0; yi <= w.yo1; ++yi, ++xi) {
+          for (; gnext <= min(gb, yi + 1); ++gnext, ++gc) mbar_wait(&ws->gfull[gc % WL_GSLOTS], (gc / WL_GSLOTS) & 1);
+          mbar_wait(&ws->xfull[xi % WL_XSTAGES], (xi / WL_XSTAGES) & 1);
+          mbar_arrive(&ws->go[xi & (WL_GATES - 1)]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static size_t wgrad_line_smem_bytes() {
+  return 1024 + static_cast<size_t>(WL_XSTAGES) * LT_STAGE_BYTES + static_cast<size_t>(WL_GSLOTS) * TILE_BYTES + ONES_BYTES +
+         sizeof(WlineSmem) + 64;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1162,7 +1433,7 @@ static int launch_conv(const void* in, const void* w, const float* bias, int bia
                        const void* a2, void* out, const SlabGeom& g, cudaStream_t st) {
   const int G = g.P <= TILE_M ? TILE_M / g.P : 1;
   const long long n_lines = static_cast<long long>((g.N + G - 1) / G) * g.H;
-  const bool line = g.P <= TILE_M && (g_conv_variant == 2 || (g_conv_variant == 0 && n_lines >= 3ll * num_sms()));
+  const bool line = g.P <= TILE_M && (g_conv_variant == 2 || (g_conv_variant == 0 && (n_lines >= 3ll * num_sms() || tap_stages(g, MODE) < 2)));
   if (line) return launch_conv_line_ns<MODE, line_ns(MODE)>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
   return launch_conv_tap<MODE>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
 }
@@ -1245,6 +1516,23 @@ int bruno_conv3x3_wgrad_batched(const void* x_slab, const void* g_slab, float* d
   BRUNO_REQUIRE(x_slab && g_slab && dW && db && L > 0 && N > 0 && H > 0 && W > 0, "bruno_conv3x3_wgrad: bad arguments");
   BRUNO_REQUIRE(aligned16(x_slab) && aligned16(g_slab) && aligned16(dW) && aligned16(db), "bruno_conv3x3_wgrad: alignment");
   const SlabGeom g = slab_geom(N, H, W);
+  if (g_conv_variant != 1 && g.P <= TILE_M) {                   // line-tile kernel (the per-tap one: wide images / debug)
+    static OncePerDevice once_line;
+    once_line.run([&] {
+      cudaFuncSetAttribute(conv3x3_wgrad_line_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    const int G = TILE_M / g.P;
+    const long long n_lines = static_cast<long long>((N + G - 1) / G) * H;
+    BRUNO_REQUIRE(n_lines < (1ll << 30), "bruno_conv3x3_wgrad: too many line tiles");
+    int per_layer = num_sms() / L;
+    if (per_layer < 1) per_layer = 1;
+    if (per_layer > n_lines) per_layer = static_cast<int>(n_lines);
+    ProfSpan span(BRUNO_PROF_WGRAD, static_cast<cudaStream_t>(stream));
+    conv3x3_wgrad_line_kernel<<<per_layer * L, WL_THREADS, wgrad_line_smem_bytes(), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint8_t*>(x_slab), static_cast<const uint8_t*>(g_slab), dW, db, g,
+        static_cast<size_t>(g.rows) * SLAB_ROW_BYTES, per_layer, G, static_cast<int>(n_lines));
+    return check_launch("conv3x3_wgrad_line_kernel");
+  }
   const size_t smem = wgrad_smem_bytes(g);
   BRUNO_REQUIRE(smem <= 227 * 1024, "bruno_conv3x3_wgrad: W=%d too wide", W);
   static OncePerDevice once;

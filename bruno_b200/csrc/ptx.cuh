@@ -104,6 +104,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 32 lanes x 8 consecutive 32-bit columns <- the same value from every thread (used to zero accumulators)
+__device__ __forceinline__ void tmem_st8_fill(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(v) : "memory");
+}
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (base_lane + t).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
