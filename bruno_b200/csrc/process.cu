@@ -1474,7 +1474,11 @@ static int launch_fwd(const float* z, const float* mu0, const float* table, floa
                       float* lp_prior, float* scratch, int B, int T, int D, const ScanGeom& g, cudaStream_t st) {
   if constexpr (VEC == 4) {
     const int v = fwd_variant();
-    if (v == 0 || v >= 10) {
+    // The running-state entry (s1 / s2 read and written back: the reference's step-by-step API, not a hot path) stays on
+    // the register-staged scan: the STATE instantiation of the ring kernel returned one wrong row in ~10 % of the runs
+    // of tests/test_process_gpu.py::test_forward_scan_variants_agree[1030-20-784-0.0-gp] (the sequence-at-once
+    // instantiation: 0 of 200, tools/dbg_proc_flaky.py); cause not found yet, so the default does not use it.
+    if ((v == 0 && s1 == nullptr) || v >= 10) {
       int rc;
       switch (v) {
         case 11: rc = launch_fwd_ring<KIND, 2, 8, 2, 3, 1>(z, mu0, table, s1, s2, lp, lp_prior, scratch, B, T, D, st); break;
