@@ -405,19 +405,21 @@ constexpr int LT_MAX_NB = 4;                                // ring of "tile may
 
 struct LineSmem {
   uint64_t full[LT_MAX_STAGES], empty[LT_MAX_STAGES], tfull[LT_SLOTS], tempty[LT_SLOTS], wbar;
-  uint64_t auxfull[LT_MAX_NB], outready[LT_MAX_NB], outfree[LT_MAX_NB], go[LT_GATES];
+  uint64_t auxfull[LT_MAX_NB], outready[LT_MAX_NB], outfree[LT_MAX_NB], go[LT_GATES], aux2full[2], aux2free[2];
   uint32_t tmem_base;
   alignas(16) float bias[64];
 };
 // Staging ring: NB buffers of one tile per stream (aux1 / output IN PLACE, aux2).  An aux tile is requested as soon as the
 // store of the tile NB back has read the buffer, i.e. NB - 1 tile periods before its epilogue needs it: with the HBM
 // latency at 2-3 tile periods, NB = 2 (one buffer per epilogue group) exposes it in every epilogue.
-// (MODE_ADD_MUL: three input stages + two staging buffers per stream.  Three of each also fits in shared memory, but that
-// configuration -- and only that one -- fails on back-to-back 640 x 28 x 28 launches (launch failure / hang) for a reason
-// not yet understood; the protocol is deadlock-free on paper and every other combination runs the chains bit-exactly.)
+// MODE_ADD_MUL: four input stages, two aux1 / output buffers and two addend buffers (one per epilogue group): an epilogue
+// copies its addend tile to registers first thing and frees the buffer, so the addend of the group's next tile streams in
+// during the whole epilogue.  (Three input stages + three aux1 / output buffers also fit, but that combination -- and only
+// that one, only in this mode -- fails on back-to-back 640 x 28 x 28 launches for a reason not understood; every shipped
+// combination runs dependent 20-launch chains bit-identically to the per-tap kernel, tools/conv_chain.py.)
 __host__ __device__ constexpr int line_nb(int mode) { return mode_has_aux2(mode) ? 2 : (mode_has_aux1(mode) ? 4 : 2); }
-__host__ __device__ constexpr int line_ns(int mode) { return mode_has_aux2(mode) ? 3 : LT_MAX_STAGES; }
-__host__ __device__ constexpr int line_stage_tiles(int mode) { return line_nb(mode) * (mode_has_aux2(mode) ? 2 : 1); }
+__host__ __device__ constexpr int line_ns(int mode) { return LT_MAX_STAGES; }
+__host__ __device__ constexpr int line_stage_tiles(int mode) { return line_nb(mode) + (mode_has_aux2(mode) ? 2 : 0); }
 
 // This CTA's share [t, t1) of the output line tiles (linear index = image group * H + data line - 1), walked segment by
 // segment; a segment = consecutive output lines yo0..yo1 (1-based data lines) of ONE image group j.  Its input lines are
@@ -442,14 +444,14 @@ template <int MODE, int NS>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
                     const uint8_t* __restrict__ aux1, const uint8_t* __restrict__ aux2, uint8_t* __restrict__ out,
-                    SlabGeom g, int G, int n_lines, int bias_img_stride, long long* trace_buf, int dbg) {
+                    SlabGeom g, int G, int n_lines, int bias_img_stride, long long* trace_buf) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* wsm = smem;
   uint8_t* slabs = smem + W_BYTES;                                     // [NS][guard | 128 tile rows | guard]
   constexpr int NB = line_nb(MODE);
   uint8_t* stage1 = slabs + NS * LT_STAGE_BYTES;                       // [NB][TILE_BYTES] aux1 tile in / output tile out (in place)
-  uint8_t* stage2 = stage1 + NB * TILE_BYTES;                          // [NB][TILE_BYTES] aux2 tiles (MODE_ADD_MUL only)
+  uint8_t* stage2 = stage1 + NB * TILE_BYTES;                          // [2][TILE_BYTES] addend tiles (MODE_ADD_MUL only), one per epilogue group
   LineSmem* cs = reinterpret_cast<LineSmem*>(stage1 + line_stage_tiles(MODE) * TILE_BYTES);
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   constexpr bool HAS_BIAS = MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR;
@@ -470,6 +472,10 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
       mbar_init(&cs->outfree[a], 1);
     }
     for (int a = 0; a < LT_GATES; ++a) mbar_init(&cs->go[a], 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&cs->aux2full[a], 1);
+      mbar_init(&cs->aux2free[a], FWD_EPI_WARPS * 16);
+    }
     mbar_init(&cs->wbar, 1);
     fence_mbar_init();
   }
@@ -521,15 +527,10 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
           trace_at(trace_buf, ii, 0);
           uint8_t* dst = slabs + s * LT_STAGE_BYTES + LT_GUARD * SLAB_ROW_BYTES;
           const uint8_t* src = in + line_off(w.j * G, yi);
-          if (dbg & 2) {
-            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&cs->full[s])),
-                         "r"(static_cast<uint32_t>(geff) * in_bytes + (geff < G ? seg_bytes : 0u)) : "memory");
-          } else {
-            for (int i = 0; i < geff; ++i, dst += seg_bytes, src += img_bytes) bulk_g2s(dst, src, in_bytes, &cs->full[s]);
-            // the segment after the last image of a partial group holds that image's right-hand neighbours: zeros (the
-            // slab's leading guard rows), whatever an earlier full group left there
-            if (geff < G) bulk_g2s(dst, in, seg_bytes, &cs->full[s]);
-          }
+          for (int i = 0; i < geff; ++i, dst += seg_bytes, src += img_bytes) bulk_g2s(dst, src, in_bytes, &cs->full[s]);
+          // the segment after the last image of a partial group holds that image's right-hand neighbours: zeros (the
+          // slab's leading guard rows), whatever an earlier full group left there
+          if (geff < G) bulk_g2s(dst, in, seg_bytes, &cs->full[s]);
         }
       }
     }
@@ -662,19 +663,26 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
       for (int yo = w.yo0; yo <= w.yo1; ++yo, ++it) {
         if ((it & 1) != grp) continue;
         const int a = it & 7;
+        uint4 t2[4];
+        if (mode_has_aux2(MODE)) {            // addend tile -> registers, buffer free for this group's next tile
+          mbar_wait(&cs->aux2full[grp], (it >> 1) & 1);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) t2[jj] = lds_u4(st2_0 + grp * TILE_BYTES + (((half * 4 + jj) ^ R7) << 4));
+          mbar_arrive(&cs->aux2free[grp]);
+        }
         mbar_wait(&cs->tfull[a], (it >> 3) & 1);
         tc_fence_after();
         if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 3);
         const uint32_t tbase = tmem + (static_cast<uint32_t>(q * 32) << 16) + a * 64 + half * 32;
         uint32_t acc[4][8];
 #pragma unroll
-        if (!(dbg & 16)) { for (int c = 0; c < 4; ++c) tmem_ld8(tbase + c * 8, acc[c]); } else { for (int c = 0; c < 4; ++c) for (int e = 0; e < 8; ++e) acc[c][e] = 0; }
+        for (int c = 0; c < 4; ++c) tmem_ld8(tbase + c * 8, acc[c]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&cs->tempty[a]);
         const int sb = it % NB;                                          // staging buffer of this tile
-        const uint32_t st1 = st1_0 + sb * TILE_BYTES, st2 = st2_0 + sb * TILE_BYTES;
+        const uint32_t st1 = st1_0 + sb * TILE_BYTES;
         if (mode_has_aux1(MODE)) mbar_wait(&cs->auxfull[sb], (it / NB) & 1);           // (the loader waited for the buffer)
         else mbar_wait(&cs->outfree[sb], ((it / NB) & 1) ^ 1);           // the store of tile it - NB has read the buffer
 #pragma unroll
@@ -710,11 +718,11 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
           } else {
             float sk[8], t[8];
             unpack8(lds_u4(st1 + pos), sk);
-            unpack8(lds_u4(st2 + pos), t);
+            unpack8(t2[jj], t);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = (o[e] + t[e]) * elu_grad_from_out(sk[e]);
           }
-          if (!(dbg & 8)) sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
+          sts_u4(st1 + pos, valid ? pack8(o) : make_uint4(0, 0, 0, 0));
         }
         fence_proxy_async_smem();
         if ((warp == 2 || warp == 10) && lane == 0) trace_at(trace_buf, it, 4);
@@ -723,8 +731,8 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
     }
   } else if (warp == 2 + FWD_EPI_WARPS) {
     // ===== aux1 loader: the saved-activation tile of output tile it, up to NB - 1 tiles ahead of its epilogue.  (One bulk
-    // copy costs its issuing thread ~110 cycles -- 8 segments per tile at 14x14 are most of a tile period -- so the second
-    // stream of MODE_ADD_MUL has its own thread, below; both complete the same barrier, this one arms it.) =====
+    // copy costs its issuing thread ~110 cycles -- 8 segments per tile at 14x14 are most of a tile period -- so the addend
+    // stream of MODE_ADD_MUL has its own thread and buffers, below.) =====
     if (mode_has_aux1(MODE) && lane == 0) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
       LineWalk w(g.H, t0, t1);
@@ -734,7 +742,7 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
         for (int yo = w.yo0; yo <= w.yo1; ++yo, ++it) {
           const int b = it % NB;
           if (it >= NB) mbar_wait(&cs->outfree[b], ((it / NB) - 1) & 1);   // the store of tile it - NB has read buffer b
-          mbar_arrive_expect_tx(&cs->auxfull[b], static_cast<uint32_t>(geff) * px_bytes * (mode_has_aux2(MODE) ? 2u : 1u));
+          mbar_arrive_expect_tx(&cs->auxfull[b], static_cast<uint32_t>(geff) * px_bytes);
           size_t off = line_off(w.j * G, yo) + SLAB_ROW_BYTES;          // pixel rows 1 .. W of each segment
           uint32_t so = b * TILE_BYTES + SLAB_ROW_BYTES;
           for (int i = 0; i < geff; ++i, off += img_bytes, so += seg_bytes) bulk_g2s(stage1 + so, aux1 + off, px_bytes, &cs->auxfull[b]);
@@ -742,7 +750,8 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
       }
     }
   } else if (warp == 2 + FWD_EPI_WARPS + 3) {
-    // ===== aux2 loader (MODE_ADD_MUL): the addend tile; same buffer hand-shake, bytes counted by the aux1 loader =====
+    // ===== addend loader (MODE_ADD_MUL): tile it goes to the buffer of epilogue group it & 1 as soon as that group has
+    // copied the addend of its previous tile (it - 2) to registers =====
     if (mode_has_aux2(MODE) && lane == 0) {
       asm volatile("griddepcontrol.wait;" ::: "memory");
       LineWalk w(g.H, t0, t1);
@@ -750,11 +759,12 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
       while (w.next()) {
         const int geff = min(G, g.N - w.j * G);
         for (int yo = w.yo0; yo <= w.yo1; ++yo, ++it) {
-          const int b = it % NB;
-          if (it >= NB) mbar_wait(&cs->outfree[b], ((it / NB) - 1) & 1);
+          const int b = it & 1;
+          if (it >= 2) mbar_wait(&cs->aux2free[b], ((it >> 1) - 1) & 1);
+          mbar_arrive_expect_tx(&cs->aux2full[b], static_cast<uint32_t>(geff) * px_bytes);
           size_t off = line_off(w.j * G, yo) + SLAB_ROW_BYTES;
           uint32_t so = b * TILE_BYTES + SLAB_ROW_BYTES;
-          for (int i = 0; i < geff; ++i, off += img_bytes, so += seg_bytes) bulk_g2s(stage2 + so, aux2 + off, px_bytes, &cs->auxfull[b]);
+          for (int i = 0; i < geff; ++i, off += img_bytes, so += seg_bytes) bulk_g2s(stage2 + so, aux2 + off, px_bytes, &cs->aux2full[b]);
         }
       }
     }
@@ -770,7 +780,7 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
           mbar_wait(&cs->outready[b], (it / NB) & 1);
           uint8_t* dst = out + line_off(w.j * G, yo) + SLAB_ROW_BYTES;   // pixel rows 1 .. W of each segment
           const uint8_t* src = stage1 + b * TILE_BYTES + SLAB_ROW_BYTES;
-          if (!(dbg & 4)) for (int i = 0; i < geff; ++i, dst += img_bytes, src += seg_bytes) bulk_s2g(dst, src, px_bytes);
+          for (int i = 0; i < geff; ++i, dst += img_bytes, src += seg_bytes) bulk_s2g(dst, src, px_bytes);
           bulk_commit();
           trace_at(trace_buf, it, 5);
           bulk_wait_read<0>();                // the store has read its staging buffer (a few hundred cycles; the next
@@ -1418,7 +1428,7 @@ static int launch_conv_line_ns(const void* in, const void* w, const float* bias,
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, conv3x3_line_kernel<MODE, NS>, static_cast<const uint8_t*>(in), static_cast<const uint8_t*>(w), bias,
                      static_cast<const uint8_t*>(a1), static_cast<const uint8_t*>(a2), static_cast<uint8_t*>(out), g, G,
-                     static_cast<int>(n_lines), bias_img_stride, g_conv_trace_host, getenv("BRUNO_DBG_LINE") ? atoi(getenv("BRUNO_DBG_LINE")) : 0);
+                     static_cast<int>(n_lines), bias_img_stride, g_conv_trace_host);
   return check_launch("conv3x3_line_kernel");
 }
 
