@@ -459,14 +459,12 @@ def main():
     achieved_spans = flops_total / (conv['total_ms'] * 1e-3) / 1e12 if conv['total_ms'] > 0 else None
     achieved = 2.0 * fwd_flops / (conv_graph_ms * 1e-3) / 1e12
     traffic, traffic_note = None, None
-    tj = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')
+    tj = os.path.join(ROOT, 'profiles', 'r02_conv_traffic.json')
     if os.path.exists(tj):
         tinfo = json.load(open(tj))
         traffic = tinfo['avg_bytes_per_launch']
-        traffic_note = ('dram read+write bytes per launch, ncu --set full capture of the 28x28 layers (%s); algorithmic bytes of '
-                        'such a launch: %.0f (in + out slab) to %.0f (in + skip + out)' % (
-                            tinfo['source'], tinfo['algorithmic_bytes_per_launch']['mode0 (in+out slab)'],
-                            tinfo['algorithmic_bytes_per_launch']['mode1 (in+skip+out)']))
+        traffic_note = ('dram read+write bytes per 640x28x28 launch, mean of modes 0 / 1 / 3, ncu --set full (%s); measured %s; '
+                        'algorithmic %s' % (tinfo['source'], tinfo['dram_bytes_per_launch'], tinfo['algorithmic_bytes_per_launch']))
     # t-process forward scan against the HBM roofline: the training shape (B = 32) is launch-bound, so the scan is also
     # timed alone on a batch far larger than L2 (16384 sequences = 1.03 GB of latents), CUDA events on the launch stream
     scan = None
@@ -554,7 +552,7 @@ def main():
                                  launches_per_step, 'off: --no_graph' if args.no_graph else 'on'),
         'strong_scaling': strong,
         'ms_per_step_eager': ms_train_eager / steps,
-        'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_tap_kernel (tcgen05 implicit GEMM, fwd + dgrad launches)',
+        'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_line_kernel (line-tile tcgen05 implicit GEMM, fwd + dgrad launches)',
                      'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                      'frac': (achieved / peak_tf) if achieved else None,
                      'frac_burst': (achieved / peak_burst) if achieved else None,
@@ -572,6 +570,15 @@ def main():
                                            'avg_launch_us': 1e3 * conv['total_ms'] / max(conv['launches'], 1),
                                            'what': 'per-launch CUDA-event spans of an EAGER step (round-1 method): the events break the '
                                                    'programmatic-dependent-launch overlap and the 14x14 layers are host-launch bound'}},
+        'roofline_wgrad': (lambda w: {'bound': 'tensor', 'kernel': 'conv3x3_wgrad_line_kernel (line-tile tcgen05 wgrad, one launch per coupling)',
+                                        'achieved': fwd_flops * steps / (w['total_ms'] * 1e-3) / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                                        'frac': fwd_flops * steps / (w['total_ms'] * 1e-3) / 1e12 / peak_tf,
+                                        'frac_burst': fwd_flops * steps / (w['total_ms'] * 1e-3) / 1e12 / peak_burst,
+                                        'launches': w['launches'], 'ms_per_step': w['total_ms'] / steps,
+                                        'how': 'per-launch CUDA-event spans of the eager step (a wgrad launch is 130-480 us: the events cost nothing); '
+                                               'algorithmic FLOPs = those of the forward convolutions',
+                                        'ncu': 'profiles/r02_wgrad_line_ncu_summary.txt: tensor pipe active 86.5 %'}
+                           if w['total_ms'] > 0 else None)(prof['conv3x3_wgrad']),
         'roofline_process_scan': scan,
         'kernel_time_ms_per_step': {k: v['total_ms'] / steps for k, v in prof.items()},
         'clocks': sampler.summary() if sampler else None,

@@ -1443,7 +1443,8 @@ static int launch_conv(const void* in, const void* w, const float* bias, int bia
                        const void* a2, void* out, const SlabGeom& g, cudaStream_t st) {
   const int G = g.P <= TILE_M ? TILE_M / g.P : 1;
   const long long n_lines = static_cast<long long>((g.N + G - 1) / G) * g.H;
-  const bool line = g.P <= TILE_M && (g_conv_variant == 2 || (g_conv_variant == 0 && (n_lines >= 3ll * num_sms() || tap_stages(g, MODE) < 2)));
+  const bool line = g.P <= TILE_M && g.P % 8 == 0 &&
+                    (g_conv_variant == 2 || (g_conv_variant == 0 && (n_lines >= 3ll * num_sms() || tap_stages(g, MODE) < 2)));
   if (line) return launch_conv_line_ns<MODE, line_ns(MODE)>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
   return launch_conv_tap<MODE>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
 }
@@ -1526,7 +1527,7 @@ int bruno_conv3x3_wgrad_batched(const void* x_slab, const void* g_slab, float* d
   BRUNO_REQUIRE(x_slab && g_slab && dW && db && L > 0 && N > 0 && H > 0 && W > 0, "bruno_conv3x3_wgrad: bad arguments");
   BRUNO_REQUIRE(aligned16(x_slab) && aligned16(g_slab) && aligned16(dW) && aligned16(db), "bruno_conv3x3_wgrad: alignment");
   const SlabGeom g = slab_geom(N, H, W);
-  if (g_conv_variant != 1 && g.P <= TILE_M) {                   // line-tile kernel (the per-tap one: wide images / debug)
+  if (g_conv_variant != 1 && g.P <= TILE_M && g.P % 8 == 0) {   // line-tile kernel (the per-tap one: odd pitches, wide images, debug)
     static OncePerDevice once_line;
     once_line.run([&] {
       cudaFuncSetAttribute(conv3x3_wgrad_line_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -4,8 +4,8 @@
 // (16-byte chunk j of buffer row R lives at chunk j ^ (R & 7)), so a contiguous run of rows can be brought into shared
 // memory with ONE 1-D bulk async copy and used directly as a K-major SW128 tcgen05 operand.
 //
-// Zero padding is part of the layout: images are laid out with a row pitch of P = round_up(W + 1, 8) (at least one shared
-// zero column between the right edge of a line and the left edge of the next; a multiple of 8 so that every image line
+// Zero padding is part of the layout: images are laid out with a row pitch of P = slab_pitch(W) >= W + 1 (at least one shared
+// zero column between the right edge of a line and the left edge of the next; normally a multiple of 8 so that every image line
 // starts at the same swizzle phase and a line can be copied to any 8-row-aligned place in shared memory -- the line-tile
 // convolution kernel gathers one line of several images into one 128-row MMA tile) and H + 1 lines per image (the zero
 // line above image n is the zero line below image n - 1).
@@ -32,10 +32,17 @@ struct SlabGeom {
   int rows;       // total buffer rows
 };
 
+// Row pitch: W + 1 rounded up to a multiple of 8 (what the line-tile kernels need) unless that wastes more than a quarter
+// of the rows (W = 16 -> 24, W = 8 -> 16: such widths keep the exact pitch W + 1 and run the per-tap kernels).
+__host__ __device__ inline int slab_pitch(int W) {
+  const int p8 = ((W + 1 + 7) / 8) * 8;
+  return 4 * p8 <= 5 * (W + 1) ? p8 : W + 1;
+}
+
 __host__ __device__ inline SlabGeom slab_geom(int N, int H, int W) {
   SlabGeom g;
   g.N = N; g.H = H; g.W = W;
-  g.P = ((W + 1 + 7) / 8) * 8;
+  g.P = slab_pitch(W);
   g.IMG = (H + 1) * g.P;
   g.HALO = ((g.P + 1 + 7) / 8) * 8;
   g.data_rows = N * g.IMG;

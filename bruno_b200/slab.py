@@ -11,7 +11,8 @@ TILE_M = 128
 class SlabGeom(object):
     def __init__(self, N, H, W):
         self.N, self.H, self.W = N, H, W
-        self.P = ((W + 1 + 7) // 8) * 8
+        p8 = ((W + 1 + 7) // 8) * 8
+        self.P = p8 if 4 * p8 <= 5 * (W + 1) else W + 1          # csrc/slab.cuh: slab_pitch
         self.IMG = (H + 1) * self.P
         self.HALO = ((self.P + 1 + 7) // 8) * 8
         self.data_rows = N * self.IMG

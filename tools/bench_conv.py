@@ -21,6 +21,7 @@ _lib.call('bruno_conv_wn_pack', V.cuda(), torch.ones(1, 64, device='cuda'), wf, 
 bias = torch.zeros(64, device='cuda')
 REP = 40
 lib = _lib.load()
+if os.environ.get('BRUNO_CONV_VARIANT'): lib.bruno_debug_conv_variant(int(os.environ['BRUNO_CONV_VARIANT']))
 
 
 def smi():

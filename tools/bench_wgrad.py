@@ -6,7 +6,8 @@ from bruno_b200 import _lib, slab
 lib = _lib.load()
 if len(sys.argv) > 1: lib.bruno_debug_conv_variant(int(sys.argv[1]))
 L = 16
-for (N, H, W) in ((640, 28, 28), (640, 14, 14)):
+shapes = [tuple(int(v) for v in a.split(',')) for a in sys.argv[2:]] or [(640, 28, 28), (640, 14, 14)]
+for (N, H, W) in shapes:
     xs = slab.alloc_slabs(L, N, H, W, 'cuda'); gs = slab.alloc_slabs(L, N, H, W, 'cuda')
     xs.random_(0, 2); gs.random_(0, 2)
     dW = torch.zeros(L, 3, 3, 64, 64, device='cuda'); db = torch.zeros(L, 64, device='cuda')
