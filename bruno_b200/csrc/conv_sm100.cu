@@ -457,29 +457,40 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
   constexpr bool HAS_BIAS = MODE == MODE_ELU || MODE == MODE_RES_ELU || MODE == MODE_LINEAR;
   if (threadIdx.x == 0) trace_at(trace_buf, 0, 8);                       // kernel entry
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < LT_MAX_STAGES; ++s) {
-      mbar_init(&cs->full[s], 1);
-      mbar_init(&cs->empty[s], 1);
+  // barriers initialised by five threads of different warps in parallel (41 serial mbarrier.init in one thread were ~800
+  // cycles of every launch's prologue)
+  {
+    const int t = threadIdx.x;
+    if (t == 0) {
+      for (int i = 0; i < LT_MAX_STAGES; ++i) {
+        mbar_init(&cs->full[i], 1);
+        mbar_init(&cs->empty[i], 1);
+      }
+      mbar_init(&cs->wbar, 1);
+      fence_mbar_init();
+    } else if (t == 32) {
+      for (int i = 0; i < LT_SLOTS; ++i) mbar_init(&cs->tfull[i], 1);
+      fence_mbar_init();
+    } else if (t == 64) {
+      for (int i = 0; i < LT_SLOTS; ++i) mbar_init(&cs->tempty[i], FWD_EPI_WARPS / 2);
+      fence_mbar_init();
+    } else if (t == 96) {
+      for (int i = 0; i < LT_MAX_NB; ++i) {
+        mbar_init(&cs->auxfull[i], 1);
+        mbar_init(&cs->outready[i], FWD_EPI_WARPS * 16);
+        mbar_init(&cs->outfree[i], 1);
+      }
+      fence_mbar_init();
+    } else if (t == 128) {
+      for (int i = 0; i < LT_GATES; ++i) mbar_init(&cs->go[i], 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&cs->aux2full[i], 1);
+        mbar_init(&cs->aux2free[i], FWD_EPI_WARPS * 16);
+      }
+      fence_mbar_init();
     }
-    for (int a = 0; a < LT_SLOTS; ++a) {
-      mbar_init(&cs->tfull[a], 1);
-      mbar_init(&cs->tempty[a], FWD_EPI_WARPS / 2);
-    }
-    for (int a = 0; a < LT_MAX_NB; ++a) {
-      mbar_init(&cs->auxfull[a], 1);
-      mbar_init(&cs->outready[a], FWD_EPI_WARPS * 16);
-      mbar_init(&cs->outfree[a], 1);
-    }
-    for (int a = 0; a < LT_GATES; ++a) mbar_init(&cs->go[a], 1);
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&cs->aux2full[a], 1);
-      mbar_init(&cs->aux2free[a], FWD_EPI_WARPS * 16);
-    }
-    mbar_init(&cs->wbar, 1);
-    fence_mbar_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 128) cs->bias[threadIdx.x - 64] = HAS_BIAS ? bias[threadIdx.x - 64] : 0.f;
+  if (threadIdx.x >= 192 && threadIdx.x < 256) cs->bias[threadIdx.x - 192] = HAS_BIAS ? bias[threadIdx.x - 192] : 0.f;
   // Rows of a stage that no copy ever writes stay zero for the whole kernel: the guards, the padding columns past W + 1
   // of every image segment (only the rows a line's neighbours can read are copied) and the rows past the last segment.
   for (int i = threadIdx.x; i < NS * (LT_STAGE_BYTES / 16); i += blockDim.x) reinterpret_cast<uint4*>(slabs)[i] = make_uint4(0, 0, 0, 0);
@@ -514,19 +525,23 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
     if (lane == 0) {
       mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
       bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);
-      asm volatile("griddepcontrol.wait;" ::: "memory");
-      trace_at(trace_buf, 0, 10);                                        // previous grid complete
       LineWalk w(g.H, t0, t1);
       int ii = 0;
-      while (w.next()) {
+      bool waited = false;                                               // the segment walk / addresses of the first tile are
+      while (w.next()) {                                                 // computed BEFORE waiting for the previous grid
         for (int yi = w.yi0(); yi <= w.yi1(); ++yi, ++ii) {
           const int s = ii % NS;
-          mbar_wait(&cs->empty[s], ((ii / NS) & 1) ^ 1);
           const int geff = min(G, g.N - w.j * G);
-          mbar_arrive_expect_tx(&cs->full[s], static_cast<uint32_t>(geff) * in_bytes + (geff < G ? seg_bytes : 0u));
-          trace_at(trace_buf, ii, 0);
           uint8_t* dst = slabs + s * LT_STAGE_BYTES + LT_GUARD * SLAB_ROW_BYTES;
           const uint8_t* src = in + line_off(w.j * G, yi);
+          if (!waited) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            trace_at(trace_buf, 0, 10);                                  // previous grid complete
+            waited = true;
+          }
+          mbar_wait(&cs->empty[s], ((ii / NS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&cs->full[s], static_cast<uint32_t>(geff) * in_bytes + (geff < G ? seg_bytes : 0u));
+          trace_at(trace_buf, ii, 0);
           for (int i = 0; i < geff; ++i, dst += seg_bytes, src += img_bytes) bulk_g2s(dst, src, in_bytes, &cs->full[s]);
           // the segment after the last image of a partial group holds that image's right-hand neighbours: zeros (the
           // slab's leading guard rows), whatever an earlier full group left there
