@@ -1447,10 +1447,12 @@ static int launch_conv_line_ns(const void* in, const void* w, const float* bias,
   return check_launch("conv3x3_line_kernel");
 }
 
-// 0 = automatic: the line-tile kernel when every CTA gets at least a few output lines (its per-CTA set-up -- 704 threads,
-// 8 TMEM slots, zeroed stages -- and the halo lines of a range that starts / ends inside an image do not pay off on a
-// 40-image few-shot episode: 1.61 vs 1.33 ms per episode), else the per-tap kernel; 1 = per-tap kernel (also the fallback
-// for a row pitch P > 128); 2 = line-tile kernel
+// 0 = automatic: the line-tile kernel when every CTA gets at least 8 output lines, else the per-tap kernel.  A CTA range
+// that starts / ends inside an image pays two halo input lines, and the line kernel's set-up (736 threads, 8 TMEM slots,
+// zeroed stages) is longer: measured cross-over (tools/bench_conv.py, both kernels, same build) 320x28x28 (15 lines per CTA)
+// 18.7 vs 22.0 us, 160x28x28 / 640x14x14 (7.6) a tie in modes 0-2 and 14.6 vs 12.8 us in MODE_ADD_MUL, 320x14x14 (3.8)
+// 10.0 vs 9.0 us, the 40-image few-shot episode 1.61 vs 1.33 ms per episode.
+// 1 = per-tap kernel (also the fallback for a row pitch that is not a multiple of 8 or exceeds 128); 2 = line-tile kernel
 static int g_conv_variant = 0;
 
 template <int MODE>
@@ -1459,7 +1461,7 @@ static int launch_conv(const void* in, const void* w, const float* bias, int bia
   const int G = g.P <= TILE_M ? TILE_M / g.P : 1;
   const long long n_lines = static_cast<long long>((g.N + G - 1) / G) * g.H;
   const bool line = g.P <= TILE_M && g.P % 8 == 0 &&
-                    (g_conv_variant == 2 || (g_conv_variant == 0 && (n_lines >= 3ll * num_sms() || tap_stages(g, MODE) < 2)));
+                    (g_conv_variant == 2 || (g_conv_variant == 0 && (n_lines >= 8ll * num_sms() || tap_stages(g, MODE) < 2)));
   if (line) return launch_conv_line_ns<MODE, line_ns(MODE)>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
   return launch_conv_tap<MODE>(in, w, bias, bias_img_stride, a1, a2, out, g, st);
 }
