@@ -523,6 +523,7 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
   if (warp == 0) {
     // ===== producer: one input line of G images per stage = G bulk copies of P rows =====
     if (lane == 0) {
+      const uint64_t pol_first = l2_policy_evict_first();
       mbar_arrive_expect_tx(&cs->wbar, W_BYTES);
       bulk_g2s(wsm, wpack, W_BYTES, &cs->wbar);
       LineWalk w(g.H, t0, t1);
@@ -542,7 +543,13 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
           mbar_wait(&cs->empty[s], ((ii / NS) & 1) ^ 1);
           mbar_arrive_expect_tx(&cs->full[s], static_cast<uint32_t>(geff) * in_bytes + (geff < G ? seg_bytes : 0u));
           trace_at(trace_buf, ii, 0);
-          for (int i = 0; i < geff; ++i, dst += seg_bytes, src += img_bytes) bulk_g2s(dst, src, in_bytes, &cs->full[s]);
+          // MODE_RES_ELU / MODE_ADD_MUL: this launch is the last reader of its input slab for now (c3's input u is next needed
+          // in the backward pass, the gradient g2 never again): evict first, keep L2 for the slabs the next launches re-read
+          if (MODE == MODE_RES_ELU || MODE == MODE_ADD_MUL) {
+            for (int i = 0; i < geff; ++i, dst += seg_bytes, src += img_bytes) bulk_g2s_hint(dst, src, in_bytes, &cs->full[s], pol_first);
+          } else {
+            for (int i = 0; i < geff; ++i, dst += seg_bytes, src += img_bytes) bulk_g2s(dst, src, in_bytes, &cs->full[s]);
+          }
           // the segment after the last image of a partial group holds that image's right-hand neighbours: zeros (the
           // slab's leading guard rows), whatever an earlier full group left there
           if (geff < G) bulk_g2s(dst, in, seg_bytes, &cs->full[s]);
@@ -749,6 +756,7 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
     // copy costs its issuing thread ~110 cycles -- 8 segments per tile at 14x14 are most of a tile period -- so the addend
     // stream of MODE_ADD_MUL has its own thread and buffers, below.) =====
     if (mode_has_aux1(MODE) && lane == 0) {
+      const uint64_t pol_first = l2_policy_evict_first();
       asm volatile("griddepcontrol.wait;" ::: "memory");
       LineWalk w(g.H, t0, t1);
       int it = 0;
@@ -760,7 +768,10 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
           mbar_arrive_expect_tx(&cs->auxfull[b], static_cast<uint32_t>(geff) * px_bytes);
           size_t off = line_off(w.j * G, yo) + SLAB_ROW_BYTES;          // pixel rows 1 .. W of each segment
           uint32_t so = b * TILE_BYTES + SLAB_ROW_BYTES;
-          for (int i = 0; i < geff; ++i, off += img_bytes, so += seg_bytes) bulk_g2s(stage1 + so, aux1 + off, px_bytes, &cs->auxfull[b]);
+          // aux1 is a saved activation: after this launch it is not read again (backward) or not before the backward pass
+          // (the skip tile of MODE_RES_ELU) -- it must not evict the slabs the next launches re-read from L2
+          for (int i = 0; i < geff; ++i, off += img_bytes, so += seg_bytes)
+            bulk_g2s_hint(stage1 + so, aux1 + off, px_bytes, &cs->auxfull[b], pol_first);
         }
       }
     }
@@ -768,6 +779,7 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
     // ===== addend loader (MODE_ADD_MUL): tile it goes to the buffer of epilogue group it & 1 as soon as that group has
     // copied the addend of its previous tile (it - 2) to registers =====
     if (mode_has_aux2(MODE) && lane == 0) {
+      const uint64_t pol_first = l2_policy_evict_first();
       asm volatile("griddepcontrol.wait;" ::: "memory");
       LineWalk w(g.H, t0, t1);
       int it = 0;
@@ -779,13 +791,15 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
           mbar_arrive_expect_tx(&cs->aux2full[b], static_cast<uint32_t>(geff) * px_bytes);
           size_t off = line_off(w.j * G, yo) + SLAB_ROW_BYTES;
           uint32_t so = b * TILE_BYTES + SLAB_ROW_BYTES;
-          for (int i = 0; i < geff; ++i, off += img_bytes, so += seg_bytes) bulk_g2s(stage2 + so, aux2 + off, px_bytes, &cs->aux2full[b]);
+          for (int i = 0; i < geff; ++i, off += img_bytes, so += seg_bytes)   // last reader of the addend slab
+            bulk_g2s_hint(stage2 + so, aux2 + off, px_bytes, &cs->aux2full[b], pol_first);
         }
       }
     }
   } else if (warp == 2 + FWD_EPI_WARPS + 1) {
     // ===== output drain: G bulk stores per tile =====
     if (lane == 0) {
+      const uint64_t pol_last = l2_policy_evict_last();
       LineWalk w(g.H, t0, t1);
       int it = 0;
       while (w.next()) {
@@ -795,7 +809,8 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
           mbar_wait(&cs->outready[b], (it / NB) & 1);
           uint8_t* dst = out + line_off(w.j * G, yo) + SLAB_ROW_BYTES;   // pixel rows 1 .. W of each segment
           const uint8_t* src = stage1 + b * TILE_BYTES + SLAB_ROW_BYTES;
-          for (int i = 0; i < geff; ++i, dst += img_bytes, src += seg_bytes) bulk_s2g(dst, src, px_bytes);
+          for (int i = 0; i < geff; ++i, dst += img_bytes, src += seg_bytes)   // the next launch(es) re-read the output slab
+            bulk_s2g_hint(dst, src, px_bytes, pol_last);
           bulk_commit();
           trace_at(trace_buf, it, 5);
           bulk_wait_read<0>();                // the store has read its staging buffer (a few hundred cycles; the next
