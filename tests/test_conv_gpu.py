@@ -42,7 +42,7 @@ def _setup(N, H, W, seed):
 
 
 @pytest.mark.parametrize('N,H,W', [(3, 28, 28), (5, 14, 14), (2, 32, 32), (1, 16, 16), (40, 14, 14), (1, 15, 15), (11, 7, 7),
-                                   (9, 1, 5), (2, 3, 39), (13, 31, 31), (3, 5, 127)])
+                                   (9, 1, 5), (2, 3, 39), (13, 31, 31), (3, 5, 127), (20, 1, 7), (5, 2, 15), (33, 3, 7)])
 def test_conv3x3_all_epilogues(N, H, W):
     from bruno_b200 import _lib, slab
     V, gain, bias, x, a1, a2, wf, wbw = _setup(N, H, W, seed=N * H)
@@ -82,7 +82,8 @@ def test_conv3x3_all_epilogues(N, H, W):
         lib.bruno_debug_conv_variant(0)
 
 
-@pytest.mark.parametrize('N,H,W', [(3, 28, 28), (5, 14, 14), (2, 32, 32), (300, 14, 14)])
+@pytest.mark.parametrize('N,H,W', [(3, 28, 28), (5, 14, 14), (2, 32, 32), (300, 14, 14), (20, 1, 7), (5, 2, 15), (33, 3, 7), (7, 5, 39),
+                                   (9, 16, 16)])
 def test_conv3x3_wgrad(N, H, W):
     from bruno_b200 import _lib, slab
     g = torch.Generator().manual_seed(7 + N)
