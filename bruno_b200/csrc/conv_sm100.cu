@@ -412,13 +412,17 @@ struct LineSmem {
 // Staging ring: NB buffers of one tile per stream (aux1 / output IN PLACE, aux2).  An aux tile is requested as soon as the
 // store of the tile NB back has read the buffer, i.e. NB - 1 tile periods before its epilogue needs it: with the HBM
 // latency at 2-3 tile periods, NB = 2 (one buffer per epilogue group) exposes it in every epilogue.
-// MODE_ADD_MUL: four input stages, two aux1 / output buffers and two addend buffers (one per epilogue group): an epilogue
+// NB must be a multiple of the number of epilogue groups (2): the groups wait on auxfull[it % NB] by phase PARITY, which is
+// only safe if consecutive users of one buffer are the same group -- with NB = 3 a buffer alternates between the groups,
+// a group that runs a tile ahead can reach the buffer while its previous phase is still open, its parity wait falls
+// through, and two epilogues share a buffer (observed: MODE_ADD_MUL at 640x28x28, where HBM-bound aux tiles land out of
+// order, failed on back-to-back launches with NB = 3 and only then).
+// MODE_ADD_MUL: three input stages, four aux1 / output buffers and two addend buffers (one per epilogue group): an epilogue
 // copies its addend tile to registers first thing and frees the buffer, so the addend of the group's next tile streams in
-// during the whole epilogue.  (Three input stages + three aux1 / output buffers also fit, but that combination -- and only
-// that one, only in this mode -- fails on back-to-back 640 x 28 x 28 launches for a reason not understood; every shipped
-// combination runs dependent 20-launch chains bit-identically to the per-tap kernel, tools/conv_chain.py.)
-__host__ __device__ constexpr int line_nb(int mode) { return mode_has_aux2(mode) ? 2 : (mode_has_aux1(mode) ? 4 : 2); }
-__host__ __device__ constexpr int line_ns(int mode) { return LT_MAX_STAGES; }
+// during the whole epilogue.
+__host__ __device__ constexpr int line_nb(int mode) { return mode_has_aux1(mode) ? 4 : 2; }
+__host__ __device__ constexpr int line_ns(int mode) { return mode_has_aux2(mode) ? 3 : LT_MAX_STAGES; }
+static_assert(line_nb(MODE_ADD_MUL) % 2 == 0 && line_nb(MODE_MUL) % 2 == 0 && line_nb(MODE_ELU) % 2 == 0, "see above");
 __host__ __device__ constexpr int line_stage_tiles(int mode) { return line_nb(mode) + (mode_has_aux2(mode) ? 2 : 0); }
 
 // This CTA's share [t, t1) of the output line tiles (linear index = image group * H + data line - 1), walked segment by
