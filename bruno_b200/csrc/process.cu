@@ -1475,9 +1475,11 @@ static int launch_fwd(const float* z, const float* mu0, const float* table, floa
   if constexpr (VEC == 4) {
     const int v = fwd_variant();
     // The running-state entry (s1 / s2 read and written back: the reference's step-by-step API, not a hot path) stays on
-    // the register-staged scan: the STATE instantiation of the ring kernel returned one wrong row in ~10 % of the runs
-    // of tests/test_process_gpu.py::test_forward_scan_variants_agree[1030-20-784-0.0-gp] (the sequence-at-once
-    // instantiation: 0 of 200, tools/dbg_proc_flaky.py); cause not found yet, so the default does not use it.
+    // the register-staged scan.  The STATE instantiation of the ring kernel returns ONE wrong row (the first row of one
+    // 4-row group, all steps) in ~20 % of launches when its z buffer is a freshly allocated copy, never when the buffer is
+    // reused -- independent of what ran before, of device synchronisation and of the output buffer
+    // (tools/dbg_proc_flaky.py).  The sequence-at-once instantiation (the product path) shows no such rows in any of these
+    // set-ups (NaN-prefilled outputs, 150 launches per case).  Cause not found; the default does not use the instantiation.
     if ((v == 0 && s1 == nullptr) || v >= 10) {
       int rc;
       switch (v) {
