@@ -903,16 +903,6 @@ __global__ void conv_epilogue_f32_kernel(float* __restrict__ acc, const float* _
   }
 }
 
-// zero the rows of a slab that heads_coupling_bwd does not write (padding positions), so the slab invariant holds
-__global__ void slab_zero_padding_kernel(uint8_t* __restrict__ slab, SlabGeom g) {
-  const int total = g.NT * TILE_M * 8;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int data_row = i >> 3, j = i & 7;
-    if (!slab_row_is_pixel(data_row, g))
-      *reinterpret_cast<uint4*>(slab + slab_chunk_off(static_cast<size_t>(g.HALO) + data_row, j)) = make_uint4(0, 0, 0, 0);
-  }
-}
-
 }  // namespace bruno
 
 using namespace bruno;
@@ -1049,7 +1039,9 @@ int bruno_heads_coupling_bwd_cond(const float* x, const void* h_slab, const floa
   once.run([&] {
     cudaFuncSetAttribute(heads_coupling_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   });
-  slab_zero_padding_kernel<<<148 * 4, 256, 0, st>>>(static_cast<uint8_t*>(g_slab), g);
+  // (no zeroing of g_slab's padding rows here: slabs are zero-initialised once by the caller and every writer -- this
+  // kernel, the convolution epilogues -- either skips the padding rows or writes zeros there; bruno_sm100.h, slab contract.
+  // The per-call slab_zero_padding_kernel launch cost 0.1 ms per training step.)
   if (C <= 4 && !dlabel_s) {
     // eight lanes per pixel, head-weight gradients in registers (see heads_coupling_bwd8_kernel)
     int nb = 0;
