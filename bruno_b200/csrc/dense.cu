@@ -335,7 +335,7 @@ static Workspace sk_workspace(cudaStream_t st) {
 }
 
 #ifndef BRUNO_NO_DEBUG
-static int g_gemm_variant = 1;   // 0: CUDA-core SGEMM, 1: tcgen05 3xTF32 (gemm_tf32.cu)
+static int g_gemm_variant = 1;   // 0: CUDA-core SGEMM, 1: tcgen05 3xTF32 (gemm_tf32.cu), 2: the same with the workspace split-K fix-up
 #else
 constexpr int g_gemm_variant = 1;
 #endif
@@ -369,10 +369,10 @@ static int gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, 
   const bool vec_ok = aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0 && K % 4 == 0 &&
                       (ta ? M % 4 == 0 : true) && (tb ? true : N % 4 == 0) && (!ep.a_kscale || aligned16(ep.a_kscale));
   const Workspace wk = sk_workspace(st);
-  if (vec_ok && g_gemm_variant == 1 && wk) {
+  if (vec_ok && g_gemm_variant >= 1 && wk) {
     int taken = 0;
     const int rc = gemm_tf32x3(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, ep, wk.ws, SK_WS_FLOATS, wk.tickets, SK_MAX_TILES,
-                               wk.sms, st, &taken);
+                               wk.sms, g_gemm_variant == 1, st, &taken);
     if (taken) return rc;
   }
   if (vec_ok) {
@@ -695,7 +695,8 @@ size_t bruno_coupling_dense_bwd_ws_floats(int N, int D, int U) {
 #ifndef BRUNO_NO_DEBUG
 int bruno_debug_gemm_variant(int variant) {
   if (variant < 0) return g_gemm_variant;
-  BRUNO_REQUIRE(variant == 0 || variant == 1, "bruno_debug_gemm_variant: 0 (CUDA-core SGEMM) or 1 (tcgen05 3xTF32)");
+  BRUNO_REQUIRE(variant >= 0 && variant <= 2,
+                "bruno_debug_gemm_variant: 0 (CUDA-core SGEMM), 1 (tcgen05 3xTF32, cluster split-K) or 2 (tcgen05, workspace split-K)");
   g_gemm_variant = variant;
   return BRUNO_OK;
 }

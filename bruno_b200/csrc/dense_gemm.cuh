@@ -24,11 +24,13 @@ __device__ __forceinline__ float gemm_epilogue_value(float v, int n, const GemmE
   return v;
 }
 
-// tcgen05 path.  `ws` / `tickets`: split-K workspace (>= ws_floats floats) and zeroed ticket counters (>= max_tiles).
+// tcgen05 path.  `cluster`: the split-K CTAs of a tile are one thread-block cluster and reduce through peer shared memory
+// (needs no workspace).  Otherwise / if the cluster launch is refused: `ws` / `tickets` = split-K workspace (>= ws_floats
+// floats) and zeroed ticket counters (>= max_tiles), both may be null (un-split then).
 // Returns BRUNO_OK, or a negative code; *taken = 0 when the shape is not eligible (caller falls back to the SIMT kernel).
 int gemm_tf32x3(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                const GemmEpi& ep, float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, cudaStream_t st,
-                int* taken);
+                const GemmEpi& ep, float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster,
+                cudaStream_t st, int* taken);
 
 void gemm_tf32x3_set_trace(long long* device_buffer);
 

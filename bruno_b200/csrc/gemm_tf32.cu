@@ -16,6 +16,7 @@
 #include "dense_gemm.cuh"
 #include <stdlib.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "ptx.cuh"
@@ -83,52 +84,76 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int N, int a_mn_major, int b_m
 template <bool MNMAJOR, int ROWS>
 struct OperandTile {
   float4 v[8];
-  uint32_t mask;    // bit i: element i is stored
+  const float* p0;   // this thread's element 0 of the K tile at k = 0
+  size_t istride;    // floats from element i to element i + 1
+  uint32_t base;     // shared-memory offset of element 0 before the per-element swizzle term
+  uint32_t mask;     // bit i: element i is inside the operand (loaded and stored)
+  int kthr;          // K index of this thread's data inside a tile (element 0)
 
-  __device__ __forceinline__ static uint32_t offset(int i, int tid) {
-    const int w = tid >> 5, l = tid & 31;
+  // Everything that does not depend on the K tile is computed once per thread (the loaders are instruction-latency
+  // bound: four warps work on a tile and nothing else hides their dependent chains).
+  __device__ __forceinline__ void init(const float* __restrict__ src, int ld, int rows_total, int r0, int tid) {
+    const int w = tid >> 5, l = tid & 31, c = l & 7;
+    mask = 0;
     if (!MNMAJOR) {
-      const int r = w * 32 + i * 4 + (l >> 3), c = l & 7;
-      return static_cast<uint32_t>(r * 128 + ((c ^ (r & 7)) << 4));
+      const int rb = w * 32 + (l >> 3);                       // element i: smem row rb + 4 i
+      p0 = src + static_cast<size_t>(r0 + rb) * ld + 4 * c;
+      istride = static_cast<size_t>(4) * ld;
+      base = static_cast<uint32_t>(rb * 128 + ((c ^ (l >> 3)) << 4));   // (rb + 4 i) & 7 = (l >> 3) ^ 4 (i & 1)
+      kthr = 4 * c;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (rb + 4 * i < ROWS && r0 + rb + 4 * i < rows_total) mask |= 1u << i;
+    } else {
+      const int a = l >> 3;
+      p0 = src + static_cast<size_t>(w * 8) * ld + r0 + a * 32 + 4 * c;
+      istride = static_cast<size_t>(ld);
+      base = static_cast<uint32_t>(a * 4096 + w * 8 * 128 + (c << 4));    // k & 3 = i & 3 flips chunk bits 1..2
+      kthr = w * 8;
+      if (a * 32 < ROWS && r0 + a * 32 + 4 * c < rows_total) mask = 0xFFu;
     }
-    const int k = w * 8 + i, a = l >> 3, c = l & 7;
-    return static_cast<uint32_t>(a * 4096 + k * 128 + (((((c >> 1) ^ (k & 3)) << 1) | (c & 1)) << 4));
   }
 
-  __device__ __forceinline__ void fetch(const float* __restrict__ src, int ld, int rows_total, int K, int r0, int k0,
-                                        const float* __restrict__ kscale, int tid) {
-    const int w = tid >> 5, l = tid & 31;
-    mask = 0;
+  __device__ __forceinline__ uint32_t offset(int i) const {
+    if (!MNMAJOR) return (base ^ (static_cast<uint32_t>(i & 1) << 6)) + static_cast<uint32_t>(i) * 512u;
+    return (base ^ (static_cast<uint32_t>(i & 3) << 5)) + static_cast<uint32_t>(i) * 128u;
+  }
+
+  __device__ __forceinline__ void fetch(int ld, int K, int k0, const float* __restrict__ kscale) {
+    if (!MNMAJOR) {
+      const float* p = p0 + k0;
+      const bool kin = k0 + kthr < K;
+      if (mask == 0xFFu && kin) {                             // full tile: eight independent loads, no predicates
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!MNMAJOR) {
-        const int r = w * 32 + i * 4 + (l >> 3), c = l & 7;
-        const int gr = r0 + r, gk = k0 + 4 * c;
-        if (r < ROWS && gr < rows_total) {
-          mask |= 1u << i;
-          if (gk < K) v[i] = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(gr) * ld + gk));
-        }
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(p + i * istride));
       } else {
-        const int k = w * 8 + i, a = l >> 3, c = l & 7;
-        const int gr = r0 + a * 32 + 4 * c, gk = k0 + k;
-        if (a * 32 < ROWS && gr < rows_total) {
-          mask |= 1u << i;
-          if (gk < K) v[i] = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(gk) * ld + gr));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (((mask >> i) & 1u) && kin) v[i] = __ldg(reinterpret_cast<const float4*>(p + i * istride));
         }
       }
-    }
-    if (kscale) {
+      if (kscale && kin) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(kscale + k0 + kthr));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (!MNMAJOR) {
-          const int gk = k0 + 4 * (l & 7);
-          if (gk < K) {
-            const float4 s = __ldg(reinterpret_cast<const float4*>(kscale + gk));
-            v[i].x *= s.x; v[i].y *= s.y; v[i].z *= s.z; v[i].w *= s.w;
-          }
-        } else {
-          const int gk = k0 + w * 8 + i;
+        for (int i = 0; i < 8; ++i) { v[i].x *= s.x; v[i].y *= s.y; v[i].z *= s.z; v[i].w *= s.w; }
+      }
+    } else {
+      const float* p = p0 + static_cast<size_t>(k0) * ld;
+      if (mask == 0xFFu && k0 + TG_BK <= K) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(p + i * istride));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (mask && k0 + kthr + i < K) v[i] = __ldg(reinterpret_cast<const float4*>(p + i * istride));
+        }
+      }
+      if (kscale) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int gk = k0 + kthr + i;
           const float s = gk < K ? __ldg(kscale + gk) : 0.f;
           v[i].x *= s; v[i].y *= s; v[i].z *= s; v[i].w *= s;
         }
@@ -136,13 +161,15 @@ struct OperandTile {
     }
   }
 
-  __device__ __forceinline__ void store(uint32_t hi_base, uint32_t lo_base, int tid) const {
+  __device__ __forceinline__ void store(uint32_t hi_base, uint32_t lo_base) const {
+    if (mask == 0xFFu) {                                      // straight-line: the eight splits interleave
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (mask & (1u << i)) {
-        const uint32_t off = offset(i, tid);
-        split_store(hi_base + off, lo_base + off, v[i]);
-      }
+      for (int i = 0; i < 8; ++i) split_store(hi_base + offset(i), lo_base + offset(i), v[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (mask & (1u << i)) split_store(hi_base + offset(i), lo_base + offset(i), v[i]);
+    }
   }
 };
 
@@ -174,7 +201,7 @@ template <bool TA, bool TB, int BN>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                    float* __restrict__ C, int ldc, GemmEpi ep, int kchunk, float* __restrict__ ws, unsigned* __restrict__ tickets,
-                   long long* trace_buf) {
+                   int cluster_reduce, long long* trace_buf) {
   constexpr int B_TILE_BYTES = BN * TG_BK * 4;
   constexpr int STAGE_BYTES = 2 * TG_TILE_BYTES + 2 * B_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
   extern __shared__ uint8_t tg_smem_raw[];
@@ -201,6 +228,7 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch_dependents();      // the next launch may set itself up; its griddepcontrol.wait sees this grid complete
   const uint32_t tmem = cs->tmem_base;
   const uint32_t stage0 = smem_u32(smem);
 
@@ -214,24 +242,27 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
     // the tensor core works on this stage and while the group waits for it to drain.
     OperandTile<TA, TG_BM> ta_;
     OperandTile<!TB, BN> tb_;
+    ta_.init(A, lda, M, m0, tid);
+    tb_.init(B, ldb, N, n0, tid);
     int kt = kt0 + grp;
+    griddep_wait();                                           // first global read of this thread
     if (kt < kt1) {
-      ta_.fetch(A, lda, M, K, m0, kt * TG_BK, ep.a_kscale, tid);
-      tb_.fetch(B, ldb, N, K, n0, kt * TG_BK, nullptr, tid);
+      ta_.fetch(lda, K, kt * TG_BK, ep.a_kscale);
+      tb_.fetch(ldb, K, kt * TG_BK, nullptr);
     }
     uint32_t j = 0;
     for (; kt < kt1; kt += TG_STAGES, ++j) {
       mbar_wait(&cs->empty[grp], (j & 1u) ^ 1u);
       if (tid == 0) gtrace(trace_buf, kt - kt0, 0);
-      ta_.store(st, st + TG_TILE_BYTES, tid);
-      tb_.store(st + 2 * TG_TILE_BYTES, st + 2 * TG_TILE_BYTES + B_TILE_BYTES, tid);
+      ta_.store(st, st + TG_TILE_BYTES);
+      tb_.store(st + 2 * TG_TILE_BYTES, st + 2 * TG_TILE_BYTES + B_TILE_BYTES);
       if (tid == 0) gtrace(trace_buf, kt - kt0, 1);
       fence_proxy_async_smem();
       mbar_arrive(&cs->full[grp]);
       if (tid == 0) gtrace(trace_buf, kt - kt0, 2);
       if (kt + TG_STAGES < kt1) {
-        ta_.fetch(A, lda, M, K, m0, (kt + TG_STAGES) * TG_BK, ep.a_kscale, tid);
-        tb_.fetch(B, ldb, N, K, n0, (kt + TG_STAGES) * TG_BK, nullptr, tid);
+        ta_.fetch(lda, K, (kt + TG_STAGES) * TG_BK, ep.a_kscale);
+        tb_.fetch(ldb, K, (kt + TG_STAGES) * TG_BK, nullptr);
       }
     }
   } else {
@@ -275,17 +306,21 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
     __syncwarp();
   }
 
-  if (warp < TG_LOADER_WARPS) {
-    // ===== epilogue.  Warps 0..3 read their TMEM lane quarter 32 columns at a time and transpose it through shared
-    // memory (the ring is idle once `done` fired), so that a warp instruction writes 32 consecutive columns of one row.
-    // With split-K the tile goes to the workspace and the LAST CTA of the tile (ticket) reduces it with all 12 warps.
-    const int S = gridDim.z;
-    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    constexpr int NCH = BN / 32;
-    float* wt = ws + static_cast<size_t>(tile) * S * (TG_BM * BN);        // [z][row][BN]
+  // ===== epilogue.  Warps 0..3 read their TMEM lane quarter 32 columns at a time and transpose it through shared memory
+  // (the ring is idle once `done` fired), so that a warp instruction handles 32 consecutive columns of one row.
+  // Split-K: the S CTAs of a tile are ONE THREAD-BLOCK CLUSTER (1, 1, S).  Each leaves its partial tile in its own shared
+  // memory; after a cluster barrier CTA z adds, for its 1/S of the rows, the S partials in z order (deterministic) from
+  // the peers' shared memory (ld.shared::cluster), applies the epilogue and writes C: no partials in global memory, no
+  // fence / ticket round trip, every CTA shares the reduction.  (Round 1 wrote the partials to a workspace and let the
+  // last CTA of a tile -- ticket -- add them: half of the 15 us launch; that path stays for a launch without cluster.)
+  const int S = gridDim.z;
+  const bool loader_warp = warp < TG_LOADER_WARPS;
+  constexpr int NCH = BN / 32;
+  constexpr int TP = BN + 1;
+  float* T = reinterpret_cast<float*>(smem);
+  const int rows = min(TG_BM, M - m0);
+  if (loader_warp) {
     // phase A: warps 0..3 copy their TMEM lane quarter into a row-major shared tile (pitch BN + 1: conflict-free both ways)
-    float* T = reinterpret_cast<float*>(smem);
-    constexpr int TP = BN + 1;
     if (warp < 4) {
       mbar_wait(&cs->done, 0);
       tc_fence_after();
@@ -301,8 +336,61 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * TG_LOADER_WARPS) : "memory");
     if (threadIdx.x == 0) gtrace(trace_buf, 60, 5);
+  }
+  if (S > 1 && cluster_reduce) {
+    __syncwarp();
+    cluster_sync_all();                                       // every partial tile of the cluster is in place
+    if (loader_warp) {
+      const int rank = static_cast<int>(cluster_ctarank());   // = blockIdx.z: cluster (1, 1, S), gridDim.z = S
+      const int rows_per = (rows + S - 1) / S;
+      const int rb = rank * rows_per;
+      const int ntask = max(0, min(rows, rb + rows_per) - rb) * NCH;
+      uint32_t peer[TG_MAX_SPLIT];
+#pragma unroll
+      for (int z = 0; z < TG_MAX_SPLIT; ++z) peer[z] = mapa_shared(smem_u32(T), static_cast<uint32_t>(z < S ? z : 0));
+      with_act(ep.act, [&](auto act) {
+        constexpr int TU = 4;
+        for (int task0 = warp; task0 < ntask; task0 += TU * TG_LOADER_WARPS) {
+          float part[TU][TG_MAX_SPLIT], old[TU];
+#pragma unroll
+          for (int u = 0; u < TU; ++u) {
+            const int task = task0 + u * TG_LOADER_WARPS;
+            const int row = rb + task / NCH, ch = task % NCH;
+            const uint32_t off = static_cast<uint32_t>((row * TP + ch * 32 + lane) * 4);
+            const bool on = task < ntask && n0 + ch * 32 + lane < N;
+#pragma unroll
+            for (int z = 0; z < TG_MAX_SPLIT; ++z) part[u][z] = (on && z < S) ? ld_dsmem_f32(peer[z] + off) : 0.f;
+            old[u] = (on && ep.accumulate) ? C[static_cast<size_t>(m0 + row) * ldc + n0 + ch * 32 + lane] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < TU; ++u) {
+            const int task = task0 + u * TG_LOADER_WARPS;
+            const int row = rb + task / NCH, ch = task % NCH;
+            const int n = n0 + ch * 32 + lane;
+            if (task < ntask && n < N) {
+              const size_t o = static_cast<size_t>(m0 + row) * ldc + n;
+              float x = 0.f;
+#pragma unroll
+              for (int z = 0; z < TG_MAX_SPLIT; ++z) x += part[u][z];
+              if (ep.col_scale) x = __fmul_rn(x, ep.col_scale[n]);
+              if (ep.bias) x = __fadd_rn(x, ep.bias[n]);
+              if (ep.pre_out) ep.pre_out[o] = x;
+              x = act_apply<decltype(act)::value>(x);
+              if (ep.accumulate) x += old[u];
+              C[o] = x;
+            }
+          }
+        }
+      });
+      if (threadIdx.x == 0) gtrace(trace_buf, 60, 6);
+    }
+    __syncwarp();
+    cluster_sync_all();                                       // no CTA leaves while a peer still reads its tile
+    if (threadIdx.x == 0) gtrace(trace_buf, 63, 6);
+  } else if (loader_warp) {
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    float* wt = ws + static_cast<size_t>(tile) * S * (TG_BM * BN);        // [z][row][BN]
     // phase B: all 12 warps write rows (a warp instruction = 32 consecutive columns of one row)
-    const int rows = min(TG_BM, M - m0);
     float* mine = wt + static_cast<size_t>(blockIdx.z) * (TG_BM * BN);
     if (S > 1) {
       for (int task = warp; task < rows * NCH; task += 2 * TG_LOADER_WARPS) {
@@ -401,42 +489,79 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
   }
 }
 
+// cluster sizes whose launch failed on this process's device (bit S): never tried again (keeps stream captures clean)
+static std::atomic<unsigned> g_cluster_refused{0u};
+
 template <bool TA, bool TB, int BN>
 int launch_tf32_bn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& ep,
-                   float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, cudaStream_t st) {
+                   float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster, cudaStream_t st) {
   constexpr size_t smem = 1024 + TG_STAGES * (2 * TG_TILE_BYTES + 2 * BN * TG_BK * 4) + sizeof(TgSmem) + 64;
   static OncePerDevice once;
   once.run([&] {
     cudaFuncSetAttribute(tf32x3_gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   });
   const int nx = ceil_div(N, BN), ny = ceil_div(M, TG_BM), tiles = nx * ny, nk = ceil_div(K, TG_BK);
-  int S = 1;
   static const char* force_s = getenv("BRUNO_TF32_SPLIT");
-  if (ws && tickets && tiles <= max_tiles) {
-    S = force_s ? atoi(force_s) : sms / tiles;
-    const int smax = nk / 2 < TG_MAX_SPLIT ? nk / 2 : TG_MAX_SPLIT;      // at least two K tiles per CTA
-    S = S > smax ? smax : S;
-    S = S < 1 ? 1 : S;
-    while (S > 1 && static_cast<size_t>(tiles) * S * TG_BM * BN > ws_floats) --S;
-  }
-  const int kchunk = ceil_div(nk, S);
-  S = ceil_div(nk, kchunk);
-  tf32x3_gemm_kernel<TA, TB, BN><<<dim3(nx, ny, S), TG_THREADS, smem, st>>>(M, N, K, A, lda, B, ldb, C, ldc, ep, kchunk, ws, tickets,
-                                                                                g_gemm_trace_host);
+  const bool have_ws = ws && tickets && tiles <= max_tiles;
+  // split-K so that ~one CTA per SM is busy; at least two K tiles per CTA
+  auto split_for = [&](bool with_cluster) {
+    int S = 1;
+    if (with_cluster || have_ws) {
+      S = force_s ? atoi(force_s) : sms / tiles;
+      const int smax = nk / 2 < TG_MAX_SPLIT ? nk / 2 : TG_MAX_SPLIT;
+      S = S > smax ? smax : S;
+      S = S < 1 ? 1 : S;
+      if (!with_cluster)
+        while (S > 1 && static_cast<size_t>(tiles) * S * TG_BM * BN > ws_floats) --S;
+    }
+    return S;
+  };
+  auto launch = [&](bool with_cluster) {
+    int S = split_for(with_cluster);
+    const int kchunk = ceil_div(nk, S);
+    S = ceil_div(nk, kchunk);
+    if (with_cluster && S > 1 && (g_cluster_refused.load(std::memory_order_relaxed) >> S & 1u)) return cudaErrorInvalidClusterSize;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nx, ny, S);
+    cfg.blockDim = dim3(TG_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // the set-up overlaps the previous launch's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+    if (with_cluster && S > 1) {
+      attr[1].id = cudaLaunchAttributeClusterDimension;                // the S CTAs of a tile reduce through peer shared memory
+      attr[1].val.clusterDim.x = 1;
+      attr[1].val.clusterDim.y = 1;
+      attr[1].val.clusterDim.z = static_cast<unsigned>(S);
+      cfg.numAttrs = 2;
+    }
+    cfg.attrs = attr;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, tf32x3_gemm_kernel<TA, TB, BN>, M, N, K, A, lda, B, ldb, C, ldc, ep, kchunk, ws,
+                                             tickets, with_cluster ? 1 : 0, g_gemm_trace_host);
+    if (e != cudaSuccess && with_cluster && S > 1) {
+      cudaGetLastError();
+      g_cluster_refused.fetch_or(1u << S, std::memory_order_relaxed);
+    }
+    return e;
+  };
+  if (cluster && launch(true) == cudaSuccess) return check_launch("tf32x3_gemm_kernel");
+  launch(false);                                                       // workspace + ticket fix-up (or un-split)
   return check_launch("tf32x3_gemm_kernel");
 }
 
 template <bool TA, bool TB>
 int launch_tf32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& ep,
-                float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, cudaStream_t st, int* taken) {
+                float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster, cudaStream_t st, int* taken) {
   *taken = 1;
   // 64-column tiles while 128-column tiles would leave most SMs without work
   const int tiles128 = ceil_div(N, 128) * ceil_div(M, TG_BM);
   static const char* force_bn = getenv("BRUNO_TF32_BN");
   const bool want64 = force_bn ? atoi(force_bn) == 64 : (tiles128 * 2 <= sms || N <= 64);
   if (want64)
-    return launch_tf32_bn<TA, TB, 64>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st);
-  return launch_tf32_bn<TA, TB, 128>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st);
+    return launch_tf32_bn<TA, TB, 64>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st);
+  return launch_tf32_bn<TA, TB, 128>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st);
 }
 
 }  // namespace
@@ -444,13 +569,13 @@ int launch_tf32(int M, int N, int K, const float* A, int lda, const float* B, in
 void gemm_tf32x3_set_trace(long long* device_buffer) { g_gemm_trace_host = device_buffer; }
 
 int gemm_tf32x3(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-                const GemmEpi& ep, float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, cudaStream_t st,
-                int* taken) {
+                const GemmEpi& ep, float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster,
+                cudaStream_t st, int* taken) {
   *taken = 0;
-  if (!ta && !tb) return launch_tf32<false, false>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st, taken);
-  if (ta && !tb) return launch_tf32<true, false>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st, taken);
-  if (!ta && tb) return launch_tf32<false, true>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st, taken);
-  return launch_tf32<true, true>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, st, taken);
+  if (!ta && !tb) return launch_tf32<false, false>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken);
+  if (ta && !tb) return launch_tf32<true, false>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken);
+  if (!ta && tb) return launch_tf32<false, true>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken);
+  return launch_tf32<true, true>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken);
 }
 
 }  // namespace bruno

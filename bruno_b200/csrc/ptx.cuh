@@ -197,6 +197,30 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// programmatic dependent launch: the dependents of this grid may be scheduled / wait for the prerequisite grids' memory
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// thread-block cluster: barrier over all threads of all CTAs (converged warps), rank, and peer shared memory
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t cta_smem_addr, uint32_t rank) {   // same offset in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_smem_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_smem_addr) : "memory");
+  return v;
+}
+
 // read-only 128-bit global load that does not allocate in L1 (streamed once)
 __device__ __forceinline__ uint4 ldg_nc_u4(const void* gptr) {
   uint4 r;

@@ -287,7 +287,9 @@ int bruno_dense_coupling_bwd(const float* x, const float* s_pre, const float* dy
 #ifndef BRUNO_NO_DEBUG
 /* DEBUG (process-wide, not thread-safe) / A-B timing: which kernel the dense-path GEMMs (bruno_sgemm and the dense couplings)
  * use when the operands are 16-byte aligned: 0 = CUDA-core SGEMM (strict fp32 FFMA), 1 = tcgen05 3xTF32 split
- * (fp32-accurate, default).  variant < 0 queries. */
+ * (fp32-accurate, default; the split-K CTAs of a tile are one thread-block cluster and reduce through peer shared memory),
+ * 2 = the same kernel with the round-1 split-K fix-up through the bound workspace (bit-identical results: both add the
+ * partials in K order).  variant < 0 queries. */
 int bruno_debug_gemm_variant(int variant);
 /* DEBUG: CTA (0,0,0) of the tcgen05 GEMM records clock64() of its pipeline events into device_buffer [64][8] (NULL = off) */
 int bruno_debug_gemm_trace(long long* device_buffer);

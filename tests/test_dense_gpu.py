@@ -30,3 +30,39 @@ def test_sgemm(ta, tb, M, N, K):
         if acc:
             r = r + C0.double()
         assert torch.allclose(C.double().cpu(), r, rtol=1e-4, atol=1e-3 * (K ** 0.5)), (C.double().cpu() - r).abs().max()
+
+
+@pytest.mark.parametrize('ta,tb', [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize('M,N,K', [(640, 512, 784), (40, 512, 784), (784, 512, 640), (130, 68, 260), (512, 784, 640)])
+def test_cluster_split_k_equals_workspace_split_k_bit_for_bit(ta, tb, M, N, K):
+    """The split-K CTAs of a tile reduce through peer shared memory (thread-block cluster, default) or through the bound
+    workspace with a ticket (variant 2): both add the K partials in K order, so the results are the same bits -- with
+    every epilogue (column scale, bias, ELU, saved pre-activation via the dense coupling, accumulate)."""
+    from bruno_b200 import _lib
+    lib = _lib.load()
+    if not hasattr(lib, 'bruno_debug_gemm_variant'):
+        pytest.skip('library built with -DBRUNO_NO_DEBUG')
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g).cuda()
+    B = torch.randn((N, K) if tb else (K, N), generator=g).cuda()
+    cs = (torch.rand(N, generator=g) + 0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    C0 = torch.randn(M, N, generator=g).cuda()
+    out = {}
+    try:
+        for variant in (1, 2):
+            lib.bruno_debug_gemm_variant(variant)
+            res = []
+            for scale, bi, act, acc in ((None, None, 0, 0), (cs, bias, 1, 0), (None, bias, 3, 1)):
+                C = C0.clone()
+                for _ in range(3):               # back-to-back launches: programmatic dependent launch between them
+                    _lib.call('bruno_sgemm', ta, tb, M, N, K, A, A.shape[1], B, B.shape[1], C, N, scale, bi, act, acc)
+                res.append(C)
+            out[variant] = res
+    finally:
+        lib.bruno_debug_gemm_variant(1)
+    torch.cuda.synchronize()
+    for a, b in zip(out[1], out[2]):
+        assert torch.equal(a, b), (a - b).abs().max().item()
+    ref = (A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double())
+    assert torch.allclose(out[1][0].double(), ref, rtol=1e-4, atol=1e-3 * (K ** 0.5))
