@@ -33,6 +33,7 @@ constexpr int TG_MAX_SPLIT = 8;
 
 struct TgSmem {
   uint64_t full[TG_STAGES], empty[TG_STAGES], done;
+  uint64_t red;       // cluster split-K: counts the bytes of partial rows the peers (and this CTA) push into this CTA
   uint32_t tmem_base;
   int last;
 };
@@ -218,6 +219,7 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
       mbar_init(&cs->empty[s], 1);
     }
     mbar_init(&cs->done, 1);
+    mbar_init(&cs->red, 1);
     fence_mbar_init();
   }
   if (warp == TG_LOADER_WARPS) {
@@ -229,6 +231,18 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
   __syncthreads();
   tc_fence_after();
   griddep_launch_dependents();      // the next launch may set itself up; its griddepcontrol.wait sees this grid complete
+  if (gridDim.z > 1 && cluster_reduce) {
+    // every CTA of the cluster runs and has initialised its barriers before anyone pushes into it.  Here, where the
+    // peers start together and nothing is in flight: the acquire side of a cluster barrier invalidates L1 (CCTL.IVALL).
+    if (threadIdx.x == 0) {                                   // bytes of partial rows this CTA will receive (see the epilogue)
+      const int Sz = gridDim.z, rws = min(TG_BM, M - m0), per = (rws + Sz - 1) / Sz, rb = static_cast<int>(cluster_ctarank()) * per;
+      const int nmine = max(0, min(rws, rb + per) - rb);
+      if (nmine > 0) mbar_arrive_expect_tx(&cs->red, static_cast<uint32_t>(Sz * nmine * BN * 4));
+    }
+    __syncwarp();
+    cluster_arrive_relaxed();
+    cluster_wait();
+  }
   const uint32_t tmem = cs->tmem_base;
   const uint32_t stage0 = smem_u32(smem);
 
@@ -306,21 +320,137 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
     __syncwarp();
   }
 
-  // ===== epilogue.  Warps 0..3 read their TMEM lane quarter 32 columns at a time and transpose it through shared memory
-  // (the ring is idle once `done` fired), so that a warp instruction handles 32 consecutive columns of one row.
-  // Split-K: the S CTAs of a tile are ONE THREAD-BLOCK CLUSTER (1, 1, S).  Each leaves its partial tile in its own shared
-  // memory; after a cluster barrier CTA z adds, for its 1/S of the rows, the S partials in z order (deterministic) from
-  // the peers' shared memory (ld.shared::cluster), applies the epilogue and writes C: no partials in global memory, no
-  // fence / ticket round trip, every CTA shares the reduction.  (Round 1 wrote the partials to a workspace and let the
-  // last CTA of a tile -- ticket -- add them: half of the 15 us launch; that path stays for a launch without cluster.)
+  // ===== epilogue.
+  // Split-K: the S CTAs of a tile are ONE THREAD-BLOCK CLUSTER (1, 1, S).  CTA z owns rows [z rows_per, (z + 1) rows_per) of
+  // the tile.  Warps 0..3 of every CTA read their TMEM lane quarter (lane = row) and PUSH each row of their partial into
+  // its owner's shared memory (st.async.shared::cluster, slot [source z][row]: fire and forget, no exposed round trip),
+  // counting the bytes on the OWNER's mbarrier (complete_tx).  When its count is complete a CTA adds the S partials of
+  // its rows in z order (deterministic) from LOCAL shared memory, applies the epilogue and writes C.  No cluster barrier
+  // in the epilogue: its release side is a GPU-scope MEMBAR, its acquire side an L1 invalidate per warp (measured: 1100
+  // cycles for the barrier and a clogged load/store pipe behind it).  No partials in global memory, no fence / ticket round trip, every CTA shares the
+  // reduction.  (Round 1 wrote the partials to a workspace and let the last CTA of a tile -- ticket -- add them: half of
+  // the 15 us launch; pulling the peers' tiles with ld.shared::cluster cost ~2000 cycles per batch of loads.  The
+  // workspace path stays for a launch without cluster.)  The push buffer is outside the operand ring: a peer may
+  // still be multiplying when the first rows arrive.
   const int S = gridDim.z;
   const bool loader_warp = warp < TG_LOADER_WARPS;
   constexpr int NCH = BN / 32;
-  constexpr int TP = BN + 1;
-  float* T = reinterpret_cast<float*>(smem);
   const int rows = min(TG_BM, M - m0);
-  if (loader_warp) {
-    // phase A: warps 0..3 copy their TMEM lane quarter into a row-major shared tile (pitch BN + 1: conflict-free both ways)
+  if (S > 1 && cluster_reduce) {
+    if constexpr (BN == 64) {
+      constexpr int PP = BN + 4;                              // 16-byte aligned rows; 16-byte stores at this pitch are conflict-free
+      float* P = reinterpret_cast<float*>(smem + TG_STAGES * STAGE_BYTES + 128);     // [S][rows_per][PP]
+      const int rank = static_cast<int>(cluster_ctarank());   // = blockIdx.z: cluster (1, 1, S), gridDim.z = S
+      const int rows_per = (rows + S - 1) / S;
+      static_assert(TG_LOADER_WARPS % NCH == 0, "a warp keeps its column chunk over the reduction tasks");
+      const int rb = rank * rows_per;
+      const int nmine = max(0, min(rows, rb + rows_per) - rb);          // rows this CTA owns
+      if (warp < 4) {
+        mbar_wait(&cs->done, 0);
+        tc_fence_after();
+        if (threadIdx.x == 0) gtrace(trace_buf, 63, 5);
+        const int r = warp * 32 + lane;
+        const int owner = r / rows_per, lr = r - owner * rows_per;
+        const bool push = r < rows;                           // owner < S then
+        const uint32_t dst = mapa_shared(smem_u32(P), static_cast<uint32_t>(push ? owner : rank)) +
+                             static_cast<uint32_t>(((rank * rows_per + lr) * PP) * 4);
+        const uint32_t dbar = mapa_shared(smem_u32(&cs->red), static_cast<uint32_t>(push ? owner : rank));
+        uint32_t v[NCH][32];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + ch * 32, v[ch]);
+        tmem_ld_wait();
+        if (threadIdx.x == 0) gtrace(trace_buf, 62, 6);
+        if (push) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              st_async_v4(dst + static_cast<uint32_t>((ch * 32 + e) * 4), v[ch][e], v[ch][e + 1], v[ch][e + 2], v[ch][e + 3], dbar);
+        }
+        if (threadIdx.x == 0) gtrace(trace_buf, 60, 5);
+      }
+      if (loader_warp && nmine > 0) {
+        // This code runs once per CTA: its cost is instruction fetch and dependent-issue latency as much as memory
+        // (an unrolled 4-task scalar version took ~2300 cycles per iteration on LOCAL shared memory), so the loops
+        // are short and not unrolled.  Fast path: a lane owns 4 consecutive columns (16 lanes per row, two rows per
+        // warp and iteration, LDS.128 / STG.128); column scale / bias are fetched before the wait.
+        const int zstride = rows_per * PP;
+        const bool vec = (ldc & 3) == 0 && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                         (ep.pre_out == nullptr || (reinterpret_cast<uintptr_t>(ep.pre_out) & 15) == 0);
+        const int half = lane >> 4, c4 = (lane & 15) * 4;
+        const bool col4_on = vec && n0 + c4 < N;
+        float cs4[4], cb4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          cs4[e] = (col4_on && ep.col_scale) ? ep.col_scale[n0 + c4 + e] : 1.f;
+          cb4[e] = (col4_on && ep.bias) ? ep.bias[n0 + c4 + e] : 0.f;
+        }
+        mbar_wait(&cs->red, 0);                               // every partial row of this CTA's rows has landed
+        if (threadIdx.x == 0) gtrace(trace_buf, 61, 5);
+        with_act(ep.act, [&](auto act) {
+          if (vec) {
+            const uint32_t psm = smem_u32(P) + static_cast<uint32_t>(c4 * 4);
+#pragma unroll 1
+            for (int task = warp; 2 * task < nmine; task += TG_LOADER_WARPS) {
+              const int lr = 2 * task + half;
+              if (col4_on && lr < nmine) {
+                float x[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int z = 0; z < TG_MAX_SPLIT; ++z)
+                  if (z < S) {
+                    const uint4 q = lds_u4(psm + static_cast<uint32_t>((z * zstride + lr * PP) * 4));
+                    x[0] += __uint_as_float(q.x); x[1] += __uint_as_float(q.y);
+                    x[2] += __uint_as_float(q.z); x[3] += __uint_as_float(q.w);
+                  }
+                const size_t o = static_cast<size_t>(m0 + rb + lr) * ldc + n0 + c4;
+                float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ep.accumulate) old = *reinterpret_cast<const float4*>(C + o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (ep.col_scale) x[e] = __fmul_rn(x[e], cs4[e]);
+                  if (ep.bias) x[e] = __fadd_rn(x[e], cb4[e]);
+                }
+                if (ep.pre_out) *reinterpret_cast<float4*>(ep.pre_out + o) = make_float4(x[0], x[1], x[2], x[3]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = act_apply<decltype(act)::value>(x[e]);
+                if (ep.accumulate) { x[0] += old.x; x[1] += old.y; x[2] += old.z; x[3] += old.w; }
+                *reinterpret_cast<float4*>(C + o) = make_float4(x[0], x[1], x[2], x[3]);
+              }
+              if (threadIdx.x == 0 && task == warp) gtrace(trace_buf, 61, 6);
+            }
+          } else {                                            // any N / ldc / alignment: one (row, 32-column chunk) per warp
+            const int ntask = nmine * NCH;
+            const int n = n0 + (warp % NCH) * 32 + lane;      // 12 % NCH == 0: a warp keeps its chunk
+#pragma unroll 1
+            for (int task = warp; task < ntask; task += TG_LOADER_WARPS) {
+              if (n < N) {
+                const float* src = P + (task / NCH) * PP + (task % NCH) * 32 + lane;
+                float x = 0.f;
+#pragma unroll
+                for (int z = 0; z < TG_MAX_SPLIT; ++z)
+                  if (z < S) x += src[z * zstride];
+                const size_t o = static_cast<size_t>(m0 + rb + task / NCH) * ldc + n;
+                if (ep.col_scale) x = __fmul_rn(x, ep.col_scale[n]);
+                if (ep.bias) x = __fadd_rn(x, ep.bias[n]);
+                if (ep.pre_out) ep.pre_out[o] = x;
+                x = act_apply<decltype(act)::value>(x);
+                if (ep.accumulate) x += C[o];
+                C[o] = x;
+              }
+            }
+          }
+        });
+        if (threadIdx.x == 0) gtrace(trace_buf, 60, 6);
+      }
+      if (threadIdx.x == 0) gtrace(trace_buf, 63, 6);
+    }
+  } else if (loader_warp) {
+    // Un-split, or split-K through the workspace: warps 0..3 copy their TMEM lane quarter into a row-major shared tile
+    // (the ring is idle once `done` fired; pitch BN + 1: conflict-free both ways), then all 12 warps handle rows (a warp
+    // instruction = 32 consecutive columns of one row); with split-K the tile goes to the workspace and the LAST CTA
+    // of the tile (ticket) adds the partials in z order.
+    constexpr int TP = BN + 1;
+    float* T = reinterpret_cast<float*>(smem);
     if (warp < 4) {
       mbar_wait(&cs->done, 0);
       tc_fence_after();
@@ -336,58 +466,6 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * TG_LOADER_WARPS) : "memory");
     if (threadIdx.x == 0) gtrace(trace_buf, 60, 5);
-  }
-  if (S > 1 && cluster_reduce) {
-    __syncwarp();
-    cluster_sync_all();                                       // every partial tile of the cluster is in place
-    if (loader_warp) {
-      const int rank = static_cast<int>(cluster_ctarank());   // = blockIdx.z: cluster (1, 1, S), gridDim.z = S
-      const int rows_per = (rows + S - 1) / S;
-      const int rb = rank * rows_per;
-      const int ntask = max(0, min(rows, rb + rows_per) - rb) * NCH;
-      uint32_t peer[TG_MAX_SPLIT];
-#pragma unroll
-      for (int z = 0; z < TG_MAX_SPLIT; ++z) peer[z] = mapa_shared(smem_u32(T), static_cast<uint32_t>(z < S ? z : 0));
-      with_act(ep.act, [&](auto act) {
-        constexpr int TU = 4;
-        for (int task0 = warp; task0 < ntask; task0 += TU * TG_LOADER_WARPS) {
-          float part[TU][TG_MAX_SPLIT], old[TU];
-#pragma unroll
-          for (int u = 0; u < TU; ++u) {
-            const int task = task0 + u * TG_LOADER_WARPS;
-            const int row = rb + task / NCH, ch = task % NCH;
-            const uint32_t off = static_cast<uint32_t>((row * TP + ch * 32 + lane) * 4);
-            const bool on = task < ntask && n0 + ch * 32 + lane < N;
-#pragma unroll
-            for (int z = 0; z < TG_MAX_SPLIT; ++z) part[u][z] = (on && z < S) ? ld_dsmem_f32(peer[z] + off) : 0.f;
-            old[u] = (on && ep.accumulate) ? C[static_cast<size_t>(m0 + row) * ldc + n0 + ch * 32 + lane] : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < TU; ++u) {
-            const int task = task0 + u * TG_LOADER_WARPS;
-            const int row = rb + task / NCH, ch = task % NCH;
-            const int n = n0 + ch * 32 + lane;
-            if (task < ntask && n < N) {
-              const size_t o = static_cast<size_t>(m0 + row) * ldc + n;
-              float x = 0.f;
-#pragma unroll
-              for (int z = 0; z < TG_MAX_SPLIT; ++z) x += part[u][z];
-              if (ep.col_scale) x = __fmul_rn(x, ep.col_scale[n]);
-              if (ep.bias) x = __fadd_rn(x, ep.bias[n]);
-              if (ep.pre_out) ep.pre_out[o] = x;
-              x = act_apply<decltype(act)::value>(x);
-              if (ep.accumulate) x += old[u];
-              C[o] = x;
-            }
-          }
-        }
-      });
-      if (threadIdx.x == 0) gtrace(trace_buf, 60, 6);
-    }
-    __syncwarp();
-    cluster_sync_all();                                       // no CTA leaves while a peer still reads its tile
-    if (threadIdx.x == 0) gtrace(trace_buf, 63, 6);
-  } else if (loader_warp) {
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
     float* wt = ws + static_cast<size_t>(tile) * S * (TG_BM * BN);        // [z][row][BN]
     // phase B: all 12 warps write rows (a warp instruction = 32 consecutive columns of one row)
@@ -483,6 +561,7 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, co
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) gtrace(trace_buf, 62, 5);
   if (warp == TG_LOADER_WARPS) {
     __syncwarp();
     tmem_dealloc(tmem, BN);
@@ -495,7 +574,11 @@ static std::atomic<unsigned> g_cluster_refused{0u};
 template <bool TA, bool TB, int BN>
 int launch_tf32_bn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& ep,
                    float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster, cudaStream_t st) {
-  constexpr size_t smem = 1024 + TG_STAGES * (2 * TG_TILE_BYTES + 2 * BN * TG_BK * 4) + sizeof(TgSmem) + 64;
+  // + the push buffer of the cluster split-K reduction (64-column tiles only): <= TG_BM + TG_MAX_SPLIT rows of BN + 4 floats
+  constexpr size_t push_bytes = BN == 64 ? static_cast<size_t>(TG_BM + TG_MAX_SPLIT) * (BN + 4) * 4 : 0;
+  constexpr size_t smem = 1024 + TG_STAGES * (2 * TG_TILE_BYTES + 2 * BN * TG_BK * 4) + 128 + push_bytes + 64;
+  static_assert(sizeof(TgSmem) <= 128, "control block");
+  cluster = cluster && BN == 64;                                       // 128-column tiles only run un-split in practice
   static OncePerDevice once;
   once.run([&] {
     cudaFuncSetAttribute(tf32x3_gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

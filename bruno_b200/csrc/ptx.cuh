@@ -205,6 +205,18 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_dsmem_v4(uint32_t cluster_smem_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(cluster_smem_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// asynchronous 16-byte store into a peer CTA's shared memory that counts its bytes on an mbarrier of that CTA
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_smem_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t cluster_mbar_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(cluster_smem_addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_mbar_addr)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
