@@ -114,6 +114,55 @@ def cpu_reference_line(args, steps, warmup, as_reference_arm):
             'cpu_baseline': cb, 'e2e': {'value': val, 'unit': 'seqs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
 
 
+def dense_gemm_sequence_graph_ms(cfg, dev, rows, reps=10):
+    """GPU time of the dense-path GEMMs of ONE training step (per dense coupling: 4 forward + 8 backward GEMMs, the shapes of
+    bruno_coupling_dense_fwd / _bwd with N = `rows`, D = latent dimension, U = hidden units) as one dependent launch sequence
+    replayed from a CUDA graph captured on a stream whose workspace is bound.  Returns (ms per step, launches, useful FLOPs)."""
+    import torch
+    from bruno_b200 import _lib
+    layers = list(getattr(cfg, 'nvp_dense_layers', []))
+    if not layers:
+        return 0.0, 0, 0.0
+    D = 1
+    for v in cfg.obs_shape[1:]:
+        D *= int(v)
+    U = int(getattr(layers[0], 'n_units', 512))
+    N = int(rows)
+    # (ta, tb, M, N, K) in the order of csrc/dense.cu
+    shapes = [(0, 0, N, U, D), (0, 0, N, U, U), (0, 0, N, D, U), (0, 0, N, D, U),
+              (1, 0, U, D, N), (1, 0, U, D, N), (0, 1, N, U, D), (0, 1, N, U, D), (1, 0, U, U, N), (0, 1, N, U, U),
+              (1, 0, D, U, N), (0, 1, N, D, U)]
+    bufs = []
+    for (ta, tb, M, Nn, K) in shapes:
+        A = torch.randn((K, M) if ta else (M, K), device=dev)
+        B = torch.randn((Nn, K) if tb else (K, Nn), device=dev)
+        bufs.append((ta, tb, M, Nn, K, A, B, torch.empty(M, Nn, device=dev)))
+    flops = sum(2.0 * M * Nn * K for (_, _, M, Nn, K) in shapes) * len(layers)
+
+    def seq():
+        for _ in layers:
+            for (ta, tb, M, Nn, K, A, B, C) in bufs:
+                _lib.call('bruno_sgemm', ta, tb, M, Nn, K, A, A.shape[1], B, B.shape[1], C, Nn, None, None, 0, 0)
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        seq()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        seq()
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, len(shapes) * len(layers), flops
+
+
 def conv_sequence_graph_ms(cfg, dev, reps=10, direction=None, height=None):
     """GPU time of the 3x3 conv launches of ONE training step in the regime the timed region runs them in: the same
     kernels, modes, shapes and data dependencies (per coupling: 2R forward launches as a dependent chain, then 2R dgrad
@@ -400,6 +449,7 @@ def main():
         prof[name] = {'total_ms': tot.value, 'launches': cnt.value}
     _lib.query('bruno_profile_enable', 0)
     conv_graph_ms, conv_graph_launches = conv_sequence_graph_ms(cfg, dev)
+    dense_ms, dense_launches, dense_flops = dense_gemm_sequence_graph_ms(cfg, dev, B * T)
 
     # The reference's own nr_gpu semantics (config_rnn/train.py:184: ONE batch of `batch_size` sequences, np.split over the
     # GPUs) = strong scaling: measured in the same run with the global batch of --batch sequences split over the ranks.
@@ -579,6 +629,16 @@ def main():
                                                'algorithmic FLOPs = those of the forward convolutions',
                                         'ncu': 'profiles/r02_wgrad_line_ncu_summary.txt: tensor pipe active 86.5 %'}
                            if w['total_ms'] > 0 else None)(prof['conv3x3_wgrad']),
+        'roofline_dense': ({'bound': 'tensor', 'kernel': 'tf32x3_gemm_kernel (3xTF32 tcgen05 GEMM, split-K inside a thread-block cluster)',
+                            'achieved': dense_flops / (dense_ms * 1e-3) / 1e12, 'peak': peak_burst / 6.0, 'unit': 'TFLOP/s',
+                            'frac': dense_flops / (dense_ms * 1e-3) / 1e12 / (peak_burst / 6.0),
+                            'peak_source': 'derived: measured bf16 burst peak / 2 (TF32 rate) / 3 (tensor products per fp32-accurate product); '
+                                           'no TF32 peak is measured on this pool',
+                            'launches': dense_launches, 'avg_launch_us': 1e3 * dense_ms / dense_launches, 'ms_per_step': dense_ms,
+                            'share_of_step': dense_ms / (ms_train / steps),
+                            'how': 'the dense-coupling GEMMs of one training step (shapes and order of csrc/dense.cu, useful FLOPs 2MNK) '
+                                   'replayed from one CUDA graph; these GEMMs are latency-bound (0.4-0.6 GFLOP each), see DESIGN 5.2b'}
+                           if dense_launches else None),
         'roofline_process_scan': scan,
         'kernel_time_ms_per_step': {k: v['total_ms'] / steps for k, v in prof.items()},
         'clocks': sampler.summary() if sampler else None,

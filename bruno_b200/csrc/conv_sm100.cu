@@ -494,16 +494,19 @@ conv3x3_line_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ 
       fence_mbar_init();
     }
   }
+  if (threadIdx.x == 0) trace_at(trace_buf, 62, 0);                      // barriers initialised (this thread's share)
   if (threadIdx.x >= 192 && threadIdx.x < 256) cs->bias[threadIdx.x - 192] = HAS_BIAS ? bias[threadIdx.x - 192] : 0.f;
   // Rows of a stage that no copy ever writes stay zero for the whole kernel: the guards, the padding columns past W + 1
   // of every image segment (only the rows a line's neighbours can read are copied) and the rows past the last segment.
   for (int i = threadIdx.x; i < NS * (LT_STAGE_BYTES / 16); i += blockDim.x) reinterpret_cast<uint4*>(slabs)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
+  if (threadIdx.x == 0) trace_at(trace_buf, 62, 1);                      // stage rows zeroed
   if (warp == 0) {
     __syncwarp();
     tmem_alloc(&cs->tmem_base, 64 * LT_SLOTS);
     tmem_relinquish();
   }
+  if (threadIdx.x == 0) trace_at(trace_buf, 62, 2);                      // TMEM allocated
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

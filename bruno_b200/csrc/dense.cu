@@ -369,10 +369,19 @@ static int gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, 
   const bool vec_ok = aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0 && K % 4 == 0 &&
                       (ta ? M % 4 == 0 : true) && (tb ? true : N % 4 == 0) && (!ep.a_kscale || aligned16(ep.a_kscale));
   const Workspace wk = sk_workspace(st);
-  if (vec_ok && g_gemm_variant >= 1 && wk) {
+  if (vec_ok && g_gemm_variant >= 1) {
+    // the cluster split-K of the tcgen05 GEMM needs no workspace; without one the fix-up variant (2) runs un-split
+    static int sms_cached[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int sms = wk ? wk.sms : sms_cached[dev & 63];
+    if (sms == 0) {
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      sms_cached[dev & 63] = sms;
+    }
     int taken = 0;
     const int rc = gemm_tf32x3(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, ep, wk.ws, SK_WS_FLOATS, wk.tickets, SK_MAX_TILES,
-                               wk.sms, g_gemm_variant == 1, st, &taken);
+                               sms, g_gemm_variant == 1, st, &taken);
     if (taken) return rc;
   }
   if (vec_ok) {

@@ -41,11 +41,13 @@ int bruno_abi_version(void);
 /* number of CUDA kernels this library has launched in this process (evidence for bench.py's gpu_launches) */
 long bruno_launch_count(void);
 
-/* Workspace of the dense-path GEMMs (bruno_sgemm, bruno_coupling_dense_*, bruno_dense_layer_*): split-K partial tiles,
- * column-reduction partials and their ticket counters.  The caller allocates bruno_workspace_bytes() bytes of device
- * memory, ZERO-FILLS them once (the kernels leave the tickets at zero), and binds them to the stream it launches on.
+/* Workspace of the dense-path GEMMs (bruno_sgemm, bruno_coupling_dense_*, bruno_dense_layer_*): column-reduction partials,
+ * the split-K partial tiles of the fallback GEMM paths (the default tcgen05 GEMM reduces its split-K partials inside a
+ * thread-block cluster through peer shared memory and does not touch it) and their ticket counters.  The caller allocates
+ * bruno_workspace_bytes() bytes of device memory, zero-initialises it once, and binds it to the stream it will launch on.
  * One workspace per stream: two streams that run GEMMs concurrently need two.  Launches on a stream without a bound
- * workspace run un-split (same results up to summation order, slower).  Unbind before freeing the memory. */
+ * workspace still work: the cluster GEMM as usual, the fallback GEMMs and the column reductions un-split (same results
+ * up to summation order, slower).  Unbind before freeing the memory. */
 size_t bruno_workspace_bytes(void);
 int bruno_workspace_bind(void* stream, void* workspace, size_t bytes);
 int bruno_workspace_unbind(void* stream);

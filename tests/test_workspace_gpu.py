@@ -43,7 +43,8 @@ def test_two_streams_run_split_k_gemms_concurrently():
 
 
 def test_gemm_without_a_workspace_still_correct():
-    """A stream with no bound workspace: the GEMM runs un-split instead of allocating."""
+    """A stream with no bound workspace: the GEMM still splits K (its thread-block-cluster reduction needs no workspace;
+    the fallback kernels would run un-split) and nothing is allocated behind the caller's back."""
     from bruno_b200 import _lib
     lib = _lib.load()
     st = torch.cuda.Stream()

@@ -14,6 +14,7 @@ sl = slab.alloc_slabs(3, N, H, W, 'cuda')
 sl[0].random_(0, 255)
 bias = torch.zeros(64, device='cuda')
 lib = _lib.load()
+if os.environ.get('BRUNO_CONV_VARIANT'): lib.bruno_debug_conv_variant(int(os.environ['BRUNO_CONV_VARIANT']))   # 1 per-tap, 2 line-tile
 
 
 def launch(mode):
@@ -36,6 +37,8 @@ for mode in (0, 1, 2, 3):
     print('mode %d  %dx%dx%d   (cycles since kernel entry of CTA 0; second of two back-to-back launches)' % (mode, N, H, W))
     print('  setup done %d | previous grid complete %d | weights landed %d | kernel end %d' % (
         rel(t[0, 9]), rel(t[0, 10]), rel(t[0, 11]), rel(t[0, 12])))
+    if int(t[62, 0]):
+        print('  prologue: barriers initialised %d | stage rows zeroed %d | TMEM allocated %d' % tuple(rel(t[62, k]) for k in (0, 1, 2)))
     cyc, ns = int(t[0, 12] - t[0, 8]), int(t[0, 14] - t[0, 13])
     print('  CTA 0 lifetime: %d cycles in %d ns = %.0f MHz effective SM clock' % (cyc, ns, 1e3 * cyc / max(ns, 1)))
     for i in range(int(os.environ.get('TRACE_TILES', '32'))):
