@@ -367,7 +367,7 @@ c1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ V1, const f
 // 512-byte warp reads, dx through 8-channel partials + xor-shuffles, dW1 / db1 in registers over all pixels of the thread
 // and ONE fixed-order block reduction + atomics at the end (see heads_coupling_bwd8_kernel).
 template <int C>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, C == 1 ? 3 : 2)
 c1_bwd8_kernel(const float* __restrict__ x, const float* __restrict__ V1, const float* __restrict__ g1w,
                const uint8_t* __restrict__ gslab, float* __restrict__ dx, float* __restrict__ dW1, float* __restrict__ db1,
                SlabGeom g, int mask_type) {
@@ -406,11 +406,20 @@ c1_bwd8_kernel(const float* __restrict__ x, const float* __restrict__ V1, const 
     return r;
   };
   int q0 = (blockIdx.x * 256 + threadIdx.x) >> 3;
-  In cur;
+  // C <= 2 has the registers for TWO pixels in flight per thread (and C = 1 for three blocks per SM): 16 resident warps with
+  // one 16-byte load each ahead cover ~45 % of the bandwidth-delay product
+  constexpr bool DEEP = C <= 2;
+  In cur, nx1;
   if (q0 < NP) cur = fetch(q0);
+  nx1 = cur;
+  if (DEEP && q0 + ngroups < NP) nx1 = fetch(q0 + ngroups);
   for (int q = q0; q < NP; q += ngroups) {
-    In nxt = cur;
-    if (q + ngroups < NP) nxt = fetch(q + ngroups);
+    In nxt = DEEP ? nx1 : cur;
+    if (DEEP) {
+      if (q + 2 * ngroups < NP) nx1 = fetch(q + 2 * ngroups);
+    } else {
+      if (q + ngroups < NP) nxt = fetch(q + ngroups);
+    }
     float gv[8];
     unpack8f(cur.gq, gv);
     const size_t xo = static_cast<size_t>(q) * C;
@@ -974,7 +983,7 @@ int bruno_c1_bwd(const float* x, const float* V1, const float* g1, const void* g
     cudaStream_t st8 = static_cast<cudaStream_t>(stream);
     const SlabGeom g8 = slab_geom(N, H, W);
     const uint8_t* gs8 = static_cast<const uint8_t*>(g_slab);
-    if (C == 1) c1_bwd8_kernel<1><<<296, 256, 0, st8>>>(x, V1, g1, gs8, dx, dW1, db1, g8, mask_type);
+    if (C == 1) c1_bwd8_kernel<1><<<444, 256, 0, st8>>>(x, V1, g1, gs8, dx, dW1, db1, g8, mask_type);
     else if (C == 2) c1_bwd8_kernel<2><<<296, 256, 0, st8>>>(x, V1, g1, gs8, dx, dW1, db1, g8, mask_type);
     else if (C == 3) c1_bwd8_kernel<3><<<296, 256, 0, st8>>>(x, V1, g1, gs8, dx, dW1, db1, g8, mask_type);
     else c1_bwd8_kernel<4><<<296, 256, 0, st8>>>(x, V1, g1, gs8, dx, dW1, db1, g8, mask_type);
