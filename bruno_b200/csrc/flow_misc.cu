@@ -715,8 +715,10 @@ slab_image_colsum_kernel(const uint8_t* __restrict__ slabs, size_t slab_stride, 
 //   * the head-weight gradients dK[k][c2] = sum_p h[p][k] d[p][c2] stay in REGISTERS (8 channels x 2C per thread) over
 //     all pixels of the thread: the shared-memory transpose + dot-product phase of the generic kernel (19 us of LDS per
 //     14x14 layer) is gone.  One fixed-order reduction per block at the end -> `partial`, same layout as above.
+//   * C >= 3 needs 174 / 212 registers: one block per SM without spills beats two with 176 bytes of stack (43.0 -> 37.8 us
+//     at 640x14x14, C = 4)
 template <int C>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, C >= 3 ? 1 : 2)
 heads_coupling_bwd8_kernel(const float* __restrict__ xin, const uint8_t* __restrict__ hslab, const float* __restrict__ Ks,
                            const float* __restrict__ bs, const float* __restrict__ Kt, const float* __restrict__ dy,
                            const float* __restrict__ dld, float* __restrict__ dx, uint8_t* __restrict__ gslab,
@@ -777,7 +779,7 @@ heads_coupling_bwd8_kernel(const float* __restrict__ xin, const uint8_t* __restr
   if (q0 < NP) cur = fetch(q0);
   for (int q = q0; q < NP; q += ngroups) {
     In nxt = cur;
-    if (q + ngroups < NP) nxt = fetch(q + ngroups);
+    if (q + ngroups < NP) nxt = fetch(q + ngroups);       // (two pixels ahead was measured: no gain here, the chain is the math)
     const int n = cur.n, yy = cur.yy, xx = cur.xx;
     const size_t R = cur.R;
     float h[8];
