@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include <mutex>
 #include "ptx.cuh"
 
 namespace bruno {
@@ -1412,6 +1413,35 @@ static int launch_fwd_variant(const float* z, const float* mu0, const float* tab
 
 // Ring kernel launch.  Returns +1 when this shape cannot take the ring path (caller falls back to the register-staged
 // kernel): T too long for the shared-memory partials.
+// Per-device launch geometry of a ring kernel instantiation: {dynamic smem opt-in, resident blocks per SM, SM count} are
+// properties of the DEVICE, and two host threads may reach a call site together: keyed by (device, slot), under a lock.
+struct RingLaunchCache {
+  struct Entry { size_t smem = 0; int threads = 0, per_sm = 0, sms = 0; };
+  Entry e[16][4];
+  std::mutex mu;
+  template <class K>
+  Entry get(K kernel, int slot, size_t smem, int threads) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    Entry& c = e[dev & 15][slot];
+    if (c.smem != smem || c.threads != threads || c.sms == 0) {
+      Entry n;
+      n.smem = smem;
+      n.threads = threads;
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess ||
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n.per_sm, kernel, threads + 32, smem) != cudaSuccess ||
+          cudaDeviceGetAttribute(&n.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        cudaGetLastError();
+        n.per_sm = 0;                                          // the caller falls back to the register-staged scan
+        n.sms = 0;
+      }
+      c = n;
+    }
+    return c;
+  }
+};
+
 constexpr int RING_CONS = 224;   // consumer threads per block at most (7 warps + 1 producer warp = 256 threads)
 static ScanGeom ring_geom(int D) {
   ScanGeom g;
@@ -1433,24 +1463,10 @@ static int launch_fwd_ring(const float* z, const float* mu0, const float* table,
                           : process_fwd_ring_kernel<KIND, NB, false, NSTAGE, RS, MINB, CPF, true>)
               : (lp_prior ? process_fwd_ring_kernel<KIND, NB, true, NSTAGE, RS, MINB, CPF, false>
                           : process_fwd_ring_kernel<KIND, NB, false, NSTAGE, RS, MINB, CPF, false>);
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  // resident blocks per SM of this instantiation at this (threads, smem): queried once per change, not per launch
-  static struct { size_t smem; int threads, per_sm; } cache[4] = {};
-  auto& ce = cache[(s1 ? 2 : 0) + (lp_prior ? 1 : 0)];
-  if (ce.smem != smem || ce.threads != g.threads) {
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, g.threads + 32, smem);
-    ce.smem = smem;
-    ce.threads = g.threads;
-    ce.per_sm = per_sm;
-  }
-  const int per_sm = ce.per_sm;
+  // resident blocks per SM of this instantiation at this (threads, smem): queried once per change and device, not per launch
+  static RingLaunchCache cache;
+  const RingLaunchCache::Entry ce = cache.get(k, (s1 ? 2 : 0) + (lp_prior ? 1 : 0), smem, g.threads);
+  const int per_sm = ce.per_sm, sm_count = ce.sms;
   if (per_sm < 1) return 1;
   const int groups = ceil_div(B, NB);
   const int resident = ceil_div(per_sm * sm_count, g.nseg);
@@ -1533,22 +1549,9 @@ static int launch_bwd_ring(const float* z, const float* mu0, const float* table,
   const size_t smem = static_cast<size_t>(NSTAGE) * NROW * g.threads * 4 * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t);
   if (smem > 226 * 1024) return 1;
   auto k = dlpp ? process_bwd_ring_kernel<KIND, NB, true, NSTAGE, MINB, CT> : process_bwd_ring_kernel<KIND, NB, false, NSTAGE, MINB, CT>;
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  static struct { size_t smem; int threads, per_sm; } cache[2] = {};
-  auto& ce = cache[dlpp ? 1 : 0];
-  if (ce.smem != smem || ce.threads != g.threads) {
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, g.threads + 32, smem);
-    ce.smem = smem;
-    ce.threads = g.threads;
-    ce.per_sm = per_sm;
-  }
+  static RingLaunchCache cache;
+  const RingLaunchCache::Entry ce = cache.get(k, dlpp ? 1 : 0, smem, g.threads);
+  const int sm_count = ce.sms;
   if (ce.per_sm < 1) return 1;
   const int groups = ceil_div(B, NB);
   int nblk = ceil_div(ce.per_sm * sm_count, g.nseg);
