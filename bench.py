@@ -114,10 +114,11 @@ def cpu_reference_line(args, steps, warmup, as_reference_arm):
             'cpu_baseline': cb, 'e2e': {'value': val, 'unit': 'seqs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
 
 
-def dense_gemm_sequence_graph_ms(cfg, dev, rows, reps=10):
-    """GPU time of the dense-path GEMMs of ONE training step (per dense coupling: 4 forward + 8 backward GEMMs, the shapes of
-    bruno_coupling_dense_fwd / _bwd with N = `rows`, D = latent dimension, U = hidden units) as one dependent launch sequence
-    replayed from a CUDA graph captured on a stream whose workspace is bound.  Returns (ms per step, launches, useful FLOPs)."""
+def dense_coupling_sequence_graph_ms(cfg, dev, rows, reps=10):
+    """GPU time of the dense couplings of ONE training step: bruno_coupling_dense_fwd for every dense coupling, then
+    bruno_coupling_dense_bwd in reverse order (the calls nn_extra_nvp._DenseCouplingFn makes, with N = `rows`, D = latent
+    dimension, U = hidden units) as one dependent launch sequence replayed from a CUDA graph captured on a stream whose
+    workspace is bound.  Returns (ms per step, kernel launches of the sequence, useful GEMM FLOPs)."""
     import torch
     from bruno_b200 import _lib
     layers = list(getattr(cfg, 'nvp_dense_layers', []))
@@ -128,26 +129,35 @@ def dense_gemm_sequence_graph_ms(cfg, dev, rows, reps=10):
         D *= int(v)
     U = int(getattr(layers[0], 'n_units', 512))
     N = int(rows)
-    # (ta, tb, M, N, K) in the order of csrc/dense.cu
-    shapes = [(0, 0, N, U, D), (0, 0, N, U, U), (0, 0, N, D, U), (0, 0, N, D, U),
-              (1, 0, U, D, N), (1, 0, U, D, N), (0, 1, N, U, D), (0, 1, N, U, D), (1, 0, U, U, N), (0, 1, N, U, U),
-              (1, 0, D, U, N), (0, 1, N, D, U)]
-    bufs = []
-    for (ta, tb, M, Nn, K) in shapes:
-        A = torch.randn((K, M) if ta else (M, K), device=dev)
-        B = torch.randn((Nn, K) if tb else (K, Nn), device=dev)
-        bufs.append((ta, tb, M, Nn, K, A, B, torch.empty(M, Nn, device=dev)))
-    flops = sum(2.0 * M * Nn * K for (_, _, M, Nn, K) in shapes) * len(layers)
+    g = torch.Generator().manual_seed(5)
+    rnd = lambda *s: (torch.randn(*s, generator=g) * 0.05).to(dev)
+    P = dict(V1=rnd(D, U), g1=torch.ones(U, device=dev), b1=torch.zeros(U, device=dev), V2=rnd(U, U), g2=torch.ones(U, device=dev),
+             b2=torch.zeros(U, device=dev), Ks=rnd(U, D), bs=torch.zeros(D, device=dev), Kt=rnd(U, D), bt=torch.zeros(D, device=dev))
+    G = {k: torch.empty_like(v) for k, v in P.items()}
+    x, dy, dx = rnd(N, D), rnd(N, D), torch.empty(N, D, device=dev)
+    y, ld, ld2, dld = torch.empty(N, D, device=dev), torch.zeros(N, device=dev), torch.empty(N, device=dev), torch.ones(N, device=dev)
+    ws = [torch.empty(_lib.query('bruno_coupling_dense_ws_floats', N, D, U), device=dev) for _ in layers]
+    ws2 = torch.empty(_lib.query('bruno_coupling_dense_bwd_ws_floats', N, D, U), device=dev)
+    # useful FLOPs of the 12 products of a coupling (4 forward, 8 backward)
+    flops = 2.0 * N * (3 * (D * U + U * U + 2 * U * D)) * len(layers)
 
     def seq():
-        for _ in layers:
-            for (ta, tb, M, Nn, K, A, B, C) in bufs:
-                _lib.call('bruno_sgemm', ta, tb, M, Nn, K, A, A.shape[1], B, B.shape[1], C, Nn, None, None, 0, 0)
+        for i, _ in enumerate(layers):
+            _lib.call('bruno_coupling_dense_fwd', x, ld, y, ld2, N, D, U, 4 + (i & 1), 0, P['V1'], P['g1'], P['b1'], P['V2'], P['g2'],
+                      P['b2'], P['Ks'], P['bs'], P['Kt'], P['bt'], ws[i])
+        for i in reversed(range(len(layers))):
+            _lib.call('bruno_coupling_dense_bwd', x, dy, dld, N, D, U, 4 + (i & 1), P['V1'], P['g1'], P['b1'], P['V2'], P['g2'], P['b2'],
+                      P['Ks'], P['Kt'], ws[i], ws2, dx, G['V1'], G['g1'], G['b1'], G['V2'], G['g2'], G['b2'], G['Ks'], G['bs'], G['Kt'],
+                      G['bt'])
 
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         seq()
+        torch.cuda.synchronize()
+        l0 = _lib.query('bruno_launch_count')
+        seq()
+        launches = _lib.query('bruno_launch_count') - l0
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, stream=side):
@@ -160,7 +170,7 @@ def dense_gemm_sequence_graph_ms(cfg, dev, rows, reps=10):
         graph.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps, len(shapes) * len(layers), flops
+    return e0.elapsed_time(e1) / reps, launches, flops
 
 
 def conv_sequence_graph_ms(cfg, dev, reps=10, direction=None, height=None):
@@ -449,7 +459,7 @@ def main():
         prof[name] = {'total_ms': tot.value, 'launches': cnt.value}
     _lib.query('bruno_profile_enable', 0)
     conv_graph_ms, conv_graph_launches = conv_sequence_graph_ms(cfg, dev)
-    dense_ms, dense_launches, dense_flops = dense_gemm_sequence_graph_ms(cfg, dev, B * T)
+    dense_ms, dense_launches, dense_flops = dense_coupling_sequence_graph_ms(cfg, dev, B * T)
 
     # The reference's own nr_gpu semantics (config_rnn/train.py:184: ONE batch of `batch_size` sequences, np.split over the
     # GPUs) = strong scaling: measured in the same run with the global batch of --batch sequences split over the ranks.
@@ -629,15 +639,18 @@ def main():
                                                'algorithmic FLOPs = those of the forward convolutions',
                                         'ncu': 'profiles/r02_wgrad_line_ncu_summary.txt: tensor pipe active 86.5 %'}
                            if w['total_ms'] > 0 else None)(prof['conv3x3_wgrad']),
-        'roofline_dense': ({'bound': 'tensor', 'kernel': 'tf32x3_gemm_kernel (3xTF32 tcgen05 GEMM, split-K inside a thread-block cluster)',
+        'roofline_dense': ({'bound': 'tensor',
+                            'kernel': 'tf32x3_gemm_kernel (3xTF32 tcgen05 GEMM, split-K inside a thread-block cluster, paired products) '
+                                      'inside bruno_coupling_dense_fwd / _bwd',
                             'achieved': dense_flops / (dense_ms * 1e-3) / 1e12, 'peak': peak_burst / 6.0, 'unit': 'TFLOP/s',
                             'frac': dense_flops / (dense_ms * 1e-3) / 1e12 / (peak_burst / 6.0),
                             'peak_source': 'derived: measured bf16 burst peak / 2 (TF32 rate) / 3 (tensor products per fp32-accurate product); '
                                            'no TF32 peak is measured on this pool',
-                            'launches': dense_launches, 'avg_launch_us': 1e3 * dense_ms / dense_launches, 'ms_per_step': dense_ms,
-                            'share_of_step': dense_ms / (ms_train / steps),
-                            'how': 'the dense-coupling GEMMs of one training step (shapes and order of csrc/dense.cu, useful FLOPs 2MNK) '
-                                   'replayed from one CUDA graph; these GEMMs are latency-bound (0.4-0.6 GFLOP each), see DESIGN 5.2b'}
+                            'launches': dense_launches, 'ms_per_step': dense_ms, 'share_of_step': dense_ms / (ms_train / steps),
+                            'how': 'ALL kernels of the dense couplings of one training step (forward calls, then backward calls in '
+                                   'reverse order: 9 GEMM launches + 14 elementwise / reduction launches per coupling) replayed from one '
+                                   'CUDA graph; useful FLOPs = the 12 matrix products per coupling (2MNK); the products are '
+                                   'latency-bound (0.4-0.6 GFLOP each), see DESIGN 5.2b'}
                            if dense_launches else None),
         'roofline_process_scan': scan,
         'kernel_time_ms_per_step': {k: v['total_ms'] / steps for k, v in prof.items()},

@@ -403,6 +403,27 @@ static int gemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, 
   return check_launch("sgemm_kernel");
 }
 
+// Two GEMMs of one shape as ONE launch of the tcgen05 kernel (GemmPair, dense_gemm.cuh): mode 1 = side by side (same flags,
+// own A / B / C / bias), mode 2 = C = op(A) op(B) + op(A2) op(B2).  Returns 1 when launched, 0 when the caller has to run
+// the two GEMMs one after the other (operands not 16-byte aligned, another GEMM variant selected, cluster launch refused),
+// a negative code on error.
+static int gemm_pair(int mode, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                     int ldc, const GemmEpi& ep, const float* A2, const float* B2, float* C2, const float* bias2, cudaStream_t st) {
+  const bool vec_ok = aligned16(A) && aligned16(B) && aligned16(A2) && aligned16(B2) && lda % 4 == 0 && ldb % 4 == 0 && K % 4 == 0 &&
+                      (ta ? M % 4 == 0 : true) && (tb ? true : N % 4 == 0) && !ep.a_kscale;
+  if (!vec_ok || g_gemm_variant != 1) return 0;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  const Workspace wk = sk_workspace(st);
+  if (wk) sms = wk.sms;
+  else cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const GemmPair pair{mode, A2, B2, C2, bias2};
+  int taken = 0;
+  const int rc = gemm_tf32x3(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, ep, nullptr, 0, nullptr, 0, sms, true, st, &taken, &pair);
+  if (rc) return rc < 0 ? rc : -1;
+  return taken;
+}
+
 __device__ __forceinline__ float dense_mask_b(int mask_type, int d) {
   // nn_extra_nvp.py:199-221: 'even' -> b = idx % 2, 'odd' -> 1 - idx % 2 on the flattened (h, w, c) index
   return mask_type == BRUNO_MASK_EVEN ? static_cast<float>(d & 1) : static_cast<float>(1 - (d & 1));
@@ -526,35 +547,87 @@ __global__ void elu_bwd_kernel(const float* __restrict__ pre, const float* __res
 // grid (N/32, MS): block (x, y) reduces rows [y M/MS, (y+1) M/MS) of 32 columns with four loads in flight per thread;
 // with MS > 1 the partials go to the workspace and the last block of a column group (ticket) adds them in y order.
 constexpr int CR_MAX_SPLIT = 16;
+// The column reduction also PRODUCES its operand where that is an elementwise map (one pass over the matrix, one launch
+// instead of two or three), same summation order in every mode (bit-identical sums):
+//   CR_PLAIN   : v = A[m,j], w = Bm[m,j]                                        out1 = sum v, out2 = sum v w
+//   CR_ELU_BWD : v = A[m,j] ELU'(Bm[m,j]) (A = dh, Bm = pre), stored to st0     out1 = sum v (db), out2 = sum v pre (r1)
+//   CR_COUPLING: the dense coupling backward (dense_coupling_bwd_kernel) at (m,j); dx -> st0, ds_pre -> st1, dt_pre -> st2
+//                                                                               out1 = sum ds_pre (dbs), out2 = sum dt_pre (dbt)
+enum { CR_PLAIN = 0, CR_ELU_BWD = 1, CR_COUPLING = 2 };
+struct ColReduceIo {
+  const float* A;      // CR_PLAIN: the matrix; CR_ELU_BWD: dh; CR_COUPLING: dy
+  const float* Bm;     // CR_PLAIN: second factor or null; CR_ELU_BWD: pre; CR_COUPLING: s_pre
+  const float* x;      // CR_COUPLING
+  const float* dld;    // CR_COUPLING: [M]
+  float *st0, *st1, *st2;
+  int mask_type;
+};
+template <int MODE>
 __global__ void __launch_bounds__(256)
-col_reduce_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ out1,
-                  float* __restrict__ out2, int M, int N, float* __restrict__ part, unsigned* __restrict__ tickets) {
+col_reduce_kernel(ColReduceIo io, float* __restrict__ out1, float* __restrict__ out2, int M, int N, float* __restrict__ part,
+                  unsigned* __restrict__ tickets) {
   __shared__ float sh[8][33];
   __shared__ int s_last;
+  const float* __restrict__ A = io.A;
+  const float* __restrict__ Bm = io.Bm;
   const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + c;
   const int MS = gridDim.y;
   const int rows = (M + MS - 1) / MS;
   const int m_begin = blockIdx.y * rows, m_end = min(M, m_begin + rows);
+  const bool two = MODE != CR_PLAIN || Bm != nullptr;
+  const bool masked = MODE == CR_COUPLING && dense_mask_b(io.mask_type, j) == 0.f;   // the transformed half of the columns
   float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
   if (j < N) {
     for (int m = m_begin + rg; m < m_end; m += 32) {
-      float v[4], w[4];
+      float v[4], w[4], xv[4], dl[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int mm = m + 8 * u;
-        v[u] = mm < m_end ? A[static_cast<size_t>(mm) * N + j] : 0.f;
-        w[u] = (Bm && mm < m_end) ? Bm[static_cast<size_t>(mm) * N + j] : 0.f;
+        const bool on = mm < m_end;
+        const size_t o = static_cast<size_t>(mm) * N + j;
+        v[u] = on ? A[o] : 0.f;
+        w[u] = (on && (MODE != CR_PLAIN || Bm) && (MODE != CR_COUPLING || masked)) ? Bm[o] : 0.f;
+        if (MODE == CR_COUPLING) {
+          xv[u] = (on && masked) ? io.x[o] : 0.f;
+          dl[u] = (on && masked) ? io.dld[mm] : 0.f;
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        a[u] += v[u];
-        b[u] = fmaf(v[u], w[u], b[u]);
+        const int mm = m + 8 * u;
+        const size_t o = static_cast<size_t>(mm) * N + j;
+        if (MODE == CR_PLAIN) {
+          a[u] += v[u];
+          b[u] = fmaf(v[u], w[u], b[u]);
+        } else if (MODE == CR_ELU_BWD) {
+          const float d = v[u] * (w[u] > 0.f ? 1.f : expf(w[u]));          // elu_bwd_kernel
+          if (mm < m_end) io.st0[o] = d;
+          a[u] += d;
+          b[u] = fmaf(d, w[u], b[u]);
+        } else {
+          const float g = v[u];                                              // dense_coupling_bwd_kernel
+          float dxv = g, dsp = 0.f, dtp = 0.f;
+          if (masked) {
+            const float s_ = tanhf(w[u]);
+            const float es = expf(s_);
+            dxv = g * es;
+            dtp = g;
+            dsp = (g * xv[u] * es + dl[u]) * (1.f - s_ * s_);
+          }
+          if (mm < m_end) {
+            io.st0[o] = dxv;
+            io.st1[o] = dsp;
+            io.st2[o] = dtp;
+          }
+          a[u] += dsp;                                                       // rows past m_end: g = 0 -> both 0
+          b[u] += dtp;
+        }
       }
     }
   }
   float sa = col_block_reduce((a[0] + a[1]) + (a[2] + a[3]), sh);
-  float sb = Bm ? col_block_reduce((b[0] + b[1]) + (b[2] + b[3]), sh) : 0.f;
+  float sb = two ? col_block_reduce((b[0] + b[1]) + (b[2] + b[3]), sh) : 0.f;
   if (MS > 1) {
     // partial layout [column group][y][2][32]
     float* mine = part + (static_cast<size_t>(blockIdx.x) * MS + blockIdx.y) * 64;
@@ -585,7 +658,8 @@ col_reduce_kernel(const float* __restrict__ A, const float* __restrict__ Bm, flo
   }
 }
 
-static void col_reduce(const float* A, const float* Bm, float* out1, float* out2, int M, int N, cudaStream_t st) {
+template <int MODE>
+static void col_reduce_io(const ColReduceIo& io, float* out1, float* out2, int M, int N, cudaStream_t st) {
   const int groups = ceil_div(N, 32);
   int ms = 1;
   const Workspace wk = sk_workspace(st);
@@ -593,8 +667,20 @@ static void col_reduce(const float* A, const float* Bm, float* out1, float* out2
     ms = max(1, min(CR_MAX_SPLIT, min(M / 32, (2 * wk.sms) / groups)));
     while (ms > 1 && static_cast<size_t>(groups) * ms * 64 > CR_WS_FLOATS) --ms;
   }
-  col_reduce_kernel<<<dim3(groups, ms), 256, 0, st>>>(A, Bm, out1, out2, M, N, wk ? wk.ws + SK_WS_FLOATS : nullptr,
-                                                      wk ? wk.tickets + SK_MAX_TILES : nullptr);
+  col_reduce_kernel<MODE><<<dim3(groups, ms), 256, 0, st>>>(io, out1, out2, M, N, wk ? wk.ws + SK_WS_FLOATS : nullptr,
+                                                            wk ? wk.tickets + SK_MAX_TILES : nullptr);
+}
+static void col_reduce(const float* A, const float* Bm, float* out1, float* out2, int M, int N, cudaStream_t st) {
+  col_reduce_io<CR_PLAIN>(ColReduceIo{A, Bm, nullptr, nullptr, nullptr, nullptr, nullptr, 0}, out1, out2, M, N, st);
+}
+// dpre = dh ELU'(pre), db = colsum(dpre), r1 = colsum(dpre pre) in one pass
+static void elu_bwd_col_reduce(const float* pre, const float* dh, float* dpre, float* db, float* r1, int M, int N, cudaStream_t st) {
+  col_reduce_io<CR_ELU_BWD>(ColReduceIo{dh, pre, nullptr, nullptr, dpre, nullptr, nullptr, 0}, db, r1, M, N, st);
+}
+// the dense coupling's elementwise backward with dbs = colsum(ds_pre), dbt = colsum(dt_pre) in one pass
+static void coupling_bwd_col_reduce(const float* x, const float* s_pre, const float* dy, const float* dld, float* dx, float* ds_pre,
+                                    float* dt_pre, float* dbs, float* dbt, int M, int N, int mask_type, cudaStream_t st) {
+  col_reduce_io<CR_COUPLING>(ColReduceIo{dy, s_pre, x, dld, dx, ds_pre, dt_pre, mask_type}, dbs, dbt, M, N, st);
 }
 
 // weight-norm backward for dense_wn.  dVraw = x^T dpre;  r1 = colsum(dpre * pre);  db = colsum(dpre).
@@ -798,8 +884,14 @@ int bruno_coupling_dense_fwd(const float* x, const float* ld_in, float* y, float
   int rc;
   if ((rc = gemm(false, false, N, U, D, w.xm, D, V1, U, w.h1, U, GemmEpi{w.sc1, b1, w.pre1, 1, 0, nullptr}, st))) return rc;
   if ((rc = gemm(false, false, N, U, U, w.h1, U, V2, U, w.h2, U, GemmEpi{w.sc2, b2, w.pre2, 1, 0, nullptr}, st))) return rc;
-  if ((rc = gemm(false, false, N, D, U, w.h2, U, Ks, D, w.s_pre, D, GemmEpi{nullptr, bs, nullptr, 0, 0, nullptr}, st))) return rc;
-  if ((rc = gemm(false, false, N, D, U, w.h2, U, Kt, D, w.t_pre, D, GemmEpi{nullptr, bt, nullptr, 0, 0, nullptr}, st))) return rc;
+  // the s and t heads read the same h2: one launch (130 tiles: no split-K at all), else two
+  rc = gemm_pair(1, false, false, N, D, U, w.h2, U, Ks, D, w.s_pre, D, GemmEpi{nullptr, bs, nullptr, 0, 0, nullptr}, w.h2, Kt, w.t_pre,
+                 bt, st);
+  if (rc < 0) return rc;
+  if (rc == 0) {
+    if ((rc = gemm(false, false, N, D, U, w.h2, U, Ks, D, w.s_pre, D, GemmEpi{nullptr, bs, nullptr, 0, 0, nullptr}, st))) return rc;
+    if ((rc = gemm(false, false, N, D, U, w.h2, U, Kt, D, w.t_pre, D, GemmEpi{nullptr, bt, nullptr, 0, 0, nullptr}, st))) return rc;
+  }
   dense_coupling_kernel<<<N, 256, 0, st>>>(x, w.s_pre, w.t_pre, ld_in, y, ld_out, D, mask_type, inverse);
   return check_launch("dense_coupling_kernel");
 }
@@ -825,17 +917,25 @@ int bruno_coupling_dense_bwd(const float* x, const float* dy, const float* dld, 
   int rc;
   const GemmEpi plain{nullptr, nullptr, nullptr, 0, 0, nullptr};
   const GemmEpi accum{nullptr, nullptr, nullptr, 0, 1, nullptr};
-  dense_coupling_bwd_kernel<<<nblk(ND), 256, 0, st>>>(x, w.s_pre, dy, dld, dx, ds_pre, dt_pre, ND, D, mask_type);
+  // elementwise coupling backward + the head-bias gradients (column sums of ds_pre, dt_pre) in one pass
+  coupling_bwd_col_reduce(x, w.s_pre, dy, dld, dx, ds_pre, dt_pre, dbs, dbt, N, D, mask_type, st);
   // heads
-  if ((rc = gemm(true, false, U, D, N, w.h2, U, ds_pre, D, dKs, D, plain, st))) return rc;
-  if ((rc = gemm(true, false, U, D, N, w.h2, U, dt_pre, D, dKt, D, plain, st))) return rc;
-  col_reduce(ds_pre, nullptr, dbs, nullptr, N, D, st);
-  col_reduce(dt_pre, nullptr, dbt, nullptr, N, D, st);
-  if ((rc = gemm(false, true, N, U, D, ds_pre, D, Ks, D, dh, U, plain, st))) return rc;
-  if ((rc = gemm(false, true, N, U, D, dt_pre, D, Kt, D, dh, U, accum, st))) return rc;
+  // dKs and dKt (same h2^T) side by side in one launch; dh = ds Ks^T + dt Kt^T as one launch whose split-K slices come from
+  // the two products; each falls back to two launches when the pair cannot run (gemm_pair)
+  rc = gemm_pair(1, true, false, U, D, N, w.h2, U, ds_pre, D, dKs, D, plain, w.h2, dt_pre, dKt, nullptr, st);
+  if (rc < 0) return rc;
+  if (rc == 0) {
+    if ((rc = gemm(true, false, U, D, N, w.h2, U, ds_pre, D, dKs, D, plain, st))) return rc;
+    if ((rc = gemm(true, false, U, D, N, w.h2, U, dt_pre, D, dKt, D, plain, st))) return rc;
+  }
+  rc = gemm_pair(2, false, true, N, U, D, ds_pre, D, Ks, D, dh, U, plain, dt_pre, Kt, nullptr, nullptr, st);
+  if (rc < 0) return rc;
+  if (rc == 0) {
+    if ((rc = gemm(false, true, N, U, D, ds_pre, D, Ks, D, dh, U, plain, st))) return rc;
+    if ((rc = gemm(false, true, N, U, D, dt_pre, D, Kt, D, dh, U, accum, st))) return rc;
+  }
   // d2
-  elu_bwd_kernel<<<nblk(NU), 256, 0, st>>>(w.pre2, dh, dpre, NU);
-  col_reduce(dpre, w.pre2, db2, r1, N, U, st);
+  elu_bwd_col_reduce(w.pre2, dh, dpre, db2, r1, N, U, st);          // dpre = dh ELU'(pre2), db2, r1 in one pass
   if ((rc = gemm(true, false, U, U, N, w.h1, U, dpre, U, dV2, U, plain, st))) return rc;
   dense_wn_bwd_kernel<<<nblk(static_cast<size_t>(U) * U), 256, 0, st>>>(V2, g2, b2, w.sc2, w.in2, r1, db2, dV2, dg2, U, U);
   {
@@ -844,8 +944,7 @@ int bruno_coupling_dense_bwd(const float* x, const float* dy, const float* dld, 
     if ((rc = gemm(false, true, N, U, U, dpre, U, V2, U, dh, U, e, st))) return rc;
   }
   // d1
-  elu_bwd_kernel<<<nblk(NU), 256, 0, st>>>(w.pre1, dh, dpre, NU);
-  col_reduce(dpre, w.pre1, db1, r1, N, U, st);
+  elu_bwd_col_reduce(w.pre1, dh, dpre, db1, r1, N, U, st);
   if ((rc = gemm(true, false, D, U, N, w.xm, D, dpre, U, dV1, U, plain, st))) return rc;
   dense_wn_bwd_kernel<<<nblk(static_cast<size_t>(D) * U), 256, 0, st>>>(V1, g1, b1, w.sc1, w.in1, r1, db1, dV1, dg1, D, U);
   {

@@ -200,18 +200,35 @@ __device__ __forceinline__ void with_act(int act, F f) {
 
 template <bool TA, bool TB, int BN>
 __global__ void __launch_bounds__(TG_THREADS, 1)
-tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                   float* __restrict__ C, int ldc, GemmEpi ep, int kchunk, float* __restrict__ ws, unsigned* __restrict__ tickets,
-                   int cluster_reduce, long long* trace_buf) {
+tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A_, int lda, const float* __restrict__ B_, int ldb,
+                   float* __restrict__ C_, int ldc, GemmEpi ep, int kchunk, float* __restrict__ ws, unsigned* __restrict__ tickets,
+                   int cluster_reduce, GemmPair pair, int nx1, long long* trace_buf) {
   constexpr int B_TILE_BYTES = BN * TG_BK * 4;
   constexpr int STAGE_BYTES = 2 * TG_TILE_BYTES + 2 * B_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
   extern __shared__ uint8_t tg_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tg_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   TgSmem* cs = reinterpret_cast<TgSmem*>(smem + TG_STAGES * STAGE_BYTES);
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * BN;
+  // pair.mode 1: the upper half of gridDim.x is the second problem; mode 2: the upper half of the split-K slices multiplies
+  // the second operand pair into the same tile (GemmPair, dense_gemm.cuh)
+  const float* __restrict__ A = A_;
+  const float* __restrict__ B = B_;
+  float* __restrict__ C = C_;
+  int bx = blockIdx.x, bz = blockIdx.z;
+  if (pair.mode == 1 && bx >= nx1) {
+    bx -= nx1;
+    A = pair.A2;
+    B = pair.B2;
+    C = pair.C2;
+    ep.bias = pair.bias2;
+  } else if (pair.mode == 2 && bz >= static_cast<int>(gridDim.z >> 1)) {
+    bz -= static_cast<int>(gridDim.z >> 1);
+    A = pair.A2;
+    B = pair.B2;
+  }
+  const int m0 = blockIdx.y * TG_BM, n0 = bx * BN;
   const int nk = (K + TG_BK - 1) / TG_BK;
-  const int kt0 = blockIdx.z * kchunk, kt1 = min(nk, kt0 + kchunk);
+  const int kt0 = bz * kchunk, kt1 = min(nk, kt0 + kchunk);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TG_STAGES; ++s) {
@@ -573,7 +590,8 @@ static std::atomic<unsigned> g_cluster_refused{0u};
 
 template <bool TA, bool TB, int BN>
 int launch_tf32_bn(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& ep,
-                   float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster, cudaStream_t st) {
+                   float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster, cudaStream_t st,
+                   const GemmPair* pair) {
   // + the push buffer of the cluster split-K reduction (64-column tiles only): <= TG_BM + TG_MAX_SPLIT rows of BN + 4 floats
   constexpr size_t push_bytes = BN == 64 ? static_cast<size_t>(TG_BM + TG_MAX_SPLIT) * (BN + 4) * 4 : 0;
   constexpr size_t smem = 1024 + TG_STAGES * (2 * TG_TILE_BYTES + 2 * BN * TG_BK * 4) + 128 + push_bytes + 64;
@@ -583,7 +601,10 @@ int launch_tf32_bn(int M, int N, int K, const float* A, int lda, const float* B,
   once.run([&] {
     cudaFuncSetAttribute(tf32x3_gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   });
-  const int nx = ceil_div(N, BN), ny = ceil_div(M, TG_BM), tiles = nx * ny, nk = ceil_div(K, TG_BK);
+  // two GEMMs in one launch (GemmPair) only on the cluster path; otherwise 1 = "not taken": the caller launches them one by one
+  const int mode = pair ? pair->mode : 0;
+  if (mode && !cluster) return 1;
+  const int nx = ceil_div(N, BN), ny = ceil_div(M, TG_BM), nxg = mode == 1 ? 2 * nx : nx, tiles = nxg * ny, nk = ceil_div(K, TG_BK);
   static const char* force_s = getenv("BRUNO_TF32_SPLIT");
   const bool have_ws = ws && tickets && tiles <= max_tiles;
   // split-K so that ~one CTA per SM is busy; at least two K tiles per CTA
@@ -601,11 +622,13 @@ int launch_tf32_bn(int M, int N, int K, const float* A, int lda, const float* B,
   };
   auto launch = [&](bool with_cluster) {
     int S = split_for(with_cluster);
+    if (mode == 2) S = S / 2 < 1 ? 1 : S / 2;                          // slices per product
     const int kchunk = ceil_div(nk, S);
     S = ceil_div(nk, kchunk);
+    if (mode == 2) S *= 2;
     if (with_cluster && S > 1 && (g_cluster_refused.load(std::memory_order_relaxed) >> S & 1u)) return cudaErrorInvalidClusterSize;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(nx, ny, S);
+    cfg.gridDim = dim3(nxg, ny, S);
     cfg.blockDim = dim3(TG_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -622,7 +645,8 @@ int launch_tf32_bn(int M, int N, int K, const float* A, int lda, const float* B,
     }
     cfg.attrs = attr;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, tf32x3_gemm_kernel<TA, TB, BN>, M, N, K, A, lda, B, ldb, C, ldc, ep, kchunk, ws,
-                                             tickets, with_cluster ? 1 : 0, g_gemm_trace_host);
+                                             tickets, with_cluster ? 1 : 0, pair ? *pair : GemmPair{0, nullptr, nullptr, nullptr, nullptr},
+                                             nx, g_gemm_trace_host);
     if (e != cudaSuccess && with_cluster && S > 1) {
       cudaGetLastError();
       g_cluster_refused.fetch_or(1u << S, std::memory_order_relaxed);
@@ -630,21 +654,27 @@ int launch_tf32_bn(int M, int N, int K, const float* A, int lda, const float* B,
     return e;
   };
   if (cluster && launch(true) == cudaSuccess) return check_launch("tf32x3_gemm_kernel");
+  if (mode) return 1;
   launch(false);                                                       // workspace + ticket fix-up (or un-split)
   return check_launch("tf32x3_gemm_kernel");
 }
 
 template <bool TA, bool TB>
 int launch_tf32(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& ep,
-                float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster, cudaStream_t st, int* taken) {
+                float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster, cudaStream_t st, int* taken,
+                const GemmPair* pair) {
   *taken = 1;
   // 64-column tiles while 128-column tiles would leave most SMs without work
-  const int tiles128 = ceil_div(N, 128) * ceil_div(M, TG_BM);
+  const int tiles128 = ceil_div(N, 128) * ceil_div(M, TG_BM) * (pair && pair->mode == 1 ? 2 : 1);
   static const char* force_bn = getenv("BRUNO_TF32_BN");
   const bool want64 = force_bn ? atoi(force_bn) == 64 : (tiles128 * 2 <= sms || N <= 64);
-  if (want64)
-    return launch_tf32_bn<TA, TB, 64>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st);
-  return launch_tf32_bn<TA, TB, 128>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st);
+  const int rc = want64 ? launch_tf32_bn<TA, TB, 64>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, pair)
+                        : launch_tf32_bn<TA, TB, 128>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, pair);
+  if (rc == 1) {                                                       // a pair that cannot run as one launch
+    *taken = 0;
+    return 0;
+  }
+  return rc;
 }
 
 }  // namespace
@@ -653,12 +683,12 @@ void gemm_tf32x3_set_trace(long long* device_buffer) { g_gemm_trace_host = devic
 
 int gemm_tf32x3(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 const GemmEpi& ep, float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster,
-                cudaStream_t st, int* taken) {
+                cudaStream_t st, int* taken, const GemmPair* pair) {
   *taken = 0;
-  if (!ta && !tb) return launch_tf32<false, false>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken);
-  if (ta && !tb) return launch_tf32<true, false>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken);
-  if (!ta && tb) return launch_tf32<false, true>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken);
-  return launch_tf32<true, true>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken);
+  if (!ta && !tb) return launch_tf32<false, false>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken, pair);
+  if (ta && !tb) return launch_tf32<true, false>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken, pair);
+  if (!ta && tb) return launch_tf32<false, true>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken, pair);
+  return launch_tf32<true, true>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, taken, pair);
 }
 
 }  // namespace bruno

@@ -24,7 +24,11 @@ _INIT_MODE = [False]                   # arg_scope([conv2d_wn, dense_wn], init=i
 #   'bf16' (default, production): tcgen05 tensor cores, bf16 operands / activations, fp32 accumulation.
 #   'fp32' (verification, inference only): the same layer evaluated entirely in fp32 on CUDA cores (nine tap GEMMs per
 #          convolution through bruno_sgemm on fp32 slabs) -- slow, used by the parity tests to show that the only
-#          difference between the production path and the reference arithmetic is the declared bf16 rounding.
+#          difference between the production path and the reference arithmetic is the declared reduced precision.
+#          The mode also routes every dense-path GEMM to the strict-fp32 FFMA kernel (bruno_debug_gemm_variant(0); the
+#          production GEMM is the 3xTF32 tensor-core split, ~8x the rounding error of an fp32 FMA chain, which the
+#          ill-conditioned Gaussian latent log-density of a sampled image amplifies to 6e-4 .. 1.2e-3 relative against
+#          5e-6 for the strict path, tests/test_reference_fixtures_gpu.py::test_sampling_branch_matches_reference).
 _PRECISION = ['bf16']
 
 
@@ -34,13 +38,21 @@ class precision(object):
     def __init__(self, p):
         assert p in ('bf16', 'fp32')
         self.p = p
+        self.prev_variant = None
 
     def __enter__(self):
         self.prev = _PRECISION[0]
         _PRECISION[0] = self.p
+        lib = _lib.load()
+        if self.p == 'fp32' and hasattr(lib, 'bruno_debug_gemm_variant'):    # absent in a -DBRUNO_NO_DEBUG build
+            self.prev_variant = lib.bruno_debug_gemm_variant(-1)
+            lib.bruno_debug_gemm_variant(0)
 
     def __exit__(self, *a):
         _PRECISION[0] = self.prev
+        if self.prev_variant is not None:
+            _lib.load().bruno_debug_gemm_variant(self.prev_variant)
+            self.prev_variant = None
 
 
 class init_scope(object):

@@ -66,3 +66,41 @@ def test_cluster_split_k_equals_workspace_split_k_bit_for_bit(ta, tb, M, N, K):
         assert torch.equal(a, b), (a - b).abs().max().item()
     ref = (A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double())
     assert torch.allclose(out[1][0].double(), ref, rtol=1e-4, atol=1e-3 * (K ** 0.5))
+
+
+@pytest.mark.parametrize('N,D,U', [(640, 784, 512), (40, 784, 512), (24, 48, 32)])
+def test_dense_coupling_paired_gemms_equal_separate_launches(N, D, U):
+    """The dense coupling runs its s / t head GEMMs (forward), dKs / dKt and dh = ds Ks^T + dt Kt^T (backward) as ONE launch
+    each (GemmPair); GEMM variant 2 has no pairs (every product its own launch, split-K through the workspace).  Same fp32
+    results up to the summation grouping -- outputs, input gradient and all ten parameter gradients."""
+    from bruno_b200 import _lib, nn_extra_nvp as nvp
+    lib = _lib.load()
+    if not hasattr(lib, 'bruno_debug_gemm_variant'):
+        pytest.skip('library built with -DBRUNO_NO_DEBUG')
+    g = torch.Generator().manual_seed(N + D + U)
+    x0 = torch.randn(N, D, generator=g).cuda()
+    layer = nvp.CouplingLayerDense('even', name='t', n_units=U)
+    layer._build(D, x0.device)
+    with torch.no_grad():
+        for n in layer._PNAMES:                       # heads are zero-initialised in the reference: move everything off zero
+            p = getattr(layer, n)
+            p.copy_(torch.randn(p.shape, generator=g).cuda() * (0.05 if n in ('Ks', 'Kt', 'bs', 'bt') else 0.3) +
+                    (1.0 if n in ('g1', 'g2') else 0.0))
+    res, launches = {}, {}
+    try:
+        for variant in (1, 2):
+            lib.bruno_debug_gemm_variant(variant)
+            x = x0.clone().requires_grad_(True)
+            params = [getattr(layer, n).requires_grad_(True) for n in layer._PNAMES]
+            l0 = _lib.query('bruno_launch_count')
+            y, _, ld = layer.forward_and_jacobian(x, None, torch.zeros(N, device='cuda'))
+            loss = (y * torch.linspace(-1, 1, D, device='cuda')).sum() + (ld * torch.linspace(0.5, 1.5, N, device='cuda')).sum()
+            grads = torch.autograd.grad(loss, [x] + params)
+            launches[variant] = _lib.query('bruno_launch_count') - l0
+            res[variant] = [y.detach(), ld.detach()] + [t.detach().clone() for t in grads]
+    finally:
+        lib.bruno_debug_gemm_variant(1)
+    assert launches[2] - launches[1] == 3, launches      # s|t heads, dKs|dKt, dh: three launches fewer with the pairs
+    for a, b in zip(res[1], res[2]):
+        scale = b.abs().max().item() + 1e-30
+        assert (a - b).abs().max().item() <= 2e-5 * scale, ((a - b).abs().max().item(), scale)

@@ -169,5 +169,7 @@ def test_sampling_branch_matches_reference(golden_dir, name):
           'fp32 mode %.2e' % (name, ex, ex32, el32))
     # pixel units in [0, 256): the fp32 path must reproduce the reference's samples to 1e-3 of the pixel range
     assert ex32 <= 0.25
-    # the Gaussian latent log-prob is quadratic in z (see tests/test_benchmark_shape_gpu.py): 1e-3 instead of 2e-4
-    assert el32 <= (1e-3 if name.endswith('_gp') else 2e-4)
+    # fp32 mode = strict-fp32 GEMMs as well: measured 2e-6 .. 3e-5 on the three configs.  (With the production 3xTF32
+    # GEMM the Gaussian latent log-prob of the sample, quadratic in z, is at 6e-4 .. 1.2e-3 depending on the split-K
+    # grouping; the strict path at 5e-6 -- the looser production bound is the declared reduced-precision bound.)
+    assert el32 <= 2e-4
