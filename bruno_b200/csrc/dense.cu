@@ -796,6 +796,12 @@ int bruno_debug_gemm_variant(int variant) {
   return BRUNO_OK;
 }
 
+int bruno_debug_gemm_plan(int M, int N, int K, int pair_mode, int sms, int* out6) {
+  BRUNO_REQUIRE(M > 0 && N > 0 && K > 0 && pair_mode >= 0 && pair_mode <= 2 && sms > 0 && out6, "bruno_debug_gemm_plan: bad arguments");
+  gemm_tf32x3_plan(M, N, K, pair_mode, sms, out6);
+  return BRUNO_OK;
+}
+
 int bruno_debug_gemm_trace(long long* device_buffer) {
   gemm_tf32x3_set_trace(device_buffer);
   return BRUNO_OK;

@@ -46,5 +46,8 @@ int gemm_tf32x3(bool ta, bool tb, int M, int N, int K, const float* A, int lda, 
                 cudaStream_t st, int* taken, const GemmPair* pair = nullptr);
 
 void gemm_tf32x3_set_trace(long long* device_buffer);
+// launch geometry of the cluster path for a shape: out = {BN, gridDim.x, gridDim.y, gridDim.z (0: the pair cannot run as one
+// launch), K tiles per split-K slice, cluster size}
+void gemm_tf32x3_plan(int M, int N, int K, int pair_mode, int sms, int out[6]);
 
 }  // namespace bruno

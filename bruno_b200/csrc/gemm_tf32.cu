@@ -585,6 +585,33 @@ tf32x3_gemm_kernel(int M, int N, int K, const float* __restrict__ A_, int lda, c
   }
 }
 
+// ---- launch geometry (pure host arithmetic: also exposed as bruno_debug_gemm_plan and tested without a GPU) ----
+// 64-column tiles while 128-column tiles would leave most SMs without work
+static int plan_bn(int M, int N, int sms, int pair_mode) {
+  static const char* force_bn = getenv("BRUNO_TF32_BN");
+  if (force_bn) return atoi(force_bn) == 64 ? 64 : 128;
+  const int tiles128 = ceil_div(N, 128) * ceil_div(M, TG_BM) * (pair_mode == 1 ? 2 : 1);
+  return (tiles128 * 2 <= sms || N <= 64) ? 64 : 128;
+}
+// split-K so that ~one CTA per SM is busy, at least two K tiles per CTA, at most TG_MAX_SPLIT slices (= the cluster size);
+// pair mode 2 gives each of the two products half of the slices.  `split_ok`: a cluster launch, or a workspace that holds
+// the partial tiles (`ws_floats`; 0 = cluster).  Returns gridDim.z and *kchunk = K tiles per slice.
+static int plan_split(int nk, int tiles, int sms, int pair_mode, bool split_ok, size_t ws_floats, int bn, int* kchunk) {
+  static const char* force_s = getenv("BRUNO_TF32_SPLIT");
+  int S = 1;
+  if (split_ok) {
+    S = force_s ? atoi(force_s) : sms / tiles;
+    const int smax = nk / 2 < TG_MAX_SPLIT ? nk / 2 : TG_MAX_SPLIT;
+    S = S > smax ? smax : S;
+    S = S < 1 ? 1 : S;
+    while (ws_floats && S > 1 && static_cast<size_t>(tiles) * S * TG_BM * bn > ws_floats) --S;
+  }
+  if (pair_mode == 2) S = S / 2 < 1 ? 1 : S / 2;                       // slices per product
+  *kchunk = ceil_div(nk, S);
+  S = ceil_div(nk, *kchunk);
+  return pair_mode == 2 ? 2 * S : S;
+}
+
 // cluster sizes whose launch failed on this process's device (bit S): never tried again (keeps stream captures clean)
 static std::atomic<unsigned> g_cluster_refused{0u};
 
@@ -605,27 +632,10 @@ int launch_tf32_bn(int M, int N, int K, const float* A, int lda, const float* B,
   const int mode = pair ? pair->mode : 0;
   if (mode && !cluster) return 1;
   const int nx = ceil_div(N, BN), ny = ceil_div(M, TG_BM), nxg = mode == 1 ? 2 * nx : nx, tiles = nxg * ny, nk = ceil_div(K, TG_BK);
-  static const char* force_s = getenv("BRUNO_TF32_SPLIT");
   const bool have_ws = ws && tickets && tiles <= max_tiles;
-  // split-K so that ~one CTA per SM is busy; at least two K tiles per CTA
-  auto split_for = [&](bool with_cluster) {
-    int S = 1;
-    if (with_cluster || have_ws) {
-      S = force_s ? atoi(force_s) : sms / tiles;
-      const int smax = nk / 2 < TG_MAX_SPLIT ? nk / 2 : TG_MAX_SPLIT;
-      S = S > smax ? smax : S;
-      S = S < 1 ? 1 : S;
-      if (!with_cluster)
-        while (S > 1 && static_cast<size_t>(tiles) * S * TG_BM * BN > ws_floats) --S;
-    }
-    return S;
-  };
   auto launch = [&](bool with_cluster) {
-    int S = split_for(with_cluster);
-    if (mode == 2) S = S / 2 < 1 ? 1 : S / 2;                          // slices per product
-    const int kchunk = ceil_div(nk, S);
-    S = ceil_div(nk, kchunk);
-    if (mode == 2) S *= 2;
+    int kchunk = nk;
+    const int S = plan_split(nk, tiles, sms, mode, with_cluster || have_ws, with_cluster ? 0 : ws_floats, BN, &kchunk);
     if (with_cluster && S > 1 && (g_cluster_refused.load(std::memory_order_relaxed) >> S & 1u)) return cudaErrorInvalidClusterSize;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nxg, ny, S);
@@ -664,10 +674,7 @@ int launch_tf32(int M, int N, int K, const float* A, int lda, const float* B, in
                 float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster, cudaStream_t st, int* taken,
                 const GemmPair* pair) {
   *taken = 1;
-  // 64-column tiles while 128-column tiles would leave most SMs without work
-  const int tiles128 = ceil_div(N, 128) * ceil_div(M, TG_BM) * (pair && pair->mode == 1 ? 2 : 1);
-  static const char* force_bn = getenv("BRUNO_TF32_BN");
-  const bool want64 = force_bn ? atoi(force_bn) == 64 : (tiles128 * 2 <= sms || N <= 64);
+  const bool want64 = plan_bn(M, N, sms, pair ? pair->mode : 0) == 64;
   const int rc = want64 ? launch_tf32_bn<TA, TB, 64>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, pair)
                         : launch_tf32_bn<TA, TB, 128>(M, N, K, A, lda, B, ldb, C, ldc, ep, ws, ws_floats, tickets, max_tiles, sms, cluster, st, pair);
   if (rc == 1) {                                                       // a pair that cannot run as one launch
@@ -680,6 +687,15 @@ int launch_tf32(int M, int N, int K, const float* A, int lda, const float* B, in
 }  // namespace
 
 void gemm_tf32x3_set_trace(long long* device_buffer) { g_gemm_trace_host = device_buffer; }
+
+void gemm_tf32x3_plan(int M, int N, int K, int pair_mode, int sms, int out[6]) {
+  const int bn = plan_bn(M, N, sms, pair_mode);
+  const bool cluster = bn == 64;                                        // 128-column tiles: no cluster, no pairs
+  const int nx = ceil_div(N, bn), ny = ceil_div(M, TG_BM), nxg = pair_mode == 1 ? 2 * nx : nx, nk = ceil_div(K, TG_BK);
+  int kchunk = nk;
+  const int S = (pair_mode && !cluster) ? 0 : plan_split(nk, nxg * ny, sms, pair_mode, cluster, 0, bn, &kchunk);
+  out[0] = bn; out[1] = nxg; out[2] = ny; out[3] = S; out[4] = kchunk; out[5] = (cluster && S > 1) ? S : 1;
+}
 
 int gemm_tf32x3(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                 const GemmEpi& ep, float* ws, size_t ws_floats, unsigned* tickets, int max_tiles, int sms, bool cluster,

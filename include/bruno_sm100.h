@@ -293,6 +293,11 @@ int bruno_dense_coupling_bwd(const float* x, const float* s_pre, const float* dy
  * 2 = the same kernel with the round-1 split-K fix-up through the bound workspace (bit-identical results: both add the
  * partials in K order).  variant < 0 queries. */
 int bruno_debug_gemm_variant(int variant);
+/* DEBUG / host logic (no GPU needed): launch geometry of the tcgen05 GEMM for a shape on a device with `sms` SMs.  pair_mode 0 =
+ * one product, 1 = two products side by side, 2 = two products K-concatenated (the dense coupling's s|t heads, dKs|dKt, dh).
+ * out6 = {tile columns, gridDim.x, gridDim.y, gridDim.z (0: the pair needs two launches), K tiles of 32 per split-K slice,
+ * thread-block cluster size}. */
+int bruno_debug_gemm_plan(int M, int N, int K, int pair_mode, int sms, int* out6);
 /* DEBUG: CTA (0,0,0) of the tcgen05 GEMM records clock64() of its pipeline events into device_buffer [64][8] (NULL = off) */
 int bruno_debug_gemm_trace(long long* device_buffer);
 #endif
