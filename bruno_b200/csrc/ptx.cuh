@@ -201,15 +201,9 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// thread-block cluster: barrier over all threads of all CTAs (converged warps), rank, and peer shared memory
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+// thread-block cluster: entry barrier (all threads of all CTAs, converged warps), rank, and peer shared memory
 __device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void st_dsmem_v4(uint32_t cluster_smem_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(cluster_smem_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 // asynchronous 16-byte store into a peer CTA's shared memory that counts its bytes on an mbarrier of that CTA
 __device__ __forceinline__ void st_async_v4(uint32_t cluster_smem_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
                                             uint32_t cluster_mbar_addr) {
@@ -227,12 +221,6 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t cta_smem_addr, uint32_t
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_smem_addr) {
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_smem_addr) : "memory");
-  return v;
-}
-
 // read-only 128-bit global load that does not allocate in L1 (streamed once)
 __device__ __forceinline__ uint4 ldg_nc_u4(const void* gptr) {
   uint4 r;
