@@ -51,3 +51,33 @@ def test_plan_invariants_on_random_shapes():
         assert p['cluster'] == (p['gz'] if p['bn'] == 64 and p['gz'] > 1 else 1)
         if p['cluster'] > 1:                               # the push buffer holds S x ceil(rows / S) partial rows
             assert p['cluster'] * -(-128 // p['cluster']) <= 128 + 8
+
+
+def test_cluster_reduction_ownership_model():
+    """Python model of the split-K reduction inside a cluster (csrc/gemm_tf32.cu, epilogue): CTA z owns rows
+    [z rows_per, (z + 1) rows_per) of the 128-row tile; every CTA pushes each of its partial rows into slot
+    [source z][local row] of the owner's buffer and the owner waits for S x (rows it owns) x 256 bytes.  Every row has exactly
+    one owner, the byte counts add up, and the slots of one owner never overlap or leave the 136-row buffer."""
+    BN, PUSH_ROWS = 64, 128 + 8
+    for S in range(2, 9):
+        for rows in list(range(1, 129)):
+            rows_per = -(-rows // S)
+            expected = [S * max(0, min(rows, (z + 1) * rows_per) - z * rows_per) * BN * 4 for z in range(S)]
+            received = [0] * S
+            slots = [set() for _ in range(S)]
+            for src in range(S):
+                for r in range(128):                      # TMEM lane = tile row
+                    if r >= rows:
+                        continue
+                    owner, lr = r // rows_per, r % rows_per
+                    assert owner < S
+                    slot = src * rows_per + lr
+                    assert slot < PUSH_ROWS and slot not in slots[owner]
+                    slots[owner].add(slot)
+                    received[owner] += BN * 4
+            assert received == expected
+            assert sum(expected) == S * rows * BN * 4
+            # the reduction of owner z reads slots z' * rows_per + lr for z' < S: exactly the slots written
+            for z in range(S):
+                nmine = max(0, min(rows, (z + 1) * rows_per) - z * rows_per)
+                assert slots[z] == {zz * rows_per + lr for zz in range(S) for lr in range(nmine)}
